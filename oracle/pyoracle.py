@@ -1,0 +1,248 @@
+"""ctypes front-end of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module (see oracle/astr_oracle.hpp).
+The product package ``astr_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libastr_oracle.so")
+HM = 5
+
+# field ids of oracle_case_get / oracle_case_set (oracle/solver.cpp: field_by_id)
+FIELD_IDS = {
+    **{f"q{n + 1}": n for n in range(5)},
+    "rho": 5, "u": 6, "v": 7, "w": 8, "prs": 9, "tmp": 10,
+    **{f"qrhs{n + 1}": 11 + n for n in range(5)},
+    "jacob": 16,
+    **{f"dxi{a + 1}{b + 1}": 17 + 3 * a + b for a in range(3) for b in range(3)},
+    **{f"dvel{m + 1}{n + 1}": 26 + 3 * m + n for m in range(3) for n in range(3)},
+    **{f"dtmp{n + 1}": 35 + n for n in range(3)},
+    **{f"sigma{n + 1}": 38 + n for n in range(6)},
+    **{f"qflux{n + 1}": 44 + n for n in range(3)},
+    **{f"x{n + 1}": 47 + n for n in range(3)},
+    **{f"qsave{n + 1}": 50 + n for n in range(5)},
+    **{f"vor{n + 1}": 55 + n for n in range(3)},
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/*.cpp into libastr_oracle.so (g++, -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in ("lineops.cpp", "miniapp.cpp", "solver.cpp", "astr_oracle.hpp")]
+    if not force and os.path.exists(_LIB):
+        if all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs):
+            return _LIB
+    r = subprocess.run(["make", "-C", _HERE, "-B"], capture_output=True, text=True)
+    if r.returncode != 0:
+        # some images ship a g++ without libgomp: retry single-threaded
+        r = subprocess.run(
+            ["make", "-C", _HERE, "-B",
+             "CXXFLAGS=-O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -Wno-unknown-pragmas"],
+            capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return _LIB
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB)
+        vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.oracle_miniapp_create.restype = vp
+        L.oracle_miniapp_create.argtypes = [ci]
+        L.oracle_miniapp_destroy.argtypes = [vp]
+        L.oracle_miniapp_run.argtypes = [vp, ci]
+        L.oracle_miniapp_run.restype = ci
+        L.oracle_miniapp_history.argtypes = [vp, vp]
+        L.oracle_miniapp_get.argtypes = [vp, ci, vp]
+        L.oracle_df_compact.argtypes = [ci, ci, vp, vp]
+        L.oracle_diff6ec.argtypes = [ci, ci, vp, vp]
+        L.oracle_compact_filter.argtypes = [ci, ci, cd, cd, vp, vp]
+        L.oracle_scheme_tables.argtypes = [ci, ci, ci, cd, vp, vp, vp, vp, vp, vp]
+        L.oracle_scheme_tables.restype = ci
+        L.oracle_num_threads.restype = ci
+        L.oracle_case_create.restype = vp
+        L.oracle_case_create.argtypes = [ci] * 9 + [cd] * 8
+        L.oracle_case_destroy.argtypes = [vp]
+        L.oracle_case_nblocks.argtypes = [vp]
+        L.oracle_case_nblocks.restype = ci
+        L.oracle_case_block_info.argtypes = [vp, ci, vp]
+        L.oracle_case_set_x.argtypes = [vp, ci, vp]
+        for name in ("gridgeom", "tgvini", "filterq", "qswap", "gradcal", "zero_qrhs", "convrsdcal6",
+                     "rhscal", "save_q", "updatefvar"):
+            getattr(L, "oracle_case_" + name).argtypes = [vp]
+        L.oracle_case_get.argtypes = [vp, ci, ci, vp]
+        L.oracle_case_set.argtypes = [vp, ci, ci, vp]
+        L.oracle_case_rk_update.argtypes = [vp, ci]
+        L.oracle_case_rk_stage.argtypes = [vp, ci]
+        L.oracle_case_set_flags.argtypes = [vp, ci, ci]
+        L.oracle_case_run.argtypes = [vp, ci]
+        L.oracle_case_run.restype = ci
+        L.oracle_case_history.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def num_threads() -> int:
+    return lib().oracle_num_threads()
+
+
+# --------------------------------------------------------------------------------------
+# single-pencil operators
+# --------------------------------------------------------------------------------------
+def df_compact(f: np.ndarray, ntype: int) -> np.ndarray:
+    """6th-order compact derivative of one pencil f(-hm:dim+hm) -> df(0:dim)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    dim = f.size - 1 - 2 * HM
+    out = np.empty(dim + 1)
+    lib().oracle_df_compact(ntype, dim, f.ctypes.data, out.ctypes.data)
+    return out
+
+
+def diff6ec(f: np.ndarray, ntype: int) -> np.ndarray:
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    dim = f.size - 1 - 2 * HM
+    out = np.empty(dim + 1)
+    lib().oracle_diff6ec(ntype, dim, f.ctypes.data, out.ctypes.data)
+    return out
+
+
+def compact_filter(f: np.ndarray, ntype: int, alfa: float = 0.49, beter_bound: float = 0.98) -> np.ndarray:
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    dim = f.size - 1 - 2 * HM
+    out = np.empty(dim + 1)
+    lib().oracle_compact_filter(ntype, dim, alfa, beter_bound, f.ctypes.data, out.ctypes.data)
+    return out
+
+
+def scheme_tables(is_filter: bool, ntype: int, dim: int, alfa: float = 0.49):
+    """(first_node, a, c, ac1, ac2, ac3) of the pre-factored tridiagonal operator."""
+    first = ctypes.c_int(0)
+    n = lib().oracle_scheme_tables(int(is_filter), ntype, dim, alfa, ctypes.byref(first), None, None, None, None, None)
+    arrs = [np.zeros(n) for _ in range(5)]
+    lib().oracle_scheme_tables(int(is_filter), ntype, dim, alfa, ctypes.byref(first), *[a.ctypes.data for a in arrs])
+    return (first.value, *arrs)
+
+
+# --------------------------------------------------------------------------------------
+# mini-app mode (pinned against tests/golden/state.ref_128)
+# --------------------------------------------------------------------------------------
+class MiniApp:
+    IDS = {**{f"q{n + 1}": n for n in range(5)}, "rho": 5, "u": 6, "v": 7, "w": 8, "prs": 9, "tmp": 10,
+           **{f"qrhs{n + 1}": 11 + n for n in range(5)}}
+
+    def __init__(self, n: int):
+        self.n = n
+        self._h = lib().oracle_miniapp_create(n)
+
+    def run(self, nsteps: int) -> np.ndarray:
+        rows = lib().oracle_miniapp_run(self._h, nsteps)
+        out = np.zeros((rows, 4))
+        lib().oracle_miniapp_history(self._h, out.ctypes.data)
+        return out
+
+    def get(self, name: str) -> np.ndarray:
+        m = self.n + 1 + 2 * HM
+        out = np.empty((m, m, m), order="F")
+        lib().oracle_miniapp_get(self._h, self.IDS[name], out.ctypes.data)
+        return out
+
+    def close(self):
+        if self._h:
+            lib().oracle_miniapp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------
+# main-solver mode on a virtual block grid
+# --------------------------------------------------------------------------------------
+class Case:
+    def __init__(self, ia, ja, ka, blocks=(1, 1, 1), homo=(True, True, True), lengths=None, reynolds=1600.0,
+                 mach=0.1, alfa_filter=0.49, deltat=1e-3, sutherland_s=110.3):
+        two_pi = 2.0 * np.pi
+        lengths = lengths or (two_pi, two_pi, two_pi)
+        self.dims = (ia, ja, ka)
+        self.blocks = tuple(blocks)
+        self._h = lib().oracle_case_create(ia, ja, ka, *blocks, *[int(h) for h in homo], *lengths, reynolds, mach,
+                                           alfa_filter, deltat, sutherland_s)
+        self.nblocks = lib().oracle_case_nblocks(self._h)
+
+    def block_info(self, ib: int) -> dict:
+        info = (ctypes.c_int * 21)()
+        lib().oracle_case_block_info(self._h, ib, info)
+        v = list(info)
+        return dict(im=v[0], jm=v[1], km=v[2], npdc=v[3:6], is_ie=v[6:12], g0=v[12:15], nb=v[15:21])
+
+    def shape(self, ib: int):
+        b = self.block_info(ib)
+        return (b["im"] + 1 + 2 * HM, b["jm"] + 1 + 2 * HM, b["km"] + 1 + 2 * HM)
+
+    def get(self, name: str, ib: int = 0) -> np.ndarray:
+        out = np.empty(self.shape(ib), order="F")
+        lib().oracle_case_get(self._h, ib, FIELD_IDS[name], out.ctypes.data)
+        return out
+
+    def set(self, name: str, arr: np.ndarray, ib: int = 0):
+        a = np.asfortranarray(arr, dtype=np.float64)
+        assert a.shape == self.shape(ib)
+        lib().oracle_case_set(self._h, ib, FIELD_IDS[name], a.ctypes.data)
+
+    def set_x(self, x: np.ndarray, ib: int = 0):
+        a = np.asfortranarray(x, dtype=np.float64)
+        lib().oracle_case_set_x(self._h, ib, a.ctypes.data)
+
+    def set_flags(self, lfilter=True, diffterm=True):
+        lib().oracle_case_set_flags(self._h, int(lfilter), int(diffterm))
+
+    def history(self) -> np.ndarray:
+        rows = lib().oracle_case_run(self._h, 0)
+        out = np.zeros((rows, 4))
+        if rows:
+            lib().oracle_case_history(self._h, out.ctypes.data)
+        return out
+
+    def run(self, nsteps: int) -> np.ndarray:
+        lib().oracle_case_run(self._h, nsteps)
+        return self.history()
+
+    def rk_update(self, rkstep: int):
+        lib().oracle_case_rk_update(self._h, rkstep)
+
+    def rk_stage(self, rkstep: int):
+        lib().oracle_case_rk_stage(self._h, rkstep)
+
+    def __getattr__(self, name):
+        if name in ("gridgeom", "tgvini", "filterq", "qswap", "gradcal", "zero_qrhs", "convrsdcal6", "rhscal",
+                    "save_q", "updatefvar"):
+            fn = getattr(lib(), "oracle_case_" + name)
+            return lambda: fn(self._h)
+        raise AttributeError(name)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().oracle_case_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,866 @@
+// oracle/solver.cpp -- TEST INFRASTRUCTURE ONLY (see astr_oracle.hpp).
+// Restatement of the MAIN solver's Runge-Kutta stage (src/mainloop.F90:396-482) on a
+// virtual isize x jsize x ksize block grid held in one process.  Each virtual block
+// is what one MPI rank (reference) / one GPU (astr_b200) owns; halo exchanges between
+// blocks are plain copies that follow src/parallel.F90 statement by statement
+// (pack everything, then unpack -- the blocking mpi_sendrecv semantics).
+//
+// Parity status: UNPINNED (no stored number in the reference covers this mode);
+// cross-checked against the pinned mini-app mode at the 1e-13 level in
+// tests/test_oracle_solver.py.
+#include "astr_oracle.hpp"
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <functional>
+
+namespace astr_oracle {
+
+struct Block {
+  int im, jm, km;
+  int rk[3];           // irk,jrk,krk
+  int g0[3];           // ig0,jg0,kg0
+  int npdc[3];         // npdci,npdcj,npdck (src/parallel.F90:1042-1228)
+  int s[3], e[3];      // is..ie, js..je, ks..ke
+  int nb[3][2];        // neighbour block index per direction (lo,hi), -1 = MPI_PROC_NULL
+  CompactScheme fds[3], fil[3];
+  Field x[3], q[5], rho, vel[3], prs, tmp, jacob, dxi[3][3];
+  Field qrhs[5], qsave[5], dvel[3][3], dtmp[3], sigma[6], qflux[3], vor[3];
+  int dim(int d) const { return d == 0 ? im : (d == 1 ? jm : km); }
+};
+
+struct Case {
+  int ia, ja, ka, size[3];
+  bool homo[3];
+  bool lfilter = true, diffterm = true;
+  double alfa_filter = 0.49, deltat = 1e-3, time = 0.0;
+  int nstep = 0;
+  int nthreads = 0;
+  Thermo th;
+  FilterCoef fc;
+  std::vector<Block> blk;
+  double force[3] = {0, 0, 0};
+  std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
+  double xmax = 0.0;
+};
+
+// ---------------------------------------------------------------------------------
+// generic accessors along a direction: l is the index along dir, (p1,p2) the others
+// ---------------------------------------------------------------------------------
+static inline double& at(Field& a, int d, int l, int p1, int p2) {
+  return d == 0 ? a(l, p1, p2) : (d == 1 ? a(p1, l, p2) : a(p1, p2, l));
+}
+static inline double at(const Field& a, int d, int l, int p1, int p2) {
+  return d == 0 ? a(l, p1, p2) : (d == 1 ? a(p1, l, p2) : a(p1, p2, l));
+}
+// extents of the two "other" indices for direction d
+static inline void others(const Block& b, int d, int& n1, int& n2) {
+  if (d == 0) { n1 = b.jm; n2 = b.km; }
+  else if (d == 1) { n1 = b.im; n2 = b.km; }
+  else { n1 = b.im; n2 = b.jm; }
+}
+
+template <class Fn>
+static void for_each_pencil(const Block& b, int d, Fn fn) {
+  int n1, n2;
+  others(b, d, n1, n2);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int p2 = 0; p2 <= n2; ++p2)
+    for (int p1 = 0; p1 <= n1; ++p1) fn(p1, p2);
+}
+
+// ---------------------------------------------------------------------------------
+// src/parallel.F90:356-484 (parapp) + :919-1248 (parallelini)
+// ---------------------------------------------------------------------------------
+static void decompose(Case& c) {
+  const int n[3] = {c.ia, c.ja, c.ka};
+  std::vector<int> mp[3], off[3];
+  for (int d = 0; d < 3; ++d) {
+    const int sz = c.size[d];
+    mp[d].assign(sz, n[d] / sz);
+    const int n2 = n[d] % sz;
+    for (int r = sz - 1; r >= sz - n2; --r) mp[d][r] += 1;  // :399-405
+    off[d].assign(sz, 0);
+    for (int r = 1; r < sz; ++r) off[d][r] = off[d][r - 1] + mp[d][r - 1];
+  }
+  const int isize = c.size[0], jsize = c.size[1], ksize = c.size[2];
+  c.blk.resize((size_t)isize * jsize * ksize);
+  for (int krk = 0; krk < ksize; ++krk)
+    for (int jrk = 0; jrk < jsize; ++jrk)
+      for (int irk = 0; irk < isize; ++irk) {
+        Block& b = c.blk[(size_t)krk * (isize * jsize) + jrk * isize + irk];
+        b.rk[0] = irk; b.rk[1] = jrk; b.rk[2] = krk;
+        b.im = mp[0][irk]; b.jm = mp[1][jrk]; b.km = mp[2][krk];
+        b.g0[0] = off[0][irk]; b.g0[1] = off[1][jrk]; b.g0[2] = off[2][krk];
+        for (int d = 0; d < 3; ++d) {
+          const int sz = c.size[d], r = b.rk[d], rm = sz - 1, dm = b.dim(d);
+          auto rank_of = [&](int rr) {
+            int cc[3] = {irk, jrk, krk};
+            cc[d] = rr;
+            return cc[2] * (isize * jsize) + cc[1] * isize + cc[0];
+          };
+          if (c.homo[d]) {  // :1042-1066
+            b.s[d] = 0; b.e[d] = dm; b.npdc[d] = 3;
+            if (sz == 1) { b.nb[d][0] = b.nb[d][1] = -1; }
+            else {
+              b.nb[d][0] = rank_of(r == 0 ? rm : r - 1);
+              b.nb[d][1] = rank_of(r == rm ? 0 : r + 1);
+            }
+          } else if (sz == 1) {  // :1071-1077 -- is..ie are NOT assigned by the reference
+            b.nb[d][0] = b.nb[d][1] = -1; b.npdc[d] = 4;
+            b.s[d] = 1; b.e[d] = dm - 1;  // extension, SURVEY.md Q4
+          } else if (r == 0) {
+            b.s[d] = 1; b.e[d] = dm; b.npdc[d] = 1;
+            b.nb[d][0] = -1; b.nb[d][1] = rank_of(r + 1);
+          } else if (r == rm) {
+            b.s[d] = 0; b.e[d] = dm - 1; b.npdc[d] = 2;
+            b.nb[d][0] = rank_of(r - 1); b.nb[d][1] = -1;
+          } else {
+            b.s[d] = 0; b.e[d] = dm; b.npdc[d] = 3;
+            b.nb[d][0] = rank_of(r - 1); b.nb[d][1] = rank_of(r + 1);
+          }
+        }
+      }
+}
+
+static void alloc_block(Block& b) {
+  auto A = [&](Field& f) { f.alloc(b.im, b.jm, b.km); };
+  for (auto& f : b.x) A(f);
+  for (auto& f : b.q) A(f);
+  A(b.rho); for (auto& f : b.vel) A(f); A(b.prs); A(b.tmp); A(b.jacob);
+  for (auto& r : b.dxi) for (auto& f : r) A(f);
+  for (auto& f : b.qrhs) A(f);
+  for (auto& f : b.qsave) A(f);
+  for (auto& r : b.dvel) for (auto& f : r) A(f);
+  for (auto& f : b.dtmp) A(f);
+  for (auto& f : b.sigma) A(f);
+  for (auto& f : b.qflux) A(f);
+  for (auto& f : b.vor) A(f);
+}
+
+// ---------------------------------------------------------------------------------
+// Halo exchanges.  `get(b)` returns the list of fields of block b to exchange.
+// ---------------------------------------------------------------------------------
+using FieldList = std::vector<Field*>;
+using Getter = std::function<FieldList(Block&)>;
+
+enum class Xmode { SWAP, QSWAP, SYNC };
+
+// One direction of array{3,4,5}d_sendrecv (src/parallel.F90:4132-4370; SWAP),
+// qswap (:4848-5318; QSWAP: 0:hm planes + shared-node average) or array3d_sync
+// (:3725-3934; SYNC: shared-node average only).
+static void exchange_dir(Case& c, int d, const Getter& get, Xmode mode) {
+  const size_t nblk = c.blk.size();
+  if (c.size[d] == 1) {
+    if (!c.homo[d]) return;
+    for (Block& b : c.blk) {
+      const int dm = b.dim(d);
+      int n1, n2;
+      others(b, d, n1, n2);
+      for (Field* f : get(b)) {
+        if (dm == 0) {  // 2-D replicate (:4296-4299)
+          if (mode == Xmode::SYNC) continue;
+          for (int p2 = 0; p2 <= n2; ++p2)
+            for (int p1 = 0; p1 <= n1; ++p1)
+              for (int l = -hm; l <= hm; ++l) at(*f, d, l, p1, p2) = at(*f, d, 0, p1, p2);
+          continue;
+        }
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1) {
+            if (mode != Xmode::SYNC) {
+              for (int l = -hm; l <= -1; ++l) at(*f, d, l, p1, p2) = at(*f, d, dm + l, p1, p2);
+              for (int l = 1; l <= hm; ++l) at(*f, d, dm + l, p1, p2) = at(*f, d, l, p1, p2);
+            }
+            if (mode != Xmode::SWAP) {
+              const double v = 0.5 * (at(*f, d, 0, p1, p2) + at(*f, d, dm, p1, p2));
+              at(*f, d, 0, p1, p2) = v;
+              at(*f, d, dm, p1, p2) = v;
+            }
+          }
+      }
+    }
+    return;
+  }
+  // multi-block: pack all, then unpack all
+  struct Buf { std::vector<double> lo, hi; };  // lo: sent to the low neighbour (planes 0|1..hm)
+  std::vector<std::vector<Buf>> bufs(nblk);
+  const int l0 = (mode == Xmode::SWAP) ? 1 : 0;
+  const int l1 = (mode == Xmode::SYNC) ? 0 : hm;
+  const int np = l1 - l0 + 1;
+  for (size_t ib = 0; ib < nblk; ++ib) {
+    Block& b = c.blk[ib];
+    const int dm = b.dim(d);
+    int n1, n2;
+    others(b, d, n1, n2);
+    FieldList fl = get(b);
+    bufs[ib].resize(fl.size());
+    for (size_t n = 0; n < fl.size(); ++n) {
+      Buf& B = bufs[ib][n];
+      const size_t cnt = (size_t)np * (n1 + 1) * (n2 + 1);
+      B.lo.resize(cnt); B.hi.resize(cnt);
+      size_t t = 0;
+      for (int p2 = 0; p2 <= n2; ++p2)
+        for (int p1 = 0; p1 <= n1; ++p1)
+          for (int l = l0; l <= l1; ++l, ++t) {
+            B.lo[t] = at(*fl[n], d, l, p1, p2);             // sbuf1 = var(l0:hm)
+            B.hi[t] = at(*fl[n], d, dm - l, p1, p2);        // sbuf2 (stored mirrored: dm-l)
+          }
+    }
+  }
+  for (size_t ib = 0; ib < nblk; ++ib) {
+    Block& b = c.blk[ib];
+    const int dm = b.dim(d);
+    int n1, n2;
+    others(b, d, n1, n2);
+    FieldList fl = get(b);
+    for (size_t n = 0; n < fl.size(); ++n) {
+      if (b.nb[d][1] >= 0) {  // from the high neighbour: its `lo` buffer
+        const Buf& R = bufs[b.nb[d][1]][n];
+        size_t t = 0;
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1)
+            for (int l = l0; l <= l1; ++l, ++t) {
+              if (l == 0) at(*fl[n], d, dm, p1, p2) = 0.5 * (at(*fl[n], d, dm, p1, p2) + R.lo[t]);
+              else at(*fl[n], d, dm + l, p1, p2) = R.lo[t];
+            }
+      }
+      if (b.nb[d][0] >= 0) {  // from the low neighbour: its `hi` buffer
+        const Block& nbk = c.blk[b.nb[d][0]];
+        (void)nbk;
+        const Buf& R = bufs[b.nb[d][0]][n];
+        size_t t = 0;
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1)
+            for (int l = l0; l <= l1; ++l, ++t) {
+              if (l == 0) at(*fl[n], d, 0, p1, p2) = 0.5 * (at(*fl[n], d, 0, p1, p2) + R.hi[t]);
+              else at(*fl[n], d, -l, p1, p2) = R.hi[t];
+            }
+      }
+    }
+  }
+}
+
+static void dataswap(Case& c, const Getter& get, int direction = -1) {
+  for (int d = 0; d < 3; ++d)
+    if (direction < 0 || direction == d) exchange_dir(c, d, get, Xmode::SWAP);
+}
+static void datasync(Case& c, const Getter& get) {
+  for (int d = 0; d < 3; ++d) exchange_dir(c, d, get, Xmode::SYNC);
+}
+
+// src/fludyna.F90:545-634 q2fvar_3da (non-COMB, nondimen) at one node
+static inline void q2fvar_node(const Thermo& th, Block& b, int i, int j, int k) {
+  const double r = b.q[0](i, j, k);
+  b.rho(i, j, k) = r;
+  const double u = b.q[1](i, j, k) / r, v = b.q[2](i, j, k) / r, w = b.q[3](i, j, k) / r;
+  b.vel[0](i, j, k) = u; b.vel[1](i, j, k) = v; b.vel[2](i, j, k) = w;
+  const double p = (b.q[4](i, j, k) - 0.5 * r * (u * u + v * v + w * w)) / th.const6;
+  b.prs(i, j, k) = p;
+  b.tmp(i, j, k) = p / r * th.const2;  // thermal_3d(pressure,density) fludyna.F90:146
+}
+
+// src/parallel.F90:4848-5318 qswap: per direction (i then j then k) halo copy,
+// shared-node average, then q2fvar on the slabs -hm:0 and dim:dim+hm of sides that
+// have a neighbour (or both sides for a single periodic block).
+static void qswap(Case& c) {
+  Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
+  for (int d = 0; d < 3; ++d) {
+    exchange_dir(c, d, gq, Xmode::QSWAP);
+    for (Block& b : c.blk) {
+      const int dm = b.dim(d);
+      int n1, n2;
+      others(b, d, n1, n2);
+      bool lo, hi;
+      if (c.size[d] == 1) { lo = hi = c.homo[d]; }
+      else { lo = b.nb[d][0] >= 0; hi = b.nb[d][1] >= 0; }
+      auto slab = [&](int la, int lb) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1)
+            for (int l = la; l <= lb; ++l) {
+              if (d == 0) q2fvar_node(c.th, b, l, p1, p2);
+              else if (d == 1) q2fvar_node(c.th, b, p1, l, p2);
+              else q2fvar_node(c.th, b, p1, p2, l);
+            }
+      };
+      if (hi) slab(dm, dm + hm);
+      if (lo) slab(-hm, 0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Grid + metrics: src/gridgeneration.F90:233-265 (gridcube), src/parallel.F90:2780-3035
+// (gridsendrecv), src/geom.F90:99-700 (gridgeom, ndims==3 branch, no lfftk).
+// ---------------------------------------------------------------------------------
+static void gridsendrecv(Case& c) {
+  // Pack/unpack relative offsets; physical boundaries get an even reflection.
+  for (int d = 0; d < 3; ++d) {
+    const size_t nblk = c.blk.size();
+    if (c.size[d] == 1) {
+      for (Block& b : c.blk) {
+        const int dm = b.dim(d);
+        if (dm == 0) continue;
+        int n1, n2;
+        others(b, d, n1, n2);
+        for (int m = 0; m < 3; ++m)
+          for (int p2 = 0; p2 <= n2; ++p2)
+            for (int p1 = 0; p1 <= n1; ++p1)
+              for (int n = 1; n <= hm; ++n) {  // :2861-2866
+                Field& x = b.x[m];
+                at(x, d, dm + n, p1, p2) = at(x, d, dm, p1, p2) + (at(x, d, n, p1, p2) - at(x, d, 0, p1, p2));
+                at(x, d, -n, p1, p2) = at(x, d, 0, p1, p2) - (at(x, d, dm, p1, p2) - at(x, d, dm - n, p1, p2));
+              }
+      }
+      continue;
+    }
+    std::vector<std::vector<double>> lo(nblk), hi(nblk);
+    for (size_t ib = 0; ib < nblk; ++ib) {
+      Block& b = c.blk[ib];
+      const int dm = b.dim(d);
+      int n1, n2;
+      others(b, d, n1, n2);
+      for (int m = 0; m < 3; ++m)
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1)
+            for (int n = 1; n <= hm; ++n) {  // :2812-2815
+              lo[ib].push_back(at(b.x[m], d, n, p1, p2) - at(b.x[m], d, 0, p1, p2));
+              hi[ib].push_back(at(b.x[m], d, dm - n, p1, p2) - at(b.x[m], d, dm, p1, p2));
+            }
+    }
+    for (size_t ib = 0; ib < nblk; ++ib) {
+      Block& b = c.blk[ib];
+      const int dm = b.dim(d);
+      int n1, n2;
+      others(b, d, n1, n2);
+      size_t t = 0;
+      for (int m = 0; m < 3; ++m)
+        for (int p2 = 0; p2 <= n2; ++p2)
+          for (int p1 = 0; p1 <= n1; ++p1)
+            for (int n = 1; n <= hm; ++n, ++t) {
+              Field& x = b.x[m];
+              if (b.nb[d][0] < 0) at(x, d, -n, p1, p2) = 2.0 * at(x, d, 0, p1, p2) - at(x, d, n, p1, p2);
+              else at(x, d, -n, p1, p2) = hi[b.nb[d][0]][t] + at(x, d, 0, p1, p2);
+              if (b.nb[d][1] < 0) at(x, d, dm + n, p1, p2) = 2.0 * at(x, d, dm, p1, p2) - at(x, d, dm - n, p1, p2);
+              else at(x, d, dm + n, p1, p2) = lo[b.nb[d][1]][t] + at(x, d, dm, p1, p2);
+            }
+    }
+  }
+}
+
+// derivative of one pencil of `src` along d at (p1,p2) -> out[0..dim]
+struct PencilWork {
+  std::vector<double> buf, df, work;
+  explicit PencilWork(int md) : buf(md + 1 + 2 * hm), df(md + 1), work(2 * (md + 8)) {}
+  double* f() { return buf.data() + hm; }
+};
+static inline void gather(const Field& a, int d, int p1, int p2, int dim, double* f) {
+  for (int l = -hm; l <= dim + hm; ++l) f[l] = at(a, d, l, p1, p2);
+}
+
+static void gridgeom(Case& c) {
+  gridsendrecv(c);
+  const int md = std::max(c.ia, std::max(c.ja, c.ka));
+  // dx(m,n) = d x_m / d xi_n   (geom.F90:130-164)
+  std::vector<std::vector<Field>> DX(c.blk.size());
+  for (size_t ib = 0; ib < c.blk.size(); ++ib) {
+    Block& b = c.blk[ib];
+    DX[ib].resize(9);
+    for (auto& f : DX[ib]) f.alloc(b.im, b.jm, b.km);
+    for (int d = 0; d < 3; ++d)
+      for_each_pencil(b, d, [&](int p1, int p2) {
+        PencilWork w(md);
+        for (int m = 0; m < 3; ++m) {
+          gather(b.x[m], d, p1, p2, b.dim(d), w.f());
+          df_compact(b.fds[d], w.f(), w.df.data(), w.work.data());
+          for (int l = 0; l <= b.dim(d); ++l) at(DX[ib][m * 3 + d], d, l, p1, p2) = w.df[l];
+        }
+      });
+  }
+  size_t cur = 0;
+  std::vector<std::vector<Field>>* cur_list = &DX;
+  Getter gdx = [&](Block& b) {
+    size_t ib = &b - c.blk.data();
+    FieldList fl;
+    for (auto& f : (*cur_list)[ib]) fl.push_back(&f);
+    return fl;
+  };
+  (void)cur;
+  dataswap(c, gdx);  // geom.F90:333
+  // jacobian :340-357
+  for (size_t ib = 0; ib < c.blk.size(); ++ib) {
+    Block& b = c.blk[ib];
+    auto dx = [&](int m, int n) -> Field& { return DX[ib][(m - 1) * 3 + (n - 1)]; };
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i)
+          b.jacob(i, j, k) = dx(1, 1)(i, j, k) * dx(2, 2)(i, j, k) * dx(3, 3)(i, j, k) +
+                             dx(1, 2)(i, j, k) * dx(2, 3)(i, j, k) * dx(3, 1)(i, j, k) +
+                             dx(1, 3)(i, j, k) * dx(2, 1)(i, j, k) * dx(3, 2)(i, j, k) -
+                             dx(1, 3)(i, j, k) * dx(2, 2)(i, j, k) * dx(3, 1)(i, j, k) -
+                             dx(1, 2)(i, j, k) * dx(2, 1)(i, j, k) * dx(3, 3)(i, j, k) -
+                             dx(1, 1)(i, j, k) * dx(2, 3)(i, j, k) * dx(3, 2)(i, j, k);
+  }
+  Getter gj = [](Block& b) { return FieldList{&b.jacob}; };
+  dataswap(c, gj);   // :383
+  datasync(c, gj);   // :385
+  // conservative-form d xi/d x :399-519.  dxi(a,b): a = xi index, b = x index.
+  for (size_t ib = 0; ib < c.blk.size(); ++ib) {
+    Block& b = c.blk[ib];
+    auto dx = [&](int m, int n) -> const Field& { return DX[ib][(m - 1) * 3 + (n - 1)]; };
+    // term list: {sweep dir, target dxi(a,b), dx(m1,n1)*x(c1) - dx(m2,n2)*x(c2)}
+    struct Term { int d, a, bb, m1, n1, c1, m2, n2, c2; };
+    static const Term terms[] = {
+        // i-sweeps (geom.F90:402-427)
+        {0, 2, 1, 2, 3, 3, 3, 3, 2}, {0, 2, 2, 3, 3, 1, 1, 3, 3}, {0, 2, 3, 1, 3, 2, 2, 3, 1},
+        {0, 3, 1, 3, 2, 2, 2, 2, 3}, {0, 3, 2, 1, 2, 3, 3, 2, 1}, {0, 3, 3, 2, 2, 1, 1, 2, 2},
+        // j-sweeps (:433-457)
+        {1, 1, 1, 3, 3, 2, 2, 3, 3}, {1, 1, 2, 1, 3, 3, 3, 3, 1}, {1, 1, 3, 2, 3, 1, 1, 3, 2},
+        {1, 3, 1, 2, 1, 3, 3, 1, 2}, {1, 3, 2, 3, 1, 1, 1, 1, 3}, {1, 3, 3, 1, 1, 2, 2, 1, 1},
+        // k-sweeps (:464-510)
+        {2, 1, 1, 2, 2, 3, 3, 2, 2}, {2, 1, 2, 3, 2, 1, 1, 2, 3}, {2, 1, 3, 1, 2, 2, 2, 2, 1},
+        {2, 2, 1, 3, 1, 2, 2, 1, 3}, {2, 2, 2, 1, 1, 3, 3, 1, 1}, {2, 2, 3, 2, 1, 1, 1, 1, 2}};
+    for (auto& r : b.dxi) for (auto& f : r) std::fill(f.v.begin(), f.v.end(), 0.0);
+    for (const Term& t : terms) {
+      for_each_pencil(b, t.d, [&](int p1, int p2) {
+        PencilWork w(md);
+        double* phi = w.f();
+        const int dm = b.dim(t.d);
+        for (int l = -hm; l <= dm + hm; ++l)
+          phi[l] = 0.5 * (at(dx(t.m1, t.n1), t.d, l, p1, p2) * at(b.x[t.c1 - 1], t.d, l, p1, p2) -
+                          at(dx(t.m2, t.n2), t.d, l, p1, p2) * at(b.x[t.c2 - 1], t.d, l, p1, p2));
+        df_compact(b.fds[t.d], phi, w.df.data(), w.work.data());
+        Field& tgt = b.dxi[t.a - 1][t.bb - 1];
+        for (int l = 0; l <= dm; ++l) at(tgt, t.d, l, p1, p2) = at(tgt, t.d, l, p1, p2) + w.df[l];
+      });
+    }
+  }
+  Getter gdxi = [](Block& b) {
+    FieldList fl;
+    for (auto& r : b.dxi) for (auto& f : r) fl.push_back(&f);
+    return fl;
+  };
+  dataswap(c, gdxi);  // :541  (the metric-identity check :546-646 has no side effects)
+  for (Block& b : c.blk)  // :662-666
+    for (int n = 0; n < 3; ++n)
+      for (int m = 0; m < 3; ++m)
+        for (int k = 0; k <= b.km; ++k)
+          for (int j = 0; j <= b.jm; ++j)
+            for (int i = 0; i <= b.im; ++i) b.dxi[m][n](i, j, k) = b.dxi[m][n](i, j, k) / b.jacob(i, j, k);
+  dataswap(c, gdxi);  // :674
+  datasync(c, gdxi);  // :676-680
+  // geombc (:682) only acts for wall bctype 41: not restated (TGV/periodic scope).
+}
+
+// ---------------------------------------------------------------------------------
+// Stage operators
+// ---------------------------------------------------------------------------------
+// src/comsolver.F90:514-632 filterq
+static void filterq(Case& c) {
+  const int md = std::max(c.ia, std::max(c.ja, c.ka));
+  Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
+  for (int d = 0; d < 3; ++d) {
+    dataswap(c, gq, d);
+    for (Block& b : c.blk) {
+      const int dm = b.dim(d);
+      for_each_pencil(b, d, [&](int p1, int p2) {
+        PencilWork w(md);
+        for (int n = 0; n < 5; ++n) {
+          gather(b.q[n], d, p1, p2, dm, w.f());
+          compact_filter(b.fil[d], c.fc, w.f(), w.df.data(), w.work.data());
+          for (int l = 0; l <= dm; ++l) at(b.q[n], d, l, p1, p2) = w.df[l];
+        }
+      });
+    }
+  }
+}
+
+// src/comsolver.F90:244-497 gradcal
+static void gradcal(Case& c) {
+  const int md = std::max(c.ia, std::max(c.ja, c.ka));
+  for (Block& b : c.blk) {
+    for (auto& r : b.dvel) for (auto& f : r) std::fill(f.v.begin(), f.v.end(), 0.0);
+    for (auto& f : b.dtmp) std::fill(f.v.begin(), f.v.end(), 0.0);
+    for (int d = 0; d < 3; ++d) {
+      const int dm = b.dim(d);
+      for_each_pencil(b, d, [&](int p1, int p2) {
+        PencilWork w(md);
+        for (int n = 0; n < 4; ++n) {
+          const Field& src = n < 3 ? b.vel[n] : b.tmp;
+          gather(src, d, p1, p2, dm, w.f());
+          df_compact(b.fds[d], w.f(), w.df.data(), w.work.data());
+          for (int m = 0; m < 3; ++m) {
+            Field& dst = n < 3 ? b.dvel[n][m] : b.dtmp[m];
+            for (int l = 0; l <= dm; ++l)
+              at(dst, d, l, p1, p2) = at(dst, d, l, p1, p2) + w.df[l] * at(b.dxi[d][m], d, l, p1, p2);
+          }
+        }
+      });
+    }
+  }
+}
+
+// src/solver.F90:2173-2341 convrsdcal6
+static void convrsdcal6(Case& c) {
+  const int md = std::max(c.ia, std::max(c.ja, c.ka));
+  for (Block& b : c.blk) {
+    for (int d = 0; d < 3; ++d) {
+      const int dm = b.dim(d);
+      const int np = md + 1 + 2 * hm;
+      int o1, o2;  // the two other directions
+      if (d == 0) { o1 = 1; o2 = 2; } else if (d == 1) { o1 = 0; o2 = 2; } else { o1 = 0; o2 = 1; }
+      for_each_pencil(b, d, [&](int p1, int p2) {
+        // loop bounds are js:je / ks:ke etc. for the non-swept indices (:2197-2198)
+        if (p1 < b.s[o1] || p1 > b.e[o1] || p2 < b.s[o2] || p2 > b.e[o2]) return;
+        std::vector<double> fb(5 * np), df(md + 1), work(2 * (md + 8));
+        double* fcs[5];
+        for (int n = 0; n < 5; ++n) fcs[n] = fb.data() + n * np + hm;
+        for (int l = -hm; l <= dm + hm; ++l) {
+          const double d1 = at(b.dxi[d][0], d, l, p1, p2), d2 = at(b.dxi[d][1], d, l, p1, p2),
+                       d3 = at(b.dxi[d][2], d, l, p1, p2);
+          const double uu = d1 * at(b.vel[0], d, l, p1, p2) + d2 * at(b.vel[1], d, l, p1, p2) +
+                            d3 * at(b.vel[2], d, l, p1, p2);
+          const double jac = at(b.jacob, d, l, p1, p2), p = at(b.prs, d, l, p1, p2);
+          fcs[0][l] = jac * at(b.q[0], d, l, p1, p2) * uu;
+          fcs[1][l] = jac * (at(b.q[1], d, l, p1, p2) * uu + d1 * p);
+          fcs[2][l] = jac * (at(b.q[2], d, l, p1, p2) * uu + d2 * p);
+          fcs[3][l] = jac * (at(b.q[3], d, l, p1, p2) * uu + d3 * p);
+          fcs[4][l] = jac * (at(b.q[4], d, l, p1, p2) + p) * uu;
+        }
+        for (int n = 0; n < 5; ++n) {
+          df_compact(b.fds[d], fcs[n], df.data(), work.data());
+          for (int l = b.s[d]; l <= b.e[d]; ++l) {
+            double& r = at(b.qrhs[n], d, l, p1, p2);
+            r = r + df[l];
+          }
+        }
+      });
+    }
+  }
+}
+
+// src/solver.F90:2354-2873 diffrsdcal6 (turbmode none, nondimen, no species)
+static void diffrsdcal6(Case& c) {
+  const int md = std::max(c.ia, std::max(c.ja, c.ka));
+  const Thermo& th = c.th;
+  for (Block& b : c.blk) {
+    for (auto& f : b.sigma) std::fill(f.v.begin(), f.v.end(), 0.0);  // :2399-2400
+    for (auto& f : b.qflux) std::fill(f.v.begin(), f.v.end(), 0.0);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) {
+          const double miu = th.miucal(b.tmp(i, j, k)) / th.reynolds;
+          auto dv = [&](int m, int n) { return b.dvel[m - 1][n - 1](i, j, k); };
+          const double s11 = dv(1, 1);
+          const double s12 = 0.5 * (dv(1, 2) + dv(2, 1));
+          const double s13 = 0.5 * (dv(1, 3) + dv(3, 1));
+          const double s22 = dv(2, 2);
+          const double s23 = 0.5 * (dv(2, 3) + dv(3, 2));
+          const double s33 = dv(3, 3);
+          const double skk = num1d3 * (s11 + s22 + s33);
+          b.vor[0](i, j, k) = dv(3, 2) - dv(2, 3);
+          b.vor[1](i, j, k) = dv(1, 3) - dv(3, 1);
+          b.vor[2](i, j, k) = dv(2, 1) - dv(1, 2);
+          const double miu2 = 2.0 * miu;
+          const double hcc = (miu / th.prandtl) / th.const5;
+          const double detk = 0.0, tau = 0.0;
+          const double sg1 = miu2 * (s11 - skk) - detk + tau;
+          const double sg2 = miu2 * s12 + tau;
+          const double sg3 = miu2 * s13 + tau;
+          const double sg4 = miu2 * (s22 - skk) - detk + tau;
+          const double sg5 = miu2 * s23 + tau;
+          const double sg6 = miu2 * (s33 - skk) - detk + tau;
+          b.sigma[0](i, j, k) = sg1; b.sigma[1](i, j, k) = sg2; b.sigma[2](i, j, k) = sg3;
+          b.sigma[3](i, j, k) = sg4; b.sigma[4](i, j, k) = sg5; b.sigma[5](i, j, k) = sg6;
+          const double u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+          b.qflux[0](i, j, k) = hcc * b.dtmp[0](i, j, k) + sg1 * u + sg2 * v + sg3 * w;
+          b.qflux[1](i, j, k) = hcc * b.dtmp[1](i, j, k) + sg2 * u + sg4 * v + sg5 * w;
+          b.qflux[2](i, j, k) = hcc * b.dtmp[2](i, j, k) + sg3 * u + sg5 * v + sg6 * w;
+        }
+  }
+  Getter gs = [](Block& b) {
+    return FieldList{&b.sigma[0], &b.sigma[1], &b.sigma[2], &b.sigma[3], &b.sigma[4], &b.sigma[5]};
+  };
+  Getter gqf = [](Block& b) { return FieldList{&b.qflux[0], &b.qflux[1], &b.qflux[2]}; };
+  dataswap(c, gs);   // :2604
+  dataswap(c, gqf);  // :2606
+  static const int sel[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};  // rows of the symmetric sigma
+  for (Block& b : c.blk) {
+    for (int d = 0; d < 3; ++d) {
+      const int dm = b.dim(d);
+      const int np = md + 1 + 2 * hm;
+      for_each_pencil(b, d, [&](int p1, int p2) {  // all pencils 0:jm,0:km (:2623-2624)
+        std::vector<double> fb(4 * np), df(md + 1), work(2 * (md + 8));
+        double* ff[4];
+        for (int n = 0; n < 4; ++n) ff[n] = fb.data() + n * np + hm;
+        for (int l = -hm; l <= dm + hm; ++l) {
+          const double d1 = at(b.dxi[d][0], d, l, p1, p2), d2 = at(b.dxi[d][1], d, l, p1, p2),
+                       d3 = at(b.dxi[d][2], d, l, p1, p2), jac = at(b.jacob, d, l, p1, p2);
+          for (int n = 0; n < 3; ++n)
+            ff[n][l] = (at(b.sigma[sel[n][0]], d, l, p1, p2) * d1 + at(b.sigma[sel[n][1]], d, l, p1, p2) * d2 +
+                        at(b.sigma[sel[n][2]], d, l, p1, p2) * d3) * jac;
+          ff[3][l] = (at(b.qflux[0], d, l, p1, p2) * d1 + at(b.qflux[1], d, l, p1, p2) * d2 +
+                      at(b.qflux[2], d, l, p1, p2) * d3) * jac;
+        }
+        for (int n = 0; n < 4; ++n) {
+          df_compact(b.fds[d], ff[n], df.data(), work.data());
+          for (int l = b.s[d]; l <= b.e[d]; ++l) {
+            double& r = at(b.qrhs[n + 1], d, l, p1, p2);
+            r = r + df[l];
+          }
+        }
+      });
+    }
+  }
+}
+
+// src/solver.F90:185-282 rhscal (conschm even -> central; flowtype tgv: no sources)
+static void rhscal(Case& c) {
+  convrsdcal6(c);
+  for (Block& b : c.blk)
+    for (auto& f : b.qrhs)
+      for (double& v : f.v) v = -v;  // :242
+  if (c.diffterm) diffrsdcal6(c);
+}
+
+// src/fludyna.F90:191-242 updatefvar
+static void updatefvar(Case& c) {
+  for (Block& b : c.blk) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) q2fvar_node(c.th, b, i, j, k);
+  }
+}
+
+// src/statistic.F90:871-990 kenergycal / enstophycal (ndims==3)
+static void statcal(Case& c) {
+  double ke = 0.0, en = 0.0;
+  for (Block& b : c.blk) {
+    double ke_b = 0.0, en_b = 0.0;
+    for (int k = 1; k <= b.km; ++k)
+      for (int j = 1; j <= b.jm; ++j)
+        for (int i = 1; i <= b.im; ++i) {
+          const double u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+          const double var1 = u * u + v * v + w * w;
+          ke_b = ke_b + b.rho(i, j, k) * var1;
+          const double o1 = b.dvel[2][1](i, j, k) - b.dvel[1][2](i, j, k);
+          const double o2 = b.dvel[0][2](i, j, k) - b.dvel[2][0](i, j, k);
+          const double o3 = b.dvel[1][0](i, j, k) - b.dvel[0][1](i, j, k);
+          const double omegam = o1 * o1 + o2 * o2 + o3 * o3;
+          en_b = en_b + b.rho(i, j, k) * omegam;
+        }
+    ke += ke_b; en += en_b;  // psum
+  }
+  const double cnt = double(c.ia * c.ja * c.ka);
+  const double pi = 4.0 * std::atan(1.0);
+  const double roinf = 1.0, uinf = 1.0;
+  ke = 0.5 * ke / cnt;
+  ke = ke / (roinf * uinf * uinf);
+  en = 0.5 * en / cnt;
+  const double l_0 = c.xmax / (2.0 * pi);
+  en = en / (roinf * ((uinf / l_0) * (uinf / l_0)));
+  c.hist.push_back(double(c.nstep));
+  c.hist.push_back(c.time);
+  c.hist.push_back(ke);
+  c.hist.push_back(en);
+}
+
+// RK update, src/mainloop.F90:441-476
+static void rk_update(Case& c, int rkstep /*1-based*/) {
+  static const double rkcoe[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {num1d3, num2d3, num2d3}};
+  const double c1 = rkcoe[rkstep - 1][0], c2 = rkcoe[rkstep - 1][1], c3 = rkcoe[rkstep - 1][2];
+  for (Block& b : c.blk)
+    for (int m = 0; m < 5; ++m) {
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int k = 0; k <= b.km; ++k)
+        for (int j = 0; j <= b.jm; ++j)
+          for (int i = 0; i <= b.im; ++i) {
+            double v = c1 * b.qsave[m](i, j, k) + c2 * b.q[m](i, j, k) * b.jacob(i, j, k) +
+                       c3 * b.qrhs[m](i, j, k) * c.deltat;
+            b.q[m](i, j, k) = v / b.jacob(i, j, k);
+          }
+    }
+}
+
+static void save_q(Case& c) {  // mainloop.F90:429-433
+  for (Block& b : c.blk)
+    for (int m = 0; m < 5; ++m)
+      for (int k = 0; k <= b.km; ++k)
+        for (int j = 0; j <= b.jm; ++j)
+          for (int i = 0; i <= b.im; ++i) b.qsave[m](i, j, k) = b.q[m](i, j, k) * b.jacob(i, j, k);
+}
+
+static void zero_qrhs(Case& c) {
+  for (Block& b : c.blk)
+    for (auto& f : b.qrhs) std::fill(f.v.begin(), f.v.end(), 0.0);
+}
+
+// One RK stage, src/mainloop.F90:396-482 (boucon / spongefilter are no-ops for TGV)
+static void rk_stage(Case& c, int rkstep) {
+  if (c.lfilter) filterq(c);
+  zero_qrhs(c);
+  qswap(c);
+  gradcal(c);
+  if (rkstep == 1) {
+    save_q(c);
+    statcal(c);  // rkfirst -> statcal
+  }
+  rhscal(c);
+  rk_update(c, rkstep);
+  updatefvar(c);
+}
+
+// src/initialisation.F90:621-702 tgvini + fludyna.F90:254-300 updateq
+static void tgvini(Case& c) {
+  const double roinf = 1.0, uinf = 1.0, l_0 = 1.0;
+  const double pinf = roinf * 1.0 / c.th.const2;  // solver.F90:120 pinf=roinf*tinf/const2
+  for (Block& b : c.blk)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) {
+          const double X = b.x[0](i, j, k), Y = b.x[1](i, j, k), Z = b.x[2](i, j, k);
+          b.rho(i, j, k) = roinf;
+          b.vel[0](i, j, k) = uinf * std::sin(X / l_0) * std::cos(Y / l_0) * std::cos(Z / l_0);
+          b.vel[1](i, j, k) = -uinf * std::cos(X / l_0) * std::sin(Y / l_0) * std::cos(Z / l_0);
+          b.vel[2](i, j, k) = 0.0;
+          b.prs(i, j, k) = pinf + b.rho(i, j, k) / 16.0 * (uinf * uinf) *
+                                      (std::cos(2.0 * X / l_0) + std::cos(2.0 * Y / l_0)) *
+                                      (std::cos(2.0 * Z / l_0) + 2.0);
+          b.tmp(i, j, k) = b.prs(i, j, k) / b.rho(i, j, k) * c.th.const2;
+          // fvar2q_3da with temperature (fludyna.F90:501-505)
+          const double r = b.rho(i, j, k), u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+          b.q[0](i, j, k) = r; b.q[1](i, j, k) = r * u; b.q[2](i, j, k) = r * v; b.q[3](i, j, k) = r * w;
+          b.q[4](i, j, k) = r * (b.tmp(i, j, k) * c.th.const1 + 0.5 * (u * u + v * v + w * w));
+        }
+}
+
+}  // namespace astr_oracle
+
+// ---------------------------------------------------------------------------------
+// C entry points (ctypes)
+// ---------------------------------------------------------------------------------
+using namespace astr_oracle;
+extern "C" {
+
+// Create a case: global grid ia x ja x ka intervals on an isize x jsize x ksize block
+// grid, periodic flags, cube [0,lx]x[0,ly]x[0,lz].  sutherland_s: 110.3 (src/) or 110.4.
+void* oracle_case_create(int ia, int ja, int ka, int isize, int jsize, int ksize, int lihomo,
+                         int ljhomo, int lkhomo, double lx, double ly, double lz, double reynolds,
+                         double mach, double alfa_filter, double deltat, double sutherland_s) {
+  Case* c = new Case();
+  c->ia = ia; c->ja = ja; c->ka = ka;
+  c->size[0] = isize; c->size[1] = jsize; c->size[2] = ksize;
+  c->homo[0] = lihomo; c->homo[1] = ljhomo; c->homo[2] = lkhomo;
+  c->alfa_filter = alfa_filter; c->deltat = deltat;
+  c->th.reynolds = reynolds; c->th.mach = mach; c->th.ref_tem = 273.15;
+  c->th.refcal(sutherland_s);
+  decompose(*c);
+  filter_coefficient_cal(c->fc, alfa_filter, 1.11, 0.98);  // comsolver.F90:121
+  for (Block& b : c->blk) {
+    alloc_block(b);
+    for (int d = 0; d < 3; ++d) {
+      fd_scheme_initiate(b.fds[d], 643, 'c', b.npdc[d], b.dim(d));
+      compact_filter_initiate(b.fil[d], b.npdc[d], b.dim(d), alfa_filter);
+    }
+    // gridcube (gridgeneration.F90:246-262)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) {
+          b.x[0](i, j, k) = lx / double(ia) * double(i + b.g0[0]);
+          b.x[1](i, j, k) = ly / double(ja) * double(j + b.g0[1]);
+          b.x[2](i, j, k) = lz / double(ka) * double(k + b.g0[2]);
+        }
+  }
+  c->xmax = lx / double(ia) * double(ia);
+  return c;
+}
+void oracle_case_destroy(void* h) { delete static_cast<Case*>(h); }
+int oracle_case_nblocks(void* h) { return int(static_cast<Case*>(h)->blk.size()); }
+// info[0..2]=im,jm,km  [3..5]=npdc  [6..11]=is,ie,js,je,ks,ke  [12..14]=ig0..  [15..20]=neighbours
+void oracle_case_block_info(void* h, int ib, int* info) {
+  const Block& b = static_cast<Case*>(h)->blk[ib];
+  info[0] = b.im; info[1] = b.jm; info[2] = b.km;
+  for (int d = 0; d < 3; ++d) {
+    info[3 + d] = b.npdc[d];
+    info[6 + 2 * d] = b.s[d]; info[7 + 2 * d] = b.e[d];
+    info[12 + d] = b.g0[d];
+    info[15 + 2 * d] = b.nb[d][0]; info[16 + 2 * d] = b.nb[d][1];
+  }
+}
+// Overwrite the node coordinates of a block (0:im,0:jm,0:km, Fortran order, 3 comps)
+void oracle_case_set_x(void* h, int ib, const double* x) {
+  Block& b = static_cast<Case*>(h)->blk[ib];
+  size_t t = 0;
+  for (int m = 0; m < 3; ++m)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) b.x[m](i, j, k) = x[t++];
+}
+void oracle_case_gridgeom(void* h) { gridgeom(*static_cast<Case*>(h)); }
+void oracle_case_tgvini(void* h) { tgvini(*static_cast<Case*>(h)); }
+
+static Field* field_by_id(Block& b, int id) {
+  // 0-4 q | 5 rho | 6-8 vel | 9 prs | 10 tmp | 11-15 qrhs | 16 jacob | 17-25 dxi(a,b) a-major
+  // 26-34 dvel(m,n) m-major | 35-37 dtmp | 38-43 sigma | 44-46 qflux | 47-49 x | 50-54 qsave
+  // 55-57 vor
+  if (id < 5) return &b.q[id];
+  if (id == 5) return &b.rho;
+  if (id < 9) return &b.vel[id - 6];
+  if (id == 9) return &b.prs;
+  if (id == 10) return &b.tmp;
+  if (id < 16) return &b.qrhs[id - 11];
+  if (id == 16) return &b.jacob;
+  if (id < 26) return &b.dxi[(id - 17) / 3][(id - 17) % 3];
+  if (id < 35) return &b.dvel[(id - 26) / 3][(id - 26) % 3];
+  if (id < 38) return &b.dtmp[id - 35];
+  if (id < 44) return &b.sigma[id - 38];
+  if (id < 47) return &b.qflux[id - 44];
+  if (id < 50) return &b.x[id - 47];
+  if (id < 55) return &b.qsave[id - 50];
+  if (id < 58) return &b.vor[id - 55];
+  return nullptr;
+}
+// Copy a field (always in the halo'd shape (im+11)(jm+11)(km+11)) out of / into a block.
+void oracle_case_get(void* h, int ib, int id, double* out) {
+  Field* f = field_by_id(static_cast<Case*>(h)->blk[ib], id);
+  std::memcpy(out, f->v.data(), f->v.size() * sizeof(double));
+}
+void oracle_case_set(void* h, int ib, int id, const double* in) {
+  Field* f = field_by_id(static_cast<Case*>(h)->blk[ib], id);
+  std::memcpy(f->v.data(), in, f->v.size() * sizeof(double));
+}
+// Stage operators, individually callable so each can be compared with its CUDA twin.
+void oracle_case_filterq(void* h) { filterq(*static_cast<Case*>(h)); }
+void oracle_case_qswap(void* h) { qswap(*static_cast<Case*>(h)); }
+void oracle_case_gradcal(void* h) { gradcal(*static_cast<Case*>(h)); }
+void oracle_case_zero_qrhs(void* h) { zero_qrhs(*static_cast<Case*>(h)); }
+void oracle_case_convrsdcal6(void* h) { convrsdcal6(*static_cast<Case*>(h)); }
+void oracle_case_rhscal(void* h) { rhscal(*static_cast<Case*>(h)); }
+void oracle_case_save_q(void* h) { save_q(*static_cast<Case*>(h)); }
+void oracle_case_rk_update(void* h, int rkstep) { rk_update(*static_cast<Case*>(h), rkstep); }
+void oracle_case_updatefvar(void* h) { updatefvar(*static_cast<Case*>(h)); }
+void oracle_case_rk_stage(void* h, int rkstep) { rk_stage(*static_cast<Case*>(h), rkstep); }
+void oracle_case_set_flags(void* h, int lfilter, int diffterm) {
+  Case* c = static_cast<Case*>(h);
+  c->lfilter = lfilter; c->diffterm = diffterm;
+}
+// nsteps full RK3 steps (mainloop.F90:103-205: rk stages, then nstep++, time+=dt)
+int oracle_case_run(void* h, int nsteps) {
+  Case* c = static_cast<Case*>(h);
+  for (int s = 0; s < nsteps; ++s) {
+    for (int rk = 1; rk <= 3; ++rk) rk_stage(*c, rk);
+    c->nstep += 1;
+    c->time = c->time + c->deltat;
+  }
+  return int(c->hist.size() / 4);
+}
+void oracle_case_history(void* h, double* out) {
+  Case* c = static_cast<Case*>(h);
+  std::memcpy(out, c->hist.data(), c->hist.size() * sizeof(double));
+}
+}
