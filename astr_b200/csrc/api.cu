@@ -1,0 +1,806 @@
+// astr_b200/csrc/api.cu -- the C ABI of include/astr_gpu.h: context, line-operator
+// tables, halo exchange, and the Runge-Kutta stage built from sweep.cu / pointwise.cu.
+//
+// Stage order and semantics follow src/mainloop.F90:396-482 (time_integration_rk):
+//   filterq -> (qrhs=0) -> [boucon: caller] -> qswap -> gradcal -> rhscal -> RK update ->
+//   [spongefilter: caller] -> updatefvar
+#include "../../include/astr_gpu.h"
+#include "common.cuh"
+#include "pointwise.cuh"
+#include "geom.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <mutex>
+
+// -------------------------------------------------------------------------------------
+// errors / counters
+// -------------------------------------------------------------------------------------
+static std::string g_err;
+static long long g_launches = 0;
+
+int astr_fail(const char* what, cudaError_t e, const char* file, int line) {
+  char buf[1024];
+  snprintf(buf, sizeof buf, "astr_gpu: %s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  g_err = buf;
+  return 1;
+}
+int astr_fail_msg(const char* msg) {
+  g_err = std::string("astr_gpu: ") + msg;
+  return 1;
+}
+void astr_count_launch(int n) { g_launches += n; }
+
+// -------------------------------------------------------------------------------------
+// NCCL through dlopen: the library loads without NCCL for single-GPU use and shares the
+// host process' libnccl.so.2 (torch's bundled copy, or the MPI application's).
+// -------------------------------------------------------------------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return false;
+#define SYM(field, name) *(void**)(&field) = dlsym(h, name); if (!field) return false;
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+#define NCCL_OK(call)                                                              \
+  do {                                                                             \
+    ncclResult_t r_ = (call);                                                      \
+    if (r_ != ncclSuccess) {                                                       \
+      g_err = std::string("astr_gpu: ") + #call + " failed: " + g_nccl.GetErrorString(r_); \
+      return 1;                                                                    \
+    }                                                                              \
+  } while (0)
+
+// -------------------------------------------------------------------------------------
+// host-side line operators (product code; the reference builds the same tables in
+// fd_scheme_initiate src/derivative.F90:63-158 and compact_filter_initiate
+// src/filter.F90:31-100, pre-factored by tridiagonal_thomas_proprocess
+// src/commfunc.F90:752-774)
+// -------------------------------------------------------------------------------------
+struct HostOp {
+  int first_node = 0, nrows = 0, ntype = 0, n = 0, C = 1, nsf = 0, nsl = 0;
+  std::vector<double> a, c, ac1, ac2, ac3, pf, qb;
+  double* d_tab = nullptr;  // 5*nrows doubles on the device
+  LineOp dev() const {
+    LineOp o;
+    o.ac1 = d_tab; o.ac2 = d_tab + nrows; o.ac3 = d_tab + 2 * nrows;
+    o.pf = d_tab + 3 * nrows; o.qb = d_tab + 4 * nrows;
+    o.first_node = first_node; o.nrows = nrows; o.ntype = ntype; o.n = n; o.C = C;
+    o.nsf = nsf; o.nsl = nsl;
+    return o;
+  }
+};
+
+static void factorise(HostOp& h) {
+  const int N = h.nrows;
+  h.ac1.assign(N, 0.0); h.ac2.assign(N, 0.0); h.ac3.assign(N, 0.0);
+  h.ac1[0] = h.c[0];
+  h.ac2[0] = 1.0;  // row 0 is not scaled by the forward sweep (commfunc.F90:800-804)
+  h.ac3[0] = 0.0;
+  for (int i = 1; i < N; ++i) {
+    h.ac1[i] = h.c[i] / (1.0 - h.a[i] * h.ac1[i - 1]);
+    h.ac2[i] = 1.0 / (1.0 - h.a[i] * h.ac1[i - 1]);
+    h.ac3[i] = h.a[i] / (1.0 - h.a[i] * h.ac1[i - 1]);
+  }
+  // chunk propagation products of the partitioned solve (sweep.cu)
+  h.C = astr_sweep_max_chunks(N);
+  h.pf.assign(N, 0.0); h.qb.assign(N, 0.0);
+  for (int c = 0; c < h.C; ++c) {
+    const int ra = (c * N) / h.C, rb = ((c + 1) * N) / h.C - 1;
+    double p = 1.0;
+    for (int r = ra; r <= rb; ++r) { p = p * (-h.ac3[r]); h.pf[r] = p; }
+    double q = 1.0;
+    for (int r = rb; r >= ra; --r) { q = q * (-h.ac1[r]); h.qb[r] = q; }
+  }
+}
+
+static void build_deriv(HostOp& h, int ntype, int n) {
+  const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
+  h.ntype = ntype; h.n = n;
+  h.first_node = p0 ? 0 : -1;
+  const int last = pm ? n : n + 1;
+  h.nrows = last - h.first_node + 1;
+  h.a.assign(h.nrows, 1.0 / 3.0); h.c.assign(h.nrows, 1.0 / 3.0);
+  const int e = h.nrows - 1;
+  h.a[0] = h.c[0] = 0.0; h.a[e] = h.c[e] = 0.0;       // explicit interface rows
+  if (p0) { h.a[0] = h.c[0] = 2.0; h.a[1] = h.c[1] = 0.25; }   // 3rd/4th-order wall rows
+  if (pm) { h.a[e] = h.c[e] = 2.0; h.a[e - 1] = h.c[e - 1] = 0.25; }
+  h.nsf = p0 ? 2 : 1; h.nsl = pm ? 2 : 1;
+  factorise(h);
+}
+
+static void build_filter(HostOp& h, int ntype, int n, double alfa) {
+  const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
+  h.ntype = ntype; h.n = n;
+  h.first_node = p0 ? 0 : -3;
+  const int last = pm ? n : n + 3;
+  h.nrows = last - h.first_node + 1;
+  h.a.assign(h.nrows, alfa); h.c.assign(h.nrows, alfa);
+  const int e = h.nrows - 1;
+  h.a[0] = h.c[0] = p0 ? 0.98 : 1.11;     // beter_bound / beter_halo, comsolver.F90:121
+  h.a[e] = h.c[e] = pm ? 0.98 : 1.11;
+  h.nsf = p0 ? 5 : 3; h.nsl = pm ? 5 : 3;
+  factorise(h);
+}
+
+static void build_filter_coef(FilterCoef& fc, double alfa, double bh, double bb) {
+  // src/filter.F90:299-432
+  const double c6[4] = {(11.0 + 10.0 * alfa) / 32.0, (15.0 + 34.0 * alfa) / 64.0, (-3.0 + 6.0 * alfa) / 32.0,
+                        (1.0 - 2.0 * alfa) / 64.0};
+  const double c8[5] = {(93.0 + 70.0 * alfa) / 256.0, (7.0 + 18.0 * alfa) / 32.0, (-7.0 + 14.0 * alfa) / 64.0,
+                        (1.0 - 2.0 * alfa) / 32.0, (-1.0 + 2.0 * alfa) / 256.0};
+  const double c10[6] = {(193.0 + 126.0 * alfa) / 512.0, (105.0 + 302.0 * alfa) / 512.0,
+                         (-15.0 + 30.0 * alfa) / 128.0, (45.0 - 90.0 * alfa) / 1024.0,
+                         (-5.0 + 10.0 * alfa) / 512.0,  (1.0 - 2.0 * alfa) / 1024.0};
+  memcpy(fc.coef6i, c6, sizeof c6); memcpy(fc.coef8i, c8, sizeof c8); memcpy(fc.coef10i, c10, sizeof c10);
+  memset(fc.coefb, 0, sizeof fc.coefb); memset(fc.coefh, 0, sizeof fc.coefh);
+  const double b3[9] = {(1.0 - 2.0 * alfa) / 256.0, (-1.0 + 2.0 * alfa) / 32.0, (7.0 + 50.0 * alfa) / 64.0,
+                        (25.0 + 14.0 * alfa) / 32.0, (35.0 + 58.0 * alfa) / 128.0, (-7.0 + 14.0 * alfa) / 32.0,
+                        (7.0 - 14.0 * alfa) / 64.0, (-1.0 + 2.0 * alfa) / 32.0, (1.0 - 2.0 * alfa) / 256.0};
+  const double b2[7] = {(-1.0 + 2.0 * alfa) / 64.0, (3.0 + 26.0 * alfa) / 32.0, (49.0 + 30.0 * alfa) / 64.0,
+                        (5.0 + 6.0 * alfa) / 16.0, (-15.0 + 30.0 * alfa) / 64.0, (3.0 - 6.0 * alfa) / 32.0,
+                        (-1.0 + 2.0 * alfa) / 64.0};
+  const double b1[7] = {(1.0 + 62.0 * alfa) / 64.0, (29.0 + 6.0 * alfa) / 32.0, (15.0 + 34.0 * alfa) / 64.0,
+                        (-5.0 + 10.0 * alfa) / 16.0, (15.0 - 30.0 * alfa) / 64.0, (-3.0 + 6.0 * alfa) / 32.0,
+                        (1.0 - 2.0 * alfa) / 64.0};
+  const double b0[7] = {(63.0 + 1.0 * bb) / 64.0, (3.0 + 29.0 * bb) / 32.0, (-15.0 + 15.0 * bb) / 64.0,
+                        (5.0 - 5.0 * bb) / 16.0, (-15.0 + 15.0 * bb) / 64.0, (3.0 - 3.0 * bb) / 32.0,
+                        (-1.0 + 1.0 * bb) / 64.0};
+  memcpy(fc.coefb[3], b3, sizeof b3); memcpy(fc.coefb[2], b2, sizeof b2);
+  memcpy(fc.coefb[1], b1, sizeof b1); memcpy(fc.coefb[0], b0, sizeof b0);
+  const double h0[11] = {(-1.0 + 1.0 * bh) / 1024.0, (5.0 - 5.0 * bh) / 512.0, (979.0 + 45.0 * bh) / 1024.0,
+                         (15.0 + 113.0 * bh) / 128.0, (-105.0 + 105.0 * bh) / 512.0, (63.0 - 63.0 * bh) / 256.0,
+                         (-105.0 + 105.0 * bh) / 512.0, (15.0 - 15.0 * bh) / 128.0, (-45.0 + 45.0 * bh) / 1024.0,
+                         (5.0 - 5.0 * bh) / 512.0, (-1.0 + 1.0 * bh) / 1024.0};
+  const double h1[11] = {(1.0 - 2.0 * alfa) / 1024.0, (-5.0 + 10.0 * alfa) / 512.0, (45.0 + 934.0 * alfa) / 1024.0,
+                         (113.0 + 30.0 * alfa) / 128.0, (105.0 + 302.0 * alfa) / 512.0,
+                         (-63.0 + 126.0 * alfa) / 256.0, (105.0 - 210.0 * alfa) / 512.0,
+                         (-15.0 + 30.0 * alfa) / 128.0, (45.0 - 90.0 * alfa) / 1024.0,
+                         (-5.0 + 10.0 * alfa) / 512.0, (1.0 - 2.0 * alfa) / 1024.0};
+  const double h2[11] = {(-1.0 + 2.0 * alfa) / 1024.0, (5.0 - 10.0 * alfa) / 512.0, (-45.0 + 90.0 * alfa) / 1024.0,
+                         (15.0 + 98.0 * alfa) / 128.0, (407.0 + 210.0 * alfa) / 512.0,
+                         (63.0 + 130.0 * alfa) / 256.0, (-105.0 + 210.0 * alfa) / 512.0,
+                         (15.0 - 30.0 * alfa) / 128.0, (-45.0 + 90.0 * alfa) / 1024.0,
+                         (5.0 - 10.0 * alfa) / 512.0, (-1.0 + 2.0 * alfa) / 1024.0};
+  memcpy(fc.coefh[0], h0, sizeof h0); memcpy(fc.coefh[1], h1, sizeof h1); memcpy(fc.coefh[2], h2, sizeof h2);
+}
+
+// -------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------
+enum ProfCat { PC_FILTER_I, PC_FILTER_J, PC_FILTER_K, PC_HALO, PC_GRAD_I, PC_GRAD_J, PC_GRAD_K, PC_VISC,
+               PC_FLUX, PC_DIV_I, PC_DIV_J, PC_DIV_K, PC_RK, PC_FVAR, PC_COUNT };
+
+struct ProfSpan { int cat; cudaEvent_t a, b; };
+
+struct Ctx {
+  astr_cfg cfg;
+  Layout L;
+  Thermo th;
+  double* pool = nullptr;        // S_CORE fields
+  double* scr = nullptr;         // 15 scratch fields, lazily allocated
+  HostOp fd[3], fl[3];
+  double* d_partial = nullptr;   // stats partial sums
+  double* d_out2 = nullptr;
+  cudaStream_t st = nullptr;
+  bool have_metrics = false, have_grad = false;
+  double force[3] = {0, 0, 0};
+  // multi-block
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  double* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send lo, send hi, recv lo, recv hi
+  size_t xbuf_doubles = 0;
+  // profiling
+  bool profile = false;
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> free_events;
+  double prof_ms[PC_COUNT] = {0};
+  long long prof_n[PC_COUNT] = {0};
+  double* slot(int s) const { return (s >= S_SCR ? scr + (size_t)(s - S_SCR) * L.fstride : pool + (size_t)s * L.fstride); }
+};
+static Ctx* g = nullptr;
+
+#define NEED_CTX()                                           \
+  do {                                                       \
+    if (!g) return astr_fail_msg("astr_gpu_init not called"); \
+  } while (0)
+#define TRY(x)                  \
+  do {                          \
+    int rc_ = (x);              \
+    if (rc_) return rc_;        \
+  } while (0)
+
+struct ProfScope {
+  int cat; bool on; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get() {
+    if (!g->free_events.empty()) { cudaEvent_t e = g->free_events.back(); g->free_events.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  explicit ProfScope(int c) : cat(c), on(g && g->profile) {
+    if (on) { a = get(); b = get(); cudaEventRecord(a, g->st); }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(b, g->st); g->spans.push_back({cat, a, b}); }
+  }
+};
+static void prof_collect() {
+  for (auto& s : g->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { g->prof_ms[s.cat] += ms; g->prof_n[s.cat] += 1; }
+    g->free_events.push_back(s.a); g->free_events.push_back(s.b);
+  }
+  g->spans.clear();
+}
+
+static int ensure_scratch() {
+  if (g->scr) return 0;
+  const size_t bytes = (size_t)(S_TOTAL - S_SCR) * g->L.fstride * sizeof(double);
+  CUDA_OK(cudaMalloc(&g->scr, bytes));
+  CUDA_OK(cudaMemsetAsync(g->scr, 0, bytes, g->st));
+  return 0;
+}
+
+static FieldList fields(int s0, int n) {
+  FieldList fl;
+  fl.nf = n;
+  for (int i = 0; i < n; ++i) fl.f[i] = g->slot(s0 + i);
+  return fl;
+}
+
+// -------------------------------------------------------------------------------------
+// halo exchange of one direction (dataswap / qswap / datasync, src/parallel.F90)
+// -------------------------------------------------------------------------------------
+static int exchange_dir(const FieldList& fl, int d, int mode) {
+  const astr_cfg& c = g->cfg;
+  ProfScope ps(PC_HALO);
+  if (c.size[d] == 1) {
+    if (!c.lhomo[d]) return 0;
+    return pw_halo_wrap(g->L, fl, d, mode, g->st);
+  }
+  if (!g->comm) return astr_fail_msg("multi-block exchange needs astr_gpu_comm_init");
+  const Layout& L = g->L;
+  const int l0 = (mode == XMODE_SWAP) ? 1 : 0, l1 = (mode == XMODE_SYNC) ? 0 : ASTR_HM;
+  const int n1 = (d == 0) ? L.jm + 1 : L.im + 1, n2 = (d == 2) ? L.jm + 1 : L.km + 1;
+  const size_t cnt = (size_t)(l1 - l0 + 1) * n1 * n2 * fl.nf;
+  if (cnt > g->xbuf_doubles) {
+    for (auto& b : g->xbuf) { if (b) cudaFree(b); b = nullptr; }
+    const size_t want = cnt;
+    for (auto& b : g->xbuf) CUDA_OK(cudaMalloc(&b, want * sizeof(double)));
+    g->xbuf_doubles = want;
+  }
+  const int lo = c.nbr[2 * d], hi = c.nbr[2 * d + 1];
+  if (lo >= 0) TRY(pw_pack(L, fl, d, 0, l0, l1, g->xbuf[0], g->st));
+  if (hi >= 0) TRY(pw_pack(L, fl, d, 1, l0, l1, g->xbuf[1], g->st));
+  NCCL_OK(g_nccl.GroupStart());
+  if (lo >= 0) NCCL_OK(g_nccl.Send(g->xbuf[0], cnt, ncclDouble, lo, g->comm, g->st));
+  if (hi >= 0) NCCL_OK(g_nccl.Send(g->xbuf[1], cnt, ncclDouble, hi, g->comm, g->st));
+  // when lo == hi (two blocks, periodic) the peer's first message is its low-side buffer,
+  // which belongs in my high halo: post that receive first.
+  if (hi >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[3], cnt, ncclDouble, hi, g->comm, g->st));
+  if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->st));
+  NCCL_OK(g_nccl.GroupEnd());
+  if (hi >= 0) TRY(pw_unpack(L, fl, d, 1, l0, l1, g->xbuf[3], g->st));
+  if (lo >= 0) TRY(pw_unpack(L, fl, d, 0, l0, l1, g->xbuf[2], g->st));
+  return 0;
+}
+
+int astr_exchange_slots(const int* slots, int nf, int d, int mode) {
+  FieldList fl;
+  fl.nf = nf;
+  for (int i = 0; i < nf; ++i) fl.f[i] = g->slot(slots[i]);
+  return exchange_dir(fl, d, mode);
+}
+double* astr_slot_ptr(int slot) { return g->slot(slot); }
+
+// gridsendrecv of one direction (src/parallel.F90:2780-3035): x lives in slots S_G+0..2
+int astr_xhalo_exchange(int d) {
+  const astr_cfg& c = g->cfg;
+  const Layout& L = g->L;
+  double* x3[3] = {g->slot(S_G), g->slot(S_G + 1), g->slot(S_G + 2)};
+  if (c.size[d] == 1) return geom_xhalo_single(L, x3, d, g->st);
+  if (!g->comm) return astr_fail_msg("multi-block gridgeom needs astr_gpu_comm_init");
+  const int n1 = (d == 0) ? L.jm + 1 : L.im + 1, n2 = (d == 2) ? L.jm + 1 : L.km + 1;
+  const size_t cnt = (size_t)3 * ASTR_HM * n1 * n2;
+  if (cnt > g->xbuf_doubles) {
+    for (auto& b : g->xbuf) { if (b) cudaFree(b); b = nullptr; }
+    for (auto& b : g->xbuf) CUDA_OK(cudaMalloc(&b, cnt * sizeof(double)));
+    g->xbuf_doubles = cnt;
+  }
+  const int lo = c.nbr[2 * d], hi = c.nbr[2 * d + 1];
+  TRY(geom_xhalo_pack(L, x3, d, g->xbuf[0], g->xbuf[1], g->st));
+  NCCL_OK(g_nccl.GroupStart());
+  if (lo >= 0) NCCL_OK(g_nccl.Send(g->xbuf[0], cnt, ncclDouble, lo, g->comm, g->st));
+  if (hi >= 0) NCCL_OK(g_nccl.Send(g->xbuf[1], cnt, ncclDouble, hi, g->comm, g->st));
+  if (hi >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[3], cnt, ncclDouble, hi, g->comm, g->st));
+  if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->st));
+  NCCL_OK(g_nccl.GroupEnd());
+  return geom_xhalo_unpack(L, x3, d, lo >= 0 ? g->xbuf[2] : nullptr, hi >= 0 ? g->xbuf[3] : nullptr, g->st);
+}
+
+static int dataswap(const FieldList& fl, int direction /*-1 all*/) {
+  for (int d = 0; d < 3; ++d)
+    if (direction < 0 || direction == d) TRY(exchange_dir(fl, d, XMODE_SWAP));
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------
+// sweeps
+// -------------------------------------------------------------------------------------
+static int sweep(int d, int optype, const double* const* in, double* const* out, int nf, int epi, int o_lo,
+                 int o_hi) {
+  SweepArgs a;
+  memset(&a, 0, sizeof a);
+  a.L = g->L;
+  a.op = (optype == OP_DERIV ? g->fd[d] : g->fl[d]).dev();
+  a.nf = nf;
+  for (int i = 0; i < nf; ++i) { a.in[i] = in[i]; a.out[i] = out[i]; }
+  a.epi = epi; a.o_lo = o_lo; a.o_hi = o_hi;
+  return astr_launch_sweep(d, optype, a, g->st);
+}
+
+int astr_sweep_slots(int d, int optype, const int* in_slots, const int* out_slots, int nf, int epi, int o_lo,
+                     int o_hi) {
+  const double* in[ASTR_MAXF]; double* out[ASTR_MAXF];
+  for (int i = 0; i < nf; ++i) { in[i] = g->slot(in_slots[i]); out[i] = g->slot(out_slots[i]); }
+  return sweep(d, optype, in, out, nf, epi, o_lo, o_hi);
+}
+
+static int dim_of(int d) { return d == 0 ? g->cfg.im : (d == 1 ? g->cfg.jm : g->cfg.km); }
+
+// -------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------
+extern "C" {
+
+const char* astr_gpu_last_error(void) { return g_err.c_str(); }
+int astr_gpu_sizeof_cfg(void) { return (int)sizeof(astr_cfg); }
+
+int astr_gpu_init(const astr_cfg* cfg) {
+  if (!cfg) return astr_fail_msg("null cfg");
+  if (cfg->abi_version != ASTR_GPU_ABI_VERSION) return astr_fail_msg("abi_version mismatch");
+  if (cfg->hm != ASTR_HM || cfg->numq != ASTR_GPU_NUMQ) return astr_fail_msg("hm must be 5 and numq 5");
+  if (cfg->ndims != 3 || cfg->km < 1) return astr_fail_msg("only ndims=3 blocks are implemented");
+  if (!cfg->nondimen) return astr_fail_msg("only nondimen=t is implemented");
+  if (!cfg->scheme_compact || cfg->conschm != 643 || cfg->difschm != 643)
+    return astr_fail_msg("only conschm=difschm=643c (central compact) is implemented");
+  if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
+  for (int d = 0; d < 3; ++d)
+    if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
+  if (g) astr_gpu_finalize();
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return astr_fail_msg("no CUDA device: this library has no CPU path");
+  if (cfg->device >= 0) CUDA_OK(cudaSetDevice(cfg->device));
+  g = new Ctx();
+  g->cfg = *cfg;
+  Layout& L = g->L;
+  L.im = cfg->im; L.jm = cfg->jm; L.km = cfg->km;
+  L.pitch = ((ASTR_IOFF + cfg->im + 1 + ASTR_HM + 1) + 15) / 16 * 16;
+  L.njt = cfg->jm + 1 + 2 * ASTR_HM; L.nkt = cfg->km + 1 + 2 * ASTR_HM;
+  L.sj = L.pitch; L.sk = (long long)L.pitch * L.njt;
+  L.org = ASTR_IOFF + L.sj * ASTR_HM + L.sk * ASTR_HM;
+  L.fstride = (L.sk * L.nkt + 31) / 32 * 32;
+  g->th.reynolds = cfg->reynolds; g->th.prandtl = cfg->prandtl; g->th.const1 = cfg->const1;
+  g->th.const2 = cfg->const2; g->th.const5 = cfg->const5; g->th.const6 = cfg->const6;
+  g->th.tempconst = cfg->tempconst; g->th.tempconst1 = cfg->tempconst1;
+  CUDA_OK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+  const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
+  CUDA_OK(cudaMalloc(&g->pool, bytes));
+  CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
+  CUDA_OK(cudaMalloc(&g->d_partial, (size_t)2 * (cfg->jm + 1) * (cfg->km + 1) * sizeof(double)));
+  CUDA_OK(cudaMalloc(&g->d_out2, 4 * sizeof(double)));
+  FilterCoef fc;
+  build_filter_coef(fc, cfg->alfa_filter, 1.11, 0.98);
+  TRY(astr_set_filter_coef(fc));
+  for (int d = 0; d < 3; ++d) {
+    const int n = dim_of(d);
+    build_deriv(g->fd[d], cfg->npdc[d], n);
+    build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
+    for (HostOp* h : {&g->fd[d], &g->fl[d]}) {
+      if (h->C < 1) return astr_fail_msg("block too small: every direction needs at least 12 nodes");
+      const size_t nb = (size_t)5 * h->nrows * sizeof(double);
+      CUDA_OK(cudaMalloc(&h->d_tab, nb));
+      std::vector<double> t;
+      t.reserve(5 * h->nrows);
+      for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb}) t.insert(t.end(), v->begin(), v->end());
+      CUDA_OK(cudaMemcpy(h->d_tab, t.data(), nb, cudaMemcpyHostToDevice));
+    }
+  }
+  g_launches = 0;
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
+int astr_gpu_finalize(void) {
+  if (!g) return 0;
+  cudaStreamSynchronize(g->st);
+  prof_collect();
+  for (auto e : g->free_events) cudaEventDestroy(e);
+  if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
+  for (auto& b : g->xbuf) if (b) cudaFree(b);
+  for (int d = 0; d < 3; ++d) { cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab); }
+  cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
+  cudaFree(g->d_partial); cudaFree(g->d_out2);
+  cudaStreamDestroy(g->st);
+  delete g;
+  g = nullptr;
+  return 0;
+}
+
+int astr_gpu_synchronize(void) {
+  NEED_CTX();
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  prof_collect();
+  return 0;
+}
+
+int astr_gpu_comm_unique_id(char id[128]) {
+  if (!g_nccl.load()) return astr_fail_msg("cannot load libnccl.so.2");
+  ncclUniqueId uid;
+  NCCL_OK(g_nccl.GetUniqueId(&uid));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(id, &uid, 128);
+  return 0;
+}
+
+int astr_gpu_comm_init(const char id[128], int nranks, int rank) {
+  NEED_CTX();
+  if (!g_nccl.load()) return astr_fail_msg("cannot load libnccl.so.2");
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  NCCL_OK(g_nccl.CommInitRank(&g->comm, nranks, uid, rank));
+  g->nranks = nranks; g->rank = rank;
+  return 0;
+}
+
+// ---- host <-> device field transfer (Fortran halo'd box <-> padded device box) --------
+static int copy_field(int slot, double* host, bool to_host) {
+  const Layout& L = g->L;
+  const size_t w = (size_t)(L.im + 1 + 2 * ASTR_HM) * sizeof(double);
+  const size_t rows = (size_t)L.njt * L.nkt;
+  double* dev = g->slot(slot) + (ASTR_IOFF - ASTR_HM);
+  if (to_host)
+    CUDA_OK(cudaMemcpy2DAsync(host, w, dev, (size_t)L.pitch * sizeof(double), w, rows, cudaMemcpyDeviceToHost, g->st));
+  else
+    CUDA_OK(cudaMemcpy2DAsync(dev, (size_t)L.pitch * sizeof(double), host, w, w, rows, cudaMemcpyHostToDevice, g->st));
+  return 0;
+}
+static size_t host_field_elems() {
+  const Layout& L = g->L;
+  return (size_t)(L.im + 1 + 2 * ASTR_HM) * L.njt * L.nkt;
+}
+
+static int api_slot(int field_id, int* slot) {
+  if (field_id < 0 || field_id >= ASTR_F_COUNT) return astr_fail_msg("bad field id");
+  if (field_id < ASTR_F_QRHS) *slot = S_Q + field_id;                        // q, rho, vel, prs, tmp
+  else if (field_id < ASTR_F_JACOB) *slot = S_QRHS + (field_id - ASTR_F_QRHS);
+  else if (field_id == ASTR_F_JACOB) *slot = S_JAC;
+  else if (field_id < ASTR_F_DVEL) *slot = S_DXI + (field_id - ASTR_F_DXI);
+  else if (field_id < ASTR_F_SIGMA) *slot = S_SCR + (field_id - ASTR_F_DVEL);  // dvel 9, dtmp 3
+  else if (field_id < ASTR_F_QFLUX) *slot = S_SIGMA + (field_id - ASTR_F_SIGMA);
+  else if (field_id < ASTR_F_X) *slot = S_QFLUX + (field_id - ASTR_F_QFLUX);
+  else if (field_id < ASTR_F_QSAVE) *slot = S_G + (field_id - ASTR_F_X);      // x lives in G slots during gridgeom
+  else if (field_id < ASTR_F_VOR) *slot = S_QSAVE + (field_id - ASTR_F_QSAVE);
+  else *slot = S_SCR + 12 + (field_id - ASTR_F_VOR);
+  return 0;
+}
+
+int astr_gpu_get_field(int field_id, double* host) {
+  NEED_CTX();
+  int s;
+  TRY(api_slot(field_id, &s));
+  if (s >= S_SCR) {
+    TRY(ensure_scratch());
+    if (!g->have_grad) return astr_fail_msg("dvel/dtmp/vor requested before gradcal");
+    TRY(pw_materialise_grad(g->L, g->pool, g->scr, g->st));
+  }
+  TRY(copy_field(s, host, true));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
+int astr_gpu_set_field(int field_id, const double* host) {
+  NEED_CTX();
+  int s;
+  TRY(api_slot(field_id, &s));
+  if (s >= S_SCR) return astr_fail_msg("dvel/dtmp/vor are derived fields");
+  TRY(copy_field(s, const_cast<double*>(host), false));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
+int astr_gpu_device_ptr(int field_id, void** dptr, long long strides[3], long long* origin) {
+  NEED_CTX();
+  int s;
+  TRY(api_slot(field_id, &s));
+  if (s >= S_SCR) TRY(ensure_scratch());
+  *dptr = g->slot(s);
+  strides[0] = 1; strides[1] = g->L.sj; strides[2] = g->L.sk;
+  *origin = g->L.org;
+  return 0;
+}
+
+int astr_gpu_set_metrics(const double* dxi, const double* jacob) {
+  NEED_CTX();
+  const size_t ne = host_field_elems();
+  // dxi(-hm:im+hm,-hm:jm+hm,-hm:km+hm,1:3,1:3): 4th index = xi direction a, 5th = x index b
+  for (int b = 0; b < 3; ++b)
+    for (int a = 0; a < 3; ++a)
+      TRY(copy_field(S_DXI + 3 * a + b, const_cast<double*>(dxi) + (size_t)(a + 3 * b) * ne, false));
+  TRY(copy_field(S_JAC, const_cast<double*>(jacob), false));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  g->have_metrics = true;
+  return 0;
+}
+
+int astr_gpu_gridgeom(const double* x) {
+  NEED_CTX();
+  TRY(ensure_scratch());
+  const size_t ne = host_field_elems();
+  for (int m = 0; m < 3; ++m) TRY(copy_field(S_G + m, const_cast<double*>(x) + (size_t)m * ne, false));
+  TRY(geom_gridgeom(g->L, g->cfg, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  g->have_metrics = true;
+  return 0;
+}
+
+int astr_gpu_upload_state(const double* q, const double* rho, const double* vel, const double* prs,
+                          const double* tmp) {
+  NEED_CTX();
+  const size_t ne = host_field_elems();
+  if (q) for (int m = 0; m < 5; ++m) TRY(copy_field(S_Q + m, const_cast<double*>(q) + m * ne, false));
+  if (rho) TRY(copy_field(S_RHO, const_cast<double*>(rho), false));
+  if (vel) for (int m = 0; m < 3; ++m) TRY(copy_field(S_VEL + m, const_cast<double*>(vel) + m * ne, false));
+  if (prs) TRY(copy_field(S_PRS, const_cast<double*>(prs), false));
+  if (tmp) TRY(copy_field(S_TMP, const_cast<double*>(tmp), false));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
+int astr_gpu_download_state(double* q, double* rho, double* vel, double* prs, double* tmp) {
+  NEED_CTX();
+  const size_t ne = host_field_elems();
+  if (q) for (int m = 0; m < 5; ++m) TRY(copy_field(S_Q + m, q + m * ne, true));
+  if (rho) TRY(copy_field(S_RHO, rho, true));
+  if (vel) for (int m = 0; m < 3; ++m) TRY(copy_field(S_VEL + m, vel + m * ne, true));
+  if (prs) TRY(copy_field(S_PRS, prs, true));
+  if (tmp) TRY(copy_field(S_TMP, tmp, true));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  prof_collect();
+  return 0;
+}
+
+// ---- stage operators -------------------------------------------------------------------
+int astr_gpu_filterq(void) {
+  NEED_CTX();
+  const astr_cfg& c = g->cfg;
+  const FieldList fq = fields(S_Q, 5);
+  for (int d = 0; d < 3; ++d) {
+    TRY(dataswap(fq, d));                          // comsolver.F90:535,562,590
+    const int n = dim_of(d);
+    const int nt = c.npdc[d];
+    // physical-boundary nodes stay unfiltered (filter.F90:141-142): in place => not written
+    const int o_lo = (nt == 1 || nt == 4) ? 1 : 0, o_hi = (nt == 2 || nt == 4) ? n - 1 : n;
+    ProfScope ps(PC_FILTER_I + d);
+    TRY(sweep(d, OP_FILTER, fq.f, fq.f, 5, EPI_STORE, o_lo, o_hi));
+  }
+  return 0;
+}
+
+int astr_gpu_qswap(void) {
+  NEED_CTX();
+  const astr_cfg& c = g->cfg;
+  const Layout& L = g->L;
+  const FieldList fq = fields(S_Q, 5);
+  for (int d = 0; d < 3; ++d) {
+    TRY(exchange_dir(fq, d, XMODE_QSWAP));
+    bool lo, hi;
+    if (c.size[d] == 1) lo = hi = (c.lhomo[d] != 0);
+    else { lo = c.nbr[2 * d] >= 0; hi = c.nbr[2 * d + 1] >= 0; }
+    const int dm = dim_of(d);
+    ProfScope ps(PC_HALO);
+    // q2fvar on the slabs dm:dm+hm and -hm:0 (parallel.F90:4904-4915 etc.)
+    for (int side = 1; side >= 0; --side) {
+      if (!(side ? hi : lo)) continue;
+      Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+      b.lo[d] = side ? dm : -ASTR_HM;
+      b.hi[d] = side ? dm + ASTR_HM : 0;
+      TRY(pw_q2fvar(L, g->pool, g->th, b, g->st));
+    }
+  }
+  return 0;
+}
+
+int astr_gpu_gradcal(void) {
+  NEED_CTX();
+  if (!g->have_metrics) return astr_fail_msg("gradcal before set_metrics/gridgeom");
+  const double* in[4] = {g->slot(S_VEL), g->slot(S_VEL + 1), g->slot(S_VEL + 2), g->slot(S_TMP)};
+  for (int d = 0; d < 3; ++d) {
+    double* out[4];
+    for (int m = 0; m < 4; ++m) out[m] = g->slot(S_RAW + 4 * d + m);
+    ProfScope ps(PC_GRAD_I + d);
+    TRY(sweep(d, OP_DERIV, in, out, 4, EPI_STORE, 0, dim_of(d)));
+  }
+  g->have_grad = true;
+  return 0;
+}
+
+int astr_gpu_rhscal(void) {
+  NEED_CTX();
+  if (!g->have_grad) return astr_fail_msg("rhscal before gradcal");
+  const astr_cfg& c = g->cfg;
+  const Layout& L = g->L;
+  if (c.diffterm) {
+    { ProfScope ps(PC_VISC); TRY(pw_visc(L, g->pool, g->th, g->st)); }
+    TRY(dataswap(fields(S_SIGMA, 9), -1));         // sigma(6)+qflux(3), solver.F90:2604-2606
+  }
+  FluxRanges fr = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
+  {
+    ProfScope ps(PC_FLUX);
+    Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+    TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
+    for (int d = 0; d < 3; ++d)                    // halo slabs of direction d (fluxes on halo nodes,
+      for (int side = 0; side < 2; ++side) {       // solver.F90:2200-2206)
+        Box h = b;
+        h.lo[d] = side ? dim_of(d) + 1 : -ASTR_HM;
+        h.hi[d] = side ? dim_of(d) + ASTR_HM : -1;
+        TRY(pw_flux(L, g->pool, h, 1 << d, fr, c.diffterm, g->st));
+      }
+  }
+  const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
+  for (int d = 0; d < 3; ++d) {
+    const double* in[5]; double* out[5];
+    for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_QRHS + m); }
+    ProfScope ps(PC_DIV_I + d);
+    TRY(sweep(d, OP_DERIV, in, out, 5, d == 0 ? EPI_STOREZ : EPI_ADD, s[d], e[d]));
+  }
+  if (c.flowtype == 1) return astr_fail_msg("src_chan forcing is not implemented yet");
+  return 0;
+}
+
+static int rk_coef(int rkstep, double dt, RkCoef& rk) {
+  if (rkstep < 1 || rkstep > 3) return astr_fail_msg("rkstep must be 1..3");
+  // src/mainloop.F90:350-362
+  const double co[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0}};
+  rk.c1 = co[rkstep - 1][0]; rk.c2 = co[rkstep - 1][1]; rk.c3 = co[rkstep - 1][2];
+  rk.dt = dt; rk.first = (rkstep == 1);
+  return 0;
+}
+
+int astr_gpu_rk_update(int rkstep, double deltat) {
+  NEED_CTX();
+  RkCoef rk;
+  TRY(rk_coef(rkstep, deltat, rk));
+  rk.with_fvar = 0;
+  ProfScope ps(PC_RK);
+  return pw_rk_update(g->L, g->pool, g->th, rk, nullptr, g->st);
+}
+
+int astr_gpu_updatefvar(void) {
+  NEED_CTX();
+  Box b = {{0, 0, 0}, {g->L.im, g->L.jm, g->L.km}};
+  ProfScope ps(PC_FVAR);
+  return pw_q2fvar(g->L, g->pool, g->th, b, g->st);
+}
+
+int astr_gpu_rk_stage(int rkstep, double deltat) {
+  NEED_CTX();
+  if (g->cfg.lfilter) TRY(astr_gpu_filterq());
+  TRY(astr_gpu_qswap());
+  TRY(astr_gpu_gradcal());
+  TRY(astr_gpu_rhscal());
+  RkCoef rk;
+  TRY(rk_coef(rkstep, deltat, rk));
+  rk.with_fvar = 1;
+  ProfScope ps(PC_RK);
+  return pw_rk_update(g->L, g->pool, g->th, rk, nullptr, g->st);
+}
+
+int astr_gpu_rk_steps(int nsteps, double deltat) {
+  NEED_CTX();
+  for (int s = 0; s < nsteps; ++s)
+    for (int rk = 1; rk <= 3; ++rk) TRY(astr_gpu_rk_stage(rk, deltat));
+  return 0;
+}
+
+int astr_gpu_dataswap(int field_id, int direction) {
+  NEED_CTX();
+  int s;
+  TRY(api_slot(field_id, &s));
+  if (s >= S_SCR) return astr_fail_msg("dataswap of a derived field");
+  return dataswap(fields(s, 1), direction - 1);
+}
+
+int astr_gpu_set_force(const double force[3]) {
+  NEED_CTX();
+  for (int i = 0; i < 3; ++i) g->force[i] = force[i];
+  return 0;
+}
+
+int astr_gpu_reduce_tgv(double out[3]) {
+  NEED_CTX();
+  if (!g->have_grad) return astr_fail_msg("reduce_tgv before gradcal");
+  TRY(pw_stats(g->L, g->pool, g->d_partial, g->d_out2, g->st));
+  double h[2];
+  CUDA_OK(cudaMemcpyAsync(h, g->d_out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  out[0] = h[0]; out[1] = h[1]; out[2] = 0.0;
+  return 0;
+}
+
+int astr_gpu_kernel_launches(long long* count) { *count = g_launches; return 0; }
+
+int astr_gpu_set_profile(int on) {
+  NEED_CTX();
+  g->profile = on != 0;
+  if (on) { memset(g->prof_ms, 0, sizeof g->prof_ms); memset(g->prof_n, 0, sizeof g->prof_n); }
+  return 0;
+}
+// ms[PC_COUNT], n[PC_COUNT]: accumulated CUDA-event time and span count per category
+int astr_gpu_get_profile(double* ms, long long* n, int cap) {
+  NEED_CTX();
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  prof_collect();
+  for (int i = 0; i < PC_COUNT && i < cap; ++i) { ms[i] = g->prof_ms[i]; n[i] = g->prof_n[i]; }
+  return PC_COUNT;
+}
+
+// Times `iters` launches of one line-solve sweep over nfields scratch-free core fields
+// (q -> G slots for the derivative, G in place for the filter) with CUDA events on the
+// library stream.  Used by bench.py for the live roofline measurement.
+int astr_gpu_bench_sweep(int op, int dir, int nfields, int iters, float* ms_per_launch) {
+  NEED_CTX();
+  if (nfields < 1 || nfields > 5 || dir < 0 || dir > 2) return astr_fail_msg("bench_sweep: bad arguments");
+  const double* in[5]; double* out[5];
+  for (int m = 0; m < nfields; ++m) {
+    in[m] = (op == OP_FILTER) ? g->slot(S_G + m) : g->slot(S_Q + m);
+    out[m] = g->slot(S_G + m);
+  }
+  cudaEvent_t a, b;
+  CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+  TRY(sweep(dir, op, in, out, nfields, EPI_STORE, 0, dim_of(dir)));
+  CUDA_OK(cudaEventRecord(a, g->st));
+  for (int it = 0; it < iters; ++it) TRY(sweep(dir, op, in, out, nfields, EPI_STORE, 0, dim_of(dir)));
+  CUDA_OK(cudaEventRecord(b, g->st));
+  CUDA_OK(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+  *ms_per_launch = ms / iters;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// astr_b200/csrc/common.cuh -- shared declarations of libastr_gpu.so (sm_100a only).
+//
+// Device data layout.  Every 3-D field, halo'd or not in the
+// reference (src/commarray.F90:63-106), lives in ONE padded box on the device:
+//
+//   index(i,j,k) = org + i + pitch*(j + njt*k),   i in [-16, pitch-16), j in [-5, jm+5], ...
+//
+// * node i=0 sits at element 16 of each row, rows are `pitch` doubles long with pitch a
+//   multiple of 16, and the pool is 256-byte aligned: node 0 of every row is 128-byte
+//   aligned, so 16-node pencil bundles are exactly one 128-byte line, node -6 is
+//   16-byte aligned (cp.async 16-byte granules) and rows never straddle sectors.
+// * all fields share the same strides, so one index serves every array of a kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#define ASTR_HM 5
+#define ASTR_IOFF 16        // element offset of node i=0 inside a row
+#define ASTR_MAXF 16        // max fields per batched launch
+#define ASTR_BW 16          // pencils per bundle (one 128-byte line of doubles)
+
+struct Layout {
+  int im, jm, km;           // nodes 0..im, 0..jm, 0..km
+  int pitch, njt, nkt;      // row pitch (doubles), jm+11, km+11
+  long long sj, sk;         // strides of j and k in doubles
+  long long org;            // offset of node (0,0,0)
+  long long fstride;        // doubles per field (multiple of 32)
+  __host__ __device__ inline long long idx(int i, int j, int k) const {
+    return org + i + sj * (long long)j + sk * (long long)k;
+  }
+};
+
+// One pre-factored tridiagonal line operator (reference `type compact_scheme`,
+// src/commtype.F90:13-23) plus the chunk-propagation tables of the partitioned solve.
+struct LineOp {
+  const double* ac1;        // src/commfunc.F90:752-774, row r = node - first_node
+  const double* ac2;        // ac2[0] := 1, ac3[0] := 0 (row 0 is never scaled, :796)
+  const double* ac3;
+  const double* pf;         // pf[r] = prod_{m=cs(c(r))..r} (-ac3[m])
+  const double* qb;         // qb[r] = prod_{m=r..ce(c(r))} (-ac1[m])
+  int first_node, nrows, ntype, n, C;
+  int nsf, nsl;             // closure rows at the first / last end
+};
+
+// coefficient tables of src/filter.F90:299-432 (only the rows the hot path reads)
+struct FilterCoef {
+  double coef6i[4], coef8i[5], coef10i[6];
+  double coefb[4][9];
+  double coefh[3][11];
+};
+
+enum { OP_DERIV = 0, OP_FILTER = 1 };
+enum { EPI_STORE = 0, EPI_STOREZ = 1, EPI_ADD = 2 };
+
+struct SweepArgs {
+  Layout L;
+  LineOp op;
+  const double* in[ASTR_MAXF];
+  double* out[ASTR_MAXF];
+  int nf;
+  int epi;
+  int o_lo, o_hi;           // nodes of the line that are written
+  int sp;                   // i-direction: smem row pitch (doubles, == 2 mod 16)
+};
+
+#define CUDA_OK(call)                                                         \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return astr_fail(#call, e_, __FILE__, __LINE__);   \
+  } while (0)
+
+int astr_fail(const char* what, cudaError_t e, const char* file, int line);
+int astr_fail_msg(const char* msg);
+void astr_count_launch(int n = 1);
+
+// sweep.cu
+int astr_set_filter_coef(const FilterCoef& fc);
+size_t astr_sweep_smem_bytes(int dir, int n, int C, int* sp_out);
+int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
+int astr_sweep_max_chunks(int nrows);

@@ -1,0 +1,436 @@
+// astr_b200/csrc/pointwise.cu -- pointwise and surface kernels of the RK stage (sm_100a).
+// All are one-thread-per-node, i fastest (coalesced 8-byte accesses on 128-byte aligned
+// rows); they are pure streaming kernels bounded by HBM bandwidth.
+#include "pointwise.cuh"
+
+namespace {
+
+constexpr int PW_T = 128;
+
+__device__ __forceinline__ bool box_node(const Box& b, int& i, int& j, int& k) {
+  i = b.lo[0] + blockIdx.x * PW_T + threadIdx.x;
+  j = b.lo[1] + blockIdx.y;
+  k = b.lo[2] + blockIdx.z;
+  return i <= b.hi[0];
+}
+inline dim3 box_grid(const Box& b) {
+  return dim3((b.hi[0] - b.lo[0] + PW_T) / PW_T, b.hi[1] - b.lo[1] + 1, b.hi[2] - b.lo[2] + 1);
+}
+inline bool box_empty(const Box& b) {
+  return b.hi[0] < b.lo[0] || b.hi[1] < b.lo[1] || b.hi[2] < b.lo[2];
+}
+
+// ---------------------------------------------------------------------------------
+// periodic wrap of a single-block direction: array{3,4,5}d_sendrecv with one block
+// (src/parallel.F90:4169-4174), qswap (:4876-4884), array3d_sync
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_halo_wrap(const Layout L, const FieldList fl, const int mode) {
+  // threads run over the two other indices (a fastest)
+  const int na = (DIR == 0) ? L.jm + 1 : L.im + 1;
+  const int nb = (DIR == 2) ? L.jm + 1 : L.km + 1;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= na || b >= nb) return;
+  double* f = fl.f[blockIdx.z];
+  long long base, sl;
+  int dm;
+  if (DIR == 0) { base = L.idx(0, a, b); sl = 1; dm = L.im; }
+  else if (DIR == 1) { base = L.idx(a, 0, b); sl = L.sj; dm = L.jm; }
+  else { base = L.idx(a, b, 0); sl = L.sk; dm = L.km; }
+  double* p = f + base;
+  if (mode != XMODE_SYNC) {
+#pragma unroll
+    for (int l = 1; l <= ASTR_HM; ++l) {
+      p[-l * sl] = p[(dm - l) * sl];
+      p[(dm + l) * sl] = p[l * sl];
+    }
+  }
+  if (mode != XMODE_SWAP) {
+    const double v = 0.5 * (p[0] + p[dm * sl]);
+    p[0] = v;
+    p[dm * sl] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// q2fvar_3da + thermal_3d (src/fludyna.F90:545-634, :136-179), nondimensional, no species
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void q2fvar_node(double* __restrict__ pool, const long long fs, const long long x,
+                                            const Thermo& th) {
+  const double r = pool[(S_Q + 0) * fs + x];
+  const double u = pool[(S_Q + 1) * fs + x] / r;
+  const double v = pool[(S_Q + 2) * fs + x] / r;
+  const double w = pool[(S_Q + 3) * fs + x] / r;
+  const double p = (pool[(S_Q + 4) * fs + x] - 0.5 * r * (u * u + v * v + w * w)) / th.const6;
+  pool[S_RHO * fs + x] = r;
+  pool[(S_VEL + 0) * fs + x] = u;
+  pool[(S_VEL + 1) * fs + x] = v;
+  pool[(S_VEL + 2) * fs + x] = w;
+  pool[S_PRS * fs + x] = p;
+  pool[S_TMP * fs + x] = p / r * th.const2;
+}
+
+__global__ void k_q2fvar(const Layout L, double* __restrict__ pool, const Thermo th, const Box b) {
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  q2fvar_node(pool, L.fstride, L.idx(i, j, k), th);
+}
+
+// ---------------------------------------------------------------------------------
+// dvel / dtmp from the raw xi-derivatives: gradcal's accumulation
+// dvel(m,n) = sum_d d(u_m)/d(xi_d) * dxi(d,n)   (src/comsolver.F90:280-484)
+// ---------------------------------------------------------------------------------
+struct Grad { double dv[3][3], dt[3]; };
+
+__device__ __forceinline__ void load_grad(const double* __restrict__ pool, const long long fs,
+                                          const long long x, Grad& g) {
+  double dxi[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) dxi[d][n] = pool[(S_DXI + 3 * d + n) * fs + x];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const double r0 = pool[(S_RAW + 0 + m) * fs + x];
+    const double r1 = pool[(S_RAW + 4 + m) * fs + x];
+    const double r2 = pool[(S_RAW + 8 + m) * fs + x];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const double v = r0 * dxi[0][n] + r1 * dxi[1][n] + r2 * dxi[2][n];
+      if (m < 3) g.dv[m][n] = v; else g.dt[n] = v;
+    }
+  }
+}
+
+__global__ void k_materialise_grad(const Layout L, const double* __restrict__ pool, double* __restrict__ out) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  Grad g;
+  load_grad(pool, fs, x, g);
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int n = 0; n < 3; ++n) out[(3 * m + n) * fs + x] = g.dv[m][n];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) out[(9 + n) * fs + x] = g.dt[n];
+  out[12 * fs + x] = g.dv[2][1] - g.dv[1][2];   // src/solver.F90:2456-2458
+  out[13 * fs + x] = g.dv[0][2] - g.dv[2][0];
+  out[14 * fs + x] = g.dv[1][0] - g.dv[0][1];
+}
+
+// ---------------------------------------------------------------------------------
+// viscous stress and heat flux, diffrsdcal6 pointwise part (src/solver.F90:2433-2602)
+// with miucal (src/fludyna.F90:791-812)
+// ---------------------------------------------------------------------------------
+__global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo th) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  Grad g;
+  load_grad(pool, fs, x, g);
+  const double t = pool[S_TMP * fs + x];
+  const double miu = (t * sqrt(t) * th.tempconst1 / (t + th.tempconst)) / th.reynolds;
+  const double s11 = g.dv[0][0];
+  const double s12 = 0.5 * (g.dv[0][1] + g.dv[1][0]);
+  const double s13 = 0.5 * (g.dv[0][2] + g.dv[2][0]);
+  const double s22 = g.dv[1][1];
+  const double s23 = 0.5 * (g.dv[1][2] + g.dv[2][1]);
+  const double s33 = g.dv[2][2];
+  const double skk = (1.0 / 3.0) * (s11 + s22 + s33);
+  const double miu2 = 2.0 * miu;
+  const double hcc = (miu / th.prandtl) / th.const5;
+  const double sg1 = miu2 * (s11 - skk);
+  const double sg2 = miu2 * s12;
+  const double sg3 = miu2 * s13;
+  const double sg4 = miu2 * (s22 - skk);
+  const double sg5 = miu2 * s23;
+  const double sg6 = miu2 * (s33 - skk);
+  pool[(S_SIGMA + 0) * fs + x] = sg1;
+  pool[(S_SIGMA + 1) * fs + x] = sg2;
+  pool[(S_SIGMA + 2) * fs + x] = sg3;
+  pool[(S_SIGMA + 3) * fs + x] = sg4;
+  pool[(S_SIGMA + 4) * fs + x] = sg5;
+  pool[(S_SIGMA + 5) * fs + x] = sg6;
+  const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+  pool[(S_QFLUX + 0) * fs + x] = hcc * g.dt[0] + sg1 * u + sg2 * v + sg3 * w;
+  pool[(S_QFLUX + 1) * fs + x] = hcc * g.dt[1] + sg2 * u + sg4 * v + sg5 * w;
+  pool[(S_QFLUX + 2) * fs + x] = hcc * g.dt[2] + sg3 * u + sg5 * v + sg6 * w;
+}
+
+// ---------------------------------------------------------------------------------
+// combined flux G_d = Fv_d - Fc_d on a box.
+//   Fc: convrsdcal6 (src/solver.F90:2200-2224), Fv: diffrsdcal6 (src/solver.F90:2623-2680)
+// the derivative is linear, so  -d(Fc)/dxi + d(Fv)/dxi = d(G)/dxi : 5 line solves per
+// direction instead of 9.
+// ---------------------------------------------------------------------------------
+template <int DMASK>
+__global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, const FluxRanges fr,
+                       const int diffterm) {
+  int ijk[3];
+  if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  const double q0 = pool[(S_Q + 0) * fs + x], q1 = pool[(S_Q + 1) * fs + x], q2 = pool[(S_Q + 2) * fs + x],
+               q3 = pool[(S_Q + 3) * fs + x], q4 = pool[(S_Q + 4) * fs + x];
+  const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+  const double p = pool[S_PRS * fs + x];
+  const double jac = pool[S_JAC * fs + x];
+  double sg[6] = {0, 0, 0, 0, 0, 0}, qf[3] = {0, 0, 0};
+  if (diffterm) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) sg[n] = pool[(S_SIGMA + n) * fs + x];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) qf[n] = pool[(S_QFLUX + n) * fs + x];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (!(DMASK & (1 << d))) continue;
+    const double d1 = pool[(S_DXI + 3 * d + 0) * fs + x];
+    const double d2 = pool[(S_DXI + 3 * d + 1) * fs + x];
+    const double d3 = pool[(S_DXI + 3 * d + 2) * fs + x];
+    // convective part only on pencils inside the is:ie / js:je / ks:ke ranges of the two
+    // other directions
+    const int o1 = (d == 0) ? 1 : 0, o2 = (d == 2) ? 1 : 2;
+    const bool conv = ijk[o1] >= fr.s[o1] && ijk[o1] <= fr.e[o1] && ijk[o2] >= fr.s[o2] && ijk[o2] <= fr.e[o2];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0, g4 = 0.0;
+    if (diffterm) {
+      g1 = (sg[0] * d1 + sg[1] * d2 + sg[2] * d3) * jac;
+      g2 = (sg[1] * d1 + sg[3] * d2 + sg[4] * d3) * jac;
+      g3 = (sg[2] * d1 + sg[4] * d2 + sg[5] * d3) * jac;
+      g4 = (qf[0] * d1 + qf[1] * d2 + qf[2] * d3) * jac;
+    }
+    if (conv) {
+      const double uu = d1 * u + d2 * v + d3 * w;
+      g0 = g0 - jac * q0 * uu;
+      g1 = g1 - jac * (q1 * uu + d1 * p);
+      g2 = g2 - jac * (q2 * uu + d2 * p);
+      g3 = g3 - jac * (q3 * uu + d3 * p);
+      g4 = g4 - jac * (q4 + p) * uu;
+    }
+    pool[(S_G + 5 * d + 0) * fs + x] = g0;
+    pool[(S_G + 5 * d + 1) * fs + x] = g1;
+    pool[(S_G + 5 * d + 2) * fs + x] = g2;
+    pool[(S_G + 5 * d + 3) * fs + x] = g3;
+    pool[(S_G + 5 * d + 4) * fs + x] = g4;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// RK3-TVD update (src/mainloop.F90:427-476) fused with updatefvar (src/fludyna.F90:191)
+// ---------------------------------------------------------------------------------
+__global__ void k_rk_update(const Layout L, double* __restrict__ pool, const Thermo th, const RkCoef rk) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double jac = pool[S_JAC * fs + x];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const double q = pool[(S_Q + m) * fs + x];
+    double qs;
+    if (rk.first) {
+      qs = q * jac;                               // mainloop.F90:429-433
+      pool[(S_QSAVE + m) * fs + x] = qs;
+    } else {
+      qs = pool[(S_QSAVE + m) * fs + x];
+    }
+    const double vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * pool[(S_QRHS + m) * fs + x] * rk.dt;
+    pool[(S_Q + m) * fs + x] = vv / jac;
+  }
+  if (rk.with_fvar) q2fvar_node(pool, fs, x, th);
+}
+
+// src_chan body force (src/solver.F90:341-352): qrhs(2:4)+=force*jacob,
+// qrhs(5)+=(force.ubulk)*jacob on all nodes 0..im,0..jm,0..km ; fe = force.ubulk
+__global__ void k_add_force(const Layout L, double* __restrict__ pool, const double f0, const double f1,
+                            const double f2, const double fe) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double jac = pool[S_JAC * fs + x];
+  pool[(S_QRHS + 1) * fs + x] = pool[(S_QRHS + 1) * fs + x] + f0 * jac;
+  pool[(S_QRHS + 2) * fs + x] = pool[(S_QRHS + 2) * fs + x] + f1 * jac;
+  pool[(S_QRHS + 3) * fs + x] = pool[(S_QRHS + 3) * fs + x] + f2 * jac;
+  pool[(S_QRHS + 4) * fs + x] = pool[(S_QRHS + 4) * fs + x] + fe * jac;
+}
+
+// ---------------------------------------------------------------------------------
+// kenergycal / enstophycal partial sums (src/statistic.F90:871-990): nodes 1..im,1..jm,1..km
+// one CTA per (j,k) row, fixed-order tree => deterministic
+// ---------------------------------------------------------------------------------
+__global__ void k_stats_rows(const Layout L, const double* __restrict__ pool, double* __restrict__ partial) {
+  const int j = 1 + blockIdx.x, k = 1 + blockIdx.y;
+  const long long fs = L.fstride;
+  double ke = 0.0, en = 0.0;
+  for (int i = 1 + threadIdx.x; i <= L.im; i += PW_T) {
+    const long long x = L.idx(i, j, k);
+    Grad g;
+    load_grad(pool, fs, x, g);
+    const double r = pool[S_RHO * fs + x];
+    const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+    ke += r * (u * u + v * v + w * w);
+    const double o1 = g.dv[2][1] - g.dv[1][2], o2 = g.dv[0][2] - g.dv[2][0], o3 = g.dv[1][0] - g.dv[0][1];
+    en += r * (o1 * o1 + o2 * o2 + o3 * o3);
+  }
+  __shared__ double s0[PW_T], s1[PW_T];
+  s0[threadIdx.x] = ke; s1[threadIdx.x] = en;
+  __syncthreads();
+  for (int h = PW_T / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) { s0[threadIdx.x] += s0[threadIdx.x + h]; s1[threadIdx.x] += s1[threadIdx.x + h]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const long long row = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    partial[2 * row] = s0[0];
+    partial[2 * row + 1] = s1[0];
+  }
+}
+__global__ void k_stats_final(const double* __restrict__ partial, const long long nrows, double* __restrict__ out2) {
+  __shared__ double s0[256], s1[256];
+  double a = 0.0, b = 0.0;
+  for (long long r = threadIdx.x; r < nrows; r += 256) { a += partial[2 * r]; b += partial[2 * r + 1]; }
+  s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) { s0[threadIdx.x] += s0[threadIdx.x + h]; s1[threadIdx.x] += s1[threadIdx.x + h]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = s0[0]; out2[1] = s1[0]; }
+}
+
+// ---------------------------------------------------------------------------------
+// face pack / unpack (multi-block exchange).  Buffer order: [field][p2][l][p1], p1 fastest.
+// side 0 packs planes l (sent to the low neighbour), side 1 packs planes dm-l.
+// unpack side 1 (from the high neighbour's side-0 buffer) -> dm+l, l==0 averages node dm;
+// unpack side 0 (from the low neighbour's side-1 buffer)  -> -l,   l==0 averages node 0.
+// (src/parallel.F90:4180-4218 dataswap, :4941-4990 qswap)
+// ---------------------------------------------------------------------------------
+template <int DIR, bool PACK>
+__global__ void k_face(const Layout L, const FieldList fl, const int side, const int l0, const int l1,
+                       double* __restrict__ buf) {
+  const int n1 = (DIR == 0) ? L.jm + 1 : L.im + 1;
+  const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
+  const int np = l1 - l0 + 1;
+  const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p1 >= n1) return;
+  const int p2 = blockIdx.y / np, l = l0 + blockIdx.y % np;
+  double* f = fl.f[blockIdx.z];
+  const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
+  const long long bi = (((long long)blockIdx.z * n2 + p2) * np + (l - l0)) * n1 + p1;
+  int node;
+  if (PACK) node = side ? dm - l : l;
+  else node = side ? dm + l : -l;
+  long long x;
+  if (DIR == 0) x = L.idx(node, p1, p2);
+  else if (DIR == 1) x = L.idx(p1, node, p2);
+  else x = L.idx(p1, p2, node);
+  if (PACK) buf[bi] = f[x];
+  else if (l == 0) f[x] = 0.5 * (f[x] + buf[bi]);
+  else f[x] = buf[bi];
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK()                        \
+  do {                                        \
+    astr_count_launch();                      \
+    CUDA_OK(cudaGetLastError());              \
+  } while (0)
+
+int pw_halo_wrap(const Layout& L, const FieldList& fl, int dir, int mode, cudaStream_t st) {
+  const int na = (dir == 0) ? L.jm + 1 : L.im + 1;
+  const int nb = (dir == 2) ? L.jm + 1 : L.km + 1;
+  dim3 grid((na + PW_T - 1) / PW_T, nb, fl.nf);
+  if (dir == 0) k_halo_wrap<0><<<grid, PW_T, 0, st>>>(L, fl, mode);
+  else if (dir == 1) k_halo_wrap<1><<<grid, PW_T, 0, st>>>(L, fl, mode);
+  else k_halo_wrap<2><<<grid, PW_T, 0, st>>>(L, fl, mode);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_q2fvar(const Layout& L, double* pool, const Thermo& th, const Box& b, cudaStream_t st) {
+  if (box_empty(b)) return 0;
+  k_q2fvar<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, b);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_visc<<<box_grid(b), PW_T, 0, st>>>(L, pool, th);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_materialise_grad(const Layout& L, double* pool, double* out, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_materialise_grad<<<box_grid(b), PW_T, 0, st>>>(L, pool, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
+            cudaStream_t st) {
+  if (box_empty(b)) return 0;
+  dim3 grid = box_grid(b);
+  switch (dmask) {
+    case 1: k_flux<1><<<grid, PW_T, 0, st>>>(L, pool, b, fr, diffterm); break;
+    case 2: k_flux<2><<<grid, PW_T, 0, st>>>(L, pool, b, fr, diffterm); break;
+    case 4: k_flux<4><<<grid, PW_T, 0, st>>>(L, pool, b, fr, diffterm); break;
+    case 3: k_flux<3><<<grid, PW_T, 0, st>>>(L, pool, b, fr, diffterm); break;
+    case 7: k_flux<7><<<grid, PW_T, 0, st>>>(L, pool, b, fr, diffterm); break;
+    default: return astr_fail_msg("pw_flux: unsupported direction mask");
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double*,
+                 cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_rk_update<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, rk);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_add_force(const Layout& L, double* pool, const double force[3], double fe, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_add_force<<<box_grid(b), PW_T, 0, st>>>(L, pool, force[0], force[1], force[2], fe);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_stats(const Layout& L, double* pool, double* partial, double* out2, cudaStream_t st) {
+  dim3 grid(L.jm, L.km);
+  k_stats_rows<<<grid, PW_T, 0, st>>>(L, pool, partial);
+  LAUNCH_CHECK();
+  k_stats_final<<<1, 256, 0, st>>>(partial, (long long)L.jm * L.km, out2);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool PACK>
+static int face_launch(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,
+                       cudaStream_t st) {
+  const int n1 = (dir == 0) ? L.jm + 1 : L.im + 1;
+  const int n2 = (dir == 2) ? L.jm + 1 : L.km + 1;
+  const int np = l1 - l0 + 1;
+  dim3 grid((n1 + PW_T - 1) / PW_T, n2 * np, fl.nf);
+  if (dir == 0) k_face<0, PACK><<<grid, PW_T, 0, st>>>(L, fl, side, l0, l1, buf);
+  else if (dir == 1) k_face<1, PACK><<<grid, PW_T, 0, st>>>(L, fl, side, l0, l1, buf);
+  else k_face<2, PACK><<<grid, PW_T, 0, st>>>(L, fl, side, l0, l1, buf);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,
+            cudaStream_t st) {
+  return face_launch<true>(L, fl, dir, side, l0, l1, buf, st);
+}
+int pw_unpack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, const double* buf,
+              cudaStream_t st) {
+  return face_launch<false>(L, fl, dir, side, l0, l1, const_cast<double*>(buf), st);
+}

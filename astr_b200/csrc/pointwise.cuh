@@ -1,0 +1,54 @@
+// astr_b200/csrc/pointwise.cuh -- declarations of the pointwise / surface kernels.
+#pragma once
+#include "common.cuh"
+
+// Internal pool slots (all share the Layout of common.cuh).
+enum Slot {
+  S_Q = 0,        // 5  conserved variables            src/commarray.F90:63
+  S_RHO = 5,      // 1
+  S_VEL = 6,      // 3
+  S_PRS = 9,      // 1
+  S_TMP = 10,     // 1
+  S_QRHS = 11,    // 5
+  S_JAC = 16,     // 1  jacob
+  S_DXI = 17,     // 9  dxi(a,b): slot 17+3a+b, a = xi index, b = x index
+  S_RAW = 26,     // 12 raw xi-derivatives: slot 26+4d+n, n=0..2 velocity, 3 temperature
+  S_SIGMA = 38,   // 6
+  S_QFLUX = 44,   // 3
+  S_G = 47,       // 15 combined flux G_d,n = Fv - Fc : slot 47+5d+n
+  S_QSAVE = 62,   // 5
+  S_CORE = 67,    // number of always-resident slots
+  S_SCR = 67,     // 15 lazily allocated scratch (dvel 9, dtmp 3, vor 3 | gridgeom temporaries)
+  S_TOTAL = 82
+};
+
+struct Thermo {
+  double reynolds, prandtl, const1, const2, const5, const6, tempconst, tempconst1;
+};
+
+struct Box { int lo[3], hi[3]; };   // inclusive node ranges
+
+enum { XMODE_SWAP = 0, XMODE_QSWAP = 1, XMODE_SYNC = 2 };
+
+struct FieldList { double* f[ASTR_MAXF]; int nf; };
+
+int pw_halo_wrap(const Layout& L, const FieldList& fl, int dir, int mode, cudaStream_t st);
+int pw_q2fvar(const Layout& L, double* pool, const Thermo& th, const Box& b, cudaStream_t st);
+int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st);
+int pw_materialise_grad(const Layout& L, double* pool, double* dvel9_dtmp3_vor3, cudaStream_t st);
+// dmask bit d => build G_d ; cmask[d][2]: conv part only where the other two indices lie in
+// [s,e] ranges (src/solver.F90:2197-2198) ; diffterm adds the viscous part.
+struct FluxRanges { int s[3], e[3]; };
+int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
+            cudaStream_t st);
+struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; };
+int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* force,
+                 cudaStream_t st);
+int pw_add_force(const Layout& L, double* pool, const double force[3], double fe, cudaStream_t st);
+int pw_stats(const Layout& L, double* pool, double* partial /*2*(jm)*(km)*/, double* out2, cudaStream_t st);
+// face pack / unpack for the multi-block exchange (src/parallel.F90:4180-4218)
+int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,
+            cudaStream_t st);
+int pw_unpack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, const double* buf,
+              cudaStream_t st);
+// Fortran (im+11)(jm+11)(km+11) box <-> padded device box is done with cudaMemcpy3D in api.cu

@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's stage-operator interface over the C ABI.
+
+Method names, argument meaning and call order are those of the reference's time loop
+(src/mainloop.F90:301-482 ``time_integration_rk``): ``filterq`` (src/comsolver.F90:514),
+``qswap`` (src/parallel.F90:4848), ``gradcal`` (src/comsolver.F90:244), ``rhscal``
+(src/solver.F90:185), the RK update (src/mainloop.F90:427-476) and ``updatefvar``
+(src/fludyna.F90:191).  Every method is a thin call into libastr_gpu.so; nothing is
+computed in Python and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import lib as _l
+from .parallel import Block
+
+HM = _l.HM
+
+
+def refcal(reynolds: float, mach: float, ref_tem: float = 273.15, gamma: float = 1.4, prandtl: float = 0.72,
+           sutherland_s: float = 110.3) -> Dict[str, float]:
+    """Reference constants of src/solver.F90:104-126 (nondimen branch)."""
+    m2 = mach * mach
+    tempconst = sutherland_s / ref_tem
+    return dict(
+        reynolds=reynolds, mach=mach, prandtl=prandtl, gamma=gamma, ref_tem=ref_tem,
+        const1=1.0 / (gamma * (gamma - 1.0) * m2),
+        const2=gamma * m2,
+        const3=(gamma - 1.0) / 3.0 * prandtl * m2,
+        const4=(gamma - 1.0) * m2 * reynolds * prandtl,
+        const5=(gamma - 1.0) * m2,
+        const6=1.0 / (gamma - 1.0),
+        const7=(gamma - 1.0) * m2 * reynolds * prandtl,
+        tempconst=tempconst, tempconst1=1.0 + tempconst,
+    )
+
+
+class RhsEngine:
+    """One block (= one MPI rank of the reference = one GPU) of the RHS / RK-stage engine."""
+
+    def __init__(self, block: Block, global_dims: Sequence[int], homo: Sequence[bool], thermo: Dict[str, float],
+                 deltat: float = 1e-3, alfa_filter: float = 0.49, lfilter: bool = True, diffterm: bool = True,
+                 device: int = -1, flowtype: int = 0):
+        self.block = block
+        self.global_dims = tuple(global_dims)
+        self.deltat = deltat
+        self.thermo = thermo
+        self._lib = _l.load()
+        c = _l.AstrCfg()
+        c.abi_version = 1
+        c.device = device
+        c.im, c.jm, c.km = block.dims
+        c.ia, c.ja, c.ka = global_dims
+        c.hm, c.numq, c.ndims = HM, 5, 3
+        c.npdc[:] = block.npdc
+        c.is_, c.js, c.ks = block.s
+        c.ie, c.je, c.ke = block.e
+        c.lhomo[:] = [int(h) for h in homo]
+        c.rank[:] = block.rk
+        c.size[:] = block.size
+        c.nbr[:] = block.nbr
+        c.my_rank = block.rank
+        c.conschm, c.difschm, c.scheme_compact, c.rkscheme = 643, 643, 1, 3
+        c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), 1, flowtype
+        c.alfa_filter = alfa_filter
+        for k, v in thermo.items():
+            setattr(c, k, v)
+        c.deltat = deltat
+        self.cfg = c
+        _l.check(self._lib.astr_gpu_init(ctypes.byref(c)))
+        self._open = True
+
+    # ---- shapes -------------------------------------------------------------------------
+    @property
+    def shape(self):
+        im, jm, km = self.block.dims
+        return (im + 1 + 2 * HM, jm + 1 + 2 * HM, km + 1 + 2 * HM)
+
+    def empty(self, ncomp: Optional[int] = None) -> np.ndarray:
+        shp = self.shape + ((ncomp,) if ncomp else ())
+        return np.zeros(shp, order="F")
+
+    @staticmethod
+    def _ptr(a: Optional[np.ndarray]):
+        if a is None:
+            return None
+        assert a.flags.f_contiguous and a.dtype == np.float64
+        return a.ctypes.data
+
+    # ---- communicator (replaces mpiinitial, src/parallel.F90:152) ---------------------------
+    def comm_init(self, nranks: int, rank: int, bcast):
+        """bcast(bytes_or_None) -> bytes broadcasts rank 0's 128-byte NCCL id (MPI_Bcast /
+        torch.distributed on the host side)."""
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _l.check(self._lib.astr_gpu_comm_unique_id(buf))
+        uid = bcast(bytes(buf.raw) if rank == 0 else None)
+        buf2 = ctypes.create_string_buffer(uid, 128)
+        _l.check(self._lib.astr_gpu_comm_init(buf2, nranks, rank))
+
+    # ---- setup ----------------------------------------------------------------------------
+    def set_metrics(self, dxi: np.ndarray, jacob: np.ndarray):
+        """dxi(-hm:im+hm,-hm:jm+hm,-hm:km+hm,3,3), jacob(...) as left by geomcal (src/geom.F90:43)."""
+        assert dxi.shape == self.shape + (3, 3) and jacob.shape == self.shape
+        _l.check(self._lib.astr_gpu_set_metrics(self._ptr(np.asfortranarray(dxi)), self._ptr(np.asfortranarray(jacob))))
+
+    def gridgeom(self, x: np.ndarray):
+        """Device-side gridgeom (src/geom.F90:99) from x(-hm:im+hm,...,3)."""
+        assert x.shape == self.shape + (3,)
+        _l.check(self._lib.astr_gpu_gridgeom(self._ptr(np.asfortranarray(x))))
+
+    def upload_state(self, q=None, rho=None, vel=None, prs=None, tmp=None):
+        _l.check(self._lib.astr_gpu_upload_state(*[self._ptr(a) for a in (q, rho, vel, prs, tmp)]))
+
+    def download_state(self, q=None, rho=None, vel=None, prs=None, tmp=None):
+        _l.check(self._lib.astr_gpu_download_state(*[self._ptr(a) for a in (q, rho, vel, prs, tmp)]))
+
+    def get(self, name: str) -> np.ndarray:
+        out = self.empty()
+        _l.check(self._lib.astr_gpu_get_field(_l.FIELD_IDS[name], out.ctypes.data))
+        return out
+
+    def set(self, name: str, arr: np.ndarray):
+        a = np.asfortranarray(arr, dtype=np.float64)
+        assert a.shape == self.shape
+        _l.check(self._lib.astr_gpu_set_field(_l.FIELD_IDS[name], a.ctypes.data))
+
+    # ---- stage operators --------------------------------------------------------------------
+    def filterq(self):
+        _l.check(self._lib.astr_gpu_filterq())
+
+    def qswap(self):
+        _l.check(self._lib.astr_gpu_qswap())
+
+    def gradcal(self):
+        _l.check(self._lib.astr_gpu_gradcal())
+
+    def rhscal(self):
+        _l.check(self._lib.astr_gpu_rhscal())
+
+    def rk_update(self, rkstep: int, deltat: Optional[float] = None):
+        _l.check(self._lib.astr_gpu_rk_update(rkstep, self.deltat if deltat is None else deltat))
+
+    def updatefvar(self):
+        _l.check(self._lib.astr_gpu_updatefvar())
+
+    def rk_stage(self, rkstep: int, deltat: Optional[float] = None):
+        _l.check(self._lib.astr_gpu_rk_stage(rkstep, self.deltat if deltat is None else deltat))
+
+    def steploop(self, nsteps: int, deltat: Optional[float] = None):
+        """nsteps x RK3 (src/mainloop.F90:103-205 without I/O hooks)."""
+        _l.check(self._lib.astr_gpu_rk_steps(nsteps, self.deltat if deltat is None else deltat))
+
+    def dataswap(self, name: str, direction: int = 0):
+        _l.check(self._lib.astr_gpu_dataswap(_l.FIELD_IDS[name], direction))
+
+    def synchronize(self):
+        _l.check(self._lib.astr_gpu_synchronize())
+
+    # ---- statistics (src/statistic.F90:871-990) -----------------------------------------------
+    def reduce_tgv(self):
+        out = (ctypes.c_double * 3)()
+        _l.check(self._lib.astr_gpu_reduce_tgv(out))
+        return out[0], out[1]
+
+    def tgv_stats(self, psum=lambda v: v, xmax: float = 2.0 * np.pi):
+        """(kenergy, enstrophy) normalised as kenergycal / enstophycal; psum sums over ranks."""
+        ke, en = self.reduce_tgv()
+        ke, en = psum(ke), psum(en)
+        ia, ja, ka = self.global_dims
+        cnt = float(ia * ja * ka)
+        l_0 = xmax / (2.0 * np.pi)
+        return 0.5 * ke / cnt, 0.5 * en / cnt / ((1.0 / l_0) ** 2)
+
+    # ---- introspection ----------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        n = ctypes.c_longlong(0)
+        self._lib.astr_gpu_kernel_launches(ctypes.byref(n))
+        return n.value
+
+    def set_profile(self, on: bool = True):
+        _l.check(self._lib.astr_gpu_set_profile(int(on)))
+
+    def get_profile(self):
+        n = len(_l.PROFILE_CATEGORIES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_longlong * n)()
+        self._lib.astr_gpu_get_profile(ms, cnt, n)
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_l.PROFILE_CATEGORIES)}
+
+    def bench_sweep(self, op: int, direction: int, nfields: int = 5, iters: int = 10) -> float:
+        ms = ctypes.c_float(0)
+        _l.check(self._lib.astr_gpu_bench_sweep(op, direction, nfields, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_open", False):
+            self._lib.astr_gpu_finalize()
+            self._open = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,150 @@
+/* =====================================================================================
+ * astr_gpu.h -- C ABI of libastr_gpu.so: the B200 (sm_100a) right-hand-side / Runge-Kutta
+ * stage engine that sits behind ASTR's Fortran driver.
+ *
+ * Every entry point replaces one stage-operator call of the reference's time loop
+ * (src/mainloop.F90:396-482, `time_integration_rk`).  The Fortran side binds them with
+ * ISO_C_BINDING (`fortran/astr_gpu_mod.F90`); the Python mirror in
+ * astr_b200/ binds them with ctypes.  All functions return 0 on success and a non-zero
+ * status otherwise; `astr_gpu_last_error()` returns the message.  The reference's own
+ * error style is print+stop (src/parallel.F90:1278 `mpistop`): the shim calls mpistop
+ * with that message.
+ *
+ * Array layout at the boundary is exactly the reference's Fortran layout
+ * (src/commarray.F90:63-106): column major, i fastest, halo'd arrays
+ * (-hm:im+hm,-hm:jm+hm,-hm:km+hm[,n]) with hm=5, the variable index slowest.
+ * The library owns device mirrors and all scratch; host pointers are only read in
+ * upload / set_* calls and only written in download / get_* / reduce_* calls, and are
+ * never retained.
+ *
+ * Threading model: one host process (MPI rank) per GPU and per block; all calls of one
+ * context come from one thread.  Calls are asynchronous on the library's CUDA streams;
+ * download / get / reduce / synchronize / finalize wait for completion.
+ * ===================================================================================== */
+#ifndef ASTR_GPU_H
+#define ASTR_GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASTR_GPU_HM 5          /* src/commvar.F90:184  parameter(hm=5) */
+#define ASTR_GPU_NUMQ 5        /* src/solver.F90:50    numq=5+num_species+num_modequ */
+#define ASTR_GPU_ABI_VERSION 1
+
+/* Everything `solvrinit` (src/comsolver.F90:47-146), `refcal` (src/solver.F90:28-173)
+ * and `parallelini` (src/parallel.F90:919-1248) have decided by the time the time loop
+ * starts.  Plain ints/doubles only, so that a Fortran `type, bind(C)` mirrors it. */
+typedef struct astr_cfg {
+  int abi_version;            /* ASTR_GPU_ABI_VERSION                                   */
+  int device;                 /* CUDA device ordinal; <0 = keep the current device       */
+  int im, jm, km;             /* local block: nodes 0..im etc. (src/commvar.F90)         */
+  int ia, ja, ka;             /* global grid intervals                                   */
+  int hm;                     /* must be 5                                               */
+  int numq;                   /* must be 5                                               */
+  int ndims;                  /* 3 (2-D blocks: km=0 -- not implemented yet)             */
+  int npdc[3];                /* npdci,npdcj,npdck: 1,2,3,4 (src/parallel.F90:1042-1228) */
+  int is, ie, js, je, ks, ke; /* qrhs accumulation ranges (src/parallel.F90:1079-1095)   */
+  int lhomo[3];               /* lihomo,ljhomo,lkhomo                                    */
+  int rank[3];                /* irk,jrk,krk                                             */
+  int size[3];                /* isize,jsize,ksize                                       */
+  int nbr[6];                 /* neighbour ranks i-,i+,j-,j+,k-,k+ ; -1 = MPI_PROC_NULL  */
+  int my_rank;                /* mpirank                                                 */
+  int conschm;                /* e.g. 643 (even first digit -> central convrsdcal6)      */
+  int difschm;                /* e.g. 643                                                */
+  int scheme_compact;         /* 1 = 'c' compact (only value implemented)                */
+  int rkscheme;               /* 3 = rk3 (TVD), src/mainloop.F90:350-362                 */
+  int lfilter;                /* filterq enabled                                         */
+  int diffterm;               /* viscous terms enabled                                   */
+  int nondimen;               /* must be 1                                               */
+  int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (set_force)  */
+  double alfa_filter;         /* 0.49 in every example                                   */
+  double reynolds, mach, prandtl, gamma, ref_tem;
+  double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */
+  double tempconst, tempconst1; /* Sutherland: 110.3/ref_tem (src/solver.F90:122)        */
+  double deltat;
+} astr_cfg;
+
+/* ---- field ids for astr_gpu_get_field / set_field / device_ptr ----------------------
+ * Same numbering as the test oracle: 0-4 q | 5 rho | 6-8 vel | 9 prs | 10 tmp |
+ * 11-15 qrhs | 16 jacob | 17-25 dxi(a,b) a-major (a = xi index, b = x index) |
+ * 26-34 dvel(m,n) m-major | 35-37 dtmp | 38-43 sigma | 44-46 qflux | 47-49 x |
+ * 50-54 qsave | 55-57 vor.  dvel/dtmp/vor are materialised on demand. */
+enum {
+  ASTR_F_Q = 0, ASTR_F_RHO = 5, ASTR_F_VEL = 6, ASTR_F_PRS = 9, ASTR_F_TMP = 10,
+  ASTR_F_QRHS = 11, ASTR_F_JACOB = 16, ASTR_F_DXI = 17, ASTR_F_DVEL = 26,
+  ASTR_F_DTMP = 35, ASTR_F_SIGMA = 38, ASTR_F_QFLUX = 44, ASTR_F_X = 47,
+  ASTR_F_QSAVE = 50, ASTR_F_VOR = 55, ASTR_F_COUNT = 58
+};
+
+/* replaces solvrinit: builds the line operators (fd_scheme_initiate
+ * src/derivative.F90:63-158, compact_filter_initiate src/filter.F90:31-100) and
+ * allocates the device mirrors of src/commarray.F90:56-110. */
+int astr_gpu_init(const astr_cfg* cfg);
+int astr_gpu_sizeof_cfg(void);   /* sizeof(astr_cfg): lets a binding verify its mirror */
+int astr_gpu_finalize(void);
+const char* astr_gpu_last_error(void);
+int astr_gpu_synchronize(void);
+
+/* multi-GPU: the NCCL communicator that replaces MPI_COMM_WORLD for halo traffic
+ * (src/parallel.F90:152 mpiinitial).  Rank 0 creates the id, the host side broadcasts
+ * the 128 bytes (MPI_Bcast / torch.distributed), every rank calls comm_init. */
+int astr_gpu_comm_unique_id(char id[128]);
+int astr_gpu_comm_init(const char id[128], int nranks, int rank);
+
+/* end of geomcal (src/geom.F90:43): dxi(-hm:im+hm,..,3,3), jacob(-hm:im+hm,..) */
+int astr_gpu_set_metrics(const double* dxi, const double* jacob);
+/* device-side gridgeom (src/geom.F90:99-700) from node coordinates x(-hm:im+hm,..,3)
+ * (only nodes 0..im,0..jm,0..km are read). */
+int astr_gpu_gridgeom(const double* x);
+
+/* end of flowinit / after boucon: q(..,numq), rho, vel(..,3), prs, tmp -- any pointer may
+ * be NULL (skipped). */
+int astr_gpu_upload_state(const double* q, const double* rho, const double* vel,
+                          const double* prs, const double* tmp);
+int astr_gpu_download_state(double* q, double* rho, double* vel, double* prs, double* tmp);
+/* one halo'd 3-D field in or out (tests, checkpointing, device-side BC staging) */
+int astr_gpu_get_field(int field_id, double* host);
+int astr_gpu_set_field(int field_id, const double* host);
+int astr_gpu_device_ptr(int field_id, void** dptr, long long strides[3], long long* origin);
+
+/* ---- stage operators, one per reference subroutine ---------------------------------- */
+int astr_gpu_filterq(void);      /* src/comsolver.F90:514  filterq                      */
+int astr_gpu_qswap(void);        /* src/parallel.F90:4848  qswap                        */
+int astr_gpu_gradcal(void);      /* src/comsolver.F90:244  gradcal                      */
+int astr_gpu_rhscal(void);       /* src/solver.F90:185     rhscal (zeroes qrhs first,
+                                    i.e. includes src/mainloop.F90:408 `qrhs=0`)        */
+int astr_gpu_rk_update(int rkstep, double deltat); /* src/mainloop.F90:427-476          */
+int astr_gpu_updatefvar(void);   /* src/fludyna.F90:191    updatefvar                   */
+/* all of the above in the order of src/mainloop.F90:396-482 (boucon/spongefilter are the
+ * caller's: usable when they are no-ops, e.g. fully periodic TGV) */
+int astr_gpu_rk_stage(int rkstep, double deltat);
+/* nsteps x (rk stages 1..3) with nothing in between */
+int astr_gpu_rk_steps(int nsteps, double deltat);
+
+/* generic halo exchange of one device field (dataswap, src/parallel.F90:3499-4382) */
+int astr_gpu_dataswap(int field_id, int direction /*0 = all, 1..3*/);
+
+/* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal */
+int astr_gpu_set_force(const double force[3]);
+
+/* statistics: out[0]=sum rho*|u|^2, out[1]=sum rho*|omega|^2 over nodes 1..im,1..jm,1..km
+ * of this block (src/statistic.F90:871-990 before psum and normalisation), out[2]=0.
+ * Requires gradcal of the current stage. */
+int astr_gpu_reduce_tgv(double out[3]);
+
+/* introspection for bench / tests */
+int astr_gpu_kernel_launches(long long* count);       /* launches since init            */
+/* CUDA-event profile of the stage, per category (filter i/j/k, halo, grad i/j/k, visc,
+ * flux, div i/j/k, rk, fvar): accumulated ms and span counts since set_profile(1). */
+int astr_gpu_set_profile(int on);
+int astr_gpu_get_profile(double* ms, long long* n, int cap);
+int astr_gpu_bench_sweep(int op /*0 deriv,1 filter*/, int dir /*0,1,2*/, int nfields,
+                         int iters, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTR_GPU_H */

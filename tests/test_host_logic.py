@@ -1,0 +1,139 @@
+"""CPU tests of the host side: block decomposition (vs the oracle's restatement of
+parapp/parallelini), the C-ABI library (loads, exports every declared symbol), and the
+algebra of the partitioned Thomas solve the CUDA kernel implements."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import astr_b200
+from astr_b200 import decompose, mpisizedis, refcal
+from astr_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("dims,size,homo", [
+    ((32, 32, 32), (1, 1, 1), (True, True, True)),
+    ((32, 32, 32), (2, 2, 2), (True, True, True)),
+    ((33, 31, 30), (2, 3, 1), (True, False, True)),
+    ((64, 48, 32), (4, 1, 2), (False, False, False)),
+    ((32, 32, 32), (1, 1, 2), (True, True, True)),
+])
+def test_decompose_matches_oracle(oracle, dims, size, homo):
+    blocks = decompose(dims, size, homo)
+    c = oracle.Case(*dims, blocks=size, homo=homo)
+    assert c.nblocks == len(blocks)
+    for ib, b in enumerate(blocks):
+        info = c.block_info(ib)
+        assert b.rank == ib
+        assert b.dims == (info["im"], info["jm"], info["km"])
+        assert list(b.npdc) == info["npdc"]
+        assert [b.s[0], b.e[0], b.s[1], b.e[1], b.s[2], b.e[2]] == info["is_ie"]
+        assert list(b.g0) == info["g0"]
+        assert b.nbr == info["nb"]
+    c.close()
+
+
+def test_mpisizedis():
+    assert mpisizedis(1, (512, 512, 512)) == (1, 1, 1)
+    assert mpisizedis(8, (512, 512, 512)) == (2, 2, 2)
+    assert mpisizedis(8, (512, 512, 512), strict3d=True) == (2, 2, 2)   # what the reference picks
+    assert mpisizedis(2, (512, 512, 512)) == (1, 1, 2)                  # k slabs (extension)
+    assert mpisizedis(4, (512, 512, 512)) == (1, 2, 2)
+    with pytest.raises(ValueError):
+        mpisizedis(2, (512, 512, 512), strict3d=True)                   # src/parallel.F90:289-297
+
+
+def test_refcal_matches_oracle_constants():
+    th = refcal(1600.0, 0.1)
+    assert th["const2"] == 1.4 * (0.1 * 0.1)
+    assert th["const6"] == 1.0 / (1.4 - 1.0)
+    assert th["tempconst"] == 110.3 / 273.15
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    so = astr_b200.build()
+    assert os.path.exists(so)
+    lib = ctypes.CDLL(so)
+    header = open(os.path.join(ROOT, "include", "astr_gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(astr_gpu_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/astr_gpu.h but not exported"
+    assert sorted(L.SYMBOLS) == declared
+    # the ctypes mirror of struct astr_cfg has the C struct's size (44 ints + 16 doubles)
+    assert lib.astr_gpu_sizeof_cfg() == ctypes.sizeof(L.AstrCfg) == 4 * 44 + 8 * 16
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    b = decompose((16, 16, 16), (1, 1, 1), (True, True, True))[0]
+    with pytest.raises(astr_b200.AstrGpuError):
+        astr_b200.RhsEngine(b, (16, 16, 16), (True, True, True), refcal(1600.0, 0.1))
+
+
+# ---- the algebra of the partitioned solve (astr_b200/csrc/sweep.cu) ------------------------------
+def _partitioned_thomas(ac1, ac2, ac3, d, C):
+    """Chunked forward/backward with zero carries + exact carry recovery, as the kernel does."""
+    N = d.size
+    cs = [(c * N) // C for c in range(C + 1)]
+    ac2 = ac2.copy(); ac3 = ac3.copy(); ac2[0] = 1.0; ac3[0] = 0.0
+    pf = np.zeros(N); qb = np.zeros(N)
+    for c in range(C):
+        p = 1.0
+        for r in range(cs[c], cs[c + 1]):
+            p *= -ac3[r]; pf[r] = p
+        q = 1.0
+        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
+            q *= -ac1[r]; qb[r] = q
+    e = np.zeros(N); ee = np.zeros(C)
+    for c in range(C):
+        prev = 0.0
+        for r in range(cs[c], cs[c + 1]):
+            prev = d[r] * ac2[r] - prev * ac3[r]; e[r] = prev
+        ee[c] = prev
+    cin = np.zeros(C)
+    for c in range(1, C):
+        cin[c] = ee[c - 1] + pf[cs[c] - 1] * cin[c - 1]
+    g = np.zeros(N); gs = np.zeros(C)
+    for c in range(C):
+        nxt = 0.0
+        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
+            nxt = (e[r] + pf[r] * cin[c]) - ac1[r] * nxt; g[r] = nxt
+        gs[c] = nxt
+    xin = np.zeros(C)
+    for c in range(C - 2, -1, -1):
+        xin[c] = gs[c + 1] + qb[cs[c + 1]] * xin[c + 1]
+    x = np.array([g[r] + qb[r] * xin[np.searchsorted(cs, r, side="right") - 1] for r in range(N)])
+    return x
+
+
+@pytest.mark.parametrize("is_filter", [False, True])
+@pytest.mark.parametrize("ntype", [1, 2, 3, 4])
+@pytest.mark.parametrize("C", [1, 2, 4, 8])
+def test_partitioned_thomas_is_exact(oracle, is_filter, ntype, C):
+    n = 128
+    first, a, c, ac1, ac2, ac3 = oracle.scheme_tables(is_filter, ntype, n)
+    N = a.size
+    rng = np.random.default_rng(C + 10 * ntype)
+    d = rng.standard_normal(N)
+    # sequential Thomas (src/commfunc.F90:790-813)
+    dd = d.copy()
+    for i in range(1, N):
+        dd[i] = dd[i] * ac2[i] - dd[i - 1] * ac3[i]
+    x = np.zeros(N); x[-1] = dd[-1]
+    for i in range(N - 2, -1, -1):
+        x[i] = dd[i] - ac1[i] * x[i + 1]
+    xp = _partitioned_thomas(ac1, ac2, ac3, d, C)
+    scale = np.abs(x).max()
+    assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * scale
+    # residual of the original system
+    res = x.copy()
+    res[1:] += a[1:] * x[:-1]
+    res[:-1] += c[:-1] * x[1:]
+    assert np.abs(res - d).max() < 1e-12 * max(1.0, scale)
