@@ -736,6 +736,20 @@ int astr_gpu_rk_steps(int nsteps, double deltat) {
   return 0;
 }
 
+int astr_gpu_rk_steps_timed(int nsteps, double deltat, float* ms) {
+  NEED_CTX();
+  cudaEvent_t a, b;
+  CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+  CUDA_OK(cudaEventRecord(a, g->st));
+  int rc = astr_gpu_rk_steps(nsteps, deltat);
+  CUDA_OK(cudaEventRecord(b, g->st));
+  CUDA_OK(cudaEventSynchronize(b));
+  CUDA_OK(cudaEventElapsedTime(ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  prof_collect();
+  return rc;
+}
+
 int astr_gpu_dataswap(int field_id, int direction) {
   NEED_CTX();
   int s;

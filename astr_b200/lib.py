@@ -31,7 +31,7 @@ SYMBOLS = [
     "astr_gpu_comm_unique_id", "astr_gpu_comm_init", "astr_gpu_set_metrics", "astr_gpu_gridgeom",
     "astr_gpu_upload_state", "astr_gpu_download_state", "astr_gpu_get_field", "astr_gpu_set_field",
     "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
-    "astr_gpu_rk_update", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps",
+    "astr_gpu_rk_update", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps", "astr_gpu_rk_steps_timed",
     "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_reduce_tgv", "astr_gpu_kernel_launches",
     "astr_gpu_set_profile", "astr_gpu_get_profile", "astr_gpu_bench_sweep",
 ]
@@ -114,6 +114,7 @@ def load() -> ctypes.CDLL:
     L.astr_gpu_rk_update.argtypes = [ci, cd]
     L.astr_gpu_rk_stage.argtypes = [ci, cd]
     L.astr_gpu_rk_steps.argtypes = [ci, cd]
+    L.astr_gpu_rk_steps_timed.argtypes = [ci, cd, ctypes.POINTER(ctypes.c_float)]
     L.astr_gpu_dataswap.argtypes = [ci, ci]
     L.astr_gpu_set_force.argtypes = [vp]
     L.astr_gpu_reduce_tgv.argtypes = [vp]

@@ -154,6 +154,13 @@ class RhsEngine:
         """nsteps x RK3 (src/mainloop.F90:103-205 without I/O hooks)."""
         _l.check(self._lib.astr_gpu_rk_steps(nsteps, self.deltat if deltat is None else deltat))
 
+    def steploop_timed(self, nsteps: int, deltat: Optional[float] = None) -> float:
+        """steploop bracketed by CUDA events on the library stream; returns milliseconds."""
+        ms = ctypes.c_float(0)
+        _l.check(self._lib.astr_gpu_rk_steps_timed(nsteps, self.deltat if deltat is None else deltat,
+                                                   ctypes.byref(ms)))
+        return ms.value
+
     def dataswap(self, name: str, direction: int = 0):
         _l.check(self._lib.astr_gpu_dataswap(_l.FIELD_IDS[name], direction))
 

@@ -123,6 +123,8 @@ int astr_gpu_updatefvar(void);   /* src/fludyna.F90:191    updatefvar           
 int astr_gpu_rk_stage(int rkstep, double deltat);
 /* nsteps x (rk stages 1..3) with nothing in between */
 int astr_gpu_rk_steps(int nsteps, double deltat);
+/* same, bracketed by CUDA events on the library stream; returns the device time in ms */
+int astr_gpu_rk_steps_timed(int nsteps, double deltat, float* ms);
 
 /* generic halo exchange of one device field (dataswap, src/parallel.F90:3499-4382) */
 int astr_gpu_dataswap(int field_id, int direction /*0 = all, 1..3*/);
