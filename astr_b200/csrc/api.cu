@@ -119,7 +119,7 @@ static void factorise(HostOp& h) {
   h.C = astr_sweep_max_chunks(N);
   h.pf.assign(N, 0.0); h.qb.assign(N, 0.0);
   for (int c = 0; c < h.C; ++c) {
-    const int ra = (c * N) / h.C, rb = ((c + 1) * N) / h.C - 1;
+    const int ra = chunk_start(c, N, h.C), rb = chunk_start(c + 1, N, h.C) - 1;
     double p = 1.0;
     for (int r = ra; r <= rb; ++r) { p = p * (-h.ac3[r]); h.pf[r] = p; }
     double q = 1.0;

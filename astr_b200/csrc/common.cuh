@@ -42,6 +42,16 @@ struct LineOp {
   int nsf, nsl;             // closure rows at the first / last end
 };
 
+// Row range of chunk c of the partitioned solve: [chunk_start(c), chunk_start(c+1)).  Odd chunks
+// start on an odd row and even chunks on an even row, so the two chunks that share a half-warp
+// in the i-direction mapping always sit an odd number of elements apart (bank-conflict free).
+__host__ __device__ inline int chunk_start(int c, int nrows, int C) {
+  if (c <= 0) return 0;
+  if (c >= C) return nrows;
+  const int s = (c * nrows) / C;
+  return (c & 1) ? (s | 1) : (s & ~1);
+}
+
 // coefficient tables of src/filter.F90:299-432 (only the rows the hot path reads)
 struct FilterCoef {
   double coef6i[4], coef8i[5], coef10i[6];
@@ -75,6 +85,6 @@ void astr_count_launch(int n = 1);
 
 // sweep.cu
 int astr_set_filter_coef(const FilterCoef& fc);
-size_t astr_sweep_smem_bytes(int dir, int n, int C, int* sp_out);
+size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out);
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
 int astr_sweep_max_chunks(int nrows);

@@ -19,8 +19,9 @@
 // recovered from the C chunk-end values with the pre-computed propagation products
 // pf/qb (exact algebra, no truncation), and the last correction x = g + qb*xin is folded
 // into the coalesced write-out loop, which also applies the epilogue (store / add).
-// The sequential dependence is therefore n/C long instead of n, and 3 CTAs per SM
-// overlap load, solve and store phases.
+// The sequential dependence is therefore n/C long instead of n.  The kernel is persistent
+// (one CTA per SM) with up to 3 independent 128-thread groups, each cycling through
+// load -> solve -> store on its own bundle buffer, so the phases overlap inside the SM.
 #include "common.cuh"
 #include <cstdio>
 
@@ -160,22 +161,60 @@ __device__ __forceinline__ void closure_last(FN F, int ntype, int n, double (&sl
   }
 }
 
-template <int DIR, int OP, int C>
-__global__ void __launch_bounds__(ASTR_BW* C) sweep_kernel(const SweepArgs a) {
-  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
-  constexpr int T = ASTR_BW * C;
-  extern __shared__ __align__(16) double sm[];
+template <int NG>
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  if (NG == 1) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-  const int tid = threadIdx.x;
+// Persistent kernel: one CTA per SM slot, NG independent groups of 16*C threads.  Every group
+// owns one bundle buffer and walks the bundle list with stride gridDim.x*NG, so that while one
+// group runs its recurrences another waits for its cp.async stage and a third streams its
+// results out: the load / solve / store phases of different bundles overlap inside the SM.
+// The operator tables (ac1, ac2, ac3, pf, qb) are staged in shared memory once per CTA.
+template <int DIR, int OP, int C, int NG>
+__global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArgs a) {
+  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
+  constexpr int T = ASTR_BW * C;  // threads per group
+  extern __shared__ __align__(16) double sm_all[];
+
   const int n = a.op.n;
   const int nrows = a.op.nrows;
   const int first_node = a.op.first_node;
   const int sp = a.sp;
   const int ntile = (DIR == 0) ? ASTR_BW * sp : (n + 11) * ASTR_BW;
+  const int nr8 = (nrows + 1) & ~1;
+  // shared memory: 5 tables | chunk-of-row bytes | NG x (tile, EE, GS, XIN)
+  const double* __restrict__ ac1 = sm_all;
+  const double* __restrict__ ac2 = sm_all + nr8;
+  const double* __restrict__ ac3 = sm_all + 2 * nr8;
+  const double* __restrict__ pf = sm_all + 3 * nr8;
+  const double* __restrict__ qb = sm_all + 4 * nr8;
+  unsigned char* ch = reinterpret_cast<unsigned char*>(sm_all + 5 * nr8);
+  const int chd = ((nrows + 15) & ~15) / 8;  // doubles occupied by ch
+  const int grp = threadIdx.x / T;
+  const int tid = threadIdx.x - grp * T;
+  double* sm = sm_all + 5 * nr8 + chd + (size_t)grp * (ntile + 2 * C * ASTR_BW);
   double* EE = sm + ntile;
   double* GS = EE + C * ASTR_BW;
-  double* XIN = GS + C * ASTR_BW;
-  unsigned char* ch = reinterpret_cast<unsigned char*>(XIN + C * ASTR_BW);
+  double* XIN = EE;  // EE is dead once every thread has passed the barrier after phase 2
+
+  {
+    double* tab = sm_all;
+    for (int r = threadIdx.x; r < nrows; r += T * NG) {
+      tab[r] = a.op.ac1[r];
+      tab[nr8 + r] = a.op.ac2[r];
+      tab[2 * nr8 + r] = a.op.ac3[r];
+      tab[3 * nr8 + r] = a.op.pf[r];
+      tab[4 * nr8 + r] = a.op.qb[r];
+      {
+        int cc = 0;
+        while (cc + 1 < C && r >= chunk_start(cc + 1, nrows, C)) ++cc;
+        ch[r] = (unsigned char)cc;
+      }
+    }
+  }
+  __syncthreads();
 
   // ---- thread -> (pencil, chunk) ----------------------------------------------------
   int p, c;
@@ -192,219 +231,256 @@ __global__ void __launch_bounds__(ASTR_BW* C) sweep_kernel(const SweepArgs a) {
   double* tile = sm + ((DIR == 0) ? (p * sp + 1) : p);  // tile[(node+5)*SL] = f(node)
   auto F = [&](int node) -> double { return tile[(node + 5) * SL]; };
 
-  // ---- where this bundle lives in global memory -------------------------------------
   const Layout& L = a.L;
-  const double* __restrict__ gin = a.in[blockIdx.z];
-  double* __restrict__ gout = a.out[blockIdx.z];
-  long long gbase, gl;   // element offset of (node 0, pencil 0); stride of a line step
-  int pmax;              // last valid pencil index inside the bundle
-  if (DIR == 0) {
-    const int j0 = blockIdx.x * ASTR_BW, k = blockIdx.y;
-    gbase = L.idx(0, j0, k); gl = 1; pmax = L.jm - j0;
-  } else if (DIR == 1) {
-    const int i0 = blockIdx.x * ASTR_BW, k = blockIdx.y;
-    gbase = L.idx(i0, 0, k); gl = L.sj; pmax = L.im - i0;
-  } else {
-    const int i0 = blockIdx.x * ASTR_BW, j = blockIdx.y;
-    gbase = L.idx(i0, j, 0); gl = L.sk; pmax = L.im - i0;
-  }
+  const int nbx = ((DIR == 0 ? L.jm : L.im) + ASTR_BW) / ASTR_BW;
+  const int nby = (DIR == 2 ? L.jm : L.km) + 1;
+  const int nbundles = nbx * nby * a.nf;
 
-  // ---- stage the bundle: global -> shared, 16 bytes per cp.async ---------------------
-  if (DIR == 0) {
-    constexpr int LW = (T < 32) ? T : 32;
-    const int lane = tid % LW, wp = tid / LW;
-    const int w2 = (n + 13) >> 1;  // nodes -6 .. n+5 (+1 pad when n is odd)
-    for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
-      if (pp > pmax) continue;
-      const double* src = gin + gbase + L.sj * pp - 6;
-      double* dst = sm + pp * sp;
-      for (int w = lane; w < w2; w += LW) cp_async16(dst + 2 * w, src + 2 * w);
-    }
-  } else {
-    const double* src0 = gin + gbase - 5 * gl;
-    const int tot = (n + 11) * 8;
-    for (int e = tid; e < tot; e += T) {
-      const int s = e >> 3, q = e & 7;
-      cp_async16(sm + s * ASTR_BW + 2 * q, src0 + (long long)s * gl + 2 * q);
-    }
-  }
-  for (int r = tid; r < nrows; r += T) ch[r] = (unsigned char)(((r + 1) * C - 1) / nrows);
-  cp_async_wait_all();
-  __syncthreads();
-
-  // ---- phase 0: everything that must see the pristine line ---------------------------
-  const int ra = (c * nrows) / C, rb = ((c + 1) * nrows) / C - 1;
+  const int ra = chunk_start(c, nrows, C), rb = chunk_start(c + 1, nrows, C) - 1;
   const int nsf = a.op.nsf, nsl = a.op.nsl;
   const int ri = (c == 0) ? nsf : ra;                    // first interior row of the chunk
   const int re = (c == C - 1) ? (nrows - 1 - nsl) : rb;  // last interior row of the chunk
-  double w[W];
-  {
-    const int m0 = first_node + ri;
-#pragma unroll
-    for (int s = 0; s < 2 * H; ++s) w[s] = F(m0 - H + s);
-    w[2 * H] = 0.0;
-  }
-  double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
-  if (c == 0) closure_first<OP>(F, a.op.ntype, n, sf);
-  if (c == C - 1) closure_last<OP>(F, a.op.ntype, n, sl);
-  __syncthreads();
+  const int epi = a.epi;
+  const int o_lo = a.o_lo, o_hi = a.o_hi;
+  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
+  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
 
-  const double* __restrict__ ac1 = a.op.ac1;
-  const double* __restrict__ ac2 = a.op.ac2;
-  const double* __restrict__ ac3 = a.op.ac3;
-  const double* __restrict__ pf = a.op.pf;
-  const double* __restrict__ qb = a.op.qb;
+  for (int bnd = blockIdx.x * NG + grp; bnd < nbundles; bnd += gridDim.x * NG) {
+    // ---- where this bundle lives in global memory -----------------------------------
+    const int bx = bnd % nbx, by = (bnd / nbx) % nby, bz = bnd / (nbx * nby);
+    const double* __restrict__ gin = a.in[bz];
+    double* __restrict__ gout = a.out[bz];
+    long long gbase, gl;   // element offset of (node 0, pencil 0); stride of a line step
+    int pmax;              // last valid pencil index inside the bundle
+    if (DIR == 0) {
+      gbase = L.idx(0, bx * ASTR_BW, by); gl = 1; pmax = L.jm - bx * ASTR_BW;
+    } else if (DIR == 1) {
+      gbase = L.idx(bx * ASTR_BW, 0, by); gl = L.sj; pmax = L.im - bx * ASTR_BW;
+    } else {
+      gbase = L.idx(bx * ASTR_BW, by, 0); gl = L.sk; pmax = L.im - bx * ASTR_BW;
+    }
 
-  // ---- phase 1: forward elimination with zero carry-in -------------------------------
-  // e(r) = d(r)*ac2(r) - e(r-1)*ac3(r)        (src/commfunc.F90:802-804)
-  double eprev = 0.0;
-  double eh[H];
-  {
-    int r = ra;
-    if (c == 0) {
+    // ---- stage the bundle: global -> shared, 16 bytes per cp.async -------------------
+    if (DIR == 0) {
+      constexpr int LW = (T < 32) ? T : 32;
+      const int lane = tid % LW, wp = tid / LW;
+      const int w2 = (n + 13) >> 1;  // nodes -6 .. n+5 (+1 pad when n is odd)
+      for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
+        if (pp > pmax) continue;
+        const double* src = gin + gbase + L.sj * pp - 6;
+        double* dst = sm + pp * sp;
+        for (int w = lane; w < w2; w += LW) cp_async16(dst + 2 * w, src + 2 * w);
+      }
+    } else {
+      const double* src0 = gin + gbase - 5 * gl;
+      const int tot = (n + 11) * 8;
+#pragma unroll 4
+      for (int e = tid; e < tot; e += T) {
+        const int s = e >> 3, q = e & 7;
+        cp_async16(sm + s * ASTR_BW + 2 * q, src0 + (long long)s * gl + 2 * q);
+      }
+    }
+    cp_async_wait_all();
+    group_sync<NG>(grp + 1, T);
+
+    // ---- phase 0: everything that must see the pristine line -------------------------
+    double w[W];
+    {
+      const int m0 = first_node + ri;
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if (k < nsf) {
-          const double e = sf[k] * __ldg(ac2 + r) - eprev * __ldg(ac3 + r);
-          tile[(first_node + r + 5) * SL] = e;
+      for (int s = 0; s < 2 * H; ++s) w[s] = F(m0 - H + s);
+      w[2 * H] = 0.0;
+    }
+    double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
+    if (c == 0) closure_first<OP>(F, a.op.ntype, n, sf);
+    if (c == C - 1) closure_last<OP>(F, a.op.ntype, n, sl);
+    group_sync<NG>(grp + 1, T);
+
+    // ---- phase 1: forward elimination with zero carry-in -----------------------------
+    // e(r) = d(r)*ac2(r) - e(r-1)*ac3(r)        (src/commfunc.F90:802-804)
+    double eprev = 0.0;
+    double eh[H];
+    {
+      int r = ra;
+      if (c == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (k < nsf) {
+            const double e = sf[k] * ac2[r] - eprev * ac3[r];
+            tile[(first_node + r + 5) * SL] = e;
+            eprev = e;
+            ++r;
+          }
+      }
+      // the first H interior rows are kept in registers until every thread is done with
+      // its right-hand overlap (those positions are the neighbour chunk's first nodes)
+#pragma unroll
+      for (int t = 0; t < H; ++t) {
+        const int node = first_node + r;
+        w[(t + 2 * H) % W] = F(node + H);
+        const double d = interior_rhs<OP>(w, t);
+        const double e = d * ac2[r] - eprev * ac3[r];
+        eh[t] = e;
+        eprev = e;
+        ++r;
+      }
+      // full groups of W rows without guards: the loads of a group are independent of the
+      // recurrence and get hoisted, only the FMA chain is sequential
+      const int nfull = (re - r + 1) / W;
+      for (int gi = 0; gi < nfull; ++gi) {
+        double* ps = tile + (first_node + r + 5) * SL;
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          const int t = H + u;
+          w[(t + 2 * H) % W] = ps[(u + H) * SL];
+          const double d = interior_rhs<OP>(w, t);
+          const double e = d * ac2[r + u] - eprev * ac3[r + u];
+          ps[u * SL] = e;
           eprev = e;
-          ++r;
         }
-    }
-    // the first H interior rows are kept in registers until every thread is done with
-    // its right-hand overlap (those positions are the neighbour chunk's first nodes)
+        r += W;
+      }
 #pragma unroll
-    for (int t = 0; t < H; ++t) {
-      const int node = first_node + r;
-      w[(t + 2 * H) % W] = F(node + H);
-      const double d = interior_rhs<OP>(w, t);
-      const double e = d * __ldg(ac2 + r) - eprev * __ldg(ac3 + r);
-      eh[t] = e;
-      eprev = e;
-      ++r;
-    }
-    while (r <= re) {
-#pragma unroll
-      for (int u = 0; u < W; ++u) {
+      for (int u = 0; u < W - 1; ++u) {
         const int t = H + u;
         if (r <= re) {
           const int node = first_node + r;
           w[(t + 2 * H) % W] = F(node + H);
           const double d = interior_rhs<OP>(w, t);
-          const double e = d * __ldg(ac2 + r) - eprev * __ldg(ac3 + r);
+          const double e = d * ac2[r] - eprev * ac3[r];
           tile[(node + 5) * SL] = e;
           eprev = e;
           ++r;
         }
       }
-    }
-    if (c == C - 1) {
+      if (c == C - 1) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if (k < nsl) {
-          const double e = sl[k] * __ldg(ac2 + r) - eprev * __ldg(ac3 + r);
-          tile[(first_node + r + 5) * SL] = e;
-          eprev = e;
-          ++r;
+        for (int k = 0; k < 5; ++k)
+          if (k < nsl) {
+            const double e = sl[k] * ac2[r] - eprev * ac3[r];
+            tile[(first_node + r + 5) * SL] = e;
+            eprev = e;
+            ++r;
+          }
+      }
+    }
+    EE[c * ASTR_BW + p] = eprev;
+    group_sync<NG>(grp + 1, T);
+#pragma unroll
+    for (int t = 0; t < H; ++t) tile[(first_node + ri + t + 5) * SL] = eh[t];
+    // true carry into this chunk: d'(ra-1)
+    double cin = 0.0;
+    for (int cc = 0; cc < c; ++cc) {
+      const int rbc = chunk_start(cc + 1, nrows, C) - 1;
+      cin = EE[cc * ASTR_BW + p] + pf[rbc] * cin;
+    }
+
+    // ---- phase 2: back substitution with zero carry-in -------------------------------
+    // x(r) = d'(r) - ac1(r)*x(r+1)              (src/commfunc.F90:808-810)
+    {
+      double gnext = 0.0;
+      int r = rb;
+      const int nfull = (rb - ra + 1) / 8;
+      for (int gi = 0; gi < nfull; ++gi) {
+        double* ps = tile + (first_node + r + 5) * SL;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double dp = ps[-u * SL] + pf[r - u] * cin;
+          const double g = dp - ac1[r - u] * gnext;
+          ps[-u * SL] = g;
+          gnext = g;
         }
+        r -= 8;
+      }
+      for (; r >= ra; --r) {
+        double* ps = tile + (first_node + r + 5) * SL;
+        const double dp = *ps + pf[r] * cin;
+        const double g = dp - ac1[r] * gnext;
+        *ps = g;
+        gnext = g;
+      }
+      GS[c * ASTR_BW + p] = gnext;
     }
-  }
-  EE[c * ASTR_BW + p] = eprev;
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < H; ++t) tile[(first_node + ri + t + 5) * SL] = eh[t];
-  // true carry into this chunk: d'(ra-1)
-  double cin = 0.0;
-  for (int cc = 0; cc < c; ++cc) {
-    const int rbc = ((cc + 1) * nrows) / C - 1;
-    cin = EE[cc * ASTR_BW + p] + __ldg(pf + rbc) * cin;
-  }
+    group_sync<NG>(grp + 1, T);
+    {
+      double xin = 0.0;
+      for (int cc = C - 1; cc > c; --cc) {
+        const int rac = chunk_start(cc, nrows, C);
+        xin = GS[cc * ASTR_BW + p] + qb[rac] * xin;
+      }
+      XIN[c * ASTR_BW + p] = xin;
+    }
+    group_sync<NG>(grp + 1, T);
 
-  // ---- phase 2: back substitution with zero carry-in ---------------------------------
-  // x(r) = d'(r) - ac1(r)*x(r+1)              (src/commfunc.F90:808-810)
-  {
-    double gnext = 0.0;
+    // ---- phase 3: coalesced write-out, x = g + qb*xin, epilogue ----------------------
+    if (DIR == 0) {
+      constexpr int LW = (T < 32) ? T : 32;
+      const int lane = tid % LW, wp = tid / LW;
+      for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
+        if (pp > pmax) continue;
+        double* orow = gout + gbase + L.sj * pp;
+        const double* srow = sm + pp * sp + 6;
 #pragma unroll 4
-    for (int r = rb; r >= ra; --r) {
-      double* ps = tile + (first_node + r + 5) * SL;
-      const double dp = *ps + __ldg(pf + r) * cin;
-      const double g = dp - __ldg(ac1 + r) * gnext;
-      *ps = g;
-      gnext = g;
-    }
-    GS[c * ASTR_BW + p] = gnext;
-  }
-  __syncthreads();
-  {
-    double xin = 0.0;
-    for (int cc = C - 1; cc > c; --cc) {
-      const int rac = (cc * nrows) / C;
-      xin = GS[cc * ASTR_BW + p] + __ldg(qb + rac) * xin;
-    }
-    XIN[c * ASTR_BW + p] = xin;
-  }
-  __syncthreads();
-
-  // ---- phase 3: coalesced write-out, x = g + qb*xin, epilogue -------------------------
-  const int epi = a.epi;
-  const int o_lo = a.o_lo, o_hi = a.o_hi;
-  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
-  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
-  if (DIR == 0) {
-    constexpr int LW = (T < 32) ? T : 32;
-    const int lane = tid % LW, wp = tid / LW;
-    for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
-      if (pp > pmax) continue;
-      double* orow = gout + gbase + L.sj * pp;
-      const double* srow = sm + pp * sp + 6;
+        for (int node = w_lo + lane; node <= w_hi; node += LW) {
+          const int r = node - first_node;
+          double x = srow[node] + qb[r] * XIN[ch[r] * ASTR_BW + pp];
+          if (epi == EPI_ADD) x = orow[node] + x;
+          else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
+          orow[node] = x;
+        }
+      }
+    } else {
+      const int pp = tid & (ASTR_BW - 1);
+      if (pp <= pmax) {
+        double* ocol = gout + gbase + pp;
 #pragma unroll 4
-      for (int node = w_lo + lane; node <= w_hi; node += LW) {
-        const int r = node - first_node;
-        double x = srow[node] + __ldg(qb + r) * XIN[ch[r] * ASTR_BW + pp];
-        if (epi == EPI_ADD) x = orow[node] + x;
-        else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-        orow[node] = x;
+        for (int node = w_lo + (tid >> 4); node <= w_hi; node += C) {
+          const int r = node - first_node;
+          double x = sm[(node + 5) * ASTR_BW + pp] + qb[r] * XIN[ch[r] * ASTR_BW + pp];
+          double* po = ocol + (long long)node * gl;
+          if (epi == EPI_ADD) x = *po + x;
+          else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
+          *po = x;
+        }
       }
     }
-  } else {
-    const int pp = tid & (ASTR_BW - 1);
-    if (pp <= pmax) {
-      double* ocol = gout + gbase + pp;
-#pragma unroll 4
-      for (int node = w_lo + (tid >> 4); node <= w_hi; node += C) {
-        const int r = node - first_node;
-        double x = sm[(node + 5) * ASTR_BW + pp] + __ldg(qb + r) * XIN[ch[r] * ASTR_BW + pp];
-        double* po = ocol + (long long)node * gl;
-        if (epi == EPI_ADD) x = *po + x;
-        else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-        *po = x;
-      }
-    }
+    // the buffer is overwritten by the next bundle's cp.async: all reads must be done
+    group_sync<NG>(grp + 1, T);
   }
 }
 
-template <int DIR, int OP, int C>
+static int g_num_sms = 0;
+
+template <int DIR, int OP, int C, int NG>
 int launch_one(const SweepArgs& a, cudaStream_t st) {
   int sp = 0;
-  const size_t smem = astr_sweep_smem_bytes(DIR, a.op.n, C, &sp);
-  static bool attr_done = false;
+  const size_t smem = astr_sweep_smem_bytes(DIR, a.op.n, C, NG, &sp);
   static size_t attr_smem = 0;
-  if (!attr_done || smem > attr_smem) {
-    CUDA_OK(cudaFuncSetAttribute(sweep_kernel<DIR, OP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(sweep_kernel<DIR, OP, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  static int occ = 0;
+  auto kern = sweep_kernel<DIR, OP, C, NG>;
+  if (smem > attr_smem || occ == 0) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    attr_done = true;
     attr_smem = smem;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ASTR_BW * C * NG, smem));
+    if (occ < 1) return astr_fail_msg("sweep: kernel does not fit on an SM");
+    if (!g_num_sms) {
+      int dev = 0;
+      CUDA_OK(cudaGetDevice(&dev));
+      CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
   }
   SweepArgs b = a;
   b.sp = sp;
   const Layout& L = a.L;
-  dim3 grid;
-  if (DIR == 0) grid = dim3((L.jm + ASTR_BW) / ASTR_BW, L.km + 1, a.nf);
-  else if (DIR == 1) grid = dim3((L.im + ASTR_BW) / ASTR_BW, L.km + 1, a.nf);
-  else grid = dim3((L.im + ASTR_BW) / ASTR_BW, L.jm + 1, a.nf);
-  sweep_kernel<DIR, OP, C><<<grid, ASTR_BW * C, smem, st>>>(b);
+  const int nbx = ((DIR == 0 ? L.jm : L.im) + ASTR_BW) / ASTR_BW;
+  const int nby = (DIR == 2 ? L.jm : L.km) + 1;
+  const long long nbundles = (long long)nbx * nby * a.nf;
+  long long grid = (long long)g_num_sms * occ;
+  const long long need = (nbundles + NG - 1) / NG;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, ASTR_BW * C * NG, smem, st>>>(b);
   astr_count_launch();
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -412,11 +488,17 @@ int launch_one(const SweepArgs& a, cudaStream_t st) {
 
 template <int DIR, int OP>
 int launch_c(const SweepArgs& a, cudaStream_t st) {
+  const int n = a.op.n;
+  const size_t cap = 227 * 1024;
   switch (a.op.C) {
-    case 1: return launch_one<DIR, OP, 1>(a, st);
-    case 2: return launch_one<DIR, OP, 2>(a, st);
-    case 4: return launch_one<DIR, OP, 4>(a, st);
-    case 8: return launch_one<DIR, OP, 8>(a, st);
+    case 1: return launch_one<DIR, OP, 1, 1>(a, st);
+    case 2: return launch_one<DIR, OP, 2, 1>(a, st);
+    case 4: return launch_one<DIR, OP, 4, 1>(a, st);
+    case 8:
+      if (astr_sweep_smem_bytes(DIR, n, 8, 3, nullptr) <= cap) return launch_one<DIR, OP, 8, 3>(a, st);
+      if (astr_sweep_smem_bytes(DIR, n, 8, 2, nullptr) <= cap) return launch_one<DIR, OP, 8, 2>(a, st);
+      if (astr_sweep_smem_bytes(DIR, n, 8, 1, nullptr) <= cap) return launch_one<DIR, OP, 8, 1>(a, st);
+      return astr_fail_msg("sweep: line too long for shared memory");
     default: return astr_fail_msg("sweep: unsupported chunk count");
   }
 }
@@ -433,20 +515,21 @@ int astr_sweep_max_chunks(int nrows) {
   return best;
 }
 
-size_t astr_sweep_smem_bytes(int dir, int n, int C, int* sp_out) {
+size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out) {
   int sp = 0;
   size_t tile;
   if (dir == 0) {
     int wdt = n + 12 + (n & 1);  // nodes -6..n+5, even count
     sp = wdt;
-    while ((sp & 15) != 2) ++sp;
+    while ((sp & 15) != 2 && (sp & 15) != 14) ++sp;   // 2*p_lo*(sp/2) must hit 8 distinct even banks
     tile = (size_t)ASTR_BW * sp;
   } else {
     tile = (size_t)(n + 11) * ASTR_BW;
   }
   if (sp_out) *sp_out = sp;
-  size_t bytes = (tile + 3 * (size_t)C * ASTR_BW) * sizeof(double) + (size_t)(n + 16);
-  return (bytes + 15) & ~(size_t)15;
+  const size_t nrows_max = (size_t)n + 8;          // >= nrows rounded up to even
+  const size_t tabs = 5 * nrows_max + ((nrows_max + 15) & ~(size_t)15) / 8;
+  return (tabs + (size_t)NG * (tile + 2 * (size_t)C * ASTR_BW)) * sizeof(double);
 }
 
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st) {

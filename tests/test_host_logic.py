@@ -81,7 +81,14 @@ def test_no_gpu_means_loud_failure():
 def _partitioned_thomas(ac1, ac2, ac3, d, C):
     """Chunked forward/backward with zero carries + exact carry recovery, as the kernel does."""
     N = d.size
-    cs = [(c * N) // C for c in range(C + 1)]
+    def chunk_start(c):   # astr_b200/csrc/common.cuh
+        if c <= 0:
+            return 0
+        if c >= C:
+            return N
+        s = (c * N) // C
+        return (s | 1) if (c & 1) else (s & ~1)
+    cs = [chunk_start(c) for c in range(C + 1)]
     ac2 = ac2.copy(); ac3 = ac3.copy(); ac2[0] = 1.0; ac3[0] = 0.0
     pf = np.zeros(N); qb = np.zeros(N)
     for c in range(C):

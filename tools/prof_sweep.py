@@ -1,0 +1,17 @@
+"""Profiling driver: a few launches of each line-solve sweep at the bench size (no setup
+beyond astr_gpu_init), for `ncu -k regex:sweep_kernel`."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from astr_b200 import RhsEngine, decompose, refcal
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+homo = (True, True, True)
+b = decompose((n, n, n), (1, 1, 1), homo)[0]
+eng = RhsEngine(b, (n, n, n), homo, refcal(1600.0, 0.1), device=0)
+for op in (0, 1):
+    for d in (0, 1, 2):
+        ms = eng.bench_sweep(op, d, 5, iters)
+        gbs = 5 * 16.0 * (n + 1) ** 3 / (ms * 1e-3) / 1e9
+        print(f"op={'deriv' if op == 0 else 'filter'} dir={'ijk'[d]} {ms:.3f} ms/launch  {gbs:.0f} GB/s", flush=True)
+eng.close()
