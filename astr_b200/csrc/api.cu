@@ -217,6 +217,7 @@ struct Ctx {
   double* d_out2 = nullptr;
   cudaStream_t st = nullptr;
   bool have_metrics = false, have_grad = false;
+  bool rhs_in_g = false;         // qrhs lives as three directional derivatives in the G slots
   double force[3] = {0, 0, 0};
   // multi-block
   ncclComm_t comm = nullptr;
@@ -527,6 +528,7 @@ int astr_gpu_get_field(int field_id, double* host) {
     if (!g->have_grad) return astr_fail_msg("dvel/dtmp/vor requested before gradcal");
     TRY(pw_materialise_grad(g->L, g->pool, g->scr, g->st));
   }
+  if (s >= S_QRHS && s < S_QRHS + 5 && g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->st));
   TRY(copy_field(s, host, true));
   CUDA_OK(cudaStreamSynchronize(g->st));
   return 0;
@@ -537,6 +539,10 @@ int astr_gpu_set_field(int field_id, const double* host) {
   int s;
   TRY(api_slot(field_id, &s));
   if (s >= S_SCR) return astr_fail_msg("dvel/dtmp/vor are derived fields");
+  if (s >= S_QRHS && s < S_QRHS + 5) {
+    if (g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->st));
+    g->rhs_in_g = false;   // the caller now owns qrhs as an array
+  }
   TRY(copy_field(s, const_cast<double*>(host), false));
   CUDA_OK(cudaStreamSynchronize(g->st));
   return 0;
@@ -680,13 +686,16 @@ int astr_gpu_rhscal(void) {
         TRY(pw_flux(L, g->pool, h, 1 << d, fr, c.diffterm, g->st));
       }
   }
+  // d(G_d)/d(xi_d) in place (zero outside is:ie etc., where the reference does not accumulate);
+  // the three directions are summed by the RK update kernel: no read-modify-write of qrhs
   const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
   for (int d = 0; d < 3; ++d) {
     const double* in[5]; double* out[5];
-    for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_QRHS + m); }
+    for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_G + 5 * d + m); }
     ProfScope ps(PC_DIV_I + d);
-    TRY(sweep(d, OP_DERIV, in, out, 5, d == 0 ? EPI_STOREZ : EPI_ADD, s[d], e[d]));
+    TRY(sweep(d, OP_DERIV, in, out, 5, EPI_STOREZ, s[d], e[d]));
   }
+  g->rhs_in_g = true;
   if (c.flowtype == 1) return astr_fail_msg("src_chan forcing is not implemented yet");
   return 0;
 }
@@ -697,6 +706,7 @@ static int rk_coef(int rkstep, double dt, RkCoef& rk) {
   const double co[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0}};
   rk.c1 = co[rkstep - 1][0]; rk.c2 = co[rkstep - 1][1]; rk.c3 = co[rkstep - 1][2];
   rk.dt = dt; rk.first = (rkstep == 1);
+  rk.rhs_in_g = g->rhs_in_g ? 1 : 0;
   return 0;
 }
 

@@ -237,10 +237,28 @@ __global__ void k_rk_update(const Layout L, double* __restrict__ pool, const The
     } else {
       qs = pool[(S_QSAVE + m) * fs + x];
     }
-    const double vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * pool[(S_QRHS + m) * fs + x] * rk.dt;
+    // qrhs = sum over directions of d(G_d)/d(xi_d); after rhscal the G slots hold the derivatives
+    double rhs;
+    if (rk.rhs_in_g)
+      rhs = pool[(S_G + m) * fs + x] + pool[(S_G + 5 + m) * fs + x] + pool[(S_G + 10 + m) * fs + x];
+    else
+      rhs = pool[(S_QRHS + m) * fs + x];
+    const double vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * rhs * rk.dt;
     pool[(S_Q + m) * fs + x] = vv / jac;
   }
   if (rk.with_fvar) q2fvar_node(pool, fs, x, th);
+}
+
+// qrhs(0:im,0:jm,0:km,:) as an array of its own (staged API / tests / source terms)
+__global__ void k_sum_qrhs(const Layout L, double* __restrict__ pool) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+#pragma unroll
+  for (int m = 0; m < 5; ++m)
+    pool[(S_QRHS + m) * fs + x] =
+        pool[(S_G + m) * fs + x] + pool[(S_G + 5 + m) * fs + x] + pool[(S_G + 10 + m) * fs + x];
 }
 
 // src_chan body force (src/solver.F90:341-352): qrhs(2:4)+=force*jacob,
@@ -393,6 +411,13 @@ int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& 
                  cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   k_rk_update<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, rk);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_sum_qrhs(const Layout& L, double* pool, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_sum_qrhs<<<box_grid(b), PW_T, 0, st>>>(L, pool);
   LAUNCH_CHECK();
   return 0;
 }

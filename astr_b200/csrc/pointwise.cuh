@@ -41,7 +41,8 @@ int pw_materialise_grad(const Layout& L, double* pool, double* dvel9_dtmp3_vor3,
 struct FluxRanges { int s[3], e[3]; };
 int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
             cudaStream_t st);
-struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; };
+struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; };
+int pw_sum_qrhs(const Layout& L, double* pool, cudaStream_t st);
 int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* force,
                  cudaStream_t st);
 int pw_add_force(const Layout& L, double* pool, const double force[3], double fe, cudaStream_t st);

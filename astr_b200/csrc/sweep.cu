@@ -272,12 +272,17 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
         for (int w = lane; w < w2; w += LW) cp_async16(dst + 2 * w, src + 2 * w);
       }
     } else {
-      const double* src0 = gin + gbase - 5 * gl;
-      const int tot = (n + 11) * 8;
+      // thread -> (16-byte column q, row s0 + k*RS): a warp fetches 4 full 128-byte rows
+      constexpr int RS = T / 8;
+      const int q = tid & 7, s0 = tid >> 3;
+      const double* src = gin + gbase + (long long)(s0 - 5) * gl + 2 * q;
+      double* dst = sm + s0 * ASTR_BW + 2 * q;
+      const long long sstep = (long long)RS * gl;
 #pragma unroll 4
-      for (int e = tid; e < tot; e += T) {
-        const int s = e >> 3, q = e & 7;
-        cp_async16(sm + s * ASTR_BW + 2 * q, src0 + (long long)s * gl + 2 * q);
+      for (int srow = s0; srow < n + 11; srow += RS) {
+        cp_async16(dst, src);
+        dst += RS * ASTR_BW;
+        src += sstep;
       }
     }
     cp_async_wait_all();
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           if (k < nsf) {
-            const double e = sf[k] * ac2[r] - eprev * ac3[r];
+            const double e = __fma_rn(-eprev, ac3[r], sf[k] * ac2[r]);
             tile[(first_node + r + 5) * SL] = e;
             eprev = e;
             ++r;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
         const int node = first_node + r;
         w[(t + 2 * H) % W] = F(node + H);
         const double d = interior_rhs<OP>(w, t);
-        const double e = d * ac2[r] - eprev * ac3[r];
+        const double e = __fma_rn(-eprev, ac3[r], d * ac2[r]);
         eh[t] = e;
         eprev = e;
         ++r;
@@ -329,12 +334,21 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
       const int nfull = (re - r + 1) / W;
       for (int gi = 0; gi < nfull; ++gi) {
         double* ps = tile + (first_node + r + 5) * SL;
+        // every load of the group first (explicitly: the compiler cannot move shared loads
+        // above the in-place stores), then the arithmetic; only one FMA per row is sequential
+        double fn[W], c2[W], c3[W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          fn[u] = ps[(u + H) * SL];
+          c2[u] = ac2[r + u];
+          c3[u] = ac3[r + u];
+        }
 #pragma unroll
         for (int u = 0; u < W; ++u) {
           const int t = H + u;
-          w[(t + 2 * H) % W] = ps[(u + H) * SL];
+          w[(t + 2 * H) % W] = fn[u];
           const double d = interior_rhs<OP>(w, t);
-          const double e = d * ac2[r + u] - eprev * ac3[r + u];
+          const double e = __fma_rn(-eprev, c3[u], d * c2[u]);
           ps[u * SL] = e;
           eprev = e;
         }
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
           const int node = first_node + r;
           w[(t + 2 * H) % W] = F(node + H);
           const double d = interior_rhs<OP>(w, t);
-          const double e = d * ac2[r] - eprev * ac3[r];
+          const double e = __fma_rn(-eprev, ac3[r], d * ac2[r]);
           tile[(node + 5) * SL] = e;
           eprev = e;
           ++r;
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           if (k < nsl) {
-            const double e = sl[k] * ac2[r] - eprev * ac3[r];
+            const double e = __fma_rn(-eprev, ac3[r], sl[k] * ac2[r]);
             tile[(first_node + r + 5) * SL] = e;
             eprev = e;
             ++r;
@@ -383,10 +397,17 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
       const int nfull = (rb - ra + 1) / 8;
       for (int gi = 0; gi < nfull; ++gi) {
         double* ps = tile + (first_node + r + 5) * SL;
+        double ev[8], pv[8], av[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const double dp = ps[-u * SL] + pf[r - u] * cin;
-          const double g = dp - ac1[r - u] * gnext;
+          ev[u] = ps[-u * SL];
+          pv[u] = pf[r - u];
+          av[u] = ac1[r - u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double dp = __fma_rn(pv[u], cin, ev[u]);
+          const double g = __fma_rn(-av[u], gnext, dp);
           ps[-u * SL] = g;
           gnext = g;
         }
@@ -394,8 +415,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
       }
       for (; r >= ra; --r) {
         double* ps = tile + (first_node + r + 5) * SL;
-        const double dp = *ps + pf[r] * cin;
-        const double g = dp - ac1[r] * gnext;
+        const double dp = __fma_rn(pf[r], cin, *ps);
+        const double g = __fma_rn(-ac1[r], gnext, dp);
         *ps = g;
         gnext = g;
       }
@@ -413,34 +434,77 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
     group_sync<NG>(grp + 1, T);
 
     // ---- phase 3: coalesced write-out, x = g + qb*xin, epilogue ----------------------
+    // chunk by chunk (xin is per chunk), 4 rows per batch with the accumulate loads up front
+    const int r_lo = w_lo - first_node, r_hi = w_hi - first_node;
     if (DIR == 0) {
       constexpr int LW = (T < 32) ? T : 32;
       const int lane = tid % LW, wp = tid / LW;
       for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
         if (pp > pmax) continue;
-        double* orow = gout + gbase + L.sj * pp;
-        const double* srow = sm + pp * sp + 6;
-#pragma unroll 4
-        for (int node = w_lo + lane; node <= w_hi; node += LW) {
-          const int r = node - first_node;
-          double x = srow[node] + qb[r] * XIN[ch[r] * ASTR_BW + pp];
-          if (epi == EPI_ADD) x = orow[node] + x;
-          else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-          orow[node] = x;
+        double* orow = gout + gbase + L.sj * pp + first_node;      // orow[r]
+        const double* srow = sm + pp * sp + 6 + first_node;        // srow[r]
+        for (int cc = 0; cc < C; ++cc) {
+          const double xin = XIN[cc * ASTR_BW + pp];
+          const int rlo = max(chunk_start(cc, nrows, C), r_lo), rhi = min(chunk_start(cc + 1, nrows, C) - 1, r_hi);
+          for (int r0 = rlo + lane; r0 <= rhi; r0 += 4 * LW) {
+            double old[4];
+            if (epi == EPI_ADD) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (r0 + k * LW <= rhi) old[k] = orow[r0 + k * LW];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = r0 + k * LW;
+              if (r <= rhi) {
+                double x = __fma_rn(qb[r], xin, srow[r]);
+                if (epi == EPI_ADD) x = old[k] + x;
+                else if (epi == EPI_STOREZ && (r < o_lo - first_node || r > o_hi - first_node)) x = 0.0;
+                orow[r] = x;
+              }
+            }
+          }
         }
       }
     } else {
-      const int pp = tid & (ASTR_BW - 1);
+      // thread -> pencil pair (16-byte column) x row slot: a warp writes 4 full 128-byte rows
+      constexpr int RS = T / 8;
+      const int pp = 2 * (tid & 7), rs = tid >> 3;
       if (pp <= pmax) {
-        double* ocol = gout + gbase + pp;
-#pragma unroll 4
-        for (int node = w_lo + (tid >> 4); node <= w_hi; node += C) {
-          const int r = node - first_node;
-          double x = sm[(node + 5) * ASTR_BW + pp] + qb[r] * XIN[ch[r] * ASTR_BW + pp];
-          double* po = ocol + (long long)node * gl;
-          if (epi == EPI_ADD) x = *po + x;
-          else if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-          *po = x;
+        const bool pair = (pp + 1 <= pmax);
+        double* ocol = gout + gbase + pp + (long long)first_node * gl;   // ocol[r*gl]
+        const double* scol = sm + (first_node + 5) * ASTR_BW + pp;        // scol[r*16]
+        for (int cc = 0; cc < C; ++cc) {
+          const double2 xin = *reinterpret_cast<const double2*>(XIN + cc * ASTR_BW + pp);
+          const int rlo = max(chunk_start(cc, nrows, C), r_lo), rhi = min(chunk_start(cc + 1, nrows, C) - 1, r_hi);
+          for (int r0 = rlo + rs; r0 <= rhi; r0 += 4 * RS) {
+            double2 old[4];
+            if (epi == EPI_ADD) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (r0 + k * RS <= rhi) {
+                  const double* po = ocol + (long long)(r0 + k * RS) * gl;
+                  if (pair) old[k] = *reinterpret_cast<const double2*>(po);
+                  else { old[k].x = *po; old[k].y = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = r0 + k * RS;
+              if (r <= rhi) {
+                const double2 gv = *reinterpret_cast<const double2*>(scol + r * ASTR_BW);
+                const double qv = qb[r];
+                double2 x;
+                x.x = __fma_rn(qv, xin.x, gv.x);
+                x.y = __fma_rn(qv, xin.y, gv.y);
+                if (epi == EPI_ADD) { x.x = old[k].x + x.x; x.y = old[k].y + x.y; }
+                else if (epi == EPI_STOREZ && (r < o_lo - first_node || r > o_hi - first_node)) { x.x = 0.0; x.y = 0.0; }
+                double* po = ocol + (long long)r * gl;
+                if (pair) *reinterpret_cast<double2*>(po) = x;
+                else *po = x.x;
+              }
+            }
+          }
         }
       }
     }

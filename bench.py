@@ -204,10 +204,10 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel family: the batched line-solve sweep ---------------
     peak, peak_src = measured_peaks()
     nst = STAGES * args.steps
-    alg = {  # algorithmic bytes per launch: fields x points x 16 B (store) / 24 B (accumulate)
+    alg = {  # algorithmic bytes per launch: fields x points x 16 B (1 read + 1 write)
         "filter_i": 5 * BYTES_STORE, "filter_j": 5 * BYTES_STORE, "filter_k": 5 * BYTES_STORE,
         "grad_i": 4 * BYTES_STORE, "grad_j": 4 * BYTES_STORE, "grad_k": 4 * BYTES_STORE,
-        "div_i": 5 * BYTES_STORE, "div_j": 5 * BYTES_ADD, "div_k": 5 * BYTES_ADD,
+        "div_i": 5 * BYTES_STORE, "div_j": 5 * BYTES_STORE, "div_k": 5 * BYTES_STORE,
     }
     kern = {}
     tot_b = tot_ms = 0.0
