@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
         ch[r] = (unsigned char)cc;
       }
     }
+    // padding rows (the paired write-out may look one row past the end)
+    for (int r = nrows + threadIdx.x; r < ((nrows + 15) & ~15); r += T * NG) ch[r] = 0;
   }
   __syncthreads();
 
@@ -437,31 +439,45 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
     // chunk by chunk (xin is per chunk), 4 rows per batch with the accumulate loads up front
     const int r_lo = w_lo - first_node, r_hi = w_hi - first_node;
     if (DIR == 0) {
+      // lanes run along the line in aligned node pairs (16-byte accesses, full 128-byte lines);
+      // the chunk of each node comes from the byte table
       constexpr int LW = (T < 32) ? T : 32;
       const int lane = tid % LW, wp = tid / LW;
+      const int n_lo = w_lo & ~1;
       for (int pp = wp; pp < ASTR_BW; pp += T / LW) {
         if (pp > pmax) continue;
-        double* orow = gout + gbase + L.sj * pp + first_node;      // orow[r]
-        const double* srow = sm + pp * sp + 6 + first_node;        // srow[r]
-        for (int cc = 0; cc < C; ++cc) {
-          const double xin = XIN[cc * ASTR_BW + pp];
-          const int rlo = max(chunk_start(cc, nrows, C), r_lo), rhi = min(chunk_start(cc + 1, nrows, C) - 1, r_hi);
-          for (int r0 = rlo + lane; r0 <= rhi; r0 += 4 * LW) {
-            double old[4];
-            if (epi == EPI_ADD) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (r0 + k * LW <= rhi) old[k] = orow[r0 + k * LW];
-            }
+        double* orow = gout + gbase + L.sj * pp;                   // orow[node]
+        const double* srow = sm + pp * sp + 6;                     // srow[node]
+        const double* xrow = XIN + pp;
+        for (int nd0 = n_lo + 2 * lane; nd0 <= w_hi; nd0 += 8 * LW) {
+          double2 old[4];
+          if (epi == EPI_ADD) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int r = r0 + k * LW;
-              if (r <= rhi) {
-                double x = __fma_rn(qb[r], xin, srow[r]);
-                if (epi == EPI_ADD) x = old[k] + x;
-                else if (epi == EPI_STOREZ && (r < o_lo - first_node || r > o_hi - first_node)) x = 0.0;
-                orow[r] = x;
+              const int nd = nd0 + 2 * k * LW;
+              if (nd <= w_hi) {
+                if (nd >= w_lo && nd + 1 <= w_hi) old[k] = *reinterpret_cast<const double2*>(orow + nd);
+                else { old[k].x = (nd >= w_lo) ? orow[nd] : 0.0; old[k].y = (nd + 1 <= w_hi) ? orow[nd + 1] : 0.0; }
               }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int nd = nd0 + 2 * k * LW;
+            if (nd <= w_hi) {
+              const int r = nd - first_node;
+              const double2 gv = *reinterpret_cast<const double2*>(srow + nd);
+              double2 x;
+              x.x = __fma_rn(qb[r], xrow[ch[r] * ASTR_BW], gv.x);
+              x.y = __fma_rn(qb[r + 1], xrow[ch[r + 1] * ASTR_BW], gv.y);
+              if (epi == EPI_ADD) { x.x = old[k].x + x.x; x.y = old[k].y + x.y; }
+              else if (epi == EPI_STOREZ) {
+                if (nd < o_lo || nd > o_hi) x.x = 0.0;
+                if (nd + 1 < o_lo || nd + 1 > o_hi) x.y = 0.0;
+              }
+              if (nd >= w_lo && nd + 1 <= w_hi) *reinterpret_cast<double2*>(orow + nd) = x;
+              else if (nd >= w_lo) orow[nd] = x.x;
+              else if (nd + 1 <= w_hi) orow[nd + 1] = x.y;
             }
           }
         }
