@@ -8,7 +8,7 @@ src/parallel.F90.  There is no CPU path: every operator raises if the CUDA libra
 GPU is missing.
 """
 from .lib import AstrCfg, AstrGpuError, build, load, lib_path, FIELD_IDS, HM  # noqa: F401
-from .parallel import Block, decompose, mpisizedis  # noqa: F401
+from .parallel import Block, HaloMessage, decompose, halo_plan, mpisizedis  # noqa: F401
 from .solver import RhsEngine, refcal  # noqa: F401
 from . import cases  # noqa: F401
 

@@ -108,3 +108,45 @@ def decompose(dims: Sequence[int], size: Sequence[int], homo: Sequence[bool]) ->
                 blocks.append(Block(rank=rank_of(0, irk), rk=rk, size=tuple(size), dims=dm, g0=g0,
                                     npdc=tuple(npdc), s=tuple(s), e=tuple(e), nbr=nbr))
     return blocks
+
+
+# --------------------------------------------------------------------------------------
+# Halo-exchange plan: which messages one block posts for one direction.  This is the
+# schedule libastr_gpu.so executes with grouped ncclSend/ncclRecv (csrc/api.cu
+# exchange_dir); it is stated here so that host code (and the gloo tests) can reason about
+# it without a GPU.
+# --------------------------------------------------------------------------------------
+@dataclass
+class HaloMessage:
+    peer: int            # rank of the neighbour
+    send_side: int       # 0: my planes l0..l1 (low side), 1: my planes dm-l (high side)
+    recv_side: int       # 1: lands in my high halo dm+l, 0: lands in my low halo -l
+    count: int           # doubles
+
+
+def halo_plan(block: Block, d: int, mode: str, nfields: int) -> Tuple[List[HaloMessage], List[HaloMessage]]:
+    """(sends, recvs) of direction d in posting order.
+
+    mode: "swap"  -> planes 1..hm          (dataswap, src/parallel.F90:4132-4370)
+          "qswap" -> planes 0..hm, plane 0 averaged with the neighbour's (qswap, :4848-5318)
+          "sync"  -> plane 0 only, averaged (array3d_sync, :3725-3934)
+    Low-side planes go to the low neighbour (which puts them in its HIGH halo) and vice
+    versa.  When both neighbours are the same rank (two blocks, periodic) the peer's first
+    message is its low-side buffer, so the receive for MY HIGH halo is posted first.
+    """
+    hm = 5
+    l0, l1 = {"swap": (1, hm), "qswap": (0, hm), "sync": (0, 0)}[mode]
+    o = [x for x in range(3) if x != d]
+    n1, n2 = block.dims[o[0]] + 1, block.dims[o[1]] + 1
+    cnt = (l1 - l0 + 1) * n1 * n2 * nfields
+    lo, hi = block.nbr[2 * d], block.nbr[2 * d + 1]
+    sends, recvs = [], []
+    if lo >= 0:
+        sends.append(HaloMessage(lo, 0, 1, cnt))
+    if hi >= 0:
+        sends.append(HaloMessage(hi, 1, 0, cnt))
+    if hi >= 0:
+        recvs.append(HaloMessage(hi, 0, 1, cnt))   # the high neighbour's low-side planes -> my high halo
+    if lo >= 0:
+        recvs.append(HaloMessage(lo, 1, 0, cnt))   # the low neighbour's high-side planes -> my low halo
+    return sends, recvs
