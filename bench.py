@@ -137,6 +137,9 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL prints its version banner on stdout at NCCL_DEBUG>=VERSION: keep stdout to ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
