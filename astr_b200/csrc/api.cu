@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -94,6 +95,7 @@ struct HostOp {
   int first_node = 0, nrows = 0, ntype = 0, n = 0, C = 1, nsf = 0, nsl = 0;
   std::vector<double> a, c, ac1, ac2, ac3, pf, qb;
   double* d_tab = nullptr;  // 5*nrows doubles on the device
+  LinePlan plan;            // register-resident engine (sweep2.cu); plan.ok == 0: not applicable
   LineOp dev() const {
     LineOp o;
     o.ac1 = d_tab; o.ac2 = d_tab + nrows; o.ac3 = d_tab + 2 * nrows;
@@ -128,74 +130,19 @@ static void factorise(HostOp& h) {
 }
 
 static void build_deriv(HostOp& h, int ntype, int n) {
-  const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
   h.ntype = ntype; h.n = n;
-  h.first_node = p0 ? 0 : -1;
-  const int last = pm ? n : n + 1;
-  h.nrows = last - h.first_node + 1;
-  h.a.assign(h.nrows, 1.0 / 3.0); h.c.assign(h.nrows, 1.0 / 3.0);
-  const int e = h.nrows - 1;
-  h.a[0] = h.c[0] = 0.0; h.a[e] = h.c[e] = 0.0;       // explicit interface rows
-  if (p0) { h.a[0] = h.c[0] = 2.0; h.a[1] = h.c[1] = 0.25; }   // 3rd/4th-order wall rows
-  if (pm) { h.a[e] = h.c[e] = 2.0; h.a[e - 1] = h.c[e - 1] = 0.25; }
-  h.nsf = p0 ? 2 : 1; h.nsl = pm ? 2 : 1;
+  build_lhs(OP_DERIV, ntype, n, 0.0, h.a, h.c, h.first_node, h.nsf, h.nsl);
+  h.nrows = (int)h.a.size();
   factorise(h);
+  build_line_plan(h.plan, OP_DERIV, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, 16);
 }
 
 static void build_filter(HostOp& h, int ntype, int n, double alfa) {
-  const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
   h.ntype = ntype; h.n = n;
-  h.first_node = p0 ? 0 : -3;
-  const int last = pm ? n : n + 3;
-  h.nrows = last - h.first_node + 1;
-  h.a.assign(h.nrows, alfa); h.c.assign(h.nrows, alfa);
-  const int e = h.nrows - 1;
-  h.a[0] = h.c[0] = p0 ? 0.98 : 1.11;     // beter_bound / beter_halo, comsolver.F90:121
-  h.a[e] = h.c[e] = pm ? 0.98 : 1.11;
-  h.nsf = p0 ? 5 : 3; h.nsl = pm ? 5 : 3;
+  build_lhs(OP_FILTER, ntype, n, alfa, h.a, h.c, h.first_node, h.nsf, h.nsl);
+  h.nrows = (int)h.a.size();
   factorise(h);
-}
-
-static void build_filter_coef(FilterCoef& fc, double alfa, double bh, double bb) {
-  // src/filter.F90:299-432
-  const double c6[4] = {(11.0 + 10.0 * alfa) / 32.0, (15.0 + 34.0 * alfa) / 64.0, (-3.0 + 6.0 * alfa) / 32.0,
-                        (1.0 - 2.0 * alfa) / 64.0};
-  const double c8[5] = {(93.0 + 70.0 * alfa) / 256.0, (7.0 + 18.0 * alfa) / 32.0, (-7.0 + 14.0 * alfa) / 64.0,
-                        (1.0 - 2.0 * alfa) / 32.0, (-1.0 + 2.0 * alfa) / 256.0};
-  const double c10[6] = {(193.0 + 126.0 * alfa) / 512.0, (105.0 + 302.0 * alfa) / 512.0,
-                         (-15.0 + 30.0 * alfa) / 128.0, (45.0 - 90.0 * alfa) / 1024.0,
-                         (-5.0 + 10.0 * alfa) / 512.0,  (1.0 - 2.0 * alfa) / 1024.0};
-  memcpy(fc.coef6i, c6, sizeof c6); memcpy(fc.coef8i, c8, sizeof c8); memcpy(fc.coef10i, c10, sizeof c10);
-  memset(fc.coefb, 0, sizeof fc.coefb); memset(fc.coefh, 0, sizeof fc.coefh);
-  const double b3[9] = {(1.0 - 2.0 * alfa) / 256.0, (-1.0 + 2.0 * alfa) / 32.0, (7.0 + 50.0 * alfa) / 64.0,
-                        (25.0 + 14.0 * alfa) / 32.0, (35.0 + 58.0 * alfa) / 128.0, (-7.0 + 14.0 * alfa) / 32.0,
-                        (7.0 - 14.0 * alfa) / 64.0, (-1.0 + 2.0 * alfa) / 32.0, (1.0 - 2.0 * alfa) / 256.0};
-  const double b2[7] = {(-1.0 + 2.0 * alfa) / 64.0, (3.0 + 26.0 * alfa) / 32.0, (49.0 + 30.0 * alfa) / 64.0,
-                        (5.0 + 6.0 * alfa) / 16.0, (-15.0 + 30.0 * alfa) / 64.0, (3.0 - 6.0 * alfa) / 32.0,
-                        (-1.0 + 2.0 * alfa) / 64.0};
-  const double b1[7] = {(1.0 + 62.0 * alfa) / 64.0, (29.0 + 6.0 * alfa) / 32.0, (15.0 + 34.0 * alfa) / 64.0,
-                        (-5.0 + 10.0 * alfa) / 16.0, (15.0 - 30.0 * alfa) / 64.0, (-3.0 + 6.0 * alfa) / 32.0,
-                        (1.0 - 2.0 * alfa) / 64.0};
-  const double b0[7] = {(63.0 + 1.0 * bb) / 64.0, (3.0 + 29.0 * bb) / 32.0, (-15.0 + 15.0 * bb) / 64.0,
-                        (5.0 - 5.0 * bb) / 16.0, (-15.0 + 15.0 * bb) / 64.0, (3.0 - 3.0 * bb) / 32.0,
-                        (-1.0 + 1.0 * bb) / 64.0};
-  memcpy(fc.coefb[3], b3, sizeof b3); memcpy(fc.coefb[2], b2, sizeof b2);
-  memcpy(fc.coefb[1], b1, sizeof b1); memcpy(fc.coefb[0], b0, sizeof b0);
-  const double h0[11] = {(-1.0 + 1.0 * bh) / 1024.0, (5.0 - 5.0 * bh) / 512.0, (979.0 + 45.0 * bh) / 1024.0,
-                         (15.0 + 113.0 * bh) / 128.0, (-105.0 + 105.0 * bh) / 512.0, (63.0 - 63.0 * bh) / 256.0,
-                         (-105.0 + 105.0 * bh) / 512.0, (15.0 - 15.0 * bh) / 128.0, (-45.0 + 45.0 * bh) / 1024.0,
-                         (5.0 - 5.0 * bh) / 512.0, (-1.0 + 1.0 * bh) / 1024.0};
-  const double h1[11] = {(1.0 - 2.0 * alfa) / 1024.0, (-5.0 + 10.0 * alfa) / 512.0, (45.0 + 934.0 * alfa) / 1024.0,
-                         (113.0 + 30.0 * alfa) / 128.0, (105.0 + 302.0 * alfa) / 512.0,
-                         (-63.0 + 126.0 * alfa) / 256.0, (105.0 - 210.0 * alfa) / 512.0,
-                         (-15.0 + 30.0 * alfa) / 128.0, (45.0 - 90.0 * alfa) / 1024.0,
-                         (-5.0 + 10.0 * alfa) / 512.0, (1.0 - 2.0 * alfa) / 1024.0};
-  const double h2[11] = {(-1.0 + 2.0 * alfa) / 1024.0, (5.0 - 10.0 * alfa) / 512.0, (-45.0 + 90.0 * alfa) / 1024.0,
-                         (15.0 + 98.0 * alfa) / 128.0, (407.0 + 210.0 * alfa) / 512.0,
-                         (63.0 + 130.0 * alfa) / 256.0, (-105.0 + 210.0 * alfa) / 512.0,
-                         (15.0 - 30.0 * alfa) / 128.0, (-45.0 + 90.0 * alfa) / 1024.0,
-                         (5.0 - 10.0 * alfa) / 512.0, (-1.0 + 2.0 * alfa) / 1024.0};
-  memcpy(fc.coefh[0], h0, sizeof h0); memcpy(fc.coefh[1], h1, sizeof h1); memcpy(fc.coefh[2], h2, sizeof h2);
+  build_line_plan(h.plan, OP_FILTER, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, 16);
 }
 
 // -------------------------------------------------------------------------------------
@@ -213,6 +160,8 @@ struct Ctx {
   double* pool = nullptr;        // S_CORE fields
   double* scr = nullptr;         // 15 scratch fields, lazily allocated
   HostOp fd[3], fl[3];
+  FilterCoef fc;
+  bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
   double* d_out2 = nullptr;
   cudaStream_t st = nullptr;
@@ -271,6 +220,7 @@ static int ensure_scratch() {
   const size_t bytes = (size_t)(S_TOTAL - S_SCR) * g->L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->scr, bytes));
   CUDA_OK(cudaMemsetAsync(g->scr, 0, bytes, g->st));
+  TRY(astr_sweep2_register_pool(1, g->scr, S_TOTAL - S_SCR, g->L));
   return 0;
 }
 
@@ -369,6 +319,11 @@ static int sweep(int d, int optype, const double* const* in, double* const* out,
   a.nf = nf;
   for (int i = 0; i < nf; ++i) { a.in[i] = in[i]; a.out[i] = out[i]; }
   a.epi = epi; a.o_lo = o_lo; a.o_hi = o_hi;
+  if (!g->legacy_sweep) {
+    const HostOp& h = (optype == OP_DERIV ? g->fd[d] : g->fl[d]);
+    const int rc = astr_launch_sweep2(d, optype, h.plan, a, g->st);
+    if (rc >= 0) return rc;
+  }
   return astr_launch_sweep(d, optype, a, g->st);
 }
 
@@ -421,15 +376,19 @@ int astr_gpu_init(const astr_cfg* cfg) {
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->pool, bytes));
   CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
+  TRY(astr_sweep2_register_pool(0, g->pool, S_CORE, g->L));
+  TRY(astr_sweep2_register_pool(1, nullptr, 0, g->L));
   CUDA_OK(cudaMalloc(&g->d_partial, (size_t)2 * (cfg->jm + 1) * (cfg->km + 1) * sizeof(double)));
   CUDA_OK(cudaMalloc(&g->d_out2, 4 * sizeof(double)));
-  FilterCoef fc;
-  build_filter_coef(fc, cfg->alfa_filter, 1.11, 0.98);
-  TRY(astr_set_filter_coef(fc));
+  build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
+  TRY(astr_set_filter_coef(g->fc));
+  { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
   for (int d = 0; d < 3; ++d) {
     const int n = dim_of(d);
     build_deriv(g->fd[d], cfg->npdc[d], n);
     build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
+    TRY(astr_sweep2_set_plan(d, OP_DERIV, g->fd[d].plan, g->fc));
+    TRY(astr_sweep2_set_plan(d, OP_FILTER, g->fl[d].plan, g->fc));
     for (HostOp* h : {&g->fd[d], &g->fl[d]}) {
       if (h->C < 1) return astr_fail_msg("block too small: every direction needs at least 12 nodes");
       const size_t nb = (size_t)5 * h->nrows * sizeof(double);
@@ -453,6 +412,7 @@ int astr_gpu_finalize(void) {
   if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
   for (auto& b : g->xbuf) if (b) cudaFree(b);
   for (int d = 0; d < 3; ++d) { cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab); }
+  astr_sweep2_register_pool(0, nullptr, 0, g->L); astr_sweep2_register_pool(1, nullptr, 0, g->L);
   cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
   cudaFree(g->d_partial); cudaFree(g->d_out2);
   cudaStreamDestroy(g->st);

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "linecore.h"
 
 #define ASTR_HM 5
 #define ASTR_IOFF 16        // element offset of node i=0 inside a row
@@ -52,13 +53,6 @@ __host__ __device__ inline int chunk_start(int c, int nrows, int C) {
   return (c & 1) ? (s | 1) : (s & ~1);
 }
 
-// coefficient tables of src/filter.F90:299-432 (only the rows the hot path reads)
-struct FilterCoef {
-  double coef6i[4], coef8i[5], coef10i[6];
-  double coefb[4][9];
-  double coefh[3][11];
-};
-
 enum { OP_DERIV = 0, OP_FILTER = 1 };
 enum { EPI_STORE = 0, EPI_STOREZ = 1, EPI_ADD = 2 };
 
@@ -88,3 +82,7 @@ int astr_set_filter_coef(const FilterCoef& fc);
 size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out);
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
 int astr_sweep_max_chunks(int nrows);
+// sweep2.cu
+int astr_sweep2_set_plan(int dir, int optype, const LinePlan& plan, const FilterCoef& fc);
+int astr_sweep2_register_pool(int which, const double* base, int nslots, const Layout& L);
+int astr_launch_sweep2(int dir, int optype, const LinePlan& plan, const SweepArgs& s, cudaStream_t st);
