@@ -128,9 +128,11 @@ __device__ __forceinline__ void role_loop(const Sweep2Args& a, const CUtensorMap
   int par = 0;
   for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
     const BundlePos bp = locate(bnd);
+    // lanes past the last pencil of a ragged bundle compute on halo / zero-filled columns and
+    // write into the unused row padding (columns -16..-9 of the same rows): no predication
     const int valid = (bp.i0 + lane) <= Lay.im;
-    double* __restrict__ gout =
-        a.out[bp.bz] + ((DIR == 1) ? Lay.idx(bp.i0 + lane, 0, bp.by) : Lay.idx(bp.i0 + lane, bp.by, 0));
+    const int icol = valid ? bp.i0 + lane : -ASTR_IOFF + (lane & 7);
+    double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
     double* sSp = &sS[par][0][lane];
     double* sPp = &sP[par][0][lane];
 
@@ -215,15 +217,26 @@ __device__ __forceinline__ void role_loop(const Sweep2Args& a, const CUtensorMap
     auto put = [&](int node, double x) {
       if (node >= w_lo && node <= w_hi) {
         if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-        st_if(gout + (long long)node * (gl8 / 8), x, valid);
+        gout[(long long)node * (gl8 / 8)] = x;
       }
     };
-    if (role != ROLE_HEAD && plain) {
+    {
+      // rows of chunk 0 can only fall below the written range, rows of the last chunk only
+      // above it (the other end is at least one full chunk away)
       double* po = gout + (long long)node0 * (gl8 / 8);
-      chunk_back<ROLE_MID>(pl.reg, e, len, t_prev, h_next, [&](int s, double x) { st_if(row_ptr(po, gl8, s), x, valid); });
-    } else {
-      chunk_back<role == ROLE_HEAD ? ROLE_HEAD : ROLE_MID>(pl.reg, e, len, t_prev, h_next,
-                                                           [&](int s, double x) { put(node0 + s, x); });
+      const int s_lo = w_lo - node0, s_hi = w_hi - node0, z_lo = o_lo - node0, z_hi = o_hi - node0;
+      if (role == ROLE_MID || plain) {
+        chunk_back<role == ROLE_HEAD ? ROLE_HEAD : ROLE_MID>(pl.reg, e, len, t_prev, h_next,
+                                                             [&](int s, double x) { st_if(row_ptr(po, gl8, s), x, valid); });
+      } else if (role == ROLE_HEAD) {
+        chunk_back<ROLE_HEAD>(pl.reg, e, len, t_prev, h_next, [&](int s, double x) {
+          if (s >= s_lo) *row_ptr(po, gl8, s) = (epi == EPI_STOREZ && s < z_lo) ? 0.0 : x;
+        });
+      } else {
+        chunk_back<ROLE_MID>(pl.reg, e, len, t_prev, h_next, [&](int s, double x) {
+          if (s <= s_hi) *row_ptr(po, gl8, s) = (epi == EPI_STOREZ && s > z_hi) ? 0.0 : x;
+        });
+      }
     }
     if (role == ROLE_HEAD) {   // element 0: P(0) = Pm1, P'(1) = Pb0 of element 1
       double x[ASTR_SMAX];
