@@ -167,6 +167,7 @@ struct Ctx {
   cudaStream_t st = nullptr;
   bool have_metrics = false, have_grad = false;
   bool rhs_in_g = false;         // qrhs lives as three directional derivatives in the G slots
+  bool sigma_partial = false;    // sigma/qflux are in memory only on the face shells (fused rhscal)
   double force[3] = {0, 0, 0};
   // multi-block
   ncclComm_t comm = nullptr;
@@ -489,6 +490,11 @@ int astr_gpu_get_field(int field_id, double* host) {
     TRY(pw_materialise_grad(g->L, g->pool, g->scr, g->st));
   }
   if (s >= S_QRHS && s < S_QRHS + 5 && g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->st));
+  if (s >= S_SIGMA && s < S_SIGMA + 9 && g->sigma_partial) {
+    // the fused rhscal keeps the interior of sigma/qflux in registers: materialise on request
+    TRY(pw_visc(g->L, g->pool, g->th, g->st));
+    g->sigma_partial = false;
+  }
   TRY(copy_field(s, host, true));
   CUDA_OK(cudaStreamSynchronize(g->st));
   return 0;
@@ -629,15 +635,18 @@ int astr_gpu_rhscal(void) {
   if (!g->have_grad) return astr_fail_msg("rhscal before gradcal");
   const astr_cfg& c = g->cfg;
   const Layout& L = g->L;
+  FluxRanges fr = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
   if (c.diffterm) {
-    { ProfScope ps(PC_VISC); TRY(pw_visc(L, g->pool, g->th, g->st)); }
+    // viscous stress + flux assembly of the block in one pass (sigma/qflux stay in registers and
+    // reach memory only on the face shells the exchange reads), then the halo exchange
+    { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, g->st)); }
+    g->sigma_partial = true;
     TRY(dataswap(fields(S_SIGMA, 9), -1));         // sigma(6)+qflux(3), solver.F90:2604-2606
   }
-  FluxRanges fr = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
   {
     ProfScope ps(PC_FLUX);
     Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-    TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
+    if (!c.diffterm) TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
     for (int d = 0; d < 3; ++d)                    // halo slabs of direction d (fluxes on halo nodes,
       for (int side = 0; side < 2; ++side) {       // solver.F90:2200-2206)
         Box h = b;

@@ -29,14 +29,34 @@ __global__ void k_halo_wrap(const Layout L, const FieldList fl, const int mode) 
   // threads run over the two other indices (a fastest)
   const int na = (DIR == 0) ? L.jm + 1 : L.im + 1;
   const int nb = (DIR == 2) ? L.jm + 1 : L.km + 1;
+  double* f = fl.f[blockIdx.z];
+  if (DIR == 0) {
+    // i direction: the halo nodes of one row are contiguous -- 8 lanes per row (lane l < 5
+    // copies halo node l+1 of both sides), so a warp touches 4 rows x 40 bytes per access
+    // instead of 32 rows x 8 bytes
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = t >> 3, l = (t & 7) + 1;
+    const int b = blockIdx.y;
+    if (a >= na || b >= nb) return;
+    double* p = f + L.idx(0, a, b);
+    const int dm = L.im;
+    if (mode != XMODE_SYNC && l <= ASTR_HM) {
+      p[-l] = p[dm - l];
+      p[dm + l] = p[l];
+    }
+    if (mode != XMODE_SWAP && l == 8) {
+      const double v = 0.5 * (p[0] + p[dm]);
+      p[0] = v;
+      p[dm] = v;
+    }
+    return;
+  }
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (a >= na || b >= nb) return;
-  double* f = fl.f[blockIdx.z];
   long long base, sl;
   int dm;
-  if (DIR == 0) { base = L.idx(0, a, b); sl = 1; dm = L.im; }
-  else if (DIR == 1) { base = L.idx(a, 0, b); sl = L.sj; dm = L.jm; }
+  if (DIR == 1) { base = L.idx(a, 0, b); sl = L.sj; dm = L.jm; }
   else { base = L.idx(a, b, 0); sl = L.sk; dm = L.km; }
   double* p = f + base;
   if (mode != XMODE_SYNC) {
@@ -125,11 +145,8 @@ __global__ void k_materialise_grad(const Layout L, const double* __restrict__ po
 // viscous stress and heat flux, diffrsdcal6 pointwise part (src/solver.F90:2433-2602)
 // with miucal (src/fludyna.F90:791-812)
 // ---------------------------------------------------------------------------------
-__global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo th) {
-  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  int i, j, k;
-  if (!box_node(b, i, j, k)) return;
-  const long long fs = L.fstride, x = L.idx(i, j, k);
+__device__ __forceinline__ void visc_node(const double* __restrict__ pool, const long long fs, const long long x,
+                                          const Thermo& th, double (&sg)[6], double (&qf)[3]) {
   Grad g;
   load_grad(pool, fs, x, g);
   const double t = pool[S_TMP * fs + x];
@@ -143,22 +160,29 @@ __global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo t
   const double skk = (1.0 / 3.0) * (s11 + s22 + s33);
   const double miu2 = 2.0 * miu;
   const double hcc = (miu / th.prandtl) / th.const5;
-  const double sg1 = miu2 * (s11 - skk);
-  const double sg2 = miu2 * s12;
-  const double sg3 = miu2 * s13;
-  const double sg4 = miu2 * (s22 - skk);
-  const double sg5 = miu2 * s23;
-  const double sg6 = miu2 * (s33 - skk);
-  pool[(S_SIGMA + 0) * fs + x] = sg1;
-  pool[(S_SIGMA + 1) * fs + x] = sg2;
-  pool[(S_SIGMA + 2) * fs + x] = sg3;
-  pool[(S_SIGMA + 3) * fs + x] = sg4;
-  pool[(S_SIGMA + 4) * fs + x] = sg5;
-  pool[(S_SIGMA + 5) * fs + x] = sg6;
+  sg[0] = miu2 * (s11 - skk);
+  sg[1] = miu2 * s12;
+  sg[2] = miu2 * s13;
+  sg[3] = miu2 * (s22 - skk);
+  sg[4] = miu2 * s23;
+  sg[5] = miu2 * (s33 - skk);
   const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
-  pool[(S_QFLUX + 0) * fs + x] = hcc * g.dt[0] + sg1 * u + sg2 * v + sg3 * w;
-  pool[(S_QFLUX + 1) * fs + x] = hcc * g.dt[1] + sg2 * u + sg4 * v + sg5 * w;
-  pool[(S_QFLUX + 2) * fs + x] = hcc * g.dt[2] + sg3 * u + sg5 * v + sg6 * w;
+  qf[0] = hcc * g.dt[0] + sg[0] * u + sg[1] * v + sg[2] * w;
+  qf[1] = hcc * g.dt[1] + sg[1] * u + sg[3] * v + sg[4] * w;
+  qf[2] = hcc * g.dt[2] + sg[2] * u + sg[4] * v + sg[5] * w;
+}
+
+__global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo th) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  double sg[6], qf[3];
+  visc_node(pool, fs, x, th, sg, qf);
+#pragma unroll
+  for (int n = 0; n < 6; ++n) pool[(S_SIGMA + n) * fs + x] = sg[n];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) pool[(S_QFLUX + n) * fs + x] = qf[n];
 }
 
 // ---------------------------------------------------------------------------------
@@ -168,23 +192,14 @@ __global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo t
 // direction instead of 9.
 // ---------------------------------------------------------------------------------
 template <int DMASK>
-__global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, const FluxRanges fr,
-                       const int diffterm) {
-  int ijk[3];
-  if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
-  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+__device__ __forceinline__ void flux_node(double* __restrict__ pool, const long long fs, const long long x,
+                                          const int (&ijk)[3], const FluxRanges& fr, const int diffterm,
+                                          const double (&sg)[6], const double (&qf)[3]) {
   const double q0 = pool[(S_Q + 0) * fs + x], q1 = pool[(S_Q + 1) * fs + x], q2 = pool[(S_Q + 2) * fs + x],
                q3 = pool[(S_Q + 3) * fs + x], q4 = pool[(S_Q + 4) * fs + x];
   const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
   const double p = pool[S_PRS * fs + x];
   const double jac = pool[S_JAC * fs + x];
-  double sg[6] = {0, 0, 0, 0, 0, 0}, qf[3] = {0, 0, 0};
-  if (diffterm) {
-#pragma unroll
-    for (int n = 0; n < 6; ++n) sg[n] = pool[(S_SIGMA + n) * fs + x];
-#pragma unroll
-    for (int n = 0; n < 3; ++n) qf[n] = pool[(S_QFLUX + n) * fs + x];
-  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     if (!(DMASK & (1 << d))) continue;
@@ -216,6 +231,44 @@ __global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, c
     pool[(S_G + 5 * d + 3) * fs + x] = g3;
     pool[(S_G + 5 * d + 4) * fs + x] = g4;
   }
+}
+
+template <int DMASK>
+__global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, const FluxRanges fr,
+                       const int diffterm) {
+  int ijk[3];
+  if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  double sg[6] = {0, 0, 0, 0, 0, 0}, qf[3] = {0, 0, 0};
+  if (diffterm) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) sg[n] = pool[(S_SIGMA + n) * fs + x];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) qf[n] = pool[(S_QFLUX + n) * fs + x];
+  }
+  flux_node<DMASK>(pool, fs, x, ijk, fr, diffterm, sg, qf);
+}
+
+// Fused interior pass: sigma / qflux stay in registers between the viscous-stress evaluation and
+// the flux assembly of all three directions.  They are written to memory only on the shells
+// within ASTR_HM nodes of a block face, which is all the halo exchange (solver.F90:2604-2606)
+// and the halo-slab flux passes read.
+__global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const Thermo th, const FluxRanges fr) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int ijk[3];
+  if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  double sg[6], qf[3];
+  visc_node(pool, fs, x, th, sg, qf);
+  const bool shell = ijk[0] <= ASTR_HM || ijk[0] >= L.im - ASTR_HM || ijk[1] <= ASTR_HM || ijk[1] >= L.jm - ASTR_HM ||
+                     ijk[2] <= ASTR_HM || ijk[2] >= L.km - ASTR_HM;
+  if (shell) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) pool[(S_SIGMA + n) * fs + x] = sg[n];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) pool[(S_QFLUX + n) * fs + x] = qf[n];
+  }
+  flux_node<7>(pool, fs, x, ijk, fr, 1, sg, qf);
 }
 
 // ---------------------------------------------------------------------------------
@@ -363,7 +416,7 @@ int pw_halo_wrap(const Layout& L, const FieldList& fl, int dir, int mode, cudaSt
   const int na = (dir == 0) ? L.jm + 1 : L.im + 1;
   const int nb = (dir == 2) ? L.jm + 1 : L.km + 1;
   dim3 grid((na + PW_T - 1) / PW_T, nb, fl.nf);
-  if (dir == 0) k_halo_wrap<0><<<grid, PW_T, 0, st>>>(L, fl, mode);
+  if (dir == 0) { grid.x = (na * 8 + PW_T - 1) / PW_T; k_halo_wrap<0><<<grid, PW_T, 0, st>>>(L, fl, mode); }
   else if (dir == 1) k_halo_wrap<1><<<grid, PW_T, 0, st>>>(L, fl, mode);
   else k_halo_wrap<2><<<grid, PW_T, 0, st>>>(L, fl, mode);
   LAUNCH_CHECK();
@@ -380,6 +433,13 @@ int pw_q2fvar(const Layout& L, double* pool, const Thermo& th, const Box& b, cud
 int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   k_visc<<<box_grid(b), PW_T, 0, st>>>(L, pool, th);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_visc_flux<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);
   LAUNCH_CHECK();
   return 0;
 }
