@@ -169,6 +169,10 @@ struct Ctx {
   bool rhs_in_g = false;         // qrhs lives as three directional derivatives in the G slots
   bool sigma_partial = false;    // sigma/qflux are in memory only on the face shells (fused rhscal)
   double force[3] = {0, 0, 0};
+  double* ycoord = nullptr;      // x(:,:,:,2) for src_chan (flowtype channel only)
+  double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
+  bool src_pending = false;      // src_chan's term is not in the G slots: consumers add d_src+4
+  const double* src() const { return src_pending ? d_src + 4 : nullptr; }
   // multi-block
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
@@ -320,6 +324,7 @@ static int sweep(int d, int optype, const double* const* in, double* const* out,
   a.nf = nf;
   for (int i = 0; i < nf; ++i) { a.in[i] = in[i]; a.out[i] = out[i]; }
   a.epi = epi; a.o_lo = o_lo; a.o_hi = o_hi;
+  if (optype == OP_DERIV && !g->cfg.scheme_compact) return pw_diff6e(d, a, g->st);   // difschm '...e'
   if (!g->legacy_sweep) {
     const HostOp& h = (optype == OP_DERIV ? g->fd[d] : g->fl[d]);
     const int rc = astr_launch_sweep2(d, optype, h.plan, a, g->st);
@@ -350,9 +355,13 @@ int astr_gpu_init(const astr_cfg* cfg) {
   if (cfg->abi_version != ASTR_GPU_ABI_VERSION) return astr_fail_msg("abi_version mismatch");
   if (cfg->hm != ASTR_HM || cfg->numq != ASTR_GPU_NUMQ) return astr_fail_msg("hm must be 5 and numq 5");
   if (cfg->ndims != 3 || cfg->km < 1) return astr_fail_msg("only ndims=3 blocks are implemented");
+  for (int n = 0; n < 6; ++n)
+    if (cfg->bctype[n] != 1 && cfg->bctype[n] != 41)
+      return astr_fail_msg("bctype must be 1 (periodic) or 41 (isothermal no-slip wall)");
   if (!cfg->nondimen) return astr_fail_msg("only nondimen=t is implemented");
-  if (!cfg->scheme_compact || cfg->conschm != 643 || cfg->difschm != 643)
-    return astr_fail_msg("only conschm=difschm=643c (central compact) is implemented");
+  // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
+  if (cfg->conschm != cfg->difschm || !(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
+    return astr_fail_msg("only conschm=difschm=643c (central compact) or 6xxe (central explicit) are implemented");
   if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
   for (int d = 0; d < 3; ++d)
     if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
@@ -379,8 +388,9 @@ int astr_gpu_init(const astr_cfg* cfg) {
   CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
   TRY(astr_sweep2_register_pool(0, g->pool, S_CORE, g->L));
   TRY(astr_sweep2_register_pool(1, nullptr, 0, g->L));
-  CUDA_OK(cudaMalloc(&g->d_partial, (size_t)2 * (cfg->jm + 1) * (cfg->km + 1) * sizeof(double)));
+  CUDA_OK(cudaMalloc(&g->d_partial, (size_t)4 * (cfg->jm + 1) * (cfg->km + 1) * sizeof(double)));
   CUDA_OK(cudaMalloc(&g->d_out2, 4 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&g->d_src, 8 * sizeof(double)));
   build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
   TRY(astr_set_filter_coef(g->fc));
   { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
@@ -415,7 +425,8 @@ int astr_gpu_finalize(void) {
   for (int d = 0; d < 3; ++d) { cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab); }
   astr_sweep2_register_pool(0, nullptr, 0, g->L); astr_sweep2_register_pool(1, nullptr, 0, g->L);
   cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
-  cudaFree(g->d_partial); cudaFree(g->d_out2);
+  cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
+  if (g->ycoord) cudaFree(g->ycoord);
   cudaStreamDestroy(g->st);
   delete g;
   g = nullptr;
@@ -489,7 +500,7 @@ int astr_gpu_get_field(int field_id, double* host) {
     if (!g->have_grad) return astr_fail_msg("dvel/dtmp/vor requested before gradcal");
     TRY(pw_materialise_grad(g->L, g->pool, g->scr, g->st));
   }
-  if (s >= S_QRHS && s < S_QRHS + 5 && g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->st));
+  if (s >= S_QRHS && s < S_QRHS + 5 && g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->src(), g->st));
   if (s >= S_SIGMA && s < S_SIGMA + 9 && g->sigma_partial) {
     // the fused rhscal keeps the interior of sigma/qflux in registers: materialise on request
     TRY(pw_visc(g->L, g->pool, g->th, g->st));
@@ -506,8 +517,9 @@ int astr_gpu_set_field(int field_id, const double* host) {
   TRY(api_slot(field_id, &s));
   if (s >= S_SCR) return astr_fail_msg("dvel/dtmp/vor are derived fields");
   if (s >= S_QRHS && s < S_QRHS + 5) {
-    if (g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->st));
+    if (g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->src(), g->st));
     g->rhs_in_g = false;   // the caller now owns qrhs as an array
+    g->src_pending = false;
   }
   TRY(copy_field(s, const_cast<double*>(host), false));
   CUDA_OK(cudaStreamSynchronize(g->st));
@@ -538,11 +550,33 @@ int astr_gpu_set_metrics(const double* dxi, const double* jacob) {
   return 0;
 }
 
+// src_chan integrates in y (src/solver.F90:321): the channel case keeps x(:,:,:,2) resident
+static int keep_ycoord(const double* dev_field) {
+  const size_t bytes = (size_t)g->L.fstride * sizeof(double);
+  if (!g->ycoord) CUDA_OK(cudaMalloc(&g->ycoord, bytes));
+  CUDA_OK(cudaMemcpyAsync(g->ycoord, dev_field, bytes, cudaMemcpyDeviceToDevice, g->st));
+  return 0;
+}
+
+int astr_gpu_set_grid(const double* x) {
+  NEED_CTX();
+  if (g->cfg.flowtype != 1) return 0;   // only src_chan reads coordinates
+  const size_t bytes = (size_t)g->L.fstride * sizeof(double);
+  if (!g->ycoord) { CUDA_OK(cudaMalloc(&g->ycoord, bytes)); CUDA_OK(cudaMemsetAsync(g->ycoord, 0, bytes, g->st)); }
+  const Layout& L = g->L;
+  const size_t w = (size_t)(L.im + 1 + 2 * ASTR_HM) * sizeof(double);
+  CUDA_OK(cudaMemcpy2DAsync(g->ycoord + (ASTR_IOFF - ASTR_HM), (size_t)L.pitch * sizeof(double),
+                            x + host_field_elems(), w, w, (size_t)L.njt * L.nkt, cudaMemcpyHostToDevice, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
 int astr_gpu_gridgeom(const double* x) {
   NEED_CTX();
   TRY(ensure_scratch());
   const size_t ne = host_field_elems();
   for (int m = 0; m < 3; ++m) TRY(copy_field(S_G + m, const_cast<double*>(x) + (size_t)m * ne, false));
+  if (g->cfg.flowtype == 1) TRY(keep_ycoord(g->slot(S_G + 1)));
   TRY(geom_gridgeom(g->L, g->cfg, g->st));
   CUDA_OK(cudaStreamSynchronize(g->st));
   g->have_metrics = true;
@@ -589,6 +623,41 @@ int astr_gpu_filterq(void) {
     ProfScope ps(PC_FILTER_I + d);
     TRY(sweep(d, OP_FILTER, fq.f, fq.f, 5, EPI_STORE, o_lo, o_hi));
   }
+  return 0;
+}
+
+// boucon (src/bc.F90:327-407): faces n=1..6 in order; a face is treated only by the ranks that
+// own it (irk==0 / irk==irkm etc.)
+int astr_gpu_boucon(void) {
+  NEED_CTX();
+  const astr_cfg& c = g->cfg;
+  for (int n = 0; n < 6; ++n) {
+    const int bt = c.bctype[n], d = n / 2, side = n % 2;
+    if (bt == 1) continue;
+    const bool mine = side ? (c.rank[d] == c.size[d] - 1) : (c.rank[d] == 0);
+    if (bt == 41) {                                   // noslip(n,twall(n)), bc.F90:6306
+      if (!mine) continue;
+      ProfScope ps(PC_HALO);
+      TRY(pw_noslip(g->L, g->pool, g->th, d, side, c.twall[n], g->st));
+    } else {
+      return astr_fail_msg("boucon: only bctype 1 (periodic) and 41 (isothermal no-slip wall) run on the device");
+    }
+  }
+  return 0;
+}
+
+// src_chan (src/solver.F90:295-353): bulk integrals -> psum -> (force, force.ubulk) on the device;
+// the term itself is added where qrhs is consumed (RK update / qrhs materialisation)
+static int src_chan() {
+  if (!g->ycoord) return astr_fail_msg("src_chan needs node coordinates: call astr_gpu_set_grid or astr_gpu_gridgeom");
+  ProfScope ps(PC_FLUX);
+  TRY(pw_bulk(g->L, g->pool, g->ycoord, g->d_partial, g->d_src, g->st));
+  if (g->cfg.size[0] * g->cfg.size[1] * g->cfg.size[2] > 1) {
+    if (!g->comm) return astr_fail_msg("src_chan psum needs astr_gpu_comm_init");
+    NCCL_OK(g_nccl.AllReduce(g->d_src, g->d_src, 4, ncclDouble, ncclSum, g->comm, g->st));
+  }
+  TRY(pw_src_coef(g->d_src, g->force, g->d_src + 4, g->st));
+  g->src_pending = true;
   return 0;
 }
 
@@ -655,9 +724,22 @@ int astr_gpu_rhscal(void) {
         TRY(pw_flux(L, g->pool, h, 1 << d, fr, c.diffterm, g->st));
       }
   }
+  const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
+  if (!c.scheme_compact) {
+    // explicit stencils cannot run in place: accumulate the three directions into qrhs
+    for (int d = 0; d < 3; ++d) {
+      const double* in[5]; double* out[5];
+      for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_QRHS + m); }
+      ProfScope ps(PC_DIV_I + d);
+      TRY(sweep(d, OP_DERIV, in, out, 5, d == 0 ? EPI_STOREZ : EPI_ADD, s[d], e[d]));
+    }
+    g->rhs_in_g = false;
+    g->src_pending = false;
+    if (c.flowtype == 1) { TRY(src_chan()); TRY(pw_add_force(g->L, g->pool, g->src(), g->st)); g->src_pending = false; }
+    return 0;
+  }
   // d(G_d)/d(xi_d) in place (zero outside is:ie etc., where the reference does not accumulate);
   // the three directions are summed by the RK update kernel: no read-modify-write of qrhs
-  const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
   for (int d = 0; d < 3; ++d) {
     const double* in[5]; double* out[5];
     for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_G + 5 * d + m); }
@@ -665,7 +747,8 @@ int astr_gpu_rhscal(void) {
     TRY(sweep(d, OP_DERIV, in, out, 5, EPI_STOREZ, s[d], e[d]));
   }
   g->rhs_in_g = true;
-  if (c.flowtype == 1) return astr_fail_msg("src_chan forcing is not implemented yet");
+  g->src_pending = false;
+  if (c.flowtype == 1) TRY(src_chan());             // solver.F90:262
   return 0;
 }
 
@@ -685,7 +768,7 @@ int astr_gpu_rk_update(int rkstep, double deltat) {
   TRY(rk_coef(rkstep, deltat, rk));
   rk.with_fvar = 0;
   ProfScope ps(PC_RK);
-  return pw_rk_update(g->L, g->pool, g->th, rk, nullptr, g->st);
+  return pw_rk_update(g->L, g->pool, g->th, rk, g->src(), g->st);
 }
 
 int astr_gpu_updatefvar(void) {
@@ -698,6 +781,7 @@ int astr_gpu_updatefvar(void) {
 int astr_gpu_rk_stage(int rkstep, double deltat) {
   NEED_CTX();
   if (g->cfg.lfilter) TRY(astr_gpu_filterq());
+  TRY(astr_gpu_boucon());
   TRY(astr_gpu_qswap());
   TRY(astr_gpu_gradcal());
   TRY(astr_gpu_rhscal());
@@ -705,7 +789,7 @@ int astr_gpu_rk_stage(int rkstep, double deltat) {
   TRY(rk_coef(rkstep, deltat, rk));
   rk.with_fvar = 1;
   ProfScope ps(PC_RK);
-  return pw_rk_update(g->L, g->pool, g->th, rk, nullptr, g->st);
+  return pw_rk_update(g->L, g->pool, g->th, rk, g->src(), g->st);
 }
 
 int astr_gpu_rk_steps(int nsteps, double deltat) {

@@ -274,7 +274,8 @@ __global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const The
 // ---------------------------------------------------------------------------------
 // RK3-TVD update (src/mainloop.F90:427-476) fused with updatefvar (src/fludyna.F90:191)
 // ---------------------------------------------------------------------------------
-__global__ void k_rk_update(const Layout L, double* __restrict__ pool, const Thermo th, const RkCoef rk) {
+__global__ void k_rk_update(const Layout L, double* __restrict__ pool, const Thermo th, const RkCoef rk,
+                            const double* __restrict__ src) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   int i, j, k;
   if (!box_node(b, i, j, k)) return;
@@ -296,6 +297,8 @@ __global__ void k_rk_update(const Layout L, double* __restrict__ pool, const The
       rhs = pool[(S_G + m) * fs + x] + pool[(S_G + 5 + m) * fs + x] + pool[(S_G + 10 + m) * fs + x];
     else
       rhs = pool[(S_QRHS + m) * fs + x];
+    // src_chan (src/solver.F90:341-352), still pending when qrhs lives in the G slots
+    if (src != nullptr && m > 0) rhs = rhs + src[m - 1] * jac;
     const double vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * rhs * rk.dt;
     pool[(S_Q + m) * fs + x] = vv / jac;
   }
@@ -303,30 +306,147 @@ __global__ void k_rk_update(const Layout L, double* __restrict__ pool, const The
 }
 
 // qrhs(0:im,0:jm,0:km,:) as an array of its own (staged API / tests / source terms)
-__global__ void k_sum_qrhs(const Layout L, double* __restrict__ pool) {
-  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  int i, j, k;
-  if (!box_node(b, i, j, k)) return;
-  const long long fs = L.fstride, x = L.idx(i, j, k);
-#pragma unroll
-  for (int m = 0; m < 5; ++m)
-    pool[(S_QRHS + m) * fs + x] =
-        pool[(S_G + m) * fs + x] + pool[(S_G + 5 + m) * fs + x] + pool[(S_G + 10 + m) * fs + x];
-}
-
-// src_chan body force (src/solver.F90:341-352): qrhs(2:4)+=force*jacob,
-// qrhs(5)+=(force.ubulk)*jacob on all nodes 0..im,0..jm,0..km ; fe = force.ubulk
-__global__ void k_add_force(const Layout L, double* __restrict__ pool, const double f0, const double f1,
-                            const double f2, const double fe) {
+__global__ void k_sum_qrhs(const Layout L, double* __restrict__ pool, const double* __restrict__ src) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   int i, j, k;
   if (!box_node(b, i, j, k)) return;
   const long long fs = L.fstride, x = L.idx(i, j, k);
   const double jac = pool[S_JAC * fs + x];
-  pool[(S_QRHS + 1) * fs + x] = pool[(S_QRHS + 1) * fs + x] + f0 * jac;
-  pool[(S_QRHS + 2) * fs + x] = pool[(S_QRHS + 2) * fs + x] + f1 * jac;
-  pool[(S_QRHS + 3) * fs + x] = pool[(S_QRHS + 3) * fs + x] + f2 * jac;
-  pool[(S_QRHS + 4) * fs + x] = pool[(S_QRHS + 4) * fs + x] + fe * jac;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    double rhs = pool[(S_G + m) * fs + x] + pool[(S_G + 5 + m) * fs + x] + pool[(S_G + 10 + m) * fs + x];
+    if (src != nullptr && m > 0) rhs = rhs + src[m - 1] * jac;
+    pool[(S_QRHS + m) * fs + x] = rhs;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// src_chan bulk integrals (src/solver.F90:317-339): trapezoidal rule in y of q(1:4) over
+// nodes 1..im,1..jm,1..km; one CTA per (j,k) row, fixed-order tree => deterministic.
+// yc = x(:,:,:,2) in the common Layout.
+// ---------------------------------------------------------------------------------
+__global__ void k_bulk_rows(const Layout L, const double* __restrict__ pool, const double* __restrict__ yc,
+                            double* __restrict__ partial) {
+  const int j = 1 + blockIdx.x, k = 1 + blockIdx.y;
+  const long long fs = L.fstride;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 1 + threadIdx.x; i <= L.im; i += PW_T) {
+    const long long x = L.idx(i, j, k), xm = x - L.sj;
+    const double dy = yc[x] - yc[xm];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] += 0.5 * (pool[(S_Q + m) * fs + xm] + pool[(S_Q + m) * fs + x]) * dy;
+  }
+  __shared__ double s[4][PW_T];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) s[m][threadIdx.x] = a[m];
+  __syncthreads();
+  for (int h = PW_T / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s[m][threadIdx.x] += s[m][threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) {
+    const long long row = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+    partial[4 * row + threadIdx.x] = s[threadIdx.x][0];
+  }
+}
+__global__ void k_bulk_final(const double* __restrict__ partial, const long long nrows, double* __restrict__ out4) {
+  __shared__ double s[4][256];
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long r = threadIdx.x; r < nrows; r += 256)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] += partial[4 * r + m];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) s[m][threadIdx.x] = a[m];
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s[m][threadIdx.x] += s[m][threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out4[threadIdx.x] = s[threadIdx.x][0];
+}
+// bulk4 = psum'ed (robulk, rho*u1 .., rho*u3 integrals) -> src4 = (force, force.ubulk)  (:336-339,:349)
+__global__ void k_src_coef(const double* __restrict__ bulk4, const double f0, const double f1, const double f2,
+                           double* __restrict__ src4) {
+  const double u1 = bulk4[1] / bulk4[0], u2 = bulk4[2] / bulk4[0], u3 = bulk4[3] / bulk4[0];
+  src4[0] = f0; src4[1] = f1; src4[2] = f2;
+  src4[3] = f0 * u1 + f1 * u2 + f2 * u3;
+}
+
+// ---------------------------------------------------------------------------------
+// explicit_central -> diff6ec (src/derivative.F90:319-413): explicit 6th-order first
+// derivative with the 2-4 boundary closure on physical-boundary ends (ntype 1/2/4).
+// One thread per node, i fastest; neighbours along j/k come from L1/L2 (a plane of a
+// 512^3 field is 2 MB).  Out of place only (in != out).
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_diff6e(const Layout L, const SweepArgs a) {
+  const int i = blockIdx.x * PW_T + threadIdx.x;
+  const int j = blockIdx.y;
+  const int nk = L.km + 1;
+  const int k = blockIdx.z % nk, f = blockIdx.z / nk;
+  if (i > L.im) return;
+  const int l = (DIR == 0) ? i : (DIR == 1 ? j : k);
+  const bool inside = (l >= a.o_lo && l <= a.o_hi);
+  if (!inside && a.epi != EPI_STOREZ) return;
+  const long long x = L.idx(i, j, k);
+  double* __restrict__ out = a.out[f];
+  if (!inside) { out[x] = 0.0; return; }
+  const double* __restrict__ v = a.in[f] + x;
+  const long long s = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk);
+  const int n = a.op.n, nt = a.op.ntype;
+  const bool lo = (nt == 1 || nt == 4), hi = (nt == 2 || nt == 4);
+  double d;
+  if (lo && l == 0) d = -0.5 * v[2 * s] + 2.0 * v[s] - 1.5 * v[0];
+  else if (lo && l == 1) d = 0.5 * (v[s] - v[-s]);
+  else if (lo && l == 2) d = (2.0 / 3.0) * (v[s] - v[-s]) - (1.0 / 12.0) * (v[2 * s] - v[-2 * s]);
+  else if (hi && l == n) d = 0.5 * v[-2 * s] - 2.0 * v[-s] + 1.5 * v[0];
+  else if (hi && l == n - 1) d = 0.5 * (v[s] - v[-s]);
+  else if (hi && l == n - 2) d = (2.0 / 3.0) * (v[s] - v[-s]) - (1.0 / 12.0) * (v[2 * s] - v[-2 * s]);
+  else d = 0.75 * (v[s] - v[-s]) - 0.15 * (v[2 * s] - v[-2 * s]) + (1.0 / 60.0) * (v[3 * s] - v[-3 * s]);
+  out[x] = (a.epi == EPI_ADD) ? out[x] + d : d;
+}
+
+// ---------------------------------------------------------------------------------
+// noslip(ndir,tw) (src/bc.F90:6306-6723; nondimen, no species, turbmode none, no wall
+// blowing): on the face node u=0, T=tw, p=(4 p1 - p2)/3 from the two interior neighbours,
+// rho=thermal(p,T) (fludyna.F90:60), q=fvar2q(rho,vel,p) (fludyna.F90:312-376).
+// Threads run over the two other indices (a fastest).
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_noslip(const Layout L, double* __restrict__ pool, const Thermo th, const int side, const double tw) {
+  const int na = (DIR == 0) ? L.jm + 1 : L.im + 1;
+  const int a = blockIdx.x * PW_T + threadIdx.x, b = blockIdx.y;
+  if (a >= na) return;
+  const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
+  const int l = side ? dm : 0;
+  const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk), sg = side ? -sd : sd;
+  const long long x = (DIR == 0) ? L.idx(l, a, b) : (DIR == 1 ? L.idx(a, l, b) : L.idx(a, b, l));
+  const long long fs = L.fstride;
+  const double pe = (1.0 / 3.0) * (4.0 * pool[S_PRS * fs + x + sg] - pool[S_PRS * fs + x + 2 * sg]);
+  const double rho = pe / tw * th.const2;
+  pool[(S_VEL + 0) * fs + x] = 0.0; pool[(S_VEL + 1) * fs + x] = 0.0; pool[(S_VEL + 2) * fs + x] = 0.0;
+  pool[S_PRS * fs + x] = pe;
+  pool[S_TMP * fs + x] = tw;
+  pool[S_RHO * fs + x] = rho;
+  pool[(S_Q + 0) * fs + x] = rho;
+  pool[(S_Q + 1) * fs + x] = 0.0; pool[(S_Q + 2) * fs + x] = 0.0; pool[(S_Q + 3) * fs + x] = 0.0;
+  pool[(S_Q + 4) * fs + x] = pe * th.const6;
+}
+
+// src_chan body force (src/solver.F90:341-352): qrhs(2:4)+=force*jacob,
+// qrhs(5)+=(force.ubulk)*jacob on all nodes 0..im,0..jm,0..km ; fe = force.ubulk
+__global__ void k_add_force(const Layout L, double* __restrict__ pool, const double* __restrict__ src) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double jac = pool[S_JAC * fs + x];
+#pragma unroll
+  for (int m = 1; m < 5; ++m) pool[(S_QRHS + m) * fs + x] = pool[(S_QRHS + m) * fs + x] + src[m - 1] * jac;
 }
 
 // ---------------------------------------------------------------------------------
@@ -467,24 +587,60 @@ int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRa
   return 0;
 }
 
-int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double*,
+int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* src,
                  cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  k_rk_update<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, rk);
+  k_rk_update<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, rk, src);
   LAUNCH_CHECK();
   return 0;
 }
 
-int pw_sum_qrhs(const Layout& L, double* pool, cudaStream_t st) {
+int pw_sum_qrhs(const Layout& L, double* pool, const double* src, cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  k_sum_qrhs<<<box_grid(b), PW_T, 0, st>>>(L, pool);
+  k_sum_qrhs<<<box_grid(b), PW_T, 0, st>>>(L, pool, src);
   LAUNCH_CHECK();
   return 0;
 }
 
-int pw_add_force(const Layout& L, double* pool, const double force[3], double fe, cudaStream_t st) {
+int pw_bulk(const Layout& L, const double* pool, const double* yc, double* partial, double* out4, cudaStream_t st) {
+  dim3 grid(L.jm, L.km);
+  k_bulk_rows<<<grid, PW_T, 0, st>>>(L, pool, yc, partial);
+  LAUNCH_CHECK();
+  k_bulk_final<<<1, 256, 0, st>>>(partial, (long long)L.jm * L.km, out4);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_src_coef(const double* bulk4, const double force[3], double* src4, cudaStream_t st) {
+  k_src_coef<<<1, 1, 0, st>>>(bulk4, force[0], force[1], force[2], src4);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st) {
+  const Layout& L = a.L;
+  for (int f = 0; f < a.nf; ++f)
+    if (a.in[f] == a.out[f]) return astr_fail_msg("explicit derivative cannot run in place");
+  dim3 grid((L.im + PW_T) / PW_T, L.jm + 1, (L.km + 1) * a.nf);
+  if (dir == 0) k_diff6e<0><<<grid, PW_T, 0, st>>>(L, a);
+  else if (dir == 1) k_diff6e<1><<<grid, PW_T, 0, st>>>(L, a);
+  else k_diff6e<2><<<grid, PW_T, 0, st>>>(L, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side, double tw, cudaStream_t st) {
+  const int na = (dir == 0) ? L.jm + 1 : L.im + 1, nb = (dir == 2) ? L.jm + 1 : L.km + 1;
+  dim3 grid((na + PW_T - 1) / PW_T, nb);
+  if (dir == 0) k_noslip<0><<<grid, PW_T, 0, st>>>(L, pool, th, side, tw);
+  else if (dir == 1) k_noslip<1><<<grid, PW_T, 0, st>>>(L, pool, th, side, tw);
+  else k_noslip<2><<<grid, PW_T, 0, st>>>(L, pool, th, side, tw);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_add_force(const Layout& L, double* pool, const double* src, cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  k_add_force<<<box_grid(b), PW_T, 0, st>>>(L, pool, force[0], force[1], force[2], fe);
+  k_add_force<<<box_grid(b), PW_T, 0, st>>>(L, pool, src);
   LAUNCH_CHECK();
   return 0;
 }

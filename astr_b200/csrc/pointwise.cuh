@@ -43,10 +43,16 @@ int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRang
 int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
             cudaStream_t st);
 struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; };
-int pw_sum_qrhs(const Layout& L, double* pool, cudaStream_t st);
-int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* force,
+// src: device (force(1:3), force.ubulk) of src_chan still to be added, or nullptr
+int pw_sum_qrhs(const Layout& L, double* pool, const double* src, cudaStream_t st);
+int pw_bulk(const Layout& L, const double* pool, const double* yc, double* partial, double* out4, cudaStream_t st);
+int pw_src_coef(const double* bulk4, const double force[3], double* src4, cudaStream_t st);
+// explicit_central (diff6ec, src/derivative.F90:350-413); a.op.n / a.op.ntype describe the line
+int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st);
+int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side, double tw, cudaStream_t st);
+int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* src,
                  cudaStream_t st);
-int pw_add_force(const Layout& L, double* pool, const double force[3], double fe, cudaStream_t st);
+int pw_add_force(const Layout& L, double* pool, const double* src /*device (force, force.ubulk)*/, cudaStream_t st);
 int pw_stats(const Layout& L, double* pool, double* partial /*2*(jm)*(km)*/, double* out2, cudaStream_t st);
 // face pack / unpack for the multi-block exchange (src/parallel.F90:4180-4218)
 int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,

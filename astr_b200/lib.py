@@ -30,9 +30,9 @@ SYMBOLS = [
     "astr_gpu_init", "astr_gpu_sizeof_cfg", "astr_gpu_finalize", "astr_gpu_last_error", "astr_gpu_synchronize",
     "astr_gpu_comm_unique_id", "astr_gpu_comm_init", "astr_gpu_set_metrics", "astr_gpu_gridgeom",
     "astr_gpu_upload_state", "astr_gpu_download_state", "astr_gpu_get_field", "astr_gpu_set_field",
-    "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
+    "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_boucon", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
     "astr_gpu_rk_update", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps", "astr_gpu_rk_steps_timed",
-    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_reduce_tgv", "astr_gpu_kernel_launches",
+    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_kernel_launches",
     "astr_gpu_set_profile", "astr_gpu_get_profile", "astr_gpu_bench_sweep",
 ]
 
@@ -58,7 +58,7 @@ class AstrCfg(ctypes.Structure):
         ("nbr", ctypes.c_int * 6), ("my_rank", ctypes.c_int),
         ("conschm", ctypes.c_int), ("difschm", ctypes.c_int), ("scheme_compact", ctypes.c_int),
         ("rkscheme", ctypes.c_int), ("lfilter", ctypes.c_int), ("diffterm", ctypes.c_int),
-        ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int),
+        ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int), ("bctype", ctypes.c_int * 6),
         ("alfa_filter", ctypes.c_double),
         ("reynolds", ctypes.c_double), ("mach", ctypes.c_double), ("prandtl", ctypes.c_double),
         ("gamma", ctypes.c_double), ("ref_tem", ctypes.c_double),
@@ -66,7 +66,7 @@ class AstrCfg(ctypes.Structure):
         ("const4", ctypes.c_double), ("const5", ctypes.c_double), ("const6", ctypes.c_double),
         ("const7", ctypes.c_double),
         ("tempconst", ctypes.c_double), ("tempconst1", ctypes.c_double),
-        ("deltat", ctypes.c_double),
+        ("deltat", ctypes.c_double), ("twall", ctypes.c_double * 6),
     ]
 
 
@@ -117,6 +117,7 @@ def load() -> ctypes.CDLL:
     L.astr_gpu_rk_steps_timed.argtypes = [ci, cd, ctypes.POINTER(ctypes.c_float)]
     L.astr_gpu_dataswap.argtypes = [ci, ci]
     L.astr_gpu_set_force.argtypes = [vp]
+    L.astr_gpu_set_grid.argtypes = [vp]
     L.astr_gpu_reduce_tgv.argtypes = [vp]
     L.astr_gpu_kernel_launches.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     L.astr_gpu_set_profile.argtypes = [ci]

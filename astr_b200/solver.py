@@ -43,14 +43,15 @@ class RhsEngine:
 
     def __init__(self, block: Block, global_dims: Sequence[int], homo: Sequence[bool], thermo: Dict[str, float],
                  deltat: float = 1e-3, alfa_filter: float = 0.49, lfilter: bool = True, diffterm: bool = True,
-                 device: int = -1, flowtype: int = 0):
+                 device: int = -1, flowtype: int = 0, bctype: Sequence[int] = (1,) * 6,
+                 twall: Sequence[float] = (0.0,) * 6, explicit: bool = False):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
         self.thermo = thermo
         self._lib = _l.load()
         c = _l.AstrCfg()
-        c.abi_version = 1
+        c.abi_version = 2
         c.device = device
         c.im, c.jm, c.km = block.dims
         c.ia, c.ja, c.ka = global_dims
@@ -63,8 +64,11 @@ class RhsEngine:
         c.size[:] = block.size
         c.nbr[:] = block.nbr
         c.my_rank = block.rank
-        c.conschm, c.difschm, c.scheme_compact, c.rkscheme = 643, 643, 1, 3
+        # conschm/difschm '643c' (compact_central) or '642e' (explicit_central), comsolver.F90:76-84
+        c.conschm, c.difschm, c.scheme_compact, c.rkscheme = (642, 642, 0, 3) if explicit else (643, 643, 1, 3)
         c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), 1, flowtype
+        c.bctype[:] = [int(b) for b in bctype]
+        c.twall[:] = [float(t) for t in twall]
         c.alfa_filter = alfa_filter
         for k, v in thermo.items():
             setattr(c, k, v)
@@ -112,6 +116,15 @@ class RhsEngine:
         assert x.shape == self.shape + (3,)
         _l.check(self._lib.astr_gpu_gridgeom(self._ptr(np.asfortranarray(x))))
 
+    def set_grid(self, x: np.ndarray):
+        """Node coordinates x(-hm:im+hm,...,3) for src_chan's y integration (channel only)."""
+        assert x.shape == self.shape + (3,)
+        _l.check(self._lib.astr_gpu_set_grid(self._ptr(np.asfortranarray(x))))
+
+    def set_force(self, force: Sequence[float]):
+        f = (ctypes.c_double * 3)(*[float(v) for v in force])
+        _l.check(self._lib.astr_gpu_set_force(f))
+
     def upload_state(self, q=None, rho=None, vel=None, prs=None, tmp=None):
         _l.check(self._lib.astr_gpu_upload_state(*[self._ptr(a) for a in (q, rho, vel, prs, tmp)]))
 
@@ -131,6 +144,9 @@ class RhsEngine:
     # ---- stage operators --------------------------------------------------------------------
     def filterq(self):
         _l.check(self._lib.astr_gpu_filterq())
+
+    def boucon(self):
+        _l.check(self._lib.astr_gpu_boucon())
 
     def qswap(self):
         _l.check(self._lib.astr_gpu_qswap())

@@ -12,7 +12,7 @@ module astr_gpu_mod
   !
   implicit none
   !
-  integer(c_int), parameter :: astr_gpu_abi_version=1
+  integer(c_int), parameter :: astr_gpu_abi_version=2
   !
   ! struct astr_cfg of include/astr_gpu.h -- same order, same types
   type, bind(c) :: astr_cfg
@@ -29,11 +29,13 @@ module astr_gpu_mod
     integer(c_int) :: my_rank
     integer(c_int) :: conschm,difschm,scheme_compact,rkscheme
     integer(c_int) :: lfilter,diffterm,nondimen,flowtype
+    integer(c_int) :: bctype(6)
     real(c_double) :: alfa_filter
     real(c_double) :: reynolds,mach,prandtl,gamma,ref_tem
     real(c_double) :: const1,const2,const3,const4,const5,const6,const7
     real(c_double) :: tempconst,tempconst1
     real(c_double) :: deltat
+    real(c_double) :: twall(6)
   end type astr_cfg
   !
   interface
@@ -70,6 +72,10 @@ module astr_gpu_mod
       import :: c_int, c_double
       real(c_double), intent(in) :: x(*)
     end function
+    integer(c_int) function astr_gpu_set_grid(x) bind(c,name='astr_gpu_set_grid')
+      import :: c_int, c_double
+      real(c_double), intent(in) :: x(*)
+    end function
     integer(c_int) function astr_gpu_upload_state(q,rho,vel,prs,tmp) bind(c,name='astr_gpu_upload_state')
       import :: c_int, c_double
       real(c_double), intent(in) :: q(*),rho(*),vel(*),prs(*),tmp(*)
@@ -89,6 +95,9 @@ module astr_gpu_mod
       real(c_double), intent(in) :: host(*)
     end function
     integer(c_int) function astr_gpu_filterq() bind(c,name='astr_gpu_filterq')
+      import :: c_int
+    end function
+    integer(c_int) function astr_gpu_boucon() bind(c,name='astr_gpu_boucon')
       import :: c_int
     end function
     integer(c_int) function astr_gpu_qswap() bind(c,name='astr_gpu_qswap')
@@ -162,7 +171,11 @@ module astr_gpu_mod
                            lihomo,ljhomo,lkhomo,irk,jrk,krk,isize,jsize,ksize,     &
                            nbr,mpirank,lfilter,diffterm,alfa_filter,reynolds,mach, &
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
-                           device)
+                           device,flowtype,conschm,difschm,bctype,twall)
+    character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
+    character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
+    integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
+    real(8), intent(in) :: twall(6)                 ! commvar twall(1:6)
     integer, intent(in) :: im,jm,km,ia,ja,ka,npdci,npdcj,npdck,is,ie,js,je,ks,ke
     logical, intent(in) :: lihomo,ljhomo,lkhomo,lfilter,diffterm
     integer, intent(in) :: irk,jrk,krk,isize,jsize,ksize,nbr(6),mpirank,device
@@ -179,9 +192,12 @@ module astr_gpu_mod
     cfg%rank=[irk,jrk,krk]; cfg%size=[isize,jsize,ksize]
     cfg%nbr=nbr          ! mpileft,mpiright,mpidown,mpiup,mpiback,mpifront ; MPI_PROC_NULL -> -1
     cfg%my_rank=mpirank
-    cfg%conschm=643; cfg%difschm=643; cfg%scheme_compact=1; cfg%rkscheme=3
+    read(conschm(1:3),*) cfg%conschm
+    read(difschm(1:3),*) cfg%difschm
+    cfg%scheme_compact=merge(1,0,difschm(4:4)=='c'); cfg%rkscheme=3
     cfg%lfilter=merge(1,0,lfilter); cfg%diffterm=merge(1,0,diffterm)
-    cfg%nondimen=1; cfg%flowtype=0
+    cfg%nondimen=1; cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
+    cfg%bctype=bctype; cfg%twall=twall
     cfg%alfa_filter=alfa_filter
     cfg%reynolds=reynolds; cfg%mach=mach; cfg%prandtl=prandtl; cfg%gamma=gamma; cfg%ref_tem=ref_tem
     cfg%const1=const(1); cfg%const2=const(2); cfg%const3=const(3); cfg%const4=const(4)

@@ -32,7 +32,7 @@ extern "C" {
 
 #define ASTR_GPU_HM 5          /* src/commvar.F90:184  parameter(hm=5) */
 #define ASTR_GPU_NUMQ 5        /* src/solver.F90:50    numq=5+num_species+num_modequ */
-#define ASTR_GPU_ABI_VERSION 1
+#define ASTR_GPU_ABI_VERSION 2
 
 /* Everything `solvrinit` (src/comsolver.F90:47-146), `refcal` (src/solver.F90:28-173)
  * and `parallelini` (src/parallel.F90:919-1248) have decided by the time the time loop
@@ -59,12 +59,16 @@ typedef struct astr_cfg {
   int lfilter;                /* filterq enabled                                         */
   int diffterm;               /* viscous terms enabled                                   */
   int nondimen;               /* must be 1                                               */
-  int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (set_force)  */
+  int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (src_chan)   */
+  int bctype[6];              /* bctype(1:6) of the input file: imin,imax,jmin,jmax,kmin,
+                                 kmax; 1 periodic/none, 41 isothermal no-slip wall
+                                 (src/bc.F90:327-407 boucon)                             */
   double alfa_filter;         /* 0.49 in every example                                   */
   double reynolds, mach, prandtl, gamma, ref_tem;
   double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */
   double tempconst, tempconst1; /* Sutherland: 110.3/ref_tem (src/solver.F90:122)        */
   double deltat;
+  double twall[6];            /* wall temperature of the bctype-41 faces (twall(1:6))    */
 } astr_cfg;
 
 /* ---- field ids for astr_gpu_get_field / set_field / device_ptr ----------------------
@@ -112,14 +116,16 @@ int astr_gpu_device_ptr(int field_id, void** dptr, long long strides[3], long lo
 
 /* ---- stage operators, one per reference subroutine ---------------------------------- */
 int astr_gpu_filterq(void);      /* src/comsolver.F90:514  filterq                      */
+int astr_gpu_boucon(void);       /* src/bc.F90:327         boucon (bctype 41 -> noslip
+                                    src/bc.F90:6306; other types: not on the device)    */
 int astr_gpu_qswap(void);        /* src/parallel.F90:4848  qswap                        */
 int astr_gpu_gradcal(void);      /* src/comsolver.F90:244  gradcal                      */
 int astr_gpu_rhscal(void);       /* src/solver.F90:185     rhscal (zeroes qrhs first,
                                     i.e. includes src/mainloop.F90:408 `qrhs=0`)        */
 int astr_gpu_rk_update(int rkstep, double deltat); /* src/mainloop.F90:427-476          */
 int astr_gpu_updatefvar(void);   /* src/fludyna.F90:191    updatefvar                   */
-/* all of the above in the order of src/mainloop.F90:396-482 (boucon/spongefilter are the
- * caller's: usable when they are no-ops, e.g. fully periodic TGV) */
+/* all of the above in the order of src/mainloop.F90:396-482 (spongefilter is the caller's:
+ * usable when there is no sponge layer) */
 int astr_gpu_rk_stage(int rkstep, double deltat);
 /* nsteps x (rk stages 1..3) with nothing in between */
 int astr_gpu_rk_steps(int nsteps, double deltat);
@@ -129,8 +135,13 @@ int astr_gpu_rk_steps_timed(int nsteps, double deltat, float* ms);
 /* generic halo exchange of one device field (dataswap, src/parallel.F90:3499-4382) */
 int astr_gpu_dataswap(int field_id, int direction /*0 = all, 1..3*/);
 
-/* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal */
+/* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal when
+ * flowtype = 1; `force` is what massfluxchan/chanfoce (src/statistic.F90:1437-1520) keep
+ * updating on the Fortran side.  src_chan integrates in y, so the channel case needs the
+ * node coordinates x(-hm:im+hm,..,3): astr_gpu_set_grid (or astr_gpu_gridgeom, which keeps
+ * them as a side effect). */
 int astr_gpu_set_force(const double force[3]);
+int astr_gpu_set_grid(const double* x);
 
 /* statistics: out[0]=sum rho*|u|^2, out[1]=sum rho*|omega|^2 over nodes 1..im,1..jm,1..km
  * of this block (src/statistic.F90:871-990 before psum and normalisation), out[2]=0.

@@ -88,6 +88,11 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_rk_update.argtypes = [vp, ci]
         L.oracle_case_rk_stage.argtypes = [vp, ci]
         L.oracle_case_set_flags.argtypes = [vp, ci, ci]
+        L.oracle_case_set_bc.argtypes = [vp, vp, vp]
+        L.oracle_case_set_flow.argtypes = [vp, ci, vp]
+        L.oracle_case_set_scheme.argtypes = [vp, ci]
+        L.oracle_case_boucon.argtypes = [vp]
+        L.oracle_case_boucon.restype = ci
         L.oracle_case_run.argtypes = [vp, ci]
         L.oracle_case_run.restype = ci
         L.oracle_case_history.argtypes = [vp, vp]
@@ -211,6 +216,24 @@ class Case:
 
     def set_flags(self, lfilter=True, diffterm=True):
         lib().oracle_case_set_flags(self._h, int(lfilter), int(diffterm))
+
+    def set_bc(self, bctype, twall=(0.0,) * 6):
+        """bctype(1:6) / twall(1:6) of the input file (imin,imax,jmin,jmax,kmin,kmax)."""
+        bt = (ctypes.c_int * 6)(*[int(b) for b in bctype])
+        tw = (ctypes.c_double * 6)(*[float(t) for t in twall])
+        lib().oracle_case_set_bc(self._h, bt, tw)
+
+    def set_flow(self, flowtype: int, force=(0.0, 0.0, 0.0)):
+        """flowtype 0 generic, 1 channel (src_chan with body force `force`)."""
+        f = (ctypes.c_double * 3)(*[float(v) for v in force])
+        lib().oracle_case_set_flow(self._h, int(flowtype), f)
+
+    def set_scheme(self, explicit: bool):
+        lib().oracle_case_set_scheme(self._h, int(explicit))
+
+    def boucon(self):
+        if lib().oracle_case_boucon(self._h) != 0:
+            raise NotImplementedError("oracle boucon: bctype not restated")
 
     def history(self) -> np.ndarray:
         rows = lib().oracle_case_run(self._h, 0)

@@ -42,6 +42,10 @@ struct Case {
   FilterCoef fc;
   std::vector<Block> blk;
   double force[3] = {0, 0, 0};
+  int flowtype = 0;          // 0 tgv / generic (no source term), 1 channel (src_chan)
+  char scheme_kind = 'c';    // difschm(4:4): 'c' compact, 'e' explicit (comsolver.F90:76-84)
+  int bctype[6] = {1, 1, 1, 1, 1, 1};      // src/readwrite.F90 bctype(1:6): imin,imax,jmin,jmax,kmin,kmax
+  double twall[6] = {0, 0, 0, 0, 0, 0};
   std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
   double xmax = 0.0;
 };
@@ -361,6 +365,13 @@ static inline void gather(const Field& a, int d, int p1, int p2, int dim, double
   for (int l = -hm; l <= dim + hm; ++l) f[l] = at(a, d, l, p1, p2);
 }
 
+// fds%central (src/derivative.F90:16-34): compact_central -> df_compact (:171-198),
+// explicit_central -> df_explicit -> diff6ec (:319-413)
+static inline void central(const Case& c, const CompactScheme& s, const double* f, double* df, double* work) {
+  if (c.scheme_kind == 'e') diff6ec(f, s.dimension, s.nbctype, df);
+  else df_compact(s, f, df, work);
+}
+
 static void gridgeom(Case& c) {
   gridsendrecv(c);
   const int md = std::max(c.ia, std::max(c.ja, c.ka));
@@ -375,7 +386,7 @@ static void gridgeom(Case& c) {
         PencilWork w(md);
         for (int m = 0; m < 3; ++m) {
           gather(b.x[m], d, p1, p2, b.dim(d), w.f());
-          df_compact(b.fds[d], w.f(), w.df.data(), w.work.data());
+          central(c, b.fds[d], w.f(), w.df.data(), w.work.data());
           for (int l = 0; l <= b.dim(d); ++l) at(DX[ib][m * 3 + d], d, l, p1, p2) = w.df[l];
         }
       });
@@ -432,7 +443,7 @@ static void gridgeom(Case& c) {
         for (int l = -hm; l <= dm + hm; ++l)
           phi[l] = 0.5 * (at(dx(t.m1, t.n1), t.d, l, p1, p2) * at(b.x[t.c1 - 1], t.d, l, p1, p2) -
                           at(dx(t.m2, t.n2), t.d, l, p1, p2) * at(b.x[t.c2 - 1], t.d, l, p1, p2));
-        df_compact(b.fds[t.d], phi, w.df.data(), w.work.data());
+        central(c, b.fds[t.d], phi, w.df.data(), w.work.data());
         Field& tgt = b.dxi[t.a - 1][t.bb - 1];
         for (int l = 0; l <= dm; ++l) at(tgt, t.d, l, p1, p2) = at(tgt, t.d, l, p1, p2) + w.df[l];
       });
@@ -491,7 +502,7 @@ static void gradcal(Case& c) {
         for (int n = 0; n < 4; ++n) {
           const Field& src = n < 3 ? b.vel[n] : b.tmp;
           gather(src, d, p1, p2, dm, w.f());
-          df_compact(b.fds[d], w.f(), w.df.data(), w.work.data());
+          central(c, b.fds[d], w.f(), w.df.data(), w.work.data());
           for (int m = 0; m < 3; ++m) {
             Field& dst = n < 3 ? b.dvel[n][m] : b.dtmp[m];
             for (int l = 0; l <= dm; ++l)
@@ -531,7 +542,7 @@ static void convrsdcal6(Case& c) {
           fcs[4][l] = jac * (at(b.q[4], d, l, p1, p2) + p) * uu;
         }
         for (int n = 0; n < 5; ++n) {
-          df_compact(b.fds[d], fcs[n], df.data(), work.data());
+          central(c, b.fds[d], fcs[n], df.data(), work.data());
           for (int l = b.s[d]; l <= b.e[d]; ++l) {
             double& r = at(b.qrhs[n], d, l, p1, p2);
             r = r + df[l];
@@ -607,7 +618,7 @@ static void diffrsdcal6(Case& c) {
                       at(b.qflux[2], d, l, p1, p2) * d3) * jac;
         }
         for (int n = 0; n < 4; ++n) {
-          df_compact(b.fds[d], ff[n], df.data(), work.data());
+          central(c, b.fds[d], ff[n], df.data(), work.data());
           for (int l = b.s[d]; l <= b.e[d]; ++l) {
             double& r = at(b.qrhs[n + 1], d, l, p1, p2);
             r = r + df[l];
@@ -618,13 +629,84 @@ static void diffrsdcal6(Case& c) {
   }
 }
 
-// src/solver.F90:185-282 rhscal (conschm even -> central; flowtype tgv: no sources)
+// src/solver.F90:295-353 src_chan (ndims==3): bulk velocities by trapezoidal integration in y over
+// nodes 1..im,1..jm,1..km of every rank (psum = sum over blocks), then the body force
+static void src_chan(Case& c) {
+  double robulk = 0.0, u1bulk = 0.0, u2bulk = 0.0, u3bulk = 0.0;
+  for (Block& b : c.blk) {
+    double ro = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+    for (int k = 1; k <= b.km; ++k)
+      for (int j = 1; j <= b.jm; ++j)
+        for (int i = 1; i <= b.im; ++i) {
+          const double dy = b.x[1](i, j, k) - b.x[1](i, j - 1, k);
+          ro = ro + 0.5 * (b.q[0](i, j - 1, k) + b.q[0](i, j, k)) * dy;
+          u1 = u1 + 0.5 * (b.q[1](i, j - 1, k) + b.q[1](i, j, k)) * dy;
+          u2 = u2 + 0.5 * (b.q[2](i, j - 1, k) + b.q[2](i, j, k)) * dy;
+          u3 = u3 + 0.5 * (b.q[3](i, j - 1, k) + b.q[3](i, j, k)) * dy;
+        }
+    robulk += ro; u1bulk += u1; u2bulk += u2; u3bulk += u3;  // psum
+  }
+  u1bulk = u1bulk / robulk; u2bulk = u2bulk / robulk; u3bulk = u3bulk / robulk;
+  const double fe = c.force[0] * u1bulk + c.force[1] * u2bulk + c.force[2] * u3bulk;
+  for (Block& b : c.blk)
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) {
+          const double jac = b.jacob(i, j, k);
+          b.qrhs[1](i, j, k) = b.qrhs[1](i, j, k) + c.force[0] * jac;
+          b.qrhs[2](i, j, k) = b.qrhs[2](i, j, k) + c.force[1] * jac;
+          b.qrhs[3](i, j, k) = b.qrhs[3](i, j, k) + c.force[2] * jac;
+          b.qrhs[4](i, j, k) = b.qrhs[4](i, j, k) + fe * jac;
+        }
+}
+
+// src/solver.F90:185-282 rhscal (conschm even -> central; flowtype channel adds src_chan :262)
 static void rhscal(Case& c) {
   convrsdcal6(c);
   for (Block& b : c.blk)
     for (auto& f : b.qrhs)
       for (double& v : f.v) v = -v;  // :242
   if (c.diffterm) diffrsdcal6(c);
+  if (c.flowtype == 1) src_chan(c);
+}
+
+// src/bc.F90:6306-6723 noslip(ndir,tw) (nondimen, no species, turbmode none, no wall blowing):
+// face node: u=0, T=tw, p extrapolated from the two interior neighbours, rho=thermal(p,T),
+// q=fvar2q(rho,vel,p) (fludyna.F90:312-376, pressure branch).  ndir: 1 imin .. 6 kmax.
+static void noslip(Case& c, int ndir, double tw) {
+  const int d = (ndir - 1) / 2, side = (ndir - 1) % 2;
+  for (Block& b : c.blk) {
+    if (side == 0 ? b.rk[d] != 0 : b.rk[d] != c.size[d] - 1) continue;
+    const int dm = b.dim(d), l = side ? dm : 0, sg = side ? -1 : 1;
+    int n1, n2;
+    others(b, d, n1, n2);
+    for (int p2 = 0; p2 <= n2; ++p2)
+      for (int p1 = 0; p1 <= n1; ++p1) {
+        const double pe = num1d3 * (4.0 * at(b.prs, d, l + sg, p1, p2) - at(b.prs, d, l + 2 * sg, p1, p2));
+        for (int m = 0; m < 3; ++m) at(b.vel[m], d, l, p1, p2) = 0.0;
+        at(b.prs, d, l, p1, p2) = pe;
+        at(b.tmp, d, l, p1, p2) = tw;
+        const double rho = pe / tw * c.th.const2;  // thermal(pressure,temperature) fludyna.F90:60
+        at(b.rho, d, l, p1, p2) = rho;
+        at(b.q[0], d, l, p1, p2) = rho;
+        at(b.q[1], d, l, p1, p2) = rho * 0.0;
+        at(b.q[2], d, l, p1, p2) = rho * 0.0;
+        at(b.q[3], d, l, p1, p2) = rho * 0.0;
+        const double var1 = 0.5 * (0.0 * 0.0 + 0.0 * 0.0 + 0.0 * 0.0);
+        at(b.q[4], d, l, p1, p2) = pe * c.th.const6 + rho * var1;
+      }
+  }
+}
+
+// src/bc.F90:327-407 boucon: faces in the order n=1..6; only the bctypes implemented so far
+static int boucon(Case& c) {
+  for (int n = 1; n <= 6; ++n) {
+    const int bt = c.bctype[n - 1];
+    if (bt == 41) noslip(c, n, c.twall[n - 1]);
+    else if (bt != 1) return -1;
+  }
+  return 0;
 }
 
 // src/fludyna.F90:191-242 updatefvar
@@ -700,10 +782,11 @@ static void zero_qrhs(Case& c) {
     for (auto& f : b.qrhs) std::fill(f.v.begin(), f.v.end(), 0.0);
 }
 
-// One RK stage, src/mainloop.F90:396-482 (boucon / spongefilter are no-ops for TGV)
+// One RK stage, src/mainloop.F90:396-482 (spongefilter is a no-op without sponge layers)
 static void rk_stage(Case& c, int rkstep) {
   if (c.lfilter) filterq(c);
   zero_qrhs(c);
+  boucon(c);
   qswap(c);
   gradcal(c);
   if (rkstep == 1) {
@@ -845,6 +928,21 @@ void oracle_case_save_q(void* h) { save_q(*static_cast<Case*>(h)); }
 void oracle_case_rk_update(void* h, int rkstep) { rk_update(*static_cast<Case*>(h), rkstep); }
 void oracle_case_updatefvar(void* h) { updatefvar(*static_cast<Case*>(h)); }
 void oracle_case_rk_stage(void* h, int rkstep) { rk_stage(*static_cast<Case*>(h), rkstep); }
+int oracle_case_boucon(void* h) { return boucon(*static_cast<Case*>(h)); }
+// bctype(1:6), twall(1:6) of the input file; flowtype 0 generic / 1 channel; force(1:3) of
+// src_chan; scheme_kind 'c' (643c) or 'e' (642e: diff6ec everywhere fds%central is called)
+void oracle_case_set_bc(void* h, const int* bctype, const double* twall) {
+  Case* c = static_cast<Case*>(h);
+  for (int n = 0; n < 6; ++n) { c->bctype[n] = bctype[n]; c->twall[n] = twall[n]; }
+}
+void oracle_case_set_flow(void* h, int flowtype, const double* force) {
+  Case* c = static_cast<Case*>(h);
+  c->flowtype = flowtype;
+  for (int n = 0; n < 3; ++n) c->force[n] = force[n];
+}
+void oracle_case_set_scheme(void* h, int explicit_scheme) {
+  static_cast<Case*>(h)->scheme_kind = explicit_scheme ? 'e' : 'c';
+}
 void oracle_case_set_flags(void* h, int lfilter, int diffterm) {
   Case* c = static_cast<Case*>(h);
   c->lfilter = lfilter; c->diffterm = diffterm;

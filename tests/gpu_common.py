@@ -31,14 +31,61 @@ def stretched_x(n, homo):
     return np.asfortranarray(x)
 
 
+def channel_x(n, lengths):
+    """grichan (src/gridgeneration.F90:272-303): uniform x,z, tanh-stretched y, varc=1.07."""
+    lx, ly, lz = lengths
+    varc = 1.07
+    var1 = np.arctanh(1.0 / varc)
+    s = [np.arange(m + 1) / m for m in n]
+    S = np.meshgrid(*s, indexing="ij")
+    x = np.stack([lx * S[0], 0.5 * ly * (1.0 + varc * np.tanh(var1 * (2.0 * S[1] - 1.0))), lz * S[2]], axis=-1)
+    return np.asfortranarray(x)
+
+
+def channel_state(c, th, amp=0.05, ib=0):
+    """Laminar Poiseuille profile of chanini (src/initialisation.F90:791-799) plus a
+    deterministic sinusoidal perturbation (the reference's synthetic-eddy seeding is random);
+    q from fvar2q with temperature (src/fludyna.F90:312-376)."""
+    X, Y, Z = (core(c.get(f"x{d + 1}", ib)) for d in range(3))
+    eta = Y - 1.0
+    rho = np.ones_like(X)
+    env = 1.0 - eta ** 2
+    u = 1.5 * env + amp * env * np.sin(2 * X) * np.cos(4 * Z) * np.cos(np.pi * eta)
+    v = amp * env * np.cos(2 * X) * np.sin(4 * Z)
+    w = amp * env * np.sin(X + 1.0) * np.sin(2 * Z)
+    tmp = 1.0 + (th["gamma"] - 1.0) * th["prandtl"] * th["mach"] ** 2 / 3.0 * 1.5 * (1.0 - eta ** 4)
+    prs = rho * tmp / th["const2"]
+    q5 = rho * (tmp * th["const1"] + 0.5 * (u * u + v * v + w * w))
+    vals = dict(rho=rho, u=u, v=v, w=w, prs=prs, tmp=tmp, q1=rho, q2=rho * u, q3=rho * v, q4=rho * w, q5=q5)
+    for name, a in vals.items():
+        full = c.get(name, ib)
+        core(full)[...] = a
+        c.set(name, full, ib)
+
+
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
-              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False):
-    c = oracle.Case(*n, homo=homo, sutherland_s=sutherland_s)
+              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False):
+    reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
+    lengths = (2 * np.pi, 2.0, np.pi) if channel else None
+    th = refcal(reynolds, mach, sutherland_s=sutherland_s)
+    c = oracle.Case(*n, homo=homo, sutherland_s=sutherland_s, reynolds=reynolds, mach=mach, lengths=lengths)
     c.set_flags(lfilter=lfilter, diffterm=diffterm)
-    if stretch:
+    c.set_scheme(explicit)
+    bctype, twall, force = (1,) * 6, (0.0,) * 6, (0.0, 0.0, 0.0)
+    if channel:
+        # examples/Channel/datin/input.chl: walls 41 with T_w=1 at jmin/jmax, body force along x
+        assert tuple(homo) == (True, False, True)
+        bctype, twall, force = (1, 1, 41, 41, 1, 1), (0, 0, 1.0, 1.0, 0, 0), (2.5e-3, 0.0, 1e-4)
+        c.set_bc(bctype, twall)
+        c.set_flow(1, force)
+        c.set_x(channel_x(n, lengths))
+    elif stretch:
         c.set_x(stretched_x(n, homo))
     c.gridgeom()
-    c.tgvini()
+    if channel:
+        channel_state(c, th)
+    else:
+        c.tgvini()
     if perturb:
         rng = np.random.default_rng(seed)
         for name in QS:
@@ -47,14 +94,16 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
             c.set(name, a)
         c.updatefvar()
     block = decompose(n, (1, 1, 1), homo)[0]
-    th = refcal(1600.0, 0.1, sutherland_s=sutherland_s)
-    eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0)
+    eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0,
+                    flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit)
+    eng.set_force(force)
+    x = eng.empty(3)
+    for d in range(3):
+        x[..., d] = c.get(f"x{d + 1}")
     if device_metrics:
-        x = eng.empty(3)
-        for d in range(3):
-            x[..., d] = c.get(f"x{d + 1}")
         eng.gridgeom(x)
     else:
+        eng.set_grid(x)
         dxi = eng.empty(9).reshape(eng.shape + (3, 3), order="F")
         for a in range(3):
             for b in range(3):

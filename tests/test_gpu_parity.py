@@ -25,6 +25,12 @@ CASES = {
     "periodic96_stretched": dict(n=(96, 40, 64), homo=(True, True, True), stretch=True),
     "wall_j": dict(n=(32, 48, 32), homo=(True, False, True), stretch=True),
     "walls_all": dict(n=(32, 32, 36), homo=(False, False, False), stretch=True),
+    # examples/Channel/datin/input.chl at reduced size: isothermal walls (bctype 41), src_chan forcing
+    # difschm=conschm=642e (examples/Hypersonic_Boundary_Layer/datin/input.M3): explicit_central / diff6ec
+    "explicit_periodic": dict(n=(32, 36, 40), homo=(True, True, True), stretch=True, explicit=True),
+    "explicit_walls": dict(n=(36, 32, 32), homo=(False, False, True), stretch=True, explicit=True),
+    "explicit_channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0, explicit=True),
+    "channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0),
 }
 
 
@@ -50,6 +56,13 @@ def test_filterq(pair):
     c, eng = pair
     c.filterq(); eng.filterq()
     assert_fields_close(c, eng, QS, OP_TOL, what="filterq")
+
+
+def test_boucon(pair):
+    c, eng = pair
+    c.filterq(); eng.filterq()
+    c.boucon(); eng.boucon()
+    assert_fields_close(c, eng, QS + PRIMS, OP_TOL, what="boucon")
 
 
 def test_qswap(pair):
@@ -128,7 +141,8 @@ def test_five_steps_and_history(oracle):
 
 def test_device_gridgeom(oracle):
     for kw in (dict(n=(32, 32, 32)), dict(n=(40, 32, 36), stretch=True),
-               dict(n=(32, 48, 32), homo=(True, False, True), stretch=True)):
+               dict(n=(32, 48, 32), homo=(True, False, True), stretch=True),
+               dict(n=(32, 48, 32), homo=(True, False, True), stretch=True, explicit=True)):
         c, eng = make_pair(oracle, device_metrics=True, **kw)
         names = ["jacob"] + [f"dxi{a + 1}{b + 1}" for a in range(3) for b in range(3)]
         worst = {}

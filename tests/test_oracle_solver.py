@@ -58,3 +58,99 @@ def test_stage_operators_compose_to_rk_stage(oracle):
     for name in ("q1", "q2", "q5", "prs", "tmp", "qrhs3"):
         np.testing.assert_array_equal(a.get(name), b.get(name))
     a.close(); b.close()
+
+
+def _channel_case(oracle, n=(24, 32, 16), explicit=False, blocks=(1, 1, 1)):
+    """examples/Channel/datin/input.chl at reduced size (see tests/gpu_common.py)."""
+    sys_path_tests()
+    from gpu_common import channel_state, channel_x
+    from astr_b200 import refcal
+    lengths = (2 * np.pi, 2.0, np.pi)
+    c = oracle.Case(*n, blocks=blocks, homo=(True, False, True), reynolds=3000.0, mach=0.3, lengths=lengths)
+    c.set_bc((1, 1, 41, 41, 1, 1), (0, 0, 1.0, 1.0, 0, 0))
+    c.set_scheme(explicit)
+    xg = channel_x(n, lengths)
+    for ib in range(c.nblocks):
+        b = c.block_info(ib)
+        g0, dims = b["g0"], (b["im"], b["jm"], b["km"])
+        c.set_x(xg[tuple(slice(g0[d], g0[d] + dims[d] + 1) for d in range(3))], ib)
+    c.gridgeom()
+    for ib in range(c.nblocks):
+        channel_state(c, refcal(3000.0, 0.3), ib=ib)
+    return c
+
+
+def sys_path_tests():
+    import os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+
+
+def test_noslip_wall_closure(oracle):
+    # bc.F90:6306: u=0, T=tw, p=(4p1-p2)/3, rho=p/T*const2, q5=p*const6 on the wall nodes only
+    from astr_b200 import refcal
+    th = refcal(3000.0, 0.3)
+    c = _channel_case(oracle)
+    before = {k: c.get(k) for k in ("prs", "q1", "u", "tmp")}
+    c.boucon()
+    for j, j1, j2 in ((5, 6, 7), (-6, -7, -8)):
+        p = c.get("prs")
+        pe = (4.0 * before["prs"][5:-5, j1, 5:-5] - before["prs"][5:-5, j2, 5:-5]) / 3.0
+        np.testing.assert_allclose(p[5:-5, j, 5:-5], pe, rtol=1e-15)
+        assert np.all(c.get("u")[5:-5, j, 5:-5] == 0.0) and np.all(c.get("q3")[5:-5, j, 5:-5] == 0.0)
+        assert np.all(c.get("tmp")[5:-5, j, 5:-5] == 1.0)
+        np.testing.assert_allclose(c.get("q1")[5:-5, j, 5:-5], pe * th["const2"], rtol=1e-15)
+        np.testing.assert_allclose(c.get("q5")[5:-5, j, 5:-5], pe * th["const6"], rtol=1e-15)
+    # interior untouched
+    np.testing.assert_array_equal(c.get("q1")[5:-5, 6:-6, 5:-5], before["q1"][5:-5, 6:-6, 5:-5])
+    c.close()
+
+
+def test_src_chan_adds_force_times_jacobian(oracle):
+    # solver.F90:341-352: qrhs(2:4)+=force*J, qrhs(5)+=force.ubulk*J ; Poiseuille: ubulk ~ 1
+    a, b = _channel_case(oracle), _channel_case(oracle)
+    force = (2.5e-3, 0.0, 1e-4)
+    a.set_flow(1, force); b.set_flow(0, force)
+    for c in (a, b):
+        c.boucon(); c.qswap(); c.gradcal(); c.zero_qrhs(); c.rhscal()
+    jac = a.get("jacob")[5:-5, 5:-5, 5:-5]
+    d2 = (a.get("qrhs2") - b.get("qrhs2"))[5:-5, 5:-5, 5:-5]
+    d4 = (a.get("qrhs4") - b.get("qrhs4"))[5:-5, 5:-5, 5:-5]
+    d5 = (a.get("qrhs5") - b.get("qrhs5"))[5:-5, 5:-5, 5:-5]
+    scale = np.abs(a.get("qrhs2")).max()
+    assert np.abs(d2 - force[0] * jac).max() < 1e-14 * scale
+    assert np.abs(d4 - force[2] * jac).max() < 1e-14 * scale
+    ub = d5 / jac
+    assert np.ptp(ub) < 1e-10 and abs(ub.mean() / force[0] - 1.0) < 0.05   # u1bulk of 1.5(1-eta^2) is 1
+    np.testing.assert_array_equal(a.get("qrhs1"), b.get("qrhs1"))
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("explicit", [False, True])
+def test_channel_runs_and_split_in_y_agrees(oracle, explicit):
+    # wall closures (ntype 4 single block; 1/2 when split in y) + noslip + src_chan stay stable and the
+    # two-block layout differs only at truncation level (psum of the bulk integrals over blocks)
+    one, two = _channel_case(oracle, explicit=explicit), _channel_case(oracle, explicit=explicit, blocks=(1, 2, 1))
+    for c in (one, two):
+        c.set_flow(1, (2.5e-3, 0.0, 0.0))
+        for rk in (1, 2, 3):
+            c.rk_stage(rk)
+    jm0 = two.block_info(0)["jm"]
+    u1 = one.get("u")[5:-5, 5:5 + jm0 + 1, 5:-5]
+    u2 = two.get("u", 0)[5:-5, 5:-5, 5:-5]
+    assert np.isfinite(u1).all() and np.abs(u1 - u2).max() < 1e-4
+    one.close(); two.close()
+
+
+def test_explicit_scheme_is_sixth_order_on_the_rhs(oracle):
+    # diff6ec vs df_compact on a smooth periodic field: both 6th order -> qrhs agree to truncation level
+    n = 32
+    a, b = oracle.Case(n, n, n), oracle.Case(n, n, n)
+    b.set_scheme(True)
+    for c in (a, b):
+        c.gridgeom(); c.tgvini(); c.qswap(); c.gradcal(); c.zero_qrhs(); c.rhscal()
+    ra, rb = a.get("qrhs2")[5:-5, 5:-5, 5:-5], b.get("qrhs2")[5:-5, 5:-5, 5:-5]
+    err = np.abs(ra - rb).max() / np.abs(ra).max()
+    assert 0.0 < err < 1e-4
+    a.close(); b.close()
