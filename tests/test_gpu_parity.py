@@ -37,6 +37,7 @@ CASES = {
 @pytest.fixture(params=list(CASES))
 def pair(request, oracle):
     c, eng = make_pair(oracle, **CASES[request.param])
+    c.case_name = request.param
     yield c, eng
     eng.close(); c.close()
 
@@ -76,7 +77,10 @@ def test_gradcal(pair):
     c, eng = pair
     c.qswap(); eng.qswap()
     c.gradcal(); eng.gradcal()
-    assert_fields_close(c, eng, DVEL + DTMP, OP_TOL, what="gradcal")
+    # channel: T = 1 + O(1e-2), so dT/dy carries the rounding of a field ~100x larger than its
+    # variation (error ~ eps*|T|/dy against max|dT/dy| ~ 0.05): conditioning, not the kernel
+    tol = 1e-12 if "channel" in c.case_name else OP_TOL
+    assert_fields_close(c, eng, DVEL + DTMP, tol, what="gradcal")
 
 
 def test_rhscal(pair):
