@@ -145,6 +145,16 @@ static void build_filter(HostOp& h, int ntype, int n, double alfa) {
   build_line_plan(h.plan, OP_FILTER, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, 16);
 }
 
+// compact_flux_initiate (src/flux.F90:32-118) for flux_uw ('+', OP_FLUXP) / flux_dw ('-', OP_FLUXM);
+// solved on the shared-memory engine (sweep.cu), so no register-engine plan
+static void build_flux(HostOp& h, int optype, int ntype, int n, double bfacmpld) {
+  h.ntype = ntype; h.n = n;
+  build_lhs(optype, ntype, n, bfacmpld, h.a, h.c, h.first_node, h.nsf, h.nsl);
+  h.nrows = (int)h.a.size();
+  factorise(h);
+  h.plan.ok = 0;
+}
+
 // -------------------------------------------------------------------------------------
 // context
 // -------------------------------------------------------------------------------------
@@ -160,6 +170,9 @@ struct Ctx {
   double* pool = nullptr;        // S_CORE fields
   double* scr = nullptr;         // 15 scratch fields, lazily allocated
   HostOp fd[3], fl[3];
+  HostOp fxp[3], fxm[3];         // flux_uw_* / flux_dw_* (conschm 543 only)
+  double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
+  bool upwind() const { return (cfg.conschm / 100) % 2 == 1; }
   FilterCoef fc;
   bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
@@ -320,14 +333,14 @@ static int sweep(int d, int optype, const double* const* in, double* const* out,
   SweepArgs a;
   memset(&a, 0, sizeof a);
   a.L = g->L;
-  a.op = (optype == OP_DERIV ? g->fd[d] : g->fl[d]).dev();
+  const HostOp& hop = optype == OP_DERIV ? g->fd[d] : optype == OP_FILTER ? g->fl[d] : optype == OP_FLUXP ? g->fxp[d] : g->fxm[d];
+  a.op = hop.dev();
   a.nf = nf;
   for (int i = 0; i < nf; ++i) { a.in[i] = in[i]; a.out[i] = out[i]; }
   a.epi = epi; a.o_lo = o_lo; a.o_hi = o_hi;
   if (optype == OP_DERIV && !g->cfg.scheme_compact) return pw_diff6e(d, a, g->st);   // difschm '...e'
-  if (!g->legacy_sweep) {
-    const HostOp& h = (optype == OP_DERIV ? g->fd[d] : g->fl[d]);
-    const int rc = astr_launch_sweep2(d, optype, h.plan, a, g->st);
+  if (!g->legacy_sweep && optype <= OP_FILTER) {
+    const int rc = astr_launch_sweep2(d, optype, hop.plan, a, g->st);
     if (rc >= 0) return rc;
   }
   return astr_launch_sweep(d, optype, a, g->st);
@@ -360,8 +373,11 @@ int astr_gpu_init(const astr_cfg* cfg) {
       return astr_fail_msg("bctype must be 1 (periodic) or 41 (isothermal no-slip wall)");
   if (!cfg->nondimen) return astr_fail_msg("only nondimen=t is implemented");
   // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
-  if (cfg->conschm != cfg->difschm || !(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
-    return astr_fail_msg("only conschm=difschm=643c (central compact) or 6xxe (central explicit) are implemented");
+  if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
+    return astr_fail_msg("difschm must be 643c (compact_central) or 6xxe (explicit_central)");
+  // conschm: central (= difschm, comsolver.F90:94-101) or 543c, the upwind compact scheme (convrsdcmp)
+  if (cfg->conschm != cfg->difschm && cfg->conschm != 543)
+    return astr_fail_msg("conschm must equal difschm (central) or be 543c (upwind compact)");
   if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
   for (int d = 0; d < 3; ++d)
     if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
@@ -382,6 +398,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   g->th.reynolds = cfg->reynolds; g->th.prandtl = cfg->prandtl; g->th.const1 = cfg->const1;
   g->th.const2 = cfg->const2; g->th.const5 = cfg->const5; g->th.const6 = cfg->const6;
   g->th.tempconst = cfg->tempconst; g->th.tempconst1 = cfg->tempconst1;
+  g->th.gamma = cfg->gamma; g->th.mach = cfg->mach;
   CUDA_OK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->pool, bytes));
@@ -400,7 +417,12 @@ int astr_gpu_init(const astr_cfg* cfg) {
     build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
     TRY(astr_sweep2_set_plan(d, OP_DERIV, g->fd[d].plan, g->fc));
     TRY(astr_sweep2_set_plan(d, OP_FILTER, g->fl[d].plan, g->fc));
-    for (HostOp* h : {&g->fd[d], &g->fl[d]}) {
+    if (g->upwind()) {
+      build_flux(g->fxp[d], OP_FLUXP, cfg->npdc[d], n, cfg->bfacmpld);
+      build_flux(g->fxm[d], OP_FLUXM, cfg->npdc[d], n, cfg->bfacmpld);
+    }
+    for (HostOp* h : {&g->fd[d], &g->fl[d], &g->fxp[d], &g->fxm[d]}) {
+      if (h->nrows == 0) continue;   // flux operators exist only for conschm 543
       if (h->C < 1) return astr_fail_msg("block too small: every direction needs at least 12 nodes");
       const size_t nb = (size_t)5 * h->nrows * sizeof(double);
       CUDA_OK(cudaMalloc(&h->d_tab, nb));
@@ -409,6 +431,12 @@ int astr_gpu_init(const astr_cfg* cfg) {
       for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb}) t.insert(t.end(), v->begin(), v->end());
       CUDA_OK(cudaMemcpy(h->d_tab, t.data(), nb, cudaMemcpyHostToDevice));
     }
+  }
+  if (g->upwind()) {
+    TRY(astr_set_flux_coef(cfg->bfacmpld));
+    const size_t ub = (size_t)UP_TOTAL * L.fstride * sizeof(double);
+    CUDA_OK(cudaMalloc(&g->up, ub));
+    CUDA_OK(cudaMemsetAsync(g->up, 0, ub, g->st));
   }
   g_launches = 0;
   CUDA_OK(cudaStreamSynchronize(g->st));
@@ -422,7 +450,12 @@ int astr_gpu_finalize(void) {
   for (auto e : g->free_events) cudaEventDestroy(e);
   if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
   for (auto& b : g->xbuf) if (b) cudaFree(b);
-  for (int d = 0; d < 3; ++d) { cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab); }
+  for (int d = 0; d < 3; ++d) {
+    cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab);
+    if (g->fxp[d].d_tab) cudaFree(g->fxp[d].d_tab);
+    if (g->fxm[d].d_tab) cudaFree(g->fxm[d].d_tab);
+  }
+  if (g->up) cudaFree(g->up);
   astr_sweep2_register_pool(0, nullptr, 0, g->L); astr_sweep2_register_pool(1, nullptr, 0, g->L);
   cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
   cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
@@ -460,24 +493,25 @@ int astr_gpu_comm_init(const char id[128], int nranks, int rank) {
 }
 
 // ---- host <-> device field transfer (Fortran halo'd box <-> padded device box) --------
-static int copy_field(int slot, double* host, bool to_host) {
+static int copy_dev(double* field, double* host, bool to_host) {
   const Layout& L = g->L;
   const size_t w = (size_t)(L.im + 1 + 2 * ASTR_HM) * sizeof(double);
   const size_t rows = (size_t)L.njt * L.nkt;
-  double* dev = g->slot(slot) + (ASTR_IOFF - ASTR_HM);
+  double* dev = field + (ASTR_IOFF - ASTR_HM);
   if (to_host)
     CUDA_OK(cudaMemcpy2DAsync(host, w, dev, (size_t)L.pitch * sizeof(double), w, rows, cudaMemcpyDeviceToHost, g->st));
   else
     CUDA_OK(cudaMemcpy2DAsync(dev, (size_t)L.pitch * sizeof(double), host, w, w, rows, cudaMemcpyHostToDevice, g->st));
   return 0;
 }
+static int copy_field(int slot, double* host, bool to_host) { return copy_dev(g->slot(slot), host, to_host); }
 static size_t host_field_elems() {
   const Layout& L = g->L;
   return (size_t)(L.im + 1 + 2 * ASTR_HM) * L.njt * L.nkt;
 }
 
 static int api_slot(int field_id, int* slot) {
-  if (field_id < 0 || field_id >= ASTR_F_COUNT) return astr_fail_msg("bad field id");
+  if (field_id < 0 || field_id >= ASTR_F_SSF) return astr_fail_msg("bad field id");
   if (field_id < ASTR_F_QRHS) *slot = S_Q + field_id;                        // q, rho, vel, prs, tmp
   else if (field_id < ASTR_F_JACOB) *slot = S_QRHS + (field_id - ASTR_F_QRHS);
   else if (field_id == ASTR_F_JACOB) *slot = S_JAC;
@@ -493,6 +527,12 @@ static int api_slot(int field_id, int* slot) {
 
 int astr_gpu_get_field(int field_id, double* host) {
   NEED_CTX();
+  if (field_id == ASTR_F_SSF || field_id == ASTR_F_LSHOCK) {
+    if (!g->up || !g->cfg.lchardecomp) return astr_fail_msg("ssf/lshock exist only with conschm 543 and lchardecomp");
+    TRY(copy_dev(g->up + (size_t)(field_id == ASTR_F_SSF ? UP_SSF : UP_LSH) * g->L.fstride, host, true));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+    return 0;
+  }
   int s;
   TRY(api_slot(field_id, &s));
   if (s >= S_SCR) {
@@ -513,6 +553,7 @@ int astr_gpu_get_field(int field_id, double* host) {
 
 int astr_gpu_set_field(int field_id, const double* host) {
   NEED_CTX();
+  if (field_id >= ASTR_F_SSF) return astr_fail_msg("ssf/lshock are derived fields");
   int s;
   TRY(api_slot(field_id, &s));
   if (s >= S_SCR) return astr_fail_msg("dvel/dtmp/vor are derived fields");
@@ -699,12 +740,57 @@ int astr_gpu_gradcal(void) {
   return 0;
 }
 
+// ducrossensor (src/commcal.F90:196-357): ssf on 0..im etc., dataswap(ssf), lshock
+int astr_gpu_ducrossensor(void) {
+  NEED_CTX();
+  if (!g->up) return astr_fail_msg("ducrossensor needs conschm 543");
+  if (!g->have_grad) return astr_fail_msg("ducrossensor before gradcal");
+  {
+    ProfScope ps(PC_FLUX);
+    TRY(uw_ducros_ssf(g->L, g->pool, g->up, g->cfg.npdc, g->st));
+  }
+  FieldList fl; fl.nf = 1; fl.f[0] = g->up + (size_t)UP_SSF * g->L.fstride;
+  TRY(dataswap(fl, -1));
+  ProfScope ps(PC_FLUX);
+  return uw_ducros_flag(g->L, g->up, g->cfg.npdc, g->cfg.shkcrt, g->st);
+}
+
+// convrsdcmp (src/solver.F90:1271-1937) of direction d; the result -(Fh(i)-Fh(i-1)) is added to the
+// five slots starting at dst0 (rmw_mask: components that already hold the viscous derivative)
+static int convrsdcmp_dir(int d, int dst0, int rmw_mask) {
+  const astr_cfg& c = g->cfg;
+  const Layout& L = g->L;
+  const int dm = dim_of(d), nt = c.npdc[d];
+  UpwindArgs ua;
+  const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
+  for (int k = 0; k < 3; ++k) { ua.s[k] = s[k]; ua.e[k] = e[k]; ua.box.lo[k] = s[k]; ua.box.hi[k] = e[k]; }
+  ua.box.lo[d] = s[d] - 1;
+  ua.lss = (nt == 1 || nt == 4) ? 0 : -ASTR_HM;           // solver.F90:1313-1327
+  ua.lee = (nt == 2 || nt == 4) ? dm : dm + ASTR_HM;
+  ua.dim = dm; ua.ntype = nt; ua.lchardecomp = c.lchardecomp; ua.sson = c.lchardecomp;
+  ProfScope ps(PC_DIV_I + d);
+  TRY(uw_sw_split(L, g->pool, g->up, g->th, d, ua.lss, ua.lee, g->st));
+  const double* in[5]; double* out[5];
+  for (int m = 0; m < 5; ++m) { in[m] = g->up + (size_t)(UP_FSW + m) * L.fstride; out[m] = g->up + (size_t)(UP_FHC + m) * L.fstride; }
+  TRY(sweep(d, OP_FLUXP, in, out, 5, EPI_STORE, -1, dm));
+  for (int m = 0; m < 5; ++m) { in[m] = g->up + (size_t)(UP_FSW + 5 + m) * L.fstride; out[m] = g->up + (size_t)(UP_FHC + 5 + m) * L.fstride; }
+  TRY(sweep(d, OP_FLUXM, in, out, 5, EPI_STORE, -1, dm));
+  TRY(uw_interface_flux(L, g->pool, g->up, g->th, d, ua, g->st));
+  return uw_fhdiff(L, g->pool, g->up, d, ua, dst0, rmw_mask, g->st);
+}
+
 int astr_gpu_rhscal(void) {
   NEED_CTX();
   if (!g->have_grad) return astr_fail_msg("rhscal before gradcal");
   const astr_cfg& c = g->cfg;
   const Layout& L = g->L;
   FluxRanges fr = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
+  const bool upw = g->upwind();
+  if (upw) {
+    // the convective part comes from convrsdcmp: the G slots carry the viscous fluxes only
+    for (int d = 0; d < 3; ++d) { fr.s[d] = 1; fr.e[d] = 0; }
+    if (c.lchardecomp) TRY(astr_gpu_ducrossensor());     // solver.F90:225
+  }
   if (c.diffterm) {
     // viscous stress + flux assembly of the block in one pass (sigma/qflux stay in registers and
     // reach memory only on the face shells the exchange reads), then the halo exchange
@@ -715,8 +801,8 @@ int astr_gpu_rhscal(void) {
   {
     ProfScope ps(PC_FLUX);
     Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-    if (!c.diffterm) TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
-    for (int d = 0; d < 3; ++d)                    // halo slabs of direction d (fluxes on halo nodes,
+    if (!c.diffterm && !upw) TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
+    for (int d = 0; d < 3 && (c.diffterm || !upw); ++d)   // halo slabs of direction d (fluxes on halo nodes,
       for (int side = 0; side < 2; ++side) {       // solver.F90:2200-2206)
         Box h = b;
         h.lo[d] = side ? dim_of(d) + 1 : -ASTR_HM;
@@ -730,8 +816,11 @@ int astr_gpu_rhscal(void) {
     for (int d = 0; d < 3; ++d) {
       const double* in[5]; double* out[5];
       for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_QRHS + m); }
-      ProfScope ps(PC_DIV_I + d);
-      TRY(sweep(d, OP_DERIV, in, out, 5, d == 0 ? EPI_STOREZ : EPI_ADD, s[d], e[d]));
+      if (c.diffterm || !upw) {
+        ProfScope ps(PC_DIV_I + d);
+        TRY(sweep(d, OP_DERIV, in, out, 5, d == 0 ? EPI_STOREZ : EPI_ADD, s[d], e[d]));
+      }
+      if (upw) TRY(convrsdcmp_dir(d, S_QRHS, (c.diffterm || d > 0) ? 31 : 0));
     }
     g->rhs_in_g = false;
     g->src_pending = false;
@@ -743,8 +832,16 @@ int astr_gpu_rhscal(void) {
   for (int d = 0; d < 3; ++d) {
     const double* in[5]; double* out[5];
     for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_G + 5 * d + m); }
-    ProfScope ps(PC_DIV_I + d);
-    TRY(sweep(d, OP_DERIV, in, out, 5, EPI_STOREZ, s[d], e[d]));
+    if (!upw) {
+      ProfScope ps(PC_DIV_I + d);
+      TRY(sweep(d, OP_DERIV, in, out, 5, EPI_STOREZ, s[d], e[d]));
+    } else {
+      if (c.diffterm) {   // the mass equation has no viscous flux: 4 fields
+        ProfScope ps(PC_DIV_I + d);
+        TRY(sweep(d, OP_DERIV, in + 1, out + 1, 4, EPI_STOREZ, s[d], e[d]));
+      }
+      TRY(convrsdcmp_dir(d, S_G + 5 * d, c.diffterm ? 30 : 0));
+    }
   }
   g->rhs_in_g = true;
   g->src_pending = false;

@@ -53,7 +53,9 @@ __host__ __device__ inline int chunk_start(int c, int nrows, int C) {
   return (c & 1) ? (s | 1) : (s & ~1);
 }
 
-enum { OP_DERIV = 0, OP_FILTER = 1 };
+// OP_FLUXP / OP_FLUXM: compact 5th-order upwind interface flux, flux_compact with flux_uw / flux_dw
+// (src/flux.F90:125-266); the solution at row `node` is the interface value fh(node), node -1..n
+enum { OP_DERIV = 0, OP_FILTER = 1, OP_FLUXP = 2, OP_FLUXM = 3 };
 enum { EPI_STORE = 0, EPI_STOREZ = 1, EPI_ADD = 2 };
 
 struct SweepArgs {
@@ -79,6 +81,7 @@ void astr_count_launch(int n = 1);
 
 // sweep.cu
 int astr_set_filter_coef(const FilterCoef& fc);
+int astr_set_flux_coef(double bfacmpld);
 size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out);
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
 int astr_sweep_max_chunks(int nrows);

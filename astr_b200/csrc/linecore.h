@@ -361,6 +361,21 @@ inline LocalFac local_factor(const std::vector<double>& a, const std::vector<dou
 inline void build_lhs(int optype, int ntype, int n, double alfa, std::vector<double>& a, std::vector<double>& c,
                       int& first_node, int& nsf, int& nsl) {
   const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
+  if (optype == 2 || optype == 3) {
+    // compact_flux_initiate (src/flux.F90:32-118), scheme 543; alfa carries bfacmpld.
+    // Unknowns are the interface values fh(first_node..last); '+' (optype 2) / '-' (optype 3).
+    first_node = p0 ? -1 : -2;
+    const int last = pm ? n : n + 1;
+    const int N = last - first_node + 1;
+    const double up = 0.5 - (1.0 / 6.0) * alfa, dn = (1.0 / 6.0) + (1.0 / 6.0) * alfa;
+    a.assign(N, optype == 2 ? up : dn); c.assign(N, optype == 2 ? dn : up);
+    const int e = N - 1;
+    a[0] = c[0] = 0.0; a[e] = c[e] = 0.0;
+    if (p0) { a[0] = c[0] = 2.0; a[1] = c[1] = 0.25; }
+    if (pm) { a[e] = c[e] = 2.0; a[e - 1] = c[e - 1] = 0.25; }
+    nsf = p0 ? 2 : 1; nsl = pm ? 2 : 1;
+    return;
+  }
   if (optype == 0) {
     first_node = p0 ? 0 : -1;
     const int last = pm ? n : n + 1;

@@ -24,6 +24,7 @@ enum Slot {
 
 struct Thermo {
   double reynolds, prandtl, const1, const2, const5, const6, tempconst, tempconst1;
+  double gamma, mach;
 };
 
 struct Box { int lo[3], hi[3]; };   // inclusive node ranges
@@ -60,3 +61,29 @@ int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int
 int pw_unpack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, const double* buf,
               cudaStream_t st);
 // Fortran (im+11)(jm+11)(km+11) box <-> padded device box is done with cudaMemcpy3D in api.cu
+
+// ---- upwind-biased compact convection (upwind.cu), conschm = '543c' -------------------------
+// fields of the lazily allocated upwind pool (same Layout as every other field)
+enum UpSlot {
+  UP_FSW = 0,     // 10 Steger-Warming split fluxes F+(5), F-(5) at nodes
+  UP_FHC = 10,    // 10 compact interface fluxes fhcp(5), fhcm(5); interface i is stored at node i
+  UP_FH = 20,     // 5  limited interface flux Fh
+  UP_SSF = 25,    // 1  Ducros sensor
+  UP_LSH = 26,    // 1  lshock as 0/1
+  UP_TOTAL = 27
+};
+struct UpwindArgs {
+  Box box;              // interfaces treated: is-1..ie along the direction, s..e in the two others
+  int s[3], e[3];       // is..ke
+  int lss, lee;         // node range of the split fluxes along the direction (solver.F90:1313-1327)
+  int dim, ntype;       // im/jm/km and npdc of the direction
+  int lchardecomp, sson;
+};
+int uw_sw_split(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, int lss, int lee,
+                cudaStream_t st);
+int uw_interface_flux(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, const UpwindArgs& a,
+                      cudaStream_t st);
+int uw_fhdiff(const Layout& L, double* pool, const double* up, int dir, const UpwindArgs& a, int dst0, int rmw_mask,
+              cudaStream_t st);
+int uw_ducros_ssf(const Layout& L, const double* pool, double* up, const int npdc[3], cudaStream_t st);
+int uw_ducros_flag(const Layout& L, double* up, const int npdc[3], double shkcrt, cudaStream_t st);

@@ -33,6 +33,16 @@ int astr_set_filter_coef(const FilterCoef& fc) {
   return 0;
 }
 
+// compact_flux_rhs interior coefficients (src/flux.F90:247-262) for the current bfacmpld
+__constant__ double c_flx[4];
+int astr_set_flux_coef(double b) {
+  const double h[4] = {1.0 / 18.0 - (1.0 / 36.0) * b, 19.0 / 18.0 - (9.0 / 36.0) * b, 5.0 / 9.0 + (9.0 / 36.0) * b,
+                       (1.0 / 36.0) * b};
+  cudaError_t e = cudaMemcpyToSymbol(c_flx, h, sizeof h);
+  if (e != cudaSuccess) return astr_fail("cudaMemcpyToSymbol(c_flx)", e, __FILE__, __LINE__);
+  return 0;
+}
+
 namespace {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
@@ -46,6 +56,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <int OP> struct OpTraits;
 template <> struct OpTraits<OP_DERIV> { static constexpr int H = 2, W = 5; };
 template <> struct OpTraits<OP_FILTER> { static constexpr int H = 5, W = 11; };
+template <> struct OpTraits<OP_FLUXP> { static constexpr int H = 2, W = 5; };
+template <> struct OpTraits<OP_FLUXM> { static constexpr int H = 2, W = 5; };
 
 // Interior right-hand side at phase t (t mod W is a compile-time constant after
 // unrolling): the value of node m+k sits in window slot (t+H+k) mod W.
@@ -58,6 +70,12 @@ __device__ __forceinline__ double interior_rhs(const double (&w)[OpTraits<OP>::W
     const double var1 = WS(1) - WS(-1);
     const double var2 = WS(2) - WS(-2);
     return (7.0 / 9.0) * var1 + (1.0 / 36.0) * var2;
+  } else if (OP == OP_FLUXP) {
+    // src/flux.F90:247-253
+    return c_flx[0] * WS(-1) + c_flx[1] * WS(0) + c_flx[2] * WS(1) + c_flx[3] * WS(2);
+  } else if (OP == OP_FLUXM) {
+    // src/flux.F90:255-261
+    return c_flx[0] * WS(2) + c_flx[1] * WS(1) + c_flx[2] * WS(0) + c_flx[3] * WS(-1);
   } else {
     // src/filter.F90:271-283
     const double var0 = WS(0) + WS(0);
@@ -77,7 +95,15 @@ __device__ __forceinline__ double interior_rhs(const double (&w)[OpTraits<OP>::W
 template <int OP, class FN>
 __device__ __forceinline__ void closure_first(FN F, int ntype, int n, double (&sf)[5]) {
   const bool phys = (ntype == 1 || ntype == 4);
-  if (OP == OP_DERIV) {
+  if (OP == OP_FLUXP || OP == OP_FLUXM) {
+    if (phys) {  // src/flux.F90:189-199, rows -1 and 0
+      sf[0] = 2.5 * F(0) + 0.5 * F(1);
+      sf[1] = 0.75 * F(0) + 0.75 * F(1);
+    } else {     // :205-209, row -2: 6th-order explicit
+      const double var1 = F(-2) + F(-1), var2 = F(-3) + F(0), var3 = F(-4) + F(1);
+      sf[0] = (37.0 / 60.0) * var1 - (2.0 / 15.0) * var2 + (1.0 / 60.0) * var3;
+    }
+  } else if (OP == OP_DERIV) {
     if (phys) {  // src/derivative.F90:230-248
       sf[0] = -2.5 * F(0) + 2.0 * F(1) + 0.5 * F(2);
       sf[1] = 0.75 * (F(2) - F(0));
@@ -118,7 +144,16 @@ __device__ __forceinline__ void closure_first(FN F, int ntype, int n, double (&s
 template <int OP, class FN>
 __device__ __forceinline__ void closure_last(FN F, int ntype, int n, double (&sl)[5]) {
   const bool phys = (ntype == 2 || ntype == 4);
-  if (OP == OP_DERIV) {
+  if (OP == OP_FLUXP || OP == OP_FLUXM) {
+    if (phys) {  // src/flux.F90:217-225, rows n-1 and n
+      sl[0] = 0.75 * F(n) + 0.75 * F(n - 1);
+      sl[1] = 2.5 * F(n) + 0.5 * F(n - 1);
+    } else {     // :231-236, row n+1
+      const int j = n + 1;
+      const double var1 = F(j) + F(j + 1), var2 = F(j - 1) + F(j + 2), var3 = F(j - 2) + F(j + 3);
+      sl[0] = (37.0 / 60.0) * var1 - (2.0 / 15.0) * var2 + (1.0 / 60.0) * var3;
+    }
+  } else if (OP == OP_DERIV) {
     if (phys) {  // src/derivative.F90:264-281
       sl[0] = 0.75 * (F(n) - F(n - 2));
       sl[1] = 2.5 * F(n) - 2.0 * F(n - 1) - 0.5 * F(n - 2);
@@ -466,9 +501,10 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
             const int nd = nd0 + 2 * k * LW;
             if (nd <= w_hi) {
               const int r = nd - first_node;
+              const int rx = max(r, 0);   // nd may sit one below the first row (its half is not stored)
               const double2 gv = *reinterpret_cast<const double2*>(srow + nd);
               double2 x;
-              x.x = __fma_rn(qb[r], xrow[ch[r] * ASTR_BW], gv.x);
+              x.x = __fma_rn(qb[rx], xrow[ch[rx] * ASTR_BW], gv.x);
               x.y = __fma_rn(qb[r + 1], xrow[ch[r + 1] * ASTR_BW], gv.y);
               if (epi == EPI_ADD) { x.x = old[k].x + x.x; x.y = old[k].y + x.y; }
               else if (epi == EPI_STOREZ) {
@@ -618,6 +654,14 @@ int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st) 
     if (dir == 0) return launch_c<0, OP_DERIV>(a, st);
     if (dir == 1) return launch_c<1, OP_DERIV>(a, st);
     return launch_c<2, OP_DERIV>(a, st);
+  } else if (optype == OP_FLUXP) {
+    if (dir == 0) return launch_c<0, OP_FLUXP>(a, st);
+    if (dir == 1) return launch_c<1, OP_FLUXP>(a, st);
+    return launch_c<2, OP_FLUXP>(a, st);
+  } else if (optype == OP_FLUXM) {
+    if (dir == 0) return launch_c<0, OP_FLUXM>(a, st);
+    if (dir == 1) return launch_c<1, OP_FLUXM>(a, st);
+    return launch_c<2, OP_FLUXM>(a, st);
   } else {
     if (dir == 0) return launch_c<0, OP_FILTER>(a, st);
     if (dir == 1) return launch_c<1, OP_FILTER>(a, st);

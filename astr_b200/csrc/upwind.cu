@@ -1,0 +1,462 @@
+// astr_b200/csrc/upwind.cu -- the upwind-biased compact convection path, conschm = '543c'
+// (sm_100a).  Replaces convrsdcmp (src/solver.F90:1271-1937) and ducrossensor
+// (src/commcal.F90:196-357); the ten compact interface-flux line solves per direction run on
+// the sweep engine (sweep.cu, OP_FLUXP / OP_FLUXM = flux_compact with flux_uw / flux_dw,
+// src/flux.F90:125-266).
+//
+// Per direction d:
+//   k_sw_split  : Steger-Warming split fluxes F+ / F- at every node of the line range
+//                 lss..lee (src/riemann.F90:23-161)                     -> 10 fields
+//   sweep x 2   : fhcp = flux_compact(flux_uw, F+), fhcm = flux_compact(flux_dw, F-),
+//                 interfaces -1..dim                                    -> 10 fields
+//   k_upwind    : per interface is-1..ie: Roe-averaged eigenvectors (chardecomp,
+//                 src/solver.F90:1958-2162), projection of the 5-node stencils and of the
+//                 compact value, MP5 limiter (mplimiter / MP5, src/flux.F90:363-501), back
+//                 projection                                            -> Fh, 5 fields
+//   k_fhdiff    : G_d -= Fh(i) - Fh(i-1) on is..ie (the RK update sums the G slots; the
+//                 viscous derivative is already there)
+// All kernels are one thread per node / interface, i fastest.  Non-dimensional gas, no
+// species; crinod is all false (lcracon off), so the first-order fallback of
+// solver.F90:1466-1470 is unreachable.
+#include "pointwise.cuh"
+
+namespace {
+
+constexpr int UW_T = 128;
+
+__device__ __forceinline__ bool box_node(const Box& b, int& i, int& j, int& k) {
+  i = b.lo[0] + blockIdx.x * UW_T + threadIdx.x;
+  j = b.lo[1] + blockIdx.y;
+  k = b.lo[2] + blockIdx.z;
+  return i <= b.hi[0];
+}
+inline dim3 box_grid(const Box& b) {
+  return dim3((b.hi[0] - b.lo[0] + UW_T) / UW_T, b.hi[1] - b.lo[1] + 1, b.hi[2] - b.lo[2] + 1);
+}
+inline bool box_empty(const Box& b) {
+  return b.hi[0] < b.lo[0] || b.hi[1] < b.lo[1] || b.hi[2] < b.lo[2];
+}
+
+// ---------------------------------------------------------------------------------
+// flux_steger_warming (src/riemann.F90:23-161), nondimen: sos = sqrt(T)/Mach (fludyna.F90:851)
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_sw_split(const Layout L, const double* __restrict__ pool, double* __restrict__ up, const Thermo th,
+                           const Box b) {
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double eps = 0.04;
+  const double gamma = th.gamma;
+  const double rho = pool[S_RHO * fs + x];
+  const double v1 = pool[(S_VEL + 0) * fs + x], v2 = pool[(S_VEL + 1) * fs + x], v3 = pool[(S_VEL + 2) * fs + x];
+  const double prs = pool[S_PRS * fs + x], tmp = pool[S_TMP * fs + x], jacob = pool[S_JAC * fs + x];
+  const double d1 = pool[(S_DXI + 3 * DIR + 0) * fs + x], d2 = pool[(S_DXI + 3 * DIR + 1) * fs + x],
+               d3 = pool[(S_DXI + 3 * DIR + 2) * fs + x];
+  double q[5];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) q[m] = pool[(S_Q + m) * fs + x];
+  const double uu = d1 * v1 + d2 * v2 + d3 * v3;
+  const double var0 = 1.0 / sqrt(d1 * d1 + d2 * d2 + d3 * d3);
+  const double g1 = d1 * var0, g2 = d2 * var0, g3 = d3 * var0;
+  const double gm2 = 0.5 / gamma;
+  const double css = sqrt(tmp) / th.mach;
+  const double csa = css / var0;
+  const double lmach = uu / csa;
+  double fp[5], fm[5];
+  if (lmach >= 1.0 || lmach <= -1.0) {
+    double f[5];
+    f[0] = jacob * q[0] * uu;
+    f[1] = jacob * (q[1] * uu + d1 * prs);
+    f[2] = jacob * (q[2] * uu + d2 * prs);
+    f[3] = jacob * (q[3] * uu + d3 * prs);
+    f[4] = jacob * (q[4] + prs) * uu;
+    const bool pos = lmach >= 1.0;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) { fp[m] = pos ? f[m] : 0.0; fm[m] = pos ? 0.0 : f[m]; }
+  } else {
+    const double l1 = uu, l4 = uu + csa, l5 = uu - csa;
+    const double l1p = 0.5 * (l1 + sqrt(l1 * l1 + eps * eps));
+    const double l4p = 0.5 * (l4 + sqrt(l4 * l4 + eps * eps));
+    const double l5p = 0.5 * (l5 + sqrt(l5 * l5 + eps * eps));
+    const double l1m = l1 - l1p, l4m = l4 - l4p, l5m = l5 - l5p;
+    const double fhi = 0.5 * (gamma - 1.0) * (v1 * v1 + v2 * v2 + v3 * v3);
+    const double jro = jacob * rho;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const double a1 = s ? l1m : l1p, a4 = s ? l4m : l4p, a5 = s ? l5m : l5p;
+      const double var1 = a1;
+      const double var2 = a4 - a5;
+      const double var3 = 2.0 * a1 - a4 - a5;
+      const double var4 = var1 - var3 * gm2;
+      double* f = s ? fm : fp;
+      f[0] = jro * var4;
+      f[1] = jro * (var4 * v1 + var2 * css * g1 * gm2);
+      f[2] = jro * (var4 * v2 + var2 * css * g2 * gm2);
+      f[3] = jro * (var4 * v3 + var2 * css * g3 * gm2);
+      f[4] = jacob * (var1 * q[4] + rho * (var2 * uu * var0 * css * gm2 - var3 * (fhi + css * css) * gm2 / (gamma - 1.0)));
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    up[(UP_FSW + m) * fs + x] = fp[m];
+    up[(UP_FSW + 5 + m) * fs + x] = fm[m];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// minmod2 / minmod4 (src/commfunc.F90:699-738), MP5 (src/flux.F90:434-501)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double minmod2(double a, double b) {
+  if (a > 0.0 && b > 0.0) return fmin(fabs(a), fabs(b));
+  if (a < 0.0 && b < 0.0) return -1.0 * fmin(fabs(a), fabs(b));
+  return 0.0;
+}
+__device__ __forceinline__ double minmod4(double a, double b, double c, double d) {
+  if (a > 0.0 && b > 0.0 && c > 0.0 && d > 0.0) return fmin(fmin(fabs(a), fabs(b)), fmin(fabs(c), fabs(d)));
+  if (a < 0.0 && b < 0.0 && c < 0.0 && d < 0.0) return -1.0 * fmin(fmin(fabs(a), fabs(b)), fmin(fabs(c), fabs(d)));
+  return 0.0;
+}
+__device__ __forceinline__ double mp5(const double (&u)[5], const double ulinear, const bool discont) {
+  double var1 = u[3] - u[2];
+  double var2 = 4.0 * (u[2] - u[1]);
+  const double uMP = u[2] + minmod2(var1, var2);
+  var1 = (ulinear - u[2]) * (ulinear - uMP);
+  if (discont && var1 >= 1.e-10) {
+    const double dm1 = u[0] - 2.0 * u[1] + u[2];
+    const double d0 = u[1] - 2.0 * u[2] + u[3];
+    const double d1 = u[2] - 2.0 * u[3] + u[4];
+    const double dhm1 = minmod4(4.0 * dm1 - d0, 4.0 * d0 - dm1, dm1, d0);
+    const double dh0 = minmod4(4.0 * d0 - d1, 4.0 * d1 - d0, d0, d1);
+    const double uUL = u[2] + 4.0 * (u[2] - u[1]);
+    const double uAV = 0.5 * (u[2] + u[3]);
+    const double uMD = uAV - 0.5 * dh0;
+    const double uLC = u[2] + 0.5 * (u[2] - u[1]) + 1.333333333333333 * dhm1;
+    var1 = fmin(fmin(u[2], u[3]), uMD);
+    var2 = fmin(fmin(u[2], uUL), uLC);
+    const double uMIN = fmax(var1, var2);
+    var1 = fmax(fmax(u[2], u[3]), uMD);
+    var2 = fmax(fmax(u[2], uUL), uLC);
+    const double uMAX = fmin(var1, var2);
+    var1 = uMIN - ulinear;
+    var2 = uMAX - ulinear;
+    return ulinear + minmod2(var1, var2);
+  }
+  return ulinear;
+}
+
+// ---------------------------------------------------------------------------------
+// chardecomp (src/solver.F90:1958-2162), without COMB.  Returns false where the reference
+// stops (degenerate metric normal).
+// ---------------------------------------------------------------------------------
+struct Eig { double R[5][5], Lm[5][5]; };
+
+__device__ __forceinline__ bool chardecomp(const double gamma, const double ro_l, const double p_l, const double E_l,
+                                           const double (&vl)[3], const double (&dl)[3], const double ro_r,
+                                           const double p_r, const double E_r, const double (&vr)[3],
+                                           const double (&dr)[3], Eig& e) {
+  const double rero = 1.e-12;
+  const double WRoe = sqrt(ro_l) / (sqrt(ro_l) + sqrt(ro_r));
+  const double WRoe1 = 1.0 - WRoe;
+  const double u1 = WRoe * vl[0] + WRoe1 * vr[0];
+  const double u2 = WRoe * vl[1] + WRoe1 * vr[1];
+  const double u3 = WRoe * vl[2] + WRoe1 * vr[2];
+  const double KRoe = 0.5 * (u1 * u1 + u2 * u2 + u3 * u3);
+  const double HL = (E_l + p_l) / ro_l;
+  const double HR = (E_r + p_r) / ro_r;
+  const double HRoe = WRoe * HL + WRoe1 * HR;
+  const double Css = sqrt((gamma - 1.0) * (HRoe - KRoe));
+  const double rcs = 1.0 / Css;
+  const double var1 = 0.5 * (dl[0] + dr[0]);
+  const double var2 = 0.5 * (dl[1] + dr[1]);
+  const double var3 = 0.5 * (dl[2] + dr[2]);
+  const double var4 = 1.0 / sqrt(var1 * var1 + var2 * var2 + var3 * var3);
+  const double g1 = var1 * var4, g2 = var2 * var4, g3 = var3 * var4;
+  const double ugp = u1 * g1 + u2 * g2 + u3 * g3;
+  const double b1 = (gamma - 1.0) / (Css * Css);
+  const double b2 = 1.0 + 2.0 * b1 * KRoe - b1 * HRoe;
+#define LE(m, n) e.Lm[(m) - 1][(n) - 1]
+#define RE(m, n) e.R[(m) - 1][(n) - 1]
+  LE(1, 1) = 0.5 * (b2 + ugp * rcs);
+  LE(1, 2) = -0.5 * (b1 * u1 + g1 * rcs);
+  LE(1, 3) = -0.5 * (b1 * u2 + g2 * rcs);
+  LE(1, 4) = -0.5 * (b1 * u3 + g3 * rcs);
+  LE(1, 5) = 0.5 * b1;
+  RE(1, 1) = 1.0; RE(2, 1) = u1 - Css * g1; RE(3, 1) = u2 - Css * g2; RE(4, 1) = u3 - Css * g3;
+  RE(5, 1) = HRoe - ugp * Css;
+  LE(2, 1) = 1.0 - b2; LE(2, 2) = b1 * u1; LE(2, 3) = b1 * u2; LE(2, 4) = b1 * u3; LE(2, 5) = -b1;
+  RE(1, 2) = 1.0; RE(2, 2) = u1; RE(3, 2) = u2; RE(4, 2) = u3; RE(5, 2) = HRoe - 1.0 / b1;
+  if (fabs(var1) > rero) {
+    const double rgp = 1.0 / g1;
+    LE(3, 1) = (ugp * g2 - u2) * rgp; LE(3, 2) = -g2; LE(3, 3) = (1.0 - g2 * g2) * rgp; LE(3, 4) = -g2 * g3 * rgp;
+    LE(3, 5) = 0.0;
+    LE(4, 1) = (ugp * g3 - u3) * rgp; LE(4, 2) = -g3; LE(4, 3) = -g2 * g3 * rgp; LE(4, 4) = (1.0 - g3 * g3) * rgp;
+    LE(4, 5) = 0.0;
+    RE(1, 3) = 0.0; RE(2, 3) = -g2; RE(3, 3) = g1; RE(4, 3) = 0.0; RE(5, 3) = u2 * g1 - u1 * g2;
+    RE(1, 4) = 0.0; RE(2, 4) = -g3; RE(3, 4) = 0.0; RE(4, 4) = g1; RE(5, 4) = u3 * g1 - u1 * g3;
+  } else if (fabs(var2) > rero) {
+    const double rgp = 1.0 / g2;
+    LE(3, 1) = (ugp * g1 - u1) * rgp; LE(3, 2) = (1.0 - g1 * g1) * rgp; LE(3, 3) = -g1; LE(3, 4) = -g1 * g3 * rgp;
+    LE(3, 5) = 0.0;
+    LE(4, 1) = (ugp * g3 - u3) * rgp; LE(4, 2) = -g1 * g3 * rgp; LE(4, 3) = -g3; LE(4, 4) = (1.0 - g3 * g3) * rgp;
+    LE(4, 5) = 0.0;
+    RE(1, 3) = 0.0; RE(2, 3) = g2; RE(3, 3) = -g1; RE(4, 3) = 0.0; RE(5, 3) = u1 * g2 - u2 * g1;
+    RE(1, 4) = 0.0; RE(2, 4) = 0.0; RE(3, 4) = -g3; RE(4, 4) = g2; RE(5, 4) = u3 * g2 - u2 * g3;
+  } else if (fabs(var3) > rero) {
+    const double rgp = 1.0 / g3;
+    LE(3, 1) = (ugp * g1 - u1) * rgp; LE(3, 2) = (1.0 - g1 * g1) * rgp; LE(3, 3) = -g1 * g2 * rgp; LE(3, 4) = -g1;
+    LE(3, 5) = 0.0;
+    LE(4, 1) = (ugp * g2 - u2) * rgp; LE(4, 2) = -g1 * g2 * rgp; LE(4, 3) = (1.0 - g2 * g2) * rgp; LE(4, 4) = -g2;
+    LE(4, 5) = 0.0;
+    RE(1, 3) = 0.0; RE(2, 3) = g3; RE(3, 3) = 0.0; RE(4, 3) = -g1; RE(5, 3) = u1 * g3 - u3 * g1;
+    RE(1, 4) = 0.0; RE(2, 4) = 0.0; RE(3, 4) = g3; RE(4, 4) = -g2; RE(5, 4) = u2 * g3 - u3 * g2;
+  } else {
+    return false;
+  }
+  LE(5, 1) = 0.5 * (b2 - ugp * rcs);
+  LE(5, 2) = -0.5 * (b1 * u1 - g1 * rcs);
+  LE(5, 3) = -0.5 * (b1 * u2 - g2 * rcs);
+  LE(5, 4) = -0.5 * (b1 * u3 - g3 * rcs);
+  LE(5, 5) = 0.5 * b1;
+  RE(1, 5) = 1.0; RE(2, 5) = u1 + Css * g1; RE(3, 5) = u2 + Css * g2; RE(4, 5) = u3 + Css * g3;
+  RE(5, 5) = HRoe + ugp * Css;
+#undef LE
+#undef RE
+  return true;
+}
+
+// ---------------------------------------------------------------------------------
+// interface loop of convrsdcmp (src/solver.F90:1359-1492 and the j/k copies)
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_upwind(const Layout L, const double* __restrict__ pool, double* __restrict__ up, const Thermo th,
+                         const UpwindArgs a) {
+  int ijk[3];
+  if (!box_node(a.box, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk);
+  const int i = ijk[DIR];
+  // window of nodes for the + and - stencils, clamped to lss..lee (iwind6, solver.F90:1236-1257)
+  long long op[5], om[5];
+#pragma unroll
+  for (int n = 1; n <= 5; ++n) {
+    int w = i + n - 3;
+    w = max(a.lss, min(a.lee, w));
+    op[n - 1] = (long long)(w - i) * sd;
+    w = i + 4 - n;
+    w = max(a.lss, min(a.lee, w));
+    om[n - 1] = (long long)(w - i) * sd;
+  }
+  double fsp[5][5], fsm[5][5], fcp[5], fcm[5];   // [component][stencil slot]
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const double* fp = up + (UP_FSW + m) * fs + x;
+    const double* fm = up + (UP_FSW + 5 + m) * fs + x;
+#pragma unroll
+    for (int n = 0; n < 5; ++n) { fsp[m][n] = fp[op[n]]; fsm[m][n] = fm[om[n]]; }
+    fcp[m] = up[(UP_FHC + m) * fs + x];
+    fcm[m] = up[(UP_FHC + 5 + m) * fs + x];
+  }
+  bool lsh = true;                      // solver.F90:1437-1447
+  if (a.sson) {
+    const double* ls = up + UP_LSH * fs + x;
+    if (i < 0) lsh = ls[sd] != 0.0;
+    else if (i + 1 > a.dim) lsh = ls[0] != 0.0;
+    else lsh = (ls[0] != 0.0) || (ls[sd] != 0.0);
+  }
+  const bool nolim = (a.ntype == 1 && (i == 0 || i == 1)) || (a.ntype == 2 && (i == a.dim - 1 || i == a.dim - 2));
+  double Fh[5];
+  if (a.lchardecomp) {
+    Eig e;
+    const long long xr = x + sd;
+    const double vl[3] = {pool[(S_VEL + 0) * fs + x], pool[(S_VEL + 1) * fs + x], pool[(S_VEL + 2) * fs + x]};
+    const double vr[3] = {pool[(S_VEL + 0) * fs + xr], pool[(S_VEL + 1) * fs + xr], pool[(S_VEL + 2) * fs + xr]};
+    const double dl[3] = {pool[(S_DXI + 3 * DIR + 0) * fs + x], pool[(S_DXI + 3 * DIR + 1) * fs + x],
+                          pool[(S_DXI + 3 * DIR + 2) * fs + x]};
+    const double dr[3] = {pool[(S_DXI + 3 * DIR + 0) * fs + xr], pool[(S_DXI + 3 * DIR + 1) * fs + xr],
+                          pool[(S_DXI + 3 * DIR + 2) * fs + xr]};
+    const bool ok = chardecomp(th.gamma, pool[S_RHO * fs + x], pool[S_PRS * fs + x], pool[(S_Q + 4) * fs + x], vl, dl,
+                               pool[S_RHO * fs + xr], pool[S_PRS * fs + xr], pool[(S_Q + 4) * fs + xr], vr, dr, e);
+    if (!ok) {
+      // the reference stops here (' !! ERROR 1 @ chardecomp'); poison the result so that it is seen
+#pragma unroll
+      for (int m = 0; m < 5; ++m) up[(UP_FH + m) * fs + x] = __longlong_as_double(0x7ff8000000000000LL);
+      return;
+    }
+    double Fhc[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      double cp[5], cm[5];
+#pragma unroll
+      for (int n = 0; n < 5; ++n) {
+        cp[n] = e.Lm[m][0] * fsp[0][n] + e.Lm[m][1] * fsp[1][n] + e.Lm[m][2] * fsp[2][n] + e.Lm[m][3] * fsp[3][n] +
+                e.Lm[m][4] * fsp[4][n];
+        cm[n] = e.Lm[m][0] * fsm[0][n] + e.Lm[m][1] * fsm[1][n] + e.Lm[m][2] * fsm[2][n] + e.Lm[m][3] * fsm[3][n] +
+                e.Lm[m][4] * fsm[4][n];
+      }
+      const double hp = e.Lm[m][0] * fcp[0] + e.Lm[m][1] * fcp[1] + e.Lm[m][2] * fcp[2] + e.Lm[m][3] * fcp[3] +
+                        e.Lm[m][4] * fcp[4];
+      const double hm = e.Lm[m][0] * fcm[0] + e.Lm[m][1] * fcm[1] + e.Lm[m][2] * fcm[2] + e.Lm[m][3] * fcm[3] +
+                        e.Lm[m][4] * fcm[4];
+      const double v1 = nolim ? hp : mp5(cp, hp, lsh);
+      const double v2 = nolim ? hm : mp5(cm, hm, lsh);
+      Fhc[m] = v1 + v2;
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+      Fh[m] = e.R[m][0] * Fhc[0] + e.R[m][1] * Fhc[1] + e.R[m][2] * Fhc[2] + e.R[m][3] * Fhc[3] + e.R[m][4] * Fhc[4];
+  } else {
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const double v1 = nolim ? fcp[m] : mp5(fsp[m], fcp[m], lsh);
+      const double v2 = nolim ? fcm[m] : mp5(fsm[m], fcm[m], lsh);
+      Fh[m] = v1 + v2;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 5; ++m) up[(UP_FH + m) * fs + x] = Fh[m];
+}
+
+// qrhs(i) += Fh(i) - Fh(i-1) on is..ie (solver.F90:1494-1498), then qrhs = -qrhs (:242): the G slot
+// of direction DIR, which already holds the viscous derivative (or nothing), gets -(Fh(i)-Fh(i-1))
+// dst0: first of the 5 destination slots (the G slots of the direction, or qrhs on the explicit
+// path); rmw_mask bit m: component m already holds a partial sum there
+template <int DIR>
+__global__ void k_fhdiff(const Layout L, double* __restrict__ pool, const double* __restrict__ up, const UpwindArgs a,
+                         const int dst0, const int rmw_mask) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int ijk[3];
+  if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk);
+  bool in = true;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) in = in && ijk[d] >= a.s[d] && ijk[d] <= a.e[d];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    double g = ((rmw_mask >> m) & 1) ? pool[(dst0 + m) * fs + x] : 0.0;
+    if (in) {
+      const double* fh = up + (UP_FH + m) * fs + x;
+      g = g - (fh[0] - fh[-sd]);
+    }
+    pool[(dst0 + m) * fs + x] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// ducrossensor (src/commcal.F90:196-357): ssf, then lshock from the +-5-node directional maxima
+// ---------------------------------------------------------------------------------
+__global__ void k_ducros_ssf(const Layout L, const double* __restrict__ pool, double* __restrict__ up,
+                             const int n0, const int n1, const int n2) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  // dvel(m,n) = sum_d raw(d,m) dxi(d,n): divergence and vorticity, gradcal's accumulation order
+  double dv[3][3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const double r0 = pool[(S_RAW + 0 + m) * fs + x], r1 = pool[(S_RAW + 4 + m) * fs + x], r2 = pool[(S_RAW + 8 + m) * fs + x];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+      dv[m][n] = r0 * pool[(S_DXI + 0 + n) * fs + x] + r1 * pool[(S_DXI + 3 + n) * fs + x] + r2 * pool[(S_DXI + 6 + n) * fs + x];
+  }
+  const double s = dv[0][0] + dv[1][1] + dv[2][2];
+  const double div2 = s * s;
+  const double ox = dv[2][1] - dv[1][2], oy = dv[0][2] - dv[2][0], oz = dv[1][0] - dv[0][1];
+  const double vort = ox * ox + oy * oy + oz * oz;
+  const double* p = pool + S_PRS * fs + x;
+  const long long ip = (n0 == 2 && i + 1 > L.im) ? 0 : 1, im_ = (n0 == 1 && i - 1 < 0) ? 0 : -1;
+  const long long jp = (n1 == 2 && j + 1 > L.jm) ? 0 : L.sj, jm_ = (n1 == 1 && j - 1 < 0) ? 0 : -L.sj;
+  const long long kp = (n2 == 2 && k + 1 > L.km) ? 0 : L.sk, km_ = (n2 == 1 && k - 1 < 0) ? 0 : -L.sk;
+  const double p0 = p[0];
+  const double dpdi = fabs(p[ip] - 2.0 * p0 + p[im_]) / (p[ip] + 2.0 * p0 + p[im_]);
+  const double dpdj = fabs(p[jp] - 2.0 * p0 + p[jm_]) / (p[jp] + 2.0 * p0 + p[jm_]);
+  const double dpdk = fabs(p[kp] - 2.0 * p0 + p[km_]) / (p[kp] + 2.0 * p0 + p[km_]);
+  up[UP_SSF * fs + x] = div2 / (div2 + vort + 1.e-30) * fmax(fmax(dpdi, dpdj), dpdk);
+}
+
+__global__ void k_ducros_flag(const Layout L, double* __restrict__ up, const int n0, const int n1, const int n2,
+                              const double shkcrt) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double* ssf = up + UP_SSF * fs + x;
+  double m = 0.0;
+#pragma unroll
+  for (int o = -ASTR_HM + 1; o <= ASTR_HM; ++o) {
+    int ii = i + o;
+    if (n0 == 1 && ii < 0) ii = 0;
+    if (n0 == 2 && ii > L.im) ii = L.im;
+    m = fmax(m, ssf[ii - i]);
+  }
+#pragma unroll
+  for (int o = -ASTR_HM + 1; o <= ASTR_HM; ++o) {
+    int jj = j + o;
+    if (n1 == 1 && jj < 0) jj = 0;
+    if (n1 == 2 && jj > L.jm) jj = L.jm;
+    m = fmax(m, ssf[(long long)(jj - j) * L.sj]);
+  }
+#pragma unroll
+  for (int o = -ASTR_HM + 1; o <= ASTR_HM; ++o) {
+    int kk = k + o;
+    if (n2 == 1 && kk < 0) kk = 0;
+    if (n2 == 2 && kk > L.km) kk = L.km;
+    m = fmax(m, ssf[(long long)(kk - k) * L.sk]);
+  }
+  up[UP_LSH * fs + x] = (m > shkcrt) ? 1.0 : 0.0;
+}
+
+#define LAUNCH_CHECK_UW()                     \
+  do {                                        \
+    astr_count_launch();                      \
+    CUDA_OK(cudaGetLastError());              \
+  } while (0)
+
+}  // namespace
+
+int uw_sw_split(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, int lss, int lee,
+                cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  b.lo[dir] = lss; b.hi[dir] = lee;
+  if (box_empty(b)) return 0;
+  if (dir == 0) k_sw_split<0><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, th, b);
+  else if (dir == 1) k_sw_split<1><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, th, b);
+  else k_sw_split<2><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, th, b);
+  LAUNCH_CHECK_UW();
+  return 0;
+}
+
+int uw_interface_flux(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, const UpwindArgs& a,
+                      cudaStream_t st) {
+  if (box_empty(a.box)) return 0;
+  if (dir == 0) k_upwind<0><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+  else if (dir == 1) k_upwind<1><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+  else k_upwind<2><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+  LAUNCH_CHECK_UW();
+  return 0;
+}
+
+int uw_fhdiff(const Layout& L, double* pool, const double* up, int dir, const UpwindArgs& a, int dst0, int rmw_mask,
+              cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  if (dir == 0) k_fhdiff<0><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, a, dst0, rmw_mask);
+  else if (dir == 1) k_fhdiff<1><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, a, dst0, rmw_mask);
+  else k_fhdiff<2><<<box_grid(b), UW_T, 0, st>>>(L, pool, up, a, dst0, rmw_mask);
+  LAUNCH_CHECK_UW();
+  return 0;
+}
+
+int uw_ducros_ssf(const Layout& L, const double* pool, double* up, const int npdc[3], cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_ducros_ssf<<<box_grid(b), UW_T, 0, st>>>(L, pool, up, npdc[0], npdc[1], npdc[2]);
+  LAUNCH_CHECK_UW();
+  return 0;
+}
+int uw_ducros_flag(const Layout& L, double* up, const int npdc[3], double shkcrt, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_ducros_flag<<<box_grid(b), UW_T, 0, st>>>(L, up, npdc[0], npdc[1], npdc[2], shkcrt);
+  LAUNCH_CHECK_UW();
+  return 0;
+}

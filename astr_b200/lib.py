@@ -23,6 +23,7 @@ FIELD_IDS = {
     **{f"x{n + 1}": 47 + n for n in range(3)},
     **{f"qsave{n + 1}": 50 + n for n in range(5)},
     **{f"vor{n + 1}": 55 + n for n in range(3)},
+    "ssf": 58, "lshock": 59,
 }
 
 # every symbol include/astr_gpu.h declares (tests check the built library exports all)
@@ -58,7 +59,8 @@ class AstrCfg(ctypes.Structure):
         ("nbr", ctypes.c_int * 6), ("my_rank", ctypes.c_int),
         ("conschm", ctypes.c_int), ("difschm", ctypes.c_int), ("scheme_compact", ctypes.c_int),
         ("rkscheme", ctypes.c_int), ("lfilter", ctypes.c_int), ("diffterm", ctypes.c_int),
-        ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int), ("bctype", ctypes.c_int * 6),
+        ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int),
+        ("recon_schem", ctypes.c_int), ("lchardecomp", ctypes.c_int), ("bctype", ctypes.c_int * 6),
         ("alfa_filter", ctypes.c_double),
         ("reynolds", ctypes.c_double), ("mach", ctypes.c_double), ("prandtl", ctypes.c_double),
         ("gamma", ctypes.c_double), ("ref_tem", ctypes.c_double),
@@ -67,6 +69,7 @@ class AstrCfg(ctypes.Structure):
         ("const7", ctypes.c_double),
         ("tempconst", ctypes.c_double), ("tempconst1", ctypes.c_double),
         ("deltat", ctypes.c_double), ("twall", ctypes.c_double * 6),
+        ("bfacmpld", ctypes.c_double), ("shkcrt", ctypes.c_double),
     ]
 
 

@@ -44,7 +44,8 @@ class RhsEngine:
     def __init__(self, block: Block, global_dims: Sequence[int], homo: Sequence[bool], thermo: Dict[str, float],
                  deltat: float = 1e-3, alfa_filter: float = 0.49, lfilter: bool = True, diffterm: bool = True,
                  device: int = -1, flowtype: int = 0, bctype: Sequence[int] = (1,) * 6,
-                 twall: Sequence[float] = (0.0,) * 6, explicit: bool = False):
+                 twall: Sequence[float] = (0.0,) * 6, explicit: bool = False, conschm: Optional[int] = None,
+                 lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -66,6 +67,9 @@ class RhsEngine:
         c.my_rank = block.rank
         # conschm/difschm '643c' (compact_central) or '642e' (explicit_central), comsolver.F90:76-84
         c.conschm, c.difschm, c.scheme_compact, c.rkscheme = (642, 642, 0, 3) if explicit else (643, 643, 1, 3)
+        if conschm is not None:      # e.g. 543: upwind compact convection (convrsdcmp) over difschm
+            c.conschm = int(conschm)
+        c.recon_schem, c.lchardecomp, c.bfacmpld, c.shkcrt = int(recon_schem), int(lchardecomp), bfacmpld, shkcrt
         c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), 1, flowtype
         c.bctype[:] = [int(b) for b in bctype]
         c.twall[:] = [float(t) for t in twall]

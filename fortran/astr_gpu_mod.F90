@@ -29,6 +29,7 @@ module astr_gpu_mod
     integer(c_int) :: my_rank
     integer(c_int) :: conschm,difschm,scheme_compact,rkscheme
     integer(c_int) :: lfilter,diffterm,nondimen,flowtype
+    integer(c_int) :: recon_schem,lchardecomp
     integer(c_int) :: bctype(6)
     real(c_double) :: alfa_filter
     real(c_double) :: reynolds,mach,prandtl,gamma,ref_tem
@@ -36,6 +37,7 @@ module astr_gpu_mod
     real(c_double) :: tempconst,tempconst1
     real(c_double) :: deltat
     real(c_double) :: twall(6)
+    real(c_double) :: bfacmpld,shkcrt
   end type astr_cfg
   !
   interface
@@ -171,10 +173,14 @@ module astr_gpu_mod
                            lihomo,ljhomo,lkhomo,irk,jrk,krk,isize,jsize,ksize,     &
                            nbr,mpirank,lfilter,diffterm,alfa_filter,reynolds,mach, &
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
-                           device,flowtype,conschm,difschm,bctype,twall)
+                           device,flowtype,conschm,difschm,bctype,twall, &
+                           recon_schem,lchardecomp,bfacmpld,shkcrt)
     character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
     character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
     integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
+    integer, intent(in) :: recon_schem              ! commvar recon_schem
+    logical, intent(in) :: lchardecomp              ! commvar lchardecomp
+    real(8), intent(in) :: bfacmpld,shkcrt          ! commvar bfacmpld, shkcrt
     real(8), intent(in) :: twall(6)                 ! commvar twall(1:6)
     integer, intent(in) :: im,jm,km,ia,ja,ka,npdci,npdcj,npdck,is,ie,js,je,ks,ke
     logical, intent(in) :: lihomo,ljhomo,lkhomo,lfilter,diffterm
@@ -198,6 +204,8 @@ module astr_gpu_mod
     cfg%lfilter=merge(1,0,lfilter); cfg%diffterm=merge(1,0,diffterm)
     cfg%nondimen=1; cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall
+    cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
+    cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt
     cfg%alfa_filter=alfa_filter
     cfg%reynolds=reynolds; cfg%mach=mach; cfg%prandtl=prandtl; cfg%gamma=gamma; cfg%ref_tem=ref_tem
     cfg%const1=const(1); cfg%const2=const(2); cfg%const3=const(3); cfg%const4=const(4)

@@ -52,14 +52,17 @@ typedef struct astr_cfg {
   int size[3];                /* isize,jsize,ksize                                       */
   int nbr[6];                 /* neighbour ranks i-,i+,j-,j+,k-,k+ ; -1 = MPI_PROC_NULL  */
   int my_rank;                /* mpirank                                                 */
-  int conschm;                /* e.g. 643 (even first digit -> central convrsdcal6)      */
-  int difschm;                /* e.g. 643                                                */
-  int scheme_compact;         /* 1 = 'c' compact (only value implemented)                */
+  int conschm;                /* 643 / 642: central convrsdcal6 (src/solver.F90:2173);
+                                 543: upwind compact convrsdcmp (src/solver.F90:1271)   */
+  int difschm;                /* 643 (compact) or 642 (explicit)                         */
+  int scheme_compact;         /* difschm(4:4): 1 = 'c' compact_central, 0 = 'e' explicit */
   int rkscheme;               /* 3 = rk3 (TVD), src/mainloop.F90:350-362                 */
   int lfilter;                /* filterq enabled                                         */
   int diffterm;               /* viscous terms enabled                                   */
   int nondimen;               /* must be 1                                               */
   int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (src_chan)   */
+  int recon_schem;            /* input-file `recon_schem` (unused by conschm '543c')     */
+  int lchardecomp;            /* characteristic decomposition + Ducros sensor on/off     */
   int bctype[6];              /* bctype(1:6) of the input file: imin,imax,jmin,jmax,kmin,
                                  kmax; 1 periodic/none, 41 isothermal no-slip wall
                                  (src/bc.F90:327-407 boucon)                             */
@@ -69,18 +72,21 @@ typedef struct astr_cfg {
   double tempconst, tempconst1; /* Sutherland: 110.3/ref_tem (src/solver.F90:122)        */
   double deltat;
   double twall[6];            /* wall temperature of the bctype-41 faces (twall(1:6))    */
+  double bfacmpld;            /* blending factor of the compact upwind scheme (flux.F90) */
+  double shkcrt;              /* shock-sensor threshold of ducrossensor (commcal.F90)    */
 } astr_cfg;
 
 /* ---- field ids for astr_gpu_get_field / set_field / device_ptr ----------------------
  * Same numbering as the test oracle: 0-4 q | 5 rho | 6-8 vel | 9 prs | 10 tmp |
  * 11-15 qrhs | 16 jacob | 17-25 dxi(a,b) a-major (a = xi index, b = x index) |
  * 26-34 dvel(m,n) m-major | 35-37 dtmp | 38-43 sigma | 44-46 qflux | 47-49 x |
- * 50-54 qsave | 55-57 vor.  dvel/dtmp/vor are materialised on demand. */
+ * 50-54 qsave | 55-57 vor | 58 ssf | 59 lshock (0/1; both only with conschm 543 and
+ * lchardecomp).  dvel/dtmp/vor are materialised on demand. */
 enum {
   ASTR_F_Q = 0, ASTR_F_RHO = 5, ASTR_F_VEL = 6, ASTR_F_PRS = 9, ASTR_F_TMP = 10,
   ASTR_F_QRHS = 11, ASTR_F_JACOB = 16, ASTR_F_DXI = 17, ASTR_F_DVEL = 26,
   ASTR_F_DTMP = 35, ASTR_F_SIGMA = 38, ASTR_F_QFLUX = 44, ASTR_F_X = 47,
-  ASTR_F_QSAVE = 50, ASTR_F_VOR = 55, ASTR_F_COUNT = 58
+  ASTR_F_QSAVE = 50, ASTR_F_VOR = 55, ASTR_F_SSF = 58, ASTR_F_LSHOCK = 59, ASTR_F_COUNT = 60
 };
 
 /* replaces solvrinit: builds the line operators (fd_scheme_initiate

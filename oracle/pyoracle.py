@@ -30,6 +30,7 @@ FIELD_IDS = {
     **{f"x{n + 1}": 47 + n for n in range(3)},
     **{f"qsave{n + 1}": 50 + n for n in range(5)},
     **{f"vor{n + 1}": 55 + n for n in range(3)},
+    "ssf": 58, "lshock": 59,
 }
 
 
@@ -91,6 +92,16 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_bc.argtypes = [vp, vp, vp]
         L.oracle_case_set_flow.argtypes = [vp, ci, vp]
         L.oracle_case_set_scheme.argtypes = [vp, ci]
+        L.oracle_case_set_upwind.argtypes = [vp, ci, ci, cd, cd]
+        L.oracle_case_ducrossensor.argtypes = [vp]
+        L.oracle_case_convrsdcmp.argtypes = [vp]
+        L.oracle_case_convrsdcmp.restype = ci
+        L.oracle_flux_compact.argtypes = [ci, ci, ci, cd, vp, vp]
+        L.oracle_mp5.argtypes = [vp, cd, ci]
+        L.oracle_mp5.restype = cd
+        L.oracle_steger_warming.argtypes = [cd, cd, vp, vp, vp]
+        L.oracle_chardecomp.argtypes = [cd, vp, vp, vp, vp]
+        L.oracle_chardecomp.restype = ci
         L.oracle_case_boucon.argtypes = [vp]
         L.oracle_case_boucon.restype = ci
         L.oracle_case_run.argtypes = [vp, ci]
@@ -130,6 +141,36 @@ def compact_filter(f: np.ndarray, ntype: int, alfa: float = 0.49, beter_bound: f
     out = np.empty(dim + 1)
     lib().oracle_compact_filter(ntype, dim, alfa, beter_bound, f.ctypes.data, out.ctypes.data)
     return out
+
+
+def flux_compact(f: np.ndarray, ntype: int, plus: bool, bfacmpld: float = 0.3) -> np.ndarray:
+    """Compact 5th-order upwind interface flux of one pencil f(-hm:dim+hm) -> fh(-1:dim)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    dim = f.size - 1 - 2 * HM
+    out = np.empty(dim + 2)
+    lib().oracle_flux_compact(ntype, dim, int(plus), bfacmpld, f.ctypes.data, out.ctypes.data)
+    return out
+
+
+def mp5(u5, ul: float, discont: bool = True) -> float:
+    u = np.ascontiguousarray(u5, dtype=np.float64)
+    return lib().oracle_mp5(u.ctypes.data, float(ul), int(discont))
+
+
+def steger_warming(rho, vel, prs, tmp, q, dxi, jacob, gamma=1.4, mach=0.1):
+    a = np.ascontiguousarray([rho, *vel, prs, tmp, *q, *dxi, jacob], dtype=np.float64)
+    fp, fm = np.zeros(5), np.zeros(5)
+    lib().oracle_steger_warming(gamma, mach, a.ctypes.data, fp.ctypes.data, fm.ctypes.data)
+    return fp, fm
+
+
+def chardecomp(left, right, gamma=1.4):
+    """left/right = (ro, p, E, vel(3), ddi(3)) -> (REV, LEV) 5x5 (src/solver.F90:1958)."""
+    l = np.ascontiguousarray(left, dtype=np.float64); r = np.ascontiguousarray(right, dtype=np.float64)
+    rev, lev = np.zeros((5, 5)), np.zeros((5, 5))
+    if lib().oracle_chardecomp(gamma, l.ctypes.data, r.ctypes.data, rev.ctypes.data, lev.ctypes.data):
+        raise ValueError("chardecomp: degenerate metric normal")
+    return rev, lev
 
 
 def scheme_tables(is_filter: bool, ntype: int, dim: int, alfa: float = 0.49):
@@ -227,6 +268,16 @@ class Case:
         """flowtype 0 generic, 1 channel (src_chan with body force `force`)."""
         f = (ctypes.c_double * 3)(*[float(v) for v in force])
         lib().oracle_case_set_flow(self._h, int(flowtype), f)
+
+    def set_upwind(self, conschm: int = 543, lchardecomp: bool = True, bfacmpld: float = 0.3, shkcrt: float = 0.01):
+        """conschm='543c' (convrsdcmp) with the input file's `recon_schem, lchardecomp, bfacmpld, shkcrt`."""
+        lib().oracle_case_set_upwind(self._h, int(conschm), int(lchardecomp), float(bfacmpld), float(shkcrt))
+
+    def ducrossensor(self):
+        lib().oracle_case_ducrossensor(self._h)
+
+    def convrsdcmp(self) -> int:
+        return lib().oracle_case_convrsdcmp(self._h)
 
     def set_scheme(self, explicit: bool):
         lib().oracle_case_set_scheme(self._h, int(explicit))

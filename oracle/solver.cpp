@@ -28,6 +28,7 @@ struct Block {
   CompactScheme fds[3], fil[3];
   Field x[3], q[5], rho, vel[3], prs, tmp, jacob, dxi[3][3];
   Field qrhs[5], qsave[5], dvel[3][3], dtmp[3], sigma[6], qflux[3], vor[3];
+  Field ssf, lshock;   // ducrossensor (allocated on first use, commcal.F90:218-219); lshock as 0/1
   int dim(int d) const { return d == 0 ? im : (d == 1 ? jm : km); }
 };
 
@@ -44,6 +45,11 @@ struct Case {
   double force[3] = {0, 0, 0};
   int flowtype = 0;          // 0 tgv / generic (no source term), 1 channel (src_chan)
   char scheme_kind = 'c';    // difschm(4:4): 'c' compact, 'e' explicit (comsolver.F90:76-84)
+  // conschm: 643 central (convrsdcal6) or 543 upwind compact (convrsdcmp); input-file line
+  // `recon_schem, lchardecomp, bfacmpld, shkcrt` (src/readwrite.F90)
+  int conschm = 643;
+  bool lchardecomp = false;
+  double bfacmpld = 0.3, shkcrt = 0.01;
   int bctype[6] = {1, 1, 1, 1, 1, 1};      // src/readwrite.F90 bctype(1:6): imin,imax,jmin,jmax,kmin,kmax
   double twall[6] = {0, 0, 0, 0, 0, 0};
   std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
@@ -629,6 +635,8 @@ static void diffrsdcal6(Case& c) {
   }
 }
 
+#include "upwind.hpp"
+
 // src/solver.F90:295-353 src_chan (ndims==3): bulk velocities by trapezoidal integration in y over
 // nodes 1..im,1..jm,1..km of every rank (psum = sum over blocks), then the body force
 static void src_chan(Case& c) {
@@ -663,7 +671,11 @@ static void src_chan(Case& c) {
 
 // src/solver.F90:185-282 rhscal (conschm even -> central; flowtype channel adds src_chan :262)
 static void rhscal(Case& c) {
-  convrsdcal6(c);
+  if ((c.conschm / 100) % 2 == 0) convrsdcal6(c);      // :216-218
+  else {                                               // conschm(4:4)=='c', :224-226
+    if (c.lchardecomp) ducrossensor(c);
+    convrsdcmp(c);
+  }
   for (Block& b : c.blk)
     for (auto& f : b.qrhs)
       for (double& v : f.v) v = -v;  // :242
@@ -906,6 +918,8 @@ static Field* field_by_id(Block& b, int id) {
   if (id < 50) return &b.x[id - 47];
   if (id < 55) return &b.qsave[id - 50];
   if (id < 58) return &b.vor[id - 55];
+  if (id == 58) return &b.ssf;
+  if (id == 59) return &b.lshock;
   return nullptr;
 }
 // Copy a field (always in the halo'd shape (im+11)(jm+11)(km+11)) out of / into a block.
@@ -939,6 +953,31 @@ void oracle_case_set_flow(void* h, int flowtype, const double* force) {
   Case* c = static_cast<Case*>(h);
   c->flowtype = flowtype;
   for (int n = 0; n < 3; ++n) c->force[n] = force[n];
+}
+// conschm digits (643 / 543) and the upwind parameters lchardecomp, bfacmpld, shkcrt
+void oracle_case_set_upwind(void* h, int conschm, int lchardecomp, double bfacmpld, double shkcrt) {
+  Case* c = static_cast<Case*>(h);
+  c->conschm = conschm; c->lchardecomp = lchardecomp != 0; c->bfacmpld = bfacmpld; c->shkcrt = shkcrt;
+}
+void oracle_case_ducrossensor(void* h) { ducrossensor(*static_cast<Case*>(h)); }
+int oracle_case_convrsdcmp(void* h) { return convrsdcmp(*static_cast<Case*>(h)); }
+// single-pencil entry points of the upwind building blocks (tests)
+void oracle_flux_compact(int ntype, int dim, int plus, double bfacmpld, const double* f /*-hm..dim+hm*/, double* fh /*-1..dim*/) {
+  CompactScheme s;
+  compact_flux_initiate(s, 543, ntype, dim, plus ? '+' : '-', bfacmpld);
+  std::vector<double> work(2 * s.size());
+  flux_compact(s, plus ? '+' : '-', bfacmpld, f + hm, fh + 1, work.data());
+}
+double oracle_mp5(const double* u5, double ul, int discont) { return mp5(u5, ul, discont != 0); }
+void oracle_steger_warming(double gamma, double mach, const double* in /*rho,vel3,prs,tmp,q5,dxi3,jacob*/, double* fp, double* fm) {
+  Thermo th; th.gamma = gamma; th.mach = mach;
+  steger_warming_node(th, in[0], in + 1, in[4], in[5], in + 6, in + 11, in[14], fp, fm);
+}
+int oracle_chardecomp(double gamma, const double* l /*ro,p,E,vel3,ddi3*/, const double* r, double* rev25, double* lev25) {
+  double REV[5][5], LEV[5][5];
+  const bool ok = chardecomp(gamma, l[0], l[1], l[2], l + 3, l + 6, r[0], r[1], r[2], r + 3, r + 6, REV, LEV);
+  std::memcpy(rev25, REV, sizeof REV); std::memcpy(lev25, LEV, sizeof LEV);
+  return ok ? 0 : 1;
 }
 void oracle_case_set_scheme(void* h, int explicit_scheme) {
   static_cast<Case*>(h)->scheme_kind = explicit_scheme ? 'e' : 'c';

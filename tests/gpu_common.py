@@ -64,7 +64,7 @@ def channel_state(c, th, amp=0.05, ib=0):
 
 
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
-              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False):
+              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
@@ -93,9 +93,25 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
             a *= 1.0 + perturb * rng.standard_normal(a.shape)
             c.set(name, a)
         c.updatefvar()
+    up_kw = {}
+    if upwind is not None:
+        # conschm='543c' (convrsdcmp).  shkcrt='auto': put the Ducros threshold in the middle of the widest
+        # gap of the oracle's sensor values around the requested quantile, so that no lshock flag sits
+        # within rounding distance of the threshold
+        up_kw = dict(conschm=543, lchardecomp=upwind.get("lchardecomp", True), bfacmpld=upwind.get("bfacmpld", 0.3),
+                     shkcrt=upwind.get("shkcrt", 0.01))
+        if up_kw["shkcrt"] == "auto":
+            c.set_upwind(543, True, up_kw["bfacmpld"], 1.0)
+            c.qswap(); c.gradcal(); c.ducrossensor()
+            v = np.sort(core(c.get("ssf")).ravel())
+            k0 = int(upwind.get("quantile", 0.7) * v.size)
+            win = v[k0 - 200:k0 + 200]
+            g = int(np.argmax(np.diff(win)))
+            up_kw["shkcrt"] = 0.5 * (win[g] + win[g + 1])
+        c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
     block = decompose(n, (1, 1, 1), homo)[0]
     eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0,
-                    flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit)
+                    flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw)
     eng.set_force(force)
     x = eng.empty(3)
     for d in range(3):

@@ -30,6 +30,15 @@ CASES = {
     "explicit_periodic": dict(n=(32, 36, 40), homo=(True, True, True), stretch=True, explicit=True),
     "explicit_walls": dict(n=(36, 32, 32), homo=(False, False, True), stretch=True, explicit=True),
     "explicit_channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0, explicit=True),
+    # conschm='543c': Steger-Warming + compact upwind flux + characteristic MP5 (convrsdcmp), Ducros sensor
+    "upwind_periodic": dict(n=(32, 36, 40), homo=(True, True, True), stretch=True, perturb=1e-2,
+                            upwind=dict(lchardecomp=True, shkcrt="auto")),
+    "upwind_walls": dict(n=(36, 32, 40), homo=(False, False, True), stretch=True, perturb=1e-2,
+                         upwind=dict(lchardecomp=True, shkcrt="auto")),
+    "upwind_nochar": dict(n=(32, 32, 32), homo=(True, False, True), stretch=True, perturb=1e-2,
+                          upwind=dict(lchardecomp=False)),
+    "upwind_explicit": dict(n=(32, 32, 32), homo=(True, True, False), stretch=True, perturb=1e-2, explicit=True,
+                            upwind=dict(lchardecomp=True, shkcrt="auto")),
     "channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0),
 }
 
@@ -91,6 +100,27 @@ def test_rhscal(pair):
     assert_fields_close(c, eng, QRHS, 5e-13, what="rhscal")
     assert_fields_close(c, eng, [f"sigma{n + 1}" for n in range(6)] + [f"qflux{n + 1}" for n in range(3)], OP_TOL,
                         what="sigma/qflux")
+
+
+def test_ducrossensor(pair):
+    c, eng = pair
+    if not eng.cfg.lchardecomp:
+        pytest.skip("Ducros sensor runs only with conschm 543 and lchardecomp")
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    ref = core(c.get("ssf"))
+    assert np.abs(core(eng.get("ssf")) - ref).max() <= 1e-12 * ref.max()
+    flags = core(c.get("lshock"))
+    assert 0.02 < flags.mean() < 0.98, "test field does not exercise both limiter branches"
+    np.testing.assert_array_equal(core(eng.get("lshock")), flags)
+
+
+def test_rhscal_upwind_inviscid(oracle):
+    c, eng = make_pair(oracle, n=(32, 32, 32), diffterm=False, perturb=1e-2, upwind=dict(lchardecomp=True, shkcrt="auto"))
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    assert_fields_close(c, eng, QRHS, 5e-13, what="convrsdcmp")
+    eng.close(); c.close()
 
 
 def test_rhscal_inviscid(oracle):
