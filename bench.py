@@ -33,6 +33,19 @@ STAGES = 3
 BYTES_STORE, BYTES_ADD = 16.0, 24.0
 
 
+def ncu_traffic(kernel: str, n: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json),
+    or None when that kernel / block size has not been captured."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if int(d.get("n", 0)) == n:
+            v = d["bytes_per_launch"].get(kernel)
+            return float(v) if v is not None else None
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,7 +240,8 @@ def run_gpu(args):
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": f"sweep_kernel<{dom}>", "achieved": kern[dom]["GBps"], "peak": peak,
-                    "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom, n),
+                    "algorithmic_bytes": alg[dom] * pts, "peak_source": peak_src,
                     "all_sweeps": {"achieved": tot_b / (tot_ms * 1e-3) / 1e9, "frac": tot_b / (tot_ms * 1e-3) / 1e9 / peak,
                                    "share_of_step": tot_ms / (ms * 1.0)},
                     "per_kernel": kern, "other_ms_per_launch": other}

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 OP_TOL = 2e-13
 STEP_TOL = 1e-12
+UPWIND_TOL = 2e-11
 
 DVEL = [f"dvel{m + 1}{n + 1}" for m in range(3) for n in range(3)]
 DTMP = [f"dtmp{n + 1}" for n in range(3)]
@@ -97,8 +98,13 @@ def test_rhscal(pair):
     c.qswap(); eng.qswap()
     c.gradcal(); eng.gradcal()
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
-    assert_fields_close(c, eng, QRHS, 5e-13, what="rhscal")
-    assert_fields_close(c, eng, [f"sigma{n + 1}" for n in range(6)] + [f"qflux{n + 1}" for n in range(3)], OP_TOL,
+    # upwind: the characteristic projection divides by the smallest admissible component of the metric
+    # normal (rgp = 1/gpd, src/solver.F90:2052) and the split fluxes are O(c/dx) with O(1) differences:
+    # rounding is amplified by ~1e2 on these grids
+    tol = UPWIND_TOL if "upwind" in c.case_name else 5e-13
+    assert_fields_close(c, eng, QRHS, tol, what="rhscal")
+    tol = 1e-12 if "channel" in c.case_name else OP_TOL      # qflux carries dT/dy: see test_gradcal
+    assert_fields_close(c, eng, [f"sigma{n + 1}" for n in range(6)] + [f"qflux{n + 1}" for n in range(3)], tol,
                         what="sigma/qflux")
 
 
@@ -119,7 +125,7 @@ def test_rhscal_upwind_inviscid(oracle):
     c, eng = make_pair(oracle, n=(32, 32, 32), diffterm=False, perturb=1e-2, upwind=dict(lchardecomp=True, shkcrt="auto"))
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
-    assert_fields_close(c, eng, QRHS, 5e-13, what="convrsdcmp")
+    assert_fields_close(c, eng, QRHS, UPWIND_TOL, what="convrsdcmp")
     eng.close(); c.close()
 
 
@@ -151,6 +157,8 @@ def test_rk_stage(pair):
     for rk in (1, 2, 3):
         c.rk_stage(rk); eng.rk_stage(rk)
     assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="3 rk stages")
+    if eng.cfg.lchardecomp:      # the shock flags must not have drifted apart over the stages
+        np.testing.assert_array_equal(core(eng.get("lshock")), core(c.get("lshock")))
 
 
 def test_five_steps_and_history(oracle):
