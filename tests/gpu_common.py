@@ -31,6 +31,20 @@ def stretched_x(n, homo):
     return np.asfortranarray(x)
 
 
+def skewed_x(n, homo):
+    """Sheared lattice with smooth 1-D stretching: y += 0.3 x, z += -0.2 x + 0.15 y.  Every metric
+    component is either exactly zero or O(1) everywhere, which keeps chardecomp's pivot division
+    (rgp = 1/gpd, src/solver.F90:2052) well conditioned; a periodic direction stays periodic up to
+    a constant coordinate jump, which gridsendrecv carries as relative offsets."""
+    L = 2 * np.pi
+    s = [np.arange(m + 1) / m for m in n]
+    S = np.meshgrid(*s, indexing="ij")
+    X = [L * (S[d] + 0.04 * np.sin(2 * np.pi * S[d])) if homo[d]
+         else L * 0.5 * (1.0 + np.tanh(1.07 * (2 * S[d] - 1)) / np.tanh(1.07)) for d in range(3)]
+    x = np.stack([X[0], X[1] + 0.3 * X[0], X[2] - 0.2 * X[0] + 0.15 * X[1]], axis=-1)
+    return np.asfortranarray(x)
+
+
 def channel_x(n, lengths):
     """grichan (src/gridgeneration.F90:272-303): uniform x,z, tanh-stretched y, varc=1.07."""
     lx, ly, lz = lengths
@@ -79,6 +93,8 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         c.set_bc(bctype, twall)
         c.set_flow(1, force)
         c.set_x(channel_x(n, lengths))
+    elif stretch == "skew":
+        c.set_x(skewed_x(n, homo))
     elif stretch:
         c.set_x(stretched_x(n, homo))
     c.gridgeom()

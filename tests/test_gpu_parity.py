@@ -32,7 +32,7 @@ CASES = {
     "explicit_walls": dict(n=(36, 32, 32), homo=(False, False, True), stretch=True, explicit=True),
     "explicit_channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0, explicit=True),
     # conschm='543c': Steger-Warming + compact upwind flux + characteristic MP5 (convrsdcmp), Ducros sensor
-    "upwind_periodic": dict(n=(32, 36, 40), homo=(True, True, True), stretch=True, perturb=1e-2,
+    "upwind_periodic": dict(n=(32, 36, 40), homo=(True, True, True), stretch="skew", perturb=1e-2,
                             upwind=dict(lchardecomp=True, shkcrt="auto")),
     "upwind_walls": dict(n=(36, 32, 40), homo=(False, False, True), stretch=True, perturb=1e-2,
                          upwind=dict(lchardecomp=True, shkcrt="auto")),
