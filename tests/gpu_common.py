@@ -77,6 +77,32 @@ def channel_state(c, th, amp=0.05, ib=0):
         c.set(name, full, ib)
 
 
+def clean_metrics(c):
+    """chardecomp picks its pivot with `abs(var1)>1.d-12` on the raw metric (src/solver.F90:2051) and then
+    divides by it: metric components that are analytically zero but come out of gridgeom as 1e-12-ish
+    rounding residue make the reference itself amplify rounding by 1e12 (both sides then compute noise).
+    The upwind parity grids therefore carry exact zeros where the metric vanishes."""
+    names = [f"dxi{a + 1}{b + 1}" for a in range(3) for b in range(3)]
+    big = max(np.abs(c.get(nm, ib)).max() for nm in names for ib in range(c.nblocks))
+    for ib in range(c.nblocks):
+        for nm in names:
+            v = c.get(nm, ib)
+            v[np.abs(v) < 1e-8 * big] = 0.0
+            c.set(nm, v, ib)
+
+
+def auto_shkcrt(c, bfacmpld=0.3, quantile=0.7):
+    """Ducros threshold in the middle of the widest gap of the oracle's sensor values around the requested
+    quantile, so that no lshock flag sits within rounding distance of the threshold."""
+    c.set_upwind(543, True, bfacmpld, 1.0)
+    c.qswap(); c.gradcal(); c.ducrossensor()
+    v = np.sort(np.concatenate([core(c.get("ssf", ib)).ravel() for ib in range(c.nblocks)]))
+    k0 = int(quantile * v.size)
+    win = v[k0 - 200:k0 + 200]
+    g = int(np.argmax(np.diff(win)))
+    return 0.5 * (win[g] + win[g + 1])
+
+
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
               lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
@@ -99,16 +125,7 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         c.set_x(stretched_x(n, homo))
     c.gridgeom()
     if upwind is not None:
-        # chardecomp picks its pivot with `abs(var1)>1.d-12` on the raw metric (src/solver.F90:2051) and then
-        # divides by it: metric components that are analytically zero but come out of gridgeom as 1e-12-ish
-        # rounding residue make the reference itself amplify rounding by 1e12 (both sides then compute noise).
-        # The parity grids therefore carry exact zeros where the metric vanishes.
-        big = max(np.abs(c.get(f"dxi{a + 1}{b + 1}")).max() for a in range(3) for b in range(3))
-        for a in range(3):
-            for b in range(3):
-                v = c.get(f"dxi{a + 1}{b + 1}")
-                v[np.abs(v) < 1e-8 * big] = 0.0
-                c.set(f"dxi{a + 1}{b + 1}", v)
+        clean_metrics(c)
     if channel:
         channel_state(c, th)
     else:
@@ -122,19 +139,11 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         c.updatefvar()
     up_kw = {}
     if upwind is not None:
-        # conschm='543c' (convrsdcmp).  shkcrt='auto': put the Ducros threshold in the middle of the widest
-        # gap of the oracle's sensor values around the requested quantile, so that no lshock flag sits
-        # within rounding distance of the threshold
+        # conschm='543c' (convrsdcmp); shkcrt='auto': see auto_shkcrt
         up_kw = dict(conschm=543, lchardecomp=upwind.get("lchardecomp", True), bfacmpld=upwind.get("bfacmpld", 0.3),
                      shkcrt=upwind.get("shkcrt", 0.01))
         if up_kw["shkcrt"] == "auto":
-            c.set_upwind(543, True, up_kw["bfacmpld"], 1.0)
-            c.qswap(); c.gradcal(); c.ducrossensor()
-            v = np.sort(core(c.get("ssf")).ravel())
-            k0 = int(upwind.get("quantile", 0.7) * v.size)
-            win = v[k0 - 200:k0 + 200]
-            g = int(np.argmax(np.diff(win)))
-            up_kw["shkcrt"] = 0.5 * (win[g] + win[g + 1])
+            up_kw["shkcrt"] = auto_shkcrt(c, up_kw["bfacmpld"], upwind.get("quantile", 0.7))
         c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
     block = decompose(n, (1, 1, 1), homo)[0]
     eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0,

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pyoracle  # noqa: E402
 from astr_b200 import RhsEngine, decompose, refcal  # noqa: E402
-from gpu_common import PRIMS, QS, GROUPS, stretched_x  # noqa: E402
+from gpu_common import PRIMS, QS, GROUPS, auto_shkcrt, channel_state, channel_x, clean_metrics  # noqa: E402
 
 HM = 5
 
@@ -27,22 +27,47 @@ def main():
     homo = tuple(bool(int(v)) for v in sys.argv[2].split(","))
     n = tuple(int(v) for v in sys.argv[3].split(","))
     nsteps = int(sys.argv[4])
-    device_metrics = len(sys.argv) > 5 and sys.argv[5] == "devgeom"
+    modes = set(sys.argv[5:])
+    device_metrics = "devgeom" in modes
+    channel, upwind = "channel" in modes, "upwind" in modes
     blocks = decompose(n, layout, homo)
     blk = blocks[rank]
-    c = pyoracle.Case(*n, blocks=layout, homo=homo)
-    if not all(homo):
-        pass
-    c.gridgeom(); c.tgvini()
+    reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)
+    th = refcal(reynolds, mach)
+    lengths = (2 * np.pi, 2.0, np.pi) if channel else None
+    c = pyoracle.Case(*n, blocks=layout, homo=homo, reynolds=reynolds, mach=mach, lengths=lengths)
+    kw = {}
+    if channel:      # examples/Channel/datin/input.chl at reduced size, split over the ranks
+        kw = dict(flowtype=1, bctype=(1, 1, 41, 41, 1, 1), twall=(0, 0, 1.0, 1.0, 0, 0))
+        force = (2.5e-3, 0.0, 1e-4)
+        c.set_bc(kw["bctype"], kw["twall"]); c.set_flow(1, force)
+        xg = channel_x(n, lengths)
+        for ib in range(world):
+            b = c.block_info(ib)
+            g0, dims = b["g0"], (b["im"], b["jm"], b["km"])
+            c.set_x(xg[tuple(slice(g0[d], g0[d] + dims[d] + 1) for d in range(3))], ib)
+    c.gridgeom()
+    if channel:
+        for ib in range(world):
+            channel_state(c, th, ib=ib)
+    else:
+        c.tgvini()
     rng = np.random.default_rng(99)
     for ib in range(world):
         for name in QS:
             a = c.get(name, ib)
-            a *= 1.0 + 1e-3 * rng.standard_normal(a.shape)
+            a *= 1.0 + (1e-2 if upwind else 1e-3) * rng.standard_normal(a.shape)
             c.set(name, a, ib)
     # shared interface nodes must hold one value: let the oracle's qswap average them first
     c.qswap(); c.updatefvar()
-    eng = RhsEngine(blk, n, homo, refcal(1600.0, 0.1), deltat=1e-3, device=local)
+    if upwind:       # conschm 543c with characteristic decomposition and the Ducros sensor
+        clean_metrics(c)
+        shk = auto_shkcrt(c)
+        c.set_upwind(543, True, 0.3, shk)
+        kw.update(conschm=543, lchardecomp=True, bfacmpld=0.3, shkcrt=shk)
+    eng = RhsEngine(blk, n, homo, th, deltat=1e-3, device=local, **kw)
+    if channel:
+        eng.set_force(force)
 
     def bcast(b):
         obj = [b]
@@ -60,13 +85,18 @@ def main():
             for b in range(3):
                 dxi[..., a, b] = c.get(f"dxi{a + 1}{b + 1}", rank)
         eng.set_metrics(dxi, c.get("jacob", rank))
+        if channel:
+            x = eng.empty(3)
+            for d in range(3):
+                x[..., d] = c.get(f"x{d + 1}", rank)
+            eng.set_grid(x)
     for name in QS + PRIMS:
         eng.set(name, c.get(name, rank))
     hist = []
     for step in range(nsteps):
         for rk in (1, 2, 3):
             if rk == 1:
-                eng.filterq(); eng.qswap(); eng.gradcal()
+                eng.filterq(); eng.boucon(); eng.qswap(); eng.gradcal()
                 ke, en = eng.reduce_tgv()
                 t = torch.tensor([ke, en], dtype=torch.float64)
                 dist.all_reduce(t)                       # psum

@@ -44,3 +44,21 @@ def test_four_blocks(oracle):
 
 def test_eight_blocks_as_the_reference_decomposes(oracle):
     _run(8, "2,2,2", "1,1,1", "48,48,48", 2, 29715)
+
+
+def test_channel_split_in_y_and_x(oracle):
+    # walls owned by different ranks, src_chan bulk integrals summed over ranks (psum -> ncclAllReduce)
+    _run(4, "2,2,1", "1,0,1", "48,48,24", 2, 29716, extra=("channel",))
+
+
+def test_channel_two_blocks(oracle):
+    _run(2, "1,2,1", "1,0,1", "32,48,24", 2, 29717, extra=("channel",))
+
+
+def test_upwind_two_blocks(oracle):
+    # conschm 543c across an interface: ssf halo exchange, interface closures of the compact flux
+    _run(2, "2,1,1", "1,1,1", "48,32,32", 2, 29718, extra=("upwind",))
+
+
+def test_upwind_eight_blocks_with_walls(oracle):
+    _run(8, "2,2,2", "0,1,0", "48,48,48", 1, 29719, extra=("upwind",))
