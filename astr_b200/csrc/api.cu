@@ -159,7 +159,7 @@ static void build_flux(HostOp& h, int optype, int ntype, int n, double bfacmpld)
 // context
 // -------------------------------------------------------------------------------------
 enum ProfCat { PC_FILTER_I, PC_FILTER_J, PC_FILTER_K, PC_HALO, PC_GRAD_I, PC_GRAD_J, PC_GRAD_K, PC_VISC,
-               PC_FLUX, PC_DIV_I, PC_DIV_J, PC_DIV_K, PC_RK, PC_FVAR, PC_COUNT };
+               PC_FLUX, PC_DIV_I, PC_DIV_J, PC_DIV_K, PC_RK, PC_FVAR, PC_XPACK, PC_XNCCL, PC_XUNPACK, PC_COUNT };
 
 struct ProfSpan { int cat; cudaEvent_t a, b; };
 
@@ -254,9 +254,9 @@ static FieldList fields(int s0, int n) {
 // -------------------------------------------------------------------------------------
 static int exchange_dir(const FieldList& fl, int d, int mode) {
   const astr_cfg& c = g->cfg;
-  ProfScope ps(PC_HALO);
   if (c.size[d] == 1) {
     if (!c.lhomo[d]) return 0;
+    ProfScope ps(PC_HALO);
     return pw_halo_wrap(g->L, fl, d, mode, g->st);
   }
   if (!g->comm) return astr_fail_msg("multi-block exchange needs astr_gpu_comm_init");
@@ -271,8 +271,12 @@ static int exchange_dir(const FieldList& fl, int d, int mode) {
     g->xbuf_doubles = want;
   }
   const int lo = c.nbr[2 * d], hi = c.nbr[2 * d + 1];
-  if (lo >= 0) TRY(pw_pack(L, fl, d, 0, l0, l1, g->xbuf[0], g->st));
-  if (hi >= 0) TRY(pw_pack(L, fl, d, 1, l0, l1, g->xbuf[1], g->st));
+  {
+    ProfScope ps(PC_XPACK);
+    if (lo >= 0) TRY(pw_pack(L, fl, d, 0, l0, l1, g->xbuf[0], g->st));
+    if (hi >= 0) TRY(pw_pack(L, fl, d, 1, l0, l1, g->xbuf[1], g->st));
+  }
+  ProfScope* pn = new ProfScope(PC_XNCCL);
   NCCL_OK(g_nccl.GroupStart());
   if (lo >= 0) NCCL_OK(g_nccl.Send(g->xbuf[0], cnt, ncclDouble, lo, g->comm, g->st));
   if (hi >= 0) NCCL_OK(g_nccl.Send(g->xbuf[1], cnt, ncclDouble, hi, g->comm, g->st));
@@ -281,6 +285,8 @@ static int exchange_dir(const FieldList& fl, int d, int mode) {
   if (hi >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[3], cnt, ncclDouble, hi, g->comm, g->st));
   if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->st));
   NCCL_OK(g_nccl.GroupEnd());
+  delete pn;
+  ProfScope pu(PC_XUNPACK);
   if (hi >= 0) TRY(pw_unpack(L, fl, d, 1, l0, l1, g->xbuf[3], g->st));
   if (lo >= 0) TRY(pw_unpack(L, fl, d, 0, l0, l1, g->xbuf[2], g->st));
   return 0;

@@ -38,7 +38,7 @@ SYMBOLS = [
 ]
 
 PROFILE_CATEGORIES = ["filter_i", "filter_j", "filter_k", "halo", "grad_i", "grad_j", "grad_k", "visc", "flux",
-                      "div_i", "div_j", "div_k", "rk", "fvar"]
+                      "div_i", "div_j", "div_k", "rk", "fvar", "xpack", "xnccl", "xunpack"]
 
 
 class AstrGpuError(RuntimeError):

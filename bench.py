@@ -150,9 +150,8 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL prints its version banner on stdout at NCCL_DEBUG>=VERSION: keep stdout to ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL writes its version banner / debug log to stdout: keep stdout to ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -162,7 +161,8 @@ def run_gpu(args):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.n
-    size = mpisizedis(world, (n, n, n))
+    size = tuple(int(v) for v in args.layout.split(",")) if args.layout else mpisizedis(world, (n, n, n))
+    assert size[0] * size[1] * size[2] == world, "--layout must multiply to the number of ranks"
     gdims = tuple(n * s for s in size)                      # weak scaling: n^3 per GPU
     homo = (True, True, True)
     block = decompose(gdims, size, homo)[rank]
@@ -248,7 +248,7 @@ def run_gpu(args):
 
     # ---- end-to-end through the C ABI with HOST buffers --------------------------------------
     # one step = upload q from pinned host memory, rebuild primitives, 3 RK stages, download q.
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, args.e2e_steps))
     h2d = d2h = 5 * int(np.prod(shp)) * 8
     barrier()
     t0 = time.perf_counter()
@@ -263,7 +263,7 @@ def run_gpu(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = pts * world * STAGES * e2e_steps / e2e_s / 1e6
+    e2e_value = pts * world * STAGES * e2e_steps / e2e_s / 1e6 if e2e_steps else None
     ke = eng_stats = None
     try:
         eng.filterq(); eng.qswap(); eng.gradcal()
@@ -297,7 +297,7 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "steps": e2e_steps, "ms_per_step": e2e_s / max(e2e_steps, 1) * 1e3,
                 "what": "astr_gpu_upload_state(q) from pinned host + updatefvar + 3 x astr_gpu_rk_stage + "
                         "astr_gpu_download_state(q)"},
         "gpu_launches": launches,
@@ -317,6 +317,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layout", default="", help="block grid isize,jsize,ksize (default: mpisizedis)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

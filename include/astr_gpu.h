@@ -157,7 +157,8 @@ int astr_gpu_reduce_tgv(double out[3]);
 /* introspection for bench / tests */
 int astr_gpu_kernel_launches(long long* count);       /* launches since init            */
 /* CUDA-event profile of the stage, per category (filter i/j/k, halo, grad i/j/k, visc,
- * flux, div i/j/k, rk, fvar): accumulated ms and span counts since set_profile(1). */
+ * flux, div i/j/k, rk, fvar, exchange pack / NCCL / unpack): accumulated ms and span counts
+ * since set_profile(1). */
 int astr_gpu_set_profile(int on);
 int astr_gpu_get_profile(double* ms, long long* n, int cap);
 int astr_gpu_bench_sweep(int op /*0 deriv,1 filter*/, int dir /*0,1,2*/, int nfields,
