@@ -51,6 +51,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (h) return true;
@@ -69,6 +70,7 @@ struct NcclApi {
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return true;
@@ -191,6 +193,13 @@ struct Ctx {
   int nranks = 1, rank = 0;
   double* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send lo, send hi, recv lo, recv hi
   size_t xbuf_doubles = 0;
+  // peer-to-peer exchange (fused pack + NVLink stores): one IPC-exported arena per rank
+  bool p2p = false;
+  char* xarena = nullptr;                 // XHeader + receive windows [direction][side]
+  char* peer_arena[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per neighbour slot (nbr[])
+  int peer_dims[6][3];
+  std::vector<void*> ipc_opened;
+  unsigned long long xseq[3] = {0, 0, 0};
   // profiling
   bool profile = false;
   std::vector<ProfSpan> spans;
@@ -252,6 +261,9 @@ static FieldList fields(int s0, int n) {
 // -------------------------------------------------------------------------------------
 // halo exchange of one direction (dataswap / qswap / datasync, src/parallel.F90)
 // -------------------------------------------------------------------------------------
+constexpr int XMAX_PLANES = 45;            // 9 fields x 5 planes (sigma+qflux) >= 5 fields x 6 planes (qswap)
+static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1);
+
 static int exchange_dir(const FieldList& fl, int d, int mode) {
   const astr_cfg& c = g->cfg;
   if (c.size[d] == 1) {
@@ -262,6 +274,7 @@ static int exchange_dir(const FieldList& fl, int d, int mode) {
   if (!g->comm) return astr_fail_msg("multi-block exchange needs astr_gpu_comm_init");
   const Layout& L = g->L;
   const int l0 = (mode == XMODE_SWAP) ? 1 : 0, l1 = (mode == XMODE_SYNC) ? 0 : ASTR_HM;
+  if (g->p2p && fl.nf * (l1 - l0 + 1) <= XMAX_PLANES) return exchange_dir_p2p(fl, d, l0, l1);
   const int n1 = (d == 0) ? L.jm + 1 : L.im + 1, n2 = (d == 2) ? L.jm + 1 : L.km + 1;
   const size_t cnt = (size_t)(l1 - l0 + 1) * n1 * n2 * fl.nf;
   if (cnt > g->xbuf_doubles) {
@@ -323,6 +336,129 @@ int astr_xhalo_exchange(int d) {
   if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->st));
   NCCL_OK(g_nccl.GroupEnd());
   return geom_xhalo_unpack(L, x3, d, lo >= 0 ? g->xbuf[2] : nullptr, hi >= 0 ? g->xbuf[3] : nullptr, g->st);
+}
+
+// ---- peer-to-peer exchange: arena layout, IPC set-up ---------------------------------------
+constexpr size_t XHEADER_BYTES = 1024;
+struct XHeader {
+  unsigned long long ready[6];             // [direction*2 + side] written by the neighbour on that side
+  unsigned long long ack[6];               // [direction*2 + side] written by the neighbour on that side
+  unsigned int csend[6], crecv[6];         // CTA completion counters (local)
+  unsigned int err;
+};
+static size_t xwin_doubles(const int dims[3], int d) {
+  const size_t n1 = (d == 0) ? dims[1] + 1 : dims[0] + 1, n2 = (d == 2) ? dims[1] + 1 : dims[2] + 1;
+  return (size_t)XMAX_PLANES * n1 * n2;
+}
+static size_t xwin_offset(const int dims[3], int d, int side) {   // bytes from the arena start
+  size_t off = XHEADER_BYTES;
+  for (int dd = 0; dd < d; ++dd) off += 2 * xwin_doubles(dims, dd) * sizeof(double);
+  return off + (size_t)side * xwin_doubles(dims, d) * sizeof(double);
+}
+static size_t xarena_bytes(const int dims[3]) { return xwin_offset(dims, 3, 0); }
+
+// Every rank exports one arena; neighbours map it with CUDA IPC.  The decision to use the
+// peer-to-peer path is collective (all ranks or none): anything that fails falls back to NCCL.
+static int p2p_setup() {
+  const astr_cfg& c = g->cfg;
+  const char* env = getenv("ASTR_XCHG");
+  int ok = !(env && strcmp(env, "nccl") == 0);
+  const int dims[3] = {c.im, c.jm, c.km};
+  struct Rec { cudaIpcMemHandle_t h; int dims[3]; int ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 16]; };
+  static_assert(sizeof(Rec) == 128, "Rec size");
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    const size_t bytes = xarena_bytes(dims);
+    if (cudaMalloc(&g->xarena, bytes) != cudaSuccess) { g->xarena = nullptr; ok = 0; cudaGetLastError(); }
+    else {
+      CUDA_OK(cudaMemsetAsync(g->xarena, 0, XHEADER_BYTES, g->st));
+      if (cudaIpcGetMemHandle(&mine.h, g->xarena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+  }
+  for (int k = 0; k < 3; ++k) mine.dims[k] = dims[k];
+  mine.ok = ok;
+  std::vector<Rec> all(g->nranks);
+  char* dbuf = nullptr;
+  CUDA_OK(cudaMalloc(&dbuf, sizeof(Rec) * g->nranks));
+  CUDA_OK(cudaMemcpyAsync(dbuf + sizeof(Rec) * g->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, g->st));
+  NCCL_OK(g_nccl.AllGather(dbuf + sizeof(Rec) * g->rank, dbuf, sizeof(Rec), ncclChar, g->comm, g->st));
+  CUDA_OK(cudaMemcpyAsync(all.data(), dbuf, sizeof(Rec) * g->nranks, cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  for (const Rec& r : all) ok = ok && r.ok;
+  // map the neighbours' arenas (a peer that is both the low and the high neighbour is opened once)
+  std::vector<std::pair<int, char*>> opened;
+  for (int s = 0; ok && s < 6; ++s) {
+    const int r = c.nbr[s];
+    if (r < 0 || c.size[s / 2] == 1) continue;
+    if (r == g->rank || r >= g->nranks) { ok = 0; break; }
+    char* base = nullptr;
+    for (auto& o : opened) if (o.first == r) base = o.second;
+    if (!base) {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      base = (char*)p;
+      opened.push_back({r, base});
+      g->ipc_opened.push_back(p);
+    }
+    g->peer_arena[s] = base;
+    for (int k = 0; k < 3; ++k) g->peer_dims[s][k] = all[r].dims[k];
+  }
+  // collective agreement
+  int* dflag = (int*)dbuf;
+  CUDA_OK(cudaMemcpyAsync(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice, g->st));
+  NCCL_OK(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, g->comm, g->st));
+  CUDA_OK(cudaMemcpyAsync(&ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  cudaFree(dbuf);
+  g->p2p = ok != 0;
+  if (!g->p2p && g->rank == 0 && !(env && strcmp(env, "nccl") == 0))
+    fprintf(stderr, "astr_gpu: peer-to-peer halo exchange unavailable (CUDA IPC), using ncclSend/ncclRecv\n");
+  return 0;
+}
+
+// one direction through peer memory: SEND (fused pack + remote stores + ready flag), RECV (wait, unpack, ack)
+static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
+  const astr_cfg& c = g->cfg;
+  const Layout& L = g->L;
+  const int dims[3] = {c.im, c.jm, c.km};
+  XHeader* hdr = reinterpret_cast<XHeader*>(g->xarena);
+  const unsigned long long seq = ++g->xseq[d];
+  XArgs sa, ra;
+  memset(&sa, 0, sizeof sa); memset(&ra, 0, sizeof ra);
+  sa.l0 = ra.l0 = l0; sa.l1 = ra.l1 = l1;
+  sa.err = ra.err = &hdr->err;
+  for (int side = 0; side < 2; ++side) {
+    const int slot = 2 * d + side;
+    if (c.nbr[slot] < 0) continue;
+    char* peer = g->peer_arena[slot];
+    XHeader* ph = reinterpret_cast<XHeader*>(peer);
+    const int oslot = 2 * d + (1 - side);      // the face of the neighbour that touches mine
+    XSide& s = sa.s[side];
+    s.active = 1;
+    s.remote = reinterpret_cast<double*>(peer + xwin_offset(g->peer_dims[slot], d, 1 - side));
+    s.wait_flag = &hdr->ack[slot]; s.wait_val = seq - 1;      // my previous data has been consumed
+    s.signal_flag = &ph->ready[oslot]; s.signal_val = seq;
+    s.counter = &hdr->csend[slot];
+    XSide& r = ra.s[side];
+    r.active = 1;
+    r.local = reinterpret_cast<const double*>(g->xarena + xwin_offset(dims, d, side));
+    r.wait_flag = &hdr->ready[slot]; r.wait_val = seq;
+    r.signal_flag = &ph->ack[oslot]; r.signal_val = seq;
+    r.counter = &hdr->crecv[slot];
+  }
+  { ProfScope ps(PC_XPACK); TRY(pw_xsend(L, fl, d, sa, g->st)); }
+  { ProfScope ps(PC_XUNPACK); TRY(pw_xrecv(L, fl, d, ra, g->st)); }
+  return 0;
+}
+
+static int p2p_check() {
+  if (!g->p2p) return 0;
+  unsigned int e = 0;
+  CUDA_OK(cudaMemcpyAsync(&e, g->xarena + offsetof(XHeader, err), sizeof e, cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  if (e) return astr_fail_msg("halo exchange timed out waiting for a neighbour (peer-to-peer flags)");
+  return 0;
 }
 
 static int dataswap(const FieldList& fl, int direction /*-1 all*/) {
@@ -456,6 +592,8 @@ int astr_gpu_finalize(void) {
   for (auto e : g->free_events) cudaEventDestroy(e);
   if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
   for (auto& b : g->xbuf) if (b) cudaFree(b);
+  for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (g->xarena) cudaFree(g->xarena);
   for (int d = 0; d < 3; ++d) {
     cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab);
     if (g->fxp[d].d_tab) cudaFree(g->fxp[d].d_tab);
@@ -476,7 +614,7 @@ int astr_gpu_synchronize(void) {
   NEED_CTX();
   CUDA_OK(cudaStreamSynchronize(g->st));
   prof_collect();
-  return 0;
+  return p2p_check();
 }
 
 int astr_gpu_comm_unique_id(char id[128]) {
@@ -495,7 +633,7 @@ int astr_gpu_comm_init(const char id[128], int nranks, int rank) {
   memcpy(&uid, id, 128);
   NCCL_OK(g_nccl.CommInitRank(&g->comm, nranks, uid, rank));
   g->nranks = nranks; g->rank = rank;
-  return 0;
+  return p2p_setup();
 }
 
 // ---- host <-> device field transfer (Fortran halo'd box <-> padded device box) --------

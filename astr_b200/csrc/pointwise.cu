@@ -524,6 +524,87 @@ __global__ void k_face(const Layout L, const FieldList fl, const int side, const
   else f[x] = buf[bi];
 }
 
+// ---------------------------------------------------------------------------------
+// Fused pack + peer-to-peer halo exchange (replaces pack -> ncclSend/Recv -> unpack).
+// SEND: every CTA first waits until the neighbour has consumed what this rank wrote into the
+// neighbour's receive window last time (ack flag, written by the neighbour into THIS rank's
+// memory), then stores its share of the face planes straight into the neighbour's window over
+// NVLink; the last CTA of a side to finish publishes `ready = seq` in the neighbour's memory.
+// RECV: every CTA waits for `ready >= seq` in its own memory, unpacks from its own window
+// (L1-bypassing loads), and the last CTA acknowledges to the neighbour.
+// Same element order, averaging of shared nodes and plane ranges as k_face above; for i-faces
+// the plane index runs fastest so that the strided gather touches each sector once.
+// A wait that lasts longer than ~4 s raises *err and gives up (no hung GPU).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int DIR, bool SEND>
+__global__ void k_xface(const Layout L, const FieldList fl, const XArgs a) {
+  const int side = blockIdx.z & 1, fld = blockIdx.z >> 1;
+  const XSide& xs = a.s[side];
+  if (!xs.active) return;
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(xs.wait_flag) < xs.wait_val) {
+      if (clock64() - t0 > (1LL << 33)) { atomicExch(a.err, 1u); break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const int n1 = (DIR == 0) ? L.jm + 1 : L.im + 1;
+  const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
+  const int np = a.l1 - a.l0 + 1;
+  const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
+  int p1, p2, l;
+  long long bi;
+  bool ok;
+  if (DIR == 0) {
+    // threads: plane fastest, then j ; blockIdx.y = k
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    l = a.l0 + t % np; p1 = t / np; p2 = blockIdx.y;
+    ok = p1 < n1;
+    bi = (((long long)fld * n2 + p2) * n1 + p1) * np + (l - a.l0);
+  } else {
+    p1 = blockIdx.x * blockDim.x + threadIdx.x;
+    p2 = blockIdx.y / np; l = a.l0 + blockIdx.y % np;
+    ok = p1 < n1;
+    bi = (((long long)fld * n2 + p2) * np + (l - a.l0)) * n1 + p1;
+  }
+  if (ok) {
+    double* f = fl.f[fld];
+    int node;
+    if (SEND) node = side ? dm - l : l;
+    else node = side ? dm + l : -l;
+    long long x;
+    if (DIR == 0) x = L.idx(node, p1, p2);
+    else if (DIR == 1) x = L.idx(p1, node, p2);
+    else x = L.idx(p1, p2, node);
+    if (SEND) xs.remote[bi] = f[x];
+    else {
+      const double v = __ldcg(xs.local + bi);
+      f[x] = (l == 0) ? 0.5 * (f[x] + v) : v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned nblk = gridDim.x * gridDim.y * (gridDim.z >> 1);
+    const unsigned prev = atomicAdd(xs.counter, 1u);
+    if (prev == nblk - 1) {
+      *xs.counter = 0u;
+      __threadfence_system();
+      st_release_sys(xs.signal_flag, xs.signal_val);
+    }
+  }
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK()                        \
@@ -667,6 +748,29 @@ static int face_launch(const Layout& L, const FieldList& fl, int dir, int side, 
   LAUNCH_CHECK();
   return 0;
 }
+template <bool SEND>
+static int xface_launch(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
+  const int n1 = (dir == 0) ? L.jm + 1 : L.im + 1;
+  const int n2 = (dir == 2) ? L.jm + 1 : L.km + 1;
+  const int np = a.l1 - a.l0 + 1;
+  if (dir == 0) {
+    dim3 grid((n1 * np + PW_T - 1) / PW_T, n2, fl.nf * 2);
+    k_xface<0, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
+  } else {
+    dim3 grid((n1 + PW_T - 1) / PW_T, n2 * np, fl.nf * 2);
+    if (dir == 1) k_xface<1, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
+    else k_xface<2, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_xsend(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
+  return xface_launch<true>(L, fl, dir, a, st);
+}
+int pw_xrecv(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
+  return xface_launch<false>(L, fl, dir, a, st);
+}
+
 int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,
             cudaStream_t st) {
   return face_launch<true>(L, fl, dir, side, l0, l1, buf, st);

@@ -60,6 +60,20 @@ int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int
             cudaStream_t st);
 int pw_unpack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, const double* buf,
               cudaStream_t st);
+// fused pack + peer-to-peer exchange (k_xface in pointwise.cu); one XSide per face of the direction
+struct XSide {
+  int active;
+  double* remote;                    // SEND: the neighbour's receive window (peer memory)
+  const double* local;               // RECV: this rank's receive window
+  const unsigned long long* wait_flag;   // in this rank's memory, written by the neighbour
+  unsigned long long wait_val;
+  unsigned long long* signal_flag;   // in the neighbour's memory
+  unsigned long long signal_val;
+  unsigned int* counter;             // CTA completion counter of this side (this rank's memory)
+};
+struct XArgs { XSide s[2]; int l0, l1; unsigned int* err; };
+int pw_xsend(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st);
+int pw_xrecv(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st);
 // Fortran (im+11)(jm+11)(km+11) box <-> padded device box is done with cudaMemcpy3D in api.cu
 
 // ---- upwind-biased compact convection (upwind.cu), conschm = '543c' -------------------------
