@@ -546,8 +546,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 template <int DIR, bool SEND>
-__global__ void k_xface(const Layout L, const FieldList fl, const XArgs a) {
-  const int side = blockIdx.z & 1, fld = blockIdx.z >> 1;
+__global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList fl, const XArgs a) {
+  const int side = blockIdx.z;
   const XSide& xs = a.s[side];
   if (!xs.active) return;
   if (threadIdx.x == 0) {
@@ -562,42 +562,53 @@ __global__ void k_xface(const Layout L, const FieldList fl, const XArgs a) {
   const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
   const int np = a.l1 - a.l0 + 1;
   const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
-  int p1, p2, l;
-  long long bi;
-  bool ok;
-  if (DIR == 0) {
-    // threads: plane fastest, then j ; blockIdx.y = k
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    l = a.l0 + t % np; p1 = t / np; p2 = blockIdx.y;
-    ok = p1 < n1;
-    bi = (((long long)fld * n2 + p2) * n1 + p1) * np + (l - a.l0);
-  } else {
-    p1 = blockIdx.x * blockDim.x + threadIdx.x;
-    p2 = blockIdx.y / np; l = a.l0 + blockIdx.y % np;
-    ok = p1 < n1;
-    bi = (((long long)fld * n2 + p2) * np + (l - a.l0)) * n1 + p1;
-  }
-  if (ok) {
-    double* f = fl.f[fld];
-    int node;
-    if (SEND) node = side ? dm - l : l;
-    else node = side ? dm + l : -l;
-    long long x;
-    if (DIR == 0) x = L.idx(node, p1, p2);
-    else if (DIR == 1) x = L.idx(p1, node, p2);
-    else x = L.idx(p1, p2, node);
-    if (SEND) xs.remote[bi] = f[x];
-    else {
-      const double v = __ldcg(xs.local + bi);
-      f[x] = (l == 0) ? 0.5 * (f[x] + v) : v;
+  // flat index over the window: DIR 0: [field][k][j][plane] (plane fastest, so that the strided gather
+  // touches every sector once); DIR 1, 2: [field][p2][plane][i] (i fastest)
+  const long long total = (long long)fl.nf * n2 * np * n1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += U * stride) {
+    double v[U];
+    long long x[U], bi[U];
+    int lz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bi[u] = base + u * stride;
+      long long r = bi[u] < total ? bi[u] : 0;
+      int p1, p2, l;
+      if (DIR == 0) { l = (int)(r % np); r /= np; p1 = (int)(r % n1); r /= n1; }
+      else { p1 = (int)(r % n1); r /= n1; l = (int)(r % np); r /= np; }
+      p2 = (int)(r % n2);
+      const int fld = (int)(r / n2);
+      l += a.l0;
+      lz[u] = l;
+      const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
+      const long long xx = (DIR == 0) ? L.idx(node, p1, p2) : (DIR == 1 ? L.idx(p1, node, p2) : L.idx(p1, p2, node));
+      x[u] = (long long)(fl.f[fld] - fl.f[0]) + xx;      // element offset from field 0
     }
+    double* f0 = fl.f[0];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (bi[u] < total) {
+        if (SEND) v[u] = f0[x[u]];
+        else {
+          v[u] = __ldcg(xs.local + bi[u]);
+          if (lz[u] == 0) v[u] = 0.5 * (f0[x[u]] + v[u]);
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (bi[u] < total) {
+        if (SEND) xs.remote[bi[u]] = v[u];
+        else f0[x[u]] = v[u];
+      }
   }
-  __threadfence_system();
+  // one system-scope release per CTA: the barrier orders the CTA's stores before thread 0's fence
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned nblk = gridDim.x * gridDim.y * (gridDim.z >> 1);
+    __threadfence_system();
     const unsigned prev = atomicAdd(xs.counter, 1u);
-    if (prev == nblk - 1) {
+    if (prev == gridDim.x - 1) {
       *xs.counter = 0u;
       __threadfence_system();
       st_release_sys(xs.signal_flag, xs.signal_val);
@@ -750,17 +761,18 @@ static int face_launch(const Layout& L, const FieldList& fl, int dir, int side, 
 }
 template <bool SEND>
 static int xface_launch(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
-  const int n1 = (dir == 0) ? L.jm + 1 : L.im + 1;
-  const int n2 = (dir == 2) ? L.jm + 1 : L.km + 1;
-  const int np = a.l1 - a.l0 + 1;
-  if (dir == 0) {
-    dim3 grid((n1 * np + PW_T - 1) / PW_T, n2, fl.nf * 2);
-    k_xface<0, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
-  } else {
-    dim3 grid((n1 + PW_T - 1) / PW_T, n2 * np, fl.nf * 2);
-    if (dir == 1) k_xface<1, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
-    else k_xface<2, SEND><<<grid, PW_T, 0, st>>>(L, fl, a);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // every field must be addressable from field 0 with one 64-bit element offset (same allocation or not:
+  // pointer differences of device allocations are fine as plain integers)
+  dim3 grid(sms * 2, 1, 2);       // 2 CTAs of 256 threads per SM and side
+  if (dir == 0) k_xface<0, SEND><<<grid, 256, 0, st>>>(L, fl, a);
+  else if (dir == 1) k_xface<1, SEND><<<grid, 256, 0, st>>>(L, fl, a);
+  else k_xface<2, SEND><<<grid, 256, 0, st>>>(L, fl, a);
   LAUNCH_CHECK();
   return 0;
 }
