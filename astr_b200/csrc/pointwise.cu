@@ -7,14 +7,27 @@ namespace {
 
 constexpr int PW_T = 128;
 
+// Thread -> node of a box.  Wide boxes: one CTA per 128 consecutive i of a (j,k) row.  Thin boxes (the
+// i-direction halo slabs, <= 16 nodes wide): the CTA's threads run over (i fastest, then j), so that a
+// 128-thread CTA covers 128/w rows instead of one row with w active threads.
+constexpr int PW_THIN = 16;
 __device__ __forceinline__ bool box_node(const Box& b, int& i, int& j, int& k) {
+  const int w = b.hi[0] - b.lo[0] + 1;
+  k = b.lo[2] + blockIdx.z;
+  if (w <= PW_THIN) {
+    const int t = blockIdx.x * PW_T + threadIdx.x;
+    i = b.lo[0] + t % w;
+    j = b.lo[1] + t / w;
+    return j <= b.hi[1];
+  }
   i = b.lo[0] + blockIdx.x * PW_T + threadIdx.x;
   j = b.lo[1] + blockIdx.y;
-  k = b.lo[2] + blockIdx.z;
   return i <= b.hi[0];
 }
 inline dim3 box_grid(const Box& b) {
-  return dim3((b.hi[0] - b.lo[0] + PW_T) / PW_T, b.hi[1] - b.lo[1] + 1, b.hi[2] - b.lo[2] + 1);
+  const int w = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1, nk = b.hi[2] - b.lo[2] + 1;
+  if (w <= PW_THIN) return dim3((w * nj + PW_T - 1) / PW_T, 1, nk);
+  return dim3((w + PW_T - 1) / PW_T, nj, nk);
 }
 inline bool box_empty(const Box& b) {
   return b.hi[0] < b.lo[0] || b.hi[1] < b.lo[1] || b.hi[2] < b.lo[2];
