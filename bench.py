@@ -150,8 +150,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # NCCL writes its version banner / debug log to stdout: keep stdout to ONE JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL (and anything else native) may write banners to fd 1: stdout must carry ONE JSON line only, so
+    # fd 1 points at stderr for the whole run and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -303,7 +306,8 @@ def run_gpu(args):
         "gpu_launches": launches,
         "tgv_sums": list(eng_stats) if eng_stats else None,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
