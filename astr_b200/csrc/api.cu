@@ -509,7 +509,9 @@ int astr_gpu_init(const astr_cfg* cfg) {
   if (!cfg) return astr_fail_msg("null cfg");
   if (cfg->abi_version != ASTR_GPU_ABI_VERSION) return astr_fail_msg("abi_version mismatch");
   if (cfg->hm != ASTR_HM || cfg->numq != ASTR_GPU_NUMQ) return astr_fail_msg("hm must be 5 and numq 5");
-  if (cfg->ndims != 3 || cfg->km < 1) return astr_fail_msg("only ndims=3 blocks are implemented");
+  // ndims=3, or ndims=2 with km=0 (the k planes -hm..hm then replicate plane 0, src/parallel.F90:4296-4299)
+  if (!((cfg->ndims == 3 && cfg->km >= 1) || (cfg->ndims == 2 && cfg->km == 0 && cfg->size[2] == 1)))
+    return astr_fail_msg("ndims must be 3 (km>=1) or 2 (km=0, ksize=1)");
   for (int n = 0; n < 6; ++n)
     if (cfg->bctype[n] != 1 && cfg->bctype[n] != 41)
       return astr_fail_msg("bctype must be 1 (periodic) or 41 (isothermal no-slip wall)");
@@ -553,7 +555,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
   TRY(astr_set_filter_coef(g->fc));
   { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < cfg->ndims; ++d) {
     const int n = dim_of(d);
     build_deriv(g->fd[d], cfg->npdc[d], n);
     build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
@@ -758,6 +760,7 @@ int astr_gpu_set_grid(const double* x) {
 
 int astr_gpu_gridgeom(const double* x) {
   NEED_CTX();
+  if (g->cfg.ndims != 3) return astr_fail_msg("device gridgeom covers ndims=3 only: pass the metrics with astr_gpu_set_metrics");
   TRY(ensure_scratch());
   const size_t ne = host_field_elems();
   for (int m = 0; m < 3; ++m) TRY(copy_field(S_G + m, const_cast<double*>(x) + (size_t)m * ne, false));
@@ -799,7 +802,7 @@ int astr_gpu_filterq(void) {
   NEED_CTX();
   const astr_cfg& c = g->cfg;
   const FieldList fq = fields(S_Q, 5);
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < c.ndims; ++d) {              // comsolver.F90:588 `if(ndims==3)` for k
     TRY(dataswap(fq, d));                          // comsolver.F90:535,562,590
     const int n = dim_of(d);
     const int nt = c.npdc[d];
@@ -874,7 +877,7 @@ int astr_gpu_gradcal(void) {
   NEED_CTX();
   if (!g->have_metrics) return astr_fail_msg("gradcal before set_metrics/gridgeom");
   const double* in[4] = {g->slot(S_VEL), g->slot(S_VEL + 1), g->slot(S_VEL + 2), g->slot(S_TMP)};
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < g->cfg.ndims; ++d) {         // comsolver.F90:418 `if(ndims==3)` for k: raw k-derivatives stay 0
     double* out[4];
     for (int m = 0; m < 4; ++m) out[m] = g->slot(S_RAW + 4 * d + m);
     ProfScope ps(PC_GRAD_I + d);
@@ -938,15 +941,15 @@ int astr_gpu_rhscal(void) {
   if (c.diffterm) {
     // viscous stress + flux assembly of the block in one pass (sigma/qflux stay in registers and
     // reach memory only on the face shells the exchange reads), then the halo exchange
-    { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, g->st)); }
+    { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, c.ndims, g->st)); }
     g->sigma_partial = true;
     TRY(dataswap(fields(S_SIGMA, 9), -1));         // sigma(6)+qflux(3), solver.F90:2604-2606
   }
   {
     ProfScope ps(PC_FLUX);
     Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-    if (!c.diffterm && !upw) TRY(pw_flux(L, g->pool, b, 7, fr, c.diffterm, g->st));
-    for (int d = 0; d < 3 && (c.diffterm || !upw); ++d)   // halo slabs of direction d (fluxes on halo nodes,
+    if (!c.diffterm && !upw) TRY(pw_flux(L, g->pool, b, c.ndims == 3 ? 7 : 3, fr, c.diffterm, g->st));
+    for (int d = 0; d < c.ndims && (c.diffterm || !upw); ++d)   // halo slabs of direction d (fluxes on halo nodes,
       for (int side = 0; side < 2; ++side) {       // solver.F90:2200-2206)
         Box h = b;
         h.lo[d] = side ? dim_of(d) + 1 : -ASTR_HM;
@@ -957,7 +960,7 @@ int astr_gpu_rhscal(void) {
   const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
   if (!c.scheme_compact) {
     // explicit stencils cannot run in place: accumulate the three directions into qrhs
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c.ndims; ++d) {
       const double* in[5]; double* out[5];
       for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_QRHS + m); }
       if (c.diffterm || !upw) {
@@ -973,7 +976,8 @@ int astr_gpu_rhscal(void) {
   }
   // d(G_d)/d(xi_d) in place (zero outside is:ie etc., where the reference does not accumulate);
   // the three directions are summed by the RK update kernel: no read-modify-write of qrhs
-  for (int d = 0; d < 3; ++d) {
+  // (2-D blocks: the G slots of the zeta direction are never written and stay zero)
+  for (int d = 0; d < c.ndims; ++d) {
     const double* in[5]; double* out[5];
     for (int m = 0; m < 5; ++m) { in[m] = g->slot(S_G + 5 * d + m); out[m] = g->slot(S_G + 5 * d + m); }
     if (!upw) {
@@ -1070,6 +1074,7 @@ int astr_gpu_set_force(const double force[3]) {
 
 int astr_gpu_reduce_tgv(double out[3]) {
   NEED_CTX();
+  if (g->cfg.ndims != 3) return astr_fail_msg("reduce_tgv covers ndims=3 only");
   if (!g->have_grad) return astr_fail_msg("reduce_tgv before gradcal");
   TRY(pw_stats(g->L, g->pool, g->d_partial, g->d_out2, g->st));
   double h[2];

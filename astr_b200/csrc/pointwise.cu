@@ -72,6 +72,15 @@ __global__ void k_halo_wrap(const Layout L, const FieldList fl, const int mode) 
   if (DIR == 1) { base = L.idx(a, 0, b); sl = L.sj; dm = L.jm; }
   else { base = L.idx(a, b, 0); sl = L.sk; dm = L.km; }
   double* p = f + base;
+  if (dm == 0) {
+    // 2-D block (ka==0): every plane -hm..hm is a copy of plane 0 (src/parallel.F90:4296-4299, :5161-5164)
+    if (mode != XMODE_SYNC) {
+      const double v = p[0];
+#pragma unroll
+      for (int l = 1; l <= ASTR_HM; ++l) { p[-l * sl] = v; p[l * sl] = v; }
+    }
+    return;
+  }
   if (mode != XMODE_SYNC) {
 #pragma unroll
     for (int l = 1; l <= ASTR_HM; ++l) {
@@ -266,6 +275,7 @@ __global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, c
 // the flux assembly of all three directions.  They are written to memory only on the shells
 // within ASTR_HM nodes of a block face, which is all the halo exchange (solver.F90:2604-2606)
 // and the halo-slab flux passes read.
+template <int DMASK>
 __global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const Thermo th, const FluxRanges fr) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   int ijk[3];
@@ -281,7 +291,7 @@ __global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const The
 #pragma unroll
     for (int n = 0; n < 3; ++n) pool[(S_QFLUX + n) * fs + x] = qf[n];
   }
-  flux_node<7>(pool, fs, x, ijk, fr, 1, sg, qf);
+  flux_node<DMASK>(pool, fs, x, ijk, fr, 1, sg, qf);
 }
 
 // ---------------------------------------------------------------------------------
@@ -339,8 +349,8 @@ __global__ void k_sum_qrhs(const Layout L, double* __restrict__ pool, const doub
 // yc = x(:,:,:,2) in the common Layout.
 // ---------------------------------------------------------------------------------
 __global__ void k_bulk_rows(const Layout L, const double* __restrict__ pool, const double* __restrict__ yc,
-                            double* __restrict__ partial) {
-  const int j = 1 + blockIdx.x, k = 1 + blockIdx.y;
+                            double* __restrict__ partial, const int k1) {
+  const int j = 1 + blockIdx.x, k = k1 + blockIdx.y;    // k1 = 0 for 2-D blocks (solver.F90:306-315)
   const long long fs = L.fstride;
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = 1 + threadIdx.x; i <= L.im; i += PW_T) {
@@ -662,9 +672,10 @@ int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st) {
   return 0;
 }
 
-int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, cudaStream_t st) {
+int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  k_visc_flux<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);
+  if (ndims == 3) k_visc_flux<7><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);
+  else k_visc_flux<3><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);    // 2-D: no zeta flux (solver.F90:2776)
   LAUNCH_CHECK();
   return 0;
 }
@@ -708,10 +719,11 @@ int pw_sum_qrhs(const Layout& L, double* pool, const double* src, cudaStream_t s
 }
 
 int pw_bulk(const Layout& L, const double* pool, const double* yc, double* partial, double* out4, cudaStream_t st) {
-  dim3 grid(L.jm, L.km);
-  k_bulk_rows<<<grid, PW_T, 0, st>>>(L, pool, yc, partial);
+  const int nk = L.km == 0 ? 1 : L.km;
+  dim3 grid(L.jm, nk);
+  k_bulk_rows<<<grid, PW_T, 0, st>>>(L, pool, yc, partial, L.km == 0 ? 0 : 1);
   LAUNCH_CHECK();
-  k_bulk_final<<<1, 256, 0, st>>>(partial, (long long)L.jm * L.km, out4);
+  k_bulk_final<<<1, 256, 0, st>>>(partial, (long long)L.jm * nk, out4);
   LAUNCH_CHECK();
   return 0;
 }

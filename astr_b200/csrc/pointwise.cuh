@@ -40,7 +40,7 @@ int pw_materialise_grad(const Layout& L, double* pool, double* dvel9_dtmp3_vor3,
 // dmask bit d => build G_d ; cmask[d][2]: conv part only where the other two indices lie in
 // [s,e] ranges (src/solver.F90:2197-2198) ; diffterm adds the viscous part.
 struct FluxRanges { int s[3], e[3]; };
-int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, cudaStream_t st);
+int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, cudaStream_t st);
 int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
             cudaStream_t st);
 struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; };

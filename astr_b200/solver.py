@@ -56,7 +56,7 @@ class RhsEngine:
         c.device = device
         c.im, c.jm, c.km = block.dims
         c.ia, c.ja, c.ka = global_dims
-        c.hm, c.numq, c.ndims = HM, 5, 3
+        c.hm, c.numq, c.ndims = HM, 5, (2 if block.dims[2] == 0 else 3)   # ka==0: 2-D block
         c.npdc[:] = block.npdc
         c.is_, c.js, c.ks = block.s
         c.ie, c.je, c.ke = block.e

@@ -44,7 +44,7 @@ typedef struct astr_cfg {
   int ia, ja, ka;             /* global grid intervals                                   */
   int hm;                     /* must be 5                                               */
   int numq;                   /* must be 5                                               */
-  int ndims;                  /* 3 (2-D blocks: km=0 -- not implemented yet)             */
+  int ndims;                  /* 3, or 2 with km=0 (src/parallel.F90:208-214)            */
   int npdc[3];                /* npdci,npdcj,npdck: 1,2,3,4 (src/parallel.F90:1042-1228) */
   int is, ie, js, je, ks, ke; /* qrhs accumulation ranges (src/parallel.F90:1079-1095)   */
   int lhomo[3];               /* lihomo,ljhomo,lkhomo                                    */

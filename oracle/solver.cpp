@@ -34,6 +34,7 @@ struct Block {
 
 struct Case {
   int ia, ja, ka, size[3];
+  int ndims() const { return ka == 0 ? 2 : 3; }   // src/parallel.F90:208-214
   bool homo[3];
   bool lfilter = true, diffterm = true;
   double alfa_filter = 0.49, deltat = 1e-3, time = 0.0;
@@ -313,9 +314,19 @@ static void gridsendrecv(Case& c) {
     if (c.size[d] == 1) {
       for (Block& b : c.blk) {
         const int dm = b.dim(d);
-        if (dm == 0) continue;
         int n1, n2;
         others(b, d, n1, n2);
+        if (dm == 0) {  // ka==0 (:3015-3021): planes -hm..hm copy x,y of plane 0, z = z(0)+k
+          for (int p2 = 0; p2 <= n2; ++p2)
+            for (int p1 = 0; p1 <= n1; ++p1)
+              for (int l = -hm; l <= hm; ++l) {
+                if (l == 0) continue;
+                at(b.x[0], d, l, p1, p2) = at(b.x[0], d, 0, p1, p2);
+                at(b.x[1], d, l, p1, p2) = at(b.x[1], d, 0, p1, p2);
+                at(b.x[2], d, l, p1, p2) = at(b.x[2], d, 0, p1, p2) + double(l);
+              }
+          continue;
+        }
         for (int m = 0; m < 3; ++m)
           for (int p2 = 0; p2 <= n2; ++p2)
             for (int p1 = 0; p1 <= n1; ++p1)
@@ -387,7 +398,7 @@ static void gridgeom(Case& c) {
     Block& b = c.blk[ib];
     DX[ib].resize(9);
     for (auto& f : DX[ib]) f.alloc(b.im, b.jm, b.km);
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < c.ndims(); ++d)
       for_each_pencil(b, d, [&](int p1, int p2) {
         PencilWork w(md);
         for (int m = 0; m < 3; ++m) {
@@ -414,6 +425,9 @@ static void gridgeom(Case& c) {
     for (int k = 0; k <= b.km; ++k)
       for (int j = 0; j <= b.jm; ++j)
         for (int i = 0; i <= b.im; ++i)
+          if (c.ndims() == 2)   // :371-375
+            b.jacob(i, j, k) = dx(1, 1)(i, j, k) * dx(2, 2)(i, j, k) - dx(1, 2)(i, j, k) * dx(2, 1)(i, j, k);
+          else
           b.jacob(i, j, k) = dx(1, 1)(i, j, k) * dx(2, 2)(i, j, k) * dx(3, 3)(i, j, k) +
                              dx(1, 2)(i, j, k) * dx(2, 3)(i, j, k) * dx(3, 1)(i, j, k) +
                              dx(1, 3)(i, j, k) * dx(2, 1)(i, j, k) * dx(3, 2)(i, j, k) -
@@ -441,6 +455,17 @@ static void gridgeom(Case& c) {
         {2, 1, 1, 2, 2, 3, 3, 2, 2}, {2, 1, 2, 3, 2, 1, 1, 2, 3}, {2, 1, 3, 1, 2, 2, 2, 2, 1},
         {2, 2, 1, 3, 1, 2, 2, 1, 3}, {2, 2, 2, 1, 1, 3, 3, 1, 1}, {2, 2, 3, 2, 1, 1, 1, 1, 2}};
     for (auto& r : b.dxi) for (auto& f : r) std::fill(f.v.begin(), f.v.end(), 0.0);
+    if (c.ndims() == 2) {   // :520-527
+      for (int k = 0; k <= b.km; ++k)
+        for (int j = 0; j <= b.jm; ++j)
+          for (int i = 0; i <= b.im; ++i) {
+            b.dxi[0][0](i, j, k) = dx(2, 2)(i, j, k);
+            b.dxi[0][1](i, j, k) = -dx(1, 2)(i, j, k);
+            b.dxi[1][0](i, j, k) = -dx(2, 1)(i, j, k);
+            b.dxi[1][1](i, j, k) = dx(1, 1)(i, j, k);
+          }
+      continue;
+    }
     for (const Term& t : terms) {
       for_each_pencil(b, t.d, [&](int p1, int p2) {
         PencilWork w(md);
@@ -479,7 +504,7 @@ static void gridgeom(Case& c) {
 static void filterq(Case& c) {
   const int md = std::max(c.ia, std::max(c.ja, c.ka));
   Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < c.ndims(); ++d) {   // comsolver.F90:588 `if(ndims==3)` for k
     dataswap(c, gq, d);
     for (Block& b : c.blk) {
       const int dm = b.dim(d);
@@ -501,7 +526,7 @@ static void gradcal(Case& c) {
   for (Block& b : c.blk) {
     for (auto& r : b.dvel) for (auto& f : r) std::fill(f.v.begin(), f.v.end(), 0.0);
     for (auto& f : b.dtmp) std::fill(f.v.begin(), f.v.end(), 0.0);
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c.ndims(); ++d) {   // comsolver.F90:418 `if(ndims==3)` for k
       const int dm = b.dim(d);
       for_each_pencil(b, d, [&](int p1, int p2) {
         PencilWork w(md);
@@ -524,7 +549,7 @@ static void gradcal(Case& c) {
 static void convrsdcal6(Case& c) {
   const int md = std::max(c.ia, std::max(c.ja, c.ka));
   for (Block& b : c.blk) {
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c.ndims(); ++d) {   // solver.F90:2284 `if(ndims==3)` for k
       const int dm = b.dim(d);
       const int np = md + 1 + 2 * hm;
       int o1, o2;  // the two other directions
@@ -607,7 +632,7 @@ static void diffrsdcal6(Case& c) {
   dataswap(c, gqf);  // :2606
   static const int sel[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};  // rows of the symmetric sigma
   for (Block& b : c.blk) {
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c.ndims(); ++d) {   // solver.F90:2776 `if(ndims==3)` for k
       const int dm = b.dim(d);
       const int np = md + 1 + 2 * hm;
       for_each_pencil(b, d, [&](int p1, int p2) {  // all pencils 0:jm,0:km (:2623-2624)
@@ -637,13 +662,14 @@ static void diffrsdcal6(Case& c) {
 
 #include "upwind.hpp"
 
-// src/solver.F90:295-353 src_chan (ndims==3): bulk velocities by trapezoidal integration in y over
+// src/solver.F90:295-353 src_chan: bulk velocities by trapezoidal integration in y over
 // nodes 1..im,1..jm,1..km of every rank (psum = sum over blocks), then the body force
 static void src_chan(Case& c) {
   double robulk = 0.0, u1bulk = 0.0, u2bulk = 0.0, u3bulk = 0.0;
   for (Block& b : c.blk) {
     double ro = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-    for (int k = 1; k <= b.km; ++k)
+    const int k1 = c.ndims() == 2 ? 0 : 1, k2 = c.ndims() == 2 ? 0 : b.km;   // :306-315
+    for (int k = k1; k <= k2; ++k)
       for (int j = 1; j <= b.jm; ++j)
         for (int i = 1; i <= b.im; ++i) {
           const double dy = b.x[1](i, j, k) - b.x[1](i, j - 1, k);
@@ -803,7 +829,7 @@ static void rk_stage(Case& c, int rkstep) {
   gradcal(c);
   if (rkstep == 1) {
     save_q(c);
-    statcal(c);  // rkfirst -> statcal
+    if (c.ndims() == 3) statcal(c);  // rkfirst -> statcal (the 2-D statistics are not restated)
   }
   rhscal(c);
   rk_update(c, rkstep);
@@ -858,7 +884,7 @@ void* oracle_case_create(int ia, int ja, int ka, int isize, int jsize, int ksize
   filter_coefficient_cal(c->fc, alfa_filter, 1.11, 0.98);  // comsolver.F90:121
   for (Block& b : c->blk) {
     alloc_block(b);
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c->ndims(); ++d) {
       fd_scheme_initiate(b.fds[d], 643, 'c', b.npdc[d], b.dim(d));
       compact_filter_initiate(b.fil[d], b.npdc[d], b.dim(d), alfa_filter);
     }
@@ -868,7 +894,7 @@ void* oracle_case_create(int ia, int ja, int ka, int isize, int jsize, int ksize
         for (int i = 0; i <= b.im; ++i) {
           b.x[0](i, j, k) = lx / double(ia) * double(i + b.g0[0]);
           b.x[1](i, j, k) = ly / double(ja) * double(j + b.g0[1]);
-          b.x[2](i, j, k) = lz / double(ka) * double(k + b.g0[2]);
+          b.x[2](i, j, k) = ka == 0 ? 0.0 : lz / double(ka) * double(k + b.g0[2]);
         }
   }
   c->xmax = lx / double(ia) * double(ia);

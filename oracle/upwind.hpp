@@ -390,7 +390,7 @@ static int convrsdcmp(Case& c) {
   int bad = 0;
   for (Block& b : c.blk) {
     const bool sson = !b.lshock.v.empty();   // allocated(lshock)
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < c.ndims(); ++d) {   // solver.F90:1719 `if(ndims==2) return` after j
       const int dm = b.dim(d), nt = b.npdc[d];
       CompactScheme uw, dw;
       compact_flux_initiate(uw, 543, nt, dm, '+', bf);   // comsolver.F90:103-108

@@ -16,7 +16,7 @@ def stretched_x(n, homo):
     distortion elsewhere, so that all 9 metric terms are non-trivial."""
     ia, ja, ka = n
     L = 2 * np.pi
-    s = [np.arange(m + 1) / m for m in n]
+    s = [np.arange(m + 1) / max(m, 1) for m in n]      # ka == 0: 2-D block, one plane
     S = np.meshgrid(*s, indexing="ij")
     X = []
     for d in range(3):
@@ -37,7 +37,7 @@ def skewed_x(n, homo):
     (rgp = 1/gpd, src/solver.F90:2052) well conditioned; a periodic direction stays periodic up to
     a constant coordinate jump, which gridsendrecv carries as relative offsets."""
     L = 2 * np.pi
-    s = [np.arange(m + 1) / m for m in n]
+    s = [np.arange(m + 1) / max(m, 1) for m in n]
     S = np.meshgrid(*s, indexing="ij")
     X = [L * (S[d] + 0.04 * np.sin(2 * np.pi * S[d])) if homo[d]
          else L * 0.5 * (1.0 + np.tanh(1.07 * (2 * S[d] - 1)) / np.tanh(1.07)) for d in range(3)]

@@ -40,6 +40,12 @@ CASES = {
                           upwind=dict(lchardecomp=False)),
     "upwind_explicit": dict(n=(32, 32, 32), homo=(True, True, False), stretch=True, perturb=1e-2, explicit=True,
                             upwind=dict(lchardecomp=True, shkcrt="auto")),
+    # 2-D blocks (ka=0, the shape of the HBL / SWLBI inputs): k planes replicate plane 0, no zeta sweeps
+    "tgv2d": dict(n=(48, 40, 0), homo=(True, True, True)),
+    "walls2d_stretched": dict(n=(40, 48, 0), homo=(False, False, True), stretch=True),
+    "upwind2d_walls": dict(n=(48, 40, 0), homo=(False, False, True), stretch=True, perturb=1e-2,
+                           upwind=dict(lchardecomp=True, shkcrt="auto")),
+    "explicit2d": dict(n=(40, 40, 0), homo=(True, False, True), stretch=True, explicit=True),
     "channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0),
 }
 
