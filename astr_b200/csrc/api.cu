@@ -185,6 +185,7 @@ struct Ctx {
   bool sigma_partial = false;    // sigma/qflux are in memory only on the face shells (fused rhscal)
   double force[3] = {0, 0, 0};
   double* ycoord = nullptr;      // x(:,:,:,2) for src_chan (flowtype channel only)
+  double* d_inflow = nullptr;    // vel_in(0:jm,0:km,3) | tmp_in(0:jm,0:km) | tmp_prof(0:jm)  (bctype(1)=11)
   double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
   bool src_pending = false;      // src_chan's term is not in the G slots: consumers add d_src+4
   const double* src() const { return src_pending ? d_src + 4 : nullptr; }
@@ -513,8 +514,10 @@ int astr_gpu_init(const astr_cfg* cfg) {
   if (!((cfg->ndims == 3 && cfg->km >= 1) || (cfg->ndims == 2 && cfg->km == 0 && cfg->size[2] == 1)))
     return astr_fail_msg("ndims must be 3 (km>=1) or 2 (km=0, ksize=1)");
   for (int n = 0; n < 6; ++n)
-    if (cfg->bctype[n] != 1 && cfg->bctype[n] != 41)
-      return astr_fail_msg("bctype must be 1 (periodic) or 41 (isothermal no-slip wall)");
+    if (!(cfg->bctype[n] == 1 || cfg->bctype[n] == 41 || (cfg->bctype[n] == 11 && n == 0) ||
+          (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n == 3)))
+      return astr_fail_msg("bctype on the device: 1 (periodic), 41 (isothermal wall, any face), 11 (inflow, imin), "
+                           "21 (outflow, imax or jmax), 51 (farfield, jmax)");
   if (!cfg->nondimen) return astr_fail_msg("only nondimen=t is implemented");
   // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
   if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
@@ -606,6 +609,7 @@ int astr_gpu_finalize(void) {
   cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
   cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
   if (g->ycoord) cudaFree(g->ycoord);
+  if (g->d_inflow) cudaFree(g->d_inflow);
   cudaStreamDestroy(g->st);
   delete g;
   g = nullptr;
@@ -827,8 +831,21 @@ int astr_gpu_boucon(void) {
       if (!mine) continue;
       ProfScope ps(PC_HALO);
       TRY(pw_noslip(g->L, g->pool, g->th, d, side, c.twall[n], g->st));
+    } else if ((bt == 11 && n == 0) || (bt == 21 && (n == 1 || n == 3)) || (bt == 51 && n == 3)) {
+      // inflow(1) bc.F90:1366, outflow(2|4) :3404, farfield(4) :3008 -- the faces the reference itself treats
+      if (!mine) continue;
+      BcArgs a;
+      a.kind = bt; a.side = side; a.pinf = c.pinf; a.deltat = c.deltat;
+      a.vel_in = a.tmp_in = a.tmp_prof = nullptr;
+      if (bt == 11) {
+        if (!g->d_inflow) return astr_fail_msg("boucon: bctype 11 needs astr_gpu_set_inflow");
+        const size_t nf = (size_t)(c.jm + 1) * (c.km + 1);
+        a.vel_in = g->d_inflow; a.tmp_in = g->d_inflow + 3 * nf; a.tmp_prof = g->d_inflow + 4 * nf;
+      }
+      ProfScope ps(PC_HALO);
+      TRY(pw_bcface(g->L, g->pool, g->th, d, a, g->st));
     } else {
-      return astr_fail_msg("boucon: only bctype 1 (periodic) and 41 (isothermal no-slip wall) run on the device");
+      return astr_fail_msg("boucon: this bctype / face combination does not run on the device");
     }
   }
   return 0;
@@ -1064,6 +1081,20 @@ int astr_gpu_dataswap(int field_id, int direction) {
   TRY(api_slot(field_id, &s));
   if (s >= S_SCR) return astr_fail_msg("dataswap of a derived field");
   return dataswap(fields(s, 1), direction - 1);
+}
+
+// inflow data of alloinflow (src/bc.F90:69-83) as profileinflow / freestreaminflow / inflowintp leave it:
+// vel_in(0:jm,0:km,1:3), tmp_in(0:jm,0:km), tmp_prof(0:jm).  Only ranks with irk==0 use it.
+int astr_gpu_set_inflow(const double* vel_in, const double* tmp_in, const double* tmp_prof) {
+  NEED_CTX();
+  const astr_cfg& c = g->cfg;
+  const size_t nf = (size_t)(c.jm + 1) * (c.km + 1), tot = 4 * nf + c.jm + 1;
+  if (!g->d_inflow) CUDA_OK(cudaMalloc(&g->d_inflow, tot * sizeof(double)));
+  CUDA_OK(cudaMemcpyAsync(g->d_inflow, vel_in, 3 * nf * sizeof(double), cudaMemcpyHostToDevice, g->st));
+  CUDA_OK(cudaMemcpyAsync(g->d_inflow + 3 * nf, tmp_in, nf * sizeof(double), cudaMemcpyHostToDevice, g->st));
+  CUDA_OK(cudaMemcpyAsync(g->d_inflow + 4 * nf, tmp_prof, (c.jm + 1) * sizeof(double), cudaMemcpyHostToDevice, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
 }
 
 int astr_gpu_set_force(const double force[3]) {

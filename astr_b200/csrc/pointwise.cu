@@ -548,6 +548,75 @@ __global__ void k_face(const Layout L, const FieldList fl, const int side, const
 }
 
 // ---------------------------------------------------------------------------------
+// inflow(1) (src/bc.F90:1366-1562), outflow(2) / outflow(4) (:3404-3617), farfield(4) (:3008-3392);
+// nondimensional gas, no species.  extrapolate(v1,v2,dv=0) = (4 v1 - v2)/3 (commfunc.F90:277-285).
+// Threads run over the two other indices of the face (a fastest).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double extrap2(double v1, double v2) { return (1.0 / 3.0) * (4.0 * v1 - v2 - 2.0 * 0.0); }
+
+template <int DIR>
+__global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo th, const BcArgs a) {
+  const int na = (DIR == 0) ? L.jm + 1 : L.im + 1;
+  const int p1 = blockIdx.x * PW_T + threadIdx.x, p2 = blockIdx.y;
+  if (p1 >= na) return;
+  const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
+  const int l = a.side ? dm : 0;
+  const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk), sg = a.side ? -sd : sd;
+  const long long x = (DIR == 0) ? L.idx(l, p1, p2) : (DIR == 1 ? L.idx(p1, l, p2) : L.idx(p1, p2, l));
+  const long long fs = L.fstride;
+  double* rho = pool + S_RHO * fs; double* prs = pool + S_PRS * fs; double* tmp = pool + S_TMP * fs;
+  double* v0 = pool + (S_VEL + 0) * fs; double* v1 = pool + (S_VEL + 1) * fs; double* v2 = pool + (S_VEL + 2) * fs;
+  bool from_T = true;       // fvar2q with temperature (true) or pressure (false)
+  if (a.kind == 11) {       // inflow, face i=0
+    const int j = p1, k = p2, nj = L.jm + 1, nk = L.km + 1;
+    const double vin0 = a.vel_in[j + (long long)nj * k], vin1 = a.vel_in[j + (long long)nj * (k + (long long)nk)],
+                 vin2 = a.vel_in[j + (long long)nj * (k + 2LL * nk)];
+    const double rho_ref = rho[x + sg];
+    const double css = sqrt(a.tmp_prof[j]) / th.mach;
+    v1[x] = vin1; v2[x] = vin2;
+    tmp[x] = a.tmp_in[j + (long long)nj * k];
+    const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]);
+    const double ue = extrap2(v0[x + sg], v0[x + 2 * sg]);
+    const double malo = vin0 / css;
+    const double blend = 0.5 * (tanh((malo - 1.0) * 6.0) + 1.0);
+    const double p = (0.5 * (a.pinf + pe) + 0.5 * rho_ref * css * (vin0 - ue)) * (1.0 - blend) + a.pinf * blend;
+    prs[x] = p;
+    v0[x] = vin0 + (a.pinf - p) / rho_ref / css;
+    rho[x] = p / tmp[x] * th.const2;
+  } else if (a.kind == 21 && DIR == 0) {   // outflow at imax: first-order copy
+    v0[x] = v0[x + sg]; v1[x] = v1[x + sg]; v2[x] = v2[x + sg];
+    prs[x] = prs[x + sg]; tmp[x] = tmp[x + sg];
+    rho[x] = prs[x] / tmp[x] * th.const2;
+  } else {                  // outflow at jmax (21) / farfield at jmax (51): second-order extrapolation
+    const double ue = extrap2(v0[x + sg], v0[x + 2 * sg]), ve = extrap2(v1[x + sg], v1[x + 2 * sg]),
+                 we = extrap2(v2[x + sg], v2[x + 2 * sg]);
+    const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]), roe = extrap2(rho[x + sg], rho[x + 2 * sg]);
+    if (a.kind == 51) {
+      prs[x] = pe; rho[x] = roe;
+    } else {
+      const double css = sqrt(tmp[x]) / th.mach;
+      const double ub = v1[x];
+      if (ub >= css) { prs[x] = pe; rho[x] = roe; }
+      else {
+        const double te = extrap2(tmp[x + sg], tmp[x + 2 * sg]);
+        const double alpha = 0.25;
+        const double p = (prs[x] + alpha * a.deltat * a.pinf + rho[x] * css * (ve - v1[x])) / (1.0 + alpha * a.deltat);
+        prs[x] = p;
+        rho[x] = p / te * th.const2;
+      }
+      from_T = false;
+    }
+    v0[x] = ue; v1[x] = ve; v2[x] = we;
+    tmp[x] = prs[x] / rho[x] * th.const2;
+  }
+  const double r = rho[x], u = v0[x], v = v1[x], w = v2[x];
+  pool[(S_Q + 0) * fs + x] = r; pool[(S_Q + 1) * fs + x] = r * u; pool[(S_Q + 2) * fs + x] = r * v;
+  pool[(S_Q + 3) * fs + x] = r * w;
+  const double var1 = 0.5 * (u * u + v * v + w * w);
+  pool[(S_Q + 4) * fs + x] = from_T ? r * (tmp[x] * th.const1 + var1) : prs[x] * th.const6 + r * var1;
+}
+
+// ---------------------------------------------------------------------------------
 // Fused pack + peer-to-peer halo exchange (replaces pack -> ncclSend/Recv -> unpack).
 // SEND: every CTA first waits until the neighbour has consumed what this rank wrote into the
 // neighbour's receive window last time (ack flag, written by the neighbour into THIS rank's
@@ -741,6 +810,16 @@ int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st) {
   if (dir == 0) k_diff6e<0><<<grid, PW_T, 0, st>>>(L, a);
   else if (dir == 1) k_diff6e<1><<<grid, PW_T, 0, st>>>(L, a);
   else k_diff6e<2><<<grid, PW_T, 0, st>>>(L, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_bcface(const Layout& L, double* pool, const Thermo& th, int dir, const BcArgs& a, cudaStream_t st) {
+  const int na = (dir == 0) ? L.jm + 1 : L.im + 1, nb = (dir == 2) ? L.jm + 1 : L.km + 1;
+  dim3 grid((na + PW_T - 1) / PW_T, nb);
+  if (dir == 0) k_bcface<0><<<grid, PW_T, 0, st>>>(L, pool, th, a);
+  else if (dir == 1) k_bcface<1><<<grid, PW_T, 0, st>>>(L, pool, th, a);
+  else k_bcface<2><<<grid, PW_T, 0, st>>>(L, pool, th, a);
   LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,15 @@ int pw_bulk(const Layout& L, const double* pool, const double* yc, double* parti
 int pw_src_coef(const double* bulk4, const double force[3], double* src4, cudaStream_t st);
 // explicit_central (diff6ec, src/derivative.F90:350-413); a.op.n / a.op.ntype describe the line
 int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st);
+// inflow (11, imin) / outflow (21, imax or jmax) / farfield (51, jmax) on one face (k_bcface)
+struct BcArgs {
+  int kind, side;
+  double pinf, deltat;
+  const double* vel_in;    // device (0:jm,0:km,3)   inflow only
+  const double* tmp_in;    // device (0:jm,0:km)
+  const double* tmp_prof;  // device (0:jm)
+};
+int pw_bcface(const Layout& L, double* pool, const Thermo& th, int dir, const BcArgs& a, cudaStream_t st);
 int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side, double tw, cudaStream_t st);
 int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* src,
                  cudaStream_t st);

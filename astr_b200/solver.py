@@ -74,6 +74,7 @@ class RhsEngine:
         c.bctype[:] = [int(b) for b in bctype]
         c.twall[:] = [float(t) for t in twall]
         c.alfa_filter = alfa_filter
+        c.pinf = 1.0 / thermo["const2"]       # roinf*tinf/const2 with roinf=tinf=1 (src/solver.F90:113-120)
         for k, v in thermo.items():
             setattr(c, k, v)
         c.deltat = deltat
@@ -124,6 +125,13 @@ class RhsEngine:
         """Node coordinates x(-hm:im+hm,...,3) for src_chan's y integration (channel only)."""
         assert x.shape == self.shape + (3,)
         _l.check(self._lib.astr_gpu_set_grid(self._ptr(np.asfortranarray(x))))
+
+    def set_inflow(self, vel_in: np.ndarray, tmp_in: np.ndarray, tmp_prof: np.ndarray):
+        """Inflow data of bctype(1)=11 (src/bc.F90:69-83): vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km), tmp_prof(0:jm)."""
+        im, jm, km = self.block.dims
+        a = [np.asfortranarray(v, dtype=np.float64) for v in (vel_in, tmp_in, tmp_prof)]
+        assert a[0].shape == (jm + 1, km + 1, 3) and a[1].shape == (jm + 1, km + 1) and a[2].shape == (jm + 1,)
+        _l.check(self._lib.astr_gpu_set_inflow(*[v.ctypes.data for v in a]))
 
     def set_force(self, force: Sequence[float]):
         f = (ctypes.c_double * 3)(*[float(v) for v in force])

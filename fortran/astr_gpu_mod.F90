@@ -37,6 +37,7 @@ module astr_gpu_mod
     real(c_double) :: tempconst,tempconst1
     real(c_double) :: deltat
     real(c_double) :: twall(6)
+    real(c_double) :: pinf
     real(c_double) :: bfacmpld,shkcrt
   end type astr_cfg
   !
@@ -77,6 +78,10 @@ module astr_gpu_mod
     integer(c_int) function astr_gpu_set_grid(x) bind(c,name='astr_gpu_set_grid')
       import :: c_int, c_double
       real(c_double), intent(in) :: x(*)
+    end function
+    integer(c_int) function astr_gpu_set_inflow(vel_in,tmp_in,tmp_prof) bind(c,name='astr_gpu_set_inflow')
+      import :: c_int, c_double
+      real(c_double), intent(in) :: vel_in(*),tmp_in(*),tmp_prof(*)
     end function
     integer(c_int) function astr_gpu_upload_state(q,rho,vel,prs,tmp) bind(c,name='astr_gpu_upload_state')
       import :: c_int, c_double
@@ -174,13 +179,14 @@ module astr_gpu_mod
                            nbr,mpirank,lfilter,diffterm,alfa_filter,reynolds,mach, &
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
                            device,flowtype,conschm,difschm,bctype,twall, &
-                           recon_schem,lchardecomp,bfacmpld,shkcrt)
+                           recon_schem,lchardecomp,bfacmpld,shkcrt,pinf)
     character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
     character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
     integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
     integer, intent(in) :: recon_schem              ! commvar recon_schem
     logical, intent(in) :: lchardecomp              ! commvar lchardecomp
     real(8), intent(in) :: bfacmpld,shkcrt          ! commvar bfacmpld, shkcrt
+    real(8), intent(in) :: pinf                     ! commvar pinf
     real(8), intent(in) :: twall(6)                 ! commvar twall(1:6)
     integer, intent(in) :: im,jm,km,ia,ja,ka,npdci,npdcj,npdck,is,ie,js,je,ks,ke
     logical, intent(in) :: lihomo,ljhomo,lkhomo,lfilter,diffterm
@@ -205,7 +211,7 @@ module astr_gpu_mod
     cfg%nondimen=1; cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall
     cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
-    cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt
+    cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt; cfg%pinf=pinf
     cfg%alfa_filter=alfa_filter
     cfg%reynolds=reynolds; cfg%mach=mach; cfg%prandtl=prandtl; cfg%gamma=gamma; cfg%ref_tem=ref_tem
     cfg%const1=const(1); cfg%const2=const(2); cfg%const3=const(3); cfg%const4=const(4)

@@ -64,14 +64,17 @@ typedef struct astr_cfg {
   int recon_schem;            /* input-file `recon_schem` (unused by conschm '543c')     */
   int lchardecomp;            /* characteristic decomposition + Ducros sensor on/off     */
   int bctype[6];              /* bctype(1:6) of the input file: imin,imax,jmin,jmax,kmin,
-                                 kmax; 1 periodic/none, 41 isothermal no-slip wall
-                                 (src/bc.F90:327-407 boucon)                             */
+                                 kmax (src/bc.F90:327-407 boucon).  On the device:
+                                 1 periodic/none; 41 isothermal wall (any face);
+                                 11 inflow (imin); 21 outflow (imax, jmax); 51 farfield
+                                 (jmax) -- the faces the reference's own routines treat   */
   double alfa_filter;         /* 0.49 in every example                                   */
   double reynolds, mach, prandtl, gamma, ref_tem;
   double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */
   double tempconst, tempconst1; /* Sutherland: 110.3/ref_tem (src/solver.F90:122)        */
   double deltat;
   double twall[6];            /* wall temperature of the bctype-41 faces (twall(1:6))    */
+  double pinf;                /* free-stream pressure roinf*tinf/const2 (solver.F90:120) */
   double bfacmpld;            /* blending factor of the compact upwind scheme (flux.F90) */
   double shkcrt;              /* shock-sensor threshold of ducrossensor (commcal.F90)    */
 } astr_cfg;
@@ -122,8 +125,11 @@ int astr_gpu_device_ptr(int field_id, void** dptr, long long strides[3], long lo
 
 /* ---- stage operators, one per reference subroutine ---------------------------------- */
 int astr_gpu_filterq(void);      /* src/comsolver.F90:514  filterq                      */
-int astr_gpu_boucon(void);       /* src/bc.F90:327         boucon (bctype 41 -> noslip
-                                    src/bc.F90:6306; other types: not on the device)    */
+int astr_gpu_boucon(void);       /* src/bc.F90:327         boucon: noslip :6306, inflow
+                                    :1366, outflow :3404, farfield :3008                */
+/* inflow data of alloinflow (src/bc.F90:69-83): vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km),
+ * tmp_prof(0:jm); call again whenever inflowintp / inflowintx refresh them (rkstep 1) */
+int astr_gpu_set_inflow(const double* vel_in, const double* tmp_in, const double* tmp_prof);
 int astr_gpu_qswap(void);        /* src/parallel.F90:4848  qswap                        */
 int astr_gpu_gradcal(void);      /* src/comsolver.F90:244  gradcal                      */
 int astr_gpu_rhscal(void);       /* src/solver.F90:185     rhscal (zeroes qrhs first,

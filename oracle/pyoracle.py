@@ -91,6 +91,9 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_flags.argtypes = [vp, ci, ci]
         L.oracle_case_set_bc.argtypes = [vp, vp, vp]
         L.oracle_case_set_flow.argtypes = [vp, ci, vp]
+        L.oracle_case_set_inflow.argtypes = [vp, ci, vp, vp, vp]
+        L.oracle_case_pinf.argtypes = [vp]
+        L.oracle_case_pinf.restype = cd
         L.oracle_case_set_scheme.argtypes = [vp, ci]
         L.oracle_case_set_upwind.argtypes = [vp, ci, ci, cd, cd]
         L.oracle_case_ducrossensor.argtypes = [vp]
@@ -278,6 +281,15 @@ class Case:
 
     def convrsdcmp(self) -> int:
         return lib().oracle_case_convrsdcmp(self._h)
+
+    def set_inflow(self, vel_in, tmp_in, tmp_prof, ib: int = 0):
+        """inflow(1) data (src/bc.F90:69-83): vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km), tmp_prof(0:jm)."""
+        a = [np.asfortranarray(v, dtype=np.float64) for v in (vel_in, tmp_in, tmp_prof)]
+        lib().oracle_case_set_inflow(self._h, ib, *[v.ctypes.data for v in a])
+
+    @property
+    def pinf(self) -> float:
+        return lib().oracle_case_pinf(self._h)
 
     def set_scheme(self, explicit: bool):
         lib().oracle_case_set_scheme(self._h, int(explicit))

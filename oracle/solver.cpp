@@ -53,6 +53,10 @@ struct Case {
   double bfacmpld = 0.3, shkcrt = 0.01;
   int bctype[6] = {1, 1, 1, 1, 1, 1};      // src/readwrite.F90 bctype(1:6): imin,imax,jmin,jmax,kmin,kmax
   double twall[6] = {0, 0, 0, 0, 0, 0};
+  double pinf = 0.0;                       // src/solver.F90:120 pinf=roinf*tinf/const2 (set in create)
+  // inflow(1) data of the blocks with irk==0 (bc.F90 alloinflow :69-83): vel_in(0:jm,0:km,3),
+  // tmp_in(0:jm,0:km), tmp_prof(0:jm); indexed [block]
+  std::vector<std::vector<double>> vel_in, tmp_in, tmp_prof;
   std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
   double xmax = 0.0;
 };
@@ -737,12 +741,137 @@ static void noslip(Case& c, int ndir, double tw) {
   }
 }
 
-// src/bc.F90:327-407 boucon: faces in the order n=1..6; only the bctypes implemented so far
+// src/commfunc.F90:277-285 extrapolate_2o with dv=0
+static inline double extrapolate2(double v1, double v2) { return num1d3 * (4.0 * v1 - v2 - 2.0 * 0.0); }
+
+// fvar2q_sca (src/fludyna.F90:312-376), nondimen: energy from temperature or from pressure
+static inline void fvar2q_T(const Thermo& th, Block& b, int i, int j, int k) {
+  const double r = b.rho(i, j, k), u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+  b.q[0](i, j, k) = r; b.q[1](i, j, k) = r * u; b.q[2](i, j, k) = r * v; b.q[3](i, j, k) = r * w;
+  const double var1 = 0.5 * (u * u + v * v + w * w);
+  b.q[4](i, j, k) = r * (b.tmp(i, j, k) * th.const1 + var1);
+}
+static inline void fvar2q_P(const Thermo& th, Block& b, int i, int j, int k) {
+  const double r = b.rho(i, j, k), u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+  b.q[0](i, j, k) = r; b.q[1](i, j, k) = r * u; b.q[2](i, j, k) = r * v; b.q[3](i, j, k) = r * w;
+  const double var1 = 0.5 * (u * u + v * v + w * w);
+  b.q[4](i, j, k) = b.prs(i, j, k) * th.const6 + r * var1;
+}
+
+// src/bc.F90:1366-1562 inflow(ndir): only ndir==1 exists in the reference (face i=0 of irk==0).
+// vel_in / tmp_in / tmp_prof are what profileinflow / freestreaminflow (+ inflowintp at rkstep 1) leave.
+static int inflow(Case& c, int ndir) {
+  if (ndir != 1) return 0;
+  for (size_t ib = 0; ib < c.blk.size(); ++ib) {
+    Block& b = c.blk[ib];
+    if (b.rk[0] != 0) continue;
+    if (c.vel_in.size() <= ib || c.vel_in[ib].empty()) return -1;
+    const int i = 0, nj = b.jm + 1, nk = b.km + 1;
+    const std::vector<double>& vin = c.vel_in[ib];
+    auto VIN = [&](int j, int k, int m) { return vin[(size_t)j + (size_t)nj * ((size_t)k + (size_t)nk * m)]; };
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j) {
+        const double rho_ref = b.rho(i + 1, j, k);
+        const double css = std::sqrt(c.tmp_prof[ib][j]) / c.th.mach;       // sos(tmp_prof(j)) fludyna.F90:851
+        b.vel[1](i, j, k) = VIN(j, k, 1);
+        b.vel[2](i, j, k) = VIN(j, k, 2);
+        b.tmp(i, j, k) = c.tmp_in[ib][(size_t)j + (size_t)nj * k];
+        const double pe = extrapolate2(b.prs(i + 1, j, k), b.prs(i + 2, j, k));
+        const double ue = extrapolate2(b.vel[0](i + 1, j, k), b.vel[0](i + 2, j, k));
+        const double pwave_in = c.pinf;
+        const double malo = VIN(j, k, 0) / css;
+        const double blend = 0.5 * (std::tanh((malo - 1.0) * 6.0) + 1.0);
+        b.prs(i, j, k) = (0.5 * (pwave_in + pe) + 0.5 * rho_ref * css * (VIN(j, k, 0) - ue)) * (1.0 - blend) + pwave_in * blend;
+        b.vel[0](i, j, k) = VIN(j, k, 0) + (c.pinf - b.prs(i, j, k)) / rho_ref / css;
+        b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;    // thermal(pressure,temperature)
+        fvar2q_T(c.th, b, i, j, k);
+      }
+  }
+  return 0;
+}
+
+// src/bc.F90:3404-3617 outflow(ndir): the reference has ndir==2 (first-order copy) and ndir==4
+// (extrapolation, subsonic branch relaxes the pressure towards pinf)
+static int outflow(Case& c, int ndir) {
+  for (Block& b : c.blk) {
+    if (ndir == 2 && b.rk[0] == c.size[0] - 1) {
+      const int i = b.im;
+      for (int k = 0; k <= b.km; ++k)
+        for (int j = 0; j <= b.jm; ++j) {
+          for (int m = 0; m < 3; ++m) b.vel[m](i, j, k) = b.vel[m](i - 1, j, k);
+          b.prs(i, j, k) = b.prs(i - 1, j, k);
+          b.tmp(i, j, k) = b.tmp(i - 1, j, k);
+          b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;
+          fvar2q_T(c.th, b, i, j, k);
+        }
+    } else if (ndir == 4 && b.rk[1] == c.size[1] - 1) {
+      const int j = b.jm;
+      const double alpha = 0.25;
+      for (int k = 0; k <= b.km; ++k)
+        for (int i = 0; i <= b.im; ++i) {
+          const double css = std::sqrt(b.tmp(i, j, k)) / c.th.mach;
+          const double ub = b.vel[1](i, j, k);
+          const double ue = extrapolate2(b.vel[0](i, j - 1, k), b.vel[0](i, j - 2, k));
+          const double ve = extrapolate2(b.vel[1](i, j - 1, k), b.vel[1](i, j - 2, k));
+          const double we = extrapolate2(b.vel[2](i, j - 1, k), b.vel[2](i, j - 2, k));
+          const double pe = extrapolate2(b.prs(i, j - 1, k), b.prs(i, j - 2, k));
+          const double te = extrapolate2(b.tmp(i, j - 1, k), b.tmp(i, j - 2, k));
+          const double roe = extrapolate2(b.rho(i, j - 1, k), b.rho(i, j - 2, k));
+          if (ub >= css) {
+            b.prs(i, j, k) = pe;
+            b.rho(i, j, k) = roe;
+          } else {
+            const double pwave_in = (b.prs(i, j, k) + alpha * c.deltat * c.pinf + b.rho(i, j, k) * css * (ve - b.vel[1](i, j, k))) /
+                                    (1.0 + alpha * c.deltat);
+            b.prs(i, j, k) = pwave_in;
+            b.tmp(i, j, k) = te;
+            b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;
+          }
+          b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ve; b.vel[2](i, j, k) = we;
+          b.tmp(i, j, k) = b.prs(i, j, k) / b.rho(i, j, k) * c.th.const2;   // nondimen branch :3596
+          fvar2q_P(c.th, b, i, j, k);
+        }
+    } else if (ndir != 2 && ndir != 4) {
+      return -1;
+    }
+  }
+  return 0;
+}
+
+// src/bc.F90:3008-3392 farfield(ndir): restated for ndir==4 (the face the HBL / SWLBI inputs use): plain
+// second-order extrapolation of the primitives
+static int farfield(Case& c, int ndir) {
+  if (ndir != 4) return -1;
+  for (Block& b : c.blk) {
+    if (b.rk[1] != c.size[1] - 1) continue;
+    const int j = b.jm;
+    for (int k = 0; k <= b.km; ++k)
+      for (int i = 0; i <= b.im; ++i) {
+        const double ue = extrapolate2(b.vel[0](i, j - 1, k), b.vel[0](i, j - 2, k));
+        const double ve = extrapolate2(b.vel[1](i, j - 1, k), b.vel[1](i, j - 2, k));
+        const double we = extrapolate2(b.vel[2](i, j - 1, k), b.vel[2](i, j - 2, k));
+        const double pe = extrapolate2(b.prs(i, j - 1, k), b.prs(i, j - 2, k));
+        const double roe = extrapolate2(b.rho(i, j - 1, k), b.rho(i, j - 2, k));
+        b.prs(i, j, k) = pe; b.rho(i, j, k) = roe;
+        b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ve; b.vel[2](i, j, k) = we;
+        b.tmp(i, j, k) = b.prs(i, j, k) / b.rho(i, j, k) * c.th.const2;
+        fvar2q_T(c.th, b, i, j, k);
+      }
+  }
+  return 0;
+}
+
+// src/bc.F90:327-407 boucon: faces in the order n=1..6; only the bctypes restated so far
 static int boucon(Case& c) {
   for (int n = 1; n <= 6; ++n) {
     const int bt = c.bctype[n - 1];
+    int rc = 0;
     if (bt == 41) noslip(c, n, c.twall[n - 1]);
-    else if (bt != 1) return -1;
+    else if (bt == 51) rc = farfield(c, n);
+    else if (bt == 11) rc = inflow(c, n);
+    else if (bt == 21) rc = outflow(c, n);
+    else if (bt != 1) rc = -1;
+    if (rc) return rc;
   }
   return 0;
 }
@@ -880,6 +1009,7 @@ void* oracle_case_create(int ia, int ja, int ka, int isize, int jsize, int ksize
   c->alfa_filter = alfa_filter; c->deltat = deltat;
   c->th.reynolds = reynolds; c->th.mach = mach; c->th.ref_tem = 273.15;
   c->th.refcal(sutherland_s);
+  c->pinf = 1.0 * 1.0 / c->th.const2;   // roinf*tinf/const2, roinf=tinf=1 (src/solver.F90:113-120)
   decompose(*c);
   filter_coefficient_cal(c->fc, alfa_filter, 1.11, 0.98);  // comsolver.F90:121
   for (Block& b : c->blk) {
@@ -975,6 +1105,17 @@ void oracle_case_set_bc(void* h, const int* bctype, const double* twall) {
   Case* c = static_cast<Case*>(h);
   for (int n = 0; n < 6; ++n) { c->bctype[n] = bctype[n]; c->twall[n] = twall[n]; }
 }
+// inflow data of block ib: vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km), tmp_prof(0:jm) (Fortran order)
+void oracle_case_set_inflow(void* h, int ib, const double* vel_in, const double* tmp_in, const double* tmp_prof) {
+  Case* c = static_cast<Case*>(h);
+  const Block& b = c->blk[ib];
+  const size_t nf = (size_t)(b.jm + 1) * (b.km + 1);
+  c->vel_in.resize(c->blk.size()); c->tmp_in.resize(c->blk.size()); c->tmp_prof.resize(c->blk.size());
+  c->vel_in[ib].assign(vel_in, vel_in + 3 * nf);
+  c->tmp_in[ib].assign(tmp_in, tmp_in + nf);
+  c->tmp_prof[ib].assign(tmp_prof, tmp_prof + b.jm + 1);
+}
+double oracle_case_pinf(void* h) { return static_cast<Case*>(h)->pinf; }
 void oracle_case_set_flow(void* h, int flowtype, const double* force) {
   Case* c = static_cast<Case*>(h);
   c->flowtype = flowtype;

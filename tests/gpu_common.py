@@ -104,7 +104,7 @@ def auto_shkcrt(c, bfacmpld=0.3, quantile=0.7):
 
 
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
-              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None):
+              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
@@ -119,6 +119,14 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         c.set_bc(bctype, twall)
         c.set_flow(1, force)
         c.set_x(channel_x(n, lengths))
+    if open_faces:
+        # the boundary set of the HBL / SWLBI inputs: inflow (imin), outflow (imax), isothermal wall (jmin),
+        # farfield (jmax) -- examples/Hypersonic_Boundary_Layer/datin/input.M3
+        assert tuple(homo) == (False, False, True)
+        bctype, twall = (11, 21, 41, 21 if open_faces == "outflow_top" else 51, 1, 1), (0, 0, 1.05, 0, 0, 0)
+        c.set_bc(bctype, twall)
+    if channel:
+        pass
     elif stretch == "skew":
         c.set_x(skewed_x(n, homo))
     elif stretch:
@@ -149,6 +157,22 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
     eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0,
                     flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw)
     eng.set_force(force)
+    if open_faces:
+        # synthetic inflow data: half of the profile supersonic (blend -> 1), half subsonic (blend -> 0)
+        jm, km = n[1], n[2]
+        yy = np.arange(jm + 1) / jm
+        vel_in = np.zeros((jm + 1, km + 1, 3), order="F")
+        vel_in[:, :, 0] = (1.0 + 14.0 * (yy > 0.5))[:, None] * (1.0 + 0.01 * np.cos(np.arange(km + 1)))[None, :]
+        vel_in[:, :, 1] = 0.02 * np.sin(3 * yy)[:, None]
+        vel_in[:, :, 2] = 0.01
+        tmp_in = np.asfortranarray(1.0 + 0.05 * yy[:, None] * np.ones((1, km + 1)))
+        tmp_prof = 1.0 + 0.05 * yy
+        c.set_inflow(vel_in, tmp_in, tmp_prof)
+        eng.set_inflow(vel_in, tmp_in, tmp_prof)
+        # make part of the jmax face supersonic outwards so that outflow(4)/farfield see both branches
+        v = c.get("v")
+        v[HM + n[0] // 2:, HM + n[1], :] = 12.0
+        c.set("v", v)
     x = eng.empty(3)
     for d in range(3):
         x[..., d] = c.get(f"x{d + 1}")

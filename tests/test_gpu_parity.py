@@ -82,6 +82,21 @@ def test_boucon(pair):
     assert_fields_close(c, eng, QS + PRIMS, OP_TOL, what="boucon")
 
 
+@pytest.mark.parametrize("n,top", [((36, 32, 24), True), ((40, 36, 0), True), ((36, 32, 20), "outflow_top")])
+def test_boucon_open_faces(oracle, n, top):
+    # inflow (imin) / outflow (imax or jmax) / wall (jmin) / farfield (jmax): bc.F90:1366, :3404, :6306, :3008
+    c, eng = make_pair(oracle, n=n, homo=(False, False, True), stretch=True, open_faces=top)
+    c.boucon(); eng.boucon()
+    assert_fields_close(c, eng, QS + PRIMS, OP_TOL, region=whole, what="boucon open faces")
+    # both branches of the characteristic switches were taken
+    u_in = core(c.get("u"))[0, :, :]
+    assert u_in.max() > 10.0 and u_in.min() < 2.0
+    c.rk_stage(1); eng.rk_stage(1)
+    assert np.isfinite(core(c.get("q5"))).all()
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="rk stage with open faces")
+    eng.close(); c.close()
+
+
 def test_qswap(pair):
     c, eng = pair
     c.qswap(); eng.qswap()

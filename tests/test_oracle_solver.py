@@ -154,3 +154,41 @@ def test_explicit_scheme_is_sixth_order_on_the_rhs(oracle):
     err = np.abs(ra - rb).max() / np.abs(ra).max()
     assert 0.0 < err < 1e-4
     a.close(); b.close()
+
+
+def test_open_face_boundary_conditions(oracle):
+    # inflow(1) bc.F90:1366, outflow(2) :3404, farfield(4) :3008 on a block with walls in i and j
+    sys_path_tests()
+    from gpu_common import stretched_x
+    n, homo = (24, 20, 12), (False, False, True)
+    c = oracle.Case(*n, homo=homo)
+    c.set_bc((11, 21, 41, 51, 1, 1), (0, 0, 1.05, 0, 0, 0))
+    c.set_x(stretched_x(n, homo)); c.gridgeom(); c.tgvini()
+    jm, km = n[1], n[2]
+    vel_in = np.zeros((jm + 1, km + 1, 3), order="F")
+    vel_in[:, :, 0] = 40.0                     # Mach 4 against css = sqrt(T)/M = 10: blend -> 1
+    tmp_in = np.ones((jm + 1, km + 1), order="F")
+    c.set_inflow(vel_in, tmp_in, np.ones(jm + 1))
+    # a linear-in-j profile: extrapolate(v1,v2,dv=0) is the one-sided zero-gradient closure (4 v1 - v2)/3
+    for name, slope in (("u", 0.01), ("prs", 0.2), ("rho", 0.003)):
+        a = c.get(name)
+        a[...] = (2.0 if name != "prs" else 70.0) + slope * np.arange(a.shape[1])[None, :, None]
+        c.set(name, a)
+    before = {k: c.get(k) for k in ("u", "prs", "rho", "tmp")}
+    c.boucon()
+    u, p, r = c.get("u"), c.get("prs"), c.get("rho")
+    # farfield at jmax (away from the i faces, which outflow / inflow own afterwards... boucon order is n=1..6)
+    jt = 5 + jm
+    for name, a in (("u", u), ("prs", p), ("rho", r)):
+        want = (4.0 * before[name][8:-8, jt - 1, 5:-5] - before[name][8:-8, jt - 2, 5:-5]) / 3.0
+        np.testing.assert_allclose(a[8:-8, jt, 5:-5], want, rtol=1e-14)
+    # supersonic inflow: p = pinf, u = vel_in
+    np.testing.assert_allclose(p[5, 6:-6, 5:-5], c.pinf, rtol=1e-9)
+    np.testing.assert_allclose(u[5, 6:-6, 5:-5], 40.0, rtol=1e-9)
+    # outflow at imax: first-order copy of the neighbour plane
+    np.testing.assert_array_equal(p[-6, 6:-6, 5:-5], p[-7, 6:-6, 5:-5])
+    # conserved variables consistent with the primitives on the treated faces
+    q1 = c.get("q1")
+    np.testing.assert_array_equal(q1[5, 6:-6, 5:-5], r[5, 6:-6, 5:-5])
+    np.testing.assert_array_equal(q1[8:-8, jt, 5:-5], r[8:-8, jt, 5:-5])
+    c.close()
