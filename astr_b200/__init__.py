@@ -9,8 +9,8 @@ GPU is missing.
 """
 from .lib import AstrCfg, AstrGpuError, build, load, lib_path, FIELD_IDS, HM  # noqa: F401
 from .parallel import Block, HaloMessage, decompose, halo_plan, mpisizedis  # noqa: F401
-from .solver import RhsEngine, refcal  # noqa: F401
+from .solver import RhsEngine, refcal, refcal_dimensional  # noqa: F401
 from . import cases  # noqa: F401
 
 __all__ = ["AstrCfg", "AstrGpuError", "build", "load", "lib_path", "FIELD_IDS", "HM", "Block", "decompose",
-           "mpisizedis", "RhsEngine", "refcal", "cases"]
+           "mpisizedis", "RhsEngine", "refcal", "refcal_dimensional", "cases"]

@@ -518,7 +518,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
           (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n == 3)))
       return astr_fail_msg("bctype on the device: 1 (periodic), 41 (isothermal wall, any face), 11 (inflow, imin), "
                            "21 (outflow, imax or jmax), 51 (farfield, jmax)");
-  if (!cfg->nondimen) return astr_fail_msg("only nondimen=t is implemented");
+
   // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
   if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
     return astr_fail_msg("difschm must be 643c (compact_central) or 6xxe (explicit_central)");
@@ -546,6 +546,10 @@ int astr_gpu_init(const astr_cfg* cfg) {
   g->th.const2 = cfg->const2; g->th.const5 = cfg->const5; g->th.const6 = cfg->const6;
   g->th.tempconst = cfg->tempconst; g->th.tempconst1 = cfg->tempconst1;
   g->th.gamma = cfg->gamma; g->th.mach = cfg->mach;
+  g->th.nondimen = cfg->nondimen ? 1 : 0;                     // src/solver.F90:124-128
+  g->th.rgas = 287.1;
+  g->th.cp = cfg->gamma / (cfg->gamma - 1.0) * g->th.rgas;
+  g->th.cv = g->th.rgas / (cfg->gamma - 1.0);
   CUDA_OK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->pool, bytes));

@@ -110,7 +110,7 @@ __device__ __forceinline__ void q2fvar_node(double* __restrict__ pool, const lon
   pool[(S_VEL + 1) * fs + x] = v;
   pool[(S_VEL + 2) * fs + x] = w;
   pool[S_PRS * fs + x] = p;
-  pool[S_TMP * fs + x] = p / r * th.const2;
+  pool[S_TMP * fs + x] = th.T_of(p, r);
 }
 
 __global__ void k_q2fvar(const Layout L, double* __restrict__ pool, const Thermo th, const Box b) {
@@ -172,7 +172,7 @@ __device__ __forceinline__ void visc_node(const double* __restrict__ pool, const
   Grad g;
   load_grad(pool, fs, x, g);
   const double t = pool[S_TMP * fs + x];
-  const double miu = (t * sqrt(t) * th.tempconst1 / (t + th.tempconst)) / th.reynolds;
+  const double miu = th.miu(t);
   const double s11 = g.dv[0][0];
   const double s12 = 0.5 * (g.dv[0][1] + g.dv[1][0]);
   const double s13 = 0.5 * (g.dv[0][2] + g.dv[2][0]);
@@ -181,7 +181,7 @@ __device__ __forceinline__ void visc_node(const double* __restrict__ pool, const
   const double s33 = g.dv[2][2];
   const double skk = (1.0 / 3.0) * (s11 + s22 + s33);
   const double miu2 = 2.0 * miu;
-  const double hcc = (miu / th.prandtl) / th.const5;
+  const double hcc = th.hcc(miu);
   sg[0] = miu2 * (s11 - skk);
   sg[1] = miu2 * s12;
   sg[2] = miu2 * s13;
@@ -450,14 +450,15 @@ __global__ void k_noslip(const Layout L, double* __restrict__ pool, const Thermo
   const long long x = (DIR == 0) ? L.idx(l, a, b) : (DIR == 1 ? L.idx(a, l, b) : L.idx(a, b, l));
   const long long fs = L.fstride;
   const double pe = (1.0 / 3.0) * (4.0 * pool[S_PRS * fs + x + sg] - pool[S_PRS * fs + x + 2 * sg]);
-  const double rho = pe / tw * th.const2;
+  const double rho = th.rho_of(pe, tw);
   pool[(S_VEL + 0) * fs + x] = 0.0; pool[(S_VEL + 1) * fs + x] = 0.0; pool[(S_VEL + 2) * fs + x] = 0.0;
   pool[S_PRS * fs + x] = pe;
   pool[S_TMP * fs + x] = tw;
   pool[S_RHO * fs + x] = rho;
   pool[(S_Q + 0) * fs + x] = rho;
   pool[(S_Q + 1) * fs + x] = 0.0; pool[(S_Q + 2) * fs + x] = 0.0; pool[(S_Q + 3) * fs + x] = 0.0;
-  pool[(S_Q + 4) * fs + x] = pe * th.const6;
+  // fvar2q with pressure (nondimen) or temperature (dimensional), bc.F90:6331-6348; velocity is zero
+  pool[(S_Q + 4) * fs + x] = th.nondimen ? pe * th.const6 : rho * (tw * th.cotem());
 }
 
 // src_chan body force (src/solver.F90:341-352): qrhs(2:4)+=force*jacob,
@@ -572,7 +573,7 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
     const double vin0 = a.vel_in[j + (long long)nj * k], vin1 = a.vel_in[j + (long long)nj * (k + (long long)nk)],
                  vin2 = a.vel_in[j + (long long)nj * (k + 2LL * nk)];
     const double rho_ref = rho[x + sg];
-    const double css = sqrt(a.tmp_prof[j]) / th.mach;
+    const double css = th.sos(a.tmp_prof[j]);
     v1[x] = vin1; v2[x] = vin2;
     tmp[x] = a.tmp_in[j + (long long)nj * k];
     const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]);
@@ -582,11 +583,11 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
     const double p = (0.5 * (a.pinf + pe) + 0.5 * rho_ref * css * (vin0 - ue)) * (1.0 - blend) + a.pinf * blend;
     prs[x] = p;
     v0[x] = vin0 + (a.pinf - p) / rho_ref / css;
-    rho[x] = p / tmp[x] * th.const2;
+    rho[x] = th.rho_of(p, tmp[x]);
   } else if (a.kind == 21 && DIR == 0) {   // outflow at imax: first-order copy
     v0[x] = v0[x + sg]; v1[x] = v1[x + sg]; v2[x] = v2[x + sg];
     prs[x] = prs[x + sg]; tmp[x] = tmp[x + sg];
-    rho[x] = prs[x] / tmp[x] * th.const2;
+    rho[x] = th.rho_of(prs[x], tmp[x]);
   } else {                  // outflow at jmax (21) / farfield at jmax (51): second-order extrapolation
     const double ue = extrap2(v0[x + sg], v0[x + 2 * sg]), ve = extrap2(v1[x + sg], v1[x + 2 * sg]),
                  we = extrap2(v2[x + sg], v2[x + 2 * sg]);
@@ -594,7 +595,7 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
     if (a.kind == 51) {
       prs[x] = pe; rho[x] = roe;
     } else {
-      const double css = sqrt(tmp[x]) / th.mach;
+      const double css = th.sos(tmp[x]);
       const double ub = v1[x];
       if (ub >= css) { prs[x] = pe; rho[x] = roe; }
       else {
@@ -602,18 +603,20 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
         const double alpha = 0.25;
         const double p = (prs[x] + alpha * a.deltat * a.pinf + rho[x] * css * (ve - v1[x])) / (1.0 + alpha * a.deltat);
         prs[x] = p;
-        rho[x] = p / te * th.const2;
+        tmp[x] = te;
+        rho[x] = th.rho_of(p, te);
       }
-      from_T = false;
+      from_T = !th.nondimen;          // bc.F90:3596-3605
     }
     v0[x] = ue; v1[x] = ve; v2[x] = we;
-    tmp[x] = prs[x] / rho[x] * th.const2;
+    if (a.kind == 51 || th.nondimen) tmp[x] = th.T_of(prs[x], rho[x]);
+    else rho[x] = th.rho_of(prs[x], tmp[x]);      // dimensional outflow: density from p and the (old or extrapolated) T
   }
   const double r = rho[x], u = v0[x], v = v1[x], w = v2[x];
   pool[(S_Q + 0) * fs + x] = r; pool[(S_Q + 1) * fs + x] = r * u; pool[(S_Q + 2) * fs + x] = r * v;
   pool[(S_Q + 3) * fs + x] = r * w;
   const double var1 = 0.5 * (u * u + v * v + w * w);
-  pool[(S_Q + 4) * fs + x] = from_T ? r * (tmp[x] * th.const1 + var1) : prs[x] * th.const6 + r * var1;
+  pool[(S_Q + 4) * fs + x] = from_T ? r * (tmp[x] * th.cotem() + var1) : prs[x] * th.const6 + r * var1;
 }
 
 // ---------------------------------------------------------------------------------

@@ -25,6 +25,22 @@ enum Slot {
 struct Thermo {
   double reynolds, prandtl, const1, const2, const5, const6, tempconst, tempconst1;
   double gamma, mach;
+  int nondimen;             // 0: SI units, rgas = 287.1 (src/solver.F90:124-148)
+  double rgas, cp, cv;
+#ifdef __CUDACC__
+  // thermal_scar (src/fludyna.F90:45-88)
+  __device__ __forceinline__ double T_of(double p, double rho) const { return nondimen ? p / rho * const2 : p / rho / rgas; }
+  __device__ __forceinline__ double rho_of(double p, double t) const { return nondimen ? p / t * const2 : p / t / rgas; }
+  __device__ __forceinline__ double cotem() const { return nondimen ? const1 : cv; }           // fvar2q, fludyna.F90:344-348
+  __device__ __forceinline__ double sos(double t) const { return nondimen ? sqrt(t) / mach : sqrt(gamma * rgas * t); }  // :832-859
+  // miucal (src/fludyna.F90:791-817) as diffrsdcal6 uses it (src/solver.F90:2456-2460)
+  __device__ __forceinline__ double miu(double t) const {
+    if (nondimen) return (t * sqrt(t) * tempconst1 / (t + tempconst)) / reynolds;
+    const double tn = t / 273.15;
+    return 1.716e-5 * tn * sqrt(tn) * (273.15 + 110.4) / (t + 110.4);
+  }
+  __device__ __forceinline__ double hcc(double m) const { return nondimen ? (m / prandtl) / const5 : cp * m / prandtl; }  // :2519-2523
+#endif
 };
 
 struct Box { int lo[3], hi[3]; };   // inclusive node ranges

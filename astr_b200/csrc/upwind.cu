@@ -60,7 +60,7 @@ __global__ void k_sw_split(const Layout L, const double* __restrict__ pool, doub
   const double var0 = 1.0 / sqrt(d1 * d1 + d2 * d2 + d3 * d3);
   const double g1 = d1 * var0, g2 = d2 * var0, g3 = d3 * var0;
   const double gm2 = 0.5 / gamma;
-  const double css = sqrt(tmp) / th.mach;
+  const double css = th.sos(tmp);
   const double csa = css / var0;
   const double lmach = uu / csa;
   double fp[5], fm[5];

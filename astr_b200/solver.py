@@ -38,6 +38,23 @@ def refcal(reynolds: float, mach: float, ref_tem: float = 273.15, gamma: float =
     )
 
 
+def refcal_dimensional(ref_tem: float, ref_vel: float, ref_len: float, ref_den: float, gamma: float = 1.4,
+                       prandtl: float = 0.72) -> Dict[str, float]:
+    """nondimen=f branch of refcal (src/solver.F90:124-148): SI units, rgas=287.1; Mach and Reynolds follow
+    from the reference state with sos (src/fludyna.F90:853) and the dimensional miucal (:809-811)."""
+    rgas = 287.1
+    cp = gamma / (gamma - 1.0) * rgas
+    cv = rgas / (gamma - 1.0)
+    pinf = ref_den * ref_tem * rgas
+    tn = ref_tem / 273.15
+    ref_miu = 1.716e-5 * tn * np.sqrt(tn) * (273.15 + 110.4) / (ref_tem + 110.4)
+    mach = ref_vel / np.sqrt(gamma * rgas * ref_tem)
+    reynolds = ref_den * ref_vel * ref_len / ref_miu
+    th = refcal(float(reynolds), float(mach), ref_tem=ref_tem, gamma=gamma, prandtl=prandtl)
+    th.update(nondimen=0, rgas=rgas, cp=cp, cv=cv, pinf=float(pinf))
+    return th
+
+
 class RhsEngine:
     """One block (= one MPI rank of the reference = one GPU) of the RHS / RK-stage engine."""
 
@@ -70,13 +87,15 @@ class RhsEngine:
         if conschm is not None:      # e.g. 543: upwind compact convection (convrsdcmp) over difschm
             c.conschm = int(conschm)
         c.recon_schem, c.lchardecomp, c.bfacmpld, c.shkcrt = int(recon_schem), int(lchardecomp), bfacmpld, shkcrt
-        c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), 1, flowtype
+        c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), int(thermo.get("nondimen", 1)), flowtype
         c.bctype[:] = [int(b) for b in bctype]
         c.twall[:] = [float(t) for t in twall]
         c.alfa_filter = alfa_filter
-        c.pinf = 1.0 / thermo["const2"]       # roinf*tinf/const2 with roinf=tinf=1 (src/solver.F90:113-120)
+        # roinf*tinf/const2 with roinf=tinf=1 (src/solver.F90:113-120), or thermal(tinf,roinf) for nondimen=f
+        c.pinf = thermo.get("pinf", 1.0 / thermo["const2"])
         for k, v in thermo.items():
-            setattr(c, k, v)
+            if k not in ("nondimen", "rgas", "cp", "cv", "pinf"):
+                setattr(c, k, v)
         c.deltat = deltat
         self.cfg = c
         _l.check(self._lib.astr_gpu_init(ctypes.byref(c)))

@@ -59,7 +59,9 @@ typedef struct astr_cfg {
   int rkscheme;               /* 3 = rk3 (TVD), src/mainloop.F90:350-362                 */
   int lfilter;                /* filterq enabled                                         */
   int diffterm;               /* viscous terms enabled                                   */
-  int nondimen;               /* must be 1                                               */
+  int nondimen;               /* 1 nondimensional; 0 SI units with rgas=287.1, cp, cv as
+                                 src/solver.F90:124-128 (mach, reynolds, const1..7, pinf
+                                 as refcal leaves them)                                  */
   int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (src_chan)   */
   int recon_schem;            /* input-file `recon_schem` (unused by conschm '543c')     */
   int lchardecomp;            /* characteristic decomposition + Ducros sensor on/off     */

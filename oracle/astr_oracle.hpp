@@ -79,11 +79,27 @@ struct Thermo {
   double gamma = 1.4, mach = 0.1, reynolds = 1600.0, prandtl = 0.72, ref_tem = 273.15;
   double const1, const2, const3, const4, const5, const6, const7;
   double tempconst, tempconst1;  // Sutherland
+  // nondimen=f (src/solver.F90:124-148): SI units, rgas=287.1, reference state ref_tem/ref_vel/ref_len/ref_den
+  bool nondimen = true;
+  double rgas = 287.1, cp = 0.0, cv = 0.0, ref_vel = 1.0, ref_len = 1.0, ref_den = 1.0;
+  double roinf = 1.0, tinf = 1.0, pinf = 0.0;
   // sutherland_s: 110.3 in src/solver.F90:122, 110.4 in miniapps/tgv_solver_3d/tgvsolver.F90:133
   void refcal(double sutherland_s);  // src/solver.F90:104-126
-  double miucal(double t) const {    // src/fludyna.F90:806-808
-    return t * std_sqrt(t) * tempconst1 / (t + tempconst);
+  void refcal_dimensional();         // src/solver.F90:124-148
+  double miucal(double t) const {    // src/fludyna.F90:791-817
+    if (nondimen) return t * std_sqrt(t) * tempconst1 / (t + tempconst);
+    const double tnondim = t / 273.15;
+    return 1.716e-5 * tnondim * std_sqrt(tnondim) * (273.15 + 110.4) / (t + 110.4);
   }
+  // viscosity as diffrsdcal6 uses it (src/solver.F90:2456-2460) and the conductivity factor (:2519-2523)
+  double miu_eff(double t) const { return nondimen ? miucal(t) / reynolds : miucal(t); }
+  double hcc(double miu) const { return nondimen ? (miu / prandtl) / const5 : cp * miu / prandtl; }
+  // thermal_scar (src/fludyna.F90:45-88)
+  double thermal_T(double p, double rho) const { return nondimen ? p / rho * const2 : p / rho / rgas; }
+  double thermal_rho(double p, double t) const { return nondimen ? p / t * const2 : p / t / rgas; }
+  double thermal_p(double rho, double t) const { return nondimen ? rho * t / const2 : rho * t * rgas; }
+  double cotem() const { return nondimen ? const1 : cv; }            // fvar2q, src/fludyna.F90:344-348
+  double sos(double t) const { return nondimen ? std_sqrt(t) / mach : std_sqrt(gamma * rgas * t); }  // :850-854
   static double std_sqrt(double v);
 };
 

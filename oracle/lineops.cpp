@@ -354,6 +354,29 @@ void Thermo::refcal(double sutherland_s) {
   const7 = (gamma - 1.0) * (mach * mach) * reynolds * prandtl;
   tempconst = sutherland_s / ref_tem;
   tempconst1 = 1.0 + tempconst;
+  nondimen = true;
+  roinf = 1.0; tinf = 1.0;
+  pinf = roinf * tinf / const2;
+}
+
+// src/solver.F90:124-148: ref_tem, ref_vel, ref_len, ref_den are inputs; Mach and Reynolds follow
+void Thermo::refcal_dimensional() {
+  nondimen = false;
+  rgas = 287.1;
+  cp = gamma / (gamma - 1.0) * rgas;
+  cv = rgas / (gamma - 1.0);
+  tinf = ref_tem; roinf = ref_den;
+  pinf = thermal_p(roinf, tinf);
+  const double ref_miu = miucal(ref_tem);
+  mach = ref_vel / sos(ref_tem);
+  reynolds = ref_den * ref_vel * ref_len / ref_miu;
+  const1 = 1.0 / (gamma * (gamma - 1.0) * (mach * mach));
+  const2 = gamma * (mach * mach);
+  const3 = (gamma - 1.0) / 3.0 * prandtl * (mach * mach);
+  const4 = (gamma - 1.0) * (mach * mach) * reynolds * prandtl;
+  const5 = (gamma - 1.0) * (mach * mach);
+  const6 = 1.0 / (gamma - 1.0);
+  const7 = (gamma - 1.0) * (mach * mach) * reynolds * prandtl;
 }
 
 }  // namespace astr_oracle

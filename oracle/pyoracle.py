@@ -92,6 +92,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_bc.argtypes = [vp, vp, vp]
         L.oracle_case_set_flow.argtypes = [vp, ci, vp]
         L.oracle_case_set_inflow.argtypes = [vp, ci, vp, vp, vp]
+        L.oracle_case_set_dimensional.argtypes = [vp, cd, cd, cd, cd]
+        L.oracle_case_thermo.argtypes = [vp, vp]
         L.oracle_case_pinf.argtypes = [vp]
         L.oracle_case_pinf.restype = cd
         L.oracle_case_set_scheme.argtypes = [vp, ci]
@@ -286,6 +288,17 @@ class Case:
         """inflow(1) data (src/bc.F90:69-83): vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km), tmp_prof(0:jm)."""
         a = [np.asfortranarray(v, dtype=np.float64) for v in (vel_in, tmp_in, tmp_prof)]
         lib().oracle_case_set_inflow(self._h, ib, *[v.ctypes.data for v in a])
+
+    def set_dimensional(self, ref_tem: float, ref_vel: float, ref_len: float, ref_den: float):
+        """nondimen=f: SI units, rgas=287.1 (src/solver.F90:124-148)."""
+        lib().oracle_case_set_dimensional(self._h, ref_tem, ref_vel, ref_len, ref_den)
+
+    def thermo(self) -> dict:
+        out = (ctypes.c_double * 14)()
+        lib().oracle_case_thermo(self._h, out)
+        keys = ["reynolds", "mach", "const1", "const2", "const3", "const4", "const5", "const6", "const7", "rgas", "cp",
+                "cv", "pinf", "nondimen"]
+        return dict(zip(keys, list(out)))
 
     @property
     def pinf(self) -> float:

@@ -274,7 +274,7 @@ static inline void q2fvar_node(const Thermo& th, Block& b, int i, int j, int k) 
   b.vel[0](i, j, k) = u; b.vel[1](i, j, k) = v; b.vel[2](i, j, k) = w;
   const double p = (b.q[4](i, j, k) - 0.5 * r * (u * u + v * v + w * w)) / th.const6;
   b.prs(i, j, k) = p;
-  b.tmp(i, j, k) = p / r * th.const2;  // thermal_3d(pressure,density) fludyna.F90:146
+  b.tmp(i, j, k) = th.thermal_T(p, r);  // thermal_3d(pressure,density) fludyna.F90:136-179
 }
 
 // src/parallel.F90:4848-5318 qswap: per direction (i then j then k) halo copy,
@@ -599,7 +599,7 @@ static void diffrsdcal6(Case& c) {
     for (int k = 0; k <= b.km; ++k)
       for (int j = 0; j <= b.jm; ++j)
         for (int i = 0; i <= b.im; ++i) {
-          const double miu = th.miucal(b.tmp(i, j, k)) / th.reynolds;
+          const double miu = th.miu_eff(b.tmp(i, j, k));   // solver.F90:2456-2460
           auto dv = [&](int m, int n) { return b.dvel[m - 1][n - 1](i, j, k); };
           const double s11 = dv(1, 1);
           const double s12 = 0.5 * (dv(1, 2) + dv(2, 1));
@@ -612,7 +612,7 @@ static void diffrsdcal6(Case& c) {
           b.vor[1](i, j, k) = dv(1, 3) - dv(3, 1);
           b.vor[2](i, j, k) = dv(2, 1) - dv(1, 2);
           const double miu2 = 2.0 * miu;
-          const double hcc = (miu / th.prandtl) / th.const5;
+          const double hcc = th.hcc(miu);                  // solver.F90:2519-2523
           const double detk = 0.0, tau = 0.0;
           const double sg1 = miu2 * (s11 - skk) - detk + tau;
           const double sg2 = miu2 * s12 + tau;
@@ -729,14 +729,15 @@ static void noslip(Case& c, int ndir, double tw) {
         for (int m = 0; m < 3; ++m) at(b.vel[m], d, l, p1, p2) = 0.0;
         at(b.prs, d, l, p1, p2) = pe;
         at(b.tmp, d, l, p1, p2) = tw;
-        const double rho = pe / tw * c.th.const2;  // thermal(pressure,temperature) fludyna.F90:60
+        const double rho = c.th.thermal_rho(pe, tw);  // thermal(pressure,temperature) fludyna.F90:45-88
         at(b.rho, d, l, p1, p2) = rho;
         at(b.q[0], d, l, p1, p2) = rho;
         at(b.q[1], d, l, p1, p2) = rho * 0.0;
         at(b.q[2], d, l, p1, p2) = rho * 0.0;
         at(b.q[3], d, l, p1, p2) = rho * 0.0;
         const double var1 = 0.5 * (0.0 * 0.0 + 0.0 * 0.0 + 0.0 * 0.0);
-        at(b.q[4], d, l, p1, p2) = pe * c.th.const6 + rho * var1;
+        // fvar2q with pressure (nondimen) or with temperature (dimensional), bc.F90:6331-6348
+        at(b.q[4], d, l, p1, p2) = c.th.nondimen ? pe * c.th.const6 + rho * var1 : rho * (tw * c.th.cotem() + var1);
       }
   }
 }
@@ -749,7 +750,7 @@ static inline void fvar2q_T(const Thermo& th, Block& b, int i, int j, int k) {
   const double r = b.rho(i, j, k), u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
   b.q[0](i, j, k) = r; b.q[1](i, j, k) = r * u; b.q[2](i, j, k) = r * v; b.q[3](i, j, k) = r * w;
   const double var1 = 0.5 * (u * u + v * v + w * w);
-  b.q[4](i, j, k) = r * (b.tmp(i, j, k) * th.const1 + var1);
+  b.q[4](i, j, k) = r * (b.tmp(i, j, k) * th.cotem() + var1);
 }
 static inline void fvar2q_P(const Thermo& th, Block& b, int i, int j, int k) {
   const double r = b.rho(i, j, k), u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
@@ -772,7 +773,7 @@ static int inflow(Case& c, int ndir) {
     for (int k = 0; k <= b.km; ++k)
       for (int j = 0; j <= b.jm; ++j) {
         const double rho_ref = b.rho(i + 1, j, k);
-        const double css = std::sqrt(c.tmp_prof[ib][j]) / c.th.mach;       // sos(tmp_prof(j)) fludyna.F90:851
+        const double css = c.th.sos(c.tmp_prof[ib][j]);                    // sos(tmp_prof(j)) fludyna.F90:832-859
         b.vel[1](i, j, k) = VIN(j, k, 1);
         b.vel[2](i, j, k) = VIN(j, k, 2);
         b.tmp(i, j, k) = c.tmp_in[ib][(size_t)j + (size_t)nj * k];
@@ -783,7 +784,7 @@ static int inflow(Case& c, int ndir) {
         const double blend = 0.5 * (std::tanh((malo - 1.0) * 6.0) + 1.0);
         b.prs(i, j, k) = (0.5 * (pwave_in + pe) + 0.5 * rho_ref * css * (VIN(j, k, 0) - ue)) * (1.0 - blend) + pwave_in * blend;
         b.vel[0](i, j, k) = VIN(j, k, 0) + (c.pinf - b.prs(i, j, k)) / rho_ref / css;
-        b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;    // thermal(pressure,temperature)
+        b.rho(i, j, k) = c.th.thermal_rho(b.prs(i, j, k), b.tmp(i, j, k)); // thermal(pressure,temperature)
         fvar2q_T(c.th, b, i, j, k);
       }
   }
@@ -801,7 +802,7 @@ static int outflow(Case& c, int ndir) {
           for (int m = 0; m < 3; ++m) b.vel[m](i, j, k) = b.vel[m](i - 1, j, k);
           b.prs(i, j, k) = b.prs(i - 1, j, k);
           b.tmp(i, j, k) = b.tmp(i - 1, j, k);
-          b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;
+          b.rho(i, j, k) = c.th.thermal_rho(b.prs(i, j, k), b.tmp(i, j, k));
           fvar2q_T(c.th, b, i, j, k);
         }
     } else if (ndir == 4 && b.rk[1] == c.size[1] - 1) {
@@ -809,7 +810,7 @@ static int outflow(Case& c, int ndir) {
       const double alpha = 0.25;
       for (int k = 0; k <= b.km; ++k)
         for (int i = 0; i <= b.im; ++i) {
-          const double css = std::sqrt(b.tmp(i, j, k)) / c.th.mach;
+          const double css = c.th.sos(b.tmp(i, j, k));
           const double ub = b.vel[1](i, j, k);
           const double ue = extrapolate2(b.vel[0](i, j - 1, k), b.vel[0](i, j - 2, k));
           const double ve = extrapolate2(b.vel[1](i, j - 1, k), b.vel[1](i, j - 2, k));
@@ -825,11 +826,16 @@ static int outflow(Case& c, int ndir) {
                                     (1.0 + alpha * c.deltat);
             b.prs(i, j, k) = pwave_in;
             b.tmp(i, j, k) = te;
-            b.rho(i, j, k) = b.prs(i, j, k) / b.tmp(i, j, k) * c.th.const2;
+            b.rho(i, j, k) = c.th.thermal_rho(b.prs(i, j, k), b.tmp(i, j, k));
           }
           b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ve; b.vel[2](i, j, k) = we;
-          b.tmp(i, j, k) = b.prs(i, j, k) / b.rho(i, j, k) * c.th.const2;   // nondimen branch :3596
-          fvar2q_P(c.th, b, i, j, k);
+          if (c.th.nondimen) {        // :3596-3600
+            b.tmp(i, j, k) = c.th.thermal_T(b.prs(i, j, k), b.rho(i, j, k));
+            fvar2q_P(c.th, b, i, j, k);
+          } else {                    // :3601-3605
+            b.rho(i, j, k) = c.th.thermal_rho(b.prs(i, j, k), b.tmp(i, j, k));
+            fvar2q_T(c.th, b, i, j, k);
+          }
         }
     } else if (ndir != 2 && ndir != 4) {
       return -1;
@@ -854,7 +860,7 @@ static int farfield(Case& c, int ndir) {
         const double roe = extrapolate2(b.rho(i, j - 1, k), b.rho(i, j - 2, k));
         b.prs(i, j, k) = pe; b.rho(i, j, k) = roe;
         b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ve; b.vel[2](i, j, k) = we;
-        b.tmp(i, j, k) = b.prs(i, j, k) / b.rho(i, j, k) * c.th.const2;
+        b.tmp(i, j, k) = c.th.thermal_T(b.prs(i, j, k), b.rho(i, j, k));
         fvar2q_T(c.th, b, i, j, k);
       }
   }
@@ -1116,6 +1122,20 @@ void oracle_case_set_inflow(void* h, int ib, const double* vel_in, const double*
   c->tmp_prof[ib].assign(tmp_prof, tmp_prof + b.jm + 1);
 }
 double oracle_case_pinf(void* h) { return static_cast<Case*>(h)->pinf; }
+// nondimen=f (src/solver.F90:124-148): SI reference state; Mach, Reynolds, const1..7, pinf follow
+void oracle_case_set_dimensional(void* h, double ref_tem, double ref_vel, double ref_len, double ref_den) {
+  Case* c = static_cast<Case*>(h);
+  c->th.ref_tem = ref_tem; c->th.ref_vel = ref_vel; c->th.ref_len = ref_len; c->th.ref_den = ref_den;
+  c->th.refcal_dimensional();
+  c->pinf = c->th.pinf;
+}
+// out: reynolds, mach, const1..const7, rgas, cp, cv, pinf, nondimen
+void oracle_case_thermo(void* h, double* out) {
+  const Thermo& t = static_cast<Case*>(h)->th;
+  const double v[14] = {t.reynolds, t.mach, t.const1, t.const2, t.const3, t.const4, t.const5, t.const6, t.const7,
+                        t.rgas, t.cp, t.cv, static_cast<Case*>(h)->pinf, t.nondimen ? 1.0 : 0.0};
+  std::memcpy(out, v, sizeof v);
+}
 void oracle_case_set_flow(void* h, int flowtype, const double* force) {
   Case* c = static_cast<Case*>(h);
   c->flowtype = flowtype;

@@ -161,7 +161,7 @@ static void steger_warming_node(const Thermo& th, double rho, const double* vel,
   const double var0 = 1.0 / std::sqrt(dxi[0] * dxi[0] + dxi[1] * dxi[1] + dxi[2] * dxi[2]);
   const double gpd[3] = {dxi[0] * var0, dxi[1] * var0, dxi[2] * var0};
   const double gm2 = 0.5 / gamma;
-  const double css = std::sqrt(tmp) / th.mach;
+  const double css = th.sos(tmp);
   const double csa = css / var0;
   const double lmach = uu / csa;
   const double lmda[5] = {uu, uu, uu, uu + csa, uu - csa};

@@ -3,7 +3,7 @@ IDENTICAL inputs (the oracle's own arrays are uploaded through the C ABI)."""
 import numpy as np
 
 import astr_b200
-from astr_b200 import RhsEngine, decompose, refcal
+from astr_b200 import RhsEngine, decompose, refcal, refcal_dimensional
 
 HM = 5
 PRIMS = ["rho", "u", "v", "w", "prs", "tmp"]
@@ -91,24 +91,59 @@ def clean_metrics(c):
             c.set(nm, v, ib)
 
 
-def auto_shkcrt(c, bfacmpld=0.3, quantile=0.7):
+def auto_shkcrt(c, bfacmpld=0.3, quantile=0.5):
     """Ducros threshold in the middle of the widest gap of the oracle's sensor values around the requested
     quantile, so that no lshock flag sits within rounding distance of the threshold."""
     c.set_upwind(543, True, bfacmpld, 1.0)
     c.qswap(); c.gradcal(); c.ducrossensor()
-    v = np.sort(np.concatenate([core(c.get("ssf", ib)).ravel() for ib in range(c.nblocks)]))
-    k0 = int(quantile * v.size)
+    # lshock compares the maximum of ssf over the -4..+5 neighbours along each direction with the threshold
+    # (src/commcal.F90:286-309): take the quantile of that local-maximum field
+    vals = []
+    for ib in range(c.nblocks):
+        f = c.get("ssf", ib)
+        m = np.zeros_like(f)
+        for ax in range(3):
+            for o in range(-HM + 1, HM + 1):
+                m = np.maximum(m, np.roll(f, -o, axis=ax))
+        vals.append(core(m).ravel())
+    v = np.sort(np.concatenate(vals))
+    k0 = min(max(int(quantile * v.size), 200), v.size - 200)
     win = v[k0 - 200:k0 + 200]
     g = int(np.argmax(np.diff(win)))
     return 0.5 * (win[g] + win[g + 1])
 
 
+def dimensional_state(c, th, ib=0):
+    """Smooth SI-unit field around the HBL reference state (Mach 3): q from fvar2q with temperature and cv."""
+    X, Y, Z = (core(c.get(f"x{d + 1}", ib)) for d in range(3))
+    rho = 0.0180119 * (1.0 + 0.1 * np.sin(X) * np.cos(Y))
+    tmp = 226.65 * (1.0 + 0.05 * np.cos(X + 0.3) * np.sin(Y) * np.cos(Z))
+    u = 900.0 * (0.6 + 0.2 * np.sin(Y) * np.cos(Z))
+    v = 900.0 * 0.1 * np.cos(X) * np.sin(Z + 0.2)
+    w = 900.0 * 0.05 * np.sin(X) * np.sin(Y)
+    prs = rho * tmp * th["rgas"]
+    q5 = rho * (tmp * th["cv"] + 0.5 * (u * u + v * v + w * w))
+    vals = dict(rho=rho, u=u, v=v, w=w, prs=prs, tmp=tmp, q1=rho, q2=rho * u, q3=rho * v, q4=rho * w, q5=q5)
+    for name, a in vals.items():
+        full = c.get(name, ib)
+        core(full)[...] = a
+        c.set(name, full, ib)
+
+
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
-              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False):
+              lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False,
+              dimensional=False):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
-    c = oracle.Case(*n, homo=homo, sutherland_s=sutherland_s, reynolds=reynolds, mach=mach, lengths=lengths)
+    deltat = 1e-5 if dimensional else 1e-3
+    c = oracle.Case(*n, homo=homo, sutherland_s=sutherland_s, reynolds=reynolds, mach=mach, lengths=lengths,
+                    deltat=deltat)
+    if dimensional:
+        # nondimen=f with the reference state of examples/Hypersonic_Boundary_Layer/datin/input.M3
+        ref = (226.65, 900.0, 1.0, 0.0180119)
+        c.set_dimensional(*ref)
+        th = refcal_dimensional(*ref)
     c.set_flags(lfilter=lfilter, diffterm=diffterm)
     c.set_scheme(explicit)
     bctype, twall, force = (1,) * 6, (0.0,) * 6, (0.0, 0.0, 0.0)
@@ -136,6 +171,8 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         clean_metrics(c)
     if channel:
         channel_state(c, th)
+    elif dimensional:
+        dimensional_state(c, th)
     else:
         c.tgvini()
     if perturb:
@@ -151,10 +188,10 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         up_kw = dict(conschm=543, lchardecomp=upwind.get("lchardecomp", True), bfacmpld=upwind.get("bfacmpld", 0.3),
                      shkcrt=upwind.get("shkcrt", 0.01))
         if up_kw["shkcrt"] == "auto":
-            up_kw["shkcrt"] = auto_shkcrt(c, up_kw["bfacmpld"], upwind.get("quantile", 0.7))
+            up_kw["shkcrt"] = auto_shkcrt(c, up_kw["bfacmpld"], upwind.get("quantile", 0.5))
         c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
     block = decompose(n, (1, 1, 1), homo)[0]
-    eng = RhsEngine(block, n, homo, th, deltat=1e-3, lfilter=lfilter, diffterm=diffterm, device=0,
+    eng = RhsEngine(block, n, homo, th, deltat=deltat, lfilter=lfilter, diffterm=diffterm, device=0,
                     flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw)
     eng.set_force(force)
     if open_faces:

@@ -46,6 +46,11 @@ CASES = {
     "upwind2d_walls": dict(n=(48, 40, 0), homo=(False, False, True), stretch=True, perturb=1e-2,
                            upwind=dict(lchardecomp=True, shkcrt="auto")),
     "explicit2d": dict(n=(40, 40, 0), homo=(True, False, True), stretch=True, explicit=True),
+    # nondimen=f: SI units (rgas, cv, dimensional Sutherland and sound speed), Mach-3 reference state of the
+    # HBL input; central and upwind convection
+    "dimensional": dict(n=(32, 36, 24), homo=(True, True, True), dimensional=True),
+    "dimensional_upwind_walls": dict(n=(36, 32, 0), homo=(False, False, True), stretch=True, dimensional=True,
+                                     upwind=dict(lchardecomp=True, shkcrt="auto")),
     "channel": dict(n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0),
 }
 

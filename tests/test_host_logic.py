@@ -144,3 +144,18 @@ def test_partitioned_thomas_is_exact(oracle, is_filter, ntype, C):
     res[1:] += a[1:] * x[:-1]
     res[:-1] += c[:-1] * x[1:]
     assert np.abs(res - d).max() < 1e-12 * max(1.0, scale)
+
+
+def test_refcal_dimensional_matches_the_oracle(oracle):
+    # nondimen=f branch of refcal (src/solver.F90:124-148) with the HBL reference state (input.M3)
+    from astr_b200 import refcal_dimensional
+    ref = (226.65, 900.0, 1.0, 0.0180119)
+    th = refcal_dimensional(*ref)
+    c = oracle.Case(16, 16, 16)
+    c.set_dimensional(*ref)
+    want = c.thermo()
+    c.close()
+    assert want["nondimen"] == 0.0 and th["nondimen"] == 0
+    for k in ("reynolds", "mach", "const1", "const2", "const5", "const6", "rgas", "cp", "cv", "pinf"):
+        assert abs(th[k] - want[k]) <= 1e-14 * abs(want[k]), k
+    assert 2.9 < th["mach"] < 3.1      # "M3"
