@@ -185,6 +185,8 @@ struct Ctx {
   bool sigma_partial = false;    // sigma/qflux are in memory only on the face shells (fused rhscal)
   double force[3] = {0, 0, 0};
   double* ycoord = nullptr;      // x(:,:,:,2) for src_chan (flowtype channel only)
+  struct Sponge { bool on = false; int beg = -1, end = -2; double* coef = nullptr; } spg[6];   // i0, im, j0, jm, k0, km
+  bool any_sponge() const { for (const Sponge& s : spg) if (s.on) return true; return false; }
   double* d_inflow = nullptr;    // vel_in(0:jm,0:km,3) | tmp_in(0:jm,0:km) | tmp_prof(0:jm)  (bctype(1)=11)
   double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
   bool src_pending = false;      // src_chan's term is not in the G slots: consumers add d_src+4
@@ -515,9 +517,10 @@ int astr_gpu_init(const astr_cfg* cfg) {
     return astr_fail_msg("ndims must be 3 (km>=1) or 2 (km=0, ksize=1)");
   for (int n = 0; n < 6; ++n)
     if (!(cfg->bctype[n] == 1 || cfg->bctype[n] == 41 || (cfg->bctype[n] == 11 && n == 0) ||
-          (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n == 3)))
+          (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n == 3) ||
+          (cfg->bctype[n] == 421 && n == 2)))
       return astr_fail_msg("bctype on the device: 1 (periodic), 41 (isothermal wall, any face), 11 (inflow, imin), "
-                           "21 (outflow, imax or jmax), 51 (farfield, jmax)");
+                           "21 (outflow, imax or jmax), 51 (farfield, jmax), 421 (slip adiabatic wall, jmin)");
 
   // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
   if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
@@ -614,6 +617,7 @@ int astr_gpu_finalize(void) {
   cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
   if (g->ycoord) cudaFree(g->ycoord);
   if (g->d_inflow) cudaFree(g->d_inflow);
+  for (auto& sp : g->spg) if (sp.coef) cudaFree(sp.coef);
   cudaStreamDestroy(g->st);
   delete g;
   g = nullptr;
@@ -835,8 +839,8 @@ int astr_gpu_boucon(void) {
       if (!mine) continue;
       ProfScope ps(PC_HALO);
       TRY(pw_noslip(g->L, g->pool, g->th, d, side, c.twall[n], g->st));
-    } else if ((bt == 11 && n == 0) || (bt == 21 && (n == 1 || n == 3)) || (bt == 51 && n == 3)) {
-      // inflow(1) bc.F90:1366, outflow(2|4) :3404, farfield(4) :3008 -- the faces the reference itself treats
+    } else if ((bt == 11 && n == 0) || (bt == 21 && (n == 1 || n == 3)) || (bt == 51 && n == 3) || (bt == 421 && n == 2)) {
+      // inflow(1) bc.F90:1366, outflow(2|4) :3404, farfield(4) :3008, slipadibwall(3) :7231
       if (!mine) continue;
       BcArgs a;
       a.kind = bt; a.side = side; a.pinf = c.pinf; a.deltat = c.deltat;
@@ -1053,6 +1057,12 @@ int astr_gpu_rk_stage(int rkstep, double deltat) {
   TRY(astr_gpu_rhscal());
   RkCoef rk;
   TRY(rk_coef(rkstep, deltat, rk));
+  if (g->any_sponge()) {                             // mainloop.F90:478: spongefilter sits between the update and updatefvar
+    rk.with_fvar = 0;
+    { ProfScope ps(PC_RK); TRY(pw_rk_update(g->L, g->pool, g->th, rk, g->src(), g->st)); }
+    TRY(astr_gpu_spongefilter());
+    return astr_gpu_updatefvar();
+  }
   rk.with_fvar = 1;
   ProfScope ps(PC_RK);
   return pw_rk_update(g->L, g->pool, g->th, rk, g->src(), g->st);
@@ -1098,6 +1108,48 @@ int astr_gpu_set_inflow(const double* vel_in, const double* tmp_in, const double
   CUDA_OK(cudaMemcpyAsync(g->d_inflow + 3 * nf, tmp_in, nf * sizeof(double), cudaMemcpyHostToDevice, g->st));
   CUDA_OK(cudaMemcpyAsync(g->d_inflow + 4 * nf, tmp_prof, (c.jm + 1) * sizeof(double), cudaMemcpyHostToDevice, g->st));
   CUDA_OK(cudaStreamSynchronize(g->st));
+  return 0;
+}
+
+// sponge layer of one face (spongelayer_define_ijk / layer_setup, src/sponge_layer.F90:442-1011, stay on the host):
+// face 0 i0, 1 im, 3 jm, 4 k0, 5 km; beg..end = node range of the layer along the face direction on this rank
+// (beg<0: the layer exists, lspg_* is set, but not on this rank: the rank still takes part in the exchange);
+// coef = sponge_damp_coef over [beg:end] x [s:e] x [s:e] of the other two directions, Fortran order
+int astr_gpu_set_sponge(int face, int beg, int end, const double* coef) {
+  NEED_CTX();
+  if (face < 0 || face > 5 || face == 2) return astr_fail_msg("set_sponge: face must be 0 (i0), 1 (im), 3 (jm), 4 (k0) or 5 (km)");
+  Ctx::Sponge& sp = g->spg[face];
+  sp.on = true; sp.beg = beg; sp.end = end;
+  if (sp.coef) { cudaFree(sp.coef); sp.coef = nullptr; }
+  if (beg >= 0) {
+    const astr_cfg& c = g->cfg;
+    const int s[3] = {c.is, c.js, c.ks}, e[3] = {c.ie, c.je, c.ke};
+    size_t cnt = (size_t)(end - beg + 1);
+    for (int o = 0; o < 3; ++o) if (o != face / 2) cnt *= (size_t)(e[o] - s[o] + 1);
+    CUDA_OK(cudaMalloc(&sp.coef, cnt * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(sp.coef, coef, cnt * sizeof(double), cudaMemcpyHostToDevice, g->st));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+  }
+  return 0;
+}
+
+// spongefilter -> spongefilter_layer (src/sponge_layer.F90:55-319)
+int astr_gpu_spongefilter(void) {
+  NEED_CTX();
+  const astr_cfg& c = g->cfg;
+  static const int faces[5] = {0, 1, 3, 4, 5};
+  const FieldList fq = fields(S_Q, 5);
+  for (int f : faces) {
+    const Ctx::Sponge& sp = g->spg[f];
+    if (!sp.on) continue;
+    const int d = f / 2;
+    TRY(dataswap(fq, d));
+    if (sp.beg < 0) continue;
+    Box b = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
+    b.lo[d] = sp.beg; b.hi[d] = sp.end;
+    ProfScope ps(PC_FVAR);
+    TRY(pw_sponge(g->L, g->pool, b, sp.coef, g->st));
+  }
   return 0;
 }
 

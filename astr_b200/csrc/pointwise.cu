@@ -584,6 +584,14 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
     prs[x] = p;
     v0[x] = vin0 + (a.pinf - p) / rho_ref / css;
     rho[x] = th.rho_of(p, tmp[x]);
+  } else if (a.kind == 421) {              // slipadibwall(3), bc.F90:7231-7430: slip, adiabatic
+    const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]);
+    const double te = extrap2(tmp[x + sg], tmp[x + 2 * sg]);
+    const double ue = extrap2(v0[x + sg], v0[x + 2 * sg]);
+    v0[x] = ue; v1[x] = 0.0; v2[x] = 0.0;
+    tmp[x] = te; prs[x] = pe;
+    rho[x] = th.rho_of(pe, te);
+    from_T = false;
   } else if (a.kind == 21 && DIR == 0) {   // outflow at imax: first-order copy
     v0[x] = v0[x + sg]; v1[x] = v1[x + sg]; v2[x] = v2[x + sg];
     prs[x] = prs[x + sg]; tmp[x] = tmp[x + sg];
@@ -617,6 +625,31 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
   pool[(S_Q + 3) * fs + x] = r * w;
   const double var1 = 0.5 * (u * u + v * v + w * w);
   pool[(S_Q + 4) * fs + x] = from_T ? r * (tmp[x] * th.cotem() + var1) : prs[x] * th.const6 + r * var1;
+}
+
+// ---------------------------------------------------------------------------------
+// spongefilter_layer (src/sponge_layer.F90:67-319): damped 7-point average of q over the layer box,
+// Jacobi style -- pass 1 writes the qrhs slots (dead between the RK update and the next rhscal), pass 2
+// copies them back.  coef is the box-shaped sponge_damp_coef in Fortran order.
+// ---------------------------------------------------------------------------------
+template <bool COPYBACK>
+__global__ void k_sponge(const Layout L, double* __restrict__ pool, const Box b, const double* __restrict__ coef) {
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  if (COPYBACK) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) pool[(S_Q + n) * fs + x] = pool[(S_QRHS + n) * fs + x];
+    return;
+  }
+  const int ni = b.hi[0] - b.lo[0] + 1, nj = b.hi[1] - b.lo[1] + 1;
+  const double var1 = coef[(long long)(i - b.lo[0]) + (long long)ni * ((j - b.lo[1]) + (long long)nj * (k - b.lo[2]))];
+#pragma unroll
+  for (int n = 0; n < 5; ++n) {
+    const double* q = pool + (S_Q + n) * fs + x;
+    pool[(S_QRHS + n) * fs + x] =
+        (1.0 - var1) * q[0] + (1.0 / 6.0) * var1 * (q[1] + q[-1] + q[L.sj] + q[-L.sj] + q[L.sk] + q[-L.sk]);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -813,6 +846,15 @@ int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st) {
   if (dir == 0) k_diff6e<0><<<grid, PW_T, 0, st>>>(L, a);
   else if (dir == 1) k_diff6e<1><<<grid, PW_T, 0, st>>>(L, a);
   else k_diff6e<2><<<grid, PW_T, 0, st>>>(L, a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_sponge(const Layout& L, double* pool, const Box& b, const double* coef, cudaStream_t st) {
+  if (box_empty(b)) return 0;
+  k_sponge<false><<<box_grid(b), PW_T, 0, st>>>(L, pool, b, coef);
+  LAUNCH_CHECK();
+  k_sponge<true><<<box_grid(b), PW_T, 0, st>>>(L, pool, b, coef);
   LAUNCH_CHECK();
   return 0;
 }

@@ -191,6 +191,14 @@ class RhsEngine:
     def rk_update(self, rkstep: int, deltat: Optional[float] = None):
         _l.check(self._lib.astr_gpu_rk_update(rkstep, self.deltat if deltat is None else deltat))
 
+    def set_sponge(self, face: int, beg: int, end: int, coef: Optional[np.ndarray] = None):
+        """Sponge layer of face 0 i0 / 1 im / 3 jm / 4 k0 / 5 km (src/sponge_layer.F90); coef over the layer box."""
+        a = np.asfortranarray(coef, dtype=np.float64) if coef is not None else None
+        _l.check(self._lib.astr_gpu_set_sponge(face, beg, end, a.ctypes.data if a is not None else None))
+
+    def spongefilter(self):
+        _l.check(self._lib.astr_gpu_spongefilter())
+
     def updatefvar(self):
         _l.check(self._lib.astr_gpu_updatefvar())
 

@@ -121,8 +121,16 @@ module astr_gpu_mod
       integer(c_int), value :: rkstep
       real(c_double), value :: deltat
     end function
+    integer(c_int) function astr_gpu_spongefilter() bind(c,name='astr_gpu_spongefilter')
+      import :: c_int
+    end function
     integer(c_int) function astr_gpu_updatefvar() bind(c,name='astr_gpu_updatefvar')
       import :: c_int
+    end function
+    integer(c_int) function astr_gpu_set_sponge(face,beg,end,coef) bind(c,name='astr_gpu_set_sponge')
+      import :: c_int, c_double
+      integer(c_int), value :: face,beg,end
+      real(c_double), intent(in) :: coef(*)
     end function
     integer(c_int) function astr_gpu_rk_stage(rkstep,deltat) bind(c,name='astr_gpu_rk_stage')
       import :: c_int, c_double

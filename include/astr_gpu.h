@@ -69,7 +69,7 @@ typedef struct astr_cfg {
                                  kmax (src/bc.F90:327-407 boucon).  On the device:
                                  1 periodic/none; 41 isothermal wall (any face);
                                  11 inflow (imin); 21 outflow (imax, jmax); 51 farfield
-                                 (jmax) -- the faces the reference's own routines treat   */
+                                 (jmax); 421 slip adiabatic wall (jmin)                  */
   double alfa_filter;         /* 0.49 in every example                                   */
   double reynolds, mach, prandtl, gamma, ref_tem;
   double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */
@@ -137,9 +137,9 @@ int astr_gpu_gradcal(void);      /* src/comsolver.F90:244  gradcal              
 int astr_gpu_rhscal(void);       /* src/solver.F90:185     rhscal (zeroes qrhs first,
                                     i.e. includes src/mainloop.F90:408 `qrhs=0`)        */
 int astr_gpu_rk_update(int rkstep, double deltat); /* src/mainloop.F90:427-476          */
+int astr_gpu_spongefilter(void); /* src/sponge_layer.F90:55 spongefilter (layer form)    */
 int astr_gpu_updatefvar(void);   /* src/fludyna.F90:191    updatefvar                   */
-/* all of the above in the order of src/mainloop.F90:396-482 (spongefilter is the caller's:
- * usable when there is no sponge layer) */
+/* all of the above in the order of src/mainloop.F90:396-482 */
 int astr_gpu_rk_stage(int rkstep, double deltat);
 /* nsteps x (rk stages 1..3) with nothing in between */
 int astr_gpu_rk_steps(int nsteps, double deltat);
@@ -148,6 +148,12 @@ int astr_gpu_rk_steps_timed(int nsteps, double deltat, float* ms);
 
 /* generic halo exchange of one device field (dataswap, src/parallel.F90:3499-4382) */
 int astr_gpu_dataswap(int field_id, int direction /*0 = all, 1..3*/);
+
+/* sponge layers (spongelayer_define_ijk / layer_setup stay on the host, src/sponge_layer.F90:442-1011):
+ * face 0 i0, 1 im, 3 jm, 4 k0, 5 km (spongefilter_layer has no j0 block); beg..end = node range of the layer
+ * along the face direction on this rank, beg<0 = the layer exists (lspg_* set) but not on this rank;
+ * coef = sponge_damp_coef over [beg:end] x the is:ie / js:je / ks:ke ranges of the other two directions */
+int astr_gpu_set_sponge(int face, int beg, int end, const double* coef);
 
 /* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal when
  * flowtype = 1; `force` is what massfluxchan/chanfoce (src/statistic.F90:1437-1520) keep

@@ -92,6 +92,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_bc.argtypes = [vp, vp, vp]
         L.oracle_case_set_flow.argtypes = [vp, ci, vp]
         L.oracle_case_set_inflow.argtypes = [vp, ci, vp, vp, vp]
+        L.oracle_case_set_sponge.argtypes = [vp, ci, ci, ci, ci, vp]
+        L.oracle_case_spongefilter.argtypes = [vp]
         L.oracle_case_set_dimensional.argtypes = [vp, cd, cd, cd, cd]
         L.oracle_case_thermo.argtypes = [vp, vp]
         L.oracle_case_pinf.argtypes = [vp]
@@ -288,6 +290,14 @@ class Case:
         """inflow(1) data (src/bc.F90:69-83): vel_in(0:jm,0:km,3), tmp_in(0:jm,0:km), tmp_prof(0:jm)."""
         a = [np.asfortranarray(v, dtype=np.float64) for v in (vel_in, tmp_in, tmp_prof)]
         lib().oracle_case_set_inflow(self._h, ib, *[v.ctypes.data for v in a])
+
+    def set_sponge(self, face: int, beg: int, end: int, coef=None, ib: int = 0):
+        """Sponge layer of face 0 i0 / 1 im / 3 jm / 4 k0 / 5 km (src/sponge_layer.F90:67-319)."""
+        a = np.asfortranarray(coef, dtype=np.float64) if coef is not None else np.zeros(1)
+        lib().oracle_case_set_sponge(self._h, ib, face, beg, end, a.ctypes.data)
+
+    def spongefilter(self):
+        lib().oracle_case_spongefilter(self._h)
 
     def set_dimensional(self, ref_tem: float, ref_vel: float, ref_len: float, ref_den: float):
         """nondimen=f: SI units, rgas=287.1 (src/solver.F90:124-148)."""

@@ -28,6 +28,11 @@ struct Block {
   CompactScheme fds[3], fil[3];
   Field x[3], q[5], rho, vel[3], prs, tmp, jacob, dxi[3][3];
   Field qrhs[5], qsave[5], dvel[3][3], dtmp[3], sigma[6], qflux[3], vor[3];
+  // spongefilter_layer (src/sponge_layer.F90:67-319): per face (i0, im, j0, jm, k0, km) the node range of the
+  // layer along the face direction on this block (beg<0: none here) and sponge_damp_coef over the box
+  // [beg:end] x [s:e] x [s:e] in Fortran order
+  struct SpongeLayer { int beg = -1, end = -2; std::vector<double> coef; };
+  SpongeLayer spg[6];
   Field ssf, lshock;   // ducrossensor (allocated on first use, commcal.F90:218-219); lshock as 0/1
   int dim(int d) const { return d == 0 ? im : (d == 1 ? jm : km); }
 };
@@ -57,6 +62,7 @@ struct Case {
   // inflow(1) data of the blocks with irk==0 (bc.F90 alloinflow :69-83): vel_in(0:jm,0:km,3),
   // tmp_in(0:jm,0:km), tmp_prof(0:jm); indexed [block]
   std::vector<std::vector<double>> vel_in, tmp_in, tmp_prof;
+  bool lspg[6] = {false, false, false, false, false, false};   // lspg_i0 .. lspg_km (global flags)
   std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
   double xmax = 0.0;
 };
@@ -867,6 +873,27 @@ static int farfield(Case& c, int ndir) {
   return 0;
 }
 
+// src/bc.F90:7231-7430 slipadibwall(ndir), restated for ndir==3 (jmin, the SWLBI input): slip (u extrapolated,
+// v=w=0), adiabatic (T extrapolated), p extrapolated, rho=thermal(p,T), q=fvar2q(pressure)
+static int slipadibwall(Case& c, int ndir) {
+  if (ndir != 3) return -1;
+  for (Block& b : c.blk) {
+    if (b.rk[1] != 0) continue;
+    const int j = 0;
+    for (int k = 0; k <= b.km; ++k)
+      for (int i = 0; i <= b.im; ++i) {
+        const double pe = num1d3 * (4.0 * b.prs(i, 1, k) - b.prs(i, 2, k));
+        const double te = num1d3 * (4.0 * b.tmp(i, 1, k) - b.tmp(i, 2, k));
+        const double ue = num1d3 * (4.0 * b.vel[0](i, 1, k) - b.vel[0](i, 2, k));
+        b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = 0.0; b.vel[2](i, j, k) = 0.0;
+        b.tmp(i, j, k) = te; b.prs(i, j, k) = pe;
+        b.rho(i, j, k) = c.th.thermal_rho(pe, te);
+        fvar2q_P(c.th, b, i, j, k);
+      }
+  }
+  return 0;
+}
+
 // src/bc.F90:327-407 boucon: faces in the order n=1..6; only the bctypes restated so far
 static int boucon(Case& c) {
   for (int n = 1; n <= 6; ++n) {
@@ -876,10 +903,49 @@ static int boucon(Case& c) {
     else if (bt == 51) rc = farfield(c, n);
     else if (bt == 11) rc = inflow(c, n);
     else if (bt == 21) rc = outflow(c, n);
+    else if (bt == 421) rc = slipadibwall(c, n);
     else if (bt != 1) rc = -1;
     if (rc) return rc;
   }
   return 0;
+}
+
+// src/sponge_layer.F90:67-319 spongefilter_layer: faces i0, im, jm, k0, km (the reference has no j0 block);
+// per face a one-direction dataswap of q, then a damped 7-point average over the layer (Jacobi: qtemp)
+static void spongefilter(Case& c) {
+  Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
+  static const int faces[5] = {0, 1, 3, 4, 5};
+  for (int f : faces) {
+    if (!c.lspg[f]) continue;
+    const int d = f / 2;
+    dataswap(c, gq, d);
+    for (Block& b : c.blk) {
+      const Block::SpongeLayer& sp = b.spg[f];
+      if (sp.beg < 0) continue;
+      int lo[3] = {b.s[0], b.s[1], b.s[2]}, hi[3] = {b.e[0], b.e[1], b.e[2]};
+      lo[d] = sp.beg; hi[d] = sp.end;
+      const int ni = hi[0] - lo[0] + 1, nj = hi[1] - lo[1] + 1, nk = hi[2] - lo[2] + 1;
+      std::vector<double> qtemp((size_t)5 * ni * nj * nk);
+      for (int n = 0; n < 5; ++n)
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) {
+              const size_t t = (size_t)(i - lo[0]) + (size_t)ni * ((size_t)(j - lo[1]) + (size_t)nj * (k - lo[2]));
+              const double var1 = sp.coef[t];
+              const Field& q = b.q[n];
+              qtemp[t + (size_t)n * ni * nj * nk] =
+                  (1.0 - var1) * q(i, j, k) + num1d6 * var1 * (q(i + 1, j, k) + q(i - 1, j, k) + q(i, j + 1, k) +
+                                                               q(i, j - 1, k) + q(i, j, k + 1) + q(i, j, k - 1));
+            }
+      for (int n = 0; n < 5; ++n)
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) {
+              const size_t t = (size_t)(i - lo[0]) + (size_t)ni * ((size_t)(j - lo[1]) + (size_t)nj * (k - lo[2]));
+              b.q[n](i, j, k) = qtemp[t + (size_t)n * ni * nj * nk];
+            }
+    }
+  }
 }
 
 // src/fludyna.F90:191-242 updatefvar
@@ -968,6 +1034,7 @@ static void rk_stage(Case& c, int rkstep) {
   }
   rhscal(c);
   rk_update(c, rkstep);
+  spongefilter(c);   // mainloop.F90:478
   updatefvar(c);
 }
 
@@ -1121,6 +1188,21 @@ void oracle_case_set_inflow(void* h, int ib, const double* vel_in, const double*
   c->tmp_in[ib].assign(tmp_in, tmp_in + nf);
   c->tmp_prof[ib].assign(tmp_prof, tmp_prof + b.jm + 1);
 }
+// sponge layer of face f (0 i0, 1 im, 3 jm, 4 k0, 5 km) on block ib: node range beg..end along the face
+// direction (beg<0: the layer exists but not on this block) and the damping coefficients over the box
+void oracle_case_set_sponge(void* h, int ib, int face, int beg, int end, const double* coef) {
+  Case* c = static_cast<Case*>(h);
+  Block& b = c->blk[ib];
+  c->lspg[face] = true;
+  b.spg[face].beg = beg; b.spg[face].end = end;
+  if (beg >= 0) {
+    const int d = face / 2;
+    size_t cnt = (size_t)(end - beg + 1);
+    for (int o = 0; o < 3; ++o) if (o != d) cnt *= (size_t)(b.e[o] - b.s[o] + 1);
+    b.spg[face].coef.assign(coef, coef + cnt);
+  }
+}
+void oracle_case_spongefilter(void* h) { spongefilter(*static_cast<Case*>(h)); }
 double oracle_case_pinf(void* h) { return static_cast<Case*>(h)->pinf; }
 // nondimen=f (src/solver.F90:124-148): SI reference state; Mach, Reynolds, const1..7, pinf follow
 void oracle_case_set_dimensional(void* h, double ref_tem, double ref_vel, double ref_len, double ref_den) {

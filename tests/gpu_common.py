@@ -132,7 +132,7 @@ def dimensional_state(c, th, ib=0):
 
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
               lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False,
-              dimensional=False):
+              dimensional=False, sponge=None, inflow_from_state=False):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
@@ -158,7 +158,10 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         # the boundary set of the HBL / SWLBI inputs: inflow (imin), outflow (imax), isothermal wall (jmin),
         # farfield (jmax) -- examples/Hypersonic_Boundary_Layer/datin/input.M3
         assert tuple(homo) == (False, False, True)
-        bctype, twall = (11, 21, 41, 21 if open_faces == "outflow_top" else 51, 1, 1), (0, 0, 1.05, 0, 0, 0)
+        bctype = (11, 21, 41, 21 if open_faces == "outflow_top" else 51, 1, 1)
+        twall = (0, 0, 568.89 if dimensional else 1.05, 0, 0, 0)       # input.M3: `41, 568.89d0`
+        if open_faces == "swbli":      # examples/SWLBI/datin/input.2d: slip adiabatic wall at jmin
+            bctype = (11, 21, 421, 51, 1, 1)
         c.set_bc(bctype, twall)
     if channel:
         pass
@@ -198,18 +201,46 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         # synthetic inflow data: half of the profile supersonic (blend -> 1), half subsonic (blend -> 0)
         jm, km = n[1], n[2]
         yy = np.arange(jm + 1) / jm
+        uref, tref = (900.0, 226.65) if dimensional else (1.0, 1.0)
+        prof = (0.2 + 0.8 * (yy > 0.5)) if dimensional else (1.0 + 14.0 * (yy > 0.5))   # sound speed ~302 m/s | 10
         vel_in = np.zeros((jm + 1, km + 1, 3), order="F")
-        vel_in[:, :, 0] = (1.0 + 14.0 * (yy > 0.5))[:, None] * (1.0 + 0.01 * np.cos(np.arange(km + 1)))[None, :]
-        vel_in[:, :, 1] = 0.02 * np.sin(3 * yy)[:, None]
-        vel_in[:, :, 2] = 0.01
-        tmp_in = np.asfortranarray(1.0 + 0.05 * yy[:, None] * np.ones((1, km + 1)))
-        tmp_prof = 1.0 + 0.05 * yy
+        vel_in[:, :, 0] = uref * prof[:, None] * (1.0 + 0.01 * np.cos(np.arange(km + 1)))[None, :]
+        vel_in[:, :, 1] = uref * 0.02 * np.sin(3 * yy)[:, None]
+        vel_in[:, :, 2] = uref * 0.01
+        tmp_in = np.asfortranarray(tref * (1.0 + 0.05 * yy[:, None] * np.ones((1, km + 1))))
+        tmp_prof = tref * (1.0 + 0.05 * yy)
+        if inflow_from_state:
+            # what profileinflow would hold for a flow that is already established: the state at i=0
+            for m, nm in enumerate(("u", "v", "w")):
+                vel_in[:, :, m] = core(c.get(nm))[0, :, :]
+            tmp_in = np.asfortranarray(core(c.get("tmp"))[0, :, :])
+            tmp_prof = tmp_in[:, 0].copy()
         c.set_inflow(vel_in, tmp_in, tmp_prof)
         eng.set_inflow(vel_in, tmp_in, tmp_prof)
-        # make part of the jmax face supersonic outwards so that outflow(4)/farfield see both branches
-        v = c.get("v")
-        v[HM + n[0] // 2:, HM + n[1], :] = 12.0
-        c.set("v", v)
+        if not inflow_from_state:
+            # make part of the jmax face supersonic outwards so that outflow(4)/farfield see both branches
+            v = c.get("v")
+            v[HM + n[0] // 2:, HM + n[1], :] = 400.0 if dimensional else 12.0
+            c.set("v", v)
+    if sponge:
+        # sponge layers as `spg_imax = 20` of the SWLBI input would define them (spongelayer_define_ijk): the
+        # damping coefficient is a smooth ramp towards the face
+        for face, width in sponge.items():
+            d = face // 2
+            dm = n[d]
+            beg, end = (block.s[d], block.s[d] + width - 1) if face % 2 == 0 else (block.e[d] - width + 1, block.e[d])
+            shape = [block.e[o] - block.s[o] + 1 for o in range(3)]
+            shape[d] = width
+            ramp = (np.arange(width) + 1.0) / width
+            if face % 2 == 0:
+                ramp = ramp[::-1]
+            idx = [None, None, None]
+            idx[d] = slice(None)
+            coef = 0.5 * ramp[tuple(idx)] ** 2 * np.ones(shape)
+            coef *= 1.0 + 0.1 * np.cos(np.arange(shape[(d + 1) % 3]))[tuple(slice(None) if o == (d + 1) % 3 else None for o in range(3))]
+            coef = np.asfortranarray(coef)
+            c.set_sponge(face, beg, end, coef)
+            eng.set_sponge(face, beg, end, coef)
     x = eng.empty(3)
     for d in range(3):
         x[..., d] = c.get(f"x{d + 1}")

@@ -102,6 +102,42 @@ def test_boucon_open_faces(oracle, n, top):
     eng.close(); c.close()
 
 
+@pytest.mark.parametrize("n,faces", [((48, 40, 0), {1: 10}), ((36, 32, 24), {0: 6, 1: 8, 3: 5, 4: 4, 5: 4})])
+def test_spongefilter(oracle, n, faces):
+    # spongefilter_layer (src/sponge_layer.F90:67-319): one-direction exchange + damped 7-point average per face
+    c, eng = make_pair(oracle, n=n, homo=(False, False, True), stretch=True, sponge=faces)
+    c.spongefilter(); eng.spongefilter()
+    assert_fields_close(c, eng, QS, OP_TOL, region=whole, what="spongefilter")
+    eng.close(); c.close()
+
+
+def test_swbli_like_stage(oracle):
+    # the option set of examples/SWLBI/datin/input.2d on a small 2-D block: 543c + 643c, characteristic
+    # decomposition + Ducros sensor, inflow / outflow / slip adiabatic wall / farfield, sponge layer at imax
+    c, eng = make_pair(oracle, n=(64, 40, 0), homo=(False, False, True), stretch=True, perturb=1e-2, lfilter=False,
+                       open_faces="swbli", inflow_from_state=True, sponge={1: 12},
+                       upwind=dict(lchardecomp=True, bfacmpld=0.3, shkcrt="auto"))
+    for rk in (1, 2, 3):
+        c.rk_stage(rk); eng.rk_stage(rk)
+    assert np.isfinite(core(c.get("q5"))).all()
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="SWLBI-like RK3 step")
+    np.testing.assert_array_equal(core(eng.get("lshock")), core(c.get("lshock")))
+    eng.close(); c.close()
+
+
+def test_hbl_like_stage(oracle):
+    # the option set of examples/Hypersonic_Boundary_Layer/datin/input.M3 on a small 2-D block: dimensional gas,
+    # 543c convection + 642e diffusion, no filter, inflow / outflow / isothermal wall / farfield
+    c, eng = make_pair(oracle, n=(56, 48, 0), homo=(False, False, True), stretch=True, lfilter=False, dimensional=True,
+                       explicit=True, open_faces=True, inflow_from_state=True,
+                       upwind=dict(lchardecomp=True, bfacmpld=0.1, shkcrt="auto"))
+    for rk in (1, 2, 3):
+        c.rk_stage(rk); eng.rk_stage(rk)
+    assert np.isfinite(core(c.get("q5"))).all()
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="HBL-like RK3 step")
+    eng.close(); c.close()
+
+
 def test_qswap(pair):
     c, eng = pair
     c.qswap(); eng.qswap()
