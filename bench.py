@@ -170,7 +170,10 @@ def run_gpu(args):
     homo = (True, True, True)
     block = decompose(gdims, size, homo)[rank]
     th = refcal(1600.0, 0.1)
-    eng = RhsEngine(block, gdims, homo, th, deltat=1e-3 * 128 / n, device=local_rank)
+    up_kw = {}
+    if args.conschm == 543:     # the upwind compact / shock-capturing convection path (config 4's scheme) on the TGV block
+        up_kw = dict(conschm=543, lchardecomp=True, bfacmpld=0.3, shkcrt=0.01)
+    eng = RhsEngine(block, gdims, homo, th, deltat=1e-3 * 128 / n, device=local_rank, **up_kw)
     if world > 1:
         def bcast(b):
             t = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -290,7 +293,10 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TGV {n}^3 per GPU ({n + 1}^3 nodes + 5-deep halos), periodic, fp64, 643c compact "
+        "config": {"workload": f"TGV {n}^3 per GPU ({n + 1}^3 nodes + 5-deep halos), periodic, fp64, "
+                               + ("543c upwind compact convection (Steger-Warming, characteristic MP5, Ducros sensor) + "
+                                  if args.conschm == 543 else "") +
+                               f"643c compact "
                                f"derivative + compact filter alfa=0.49, RK3, Re=1600 M=0.1; block grid "
                                f"{size[0]}x{size[1]}x{size[2]}",
                    "points_per_gpu": pts, "stages_per_step": STAGES,
@@ -321,6 +327,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--conschm", type=int, default=643, choices=[643, 543],
+                    help="643: central compact convection (the BASELINE metric); 543: upwind compact path")
     ap.add_argument("--layout", default="", help="block grid isize,jsize,ksize (default: mpisizedis)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
