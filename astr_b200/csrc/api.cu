@@ -187,6 +187,7 @@ struct Ctx {
   double* ycoord = nullptr;      // x(:,:,:,2) for src_chan (flowtype channel only)
   struct Sponge { bool on = false; int beg = -1, end = -2; double* coef = nullptr; } spg[6];   // i0, im, j0, jm, k0, km
   bool any_sponge() const { for (const Sponge& s : spg) if (s.on) return true; return false; }
+  double* stage = nullptr;       // dense host-layout staging field of the upload path
   double* d_inflow = nullptr;    // vel_in(0:jm,0:km,3) | tmp_in(0:jm,0:km) | tmp_prof(0:jm)  (bctype(1)=11)
   double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
   bool src_pending = false;      // src_chan's term is not in the G slots: consumers add d_src+4
@@ -617,6 +618,7 @@ int astr_gpu_finalize(void) {
   cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
   if (g->ycoord) cudaFree(g->ycoord);
   if (g->d_inflow) cudaFree(g->d_inflow);
+  if (g->stage) cudaFree(g->stage);
   for (auto& sp : g->spg) if (sp.coef) cudaFree(sp.coef);
   cudaStreamDestroy(g->st);
   delete g;
@@ -655,6 +657,13 @@ static int copy_dev(double* field, double* host, bool to_host) {
   const Layout& L = g->L;
   const size_t w = (size_t)(L.im + 1 + 2 * ASTR_HM) * sizeof(double);
   const size_t rows = (size_t)L.njt * L.nkt;
+  if (!to_host && rows * w >= ((size_t)8 << 20)) {
+    // uploads: one contiguous DMA into a dense staging field + a re-pitch kernel (measured on the bench box:
+    // 54 GB/s contiguous against 30 GB/s for the pitched 2-D host-to-device copy); stream order protects the buffer
+    if (!g->stage) CUDA_OK(cudaMalloc(&g->stage, rows * w));
+    CUDA_OK(cudaMemcpyAsync(g->stage, host, rows * w, cudaMemcpyHostToDevice, g->st));
+    return pw_repitch(L, g->stage, field, g->st);
+  }
   double* dev = field + (ASTR_IOFF - ASTR_HM);
   if (to_host)
     CUDA_OK(cudaMemcpy2DAsync(host, w, dev, (size_t)L.pitch * sizeof(double), w, rows, cudaMemcpyDeviceToHost, g->st));

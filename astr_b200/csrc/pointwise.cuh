@@ -74,6 +74,7 @@ struct BcArgs {
   const double* tmp_in;    // device (0:jm,0:km)
   const double* tmp_prof;  // device (0:jm)
 };
+int pw_repitch(const Layout& L, const double* stage, double* field, cudaStream_t st);
 int pw_sponge(const Layout& L, double* pool, const Box& b, const double* coef, cudaStream_t st);
 int pw_bcface(const Layout& L, double* pool, const Thermo& th, int dir, const BcArgs& a, cudaStream_t st);
 int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side, double tw, cudaStream_t st);
