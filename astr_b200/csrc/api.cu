@@ -14,6 +14,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <mutex>
@@ -176,10 +177,14 @@ struct Ctx {
   double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
   bool upwind() const { return (cfg.conschm / 100) % 2 == 1; }
   FilterCoef fc;
+  bool overlap = true;           // ASTR_OVERLAP=0: no side-stream overlap of the sigma/qflux exchange
   bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
   double* d_out2 = nullptr;
   cudaStream_t st = nullptr;
+  cudaStream_t cur = nullptr;    // stream the halo exchanges are issued on: st, or xst while an exchange overlaps compute
+  cudaStream_t xst = nullptr;
+  cudaEvent_t ev_shell = nullptr, ev_xdone = nullptr;
   bool have_metrics = false, have_grad = false;
   bool rhs_in_g = false;         // qrhs lives as three directional derivatives in the G slots
   bool sigma_partial = false;    // sigma/qflux are in memory only on the face shells (fused rhscal)
@@ -225,16 +230,16 @@ static Ctx* g = nullptr;
   } while (0)
 
 struct ProfScope {
-  int cat; bool on; cudaEvent_t a = nullptr, b = nullptr;
+  int cat; bool on; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t st = nullptr;
   static cudaEvent_t get() {
     if (!g->free_events.empty()) { cudaEvent_t e = g->free_events.back(); g->free_events.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
   explicit ProfScope(int c) : cat(c), on(g && g->profile) {
-    if (on) { a = get(); b = get(); cudaEventRecord(a, g->st); }
+    if (on) { a = get(); b = get(); st = g->cur; cudaEventRecord(a, st); }
   }
   ~ProfScope() {
-    if (on) { cudaEventRecord(b, g->st); g->spans.push_back({cat, a, b}); }
+    if (on) { cudaEventRecord(b, st); g->spans.push_back({cat, a, b}); }
   }
 };
 static void prof_collect() {
@@ -273,7 +278,7 @@ static int exchange_dir(const FieldList& fl, int d, int mode) {
   if (c.size[d] == 1) {
     if (!c.lhomo[d]) return 0;
     ProfScope ps(PC_HALO);
-    return pw_halo_wrap(g->L, fl, d, mode, g->st);
+    return pw_halo_wrap(g->L, fl, d, mode, g->cur);
   }
   if (!g->comm) return astr_fail_msg("multi-block exchange needs astr_gpu_comm_init");
   const Layout& L = g->L;
@@ -290,22 +295,22 @@ static int exchange_dir(const FieldList& fl, int d, int mode) {
   const int lo = c.nbr[2 * d], hi = c.nbr[2 * d + 1];
   {
     ProfScope ps(PC_XPACK);
-    if (lo >= 0) TRY(pw_pack(L, fl, d, 0, l0, l1, g->xbuf[0], g->st));
-    if (hi >= 0) TRY(pw_pack(L, fl, d, 1, l0, l1, g->xbuf[1], g->st));
+    if (lo >= 0) TRY(pw_pack(L, fl, d, 0, l0, l1, g->xbuf[0], g->cur));
+    if (hi >= 0) TRY(pw_pack(L, fl, d, 1, l0, l1, g->xbuf[1], g->cur));
   }
   ProfScope* pn = new ProfScope(PC_XNCCL);
   NCCL_OK(g_nccl.GroupStart());
-  if (lo >= 0) NCCL_OK(g_nccl.Send(g->xbuf[0], cnt, ncclDouble, lo, g->comm, g->st));
-  if (hi >= 0) NCCL_OK(g_nccl.Send(g->xbuf[1], cnt, ncclDouble, hi, g->comm, g->st));
+  if (lo >= 0) NCCL_OK(g_nccl.Send(g->xbuf[0], cnt, ncclDouble, lo, g->comm, g->cur));
+  if (hi >= 0) NCCL_OK(g_nccl.Send(g->xbuf[1], cnt, ncclDouble, hi, g->comm, g->cur));
   // when lo == hi (two blocks, periodic) the peer's first message is its low-side buffer,
   // which belongs in my high halo: post that receive first.
-  if (hi >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[3], cnt, ncclDouble, hi, g->comm, g->st));
-  if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->st));
+  if (hi >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[3], cnt, ncclDouble, hi, g->comm, g->cur));
+  if (lo >= 0) NCCL_OK(g_nccl.Recv(g->xbuf[2], cnt, ncclDouble, lo, g->comm, g->cur));
   NCCL_OK(g_nccl.GroupEnd());
   delete pn;
   ProfScope pu(PC_XUNPACK);
-  if (hi >= 0) TRY(pw_unpack(L, fl, d, 1, l0, l1, g->xbuf[3], g->st));
-  if (lo >= 0) TRY(pw_unpack(L, fl, d, 0, l0, l1, g->xbuf[2], g->st));
+  if (hi >= 0) TRY(pw_unpack(L, fl, d, 1, l0, l1, g->xbuf[3], g->cur));
+  if (lo >= 0) TRY(pw_unpack(L, fl, d, 0, l0, l1, g->xbuf[2], g->cur));
   return 0;
 }
 
@@ -451,8 +456,8 @@ static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
     r.signal_flag = &ph->ack[oslot]; r.signal_val = seq;
     r.counter = &hdr->crecv[slot];
   }
-  { ProfScope ps(PC_XPACK); TRY(pw_xsend(L, fl, d, sa, g->st)); }
-  { ProfScope ps(PC_XUNPACK); TRY(pw_xrecv(L, fl, d, ra, g->st)); }
+  { ProfScope ps(PC_XPACK); TRY(pw_xsend(L, fl, d, sa, g->cur)); }
+  { ProfScope ps(PC_XUNPACK); TRY(pw_xrecv(L, fl, d, ra, g->cur)); }
   return 0;
 }
 
@@ -555,6 +560,10 @@ int astr_gpu_init(const astr_cfg* cfg) {
   g->th.cp = cfg->gamma / (cfg->gamma - 1.0) * g->th.rgas;
   g->th.cv = g->th.rgas / (cfg->gamma - 1.0);
   CUDA_OK(cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&g->xst, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&g->ev_shell, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&g->ev_xdone, cudaEventDisableTiming));
+  g->cur = g->st;
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->pool, bytes));
   CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
@@ -566,6 +575,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
   TRY(astr_set_filter_coef(g->fc));
   { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
+  { const char* e = getenv("ASTR_OVERLAP"); g->overlap = !(e && e[0] == '0'); }
   for (int d = 0; d < cfg->ndims; ++d) {
     const int n = dim_of(d);
     build_deriv(g->fd[d], cfg->npdc[d], n);
@@ -621,6 +631,8 @@ int astr_gpu_finalize(void) {
   if (g->stage) cudaFree(g->stage);
   for (auto& sp : g->spg) if (sp.coef) cudaFree(sp.coef);
   cudaStreamDestroy(g->st);
+  cudaStreamDestroy(g->xst);
+  cudaEventDestroy(g->ev_shell); cudaEventDestroy(g->ev_xdone);
   delete g;
   g = nullptr;
   return 0;
@@ -710,7 +722,8 @@ int astr_gpu_get_field(int field_id, double* host) {
   if (s >= S_QRHS && s < S_QRHS + 5 && g->rhs_in_g) TRY(pw_sum_qrhs(g->L, g->pool, g->src(), g->st));
   if (s >= S_SIGMA && s < S_SIGMA + 9 && g->sigma_partial) {
     // the fused rhscal keeps the interior of sigma/qflux in registers: materialise on request
-    TRY(pw_visc(g->L, g->pool, g->th, g->st));
+    const Box all = {{0, 0, 0}, {g->L.im, g->L.jm, g->L.km}};
+    TRY(pw_visc(g->L, g->pool, g->th, all, g->st));
     g->sigma_partial = false;
   }
   TRY(copy_field(s, host, true));
@@ -973,11 +986,38 @@ int astr_gpu_rhscal(void) {
     if (c.lchardecomp) TRY(astr_gpu_ducrossensor());     // solver.F90:225
   }
   if (c.diffterm) {
-    // viscous stress + flux assembly of the block in one pass (sigma/qflux stay in registers and
-    // reach memory only on the face shells the exchange reads), then the halo exchange
-    { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, c.ndims, g->st)); }
+    const bool multi = c.size[0] * c.size[1] * c.size[2] > 1;
+    if (multi && g->overlap) {
+      // multi-block: the sigma/qflux exchange (solver.F90:2604-2606) is hidden behind the interior pass.
+      // 1. stresses on the face shells only (what the exchange sends), 2. exchange on the side stream,
+      // 3. meanwhile the fused stress + flux pass over the whole block on the main stream, 4. join.
+      {
+        ProfScope ps(PC_VISC);
+        for (int d = 0; d < c.ndims; ++d)
+          for (int side = 0; side < 2; ++side) {
+            Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+            const int dm = dim_of(d);
+            b.lo[d] = side ? std::max(dm - ASTR_HM, 0) : 0;
+            b.hi[d] = side ? dm : std::min(ASTR_HM, dm);
+            TRY(pw_visc(L, g->pool, g->th, b, g->st));
+          }
+      }
+      CUDA_OK(cudaEventRecord(g->ev_shell, g->st));
+      CUDA_OK(cudaStreamWaitEvent(g->xst, g->ev_shell, 0));
+      g->cur = g->xst;
+      const int rc = dataswap(fields(S_SIGMA, 9), -1);
+      g->cur = g->st;
+      if (rc) return rc;
+      CUDA_OK(cudaEventRecord(g->ev_xdone, g->xst));
+      { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, c.ndims, 0, g->st)); }
+      CUDA_OK(cudaStreamWaitEvent(g->st, g->ev_xdone, 0));
+    } else {
+      // viscous stress + flux assembly of the block in one pass (sigma/qflux stay in registers and
+      // reach memory only on the face shells the exchange reads), then the halo exchange
+      { ProfScope ps(PC_VISC); TRY(pw_visc_flux(L, g->pool, g->th, fr, c.ndims, 1, g->st)); }
+      TRY(dataswap(fields(S_SIGMA, 9), -1));         // sigma(6)+qflux(3), solver.F90:2604-2606
+    }
     g->sigma_partial = true;
-    TRY(dataswap(fields(S_SIGMA, 9), -1));         // sigma(6)+qflux(3), solver.F90:2604-2606
   }
   {
     ProfScope ps(PC_FLUX);

@@ -194,8 +194,7 @@ __device__ __forceinline__ void visc_node(const double* __restrict__ pool, const
   qf[2] = hcc * g.dt[2] + sg[2] * u + sg[4] * v + sg[5] * w;
 }
 
-__global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo th) {
-  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+__global__ void k_visc(const Layout L, double* __restrict__ pool, const Thermo th, const Box b) {
   int i, j, k;
   if (!box_node(b, i, j, k)) return;
   const long long fs = L.fstride, x = L.idx(i, j, k);
@@ -276,7 +275,8 @@ __global__ void k_flux(const Layout L, double* __restrict__ pool, const Box b, c
 // within ASTR_HM nodes of a block face, which is all the halo exchange (solver.F90:2604-2606)
 // and the halo-slab flux passes read.
 template <int DMASK>
-__global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const Thermo th, const FluxRanges fr) {
+__global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const Thermo th, const FluxRanges fr,
+                            const int store_shell) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
   int ijk[3];
   if (!box_node(b, ijk[0], ijk[1], ijk[2])) return;
@@ -285,7 +285,7 @@ __global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const The
   visc_node(pool, fs, x, th, sg, qf);
   const bool shell = ijk[0] <= ASTR_HM || ijk[0] >= L.im - ASTR_HM || ijk[1] <= ASTR_HM || ijk[1] >= L.jm - ASTR_HM ||
                      ijk[2] <= ASTR_HM || ijk[2] >= L.km - ASTR_HM;
-  if (shell) {
+  if (shell && store_shell) {
 #pragma unroll
     for (int n = 0; n < 6; ++n) pool[(S_SIGMA + n) * fs + x] = sg[n];
 #pragma unroll
@@ -783,17 +783,18 @@ int pw_q2fvar(const Layout& L, double* pool, const Thermo& th, const Box& b, cud
   return 0;
 }
 
-int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st) {
-  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  k_visc<<<box_grid(b), PW_T, 0, st>>>(L, pool, th);
+int pw_visc(const Layout& L, double* pool, const Thermo& th, const Box& b, cudaStream_t st) {
+  if (box_empty(b)) return 0;
+  k_visc<<<box_grid(b), PW_T, 0, st>>>(L, pool, th, b);
   LAUNCH_CHECK();
   return 0;
 }
 
-int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, cudaStream_t st) {
+int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, int store_shell,
+                 cudaStream_t st) {
   Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
-  if (ndims == 3) k_visc_flux<7><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);
-  else k_visc_flux<3><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr);    // 2-D: no zeta flux (solver.F90:2776)
+  if (ndims == 3) k_visc_flux<7><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr, store_shell);
+  else k_visc_flux<3><<<box_grid(b), PW_T, 0, st>>>(L, pool, th, fr, store_shell);    // 2-D: no zeta flux (solver.F90:2776)
   LAUNCH_CHECK();
   return 0;
 }

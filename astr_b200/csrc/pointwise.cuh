@@ -51,12 +51,14 @@ struct FieldList { double* f[ASTR_MAXF]; int nf; };
 
 int pw_halo_wrap(const Layout& L, const FieldList& fl, int dir, int mode, cudaStream_t st);
 int pw_q2fvar(const Layout& L, double* pool, const Thermo& th, const Box& b, cudaStream_t st);
-int pw_visc(const Layout& L, double* pool, const Thermo& th, cudaStream_t st);
+int pw_visc(const Layout& L, double* pool, const Thermo& th, const Box& b, cudaStream_t st);
 int pw_materialise_grad(const Layout& L, double* pool, double* dvel9_dtmp3_vor3, cudaStream_t st);
 // dmask bit d => build G_d ; cmask[d][2]: conv part only where the other two indices lie in
 // [s,e] ranges (src/solver.F90:2197-2198) ; diffterm adds the viscous part.
 struct FluxRanges { int s[3], e[3]; };
-int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, cudaStream_t st);
+// store_shell: write sigma/qflux on the face shells (0: a separate shell pass already did)
+int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRanges& fr, int ndims, int store_shell,
+                 cudaStream_t st);
 int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
             cudaStream_t st);
 struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; };
