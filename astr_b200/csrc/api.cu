@@ -177,7 +177,7 @@ struct Ctx {
   double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
   bool upwind() const { return (cfg.conschm / 100) % 2 == 1; }
   FilterCoef fc;
-  bool overlap = true;           // ASTR_OVERLAP=0: no side-stream overlap of the sigma/qflux exchange
+  bool overlap = false;          // ASTR_OVERLAP=1: side-stream overlap of the sigma/qflux exchange (measured slower at 2 GPUs)
   bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
   double* d_out2 = nullptr;
@@ -575,7 +575,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
   TRY(astr_set_filter_coef(g->fc));
   { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
-  { const char* e = getenv("ASTR_OVERLAP"); g->overlap = !(e && e[0] == '0'); }
+  { const char* e = getenv("ASTR_OVERLAP"); g->overlap = (e && e[0] == '1'); }
   for (int d = 0; d < cfg->ndims; ++d) {
     const int n = dim_of(d);
     build_deriv(g->fd[d], cfg->npdc[d], n);
