@@ -532,8 +532,16 @@ int astr_gpu_init(const astr_cfg* cfg) {
   if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
     return astr_fail_msg("difschm must be 643c (compact_central) or 6xxe (explicit_central)");
   // conschm: central (= difschm, comsolver.F90:94-101) or 543c, the upwind compact scheme (convrsdcmp)
-  if (cfg->conschm != cfg->difschm && cfg->conschm != 543)
-    return astr_fail_msg("conschm must equal difschm (central) or be 543c (upwind compact)");
+  if (cfg->conschm_explicit) {
+    // conschm '<odd>..e': convrsduwd with recons_exp; the reference stops for npdcj/npdck == 4 (solver.F90:810-821)
+    if ((cfg->conschm / 100) % 2 != 1) return astr_fail_msg("conschm_explicit needs an odd leading digit (upwind-biased)");
+    const int rs = cfg->recon_schem;
+    if (!(rs == -1 || rs == 0 || rs == 1 || rs == 2 || rs == 3 || rs == 5 || rs == 6))
+      return astr_fail_msg("recon_schem must be -1, 0, 1, 2, 3, 5 or 6 (src/flux.F90:269-350)");
+    if (cfg->npdc[1] == 4 || (cfg->ndims == 3 && cfg->npdc[2] == 4))
+      return astr_fail_msg("convrsduwd stops for npdcj/npdck == 4 (src/solver.F90:810-821, :1002-1013)");
+  } else if (cfg->conschm != cfg->difschm && cfg->conschm != 543)
+    return astr_fail_msg("conschm must equal difschm (central), be 543c (upwind compact) or an explicit upwind scheme");
   if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
   for (int d = 0; d < 3; ++d)
     if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
@@ -582,7 +590,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
     build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
     TRY(astr_sweep2_set_plan(d, OP_DERIV, g->fd[d].plan, g->fc));
     TRY(astr_sweep2_set_plan(d, OP_FILTER, g->fl[d].plan, g->fc));
-    if (g->upwind()) {
+    if (g->upwind() && !cfg->conschm_explicit) {
       build_flux(g->fxp[d], OP_FLUXP, cfg->npdc[d], n, cfg->bfacmpld);
       build_flux(g->fxm[d], OP_FLUXM, cfg->npdc[d], n, cfg->bfacmpld);
     }
@@ -707,7 +715,7 @@ static int api_slot(int field_id, int* slot) {
 int astr_gpu_get_field(int field_id, double* host) {
   NEED_CTX();
   if (field_id == ASTR_F_SSF || field_id == ASTR_F_LSHOCK) {
-    if (!g->up || !g->cfg.lchardecomp) return astr_fail_msg("ssf/lshock exist only with conschm 543 and lchardecomp");
+    if (!g->up) return astr_fail_msg("ssf/lshock exist only on the upwind convection paths");
     TRY(copy_dev(g->up + (size_t)(field_id == ASTR_F_SSF ? UP_SSF : UP_LSH) * g->L.fstride, host, true));
     CUDA_OK(cudaStreamSynchronize(g->st));
     return 0;
@@ -961,9 +969,16 @@ static int convrsdcmp_dir(int d, int dst0, int rmw_mask) {
   ua.box.lo[d] = s[d] - 1;
   ua.lss = (nt == 1 || nt == 4) ? 0 : -ASTR_HM;           // solver.F90:1313-1327
   ua.lee = (nt == 2 || nt == 4) ? dm : dm + ASTR_HM;
-  ua.dim = dm; ua.ntype = nt; ua.lchardecomp = c.lchardecomp; ua.sson = c.lchardecomp;
+  ua.dim = dm; ua.ntype = nt; ua.lchardecomp = c.lchardecomp;
+  ua.explicit_recons = c.conschm_explicit; ua.recon_schem = c.recon_schem; ua.bfacmpld = c.bfacmpld;
+  // lshock exists (`allocated(lshock)`) exactly when ducrossensor runs (solver.F90:221,225)
+  ua.sson = c.conschm_explicit ? (c.recon_schem == 5 || c.lchardecomp) : c.lchardecomp;
   ProfScope ps(PC_DIV_I + d);
   TRY(uw_sw_split(L, g->pool, g->up, g->th, d, ua.lss, ua.lee, g->st));
+  if (c.conschm_explicit) {          // convrsduwd: no compact flux solves
+    TRY(uw_interface_flux(L, g->pool, g->up, g->th, d, ua, g->st));
+    return uw_fhdiff(L, g->pool, g->up, d, ua, dst0, rmw_mask, g->st);
+  }
   const double* in[5]; double* out[5];
   for (int m = 0; m < 5; ++m) { in[m] = g->up + (size_t)(UP_FSW + m) * L.fstride; out[m] = g->up + (size_t)(UP_FHC + m) * L.fstride; }
   TRY(sweep(d, OP_FLUXP, in, out, 5, EPI_STORE, -1, dm));
@@ -983,7 +998,8 @@ int astr_gpu_rhscal(void) {
   if (upw) {
     // the convective part comes from convrsdcmp: the G slots carry the viscous fluxes only
     for (int d = 0; d < 3; ++d) { fr.s[d] = 1; fr.e[d] = 0; }
-    if (c.lchardecomp) TRY(astr_gpu_ducrossensor());     // solver.F90:225
+    // solver.F90:221 (explicit: recon_schem==5 .or. lchardecomp), :225 (compact: lchardecomp)
+    if (c.lchardecomp || (c.conschm_explicit && c.recon_schem == 5)) TRY(astr_gpu_ducrossensor());
   }
   if (c.diffterm) {
     const bool multi = c.size[0] * c.size[1] * c.size[2] > 1;

@@ -121,6 +121,9 @@ struct UpwindArgs {
   int lss, lee;         // node range of the split fluxes along the direction (solver.F90:1313-1327)
   int dim, ntype;       // im/jm/km and npdc of the direction
   int lchardecomp, sson;
+  int explicit_recons;  // 1: convrsduwd (explicit reconstruction recons_exp), 0: convrsdcmp (compact flux)
+  int recon_schem;      // recons_exp scheme: -1, 0 (linear), 1 WENO, 2 WENO-Z, 3 MP, 5 MP-LD, 6 ROUND
+  double bfacmpld;
 };
 int uw_sw_split(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, int lss, int lee,
                 cudaStream_t st);

@@ -145,6 +145,8 @@ __device__ __forceinline__ double mp5(const double (&u)[5], const double ulinear
   return ulinear;
 }
 
+#include "recons.cuh"
+
 // ---------------------------------------------------------------------------------
 // chardecomp (src/solver.F90:1958-2162), without COMB.  Returns false where the reference
 // stops (degenerate metric normal).
@@ -317,6 +319,81 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
   for (int m = 0; m < 5; ++m) up[(UP_FH + m) * fs + x] = Fh[m];
 }
 
+// ---------------------------------------------------------------------------------
+// interface loop of convrsduwd (src/solver.F90:622-790 and the j/k copies): 8-node stencils, explicit
+// reconstruction recons_exp, characteristic projection only where lchardecomp and the interface is flagged
+// ---------------------------------------------------------------------------------
+template <int DIR>
+__global__ void k_upwind_exp(const Layout L, const double* __restrict__ pool, double* __restrict__ up, const Thermo th,
+                             const UpwindArgs a) {
+  int ijk[3];
+  if (!box_node(a.box, ijk[0], ijk[1], ijk[2])) return;
+  const long long fs = L.fstride, x = L.idx(ijk[0], ijk[1], ijk[2]);
+  const long long sd = (DIR == 0) ? 1 : (DIR == 1 ? L.sj : L.sk);
+  const int i = ijk[DIR];
+  bool lsh = true;                      // solver.F90:640-650
+  if (a.sson) {
+    const double* ls = up + UP_LSH * fs + x;
+    if (i < 0) lsh = ls[sd] != 0.0;
+    else if (i + 1 > a.dim) lsh = ls[0] != 0.0;
+    else lsh = (ls[0] != 0.0) || (ls[sd] != 0.0);
+  }
+  const bool chr = a.lchardecomp && lsh;
+  Eig e;
+  if (chr) {
+    const long long xr = x + sd;
+    const double vl[3] = {pool[(S_VEL + 0) * fs + x], pool[(S_VEL + 1) * fs + x], pool[(S_VEL + 2) * fs + x]};
+    const double vr[3] = {pool[(S_VEL + 0) * fs + xr], pool[(S_VEL + 1) * fs + xr], pool[(S_VEL + 2) * fs + xr]};
+    const double dl[3] = {pool[(S_DXI + 3 * DIR + 0) * fs + x], pool[(S_DXI + 3 * DIR + 1) * fs + x],
+                          pool[(S_DXI + 3 * DIR + 2) * fs + x]};
+    const double dr[3] = {pool[(S_DXI + 3 * DIR + 0) * fs + xr], pool[(S_DXI + 3 * DIR + 1) * fs + xr],
+                          pool[(S_DXI + 3 * DIR + 2) * fs + xr]};
+    if (!chardecomp(th.gamma, pool[S_RHO * fs + x], pool[S_PRS * fs + x], pool[(S_Q + 4) * fs + x], vl, dl,
+                    pool[S_RHO * fs + xr], pool[S_PRS * fs + xr], pool[(S_Q + 4) * fs + xr], vr, dr, e)) {
+#pragma unroll
+      for (int m = 0; m < 5; ++m) up[(UP_FH + m) * fs + x] = __longlong_as_double(0x7ff8000000000000LL);
+      return;
+    }
+  }
+  // stencil node offsets, clamped to lss..lee (iwind8, solver.F90:1213-1234)
+  long long op[8], om[8];
+#pragma unroll
+  for (int n = 1; n <= 8; ++n) {
+    op[n - 1] = (long long)(iwind8(i, n, a.lss, a.lee, '+') - i) * sd;
+    om[n - 1] = (long long)(iwind8(i, n, a.lss, a.lee, '-') - i) * sd;
+  }
+  double Fhc[5];
+#pragma unroll 1
+  for (int m = 0; m < 5; ++m) {
+    double cp[8], cm[8];
+    if (chr) {
+      const double l0 = e.Lm[m][0], l1 = e.Lm[m][1], l2 = e.Lm[m][2], l3 = e.Lm[m][3], l4 = e.Lm[m][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const double* fp = up + UP_FSW * fs + x + op[n];
+        const double* fm = up + (UP_FSW + 5) * fs + x + om[n];
+        cp[n] = l0 * fp[0] + l1 * fp[fs] + l2 * fp[2 * fs] + l3 * fp[3 * fs] + l4 * fp[4 * fs];
+        cm[n] = l0 * fm[0] + l1 * fm[fs] + l2 * fm[2 * fs] + l3 * fm[3 * fs] + l4 * fm[4 * fs];
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        cp[n] = up[(UP_FSW + m) * fs + x + op[n]];
+        cm[n] = up[(UP_FSW + 5 + m) * fs + x + om[n]];
+      }
+    }
+    const double v1 = recons_exp(cp, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
+    const double v2 = recons_exp(cm, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
+    Fhc[m] = v1 + v2;
+  }
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    double r = Fhc[m];
+    if (chr) r = e.R[m][0] * Fhc[0] + e.R[m][1] * Fhc[1] + e.R[m][2] * Fhc[2] + e.R[m][3] * Fhc[3] + e.R[m][4] * Fhc[4];
+    up[(UP_FH + m) * fs + x] = r;
+  }
+}
+
 // qrhs(i) += Fh(i) - Fh(i-1) on is..ie (solver.F90:1494-1498), then qrhs = -qrhs (:242): the G slot
 // of direction DIR, which already holds the viscous derivative (or nothing), gets -(Fh(i)-Fh(i-1))
 // dst0: first of the 5 destination slots (the G slots of the direction, or qrhs on the explicit
@@ -431,7 +508,11 @@ int uw_sw_split(const Layout& L, const double* pool, double* up, const Thermo& t
 int uw_interface_flux(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, const UpwindArgs& a,
                       cudaStream_t st) {
   if (box_empty(a.box)) return 0;
-  if (dir == 0) k_upwind<0><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+  if (a.explicit_recons) {
+    if (dir == 0) k_upwind_exp<0><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+    else if (dir == 1) k_upwind_exp<1><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+    else k_upwind_exp<2><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
+  } else if (dir == 0) k_upwind<0><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
   else if (dir == 1) k_upwind<1><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
   else k_upwind<2><<<box_grid(a.box), UW_T, 0, st>>>(L, pool, up, th, a);
   LAUNCH_CHECK_UW();

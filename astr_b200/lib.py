@@ -60,7 +60,7 @@ class AstrCfg(ctypes.Structure):
         ("conschm", ctypes.c_int), ("difschm", ctypes.c_int), ("scheme_compact", ctypes.c_int),
         ("rkscheme", ctypes.c_int), ("lfilter", ctypes.c_int), ("diffterm", ctypes.c_int),
         ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int),
-        ("recon_schem", ctypes.c_int), ("lchardecomp", ctypes.c_int), ("bctype", ctypes.c_int * 6),
+        ("recon_schem", ctypes.c_int), ("conschm_explicit", ctypes.c_int), ("lchardecomp", ctypes.c_int), ("bctype", ctypes.c_int * 6),
         ("alfa_filter", ctypes.c_double),
         ("reynolds", ctypes.c_double), ("mach", ctypes.c_double), ("prandtl", ctypes.c_double),
         ("gamma", ctypes.c_double), ("ref_tem", ctypes.c_double),

@@ -62,7 +62,8 @@ class RhsEngine:
                  deltat: float = 1e-3, alfa_filter: float = 0.49, lfilter: bool = True, diffterm: bool = True,
                  device: int = -1, flowtype: int = 0, bctype: Sequence[int] = (1,) * 6,
                  twall: Sequence[float] = (0.0,) * 6, explicit: bool = False, conschm: Optional[int] = None,
-                 lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3):
+                 lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
+                 conschm_explicit: bool = False):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -87,6 +88,7 @@ class RhsEngine:
         if conschm is not None:      # e.g. 543: upwind compact convection (convrsdcmp) over difschm
             c.conschm = int(conschm)
         c.recon_schem, c.lchardecomp, c.bfacmpld, c.shkcrt = int(recon_schem), int(lchardecomp), bfacmpld, shkcrt
+        c.conschm_explicit = int(conschm_explicit)      # conschm '<odd>..e': convrsduwd + recons_exp
         c.lfilter, c.diffterm, c.nondimen, c.flowtype = int(lfilter), int(diffterm), int(thermo.get("nondimen", 1)), flowtype
         c.bctype[:] = [int(b) for b in bctype]
         c.twall[:] = [float(t) for t in twall]

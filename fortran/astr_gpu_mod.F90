@@ -29,7 +29,7 @@ module astr_gpu_mod
     integer(c_int) :: my_rank
     integer(c_int) :: conschm,difschm,scheme_compact,rkscheme
     integer(c_int) :: lfilter,diffterm,nondimen,flowtype
-    integer(c_int) :: recon_schem,lchardecomp
+    integer(c_int) :: recon_schem,conschm_explicit,lchardecomp
     integer(c_int) :: bctype(6)
     real(c_double) :: alfa_filter
     real(c_double) :: reynolds,mach,prandtl,gamma,ref_tem
@@ -219,6 +219,7 @@ module astr_gpu_mod
     cfg%nondimen=1; cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall
     cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
+    cfg%conschm_explicit=merge(1,0,conschm(4:4)=='e' .and. mod(cfg%conschm/100,2)==1)
     cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt; cfg%pinf=pinf
     cfg%alfa_filter=alfa_filter
     cfg%reynolds=reynolds; cfg%mach=mach; cfg%prandtl=prandtl; cfg%gamma=gamma; cfg%ref_tem=ref_tem

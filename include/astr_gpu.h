@@ -63,7 +63,10 @@ typedef struct astr_cfg {
                                  src/solver.F90:124-128 (mach, reynolds, const1..7, pinf
                                  as refcal leaves them)                                  */
   int flowtype;               /* 0 = tgv / generic (no source), 1 = channel (src_chan)   */
-  int recon_schem;            /* input-file `recon_schem` (unused by conschm '543c')     */
+  int recon_schem;            /* input-file `recon_schem`: scheme of recons_exp for the
+                                 explicit family (-1, 0, 1, 2, 3, 5, 6; flux.F90:269-350) */
+  int conschm_explicit;       /* conschm(4:4)=='e' with an odd first digit: convrsduwd
+                                 (src/solver.F90:548); 0: '543c' / central                */
   int lchardecomp;            /* characteristic decomposition + Ducros sensor on/off     */
   int bctype[6];              /* bctype(1:6) of the input file: imin,imax,jmin,jmax,kmin,
                                  kmax (src/bc.F90:327-407 boucon).  On the device:

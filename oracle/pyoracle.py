@@ -36,7 +36,8 @@ FIELD_IDS = {
 
 def build(force: bool = False) -> str:
     """Compile oracle/*.cpp into libastr_oracle.so (g++, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lineops.cpp", "miniapp.cpp", "solver.cpp", "astr_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("lineops.cpp", "miniapp.cpp", "solver.cpp", "astr_oracle.hpp", "upwind.hpp",
+                                             "recons.hpp")]
     if not force and os.path.exists(_LIB):
         if all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in srcs):
             return _LIB
@@ -100,6 +101,11 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_pinf.restype = cd
         L.oracle_case_set_scheme.argtypes = [vp, ci]
         L.oracle_case_set_upwind.argtypes = [vp, ci, ci, cd, cd]
+        L.oracle_case_set_upwind_explicit.argtypes = [vp, ci, ci, cd, cd]
+        L.oracle_case_convrsduwd.argtypes = [vp]
+        L.oracle_case_convrsduwd.restype = ci
+        L.oracle_recons_exp.argtypes = [vp, ci, ci, ci, ci, ci, cd]
+        L.oracle_recons_exp.restype = cd
         L.oracle_case_ducrossensor.argtypes = [vp]
         L.oracle_case_convrsdcmp.argtypes = [vp]
         L.oracle_case_convrsdcmp.restype = ci
@@ -157,6 +163,13 @@ def flux_compact(f: np.ndarray, ntype: int, plus: bool, bfacmpld: float = 0.3) -
     out = np.empty(dim + 2)
     lib().oracle_flux_compact(ntype, dim, int(plus), bfacmpld, f.ctypes.data, out.ctypes.data)
     return out
+
+
+def recons_exp(f8, inode: int, dim: int, ntype: int, reschem: int, shock: bool = True, bfacmpld: float = 0.3) -> float:
+    """recons_exp(f(1:8), ...) of src/flux.F90:269-350 (interface between f(4) and f(5))."""
+    f = np.ascontiguousarray(f8, dtype=np.float64)
+    assert f.size == 8
+    return lib().oracle_recons_exp(f.ctypes.data, inode, dim, ntype, reschem, int(shock), bfacmpld)
 
 
 def mp5(u5, ul: float, discont: bool = True) -> float:
@@ -279,6 +292,14 @@ class Case:
     def set_upwind(self, conschm: int = 543, lchardecomp: bool = True, bfacmpld: float = 0.3, shkcrt: float = 0.01):
         """conschm='543c' (convrsdcmp) with the input file's `recon_schem, lchardecomp, bfacmpld, shkcrt`."""
         lib().oracle_case_set_upwind(self._h, int(conschm), int(lchardecomp), float(bfacmpld), float(shkcrt))
+
+    def set_upwind_explicit(self, recon_schem: int = 3, lchardecomp: bool = True, bfacmpld: float = 0.3,
+                            shkcrt: float = 0.01):
+        """conschm='<odd>..e' (convrsduwd, src/solver.F90:548) with `recon_schem` of recons_exp."""
+        lib().oracle_case_set_upwind_explicit(self._h, int(recon_schem), int(lchardecomp), float(bfacmpld), float(shkcrt))
+
+    def convrsduwd(self) -> int:
+        return lib().oracle_case_convrsduwd(self._h)
 
     def ducrossensor(self):
         lib().oracle_case_ducrossensor(self._h)

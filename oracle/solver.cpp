@@ -54,6 +54,8 @@ struct Case {
   // conschm: 643 central (convrsdcal6) or 543 upwind compact (convrsdcmp); input-file line
   // `recon_schem, lchardecomp, bfacmpld, shkcrt` (src/readwrite.F90)
   int conschm = 643;
+  bool conschm_explicit = false;   // conschm(4:4)=='e' with an odd first digit: convrsduwd (solver.F90:220-223)
+  int recon_schem = 3;             // reconstruction scheme of recons_exp (flux.F90:269-350)
   bool lchardecomp = false;
   double bfacmpld = 0.3, shkcrt = 0.01;
   int bctype[6] = {1, 1, 1, 1, 1, 1};      // src/readwrite.F90 bctype(1:6): imin,imax,jmin,jmax,kmin,kmax
@@ -671,6 +673,7 @@ static void diffrsdcal6(Case& c) {
 }
 
 #include "upwind.hpp"
+#include "recons.hpp"
 
 // src/solver.F90:295-353 src_chan: bulk velocities by trapezoidal integration in y over
 // nodes 1..im,1..jm,1..km of every rank (psum = sum over blocks), then the body force
@@ -708,7 +711,10 @@ static void src_chan(Case& c) {
 // src/solver.F90:185-282 rhscal (conschm even -> central; flowtype channel adds src_chan :262)
 static void rhscal(Case& c) {
   if ((c.conschm / 100) % 2 == 0) convrsdcal6(c);      // :216-218
-  else {                                               // conschm(4:4)=='c', :224-226
+  else if (c.conschm_explicit) {                       // conschm(4:4)=='e', :220-223
+    if (c.recon_schem == 5 || c.lchardecomp) ducrossensor(c);
+    convrsduwd(c);
+  } else {                                             // conschm(4:4)=='c', :224-226
     if (c.lchardecomp) ducrossensor(c);
     convrsdcmp(c);
   }
@@ -1226,7 +1232,18 @@ void oracle_case_set_flow(void* h, int flowtype, const double* force) {
 // conschm digits (643 / 543) and the upwind parameters lchardecomp, bfacmpld, shkcrt
 void oracle_case_set_upwind(void* h, int conschm, int lchardecomp, double bfacmpld, double shkcrt) {
   Case* c = static_cast<Case*>(h);
-  c->conschm = conschm; c->lchardecomp = lchardecomp != 0; c->bfacmpld = bfacmpld; c->shkcrt = shkcrt;
+  c->conschm = conschm; c->conschm_explicit = false;
+  c->lchardecomp = lchardecomp != 0; c->bfacmpld = bfacmpld; c->shkcrt = shkcrt;
+}
+// explicit upwind family: conschm='<odd>..e' with recon_schem (-1, 0, 1, 2, 3, 5, 6)
+void oracle_case_set_upwind_explicit(void* h, int recon_schem, int lchardecomp, double bfacmpld, double shkcrt) {
+  Case* c = static_cast<Case*>(h);
+  c->conschm = 753; c->conschm_explicit = true; c->recon_schem = recon_schem;
+  c->lchardecomp = lchardecomp != 0; c->bfacmpld = bfacmpld; c->shkcrt = shkcrt;
+}
+int oracle_case_convrsduwd(void* h) { return convrsduwd(*static_cast<Case*>(h)); }
+double oracle_recons_exp(const double* f8, int inode, int dim, int ntype, int reschem, int shock, double bfacmpld) {
+  return recons_exp(f8, inode, dim, ntype, reschem, shock != 0, bfacmpld);
 }
 void oracle_case_ducrossensor(void* h) { ducrossensor(*static_cast<Case*>(h)); }
 int oracle_case_convrsdcmp(void* h) { return convrsdcmp(*static_cast<Case*>(h)); }

@@ -192,7 +192,12 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
                      shkcrt=upwind.get("shkcrt", 0.01))
         if up_kw["shkcrt"] == "auto":
             up_kw["shkcrt"] = auto_shkcrt(c, up_kw["bfacmpld"], upwind.get("quantile", 0.5))
-        c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
+        if "recon_schem" in upwind:
+            # conschm='753e': the explicit upwind family (convrsduwd + recons_exp, src/solver.F90:548)
+            up_kw.update(conschm=753, conschm_explicit=True, recon_schem=upwind["recon_schem"])
+            c.set_upwind_explicit(upwind["recon_schem"], up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
+        else:
+            c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
     block = decompose(n, (1, 1, 1), homo)[0]
     eng = RhsEngine(block, n, homo, th, deltat=deltat, lfilter=lfilter, diffterm=diffterm, device=0,
                     flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw)

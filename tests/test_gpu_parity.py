@@ -191,6 +191,28 @@ def test_rhscal_upwind_inviscid(oracle):
     eng.close(); c.close()
 
 
+@pytest.mark.parametrize("recon_schem", [-1, 0, 1, 2, 3, 5, 6])
+@pytest.mark.parametrize("lchardecomp", [True, False])
+def test_explicit_upwind_family(oracle, recon_schem, lchardecomp):
+    # conschm='753e': convrsduwd (src/solver.F90:548-1201) with every reconstruction recons_exp offers
+    # (src/flux.F90:269-350): linear upwind, WENO, WENO-Z, MP, MP-LD, ROUND; walls in i exercise the
+    # near-boundary scheme ladder (ntype 1/2 need two blocks: see the multi-GPU test), periodic j, k
+    c, eng = make_pair(oracle, n=(36, 32, 24), homo=(False, True, True), stretch=True, perturb=1e-2,
+                       upwind=dict(lchardecomp=lchardecomp, shkcrt="auto", recon_schem=recon_schem))
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    # WENO weights divide by (beta+1e-6)^2 and ROUND by a1c^4, a2c^8: smooth but stiff functions of the data
+    tol = 2e-10 if recon_schem in (1, 2, 6) else UPWIND_TOL
+    assert_fields_close(c, eng, QRHS, tol, what=f"convrsduwd recon_schem={recon_schem}")
+    if lchardecomp or recon_schem == 5:
+        np.testing.assert_array_equal(core(eng.get("lshock")), core(c.get("lshock")))
+    for rk in (1, 2):
+        c.rk_stage(rk); eng.rk_stage(rk)
+    assert np.isfinite(core(c.get("q5"))).all()
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="2 rk stages, explicit upwind")
+    eng.close(); c.close()
+
+
 def test_rhscal_inviscid(oracle):
     c, eng = make_pair(oracle, n=(32, 32, 32), diffterm=False)
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()

@@ -130,3 +130,70 @@ def test_upwind_run_is_stable_and_close_to_central(oracle):
     ha, hb = a.history(), b.history()
     assert np.isfinite(hb).all() and np.abs(ha[:, 2] - hb[:, 2]).max() < 1e-5
     a.close(); b.close()
+
+
+# ---- explicit upwind family (oracle/recons.hpp) ---------------------------------------------------
+def _poly_window(deg, rng):
+    """point values f(j) of the derivative of a random polynomial primitive P of degree deg+1 on the 8
+    nodes -3..4; a reconstruction that is exact for degree `deg` returns P(1/2)-P(-1/2) for the interface
+    between nodes 0 and 1 (flux form: f(j) = P(j+1/2)-P(j-1/2))."""
+    coef = rng.standard_normal(deg + 2)
+    P = np.polynomial.Polynomial(coef)
+    j = np.arange(-3, 5)
+    f = P(j + 0.5) - P(j - 0.5)
+    return f, P.deriv()(0.5)
+
+
+@pytest.mark.parametrize("reschem,deg", [(0, 6), (3, 6), (5, 6)])
+def test_linear_parts_of_the_explicit_schemes_are_exact_for_polynomials(oracle, reschem, deg):
+    # suw7 (7th order), MP7 and MP7LD without limiting reproduce the flux-form identity for degree <= 6
+    # (MP7LD with weight 1 is the 8th-order central scheme: degree 7)
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        f, want = _poly_window(deg, rng)
+        # scale down the non-linear content so that the MP switch stays off: (ul-u3)(ul-uMP) < 1e-10
+        f = 1.0 + 1e-6 * f
+        got = oracle.recons_exp(f, 10, 64, 3, reschem, shock=False, bfacmpld=0.3)
+        assert abs(got - (1.0 + 1e-6 * want)) < 1e-13
+
+
+def test_mp7ld_weight_one_is_the_eighth_order_central_scheme(oracle):
+    rng = np.random.default_rng(4)
+    f, want = _poly_window(7, rng)
+    got = oracle.recons_exp(f, 10, 64, 3, 5, shock=False, bfacmpld=1.0)
+    assert abs(got - want) < 1e-11 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("reschem", [1, 2])
+def test_weno_weights_are_convex_and_order_is_high(oracle, reschem):
+    errs = []
+    for n in (16, 32):
+        x = 2 * np.pi * np.arange(-6, n + 8) / n
+        f = np.sin(x)
+        fh = np.array([oracle.recons_exp(f[i + 3:i + 11], i, n, 3, reschem) for i in range(-1, n + 1)])
+        d = (fh[1:] - fh[:-1]) * n / (2 * np.pi)
+        errs.append(np.abs(d - np.cos(x[6:6 + n + 1])).max())
+    assert errs[0] / errs[1] > 2 ** 4
+    step = np.array([0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0])
+    assert -1e-3 < oracle.recons_exp(step, 10, 64, 3, reschem) < 1.0 + 1e-3     # essentially non-oscillatory
+
+
+def test_recons_exp_boundary_ladder(oracle):
+    # flux.F90:276-296: first interface of an ntype-1 block is the plain average, the second SUW3
+    f = np.arange(8, dtype=float) ** 2
+    assert oracle.recons_exp(f, 0, 64, 1, 3) == 0.5 * (f[3] + f[4])
+    assert abs(oracle.recons_exp(f, 1, 64, 1, 3) - (-f[2] / 6 + 5 * f[3] / 6 + f[4] / 3)) < 1e-14
+    assert oracle.recons_exp(f, 63, 64, 2, 3) == 0.5 * (f[3] + f[4])
+    assert oracle.recons_exp(f, 5, 64, 1, -1) == f[3]
+    assert np.isnan(oracle.recons_exp(f, 5, 64, 3, 4))          # the reference stops on reschem 4
+
+
+def test_convrsduwd_linear_scheme_matches_central_to_truncation(oracle):
+    n = 32
+    a, b = oracle.Case(n, n, n), oracle.Case(n, n, n)
+    b.set_upwind_explicit(0, False, 0.3, 1.0)
+    for c in (a, b):
+        c.gridgeom(); c.tgvini(); c.qswap(); c.gradcal(); c.zero_qrhs(); c.rhscal()
+    ra, rb = a.get("qrhs5")[5:-5, 5:-5, 5:-5], b.get("qrhs5")[5:-5, 5:-5, 5:-5]
+    assert 0.0 < np.abs(ra - rb).max() < 0.05 * np.abs(ra).max()
+    a.close(); b.close()
