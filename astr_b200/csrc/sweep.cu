@@ -602,6 +602,191 @@ int launch_one(const SweepArgs& a, cudaStream_t st) {
   return 0;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Warp-per-line engine for the i direction (the line is contiguous in memory).
+// A warp owns one line: coalesced 16-byte loads bring nodes -6..n+5 into a per-warp shared line buffer,
+// lane c then owns rows [chunk32_start(c), chunk32_start(c+1)) (<= 17) in REGISTERS: right-hand sides from
+// a rotating window over the buffer (one LDS per row), forward and backward recurrences of the reference
+// (src/commfunc.F90:790-813) with zero carries, the true carries from two warp-level scans of affine maps
+// (5 shuffle steps each) instead of block barriers, solution back into the buffer and out with coalesced
+// 16-byte stores.  No CTA-level synchronisation inside the line loop: warps are independent, so the SM
+// hides latency with 16 warps of independent lines.  Same tables, closures and epilogues as above.
+// -------------------------------------------------------------------------------------------------
+constexpr int W3_WARPS = 8;           // warps per CTA
+constexpr int W3_PADF = 8;            // buffer index = node + W3_PADF (window reads of closure rows may reach node -8)
+
+template <int OP>
+__global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArgs a) {
+  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
+  constexpr int LCH = ASTR_W3_LCH;
+  extern __shared__ __align__(16) double sm_all[];
+  const int n = a.op.n, nrows = a.op.nrows, first_node = a.op.first_node;
+  const int nr8 = (nrows + 1) & ~1;
+  const double* __restrict__ ac1 = sm_all;
+  const double* __restrict__ ac2 = sm_all + nr8;
+  const double* __restrict__ ac3 = sm_all + 2 * nr8;
+  const double* __restrict__ pf = sm_all + 3 * nr8;
+  const double* __restrict__ qb = sm_all + 4 * nr8;
+  const int lbn = (n + 2 * W3_PADF + 2 + 1) & ~1;         // doubles per line buffer (even)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* LB = sm_all + 5 * nr8 + (size_t)warp * lbn;     // LB[node + W3_PADF] = f(node)
+  for (int r = threadIdx.x; r < nrows; r += W3_WARPS * 32) {
+    sm_all[r] = a.op.ac1[r];
+    sm_all[nr8 + r] = a.op.ac2[r];
+    sm_all[2 * nr8 + r] = a.op.ac3[r];
+    sm_all[3 * nr8 + r] = a.op.pf32[r];
+    sm_all[4 * nr8 + r] = a.op.qb32[r];
+  }
+  // window reads of closure rows may touch the pads: keep them finite
+  for (int t = lane; t < lbn; t += 32) LB[t] = 0.0;
+  __syncthreads();
+
+  const Layout& L = a.L;
+  const int ra = chunk32_start(lane, nrows), rb = chunk32_start(lane + 1, nrows) - 1;
+  const int nsf = a.op.nsf, nsl = a.op.nsl;
+  const int epi = a.epi, o_lo = a.o_lo, o_hi = a.o_hi;
+  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
+  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
+  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
+  const long long wstride = (long long)gridDim.x * W3_WARPS;
+  const int npair = (n + 13) >> 1;                         // node pairs -6.. (n+5 or n+6)
+  auto F = [&](int node) -> double { return LB[node + W3_PADF]; };
+
+  for (long long ln = (long long)blockIdx.x * W3_WARPS + warp; ln < nlines; ln += wstride) {
+    const int j = (int)(ln % (L.jm + 1));
+    const int k = (int)((ln / (L.jm + 1)) % (L.km + 1));
+    const int f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
+    const double* __restrict__ grow = a.in[f] + L.idx(0, j, k);
+    double* __restrict__ orow = a.out[f] + L.idx(0, j, k);
+    // ---- line -> buffer (node -6 is 16-byte aligned in global memory; W3_PADF - 6 is even) ----------------
+    for (int w = lane; w < npair; w += 32)
+      *reinterpret_cast<double2*>(LB + (W3_PADF - 6) + 2 * w) = *reinterpret_cast<const double2*>(grow - 6 + 2 * w);
+    __syncwarp();
+    // ---- right-hand sides and forward elimination with zero carry-in ---------------------------------
+    double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
+    if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
+    if (lane == 31) closure_last<OP>(F, a.op.ntype, n, sl);
+    double e[LCH];
+    double w[W];
+    {
+      const double* p = LB + W3_PADF + first_node + ra - H;
+#pragma unroll
+      for (int s = 0; s < 2 * H; ++s) w[s] = p[s];
+      w[2 * H] = 0.0;
+    }
+    double eprev = 0.0;
+#pragma unroll
+    for (int s = 0; s < LCH; ++s) {
+      const int r = ra + s;
+      if (r <= rb) {
+        w[(s + 2 * H) % W] = LB[W3_PADF + first_node + r + H];
+        double d = interior_rhs<OP>(w, s);
+        if (lane == 0 && s < nsf) d = sf[s < 5 ? s : 4];
+        if (lane == 31 && r >= nrows - nsl) {
+          const int kk = r - (nrows - nsl);
+          d = kk == 0 ? sl[0] : kk == 1 ? sl[1] : kk == 2 ? sl[2] : kk == 3 ? sl[3] : sl[4];
+        }
+        const double ev = __fma_rn(-eprev, ac3[r], d * ac2[r]);
+        e[s] = ev;
+        eprev = ev;
+      } else {
+        e[s] = 0.0;
+      }
+    }
+    // ---- carry into each chunk: d'(ra-1) = EE(c-1) + pf(rb(c-1)) * d'(ra(c-1)-1)  (exclusive scan of x -> A x + B) --
+    double cin;
+    {
+      double A = pf[rb], B = eprev;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double Ap = __shfl_up_sync(0xffffffffu, A, off), Bp = __shfl_up_sync(0xffffffffu, B, off);
+        if (lane >= off) { B = __fma_rn(A, Bp, B); A = A * Ap; }
+      }
+      cin = __shfl_up_sync(0xffffffffu, B, 1);
+      if (lane == 0) cin = 0.0;
+    }
+    // ---- back substitution with zero carry-in ---------------------------------------------------------
+    double gnext = 0.0;
+#pragma unroll
+    for (int s = LCH - 1; s >= 0; --s) {
+      const int r = ra + s;
+      if (r <= rb) {
+        const double dp = __fma_rn(pf[r], cin, e[s]);
+        const double g = __fma_rn(-ac1[r], gnext, dp);
+        e[s] = g;
+        gnext = g;
+      }
+    }
+    // ---- x(rb+1) of each chunk: x(ra(c)) = GS(c) + qb(ra(c)) * x(rb(c)+1)  (suffix scan from the last chunk) -----
+    double xin;
+    {
+      double A = qb[ra], B = gnext;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double Ap = __shfl_down_sync(0xffffffffu, A, off), Bp = __shfl_down_sync(0xffffffffu, B, off);
+        if (lane + off < 32) { B = __fma_rn(A, Bp, B); A = A * Ap; }
+      }
+      xin = __shfl_down_sync(0xffffffffu, B, 1);
+      if (lane == 31) xin = 0.0;
+    }
+    __syncwarp();                      // every lane is done reading the pristine line
+#pragma unroll
+    for (int s = 0; s < LCH; ++s) {
+      const int r = ra + s;
+      if (r <= rb) LB[W3_PADF + first_node + r] = __fma_rn(qb[r], xin, e[s]);
+    }
+    __syncwarp();
+    // ---- buffer -> global, aligned node pairs, epilogue ------------------------------------------------
+    for (int nd = (w_lo & ~1) + 2 * lane; nd <= w_hi; nd += 64) {
+      const bool vx = nd >= w_lo, vy = nd + 1 <= w_hi;
+      double2 x = *reinterpret_cast<const double2*>(LB + W3_PADF + nd);
+      if (epi == EPI_ADD) {
+        if (vx) x.x = orow[nd] + x.x;
+        if (vy) x.y = orow[nd + 1] + x.y;
+      } else if (epi == EPI_STOREZ) {
+        if (nd < o_lo || nd > o_hi) x.x = 0.0;
+        if (nd + 1 < o_lo || nd + 1 > o_hi) x.y = 0.0;
+      }
+      if (vx && vy) *reinterpret_cast<double2*>(orow + nd) = x;
+      else if (vx) orow[nd] = x.x;
+      else if (vy) orow[nd + 1] = x.y;
+    }
+    __syncwarp();                      // the buffer is overwritten by the next line
+  }
+}
+
+template <int OP>
+int launch3(const SweepArgs& a, cudaStream_t st) {
+  auto kern = sweep3_kernel<OP>;
+  const int nr8 = (a.op.nrows + 1) & ~1;
+  const int lbn = (a.op.n + 2 * W3_PADF + 2 + 1) & ~1;
+  const size_t smem = ((size_t)5 * nr8 + (size_t)W3_WARPS * lbn) * sizeof(double);
+  static size_t attr_smem = 0;
+  static int occ = 0;
+  if (smem > attr_smem || occ == 0) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_smem = smem;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W3_WARPS * 32, smem));
+    if (occ < 1) return astr_fail_msg("sweep3: kernel does not fit on an SM");
+    if (!g_num_sms) {
+      int dev = 0;
+      CUDA_OK(cudaGetDevice(&dev));
+      CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+  }
+  const Layout& L = a.L;
+  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
+  long long grid = (long long)g_num_sms * occ;
+  const long long need = (nlines + W3_WARPS - 1) / W3_WARPS;
+  if (grid > need) grid = need;
+  kern<<<(unsigned)grid, W3_WARPS * 32, smem, st>>>(a);
+  astr_count_launch();
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <int DIR, int OP>
 int launch_c(const SweepArgs& a, cudaStream_t st) {
   const int n = a.op.n;
@@ -646,6 +831,19 @@ size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out) {
   const size_t nrows_max = (size_t)n + 8;          // >= nrows rounded up to even
   const size_t tabs = 5 * nrows_max + ((nrows_max + 15) & ~(size_t)15) / 8;
   return (tabs + (size_t)NG * (tile + 2 * (size_t)C * ASTR_BW)) * sizeof(double);
+}
+
+// i direction only; lines of 8*32 .. 17*32 rows (every lane chunk then holds the H-row window and, at the two
+// ends, the closure rows).  Returns -1 when it does not apply: the caller uses the shared-memory engine.
+int astr_launch_sweep3(int optype, const SweepArgs& a, cudaStream_t st) {
+  if (!a.op.pf32 || a.op.nrows < 8 * 32 || a.op.nrows > ASTR_W3_LCH * 32) return -1;
+  if (a.nf < 1 || a.nf > ASTR_MAXF) return astr_fail_msg("sweep: bad field count");
+  switch (optype) {
+    case OP_DERIV: return launch3<OP_DERIV>(a, st);
+    case OP_FILTER: return launch3<OP_FILTER>(a, st);
+    case OP_FLUXP: return launch3<OP_FLUXP>(a, st);
+    default: return launch3<OP_FLUXM>(a, st);
+  }
 }
 
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st) {

@@ -308,3 +308,26 @@ def test_launch_counter_counts_kernels(oracle):
     eng.rk_stage(1)
     assert eng.kernel_launches() - n0 >= 20
     eng.close(); c.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=(300, 16, 16), homo=(True, True, True)),
+    dict(n=(320, 14, 18), homo=(False, True, True), stretch=True),
+    dict(n=(288, 16, 12), homo=(True, True, True), stretch="skew", perturb=1e-2,
+         upwind=dict(lchardecomp=True, shkcrt="auto")),
+], ids=["periodic300", "walls_i320", "upwind288"])
+def test_warp_per_line_engine(oracle, kw, monkeypatch):
+    # ASTR_SWEEP_W3=1: long i lines (8*32..17*32 rows) run on the warp-per-line engine (sweep3_kernel): every
+    # operator that sweeps in i -- filter, gradient, flux divergence, compact upwind fluxes -- against the oracle
+    monkeypatch.setenv("ASTR_SWEEP_W3", "1")
+    c, eng = make_pair(oracle, **kw)
+    c.filterq(); eng.filterq()
+    assert_fields_close(c, eng, QS, OP_TOL, what="filterq (warp-per-line)")
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    assert_fields_close(c, eng, DVEL + DTMP, OP_TOL, what="gradcal (warp-per-line)")
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    assert_fields_close(c, eng, QRHS, UPWIND_TOL if "upwind" in kw else 5e-13, what="rhscal (warp-per-line)")
+    for rk in (1, 2, 3):
+        c.rk_stage(rk); eng.rk_stage(rk)
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="3 rk stages (warp-per-line)")
+    eng.close(); c.close()

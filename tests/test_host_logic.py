@@ -159,3 +159,67 @@ def test_refcal_dimensional_matches_the_oracle(oracle):
     for k in ("reynolds", "mach", "const1", "const2", "const5", "const6", "rgas", "cp", "cv", "pinf"):
         assert abs(th[k] - want[k]) <= 1e-14 * abs(want[k]), k
     assert 2.9 < th["mach"] < 3.1      # "M3"
+
+
+def _warp_line_thomas(ac1, ac2, ac3, d):
+    """The warp-per-line engine's algebra (astr_b200/csrc/sweep.cu sweep3_kernel): 32 lane chunks, zero-carry
+    recurrences, carries from Hillis-Steele scans of the affine maps x -> A x + B, exactly as the kernel."""
+    N = d.size
+    cs = [(c * N) // 32 for c in range(33)]
+    ac2 = ac2.copy(); ac3 = ac3.copy(); ac2[0] = 1.0; ac3[0] = 0.0
+    pf = np.zeros(N); qb = np.zeros(N)
+    for c in range(32):
+        p = 1.0
+        for r in range(cs[c], cs[c + 1]):
+            p *= -ac3[r]; pf[r] = p
+        q = 1.0
+        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
+            q *= -ac1[r]; qb[r] = q
+    e = np.zeros(N); A = np.zeros(32); B = np.zeros(32)
+    for c in range(32):
+        prev = 0.0
+        for r in range(cs[c], cs[c + 1]):
+            prev = d[r] * ac2[r] - prev * ac3[r]; e[r] = prev
+        A[c] = pf[cs[c + 1] - 1]; B[c] = prev
+    off = 1
+    while off < 32:                       # shfl_up scan
+        Ap, Bp = np.roll(A, off), np.roll(B, off)
+        m = np.arange(32) >= off
+        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
+        off *= 2
+    cin = np.concatenate([[0.0], B[:-1]])
+    g = np.zeros(N); A = np.zeros(32); B = np.zeros(32)
+    for c in range(32):
+        nxt = 0.0
+        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
+            nxt = (e[r] + pf[r] * cin[c]) - ac1[r] * nxt; g[r] = nxt
+        A[c] = qb[cs[c]]; B[c] = nxt
+    off = 1
+    while off < 32:                       # shfl_down scan
+        Ap, Bp = np.roll(A, -off), np.roll(B, -off)
+        m = np.arange(32) + off < 32
+        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
+        off *= 2
+    xin = np.concatenate([B[1:], [0.0]])
+    x = np.zeros(N)
+    for c in range(32):
+        for r in range(cs[c], cs[c + 1]):
+            x[r] = g[r] + qb[r] * xin[c]
+    return x
+
+
+@pytest.mark.parametrize("is_filter", [False, True])
+@pytest.mark.parametrize("ntype", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [300, 512])
+def test_warp_per_line_partition_is_exact(oracle, is_filter, ntype, n):
+    first, a, c, ac1, ac2, ac3 = oracle.scheme_tables(is_filter, ntype, n)
+    N = a.size
+    d = np.random.default_rng(n + ntype).standard_normal(N)
+    dd = d.copy()
+    for i in range(1, N):
+        dd[i] = dd[i] * ac2[i] - dd[i - 1] * ac3[i]
+    x = np.zeros(N); x[-1] = dd[-1]
+    for i in range(N - 2, -1, -1):
+        x[i] = dd[i] - ac1[i] * x[i + 1]
+    xp = _warp_line_thomas(ac1, ac2, ac3, d)
+    assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * np.abs(x).max()
