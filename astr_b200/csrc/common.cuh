@@ -57,9 +57,11 @@ __host__ __device__ inline int chunk_start(int c, int nrows, int C) {
 
 // OP_FLUXP / OP_FLUXM: compact 5th-order upwind interface flux, flux_compact with flux_uw / flux_dw
 // (src/flux.F90:125-266); the solution at row `node` is the interface value fh(node), node -1..n
-// warp-per-line engine (sweep.cu, i direction): lane c owns rows [chunk32_start(c), chunk32_start(c+1))
-__host__ __device__ inline int chunk32_start(int c, int nrows) { return (c * nrows) / 32; }
-#define ASTR_W3_LCH 17      // rows per lane chunk: lines of 8*32 .. 17*32 rows
+// warp-per-line engine (sweep.cu, i direction): lane c owns rows [chunk32_start(c), chunk32_start(c+1)).
+// Every chunk is ASTR_W3_LCH = 17 rows long (the last ones shorter or empty): an odd lane stride keeps the
+// lanes' shared-memory accesses (line buffer and operator tables) on distinct banks.
+#define ASTR_W3_LCH 17      // rows per lane chunk: lines of up to 17*32 rows
+__host__ __device__ inline int chunk32_start(int c, int nrows) { return (c * ASTR_W3_LCH < nrows) ? c * ASTR_W3_LCH : nrows; }
 
 enum { OP_DERIV = 0, OP_FILTER = 1, OP_FLUXP = 2, OP_FLUXM = 3 };
 enum { EPI_STORE = 0, EPI_STOREZ = 1, EPI_ADD = 2 };

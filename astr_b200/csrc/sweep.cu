@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
     // ---- right-hand sides and forward elimination with zero carry-in ---------------------------------
     double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
     if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
-    if (lane == 31) closure_last<OP>(F, a.op.ntype, n, sl);
+    if (rb >= nrows - nsl && ra <= rb) closure_last<OP>(F, a.op.ntype, n, sl);   // lanes that own tail closure rows
     double e[LCH];
     double w[W];
     {
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
         w[(s + 2 * H) % W] = LB[W3_PADF + first_node + r + H];
         double d = interior_rhs<OP>(w, s);
         if (lane == 0 && s < nsf) d = sf[s < 5 ? s : 4];
-        if (lane == 31 && r >= nrows - nsl) {
+        if (r >= nrows - nsl) {
           const int kk = r - (nrows - nsl);
           d = kk == 0 ? sl[0] : kk == 1 ? sl[1] : kk == 2 ? sl[2] : kk == 3 ? sl[3] : sl[4];
         }
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
     // ---- carry into each chunk: d'(ra-1) = EE(c-1) + pf(rb(c-1)) * d'(ra(c-1)-1)  (exclusive scan of x -> A x + B) --
     double cin;
     {
-      double A = pf[rb], B = eprev;
+      double A = (ra <= rb) ? pf[rb] : 1.0, B = eprev;     // an empty chunk is the identity map
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const double Ap = __shfl_up_sync(0xffffffffu, A, off), Bp = __shfl_up_sync(0xffffffffu, B, off);
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
     // ---- x(rb+1) of each chunk: x(ra(c)) = GS(c) + qb(ra(c)) * x(rb(c)+1)  (suffix scan from the last chunk) -----
     double xin;
     {
-      double A = qb[ra], B = gnext;
+      double A = (ra <= rb) ? qb[ra] : 1.0, B = gnext;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const double Ap = __shfl_down_sync(0xffffffffu, A, off), Bp = __shfl_down_sync(0xffffffffu, B, off);
@@ -836,7 +836,7 @@ size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out) {
 // i direction only; lines of 8*32 .. 17*32 rows (every lane chunk then holds the H-row window and, at the two
 // ends, the closure rows).  Returns -1 when it does not apply: the caller uses the shared-memory engine.
 int astr_launch_sweep3(int optype, const SweepArgs& a, cudaStream_t st) {
-  if (!a.op.pf32 || a.op.nrows < 8 * 32 || a.op.nrows > ASTR_W3_LCH * 32) return -1;
+  if (!a.op.pf32 || a.op.nrows < 8 * 32 || a.op.nrows > ASTR_W3_LCH * 32) return -1;   // < 256 rows: too few lanes busy
   if (a.nf < 1 || a.nf > ASTR_MAXF) return astr_fail_msg("sweep: bad field count");
   switch (optype) {
     case OP_DERIV: return launch3<OP_DERIV>(a, st);

@@ -165,7 +165,7 @@ def _warp_line_thomas(ac1, ac2, ac3, d):
     """The warp-per-line engine's algebra (astr_b200/csrc/sweep.cu sweep3_kernel): 32 lane chunks, zero-carry
     recurrences, carries from Hillis-Steele scans of the affine maps x -> A x + B, exactly as the kernel."""
     N = d.size
-    cs = [(c * N) // 32 for c in range(33)]
+    cs = [min(17 * c, N) for c in range(33)]      # chunk32_start, astr_b200/csrc/common.cuh
     ac2 = ac2.copy(); ac3 = ac3.copy(); ac2[0] = 1.0; ac3[0] = 0.0
     pf = np.zeros(N); qb = np.zeros(N)
     for c in range(32):
@@ -180,7 +180,7 @@ def _warp_line_thomas(ac1, ac2, ac3, d):
         prev = 0.0
         for r in range(cs[c], cs[c + 1]):
             prev = d[r] * ac2[r] - prev * ac3[r]; e[r] = prev
-        A[c] = pf[cs[c + 1] - 1]; B[c] = prev
+        A[c] = pf[cs[c + 1] - 1] if cs[c + 1] > cs[c] else 1.0; B[c] = prev
     off = 1
     while off < 32:                       # shfl_up scan
         Ap, Bp = np.roll(A, off), np.roll(B, off)
@@ -193,7 +193,7 @@ def _warp_line_thomas(ac1, ac2, ac3, d):
         nxt = 0.0
         for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
             nxt = (e[r] + pf[r] * cin[c]) - ac1[r] * nxt; g[r] = nxt
-        A[c] = qb[cs[c]]; B[c] = nxt
+        A[c] = qb[cs[c]] if cs[c + 1] > cs[c] else 1.0; B[c] = nxt
     off = 1
     while off < 32:                       # shfl_down scan
         Ap, Bp = np.roll(A, -off), np.roll(B, -off)
