@@ -630,7 +630,8 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
   const double* __restrict__ qb = sm_all + 4 * nr8;
   const int lbn = (n + 2 * W3_PADF + 2 + 1) & ~1;         // doubles per line buffer (even)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* LB = sm_all + 5 * nr8 + (size_t)warp * lbn;     // LB[node + W3_PADF] = f(node)
+  double* LBa = sm_all + 5 * nr8 + (size_t)warp * 2 * lbn;   // two line buffers per warp: the next line is
+  double* LBb = LBa + lbn;                                   // fetched (cp.async) under the solve of this one
   for (int r = threadIdx.x; r < nrows; r += W3_WARPS * 32) {
     sm_all[r] = a.op.ac1[r];
     sm_all[nr8 + r] = a.op.ac2[r];
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
     sm_all[4 * nr8 + r] = a.op.qb32[r];
   }
   // window reads of closure rows may touch the pads: keep them finite
-  for (int t = lane; t < lbn; t += 32) LB[t] = 0.0;
+  for (int t = lane; t < 2 * lbn; t += 32) LBa[t] = 0.0;
   __syncthreads();
 
   const Layout& L = a.L;
@@ -651,18 +652,31 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
   const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
   const long long wstride = (long long)gridDim.x * W3_WARPS;
   const int npair = (n + 13) >> 1;                         // node pairs -6.. (n+5 or n+6)
+  double* LB = LBa;
   auto F = [&](int node) -> double { return LB[node + W3_PADF]; };
-
-  for (long long ln = (long long)blockIdx.x * W3_WARPS + warp; ln < nlines; ln += wstride) {
+  auto row_of = [&](long long ln, int& f) -> long long {
     const int j = (int)(ln % (L.jm + 1));
     const int k = (int)((ln / (L.jm + 1)) % (L.km + 1));
-    const int f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
-    const double* __restrict__ grow = a.in[f] + L.idx(0, j, k);
-    double* __restrict__ orow = a.out[f] + L.idx(0, j, k);
-    // ---- line -> buffer (node -6 is 16-byte aligned in global memory; W3_PADF - 6 is even) ----------------
-    for (int w = lane; w < npair; w += 32)
-      *reinterpret_cast<double2*>(LB + (W3_PADF - 6) + 2 * w) = *reinterpret_cast<const double2*>(grow - 6 + 2 * w);
+    f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
+    return L.idx(0, j, k);
+  };
+  // line -> buffer: 16-byte cp.async (node -6 is 16-byte aligned in global memory; W3_PADF - 6 is even)
+  auto fetch = [&](long long ln, double* buf) {
+    int f;
+    const long long off = row_of(ln, f);
+    const double* __restrict__ grow = a.in[f] + off;
+    for (int w = lane; w < npair; w += 32) cp_async16(buf + (W3_PADF - 6) + 2 * w, grow - 6 + 2 * w);
+  };
+
+  const long long ln0 = (long long)blockIdx.x * W3_WARPS + warp;
+  if (ln0 < nlines) fetch(ln0, LB);
+  for (long long ln = ln0; ln < nlines; ln += wstride) {
+    int f;
+    const long long off = row_of(ln, f);
+    double* __restrict__ orow = a.out[f] + off;
+    cp_async_wait_all();
     __syncwarp();
+    if (ln + wstride < nlines) fetch(ln + wstride, LB == LBa ? LBb : LBa);   // in flight during the solve
     // ---- right-hand sides and forward elimination with zero carry-in ---------------------------------
     double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
     if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
@@ -752,7 +766,8 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
       else if (vx) orow[nd] = x.x;
       else if (vy) orow[nd + 1] = x.y;
     }
-    __syncwarp();                      // the buffer is overwritten by the next line
+    __syncwarp();                      // this buffer is refilled two lines from now
+    LB = (LB == LBa) ? LBb : LBa;
   }
 }
 
@@ -761,7 +776,7 @@ int launch3(const SweepArgs& a, cudaStream_t st) {
   auto kern = sweep3_kernel<OP>;
   const int nr8 = (a.op.nrows + 1) & ~1;
   const int lbn = (a.op.n + 2 * W3_PADF + 2 + 1) & ~1;
-  const size_t smem = ((size_t)5 * nr8 + (size_t)W3_WARPS * lbn) * sizeof(double);
+  const size_t smem = ((size_t)5 * nr8 + (size_t)W3_WARPS * 2 * lbn) * sizeof(double);
   static size_t attr_smem = 0;
   static int occ = 0;
   if (smem > attr_smem || occ == 0) {
