@@ -187,7 +187,7 @@ module astr_gpu_mod
                            nbr,mpirank,lfilter,diffterm,alfa_filter,reynolds,mach, &
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
                            device,flowtype,conschm,difschm,bctype,twall, &
-                           recon_schem,lchardecomp,bfacmpld,shkcrt,pinf)
+                           recon_schem,lchardecomp,bfacmpld,shkcrt,pinf,ndims,nondimen)
     character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
     character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
     integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
@@ -195,6 +195,8 @@ module astr_gpu_mod
     logical, intent(in) :: lchardecomp              ! commvar lchardecomp
     real(8), intent(in) :: bfacmpld,shkcrt          ! commvar bfacmpld, shkcrt
     real(8), intent(in) :: pinf                     ! commvar pinf
+    integer, intent(in) :: ndims                    ! commvar ndims (3, or 2 with km=0)
+    logical, intent(in) :: nondimen                 ! commvar nondimen
     real(8), intent(in) :: twall(6)                 ! commvar twall(1:6)
     integer, intent(in) :: im,jm,km,ia,ja,ka,npdci,npdcj,npdck,is,ie,js,je,ks,ke
     logical, intent(in) :: lihomo,ljhomo,lkhomo,lfilter,diffterm
@@ -205,7 +207,7 @@ module astr_gpu_mod
     if(astr_gpu_sizeof_cfg()/=int(c_sizeof(cfg),c_int)) stop ' !! astr_cfg layout mismatch'
     cfg%abi_version=astr_gpu_abi_version; cfg%device=device
     cfg%im=im; cfg%jm=jm; cfg%km=km; cfg%ia=ia; cfg%ja=ja; cfg%ka=ka
-    cfg%hm=5; cfg%numq=5; cfg%ndims=3
+    cfg%hm=5; cfg%numq=5; cfg%ndims=ndims
     cfg%npdc=[npdci,npdcj,npdck]
     cfg%is=is; cfg%ie=ie; cfg%js=js; cfg%je=je; cfg%ks=ks; cfg%ke=ke
     cfg%lhomo=merge(1,0,[lihomo,ljhomo,lkhomo])
@@ -216,7 +218,7 @@ module astr_gpu_mod
     read(difschm(1:3),*) cfg%difschm
     cfg%scheme_compact=merge(1,0,difschm(4:4)=='c'); cfg%rkscheme=3
     cfg%lfilter=merge(1,0,lfilter); cfg%diffterm=merge(1,0,diffterm)
-    cfg%nondimen=1; cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
+    cfg%nondimen=merge(1,0,nondimen); cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall
     cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
     cfg%conschm_explicit=merge(1,0,conschm(4:4)=='e' .and. mod(cfg%conschm/100,2)==1)
