@@ -223,3 +223,31 @@ def test_warp_per_line_partition_is_exact(oracle, is_filter, ntype, n):
         x[i] = dd[i] - ac1[i] * x[i + 1]
     xp = _warp_line_thomas(ac1, ac2, ac3, d)
     assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * np.abs(x).max()
+
+
+def test_fortran_module_binds_every_stage_operator():
+    # fortran/astr_gpu_mod.F90 is the bind(C) layer a maintainer adds: every entry point of the header except the
+    # introspection / profiling helpers (bench and tests only) must have an interface there, and the derived type
+    # must list the members of struct astr_cfg in the same order
+    hdr = open(os.path.join(ROOT, "include", "astr_gpu.h")).read()
+    f90 = open(os.path.join(ROOT, "fortran", "astr_gpu_mod.F90")).read()
+    declared = set(re.findall(r"\b(astr_gpu_[a-z_0-9]+)\s*\(", hdr))
+    bound = set(re.findall(r"name='(astr_gpu_[a-z_0-9]+)'", f90))
+    helpers = {"astr_gpu_bench_sweep", "astr_gpu_device_ptr", "astr_gpu_get_profile", "astr_gpu_kernel_launches",
+               "astr_gpu_rk_steps_timed", "astr_gpu_set_profile"}
+    assert declared - bound <= helpers, sorted(declared - bound - helpers)
+    struct = hdr[hdr.index("typedef struct astr_cfg {"):hdr.index("} astr_cfg;")]
+    c_members = []
+    for line in struct.splitlines()[1:]:
+        line = line.split("/*")[0].strip()
+        m = re.match(r"(int|double)\s+(.*);", line)
+        if m:
+            c_members += [re.sub(r"\[\d+\]", "", v).strip() for v in m.group(2).split(",")]
+    ftype = f90[f90.index("type, bind(c) :: astr_cfg"):f90.index("end type astr_cfg")]
+    f_members = []
+    for line in ftype.splitlines()[1:]:
+        m = re.match(r"\s*(integer\(c_int\)|real\(c_double\))\s*::\s*(.*)", line)
+        if m:
+            f_members += [re.sub(r"\(\d+\)", "", v).strip() for v in m.group(2).split(",")]
+    assert [m.lower() for m in c_members] == [m.lower() for m in f_members]
+    assert [f[0] for f in L.AstrCfg._fields_] == [("is_" if m == "is" else m) for m in c_members]
