@@ -249,13 +249,9 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
     w = max(a.lss, min(a.lee, w));
     om[n - 1] = (long long)(w - i) * sd;
   }
-  double fsp[5][5], fsm[5][5], fcp[5], fcm[5];   // [component][stencil slot]
+  double fcp[5], fcm[5];
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
-    const double* fp = up + (UP_FSW + m) * fs + x;
-    const double* fm = up + (UP_FSW + 5 + m) * fs + x;
-#pragma unroll
-    for (int n = 0; n < 5; ++n) { fsp[m][n] = fp[op[n]]; fsm[m][n] = fm[om[n]]; }
     fcp[m] = up[(UP_FHC + m) * fs + x];
     fcm[m] = up[(UP_FHC + 5 + m) * fs + x];
   }
@@ -268,6 +264,23 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
   }
   const bool nolim = (a.ntype == 1 && (i == 0 || i == 1)) || (a.ntype == 2 && (i == a.dim - 1 || i == a.dim - 2));
   double Fh[5];
+  if (nolim || !lsh) {
+    // the limiter is off at this interface (mplimiter returns the compact value, MP5 with discont=.false. returns
+    // ul): Fhc = LEV (fhcp + fhcm) and Fh = REV Fhc = fhcp + fhcm up to rounding (LEV REV = I), so the
+    // eigen-decomposition and the stencil projections are skipped.  The reference does the same in convrsduwd
+    // (`if(lchardecomp .and. lsh)`, solver.F90:661); in smooth flow this is almost every interface.
+#pragma unroll
+    for (int m = 0; m < 5; ++m) up[(UP_FH + m) * fs + x] = fcp[m] + fcm[m];
+    return;
+  }
+  double fsp[5][5], fsm[5][5];          // [component][stencil slot]
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const double* fp = up + (UP_FSW + m) * fs + x;
+    const double* fm = up + (UP_FSW + 5 + m) * fs + x;
+#pragma unroll
+    for (int n = 0; n < 5; ++n) { fsp[m][n] = fp[op[n]]; fsm[m][n] = fm[om[n]]; }
+  }
   if (a.lchardecomp) {
     Eig e;
     const long long xr = x + sd;
