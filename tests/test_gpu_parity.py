@@ -329,8 +329,10 @@ def test_warp_per_line_engine(oracle, kw, monkeypatch):
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
     assert_fields_close(c, eng, DVEL + DTMP, 2e-11, what="gradcal (warp-per-line)")
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
-    assert_fields_close(c, eng, QRHS, 1e-10 if "upwind" in kw else 3e-11, what="rhscal (warp-per-line)")
+    # upwind: the split fluxes are O(c/dx_i) on this fine-in-i grid while their differences are O(1); the
+    # reference's REV*LEV round trip at unflagged interfaces (skipped on the device) is rounding noise of that size
+    assert_fields_close(c, eng, QRHS, 2e-9 if "upwind" in kw else 3e-11, what="rhscal (warp-per-line)")
     for rk in (1, 2, 3):
         c.rk_stage(rk); eng.rk_stage(rk)
-    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="3 rk stages (warp-per-line)")
+    assert_fields_close(c, eng, QS + PRIMS, 1e-11 if "upwind" in kw else STEP_TOL, what="3 rk stages (warp-per-line)")
     eng.close(); c.close()
