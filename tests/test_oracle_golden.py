@@ -13,8 +13,9 @@ def test_golden_file_shape(golden):
 
 
 def test_miniapp_reproduces_golden_bitwise(oracle, golden):
-    # 12 rows = 36 RK stages by default (~20 s on 8 cores); ASTR_GOLDEN_ROWS=100 checks all
-    rows = int(os.environ.get("ASTR_GOLDEN_ROWS", "12"))
+    # 40 rows = 120 RK stages by default (~65 s on 8 cores); ASTR_GOLDEN_ROWS=100 checks the whole file
+    # (all 100 rows reproduce bit for bit: 162 s on 8 cores, last checked at the end of round 1)
+    rows = int(os.environ.get("ASTR_GOLDEN_ROWS", "40"))
     m = oracle.MiniApp(128)
     h = m.run(rows)
     m.close()
