@@ -5,6 +5,8 @@ Tolerance: fp64, relative to the max-norm of each field.  Operator-level 2e-13 (
 build contracts a*b+c into FMA and the partitioned solve re-associates the carries; the
 oracle is compiled with -ffp-contract=off), multi-step 1e-12 as BASELINE.json's north_star
 states."""
+import os
+
 import numpy as np
 import pytest
 
@@ -287,7 +289,7 @@ def test_golden_history_through_the_gpu_path(oracle, golden):
     compares kinetic energy / enstrophy with the reference's shipped golden history."""
     n = (128, 128, 128)
     c, eng = make_pair(oracle, n=n, perturb=0.0, sutherland_s=110.4)
-    rows = 8
+    rows = int(os.environ.get("ASTR_GPU_GOLDEN_ROWS", "100"))      # the whole shipped history (100 RK3 steps)
     hist = []
     for step in range(rows):
         for rk in (1, 2, 3):
