@@ -20,7 +20,8 @@ def test_product_sources_never_reference_the_oracle():
                     bad.append(os.path.join(base, f))
     assert not bad, bad
     hdr = open(os.path.join(ROOT, "include", "astr_gpu.h")).read()
-    assert "torch" not in hdr and "at::" not in hdr          # plain C ABI: pointers, ints, doubles
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)       # declarations only, comments stripped
+    assert "torch" not in code and "at::" not in code and "std::" not in code   # plain C ABI: pointers, ints, doubles
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
