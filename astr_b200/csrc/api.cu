@@ -96,14 +96,15 @@ static NcclApi g_nccl;
 // -------------------------------------------------------------------------------------
 struct HostOp {
   int first_node = 0, nrows = 0, ntype = 0, n = 0, C = 1, nsf = 0, nsl = 0;
-  std::vector<double> a, c, ac1, ac2, ac3, pf, qb, pf32, qb32;
-  double* d_tab = nullptr;  // 7*nrows doubles on the device
+  std::vector<double> a, c, ac1, ac2, ac3, pf, qb, pf32, qb32, pad5;
+  double* d_tab = nullptr;  // 7*nrows (+ 5*ASTR_W3_ROWS padded) doubles on the device
   LinePlan plan;            // register-resident engine (sweep2.cu); plan.ok == 0: not applicable
   LineOp dev() const {
     LineOp o;
     o.ac1 = d_tab; o.ac2 = d_tab + nrows; o.ac3 = d_tab + 2 * nrows;
     o.pf = d_tab + 3 * nrows; o.qb = d_tab + 4 * nrows;
     o.pf32 = d_tab + 5 * nrows; o.qb32 = d_tab + 6 * nrows;
+    o.pad5 = pad5.empty() ? nullptr : d_tab + 7 * nrows;
     o.first_node = first_node; o.nrows = nrows; o.ntype = ntype; o.n = n; o.C = C;
     o.nsf = nsf; o.nsl = nsl;
     return o;
@@ -139,6 +140,21 @@ static void factorise(HostOp& h) {
     for (int r = ra; r <= rb; ++r) { p = p * (-h.ac3[r]); h.pf32[r] = p; }
     double q = 1.0;
     for (int r = rb; r >= ra; --r) { q = q * (-h.ac1[r]); h.qb32[r] = q; }
+  }
+  // padded variant: ac1 | ac2 | ac3 | pf | qb on ASTR_W3_ROWS rows, neutral beyond the line
+  h.pad5.clear();
+  if (N <= ASTR_W3_ROWS) {
+    const int R = ASTR_W3_ROWS;
+    h.pad5.assign((size_t)5 * R, 0.0);
+    double* p1 = h.pad5.data(); double* p2 = p1 + R; double* p3 = p2 + R; double* pp = p3 + R; double* pq = pp + R;
+    for (int r = 0; r < R; ++r) { p1[r] = r < N ? h.ac1[r] : 0.0; p2[r] = r < N ? h.ac2[r] : 1.0; p3[r] = r < N ? h.ac3[r] : 0.0; }
+    for (int c = 0; c < 32; ++c) {
+      const int ra = ASTR_W3_LCH * c, rb = ra + ASTR_W3_LCH - 1;
+      double p = 1.0;
+      for (int r = ra; r <= rb; ++r) { p = p * (-p3[r]); pp[r] = p; }
+      double q = 1.0;
+      for (int r = rb; r >= ra; --r) { q = q * (-p1[r]); pq[r] = q; }
+    }
   }
 }
 
@@ -187,7 +203,7 @@ struct Ctx {
   double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
   bool upwind() const { return (cfg.conschm / 100) % 2 == 1; }
   FilterCoef fc;
-  bool warp_lines = false;       // ASTR_SWEEP_W3=1: warp-per-line engine for long i lines (sweep3_kernel)
+  int warp_lines = 0;            // ASTR_SWEEP_W3=1: warp-per-line engine for long i lines (sweep3_kernel); 2: padded variant
   bool overlap = false;          // ASTR_OVERLAP=1: side-stream overlap of the sigma/qflux exchange (measured slower at 2 GPUs)
   bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
@@ -506,7 +522,7 @@ static int sweep(int d, int optype, const double* const* in, double* const* out,
     if (rc >= 0) return rc;
   }
   if (d == 0 && g->warp_lines) {
-    const int rc = astr_launch_sweep3(optype, a, g->st);
+    const int rc = astr_launch_sweep3(optype, a, g->warp_lines, g->st);
     if (rc >= 0) return rc;
   }
   return astr_launch_sweep(d, optype, a, g->st);
@@ -599,7 +615,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   TRY(astr_set_filter_coef(g->fc));
   { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
   { const char* e = getenv("ASTR_OVERLAP"); g->overlap = (e && e[0] == '1'); }
-  { const char* e = getenv("ASTR_SWEEP_W3"); g->warp_lines = (e && e[0] == '1'); }
+  { const char* e = getenv("ASTR_SWEEP_W3"); g->warp_lines = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
   for (int d = 0; d < cfg->ndims; ++d) {
     const int n = dim_of(d);
     build_deriv(g->fd[d], cfg->npdc[d], n);
@@ -613,11 +629,11 @@ int astr_gpu_init(const astr_cfg* cfg) {
     for (HostOp* h : {&g->fd[d], &g->fl[d], &g->fxp[d], &g->fxm[d]}) {
       if (h->nrows == 0) continue;   // flux operators exist only for conschm 543
       if (h->C < 1) return astr_fail_msg("block too small: every direction needs at least 12 nodes");
-      const size_t nb = (size_t)7 * h->nrows * sizeof(double);
+      const size_t nb = ((size_t)7 * h->nrows + h->pad5.size()) * sizeof(double);
       CUDA_OK(cudaMalloc(&h->d_tab, nb));
       std::vector<double> t;
-      t.reserve(7 * h->nrows);
-      for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb, &h->pf32, &h->qb32}) t.insert(t.end(), v->begin(), v->end());
+      t.reserve(7 * h->nrows + h->pad5.size());
+      for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb, &h->pf32, &h->qb32, &h->pad5}) t.insert(t.end(), v->begin(), v->end());
       CUDA_OK(cudaMemcpy(h->d_tab, t.data(), nb, cudaMemcpyHostToDevice));
     }
   }

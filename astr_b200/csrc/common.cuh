@@ -41,6 +41,7 @@ struct LineOp {
   const double* qb;         // qb[r] = prod_{m=r..ce(c(r))} (-ac1[m])
   const double* pf32;       // the same two products for the 32-chunk partition of the warp-per-line
   const double* qb32;       // engine (chunk32_start below); nullptr when that engine does not apply
+  const double* pad5;       // ac1|ac2|ac3|pf|qb padded to ASTR_W3_ROWS neutral rows (experimental padded variant)
   int first_node, nrows, ntype, n, C;
   int nsf, nsl;             // closure rows at the first / last end
 };
@@ -61,6 +62,7 @@ __host__ __device__ inline int chunk_start(int c, int nrows, int C) {
 // Every chunk is ASTR_W3_LCH = 17 rows long (the last ones shorter or empty): an odd lane stride keeps the
 // lanes' shared-memory accesses (line buffer and operator tables) on distinct banks.
 #define ASTR_W3_LCH 17      // rows per lane chunk: lines of up to 17*32 rows
+#define ASTR_W3_ROWS (32 * ASTR_W3_LCH)
 __host__ __device__ inline int chunk32_start(int c, int nrows) { return (c * ASTR_W3_LCH < nrows) ? c * ASTR_W3_LCH : nrows; }
 
 enum { OP_DERIV = 0, OP_FILTER = 1, OP_FLUXP = 2, OP_FLUXM = 3 };
@@ -92,7 +94,7 @@ int astr_set_filter_coef(const FilterCoef& fc);
 int astr_set_flux_coef(double bfacmpld);
 size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out);
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
-int astr_launch_sweep3(int optype, const SweepArgs& a, cudaStream_t st);   // -1: not applicable
+int astr_launch_sweep3(int optype, const SweepArgs& a, int variant, cudaStream_t st);   // -1: not applicable
 int astr_sweep_max_chunks(int nrows);
 // sweep2.cu
 int astr_sweep2_set_plan(int dir, int optype, const LinePlan& plan, const FilterCoef& fc);

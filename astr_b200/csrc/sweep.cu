@@ -771,12 +771,164 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (ASTR_SWEEP_W3=2; written at the end of round 1 without a GPU to time it -- its parity test
+// runs only with ASTR_TEST_EXPERIMENTAL=1): the warp-per-line engine with the overheads the SASS of
+// sweep3_kernel shows removed.  The operator tables are padded to 32 x 17 rows with neutral rows (ac2 = 1,
+// ac1 = ac3 = 0), so every lane runs the same 17 unguarded rows; per-lane base pointers turn all table and
+// buffer accesses of the unrolled rows into immediate offsets; the few rows whose right-hand side is a tail
+// closure (or padding) are recomputed afterwards by the lanes that own them.
+// -------------------------------------------------------------------------------------------------
+constexpr int W3P_LBN = 560;          // doubles per line buffer: node -8 .. first_node + 543 + H
+
 template <int OP>
+__global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3p_kernel(const SweepArgs a) {
+  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
+  constexpr int LCH = ASTR_W3_LCH, NR = ASTR_W3_ROWS;
+  extern __shared__ __align__(16) double sm_all[];
+  const int n = a.op.n, nrows = a.op.nrows, first_node = a.op.first_node;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* LBa = sm_all + 5 * NR + (size_t)warp * 2 * W3P_LBN;
+  double* LBb = LBa + W3P_LBN;
+  for (int r = threadIdx.x; r < 5 * NR; r += W3_WARPS * 32) sm_all[r] = a.op.pad5[r];
+  for (int t = lane; t < 2 * W3P_LBN; t += 32) LBa[t] = 0.0;
+  __syncthreads();
+  // per-lane views of the tables: entry s of lane c is row 17 c + s
+  const double* __restrict__ t1 = sm_all + LCH * lane;
+  const double* __restrict__ t2 = sm_all + NR + LCH * lane;
+  const double* __restrict__ t3 = sm_all + 2 * NR + LCH * lane;
+  const double* __restrict__ tp = sm_all + 3 * NR + LCH * lane;
+  const double* __restrict__ tq = sm_all + 4 * NR + LCH * lane;
+
+  const Layout& L = a.L;
+  const int nsf = a.op.nsf, nsl = a.op.nsl;
+  const int epi = a.epi, o_lo = a.o_lo, o_hi = a.o_hi;
+  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
+  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
+  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
+  const long long wstride = (long long)gridDim.x * W3_WARPS;
+  const int npair = (n + 13) >> 1;
+  // k = row - (nrows - nsl): k < 0 regular row, 0 <= k < nsl tail closure row, k >= nsl padding
+  const int k0 = LCH * lane - (nrows - nsl);
+  const bool fix_tail = k0 + LCH - 1 >= 0;
+  double* LB = LBa;
+  auto F = [&](int node) -> double { return LB[node + W3_PADF]; };
+  auto row_of = [&](long long ln, int& f) -> long long {
+    const int j = (int)(ln % (L.jm + 1));
+    const int k = (int)((ln / (L.jm + 1)) % (L.km + 1));
+    f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
+    return L.idx(0, j, k);
+  };
+  auto fetch = [&](long long ln, double* buf) {
+    int f;
+    const long long off = row_of(ln, f);
+    const double* __restrict__ grow = a.in[f] + off;
+    for (int w = lane; w < npair; w += 32) cp_async16(buf + (W3_PADF - 6) + 2 * w, grow - 6 + 2 * w);
+  };
+
+  const long long ln0 = (long long)blockIdx.x * W3_WARPS + warp;
+  if (ln0 < nlines) fetch(ln0, LB);
+  for (long long ln = ln0; ln < nlines; ln += wstride) {
+    int f;
+    const long long off = row_of(ln, f);
+    double* __restrict__ orow = a.out[f] + off;
+    cp_async_wait_all();
+    __syncwarp();
+    if (ln + wstride < nlines) fetch(ln + wstride, LB == LBa ? LBb : LBa);
+    double* __restrict__ lw = LB + W3_PADF + first_node + LCH * lane;      // lw[s] = f(node of row 17 lane + s)
+    double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
+    if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
+    if (fix_tail && k0 < nsl) closure_last<OP>(F, a.op.ntype, n, sl);
+    double e[LCH];
+    double w[W];
+#pragma unroll
+    for (int s = 0; s < 2 * H; ++s) w[s] = lw[s - H];
+    w[2 * H] = 0.0;
+    double eprev = 0.0;
+#pragma unroll
+    for (int s = 0; s < LCH; ++s) {
+      w[(s + 2 * H) % W] = lw[s + H];
+      double d = interior_rhs<OP>(w, s);
+      if (s < 5) { if (lane == 0 && s < nsf) d = sf[s]; }
+      const double ev = __fma_rn(-eprev, t3[s], d * t2[s]);
+      e[s] = ev;
+      eprev = ev;
+    }
+    if (fix_tail) {      // the last lanes: tail closure rows and padding get their own right-hand sides
+      double ep = 0.0;
+#pragma unroll
+      for (int s = 0; s < LCH; ++s) {
+        const int k = k0 + s;
+        if (k < 0) ep = e[s];
+        else {
+          const double d = k == 0 ? sl[0] : k == 1 ? sl[1] : k == 2 ? sl[2] : k == 3 ? sl[3] : k == 4 ? sl[4] : 0.0;
+          ep = __fma_rn(-ep, t3[s], (k < nsl ? d : 0.0) * t2[s]);
+          e[s] = ep;
+        }
+      }
+      eprev = ep;
+    }
+    double cin;
+    {
+      double A = tp[LCH - 1], B = eprev;
+#pragma unroll
+      for (int off2 = 1; off2 < 32; off2 <<= 1) {
+        const double Ap = __shfl_up_sync(0xffffffffu, A, off2), Bp = __shfl_up_sync(0xffffffffu, B, off2);
+        if (lane >= off2) { B = __fma_rn(A, Bp, B); A = A * Ap; }
+      }
+      cin = __shfl_up_sync(0xffffffffu, B, 1);
+      if (lane == 0) cin = 0.0;
+    }
+    double gnext = 0.0;
+#pragma unroll
+    for (int s = LCH - 1; s >= 0; --s) {
+      const double dp = __fma_rn(tp[s], cin, e[s]);
+      const double g = __fma_rn(-t1[s], gnext, dp);
+      e[s] = g;
+      gnext = g;
+    }
+    double xin;
+    {
+      double A = tq[0], B = gnext;
+#pragma unroll
+      for (int off2 = 1; off2 < 32; off2 <<= 1) {
+        const double Ap = __shfl_down_sync(0xffffffffu, A, off2), Bp = __shfl_down_sync(0xffffffffu, B, off2);
+        if (lane + off2 < 32) { B = __fma_rn(A, Bp, B); A = A * Ap; }
+      }
+      xin = __shfl_down_sync(0xffffffffu, B, 1);
+      if (lane == 31) xin = 0.0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < LCH; ++s) lw[s] = __fma_rn(tq[s], xin, e[s]);
+    __syncwarp();
+    for (int nd = (w_lo & ~1) + 2 * lane; nd <= w_hi; nd += 64) {
+      const bool vx = nd >= w_lo, vy = nd + 1 <= w_hi;
+      double2 x = *reinterpret_cast<const double2*>(LB + W3_PADF + nd);
+      if (epi == EPI_ADD) {
+        if (vx) x.x = orow[nd] + x.x;
+        if (vy) x.y = orow[nd + 1] + x.y;
+      } else if (epi == EPI_STOREZ) {
+        if (nd < o_lo || nd > o_hi) x.x = 0.0;
+        if (nd + 1 < o_lo || nd + 1 > o_hi) x.y = 0.0;
+      }
+      if (vx && vy) *reinterpret_cast<double2*>(orow + nd) = x;
+      else if (vx) orow[nd] = x.x;
+      else if (vy) orow[nd + 1] = x.y;
+    }
+    __syncwarp();
+    LB = (LB == LBa) ? LBb : LBa;
+  }
+}
+
+template <int OP, bool PADDED>
 int launch3(const SweepArgs& a, cudaStream_t st) {
-  auto kern = sweep3_kernel<OP>;
+  auto kern = PADDED ? sweep3p_kernel<OP> : sweep3_kernel<OP>;
   const int nr8 = (a.op.nrows + 1) & ~1;
   const int lbn = (a.op.n + 2 * W3_PADF + 2 + 1) & ~1;
-  const size_t smem = ((size_t)5 * nr8 + (size_t)W3_WARPS * 2 * lbn) * sizeof(double);
+  const size_t smem = PADDED ? ((size_t)5 * ASTR_W3_ROWS + (size_t)W3_WARPS * 2 * W3P_LBN) * sizeof(double)
+                             : ((size_t)5 * nr8 + (size_t)W3_WARPS * 2 * lbn) * sizeof(double);
   static size_t attr_smem = 0;
   static int occ = 0;
   if (smem > attr_smem || occ == 0) {
@@ -850,14 +1002,22 @@ size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out) {
 
 // i direction only; lines of 8*32 .. 17*32 rows (every lane chunk then holds the H-row window and, at the two
 // ends, the closure rows).  Returns -1 when it does not apply: the caller uses the shared-memory engine.
-int astr_launch_sweep3(int optype, const SweepArgs& a, cudaStream_t st) {
+int astr_launch_sweep3(int optype, const SweepArgs& a, int variant, cudaStream_t st) {
   if (!a.op.pf32 || a.op.nrows < 8 * 32 || a.op.nrows > ASTR_W3_LCH * 32) return -1;   // < 256 rows: too few lanes busy
   if (a.nf < 1 || a.nf > ASTR_MAXF) return astr_fail_msg("sweep: bad field count");
+  if (variant == 2 && a.op.pad5 && a.op.first_node >= -3 && a.op.n + 6 + W3_PADF < W3P_LBN) {   // experimental padded variant
+    switch (optype) {
+      case OP_DERIV: return launch3<OP_DERIV, true>(a, st);
+      case OP_FILTER: return launch3<OP_FILTER, true>(a, st);
+      case OP_FLUXP: return launch3<OP_FLUXP, true>(a, st);
+      default: return launch3<OP_FLUXM, true>(a, st);
+    }
+  }
   switch (optype) {
-    case OP_DERIV: return launch3<OP_DERIV>(a, st);
-    case OP_FILTER: return launch3<OP_FILTER>(a, st);
-    case OP_FLUXP: return launch3<OP_FLUXP>(a, st);
-    default: return launch3<OP_FLUXM>(a, st);
+    case OP_DERIV: return launch3<OP_DERIV, false>(a, st);
+    case OP_FILTER: return launch3<OP_FILTER, false>(a, st);
+    case OP_FLUXP: return launch3<OP_FLUXP, false>(a, st);
+    default: return launch3<OP_FLUXM, false>(a, st);
   }
 }
 

@@ -251,3 +251,67 @@ def test_fortran_module_binds_every_stage_operator():
             f_members += [re.sub(r"\(\d+\)", "", v).strip() for v in m.group(2).split(",")]
     assert [m.lower() for m in c_members] == [m.lower() for m in f_members]
     assert [f[0] for f in L.AstrCfg._fields_] == [("is_" if m == "is" else m) for m in c_members]
+
+
+def _warp_line_thomas_padded(ac1, ac2, ac3, d):
+    """The experimental padded variant (sweep3p_kernel): tables extended to 32 x 17 neutral rows (ac2 = 1,
+    ac1 = ac3 = 0) and zero right-hand sides there, every lane runs 17 unguarded rows."""
+    N, R = d.size, 32 * 17
+    p1 = np.zeros(R); p2 = np.ones(R); p3 = np.zeros(R); dd = np.zeros(R)
+    p1[:N] = ac1; p2[:N] = ac2; p3[:N] = ac3; p2[0] = 1.0; p3[0] = 0.0; dd[:N] = d
+    pf = np.zeros(R); qb = np.zeros(R)
+    for c in range(32):
+        p = 1.0
+        for r in range(17 * c, 17 * c + 17):
+            p *= -p3[r]; pf[r] = p
+        q = 1.0
+        for r in range(17 * c + 16, 17 * c - 1, -1):
+            q *= -p1[r]; qb[r] = q
+    e = np.zeros(R); A = np.zeros(32); B = np.zeros(32)
+    for c in range(32):
+        prev = 0.0
+        for r in range(17 * c, 17 * c + 17):
+            prev = dd[r] * p2[r] - prev * p3[r]; e[r] = prev
+        A[c] = pf[17 * c + 16]; B[c] = prev
+    off = 1
+    while off < 32:
+        Ap, Bp = np.roll(A, off), np.roll(B, off)
+        m = np.arange(32) >= off
+        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
+        off *= 2
+    cin = np.concatenate([[0.0], B[:-1]])
+    g = np.zeros(R); A = np.zeros(32); B = np.zeros(32)
+    for c in range(32):
+        nxt = 0.0
+        for r in range(17 * c + 16, 17 * c - 1, -1):
+            nxt = (e[r] + pf[r] * cin[c]) - p1[r] * nxt; g[r] = nxt
+        A[c] = qb[17 * c]; B[c] = nxt
+    off = 1
+    while off < 32:
+        Ap, Bp = np.roll(A, -off), np.roll(B, -off)
+        m = np.arange(32) + off < 32
+        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
+        off *= 2
+    xin = np.concatenate([B[1:], [0.0]])
+    x = np.array([g[r] + qb[r] * xin[r // 17] for r in range(R)])
+    assert np.all(x[N:] == 0.0)          # the padding solves to exactly zero
+    return x[:N]
+
+
+@pytest.mark.parametrize("is_filter", [False, True])
+@pytest.mark.parametrize("ntype", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [300, 512, 536])
+def test_padded_warp_per_line_partition_is_exact(oracle, is_filter, ntype, n):
+    first, a, c, ac1, ac2, ac3 = oracle.scheme_tables(is_filter, ntype, n)
+    N = a.size
+    if N > 32 * 17:
+        pytest.skip("line longer than 32 x 17 rows")
+    d = np.random.default_rng(n + ntype).standard_normal(N)
+    dd = d.copy()
+    for i in range(1, N):
+        dd[i] = dd[i] * ac2[i] - dd[i - 1] * ac3[i]
+    x = np.zeros(N); x[-1] = dd[-1]
+    for i in range(N - 2, -1, -1):
+        x[i] = dd[i] - ac1[i] * x[i + 1]
+    xp = _warp_line_thomas_padded(ac1, ac2, ac3, d)
+    assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * np.abs(x).max()
