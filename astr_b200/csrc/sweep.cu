@@ -773,9 +773,8 @@ __global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArg
 
 
 // -------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (ASTR_SWEEP_W3=2; written at the end of round 1 without a GPU to time it -- its parity test
-// runs only with ASTR_TEST_EXPERIMENTAL=1): the warp-per-line engine with the overheads the SASS of
-// sweep3_kernel shows removed.  The operator tables are padded to 32 x 17 rows with neutral rows (ac2 = 1,
+// EXPERIMENTAL (ASTR_SWEEP_W3=2; parity-tested, not yet timed): the warp-per-line engine with the overheads
+// the SASS of sweep3_kernel shows removed.  The operator tables are padded to 32 x 17 rows with neutral rows (ac2 = 1,
 // ac1 = ac3 = 0), so every lane runs the same 17 unguarded rows; per-lane base pointers turn all table and
 // buffer accesses of the unrolled rows into immediate offsets; the few rows whose right-hand side is a tail
 // closure (or padding) are recomputed afterwards by the lanes that own them.

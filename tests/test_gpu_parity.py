@@ -320,13 +320,12 @@ def test_launch_counter_counts_kernels(oracle):
 ], ids=["periodic300", "walls_i320", "upwind288"])
 @pytest.mark.parametrize("variant", ["1", "2"])
 def test_warp_per_line_engine(oracle, kw, variant, monkeypatch):
-    # ASTR_SWEEP_W3=1: long i lines (8*32..17*32 rows) run on the warp-per-line engine (sweep3_kernel): every
+    # ASTR_SWEEP_W3=1 / 2: long i lines (8*32..17*32 rows) run on the warp-per-line engine (sweep3_kernel, or its
+    # padded variant sweep3p_kernel): every
     # operator that sweeps in i -- filter, gradient, flux divergence, compact upwind fluxes -- against the oracle
     # tolerances: with 300 intervals in i against 16 in j, k the i-derivative of an O(1) field is ~20x smaller
     # than its rounding scale eps*|f|/dx relative to the j, k entries of the same tensor; the shared-memory
     # engine shows the same 1.5e-12 / 5e-12 / 6.5e-12 on these grids (measured), so this is conditioning
-    if variant == "2" and os.environ.get("ASTR_TEST_EXPERIMENTAL") != "1":
-        pytest.skip("padded variant (sweep3p_kernel) was written without a GPU at hand: ASTR_TEST_EXPERIMENTAL=1 runs it")
     monkeypatch.setenv("ASTR_SWEEP_W3", variant)
     c, eng = make_pair(oracle, **kw)
     c.filterq(); eng.filterq()
