@@ -96,15 +96,13 @@ static NcclApi g_nccl;
 // -------------------------------------------------------------------------------------
 struct HostOp {
   int first_node = 0, nrows = 0, ntype = 0, n = 0, C = 1, nsf = 0, nsl = 0;
-  std::vector<double> a, c, ac1, ac2, ac3, pf, qb, pf32, qb32, pad5;
-  double* d_tab = nullptr;  // 7*nrows (+ 5*ASTR_W3_ROWS padded) doubles on the device
+  std::vector<double> a, c, ac1, ac2, ac3, pf, qb;
+  double* d_tab = nullptr;  // 5*nrows doubles on the device
   LinePlan plan;            // register-resident engine (sweep2.cu); plan.ok == 0: not applicable
   LineOp dev() const {
     LineOp o;
     o.ac1 = d_tab; o.ac2 = d_tab + nrows; o.ac3 = d_tab + 2 * nrows;
     o.pf = d_tab + 3 * nrows; o.qb = d_tab + 4 * nrows;
-    o.pf32 = d_tab + 5 * nrows; o.qb32 = d_tab + 6 * nrows;
-    o.pad5 = pad5.empty() ? nullptr : d_tab + 7 * nrows;
     o.first_node = first_node; o.nrows = nrows; o.ntype = ntype; o.n = n; o.C = C;
     o.nsf = nsf; o.nsl = nsl;
     return o;
@@ -132,56 +130,32 @@ static void factorise(HostOp& h) {
     double q = 1.0;
     for (int r = rb; r >= ra; --r) { q = q * (-h.ac1[r]); h.qb[r] = q; }
   }
-  // the same products for the 32-chunk partition of the warp-per-line engine (sweep3_kernel)
-  h.pf32.assign(N, 0.0); h.qb32.assign(N, 0.0);
-  for (int c = 0; c < 32; ++c) {
-    const int ra = chunk32_start(c, N), rb = chunk32_start(c + 1, N) - 1;
-    double p = 1.0;
-    for (int r = ra; r <= rb; ++r) { p = p * (-h.ac3[r]); h.pf32[r] = p; }
-    double q = 1.0;
-    for (int r = rb; r >= ra; --r) { q = q * (-h.ac1[r]); h.qb32[r] = q; }
-  }
-  // padded variant: ac1 | ac2 | ac3 | pf | qb on ASTR_W3_ROWS rows, neutral beyond the line
-  h.pad5.clear();
-  if (N <= ASTR_W3_ROWS) {
-    const int R = ASTR_W3_ROWS;
-    h.pad5.assign((size_t)5 * R, 0.0);
-    double* p1 = h.pad5.data(); double* p2 = p1 + R; double* p3 = p2 + R; double* pp = p3 + R; double* pq = pp + R;
-    for (int r = 0; r < R; ++r) { p1[r] = r < N ? h.ac1[r] : 0.0; p2[r] = r < N ? h.ac2[r] : 1.0; p3[r] = r < N ? h.ac3[r] : 0.0; }
-    for (int c = 0; c < 32; ++c) {
-      const int ra = ASTR_W3_LCH * c, rb = ra + ASTR_W3_LCH - 1;
-      double p = 1.0;
-      for (int r = ra; r <= rb; ++r) { p = p * (-p3[r]); pp[r] = p; }
-      double q = 1.0;
-      for (int r = rb; r >= ra; --r) { q = q * (-p1[r]); pq[r] = q; }
-    }
-  }
 }
 
-static void build_deriv(HostOp& h, int ntype, int n) {
+// dir 0 (i lines): the register engine needs 16-byte aligned chunk windows (linecore.h, align_even)
+static void build_deriv(HostOp& h, int ntype, int n, int dir) {
   h.ntype = ntype; h.n = n;
   build_lhs(OP_DERIV, ntype, n, 0.0, h.a, h.c, h.first_node, h.nsf, h.nsl);
   h.nrows = (int)h.a.size();
   factorise(h);
-  build_line_plan(h.plan, OP_DERIV, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, 16);
+  build_line_plan(h.plan, OP_DERIV, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, ASTR_NWMAX, dir == 0);
 }
 
-static void build_filter(HostOp& h, int ntype, int n, double alfa) {
+static void build_filter(HostOp& h, int ntype, int n, double alfa, int dir) {
   h.ntype = ntype; h.n = n;
   build_lhs(OP_FILTER, ntype, n, alfa, h.a, h.c, h.first_node, h.nsf, h.nsl);
   h.nrows = (int)h.a.size();
   factorise(h);
-  build_line_plan(h.plan, OP_FILTER, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, 16);
+  build_line_plan(h.plan, OP_FILTER, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, ASTR_NWMAX, dir == 0);
 }
 
-// compact_flux_initiate (src/flux.F90:32-118) for flux_uw ('+', OP_FLUXP) / flux_dw ('-', OP_FLUXM);
-// solved on the shared-memory engine (sweep.cu), so no register-engine plan
-static void build_flux(HostOp& h, int optype, int ntype, int n, double bfacmpld) {
+// compact_flux_initiate (src/flux.F90:32-118) for flux_uw ('+', OP_FLUXP) / flux_dw ('-', OP_FLUXM)
+static void build_flux(HostOp& h, int optype, int ntype, int n, double bfacmpld, int dir) {
   h.ntype = ntype; h.n = n;
   build_lhs(optype, ntype, n, bfacmpld, h.a, h.c, h.first_node, h.nsf, h.nsl);
   h.nrows = (int)h.a.size();
   factorise(h);
-  h.plan.ok = 0;
+  build_line_plan(h.plan, optype, ntype, n, h.first_node, h.nsf, h.nsl, h.a, h.c, ASTR_NWMAX, dir == 0);
 }
 
 // -------------------------------------------------------------------------------------
@@ -203,9 +177,6 @@ struct Ctx {
   double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
   bool upwind() const { return (cfg.conschm / 100) % 2 == 1; }
   FilterCoef fc;
-  int warp_lines = 0;            // ASTR_SWEEP_W3=1: warp-per-line engine for long i lines (sweep3_kernel); 2: padded variant
-  bool overlap = false;          // ASTR_OVERLAP=1: side-stream overlap of the sigma/qflux exchange (measured slower at 2 GPUs)
-  bool legacy_sweep = false;     // ASTR_SWEEP_LEGACY=1: always use the shared-memory engine (sweep.cu)
   double* d_partial = nullptr;   // stats partial sums
   double* d_out2 = nullptr;
   cudaStream_t st = nullptr;
@@ -397,8 +368,7 @@ static size_t xarena_bytes(const int dims[3]) { return xwin_offset(dims, 3, 0); 
 // peer-to-peer path is collective (all ranks or none): anything that fails falls back to NCCL.
 static int p2p_setup() {
   const astr_cfg& c = g->cfg;
-  const char* env = getenv("ASTR_XCHG");
-  int ok = !(env && strcmp(env, "nccl") == 0);
+  int ok = !c.xchg_nccl;
   const int dims[3] = {c.im, c.jm, c.km};
   struct Rec { cudaIpcMemHandle_t h; int dims[3]; int ok; char pad[128 - sizeof(cudaIpcMemHandle_t) - 16]; };
   static_assert(sizeof(Rec) == 128, "Rec size");
@@ -448,7 +418,7 @@ static int p2p_setup() {
   CUDA_OK(cudaStreamSynchronize(g->st));
   cudaFree(dbuf);
   g->p2p = ok != 0;
-  if (!g->p2p && g->rank == 0 && !(env && strcmp(env, "nccl") == 0))
+  if (!g->p2p && g->rank == 0 && !c.xchg_nccl)
     fprintf(stderr, "astr_gpu: peer-to-peer halo exchange unavailable (CUDA IPC), using ncclSend/ncclRecv\n");
   return 0;
 }
@@ -517,12 +487,8 @@ static int sweep(int d, int optype, const double* const* in, double* const* out,
   for (int i = 0; i < nf; ++i) { a.in[i] = in[i]; a.out[i] = out[i]; }
   a.epi = epi; a.o_lo = o_lo; a.o_hi = o_hi;
   if (optype == OP_DERIV && !g->cfg.scheme_compact) return pw_diff6e(d, a, g->st);   // difschm '...e'
-  if (!g->legacy_sweep && optype <= OP_FILTER) {
+  if (!g->cfg.legacy_sweep) {
     const int rc = astr_launch_sweep2(d, optype, hop.plan, a, g->st);
-    if (rc >= 0) return rc;
-  }
-  if (d == 0 && g->warp_lines) {
-    const int rc = astr_launch_sweep3(optype, a, g->warp_lines, g->st);
     if (rc >= 0) return rc;
   }
   return astr_launch_sweep(d, optype, a, g->st);
@@ -608,32 +574,32 @@ int astr_gpu_init(const astr_cfg* cfg) {
   CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
   TRY(astr_sweep2_register_pool(0, g->pool, S_CORE, g->L));
   TRY(astr_sweep2_register_pool(1, nullptr, 0, g->L));
+  TRY(astr_sweep2_register_pool(2, nullptr, 0, g->L));
   CUDA_OK(cudaMalloc(&g->d_partial, (size_t)4 * (cfg->jm + 1) * (cfg->km + 1) * sizeof(double)));
   CUDA_OK(cudaMalloc(&g->d_out2, 4 * sizeof(double)));
   CUDA_OK(cudaMalloc(&g->d_src, 8 * sizeof(double)));
-  build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98);
+  build_filter_coef(g->fc, cfg->alfa_filter, 1.11, 0.98, cfg->bfacmpld);
   TRY(astr_set_filter_coef(g->fc));
-  { const char* e = getenv("ASTR_SWEEP_LEGACY"); g->legacy_sweep = (e && e[0] == '1'); }
-  { const char* e = getenv("ASTR_OVERLAP"); g->overlap = (e && e[0] == '1'); }
-  { const char* e = getenv("ASTR_SWEEP_W3"); g->warp_lines = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
   for (int d = 0; d < cfg->ndims; ++d) {
     const int n = dim_of(d);
-    build_deriv(g->fd[d], cfg->npdc[d], n);
-    build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter);
+    build_deriv(g->fd[d], cfg->npdc[d], n, d);
+    build_filter(g->fl[d], cfg->npdc[d], n, cfg->alfa_filter, d);
     TRY(astr_sweep2_set_plan(d, OP_DERIV, g->fd[d].plan, g->fc));
     TRY(astr_sweep2_set_plan(d, OP_FILTER, g->fl[d].plan, g->fc));
     if (g->upwind() && !cfg->conschm_explicit) {
-      build_flux(g->fxp[d], OP_FLUXP, cfg->npdc[d], n, cfg->bfacmpld);
-      build_flux(g->fxm[d], OP_FLUXM, cfg->npdc[d], n, cfg->bfacmpld);
+      build_flux(g->fxp[d], OP_FLUXP, cfg->npdc[d], n, cfg->bfacmpld, d);
+      build_flux(g->fxm[d], OP_FLUXM, cfg->npdc[d], n, cfg->bfacmpld, d);
+      TRY(astr_sweep2_set_plan(d, OP_FLUXP, g->fxp[d].plan, g->fc));
+      TRY(astr_sweep2_set_plan(d, OP_FLUXM, g->fxm[d].plan, g->fc));
     }
     for (HostOp* h : {&g->fd[d], &g->fl[d], &g->fxp[d], &g->fxm[d]}) {
       if (h->nrows == 0) continue;   // flux operators exist only for conschm 543
       if (h->C < 1) return astr_fail_msg("block too small: every direction needs at least 12 nodes");
-      const size_t nb = ((size_t)7 * h->nrows + h->pad5.size()) * sizeof(double);
+      const size_t nb = (size_t)5 * h->nrows * sizeof(double);
       CUDA_OK(cudaMalloc(&h->d_tab, nb));
       std::vector<double> t;
-      t.reserve(7 * h->nrows + h->pad5.size());
-      for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb, &h->pf32, &h->qb32, &h->pad5}) t.insert(t.end(), v->begin(), v->end());
+      t.reserve(5 * h->nrows);
+      for (auto* v : {&h->ac1, &h->ac2, &h->ac3, &h->pf, &h->qb}) t.insert(t.end(), v->begin(), v->end());
       CUDA_OK(cudaMemcpy(h->d_tab, t.data(), nb, cudaMemcpyHostToDevice));
     }
   }
@@ -642,6 +608,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
     const size_t ub = (size_t)UP_TOTAL * L.fstride * sizeof(double);
     CUDA_OK(cudaMalloc(&g->up, ub));
     CUDA_OK(cudaMemsetAsync(g->up, 0, ub, g->st));
+    TRY(astr_sweep2_register_pool(2, g->up, UP_TOTAL, g->L));
   }
   g_launches = 0;
   CUDA_OK(cudaStreamSynchronize(g->st));
@@ -663,7 +630,7 @@ int astr_gpu_finalize(void) {
     if (g->fxm[d].d_tab) cudaFree(g->fxm[d].d_tab);
   }
   if (g->up) cudaFree(g->up);
-  astr_sweep2_register_pool(0, nullptr, 0, g->L); astr_sweep2_register_pool(1, nullptr, 0, g->L);
+  for (int k = 0; k < 3; ++k) astr_sweep2_register_pool(k, nullptr, 0, g->L);
   cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
   cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
   if (g->ycoord) cudaFree(g->ycoord);
@@ -1035,7 +1002,7 @@ int astr_gpu_rhscal(void) {
   }
   if (c.diffterm) {
     const bool multi = c.size[0] * c.size[1] * c.size[2] > 1;
-    if (multi && g->overlap) {
+    if (multi && g->cfg.overlap_visc) {
       // multi-block: the sigma/qflux exchange (solver.F90:2604-2606) is hidden behind the interior pass.
       // 1. stresses on the face shells only (what the exchange sends), 2. exchange on the side stream,
       // 3. meanwhile the fused stress + flux pass over the whole block on the main stream, 4. join.

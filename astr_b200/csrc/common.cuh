@@ -39,9 +39,6 @@ struct LineOp {
   const double* ac3;
   const double* pf;         // pf[r] = prod_{m=cs(c(r))..r} (-ac3[m])
   const double* qb;         // qb[r] = prod_{m=r..ce(c(r))} (-ac1[m])
-  const double* pf32;       // the same two products for the 32-chunk partition of the warp-per-line
-  const double* qb32;       // engine (chunk32_start below); nullptr when that engine does not apply
-  const double* pad5;       // ac1|ac2|ac3|pf|qb padded to ASTR_W3_ROWS neutral rows (experimental padded variant)
   int first_node, nrows, ntype, n, C;
   int nsf, nsl;             // closure rows at the first / last end
 };
@@ -58,13 +55,6 @@ __host__ __device__ inline int chunk_start(int c, int nrows, int C) {
 
 // OP_FLUXP / OP_FLUXM: compact 5th-order upwind interface flux, flux_compact with flux_uw / flux_dw
 // (src/flux.F90:125-266); the solution at row `node` is the interface value fh(node), node -1..n
-// warp-per-line engine (sweep.cu, i direction): lane c owns rows [chunk32_start(c), chunk32_start(c+1)).
-// Every chunk is ASTR_W3_LCH = 17 rows long (the last ones shorter or empty): an odd lane stride keeps the
-// lanes' shared-memory accesses (line buffer and operator tables) on distinct banks.
-#define ASTR_W3_LCH 17      // rows per lane chunk: lines of up to 17*32 rows
-#define ASTR_W3_ROWS (32 * ASTR_W3_LCH)
-__host__ __device__ inline int chunk32_start(int c, int nrows) { return (c * ASTR_W3_LCH < nrows) ? c * ASTR_W3_LCH : nrows; }
-
 enum { OP_DERIV = 0, OP_FILTER = 1, OP_FLUXP = 2, OP_FLUXM = 3 };
 enum { EPI_STORE = 0, EPI_STOREZ = 1, EPI_ADD = 2 };
 
@@ -94,7 +84,6 @@ int astr_set_filter_coef(const FilterCoef& fc);
 int astr_set_flux_coef(double bfacmpld);
 size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out);
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st);
-int astr_launch_sweep3(int optype, const SweepArgs& a, int variant, cudaStream_t st);   // -1: not applicable
 int astr_sweep_max_chunks(int nrows);
 // sweep2.cu
 int astr_sweep2_set_plan(int dir, int optype, const LinePlan& plan, const FilterCoef& fc);

@@ -1,31 +1,37 @@
 // astr_b200/csrc/linecore.h -- the register-resident partitioned line solve (sweep2.cu).
 //
 // Same linear systems as the reference's compact operators -- `fds%central`
-// (src/derivative.F90:171-306), `compact_filter` (src/filter.F90:112-285), unit-diagonal
-// tridiagonal rows a(r) x(r-1) + x(r) + c(r) x(r+1) = d(r) (src/commfunc.F90:752-813) --
-// but factorised for a GPU: the rows are cut into ELEMENTS
+// (src/derivative.F90:171-306), `compact_filter` (src/filter.F90:112-285), `flux_compact`
+// (src/flux.F90:125-266): unit-diagonal tridiagonal rows a(r) x(r-1) + x(r) + c(r) x(r+1) = d(r)
+// (src/commfunc.F90:752-813) -- but factorised for a GPU.  The rows are cut into ELEMENTS
 //
 //     [head block | regular chunk 0 | regular chunk 1 | ... | regular chunk NW-1 | tail block]
 //
-// * head / tail block: the 1-2 closure rows whose LEFT-hand side differs from the interior
-//   (explicit interface rows a=c=0, wall rows a=c=2 and 1/4, filter end rows 1.11 / 0.98);
-// * regular chunks: rows with the interior coefficients (alpha, 1, alpha).  Every chunk is
-//   factorised from a FRESH start, so all chunks share one set of coefficient tables
-//   (m, g, ac1, ev below), which the kernels read as immediate constant-bank operands.
+// * regular chunks: ASTR_LMAX rows with the interior left- AND right-hand side.  Every chunk
+//   is factorised from a FRESH start, so all chunks of all pencils share ONE set of coefficient
+//   tables (m, g, ac1, ev), which the kernels read as immediate constant-bank operands, and all
+//   chunk threads run the same straight-line code.
+// * head block: the closure rows of the first end (explicit interface rows, wall rows, filter
+//   end rows) plus the rows that do not fill a whole chunk; tail block: the closure rows of the
+//   last end (+ at most one interior row, see `align_even`).  Generic tables, one dedicated warp.
 //
-// A thread owns one chunk in registers:
+// A thread owns one element of one pencil in registers:
 //   pass 1  e(s) = d(s) m(s) - e(s-1) g(s)                       local forward elimination
 //   pass 2  y(s) = e(s) - ac1(s) y(s+1)                          local solution, zero carries;
 //           only its head yh = y(0) and tail yt = e(len-1) leave the thread
-//   scan    the heads/tails of all elements of a pencil obey a block-tridiagonal system
-//           whose block LU collapses to two scalar recurrences (P forward, h backward)
+//   scan    the heads/tails of all elements of a pencil obey a block-tridiagonal system whose
+//           block LU collapses to two scalar recurrences (P forward, P' backward)
 //   pass 3  x(s) = (e(s) - ev(s) t_prev) - ac1(s) x(s+1),  x(len) = h_next
-// with t_prev the true solution at the last row of the previous element and h_next at the
-// first row of the next one.  Exact algebra (no truncation of the coupling); differences
-// from the reference's single Thomas sweep are rounding only.
+// with t_prev the true solution at the last row of the previous element and h_next at the first
+// row of the next one.  The recurrences P(e) = S(e) - K(e) P(e-1) contract by |K| (the product of
+// the elimination factors over a whole chunk: 1e-14 per chunk for the derivative, 1e-3 for the
+// filter at alfa = 0.49), so each thread evaluates them over the W nearest elements only, with W
+// chosen by the host so that the dropped terms are below 1e-20 relative -- four decades under the
+// rounding of a double.  Everything else is exact algebra; differences from the reference's
+// single Thomas sweep are rounding only (tests/test_host_logic.py drives these functions on the
+// CPU against the oracle).
 //
-// Header shared by nvcc (device + host) and g++ (tests/emul_sweep2.cpp drives the same
-// functions on the CPU against the oracle).
+// Header shared by nvcc (device + host) and g++ (tests/emul_sweep2.cpp).
 #pragma once
 #include <cmath>
 
@@ -35,36 +41,42 @@
 #define ASTR_HD inline
 #endif
 
-#define ASTR_LMAX 33   // rows of a full regular chunk
-#define ASTR_EMAX 18   // elements per line: 16 regular chunks + head + tail block
-#define ASTR_SMAX 2    // rows of a head / tail block
+#define ASTR_LMAX 34     // rows of a regular chunk (even: all chunk windows of an i line share one 16-byte alignment)
+#define ASTR_NWMAX 15    // regular chunks per line (warps 0..NW-1; warp NW owns the head and tail blocks)
+#define ASTR_HS 40       // slots of the head block: <= 5 closure rows + ASTR_LMAX remainder rows (+1 alignment row)
+#define ASTR_TS 6        // slots of the tail block: <= 5 closure rows + 1 interior row
+#define ASTR_EMAX (ASTR_NWMAX + 2)
+#define ASTR_WPAD 8      // most elements the truncated reduced scan may look at on each side
 
-struct RegTab {        // fresh-start factorisation of rows (alpha, 1, alpha)
+struct RegTab {          // fresh-start factorisation of ASTR_LMAX interior rows (a, 1, c)
   double m[ASTR_LMAX], g[ASTR_LMAX], ac1[ASTR_LMAX], ev[ASTR_LMAX];
 };
-struct SpecTab {       // head / tail block
-  int len, pad;
-  double m[ASTR_SMAX], g[ASTR_SMAX], ac1[ASTR_SMAX], ev[ASTR_SMAX];
+// Head / tail block: rows first, then NEUTRAL slots (m = 0, g = -1, q = 0, ac1 = -1, ev = 0) that
+// pass e forward and x backward unchanged, so the unrolled code needs no length guards.
+template <int S> struct SpecTab {
+  int len, nclos;        // rows of the block; rows among them with a closure right-hand side
+  double m[S], g[S], q[S], ac1[S], ev[S];
 };
-struct ElemTab {       // reduced-system coefficients of one element (reduced_scan below)
+struct ElemTab {         // reduced-system coefficients of one element (reduced_scan below)
   double gamma, K, Q, gammap, Kp, Qp, D, pad;
 };
 struct LinePlan {
   int optype, ntype, n, first_node, nrows;
-  int sh, st;          // rows of the head / tail block
-  int nsf, nsl;        // rows with a closure RIGHT-hand side at each end (>= sh, st)
-  int NW, Lr, len0;    // regular chunks: chunk 0 has len0 rows, the others Lr
-  int E;               // NW + 2
-  int ok;              // 0: this line cannot be handled by sweep2 (fall back)
+  int nsf, nsl;          // rows with a closure RIGHT-hand side at each end
+  int sh, st;            // rows of the head / tail block (sh >= nsf, st = nsl or nsl + 1)
+  int NW;                // regular chunks
+  int E;                 // NW + 2
+  int W;                 // reduced scan: elements looked at on each side (<= ASTR_WPAD)
+  int ok;                // 0: this line cannot be handled by sweep2 (fall back to sweep.cu)
+  int pad;
   RegTab reg;
-  SpecTab head, tail;
-  ElemTab el[ASTR_EMAX];
+  SpecTab<ASTR_HS> head;
+  SpecTab<ASTR_TS> tail;
+  ElemTab el[ASTR_EMAX + 2 * ASTR_WPAD];   // element e at index e + ASTR_WPAD; neutral entries around
 };
 
 // first row of regular chunk w
-ASTR_HD int plan_chunk_row(const LinePlan& p, int w) {
-  return p.sh + (w == 0 ? 0 : p.len0 + (w - 1) * p.Lr);
-}
+ASTR_HD int plan_chunk_row(const LinePlan& p, int w) { return p.sh + w * ASTR_LMAX; }
 
 ASTR_HD double fma_(double a, double b, double c) {
 #ifdef __CUDA_ARCH__
@@ -83,75 +95,55 @@ ASTR_HD double fma_(double a, double b, double c) {
 //     P'(e) = S'(e) - K'(e) P'(e+1), S'(e) = yh(e) + gamma'(e) yt(e);
 // at the interface in front of element e the two meet:
 //     t(e-1) = D(e) (P(e-1) - Q(e-1) P'(e)),   h(e) = D(e) (P'(e) - Q'(e) P(e-1)).
-// A thread of element `me` runs the forward recurrence up to me and the backward one down to me.
-struct ScanOut { double Pm1, Pm, Pb0, Pb1; };   // P(me-1), P(me), P'(me), P'(me+1)
+// S(idx), SP(idx): published sums at PADDED element index idx = e + ASTR_WPAD (zero outside 0..E-1).
+struct ScanOut { double t_prev, h_next; };
 
 template <class GETS, class GETSP>
 ASTR_HD ScanOut reduced_scan(const LinePlan& pl, GETS S, GETSP SP, int me) {
-  ScanOut o;
-  const int E = pl.E;
+  const int W = pl.W;
+  const int c = me + ASTR_WPAD;
   double pf = 0.0, pf1 = 0.0;
-#pragma unroll
-  for (int e = 0; e < ASTR_EMAX; ++e) {
-    if (e > me) break;
+  for (int t = W; t >= 0; --t) {
     pf1 = pf;
-    pf = fma_(-pl.el[e].K, pf, S(e));
+    pf = fma_(-pl.el[c - t].K, pf, S(c - t));
   }
-  o.Pm = pf; o.Pm1 = pf1;
   double pb = 0.0, pb1 = 0.0;
-#pragma unroll
-  for (int e = ASTR_EMAX - 1; e >= 0; --e) {
-    if (e < me) break;
-    if (e < E) {
-      pb1 = pb;
-      pb = fma_(-pl.el[e].Kp, pb, SP(e));
-    }
+  for (int t = W; t >= 0; --t) {
+    pb1 = pb;
+    pb = fma_(-pl.el[c + t].Kp, pb, SP(c + t));
   }
-  o.Pb0 = pb; o.Pb1 = pb1;
+  ScanOut o;
+  o.t_prev = pl.el[c].D * fma_(-pl.el[c - 1].Q, pb, pf1);        // element 0: P(-1) = 0, Q(-1) = 0
+  o.h_next = pl.el[c + 1].D * fma_(-pl.el[c + 1].Qp, pf, pb1);   // element E-1: P'(E) = 0, Q'(E) = 0
   return o;
-}
-// true solution at the last row of element me-1 / the first row of element me+1
-ASTR_HD double scan_t_prev(const LinePlan& pl, int me, double Pm1, double Pb0) {
-  return (me > 0) ? pl.el[me].D * fma_(-pl.el[me > 0 ? me - 1 : 0].Q, Pb0, Pm1) : 0.0;
-}
-ASTR_HD double scan_h_next(const LinePlan& pl, int me, double Pm, double Pb1) {
-  return (me + 1 < pl.E) ? pl.el[me + 1].D * fma_(-pl.el[me + 1].Qp, Pm, Pb1) : 0.0;
-}
-
-// ---- head / tail block (<= ASTR_SMAX rows) ----------------------------------------------
-ASTR_HD void spec_forward(const SpecTab& t, const double* d, double* e, double& yh, double& yt) {
-  e[0] = d[0];
-#pragma unroll
-  for (int s = 1; s < ASTR_SMAX; ++s) e[s] = (s < t.len) ? fma_(-e[s - 1], t.g[s], d[s] * t.m[s]) : 0.0;
-  double y = 0.0;
-  yt = 0.0;
-#pragma unroll
-  for (int s = ASTR_SMAX - 1; s >= 0; --s)
-    if (s < t.len) {
-      if (s == t.len - 1) yt = e[s];
-      y = fma_(-t.ac1[s], y, e[s]);
-    }
-  yh = y;
-}
-ASTR_HD void spec_back(const SpecTab& t, const double* e, double t_prev, double h_next, double* x) {
-  double xn = h_next;
-#pragma unroll
-  for (int s = ASTR_SMAX - 1; s >= 0; --s) {
-    if (s < t.len) { xn = fma_(-t.ac1[s], xn, fma_(-t.ev[s], t_prev, e[s])); x[s] = xn; } else x[s] = 0.0;
-  }
 }
 
 // ---- right-hand sides -----------------------------------------------------------------
-// coefficient tables of src/filter.F90:299-432 (only the rows the hot path reads)
+// coefficient tables of src/filter.F90:299-432 (only the rows the hot path reads) and the interior
+// coefficients of compact_flux_rhs (src/flux.F90:247-262)
 struct FilterCoef {
   double coef6i[4], coef8i[5], coef10i[6];
   double coefb[4][9];
   double coefh[3][11];
+  double flx[4];
 };
 
 template <int OP> struct OpT;
-template <> struct OpT<0> { static constexpr int H = 2; };   // OP_DERIV
-template <> struct OpT<1> { static constexpr int H = 5; };   // OP_FILTER
+// H: half width of the interior stencil; HB: reach of the head block's window in front of the first row
+template <> struct OpT<0> { static constexpr int H = 2, HB = 3; };   // OP_DERIV (interface row: 7-point explicit)
+template <> struct OpT<1> { static constexpr int H = 5, HB = 5; };   // OP_FILTER
+template <> struct OpT<2> { static constexpr int H = 2, HB = 2; };   // OP_FLUXP
+template <> struct OpT<3> { static constexpr int H = 2, HB = 2; };   // OP_FLUXM
+
+// first row of the system as a node index: fd_scheme_initiate (src/derivative.F90:74-93),
+// compact_filter_initiate (src/filter.F90:44-71), compact_flux_initiate (src/flux.F90:44-70)
+template <int OP> ASTR_HD constexpr int op_first_node(bool p0) {
+  return OP == 0 ? (p0 ? 0 : -1) : OP == 1 ? (p0 ? 0 : -3) : (p0 ? -1 : -2);
+}
+// node of the row in front of the closure rows of the last end, relative to n
+template <int OP> ASTR_HD constexpr int op_tail_interior_off(bool pm) {
+  return OP == 0 ? (pm ? -2 : 0) : OP == 1 ? (pm ? -5 : 0) : (pm ? -2 : 0);
+}
 
 // interior right-hand side of the row whose node sits at window slot s + H
 template <int OP, int WN>
@@ -163,6 +155,12 @@ ASTR_HD double reg_rhs(const double (&wv)[WN], int s, const FilterCoef& fc) {
     const double var1 = WS(1) - WS(-1);
     const double var2 = WS(2) - WS(-2);
     return (7.0 / 9.0) * var1 + (1.0 / 36.0) * var2;
+  } else if (OP == 2) {
+    // src/flux.F90:247-253
+    return fc.flx[0] * WS(-1) + fc.flx[1] * WS(0) + fc.flx[2] * WS(1) + fc.flx[3] * WS(2);
+  } else if (OP == 3) {
+    // src/flux.F90:255-261
+    return fc.flx[0] * WS(2) + fc.flx[1] * WS(1) + fc.flx[2] * WS(0) + fc.flx[3] * WS(-1);
   } else {
     // src/filter.F90:271-283
     const double var0 = WS(0) + WS(0);
@@ -177,21 +175,32 @@ ASTR_HD double reg_rhs(const double (&wv)[WN], int s, const FilterCoef& fc) {
 #undef WS
 }
 
-// Closure rows at the first end.  hw[k] = f(k - 5), k = 0..13 (nodes -5..8).  sf[k] is row k.
-template <int OP>
-ASTR_HD void closure_head(const double (&hw)[14], bool phys, const FilterCoef& fc, double (&sf)[5]) {
-#define F(node) hw[(node) + 5]
+// Closure rows at the first end.  hw[k] = f(first_node - HB + k): the head block's window (HB: how far the
+// closure and interior stencils reach in front of the first row).  sf[k] is row k.
+template <int OP, bool P0, int HWN>
+ASTR_HD void closure_head(const double (&hw)[HWN], const FilterCoef& fc, double (&sf)[5]) {
+  constexpr int HB = OpT<OP>::HB;
+  constexpr int FN = op_first_node<OP>(P0);
+#define F(node) hw[(node) - FN + HB]
 #pragma unroll
   for (int k = 0; k < 5; ++k) sf[k] = 0.0;
   if (OP == 0) {
-    if (phys) {  // src/derivative.F90:230-248
+    if (P0) {    // src/derivative.F90:230-248
       sf[0] = -2.5 * F(0) + 2.0 * F(1) + 0.5 * F(2);
       sf[1] = 0.75 * (F(2) - F(0));
     } else {     // :250-260, row of ghost node -1
       sf[0] = 0.75 * (F(0) - F(-2)) - 0.15 * (F(1) - F(-3)) + (1.0 / 60.0) * (F(2) - F(-4));
     }
+  } else if (OP == 2 || OP == 3) {
+    if (P0) {    // src/flux.F90:189-199, rows -1 and 0
+      sf[0] = 2.5 * F(0) + 0.5 * F(1);
+      sf[1] = 0.75 * F(0) + 0.75 * F(1);
+    } else {     // :205-209, row -2: 6th-order explicit
+      const double var1 = F(-2) + F(-1), var2 = F(-3) + F(0), var3 = F(-4) + F(1);
+      sf[0] = (37.0 / 60.0) * var1 - (2.0 / 15.0) * var2 + (1.0 / 60.0) * var3;
+    }
   } else {
-    if (phys) {  // src/filter.F90:176-204
+    if (P0) {    // src/filter.F90:176-204
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         double v = 0.0;
@@ -220,22 +229,30 @@ ASTR_HD void closure_head(const double (&hw)[14], bool phys, const FilterCoef& f
 #undef F
 }
 
-// Closure rows at the last end.  tw[k] = f(n - 8 + k), k = 0..13 (nodes n-8..n+5).
+// Closure rows at the last end.  tw[k] = f(n - 10 + k), k = 0..15 (nodes n-10..n+5).
 // sl[k] is row nrows - nsl + k.
-template <int OP>
-ASTR_HD void closure_tail(const double (&tw)[14], bool phys, const FilterCoef& fc, double (&sl)[5]) {
-#define F(off) tw[(off) + 8]     // F(off) = f(n + off)
+template <int OP, bool PM>
+ASTR_HD void closure_tail(const double (&tw)[16], const FilterCoef& fc, double (&sl)[5]) {
+#define F(off) tw[(off) + 10]    // F(off) = f(n + off)
 #pragma unroll
   for (int k = 0; k < 5; ++k) sl[k] = 0.0;
   if (OP == 0) {
-    if (phys) {  // src/derivative.F90:264-281
+    if (PM) {    // src/derivative.F90:264-281
       sl[0] = 0.75 * (F(0) - F(-2));
       sl[1] = 2.5 * F(0) - 2.0 * F(-1) - 0.5 * F(-2);
     } else {     // :283-292, row of ghost node n+1
       sl[0] = 0.75 * (F(2) - F(0)) - 0.15 * (F(3) - F(-1)) + (1.0 / 60.0) * (F(4) - F(-2));
     }
+  } else if (OP == 2 || OP == 3) {
+    if (PM) {    // src/flux.F90:217-225, rows n-1 and n
+      sl[0] = 0.75 * F(0) + 0.75 * F(-1);
+      sl[1] = 2.5 * F(0) + 0.5 * F(-1);
+    } else {     // :231-236, row n+1
+      const double var1 = F(1) + F(2), var2 = F(0) + F(3), var3 = F(-1) + F(4);
+      sl[0] = (37.0 / 60.0) * var1 - (2.0 / 15.0) * var2 + (1.0 / 60.0) * var3;
+    }
   } else {
-    if (phys) {  // src/filter.F90:222-249 ; rows n-4, n-3, n-2, n-1, n
+    if (PM) {    // src/filter.F90:222-249 ; rows n-4, n-3, n-2, n-1, n
       {
         const double v0 = F(-4) + F(-4), v1 = F(-3) + F(-5), v2 = F(-2) + F(-6), v3 = F(-1) + F(-7),
                      v4 = F(0) + F(-8);
@@ -265,64 +282,81 @@ ASTR_HD void closure_tail(const double (&tw)[14], bool phys, const FilterCoef& f
 #undef F
 }
 
-// ---- regular chunk, passes 1 and 2 ------------------------------------------------------
-// ROLE_MID : full chunk (ASTR_LMAX rows), interior right-hand sides only.
-// ROLE_TAIL: full chunk whose last rows are closure rows with interior left-hand side (filter:
-//            2 rows at an interface end, 4 at a wall) -> ov[0..]; static slots.
-// ROLE_HEAD: chunk 0, `len` <= ASTR_LMAX rows, first rows closure rows (same counts) -> ov[0..].
-enum { ROLE_MID = 0, ROLE_HEAD = 1, ROLE_TAIL = 2 };
-
-// closure rows inside the regular chunk at one end
-template <int OP> ASTR_HD int n_override(bool phys) { return OP == 0 ? 0 : (phys ? 4 : 2); }
-
-template <int OP, int ROLE, int WN>
-ASTR_HD void chunk_forward(const RegTab& t, const FilterCoef& fc, const double (&wv)[WN], int len, bool phys,
-                           const double (&ov)[4], double (&e)[ASTR_LMAX], double& yh, double& yt) {
+// ---- regular chunk ------------------------------------------------------------------------
+// passes 1 and 2: wv[s] = f(node0 - H + s), s = 0 .. ASTR_LMAX + 2H - 1
+template <int OP, int WN>
+ASTR_HD void chunk_forward(const RegTab& t, const FilterCoef& fc, const double (&wv)[WN], double (&e)[ASTR_LMAX],
+                           double& yh, double& yt) {
   constexpr int L = ASTR_LMAX;
-  if (ROLE != ROLE_HEAD) {
 #pragma unroll
-    for (int s = 0; s < L; ++s) {
-      double d = reg_rhs<OP>(wv, s, fc);
-      if (ROLE == ROLE_TAIL && OP == 1) {
-        if (s >= L - 4 && phys) d = ov[s >= L - 4 ? s - (L - 4) : 0];
-        if (s >= L - 2 && !phys) d = ov[s >= L - 2 ? s - (L - 2) : 0];
-      }
-      e[s] = (s == 0) ? d : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d * t.m[s]);
-    }
-    double y = e[L - 1];
-#pragma unroll
-    for (int s = L - 2; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s]);
-    yh = y; yt = e[L - 1];
-  } else {
-    // chunk 0: `len` rows (uniform across the warp: the guards are branches, not selects)
-    yt = 0.0;
-#pragma unroll
-    for (int s = 0; s < L; ++s) {
-      if (s >= len) break;
-      double d = reg_rhs<OP>(wv, s, fc);
-      if (OP == 1 && s < 4 && (phys || s < 2)) d = ov[s < 4 ? s : 0];
-      e[s] = (s == 0) ? d : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d * t.m[s]);
-      yt = e[s];
-    }
-    double y = 0.0;
-#pragma unroll
-    for (int s = L - 1; s >= 0; --s)
-      if (s < len) y = fma_(-t.ac1[s], y, e[s]);
-    yh = y;
+  for (int s = 0; s < L; ++s) {
+    const double d = reg_rhs<OP>(wv, s, fc);
+    e[s] = (s == 0) ? d : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d * t.m[s]);
   }
+  double y = e[L - 1];
+#pragma unroll
+  for (int s = L - 2; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s]);
+  yh = y; yt = e[L - 1];
 }
-
-// ---- regular chunk, pass 3: ST(s, x) receives the solution of row s (descending) ---------
-template <int ROLE, class ST>
-ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], int len, double t_prev, double h_next, ST st) {
+// pass 3: ST(s, x) receives the solution of row s (descending)
+template <class ST>
+ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_prev, double h_next, ST st) {
   double x = h_next;
 #pragma unroll
   for (int s = ASTR_LMAX - 1; s >= 0; --s) {
-    if (ROLE != ROLE_HEAD || s < len) {
-      x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s]));
-      st(s, x);
-    }
+    x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s]));
+    st(s, x);
   }
+}
+
+// ---- head / tail block ----------------------------------------------------------------------
+// d[s]: right-hand side of slot s (any finite value on neutral slots)
+template <int S>
+ASTR_HD void spec_forward(const SpecTab<S>& t, const double (&d)[S], double (&e)[S], double& yh, double& yt) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) e[s] = (s == 0) ? d[0] * t.m[0] : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d[s] * t.m[s]);
+  yt = e[S - 1];
+  double y = 0.0;
+#pragma unroll
+  for (int s = S - 1; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s] * t.q[s]);
+  yh = y;
+}
+template <int S, class ST>
+ASTR_HD void spec_back(const SpecTab<S>& t, const double (&e)[S], double t_prev, double h_next, ST st) {
+  double x = h_next;
+#pragma unroll
+  for (int s = S - 1; s >= 0; --s) {
+    x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s] * t.q[s]));
+    st(s, x);
+  }
+}
+// right-hand sides of the head block: closure rows first, interior rows behind them
+template <int OP, bool P0, int HWN>
+ASTR_HD void head_rhs(const double (&hw)[HWN], const FilterCoef& fc, int nsf, double (&d)[ASTR_HS]) {
+  double sf[5];
+  closure_head<OP, P0>(hw, fc, sf);
+#pragma unroll
+  for (int s = 0; s < ASTR_HS; ++s) {
+    double v = reg_rhs<OP>(hw, s + (OpT<OP>::HB - OpT<OP>::H), fc);
+    if (s < 5) { if (s < nsf) v = sf[s]; }
+    d[s] = v;
+  }
+}
+// tail block: (one interior row when st == nsl + 1,) then the closure rows
+template <int OP, bool PM>
+ASTR_HD void tail_rhs(const double (&tw)[16], const FilterCoef& fc, int extra, double (&d)[ASTR_TS]) {
+  constexpr int H = OpT<OP>::H;
+  constexpr int TO = op_tail_interior_off<OP>(PM);
+  double sl[5];
+  closure_tail<OP, PM>(tw, fc, sl);
+  // the interior stencil of node n + TO reads tw[TO + 10 - H .. TO + 10 + H]
+  double ww[2 * H + 1];
+#pragma unroll
+  for (int k = 0; k <= 2 * H; ++k) ww[k] = tw[TO + 10 - H + k];
+  const double di = reg_rhs<OP>(ww, 0, fc);
+  d[0] = extra ? di : sl[0];
+#pragma unroll
+  for (int s = 1; s < ASTR_TS; ++s) d[s] = extra ? sl[s - 1] : (s < 5 ? sl[s < 5 ? s : 4] : 0.0);
 }
 
 // =======================================================================================
@@ -398,8 +432,8 @@ inline void build_lhs(int optype, int ntype, int n, double alfa, std::vector<dou
   }
 }
 
-// src/filter.F90:299-432
-inline void build_filter_coef(FilterCoef& fc, double alfa, double bh, double bb) {
+// src/filter.F90:299-432 ; flux coefficients src/flux.F90:247-262 for bfacmpld = b
+inline void build_filter_coef(FilterCoef& fc, double alfa, double bh, double bb, double b = 0.0) {
   const double c6[4] = {(11.0 + 10.0 * alfa) / 32.0, (15.0 + 34.0 * alfa) / 64.0, (-3.0 + 6.0 * alfa) / 32.0,
                         (1.0 - 2.0 * alfa) / 64.0};
   const double c8[5] = {(93.0 + 70.0 * alfa) / 256.0, (7.0 + 18.0 * alfa) / 32.0, (-7.0 + 14.0 * alfa) / 64.0,
@@ -441,60 +475,68 @@ inline void build_filter_coef(FilterCoef& fc, double alfa, double bh, double bb)
                          (15.0 - 30.0 * alfa) / 128.0, (-45.0 + 90.0 * alfa) / 1024.0,
                          (5.0 - 10.0 * alfa) / 512.0, (-1.0 + 2.0 * alfa) / 1024.0};
   for (int j = 0; j < 11; ++j) { fc.coefh[0][j] = h0[j]; fc.coefh[1][j] = h1[j]; fc.coefh[2][j] = h2[j]; }
+  // compact_flux_rhs interior coefficients (src/flux.F90:247-262)
+  fc.flx[0] = 1.0 / 18.0 - (1.0 / 36.0) * b; fc.flx[1] = 19.0 / 18.0 - (9.0 / 36.0) * b;
+  fc.flx[2] = 5.0 / 9.0 + (9.0 / 36.0) * b;  fc.flx[3] = (1.0 / 36.0) * b;
+}
+
+template <int S>
+inline void fill_spec(SpecTab<S>& t, const LocalFac& f, int len, int nclos) {
+  t.len = len; t.nclos = nclos;
+  for (int i = 0; i < S; ++i) {
+    const bool r = i < len;
+    t.m[i] = r ? f.m[i] : 0.0; t.g[i] = r ? f.g[i] : -1.0; t.q[i] = r ? 1.0 : 0.0;
+    t.ac1[i] = r ? f.ac1[i] : -1.0; t.ev[i] = r ? f.ev[i] : 0.0;
+  }
 }
 
 // a, c: the LHS rows exactly as the reference sets them (fd_scheme_initiate
-// src/derivative.F90:63-158, compact_filter_initiate src/filter.F90:31-100).
-// maxw: most regular chunks a line may be cut into (warps per CTA).
+// src/derivative.F90:63-158, compact_filter_initiate src/filter.F90:31-100, compact_flux_initiate
+// src/flux.F90:32-118).  maxw: most regular chunks a line may be cut into.  align_even (i lines):
+// node0 - H + 6 of every chunk must be even, so that the chunk windows start on a 16-byte boundary of
+// the shared-memory line (node -6 sits at an aligned position); one interior row may move to the tail block.
 inline void build_line_plan(LinePlan& p, int optype, int ntype, int n, int first_node, int nsf, int nsl,
-                            const std::vector<double>& a, const std::vector<double>& c, int maxw) {
+                            const std::vector<double>& a, const std::vector<double>& c, int maxw, bool align_even) {
   p = LinePlan();
   p.optype = optype; p.ntype = ntype; p.n = n; p.first_node = first_node;
   p.nrows = (int)a.size(); p.nsf = nsf; p.nsl = nsl;
-  const int N = p.nrows;
-  const bool p0 = (ntype == 1 || ntype == 4), pm = (ntype == 2 || ntype == 4);
-  // head / tail block = leading / trailing rows whose coefficients differ from the interior
-  const bool deriv = (optype == 0);
-  p.sh = (deriv && p0) ? 2 : 1;
-  p.st = (deriv && pm) ? 2 : 1;
-  const int nreg = N - p.sh - p.st;
-  const double alpha = (nreg > 0) ? a[p.sh] : 0.0;
+  const int N = p.nrows, L = ASTR_LMAX;
+  const int H = (optype == 1) ? 5 : 2;
   p.ok = 0;
-  if (nreg < 12 || n < 9) return;
-  for (int r = p.sh; r < N - p.st; ++r)
-    if (a[r] != alpha || c[r] != alpha) return;     // not a Toeplitz interior: not ours
-  int NW = (nreg + ASTR_LMAX - 1) / ASTR_LMAX;
-  if (NW < 2 || NW > maxw || NW + 2 > ASTR_EMAX) return;
-  // every chunk is full except chunk 0, which takes the remainder and must hold the closure
-  // right-hand-side rows of the first end
-  const int Lr = ASTR_LMAX;
-  const int len0 = nreg - (NW - 1) * Lr;
-  if (len0 < (nsf - p.sh > 1 ? nsf - p.sh : 1)) return;
-  p.NW = NW; p.Lr = Lr; p.len0 = len0; p.E = NW + 2;
+  const int nreg = N - nsf - nsl;
+  if (nreg < L || n < 12) return;
+  const double aa = a[nsf], cc = c[nsf];
+  for (int r = nsf; r < N - nsl; ++r)
+    if (a[r] != aa || c[r] != cc) return;           // not a Toeplitz interior: not ours
+  if (maxw > ASTR_NWMAX) maxw = ASTR_NWMAX;
+  int NW = nreg / L;
+  if (NW > maxw) return;
+  int rem = nreg - NW * L, rem_t = 0;
+  if (align_even && (((first_node + nsf + rem - H + 6) & 1) != 0)) {
+    if (rem == 0) { NW -= 1; rem = L; }
+    if (NW < 1) return;
+    rem -= 1; rem_t = 1;
+  }
+  p.sh = nsf + rem; p.st = nsl + rem_t; p.NW = NW; p.E = NW + 2;
+  if (p.sh > ASTR_HS || p.st > ASTR_TS) return;
   // tables
   {
-    std::vector<double> ra(ASTR_LMAX, alpha), rc(ASTR_LMAX, alpha);
-    LocalFac f = local_factor(ra, rc, 0, ASTR_LMAX, false, false);
-    for (int i = 0; i < ASTR_LMAX; ++i) { p.reg.m[i] = f.m[i]; p.reg.g[i] = f.g[i]; p.reg.ac1[i] = f.ac1[i]; p.reg.ev[i] = f.ev[i]; }
+    std::vector<double> ra(L, aa), rc(L, cc);
+    const LocalFac f = local_factor(ra, rc, 0, L, false, false);
+    for (int i = 0; i < L; ++i) { p.reg.m[i] = f.m[i]; p.reg.g[i] = f.g[i]; p.reg.ac1[i] = f.ac1[i]; p.reg.ev[i] = f.ev[i]; }
   }
   std::vector<LocalFac> fac(p.E);
   fac[0] = local_factor(a, c, 0, p.sh, true, false);
-  for (int w = 0; w < NW; ++w) fac[w + 1] = local_factor(a, c, plan_chunk_row(p, w), w == 0 ? len0 : Lr, false, false);
+  for (int w = 0; w < NW; ++w) fac[w + 1] = local_factor(a, c, plan_chunk_row(p, w), L, false, false);
   fac[p.E - 1] = local_factor(a, c, N - p.st, p.st, false, true);
-  auto fill = [](SpecTab& t, const LocalFac& f, int len) {
-    t.len = len; t.pad = 0;
-    for (int i = 0; i < ASTR_SMAX; ++i) {
-      t.m[i] = i < len ? f.m[i] : 1.0; t.g[i] = i < len ? f.g[i] : 0.0;
-      t.ac1[i] = i < len ? f.ac1[i] : 0.0; t.ev[i] = i < len ? f.ev[i] : 0.0;
-    }
-  };
-  fill(p.head, fac[0], p.sh);
-  fill(p.tail, fac[p.E - 1], p.st);
-  for (int e = 0; e < ASTR_EMAX; ++e) p.el[e] = ElemTab{0, 0, 0, 0, 0, 0, 1, 0};
+  fill_spec(p.head, fac[0], p.sh, nsf);
+  fill_spec(p.tail, fac[p.E - 1], p.st, nsl);
+  const int NE = ASTR_EMAX + 2 * ASTR_WPAD;
+  for (int e = 0; e < NE; ++e) p.el[e] = ElemTab{0, 0, 0, 0, 0, 0, 1, 0};
   double Qprev = 0.0;
   for (int e = 0; e < p.E; ++e) {          // elimination from the first end
     const LocalFac& f = fac[e];
-    ElemTab& t = p.el[e];
+    ElemTab& t = p.el[e + ASTR_WPAD];
     const double mu = 1.0 / (1.0 - f.vh * Qprev);
     const double B = mu * f.wh;
     t.gamma = f.vt * Qprev * mu;
@@ -505,7 +547,7 @@ inline void build_line_plan(LinePlan& p, int optype, int ntype, int n, int first
   double Qnext = 0.0;
   for (int e = p.E - 1; e >= 0; --e) {     // elimination from the last end (roles of v and w swapped)
     const LocalFac& f = fac[e];
-    ElemTab& t = p.el[e];
+    ElemTab& t = p.el[e + ASTR_WPAD];
     const double mu = 1.0 / (1.0 - f.wt * Qnext);
     const double B = mu * f.vt;
     t.gammap = f.wh * Qnext * mu;
@@ -513,6 +555,27 @@ inline void build_line_plan(LinePlan& p, int optype, int ntype, int n, int first
     t.Qp = f.vh + f.wh * Qnext * B;
     Qnext = t.Qp;
   }
-  for (int e = 1; e < p.E; ++e) p.el[e].D = 1.0 / (1.0 - p.el[e - 1].Q * p.el[e].Qp);
+  // P(E-1) and P'(0) are never used (they would only feed the interfaces outside the system)
+  p.el[p.E - 1 + ASTR_WPAD].K = 0.0;
+  p.el[ASTR_WPAD].Kp = 0.0;
+  for (int e = 1; e < p.E; ++e) p.el[e + ASTR_WPAD].D = 1.0 / (1.0 - p.el[e - 1 + ASTR_WPAD].Q * p.el[e + ASTR_WPAD].Qp);
+  // truncation window of the reduced scan: P(e) = S(e) - K(e) P(e-1).  A thread of element e needs P(e) and
+  // P(e-1); evaluated over the elements e-W..e, the first dropped term of P(e-1) carries the factor
+  // K(e-1) K(e-2) ... K(e-W).  Smallest W that keeps every product of W consecutive factors under 1e-20.
+  int W = 1;
+  for (; W <= p.E; ++W) {
+    double worst = 0.0;
+    for (int e = 0; e < p.E; ++e) {
+      double pk = 1.0, pkp = 1.0;
+      for (int k = 0; k < W; ++k) {
+        pk *= (e - k >= 0) ? std::fabs(p.el[e - k + ASTR_WPAD].K) : 0.0;
+        pkp *= (e + k < p.E) ? std::fabs(p.el[e + k + ASTR_WPAD].Kp) : 0.0;
+      }
+      worst = std::fmax(worst, std::fmax(pk, pkp));
+    }
+    if (worst < 1e-20) break;
+  }
+  if (W > ASTR_WPAD) return;               // slowly decaying coupling (alfa very close to 1/2): fall back
+  p.W = W;
   p.ok = 1;
 }

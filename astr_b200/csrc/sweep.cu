@@ -572,8 +572,11 @@ int launch_one(const SweepArgs& a, cudaStream_t st) {
   int sp = 0;
   const size_t smem = astr_sweep_smem_bytes(DIR, a.op.n, C, NG, &sp);
   static size_t attr_smem = 0;
-  static int occ = 0;
+  static int occ = 0, attr_dev = -1;
   auto kern = sweep_kernel<DIR, OP, C, NG>;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (dev != attr_dev) { attr_smem = 0; occ = 0; attr_dev = dev; g_num_sms = 0; }   // attributes are per device
   if (smem > attr_smem || occ == 0) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -602,356 +605,6 @@ int launch_one(const SweepArgs& a, cudaStream_t st) {
   return 0;
 }
 
-
-// -------------------------------------------------------------------------------------------------
-// Warp-per-line engine for the i direction (the line is contiguous in memory).
-// A warp owns one line: coalesced 16-byte loads bring nodes -6..n+5 into a per-warp shared line buffer,
-// lane c then owns rows [chunk32_start(c), chunk32_start(c+1)) (<= 17) in REGISTERS: right-hand sides from
-// a rotating window over the buffer (one LDS per row), forward and backward recurrences of the reference
-// (src/commfunc.F90:790-813) with zero carries, the true carries from two warp-level scans of affine maps
-// (5 shuffle steps each) instead of block barriers, solution back into the buffer and out with coalesced
-// 16-byte stores.  No CTA-level synchronisation inside the line loop: warps are independent, so the SM
-// hides latency with 16 warps of independent lines.  Same tables, closures and epilogues as above.
-// -------------------------------------------------------------------------------------------------
-constexpr int W3_WARPS = 8;           // warps per CTA
-constexpr int W3_PADF = 8;            // buffer index = node + W3_PADF (window reads of closure rows may reach node -8)
-
-template <int OP>
-__global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3_kernel(const SweepArgs a) {
-  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
-  constexpr int LCH = ASTR_W3_LCH;
-  extern __shared__ __align__(16) double sm_all[];
-  const int n = a.op.n, nrows = a.op.nrows, first_node = a.op.first_node;
-  const int nr8 = (nrows + 1) & ~1;
-  const double* __restrict__ ac1 = sm_all;
-  const double* __restrict__ ac2 = sm_all + nr8;
-  const double* __restrict__ ac3 = sm_all + 2 * nr8;
-  const double* __restrict__ pf = sm_all + 3 * nr8;
-  const double* __restrict__ qb = sm_all + 4 * nr8;
-  const int lbn = (n + 2 * W3_PADF + 2 + 1) & ~1;         // doubles per line buffer (even)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* LBa = sm_all + 5 * nr8 + (size_t)warp * 2 * lbn;   // two line buffers per warp: the next line is
-  double* LBb = LBa + lbn;                                   // fetched (cp.async) under the solve of this one
-  for (int r = threadIdx.x; r < nrows; r += W3_WARPS * 32) {
-    sm_all[r] = a.op.ac1[r];
-    sm_all[nr8 + r] = a.op.ac2[r];
-    sm_all[2 * nr8 + r] = a.op.ac3[r];
-    sm_all[3 * nr8 + r] = a.op.pf32[r];
-    sm_all[4 * nr8 + r] = a.op.qb32[r];
-  }
-  // window reads of closure rows may touch the pads: keep them finite
-  for (int t = lane; t < 2 * lbn; t += 32) LBa[t] = 0.0;
-  __syncthreads();
-
-  const Layout& L = a.L;
-  const int ra = chunk32_start(lane, nrows), rb = chunk32_start(lane + 1, nrows) - 1;
-  const int nsf = a.op.nsf, nsl = a.op.nsl;
-  const int epi = a.epi, o_lo = a.o_lo, o_hi = a.o_hi;
-  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
-  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
-  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
-  const long long wstride = (long long)gridDim.x * W3_WARPS;
-  const int npair = (n + 13) >> 1;                         // node pairs -6.. (n+5 or n+6)
-  double* LB = LBa;
-  auto F = [&](int node) -> double { return LB[node + W3_PADF]; };
-  auto row_of = [&](long long ln, int& f) -> long long {
-    const int j = (int)(ln % (L.jm + 1));
-    const int k = (int)((ln / (L.jm + 1)) % (L.km + 1));
-    f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
-    return L.idx(0, j, k);
-  };
-  // line -> buffer: 16-byte cp.async (node -6 is 16-byte aligned in global memory; W3_PADF - 6 is even)
-  auto fetch = [&](long long ln, double* buf) {
-    int f;
-    const long long off = row_of(ln, f);
-    const double* __restrict__ grow = a.in[f] + off;
-    for (int w = lane; w < npair; w += 32) cp_async16(buf + (W3_PADF - 6) + 2 * w, grow - 6 + 2 * w);
-  };
-
-  const long long ln0 = (long long)blockIdx.x * W3_WARPS + warp;
-  if (ln0 < nlines) fetch(ln0, LB);
-  for (long long ln = ln0; ln < nlines; ln += wstride) {
-    int f;
-    const long long off = row_of(ln, f);
-    double* __restrict__ orow = a.out[f] + off;
-    cp_async_wait_all();
-    __syncwarp();
-    if (ln + wstride < nlines) fetch(ln + wstride, LB == LBa ? LBb : LBa);   // in flight during the solve
-    // ---- right-hand sides and forward elimination with zero carry-in ---------------------------------
-    double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
-    if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
-    if (rb >= nrows - nsl && ra <= rb) closure_last<OP>(F, a.op.ntype, n, sl);   // lanes that own tail closure rows
-    double e[LCH];
-    double w[W];
-    {
-      const double* p = LB + W3_PADF + first_node + ra - H;
-#pragma unroll
-      for (int s = 0; s < 2 * H; ++s) w[s] = p[s];
-      w[2 * H] = 0.0;
-    }
-    double eprev = 0.0;
-#pragma unroll
-    for (int s = 0; s < LCH; ++s) {
-      const int r = ra + s;
-      if (r <= rb) {
-        w[(s + 2 * H) % W] = LB[W3_PADF + first_node + r + H];
-        double d = interior_rhs<OP>(w, s);
-        if (lane == 0 && s < nsf) d = sf[s < 5 ? s : 4];
-        if (r >= nrows - nsl) {
-          const int kk = r - (nrows - nsl);
-          d = kk == 0 ? sl[0] : kk == 1 ? sl[1] : kk == 2 ? sl[2] : kk == 3 ? sl[3] : sl[4];
-        }
-        const double ev = __fma_rn(-eprev, ac3[r], d * ac2[r]);
-        e[s] = ev;
-        eprev = ev;
-      } else {
-        e[s] = 0.0;
-      }
-    }
-    // ---- carry into each chunk: d'(ra-1) = EE(c-1) + pf(rb(c-1)) * d'(ra(c-1)-1)  (exclusive scan of x -> A x + B) --
-    double cin;
-    {
-      double A = (ra <= rb) ? pf[rb] : 1.0, B = eprev;     // an empty chunk is the identity map
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double Ap = __shfl_up_sync(0xffffffffu, A, off), Bp = __shfl_up_sync(0xffffffffu, B, off);
-        if (lane >= off) { B = __fma_rn(A, Bp, B); A = A * Ap; }
-      }
-      cin = __shfl_up_sync(0xffffffffu, B, 1);
-      if (lane == 0) cin = 0.0;
-    }
-    // ---- back substitution with zero carry-in ---------------------------------------------------------
-    double gnext = 0.0;
-#pragma unroll
-    for (int s = LCH - 1; s >= 0; --s) {
-      const int r = ra + s;
-      if (r <= rb) {
-        const double dp = __fma_rn(pf[r], cin, e[s]);
-        const double g = __fma_rn(-ac1[r], gnext, dp);
-        e[s] = g;
-        gnext = g;
-      }
-    }
-    // ---- x(rb+1) of each chunk: x(ra(c)) = GS(c) + qb(ra(c)) * x(rb(c)+1)  (suffix scan from the last chunk) -----
-    double xin;
-    {
-      double A = (ra <= rb) ? qb[ra] : 1.0, B = gnext;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double Ap = __shfl_down_sync(0xffffffffu, A, off), Bp = __shfl_down_sync(0xffffffffu, B, off);
-        if (lane + off < 32) { B = __fma_rn(A, Bp, B); A = A * Ap; }
-      }
-      xin = __shfl_down_sync(0xffffffffu, B, 1);
-      if (lane == 31) xin = 0.0;
-    }
-    __syncwarp();                      // every lane is done reading the pristine line
-#pragma unroll
-    for (int s = 0; s < LCH; ++s) {
-      const int r = ra + s;
-      if (r <= rb) LB[W3_PADF + first_node + r] = __fma_rn(qb[r], xin, e[s]);
-    }
-    __syncwarp();
-    // ---- buffer -> global, aligned node pairs, epilogue ------------------------------------------------
-    for (int nd = (w_lo & ~1) + 2 * lane; nd <= w_hi; nd += 64) {
-      const bool vx = nd >= w_lo, vy = nd + 1 <= w_hi;
-      double2 x = *reinterpret_cast<const double2*>(LB + W3_PADF + nd);
-      if (epi == EPI_ADD) {
-        if (vx) x.x = orow[nd] + x.x;
-        if (vy) x.y = orow[nd + 1] + x.y;
-      } else if (epi == EPI_STOREZ) {
-        if (nd < o_lo || nd > o_hi) x.x = 0.0;
-        if (nd + 1 < o_lo || nd + 1 > o_hi) x.y = 0.0;
-      }
-      if (vx && vy) *reinterpret_cast<double2*>(orow + nd) = x;
-      else if (vx) orow[nd] = x.x;
-      else if (vy) orow[nd + 1] = x.y;
-    }
-    __syncwarp();                      // this buffer is refilled two lines from now
-    LB = (LB == LBa) ? LBb : LBa;
-  }
-}
-
-
-// -------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (ASTR_SWEEP_W3=2; parity-tested, not yet timed): the warp-per-line engine with the overheads
-// the SASS of sweep3_kernel shows removed.  The operator tables are padded to 32 x 17 rows with neutral rows (ac2 = 1,
-// ac1 = ac3 = 0), so every lane runs the same 17 unguarded rows; per-lane base pointers turn all table and
-// buffer accesses of the unrolled rows into immediate offsets; the few rows whose right-hand side is a tail
-// closure (or padding) are recomputed afterwards by the lanes that own them.
-// -------------------------------------------------------------------------------------------------
-constexpr int W3P_LBN = 560;          // doubles per line buffer: node -8 .. first_node + 543 + H
-
-template <int OP>
-__global__ void __launch_bounds__(W3_WARPS * 32, 2) sweep3p_kernel(const SweepArgs a) {
-  constexpr int H = OpTraits<OP>::H, W = OpTraits<OP>::W;
-  constexpr int LCH = ASTR_W3_LCH, NR = ASTR_W3_ROWS;
-  extern __shared__ __align__(16) double sm_all[];
-  const int n = a.op.n, nrows = a.op.nrows, first_node = a.op.first_node;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* LBa = sm_all + 5 * NR + (size_t)warp * 2 * W3P_LBN;
-  double* LBb = LBa + W3P_LBN;
-  for (int r = threadIdx.x; r < 5 * NR; r += W3_WARPS * 32) sm_all[r] = a.op.pad5[r];
-  for (int t = lane; t < 2 * W3P_LBN; t += 32) LBa[t] = 0.0;
-  __syncthreads();
-  // per-lane views of the tables: entry s of lane c is row 17 c + s
-  const double* __restrict__ t1 = sm_all + LCH * lane;
-  const double* __restrict__ t2 = sm_all + NR + LCH * lane;
-  const double* __restrict__ t3 = sm_all + 2 * NR + LCH * lane;
-  const double* __restrict__ tp = sm_all + 3 * NR + LCH * lane;
-  const double* __restrict__ tq = sm_all + 4 * NR + LCH * lane;
-
-  const Layout& L = a.L;
-  const int nsf = a.op.nsf, nsl = a.op.nsl;
-  const int epi = a.epi, o_lo = a.o_lo, o_hi = a.o_hi;
-  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo;
-  const int w_hi = (epi == EPI_STOREZ) ? n : o_hi;
-  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
-  const long long wstride = (long long)gridDim.x * W3_WARPS;
-  const int npair = (n + 13) >> 1;
-  // k = row - (nrows - nsl): k < 0 regular row, 0 <= k < nsl tail closure row, k >= nsl padding
-  const int k0 = LCH * lane - (nrows - nsl);
-  const bool fix_tail = k0 + LCH - 1 >= 0;
-  double* LB = LBa;
-  auto F = [&](int node) -> double { return LB[node + W3_PADF]; };
-  auto row_of = [&](long long ln, int& f) -> long long {
-    const int j = (int)(ln % (L.jm + 1));
-    const int k = (int)((ln / (L.jm + 1)) % (L.km + 1));
-    f = (int)(ln / ((long long)(L.jm + 1) * (L.km + 1)));
-    return L.idx(0, j, k);
-  };
-  auto fetch = [&](long long ln, double* buf) {
-    int f;
-    const long long off = row_of(ln, f);
-    const double* __restrict__ grow = a.in[f] + off;
-    for (int w = lane; w < npair; w += 32) cp_async16(buf + (W3_PADF - 6) + 2 * w, grow - 6 + 2 * w);
-  };
-
-  const long long ln0 = (long long)blockIdx.x * W3_WARPS + warp;
-  if (ln0 < nlines) fetch(ln0, LB);
-  for (long long ln = ln0; ln < nlines; ln += wstride) {
-    int f;
-    const long long off = row_of(ln, f);
-    double* __restrict__ orow = a.out[f] + off;
-    cp_async_wait_all();
-    __syncwarp();
-    if (ln + wstride < nlines) fetch(ln + wstride, LB == LBa ? LBb : LBa);
-    double* __restrict__ lw = LB + W3_PADF + first_node + LCH * lane;      // lw[s] = f(node of row 17 lane + s)
-    double sf[5] = {0, 0, 0, 0, 0}, sl[5] = {0, 0, 0, 0, 0};
-    if (lane == 0) closure_first<OP>(F, a.op.ntype, n, sf);
-    if (fix_tail && k0 < nsl) closure_last<OP>(F, a.op.ntype, n, sl);
-    double e[LCH];
-    double w[W];
-#pragma unroll
-    for (int s = 0; s < 2 * H; ++s) w[s] = lw[s - H];
-    w[2 * H] = 0.0;
-    double eprev = 0.0;
-#pragma unroll
-    for (int s = 0; s < LCH; ++s) {
-      w[(s + 2 * H) % W] = lw[s + H];
-      double d = interior_rhs<OP>(w, s);
-      if (s < 5) { if (lane == 0 && s < nsf) d = sf[s]; }
-      const double ev = __fma_rn(-eprev, t3[s], d * t2[s]);
-      e[s] = ev;
-      eprev = ev;
-    }
-    if (fix_tail) {      // the last lanes: tail closure rows and padding get their own right-hand sides
-      double ep = 0.0;
-#pragma unroll
-      for (int s = 0; s < LCH; ++s) {
-        const int k = k0 + s;
-        if (k < 0) ep = e[s];
-        else {
-          const double d = k == 0 ? sl[0] : k == 1 ? sl[1] : k == 2 ? sl[2] : k == 3 ? sl[3] : k == 4 ? sl[4] : 0.0;
-          ep = __fma_rn(-ep, t3[s], (k < nsl ? d : 0.0) * t2[s]);
-          e[s] = ep;
-        }
-      }
-      eprev = ep;
-    }
-    double cin;
-    {
-      double A = tp[LCH - 1], B = eprev;
-#pragma unroll
-      for (int off2 = 1; off2 < 32; off2 <<= 1) {
-        const double Ap = __shfl_up_sync(0xffffffffu, A, off2), Bp = __shfl_up_sync(0xffffffffu, B, off2);
-        if (lane >= off2) { B = __fma_rn(A, Bp, B); A = A * Ap; }
-      }
-      cin = __shfl_up_sync(0xffffffffu, B, 1);
-      if (lane == 0) cin = 0.0;
-    }
-    double gnext = 0.0;
-#pragma unroll
-    for (int s = LCH - 1; s >= 0; --s) {
-      const double dp = __fma_rn(tp[s], cin, e[s]);
-      const double g = __fma_rn(-t1[s], gnext, dp);
-      e[s] = g;
-      gnext = g;
-    }
-    double xin;
-    {
-      double A = tq[0], B = gnext;
-#pragma unroll
-      for (int off2 = 1; off2 < 32; off2 <<= 1) {
-        const double Ap = __shfl_down_sync(0xffffffffu, A, off2), Bp = __shfl_down_sync(0xffffffffu, B, off2);
-        if (lane + off2 < 32) { B = __fma_rn(A, Bp, B); A = A * Ap; }
-      }
-      xin = __shfl_down_sync(0xffffffffu, B, 1);
-      if (lane == 31) xin = 0.0;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < LCH; ++s) lw[s] = __fma_rn(tq[s], xin, e[s]);
-    __syncwarp();
-    for (int nd = (w_lo & ~1) + 2 * lane; nd <= w_hi; nd += 64) {
-      const bool vx = nd >= w_lo, vy = nd + 1 <= w_hi;
-      double2 x = *reinterpret_cast<const double2*>(LB + W3_PADF + nd);
-      if (epi == EPI_ADD) {
-        if (vx) x.x = orow[nd] + x.x;
-        if (vy) x.y = orow[nd + 1] + x.y;
-      } else if (epi == EPI_STOREZ) {
-        if (nd < o_lo || nd > o_hi) x.x = 0.0;
-        if (nd + 1 < o_lo || nd + 1 > o_hi) x.y = 0.0;
-      }
-      if (vx && vy) *reinterpret_cast<double2*>(orow + nd) = x;
-      else if (vx) orow[nd] = x.x;
-      else if (vy) orow[nd + 1] = x.y;
-    }
-    __syncwarp();
-    LB = (LB == LBa) ? LBb : LBa;
-  }
-}
-
-template <int OP, bool PADDED>
-int launch3(const SweepArgs& a, cudaStream_t st) {
-  auto kern = PADDED ? sweep3p_kernel<OP> : sweep3_kernel<OP>;
-  const int nr8 = (a.op.nrows + 1) & ~1;
-  const int lbn = (a.op.n + 2 * W3_PADF + 2 + 1) & ~1;
-  const size_t smem = PADDED ? ((size_t)5 * ASTR_W3_ROWS + (size_t)W3_WARPS * 2 * W3P_LBN) * sizeof(double)
-                             : ((size_t)5 * nr8 + (size_t)W3_WARPS * 2 * lbn) * sizeof(double);
-  static size_t attr_smem = 0;
-  static int occ = 0;
-  if (smem > attr_smem || occ == 0) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_smem = smem;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W3_WARPS * 32, smem));
-    if (occ < 1) return astr_fail_msg("sweep3: kernel does not fit on an SM");
-    if (!g_num_sms) {
-      int dev = 0;
-      CUDA_OK(cudaGetDevice(&dev));
-      CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-  }
-  const Layout& L = a.L;
-  const long long nlines = (long long)a.nf * (L.km + 1) * (L.jm + 1);
-  long long grid = (long long)g_num_sms * occ;
-  const long long need = (nlines + W3_WARPS - 1) / W3_WARPS;
-  if (grid > need) grid = need;
-  kern<<<(unsigned)grid, W3_WARPS * 32, smem, st>>>(a);
-  astr_count_launch();
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 template <int DIR, int OP>
 int launch_c(const SweepArgs& a, cudaStream_t st) {
@@ -997,27 +650,6 @@ size_t astr_sweep_smem_bytes(int dir, int n, int C, int NG, int* sp_out) {
   const size_t nrows_max = (size_t)n + 8;          // >= nrows rounded up to even
   const size_t tabs = 5 * nrows_max + ((nrows_max + 15) & ~(size_t)15) / 8;
   return (tabs + (size_t)NG * (tile + 2 * (size_t)C * ASTR_BW)) * sizeof(double);
-}
-
-// i direction only; lines of 8*32 .. 17*32 rows (every lane chunk then holds the H-row window and, at the two
-// ends, the closure rows).  Returns -1 when it does not apply: the caller uses the shared-memory engine.
-int astr_launch_sweep3(int optype, const SweepArgs& a, int variant, cudaStream_t st) {
-  if (!a.op.pf32 || a.op.nrows < 8 * 32 || a.op.nrows > ASTR_W3_LCH * 32) return -1;   // < 256 rows: too few lanes busy
-  if (a.nf < 1 || a.nf > ASTR_MAXF) return astr_fail_msg("sweep: bad field count");
-  if (variant == 2 && a.op.pad5 && a.op.first_node >= -3 && a.op.n + 6 + W3_PADF < W3P_LBN) {   // experimental padded variant
-    switch (optype) {
-      case OP_DERIV: return launch3<OP_DERIV, true>(a, st);
-      case OP_FILTER: return launch3<OP_FILTER, true>(a, st);
-      case OP_FLUXP: return launch3<OP_FLUXP, true>(a, st);
-      default: return launch3<OP_FLUXM, true>(a, st);
-    }
-  }
-  switch (optype) {
-    case OP_DERIV: return launch3<OP_DERIV, false>(a, st);
-    case OP_FILTER: return launch3<OP_FILTER, false>(a, st);
-    case OP_FLUXP: return launch3<OP_FLUXP, false>(a, st);
-    default: return launch3<OP_FLUXM, false>(a, st);
-  }
 }
 
 int astr_launch_sweep(int dir, int optype, const SweepArgs& a, cudaStream_t st) {

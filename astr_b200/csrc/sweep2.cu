@@ -1,23 +1,30 @@
-// astr_b200/csrc/sweep2.cu -- register-resident batched line solves (sm_100a), j and k sweeps.
+// astr_b200/csrc/sweep2.cu -- register-resident batched line solves (sm_100a), all three directions.
 //
-// Operators: `fds%central` (src/derivative.F90:171-306) and `compact_filter`
-// (src/filter.F90:112-285), same closures and coefficient tables as sweep.cu; the algebra
-// (fresh-start chunk factorisation + two-sided reduced scan) is documented in linecore.h.
+// Operators: `fds%central` (src/derivative.F90:171-306), `compact_filter` (src/filter.F90:112-285)
+// and `flux_compact` (src/flux.F90:125-266): same closures and coefficient tables as the reference;
+// the algebra (fresh-start chunk factorisation + truncated two-sided reduced scan) is documented in
+// linecore.h.
 //
-// Mapping.  A CTA owns a bundle of 32 neighbouring pencils (32 consecutive i => every line
-// position is one contiguous 256-byte segment) and the whole line of each.
-//  * TMA: one elected thread fetches the bundle as 2-3 `cp.async.bulk.tensor` boxes of
-//    (32 pencils x <=256 line nodes) into a [node][32] shared-memory tile, completion on an
-//    mbarrier.  The fetch of bundle b+1 is issued as soon as every warp has copied its rows of
-//    bundle b into registers, so it runs under the arithmetic and the write-out of bundle b.
-//  * warp w owns regular chunk w (<= 33 rows) of all 32 lines, lane = pencil: rows (+ stencil
-//    overlap) come from the tile with immediate-offset, conflict-free LDS.64; the recurrences
-//    run in registers; the coefficient tables live in __constant__ memory and are consumed as
-//    immediate constant-bank operands.
-//  * one named barrier per phase; the chunk boundary values of all elements of a pencil are
-//    exchanged through 2 doubles per thread (S, S') and resolved by a redundant scan.
-//  * the solution goes straight from registers to global memory, 256 contiguous bytes per warp
-//    and row.  HBM traffic: 1 read + 1 write per node.
+// Mapping.  A CTA owns a BUNDLE of 32 neighbouring pencils and the whole line of each; lane = pencil.
+//  * warps 0..NW-1: regular chunk w (ASTR_LMAX rows) of all 32 lines.  Rows (+ stencil overlap) are
+//    copied once from the shared-memory tile into registers; the three recurrences run in registers
+//    with the coefficient tables as immediate constant-bank operands.  All regular warps execute the
+//    same straight-line code, so none of them is the straggler of a barrier.
+//  * warp NW ("special warp"): the head and tail blocks (closure rows + the rows that do not fill a
+//    chunk), and the producer: it refills the tile as soon as every warp has arrived on the `empty`
+//    mbarrier -- the regular warps never block on a CTA barrier between reading the tile and
+//    publishing their boundary sums.
+//  * one named barrier per bundle: after it every element resolves its two boundary values from the
+//    published sums S / S' of the W nearest elements.
+// j / k sweeps (sweep2_kernel): 32 consecutive i => every line position is one contiguous 256-byte
+//    segment.  TMA (`cp.async.bulk.tensor`, 2-3 boxes of 32 pencils x <=256 nodes) fills a [node][32]
+//    tile, completion on the `full` mbarrier; the solution goes straight from registers to global
+//    memory, 256 contiguous bytes per warp and row.
+// i sweeps (sweep2i_kernel): 32 consecutive j, each line contiguous in memory.  One bulk copy
+//    (`cp.async.bulk.shared.global`) per line fills a [line][node] tile whose row pitch is 2 (mod 16)
+//    doubles, so that the lane-per-line 16-byte accesses (LDS.128 / STS.128) are conflict-free; the
+//    solution is staged through a 16-line output tile and leaves as full, aligned 128-byte lines.
+// HBM traffic: 1 read + 1 write per node.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdio>
@@ -25,16 +32,40 @@
 namespace {
 
 // operator tables: written once per (operator, direction) by astr_sweep2_set_plan
-__constant__ LinePlan c_plan[2][3];
+__constant__ LinePlan c_plan[4][3];
 __constant__ FilterCoef c_fc2;
+
+constexpr int ESZ = ASTR_EMAX + 2 * ASTR_WPAD;   // padded element slots of the S / S' exchange
+
+struct FastDiv {           // n / d for 0 <= n < 2^31 without a hardware divide
+  unsigned d, m, s1, s2;
+};
+FastDiv make_fastdiv(unsigned d) {
+  FastDiv f;
+  f.d = d;
+  unsigned l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l < 1 ? 0 : l - 1;
+  return f;
+}
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) {
+  const unsigned t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
 
 struct Sweep2Args {
   Layout L;
-  int NW;
-  int rb, nbox;              // line nodes per TMA box, boxes per bundle
-  int slot[ASTR_MAXF];       // 4th tensor coordinate of each input field
+  int rb, nbox;              // j/k: line nodes per TMA box, boxes per bundle
+  int sp;                    // i: row pitch of the shared-memory line tile (doubles, == 2 mod 16)
+  int slot[ASTR_MAXF];       // j/k: 4th tensor coordinate of each input field
+  const double* in[ASTR_MAXF];
   double* out[ASTR_MAXF];
   int nf, epi, o_lo, o_hi;
+  FastDiv dx, dxy;           // bundle index -> (bx, by, bz)
+  int nby;
+  FastDiv dpair;             // i: copy-out item -> (line, node pair)
 };
 
 __device__ __forceinline__ void cta_sync(int id, int nthreads) {
@@ -53,6 +84,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
   unsigned ok;
@@ -68,191 +102,230 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-struct BundlePos { int i0, by, bz; };
+struct BundlePos { int bx, by, bz; };
+__device__ __forceinline__ BundlePos locate(unsigned bnd, const Sweep2Args& a) {
+  BundlePos p;
+  const unsigned q = fdiv(bnd, a.dx);
+  p.bx = (int)(bnd - q * a.dx.d);
+  const unsigned z = fdiv(bnd, a.dxy);
+  p.bz = (int)z;
+  p.by = (int)(q - z * (unsigned)a.nby);
+  return p;
+}
 
-// One instantiation per warp role, each with its own bundle loop (register allocation of the
-// hot ROLE_MID path is not polluted by the closure code); all warps of the CTA meet at the
-// same named barriers.
-template <int DIR, int OP, int role>
-__device__ __forceinline__ void role_loop(const Sweep2Args& a, const CUtensorMap* tm, const double* tile,
-                                          double (*sS)[ASTR_EMAX][32], double (*sP)[ASTR_EMAX][32],
-                                          unsigned long long* mbar) {
+// epilogue of one solution value: is node written, and with what
+struct OutRange {
+  int w_lo, w_hi, o_lo, o_hi, storez;
+  __device__ __forceinline__ OutRange(const Sweep2Args& a, int n)
+      : w_lo(a.epi == EPI_STOREZ ? 0 : a.o_lo), w_hi(a.epi == EPI_STOREZ ? n : a.o_hi), o_lo(a.o_lo), o_hi(a.o_hi),
+        storez(a.epi == EPI_STOREZ) {}
+  __device__ __forceinline__ bool writes(int node) const { return node >= w_lo && node <= w_hi; }
+  __device__ __forceinline__ double value(int node, double x) const {
+    return (storez && (node < o_lo || node > o_hi)) ? 0.0 : x;
+  }
+};
+
+// head / tail block right-hand sides, dispatched on the (warp-uniform) end types
+template <int OP, int HWN>
+__device__ __forceinline__ void head_rhs_any(bool p0, const double (&hw)[HWN], const FilterCoef& fc, int nsf,
+                                             double (&d)[ASTR_HS]) {
+  if (p0) head_rhs<OP, true>(hw, fc, nsf, d);
+  else head_rhs<OP, false>(hw, fc, nsf, d);
+}
+template <int OP>
+__device__ __forceinline__ void tail_rhs_any(bool pm, const double (&tw)[16], const FilterCoef& fc, int extra,
+                                             double (&d)[ASTR_TS]) {
+  if (pm) tail_rhs<OP, true>(tw, fc, extra, d);
+  else tail_rhs<OP, false>(tw, fc, extra, d);
+}
+
+// =============================================================================================
+// j / k sweeps
+// =============================================================================================
+template <int DIR, int OP>
+__device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* tile, double (*sS)[ESZ][32],
+                                             double (*sP)[ESZ][32], unsigned long long* full, unsigned long long* empty) {
   constexpr int H = OpT<OP>::H;
   constexpr int L = ASTR_LMAX;
   constexpr int WN = L + 2 * H;
-
   const LinePlan& pl = c_plan[OP][DIR];
   const FilterCoef& fc = c_fc2;
   const Layout& Lay = a.L;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int NW = pl.NW, E = pl.E, n = pl.n;
-  const int len = (role == ROLE_HEAD) ? pl.len0 : L;
+  const int n = pl.n;
   const int node0 = pl.first_node + plan_chunk_row(pl, w);
-  const bool p0 = (pl.ntype == 1 || pl.ntype == 4), pm = (pl.ntype == 2 || pl.ntype == 4);
-  const int epi = a.epi, o_lo = a.o_lo, o_hi = a.o_hi;
-  const int w_lo = (epi == EPI_STOREZ) ? 0 : o_lo, w_hi = (epi == EPI_STOREZ) ? n : o_hi;
+  const OutRange R(a, n);
   // a chunk whose rows are all written unmodified needs no per-row range checks
-  const bool plain = node0 >= o_lo && node0 + len - 1 <= o_hi;
+  const bool plain = node0 >= a.o_lo && node0 + L - 1 <= a.o_hi;
   const int me = w + 1;
-  const int nthreads = NW * 32;
-
-  const int nbx = (Lay.im + 32) / 32;
-  const int nby = (DIR == 2 ? Lay.jm : Lay.km) + 1;
-  const int nbundles = nbx * nby * a.nf;
+  const int nthreads = (pl.NW + 1) * 32;
+  const int nbundles = (int)(a.dxy.d * (unsigned)a.nf);
   const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);   // bytes per line step
-  const unsigned tile_bytes = (unsigned)(a.rb * a.nbox) * 256u;
-
-  auto locate = [&](int bnd) {
-    BundlePos p;
-    p.i0 = (bnd % nbx) * 32; p.by = (bnd / nbx) % nby; p.bz = bnd / (nbx * nby);
-    return p;
-  };
-  // elected thread: fetch one bundle into the tile.  Tensor coordinates (x, y, z, slot) =
-  // (i + 16, j + 5, k + 5, field); out-of-range columns of a ragged bundle are zero-filled.
-  auto fetch = [&](int bnd) {
-    const BundlePos p = locate(bnd);
-    mbar_expect_tx(mbar, tile_bytes);
-    for (int b = 0; b < a.nbox; ++b) {
-      void* dst = const_cast<double*>(tile) + (size_t)b * a.rb * 32;
-      if (DIR == 1) tma_load_4d(dst, tm, p.i0 + ASTR_IOFF, b * a.rb, p.by + ASTR_HM, a.slot[p.bz], mbar);
-      else tma_load_4d(dst, tm, p.i0 + ASTR_IOFF, p.by + ASTR_HM, b * a.rb, a.slot[p.bz], mbar);
-    }
-  };
-
-  if (role == ROLE_HEAD && lane == 0 && (int)blockIdx.x < nbundles) fetch(blockIdx.x);
 
   // tl[node * 32] = f(node) of this thread's pencil
   const double* tl = tile + ASTR_HM * 32 + lane;
+  const double* wp = tl + (node0 - H) * 32;
   unsigned phase = 0;
   int par = 0;
   for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
-    const BundlePos bp = locate(bnd);
-    // lanes past the last pencil of a ragged bundle compute on halo / zero-filled columns and
-    // write into the unused row padding (columns -16..-9 of the same rows): no predication
-    const int valid = (bp.i0 + lane) <= Lay.im;
-    const int icol = valid ? bp.i0 + lane : -ASTR_IOFF + (lane & 7);
+    const BundlePos bp = locate(bnd, a);
+    const int i0 = bp.bx * 32;
+    // lanes past the last pencil of a ragged bundle compute on halo / zero-filled columns; their stores are
+    // predicated off
+    const int valid = (i0 + lane) <= Lay.im;
+    const int icol = valid ? i0 + lane : 0;
     double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
-    double* sSp = &sS[par][0][lane];
-    double* sPp = &sP[par][0][lane];
 
-    mbar_wait(mbar, phase);
+    mbar_wait(full, phase);
     phase ^= 1;
-
-    // ---- phase A: tile -> registers ----------------------------------------------------------
-    double ov[4] = {0, 0, 0, 0};
-    double sd[5] = {0, 0, 0, 0, 0};  // closure right-hand sides of this end
-    if (role == ROLE_HEAD) {
-      double hw[14];
-#pragma unroll
-      for (int k = 0; k < 14; ++k) hw[k] = tl[(k - 5) * 32];
-      closure_head<OP>(hw, p0, fc, sd);
-    } else if (role == ROLE_TAIL) {
-      double tw[14];
-      const double* p = tl + (n - 8) * 32;
-#pragma unroll
-      for (int k = 0; k < 14; ++k) tw[k] = p[k * 32];
-      closure_tail<OP>(tw, pm, fc, sd);
-    }
-    // the chunk (+ stencil overlap).  Window slots outside the halo (filter, interface ends:
-    // 2 slots) only feed rows whose right-hand side is a closure row.
+    // ---- tile -> registers: the chunk (+ stencil overlap) -------------------------------------
     double wv[WN];
-    {
-      const double* p = tl + (node0 - H) * 32;
 #pragma unroll
-      for (int s = 0; s < WN; ++s) {
-        bool skip = false;
-        if (OP == 1 && role == ROLE_HEAD && !p0 && s < 2) skip = true;
-        if (OP == 1 && role == ROLE_TAIL && !pm && s >= WN - 2) skip = true;
-        if (role == ROLE_HEAD && s >= len + 2 * H) skip = true;
-        wv[s] = skip ? 0.0 : p[s * 32];
-      }
-    }
-    cta_sync(1, nthreads);          // every warp holds its rows: the tile may be overwritten
-    if (role == ROLE_HEAD && lane == 0 && bnd + (int)gridDim.x < nbundles) fetch(bnd + gridDim.x);
+    for (int s = 0; s < WN; ++s) wv[s] = wp[s * 32];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty);      // this warp is done with the tile
 
-    // ---- phase B: eliminate, publish S / S' --------------------------------------------------
-    double se[ASTR_SMAX] = {0, 0};   // forward-eliminated rows of the head / tail block
-    if (role == ROLE_HEAD) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ov[k] = (pl.sh == 1) ? sd[1 + k] : (k < 3 ? sd[(2 + k) < 5 ? 2 + k : 4] : 0.0);
-      double yh, yt;
-      spec_forward(pl.head, sd, se, yh, yt);
-      sSp[0] = fma_(pl.el[0].gamma, yh, yt);
-      sPp[0] = fma_(pl.el[0].gammap, yt, yh);
-    } else if (role == ROLE_TAIL) {
-      // rows nrows-nsl .. nrows-st-1 are regular rows with a closure right-hand side
-      const int nov_t = pl.nsl - pl.st;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ov[k] = sd[k];
-      double dt[ASTR_SMAX];
-#pragma unroll
-      for (int k = 0; k < ASTR_SMAX; ++k) {
-        double v = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
-          if (j == nov_t + k) v = sd[j];
-        dt[k] = v;
-      }
-      double yh, yt;
-      spec_forward(pl.tail, dt, se, yh, yt);
-      sSp[(E - 1) * 32] = fma_(pl.el[E - 1].gamma, yh, yt);
-      sPp[(E - 1) * 32] = fma_(pl.el[E - 1].gammap, yt, yh);
-    }
+    // ---- eliminate, publish S / S' ------------------------------------------------------------
     double e[L];
     {
       double yh, yt;
-      chunk_forward<OP, role>(pl.reg, fc, wv, len, role == ROLE_HEAD ? p0 : pm, ov, e, yh, yt);
-      sSp[me * 32] = fma_(pl.el[me].gamma, yh, yt);
-      sPp[me * 32] = fma_(pl.el[me].gammap, yt, yh);
+      chunk_forward<OP>(pl.reg, fc, wv, e, yh, yt);
+      sS[par][me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt);
+      sP[par][me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
     }
-    cta_sync(2, nthreads);
+    cta_sync(1, nthreads);
 
-    // ---- phase C: boundary values of this chunk, solution, write-out -------------------------
-    const ScanOut so = reduced_scan(
-        pl, [&](int el) { return sSp[el * 32]; }, [&](int el) { return sPp[el * 32]; }, me);
-    const double t_prev = scan_t_prev(pl, me, so.Pm1, so.Pb0);
-    const double h_next = scan_h_next(pl, me, so.Pm, so.Pb1);
+    // ---- boundary values of this chunk, solution, write-out -----------------------------------
+    const double* sSl = &sS[par][0][lane];
+    const double* sPl = &sP[par][0][lane];
+    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * 32]; }, [&](int idx) { return sPl[idx * 32]; }, me);
+    double* po = gout + (long long)node0 * (gl8 / 8);
+    if (plain) {
+      chunk_back(pl.reg, e, so.t_prev, so.h_next, [&](int s, double x) { st_if(row_ptr(po, gl8, s), x, valid); });
+    } else {
+      chunk_back(pl.reg, e, so.t_prev, so.h_next, [&](int s, double x) {
+        const int node = node0 + s;
+        st_if(row_ptr(po, gl8, s), R.value(node, x), valid && R.writes(node));
+      });
+    }
+    // sS/sP are double-buffered by bundle parity: a warp can run at most one barrier ahead of the slowest one
+  }
+}
 
-    auto put = [&](int node, double x) {
-      if (node >= w_lo && node <= w_hi) {
-        if (epi == EPI_STOREZ && (node < o_lo || node > o_hi)) x = 0.0;
-        gout[(long long)node * (gl8 / 8)] = x;
-      }
-    };
+template <int DIR, int OP>
+__device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensorMap* tm, const double* tile,
+                                             double (*sS)[ESZ][32], double (*sP)[ESZ][32], unsigned long long* full,
+                                             unsigned long long* empty) {
+  constexpr int H = OpT<OP>::H, HB = OpT<OP>::HB;
+  constexpr int HWN = ASTR_HS + HB + H;
+  const LinePlan& pl = c_plan[OP][DIR];
+  const FilterCoef& fc = c_fc2;
+  const Layout& Lay = a.L;
+  const int lane = threadIdx.x & 31;
+  const int n = pl.n, E = pl.E;
+  const bool p0 = (pl.ntype == 1 || pl.ntype == 4), pm = (pl.ntype == 2 || pl.ntype == 4);
+  const OutRange R(a, n);
+  const int nthreads = (pl.NW + 1) * 32;
+  const int nbundles = (int)(a.dxy.d * (unsigned)a.nf);
+  const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);
+  const unsigned tile_bytes = (unsigned)(a.rb * a.nbox) * 256u;
+  const int hwlim = max(14, pl.sh + HB + H);          // 14: reach of the closure rows
+  const int hnode0 = pl.first_node - HB;              // node of window slot 0
+  const int tnode0 = pl.first_node + pl.nrows - pl.st; // node of the first tail row
+
+  // elected thread: fetch one bundle into the tile.  Tensor coordinates (x, y, z, slot) =
+  // (i + 16, j + 5, k + 5, field); out-of-range columns of a ragged bundle are zero-filled.
+  auto fetch = [&](int bnd) {
+    const BundlePos p = locate(bnd, a);
+    mbar_expect_tx(full, tile_bytes);
+    for (int b = 0; b < a.nbox; ++b) {
+      void* dst = const_cast<double*>(tile) + (size_t)b * a.rb * 32;
+      if (DIR == 1) tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, b * a.rb, p.by + ASTR_HM, a.slot[p.bz], full);
+      else tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, p.by + ASTR_HM, b * a.rb, a.slot[p.bz], full);
+    }
+  };
+  if (lane == 0 && (int)blockIdx.x < nbundles) fetch(blockIdx.x);
+  __syncwarp();
+
+  const double* tl = tile + ASTR_HM * 32 + lane;
+  const double* hp = tl + hnode0 * 32;
+  const double* tp = tl + (n - 10) * 32;
+  unsigned phase = 0;
+  int par = 0;
+  for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
+    const BundlePos bp = locate(bnd, a);
+    const int i0 = bp.bx * 32;
+    const int valid = (i0 + lane) <= Lay.im;
+    const int icol = valid ? i0 + lane : 0;
+    double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
+
+    mbar_wait(full, phase);
+    // ---- tile -> right-hand sides of the two blocks (the windows die before the tile is released) ----
+    double dh[ASTR_HS], dt[ASTR_TS];
     {
-      // rows of chunk 0 can only fall below the written range, rows of the last chunk only
-      // above it (the other end is at least one full chunk away)
-      double* po = gout + (long long)node0 * (gl8 / 8);
-      const int s_lo = w_lo - node0, s_hi = w_hi - node0, z_lo = o_lo - node0, z_hi = o_hi - node0;
-      if (role == ROLE_MID || plain) {
-        chunk_back<role == ROLE_HEAD ? ROLE_HEAD : ROLE_MID>(pl.reg, e, len, t_prev, h_next,
-                                                             [&](int s, double x) { st_if(row_ptr(po, gl8, s), x, valid); });
-      } else if (role == ROLE_HEAD) {
-        chunk_back<ROLE_HEAD>(pl.reg, e, len, t_prev, h_next, [&](int s, double x) {
-          if (s >= s_lo) *row_ptr(po, gl8, s) = (epi == EPI_STOREZ && s < z_lo) ? 0.0 : x;
-        });
-      } else {
-        chunk_back<ROLE_MID>(pl.reg, e, len, t_prev, h_next, [&](int s, double x) {
-          if (s <= s_hi) *row_ptr(po, gl8, s) = (epi == EPI_STOREZ && s > z_hi) ? 0.0 : x;
-        });
+      double hw[HWN], tw[16];
+#pragma unroll
+      for (int k = 0; k < HWN; ++k) {
+        bool in = k < hwlim;
+        if (k < 3) in = in && (hnode0 + k >= -ASTR_HM);   // filter, interface end: slots in front of the halo
+        hw[k] = in ? hp[k * 32] : 0.0;
       }
-    }
-    if (role == ROLE_HEAD) {   // element 0: P(0) = Pm1, P'(1) = Pb0 of element 1
-      double x[ASTR_SMAX];
-      spec_back(pl.head, se, 0.0, scan_h_next(pl, 0, so.Pm1, so.Pb0), x);
 #pragma unroll
-      for (int k = 0; k < ASTR_SMAX; ++k)
-        if (k < pl.sh) put(pl.first_node + k, x[k]);
-    } else if (role == ROLE_TAIL) {   // element E-1: P(E-2) = Pm, P'(E-1) = Pb1 of element E-2
-      double x[ASTR_SMAX];
-      spec_back(pl.tail, se, scan_t_prev(pl, E - 1, so.Pm, so.Pb1), 0.0, x);
-#pragma unroll
-      for (int k = 0; k < ASTR_SMAX; ++k)
-        if (k < pl.st) put(pl.first_node + pl.nrows - pl.st + k, x[k]);
+      for (int k = 0; k < 16; ++k) tw[k] = tp[k * 32];
+      head_rhs_any<OP>(p0, hw, fc, pl.nsf, dh);
+      tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
-    // sS/sP are double-buffered by bundle parity: a warp can run at most one barrier ahead of
-    // the slowest one, so phase B of the next bundle never overwrites values still being read
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty);
+
+    // ---- eliminate, publish S / S' -------------------------------------------------------------
+    double he[ASTR_HS], te[ASTR_TS];
+    {
+      double yh, yt;
+      spec_forward(pl.head, dh, he, yh, yt);
+      sS[par][ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gamma, yh, yt);
+      sP[par][ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
+      spec_forward(pl.tail, dt, te, yh, yt);
+      sS[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
+      sP[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+    }
+    // producer: every warp has copied its rows into registers -> the tile may be overwritten
+    if (lane == 0 && bnd + (int)gridDim.x < nbundles) {
+      mbar_wait(empty, phase);
+      fetch(bnd + gridDim.x);
+    }
+    __syncwarp();
+    phase ^= 1;
+    cta_sync(1, nthreads);
+
+    // ---- solution of the two blocks, write-out --------------------------------------------------
+    const double* sSl = &sS[par][0][lane];
+    const double* sPl = &sP[par][0][lane];
+    auto GS = [&](int idx) { return sSl[idx * 32]; };
+    auto GP = [&](int idx) { return sPl[idx * 32]; };
+    {
+      const ScanOut so = reduced_scan(pl, GS, GP, 0);
+      double* po = gout + (long long)pl.first_node * (gl8 / 8);
+      const int sh = pl.sh;
+      spec_back(pl.head, he, so.t_prev, so.h_next, [&](int s, double x) {
+        const int node = pl.first_node + s;
+        st_if(row_ptr(po, gl8, s), R.value(node, x), valid && s < sh && R.writes(node));
+      });
+    }
+    {
+      const ScanOut so = reduced_scan(pl, GS, GP, E - 1);
+      double* po = gout + (long long)tnode0 * (gl8 / 8);
+      const int st = pl.st;
+      spec_back(pl.tail, te, so.t_prev, so.h_next, [&](int s, double x) {
+        const int node = tnode0 + s;
+        st_if(row_ptr(po, gl8, s), R.value(node, x), valid && s < st && R.writes(node));
+      });
+    }
   }
 }
 
@@ -260,18 +333,240 @@ template <int DIR, int OP>
 __global__ void __launch_bounds__(512, 1)
 sweep2_kernel(const __grid_constant__ Sweep2Args a, const __grid_constant__ CUtensorMap tm) {
   extern __shared__ __align__(128) double tile[];
-  __shared__ double sS[2][ASTR_EMAX][32];
-  __shared__ double sP[2][ASTR_EMAX][32];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ double sS[2][ESZ][32];
+  __shared__ double sP[2][ESZ][32];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const int NW = c_plan[OP][DIR].NW;
+  for (int i = threadIdx.x; i < 2 * ESZ * 32; i += blockDim.x) { (&sS[0][0][0])[i] = 0.0; (&sP[0][0][0])[i] = 0.0; }
   if (threadIdx.x == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], NW + 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int w = threadIdx.x >> 5;
-  if (w == 0) role_loop<DIR, OP, ROLE_HEAD>(a, &tm, tile, sS, sP, &mbar);
-  else if (w == a.NW - 1) role_loop<DIR, OP, ROLE_TAIL>(a, &tm, tile, sS, sP, &mbar);
-  else role_loop<DIR, OP, ROLE_MID>(a, &tm, tile, sS, sP, &mbar);
+  if (w < NW) regular_loop<DIR, OP>(a, tile, sS, sP, &mbar[0], &mbar[1]);
+  else special_loop<DIR, OP>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
+}
+
+// =============================================================================================
+// i sweeps
+// =============================================================================================
+// regular chunk: x of rows s = 0..L-1 into the output tile row `orow` (node0 at column c0)
+template <int OP>
+__device__ __forceinline__ void stage_chunk(double* orow, const double (&x)[ASTR_LMAX]) {
+  constexpr int L = ASTR_LMAX;
+  // orow is the address of row 0's node; it is 16-byte aligned when H is even (node0 - H + 6 is even)
+  if ((OpT<OP>::H & 1) == 0) {
+#pragma unroll
+    for (int s = 0; s < L; s += 2) *reinterpret_cast<double2*>(orow + s) = make_double2(x[s], x[s + 1]);
+  } else {
+    orow[0] = x[0];
+#pragma unroll
+    for (int s = 1; s + 1 < L; s += 2) *reinterpret_cast<double2*>(orow + s) = make_double2(x[s], x[s + 1]);
+    orow[L - 1] = x[L - 1];
+  }
+}
+
+// state shared by the two role loops of the i kernel
+struct ICtx {
+  double* tin;               // [32][sp]: column c of a row = node c - 6
+  double* tout;              // [16][sp]
+  double (*sS)[32];          // [ESZ][32]
+  double (*sP)[32];
+  unsigned long long* full;
+  unsigned long long* empty;
+  int sp, nthreads, nbundles, pl0, npairs;
+};
+
+// registers -> output tile happened for the lanes of round r; now the tile leaves as full aligned lines
+__device__ __forceinline__ void copy_out_round(const Sweep2Args& a, const ICtx& c, const OutRange& R, double* __restrict__ gout,
+                                               int j0, int by, int r) {
+  const Layout& Lay = a.L;
+  cta_sync(2, c.nthreads);
+  const int nl = min(16, Lay.jm - (j0 + 16 * r) + 1);     // valid lines of this round
+  for (int it = threadIdx.x; it < nl * c.npairs; it += c.nthreads) {
+    const int ll = (int)fdiv((unsigned)it, a.dpair);
+    const int node = c.pl0 + 2 * (it - ll * c.npairs);
+    const double2 v = *reinterpret_cast<const double2*>(c.tout + ll * c.sp + 6 + node);
+    double* po = gout + Lay.idx(node, j0 + 16 * r + ll, by);
+    const bool w0 = R.writes(node), w1 = R.writes(node + 1);
+    if (w0 && w1) *reinterpret_cast<double2*>(po) = make_double2(R.value(node, v.x), R.value(node + 1, v.y));
+    else if (w0) po[0] = R.value(node, v.x);
+    else if (w1) po[1] = R.value(node + 1, v.y);
+  }
+  // after round 1 the output tile is next written behind barrier 1 of the following bundle
+  if (r == 0) cta_sync(3, c.nthreads);
+}
+
+template <int OP>
+__device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& c) {
+  constexpr int H = OpT<OP>::H;
+  constexpr int L = ASTR_LMAX;
+  constexpr int WN = L + 2 * H;
+  const LinePlan& pl = c_plan[OP][0];
+  const FilterCoef& fc = c_fc2;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const OutRange R(a, pl.n);
+  const int node0 = pl.first_node + plan_chunk_row(pl, w);
+  const int me = w + 1;
+  // 16-byte loads: node0 - H + 6 is even (build_line_plan, align_even)
+  const double2* wp = reinterpret_cast<const double2*>(c.tin + lane * c.sp + 6 + (node0 - H));
+  double* orow = c.tout + (lane & 15) * c.sp + 6 + node0;
+  const double* sSl = &c.sS[0][lane];
+  const double* sPl = &c.sP[0][lane];
+  unsigned phase = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x) {
+    const BundlePos bp = locate(bnd, a);
+    mbar_wait(c.full, phase);
+    phase ^= 1;
+    double wv[WN];
+#pragma unroll
+    for (int s = 0; s < WN / 2; ++s) { const double2 v = wp[s]; wv[2 * s] = v.x; wv[2 * s + 1] = v.y; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.empty);
+    double e[L];
+    {
+      double yh, yt;
+      chunk_forward<OP>(pl.reg, fc, wv, e, yh, yt);
+      c.sS[me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt);
+      c.sP[me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
+    }
+    cta_sync(1, c.nthreads);
+    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * 32]; }, [&](int idx) { return sPl[idx * 32]; }, me);
+    {
+      double x = so.h_next;
+#pragma unroll
+      for (int s = L - 1; s >= 0; --s) {
+        x = fma_(-pl.reg.ac1[s], x, fma_(-pl.reg.ev[s], so.t_prev, e[s]));
+        e[s] = x;
+      }
+    }
+    // two rounds of 16 lines: registers -> output tile -> global
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      if ((lane >> 4) == r) stage_chunk<OP>(orow, e);
+      copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
+    }
+  }
+}
+
+template <int OP>
+__device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& c) {
+  constexpr int H = OpT<OP>::H, HB = OpT<OP>::HB;
+  constexpr int HWN = ASTR_HS + HB + H;
+  const LinePlan& pl = c_plan[OP][0];
+  const FilterCoef& fc = c_fc2;
+  const Layout& Lay = a.L;
+  const int lane = threadIdx.x & 31;
+  const int n = pl.n, E = pl.E;
+  const OutRange R(a, n);
+  const unsigned line_bytes = (unsigned)(((n + 13) & ~1) * 8);   // nodes -6..n+5 (+1 when n is odd)
+  const bool p0 = (pl.ntype == 1 || pl.ntype == 4), pm = (pl.ntype == 2 || pl.ntype == 4);
+  const int hwlim = max(14, pl.sh + HB + H);
+  const int hnode0 = pl.first_node - HB;
+  const int tnode0 = pl.first_node + pl.nrows - pl.st;
+  const double* lrow = c.tin + lane * c.sp + 6;            // lrow[node] = f(node) of this thread's line
+  double* orow = c.tout + (lane & 15) * c.sp + 6;          // orow[node]
+  const double* sSl = &c.sS[0][lane];
+  const double* sPl = &c.sP[0][lane];
+
+  // producer: one bulk copy per line of the bundle
+  auto fetch = [&](int bnd) {
+    const BundlePos p = locate(bnd, a);
+    const int j0 = p.bx * 32;
+    const int nvalid = min(32, Lay.jm - j0 + 1);
+    if (lane == 0) mbar_expect_tx(c.full, line_bytes * (unsigned)nvalid);
+    __syncwarp();
+    if (lane < nvalid) bulk_load(c.tin + lane * c.sp, a.in[p.bz] + Lay.idx(-6, j0 + lane, p.by), line_bytes, c.full);
+  };
+  if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x);
+
+  unsigned phase = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x) {
+    const BundlePos bp = locate(bnd, a);
+    mbar_wait(c.full, phase);
+    double dh[ASTR_HS], dt[ASTR_TS];
+    {
+      double hw[HWN], tw[16];
+#pragma unroll
+      for (int k = 0; k < HWN; ++k) {
+        bool in = k < hwlim;
+        if (k < 3) in = in && (hnode0 + k >= -ASTR_HM);
+        hw[k] = in ? lrow[hnode0 + k] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tw[k] = lrow[n - 10 + k];
+      head_rhs_any<OP>(p0, hw, fc, pl.nsf, dh);
+      tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.empty);
+    double he[ASTR_HS], te[ASTR_TS];
+    {
+      double yh, yt;
+      spec_forward(pl.head, dh, he, yh, yt);
+      c.sS[ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gamma, yh, yt);
+      c.sP[ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
+      spec_forward(pl.tail, dt, te, yh, yt);
+      c.sS[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
+      c.sP[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+    }
+    if (bnd + (int)gridDim.x < c.nbundles) {
+      if (lane == 0) mbar_wait(c.empty, phase);
+      __syncwarp();
+      fetch(bnd + gridDim.x);
+    }
+    phase ^= 1;
+    cta_sync(1, c.nthreads);
+    auto GS = [&](int idx) { return sSl[idx * 32]; };
+    auto GP = [&](int idx) { return sPl[idx * 32]; };
+    {
+      const ScanOut s0 = reduced_scan(pl, GS, GP, 0);
+      spec_back(pl.head, he, s0.t_prev, s0.h_next, [&](int s, double x) { he[s] = x; });
+      const ScanOut s1 = reduced_scan(pl, GS, GP, E - 1);
+      spec_back(pl.tail, te, s1.t_prev, s1.h_next, [&](int s, double x) { te[s] = x; });
+    }
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      if ((lane >> 4) == r) {
+#pragma unroll
+        for (int s = 0; s < ASTR_HS; ++s) if (s < pl.sh) orow[pl.first_node + s] = he[s];
+#pragma unroll
+        for (int s = 0; s < ASTR_TS; ++s) if (s < pl.st) orow[tnode0 + s] = te[s];
+      }
+      copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
+    }
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(512, 1) sweep2i_kernel(const __grid_constant__ Sweep2Args a) {
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  const LinePlan& pl = c_plan[OP][0];
+  ICtx c;
+  c.sp = a.sp;
+  c.tin = smem;
+  c.tout = smem + 32 * c.sp;
+  c.sS = reinterpret_cast<double (*)[32]>(c.tout + 16 * c.sp);
+  c.sP = c.sS + ESZ;
+  c.full = &mbar[0]; c.empty = &mbar[1];
+  const int NW = pl.NW;
+  c.nthreads = (NW + 1) * 32;
+  c.nbundles = (int)(a.dxy.d * (unsigned)a.nf);
+  const OutRange R(a, pl.n);
+  c.pl0 = R.w_lo & ~1;
+  c.npairs = (int)a.dpair.d;
+  for (int i = threadIdx.x; i < 2 * ESZ * 32; i += blockDim.x) (&c.sS[0][0])[i] = 0.0;
+  if (threadIdx.x == 0) {
+    mbar_init(c.full, 1);
+    mbar_init(c.empty, NW + 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if ((int)(threadIdx.x >> 5) < NW) regular_loop_i<OP>(a, c);
+  else special_loop_i<OP>(a, c);
 }
 
 int g_sms = 0;
@@ -288,7 +583,8 @@ struct PoolMap {
   CUtensorMap tm[3];        // per sweep direction (box shape differs); [0] unused
   int rb[3] = {0, 0, 0}, nbox[3] = {0, 0, 0};
 };
-PoolMap g_maps[2];
+constexpr int NPOOLS = 3;
+PoolMap g_maps[NPOOLS];
 
 int make_map(PoolMap& pm, const Layout& L, int dir) {
   const int rows = (dir == 1 ? L.njt : L.nkt);
@@ -299,9 +595,11 @@ int make_map(PoolMap& pm, const Layout& L, int dir) {
   const cuuint64_t gstr[3] = {(cuuint64_t)L.sj * 8, (cuuint64_t)L.sk * 8, (cuuint64_t)L.fstride * 8};
   const cuuint32_t box[4] = {32, (cuuint32_t)(dir == 1 ? rb : 1), (cuuint32_t)(dir == 2 ? rb : 1), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
+  // 128-byte L2 promotion: the 256-byte box rows start at a 128-byte (not 256-byte) boundary, so the 256-byte
+  // promotion made every row fetch two extra half lines (ncu: 17 % more L2 read sectors than TMA bytes)
   const CUresult r = g_encode(&pm.tm[dir], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(pm.base), gdim, gstr,
                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[96];
     snprintf(buf, sizeof buf, "sweep2: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -310,32 +608,70 @@ int make_map(PoolMap& pm, const Layout& L, int dir) {
   return 0;
 }
 
+struct LaunchCache { int dev = -1, threads = 0, occ = 0; size_t smem = 0; };
+
+template <class K>
+int prepare(K kern, LaunchCache& lc, int threads, size_t smem) {
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (lc.dev == dev && lc.threads == threads && lc.smem == smem) return 0;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.occ, kern, threads, smem));
+  if (lc.occ < 1) return astr_fail_msg("sweep2: kernel does not fit on an SM");
+  CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  lc.dev = dev; lc.threads = threads; lc.smem = smem;
+  return 0;
+}
+
 template <int DIR, int OP>
-int launch2(Sweep2Args& a, const PoolMap& pm, cudaStream_t st) {
+int launch2(Sweep2Args& a, const PoolMap& pm, int NW, cudaStream_t st) {
   auto kern = sweep2_kernel<DIR, OP>;
-  const int threads = a.NW * 32;
+  const int threads = (NW + 1) * 32;
   a.rb = pm.rb[DIR]; a.nbox = pm.nbox[DIR];
   const size_t smem = (size_t)a.rb * a.nbox * 256;
-  static int occ_threads = 0, occ = 0;
-  static size_t occ_smem = 0;
-  if (occ_threads != threads || occ_smem != smem) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) return astr_fail_msg("sweep2: kernel does not fit on an SM");
-    occ_threads = threads; occ_smem = smem;
-    if (!g_sms) {
-      int dev = 0;
-      CUDA_OK(cudaGetDevice(&dev));
-      CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-  }
+  static LaunchCache lc;
+  const int rc = prepare(kern, lc, threads, smem);
+  if (rc) return rc;
   const Layout& L = a.L;
   const long long nbx = (L.im + 32) / 32;
   const long long nby = (DIR == 2 ? L.jm : L.km) + 1;
   const long long nbundles = nbx * nby * a.nf;
-  long long grid = (long long)g_sms * occ;
+  a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
+  a.dpair = make_fastdiv(1);
+  long long grid = (long long)g_sms * lc.occ;
   if (grid > nbundles) grid = nbundles;
   kern<<<(unsigned)grid, threads, smem, st>>>(a, pm.tm[DIR]);
+  astr_count_launch();
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int OP>
+int launch2i(Sweep2Args& a, const LinePlan& plan, cudaStream_t st) {
+  auto kern = sweep2i_kernel<OP>;
+  const int NW = plan.NW, n = plan.n;
+  // the chunk windows must start on a 16-byte boundary of the shared-memory line (build_line_plan, align_even)
+  if (((plan.first_node + plan.sh - OpT<OP>::H + 6) & 1) != 0) return -1;
+  const int threads = (NW + 1) * 32;
+  int sp = n + 12;
+  while ((sp & 15) != 2) ++sp;
+  a.sp = sp;
+  const size_t smem = ((size_t)48 * sp + 2 * ESZ * 32) * sizeof(double);
+  if (smem > 227 * 1024) return -1;
+  static LaunchCache lc;
+  const int rc = prepare(kern, lc, threads, smem);
+  if (rc) return rc;
+  const Layout& L = a.L;
+  const long long nbx = (L.jm + 32) / 32;
+  const long long nby = L.km + 1;
+  const long long nbundles = nbx * nby * a.nf;
+  a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
+  const int w_lo = (a.epi == EPI_STOREZ) ? 0 : a.o_lo, w_hi = (a.epi == EPI_STOREZ) ? n : a.o_hi;
+  const int pl0 = w_lo & ~1;
+  a.dpair = make_fastdiv((unsigned)((w_hi - pl0) / 2 + 1));
+  long long grid = (long long)g_sms * lc.occ;
+  if (grid > nbundles) grid = nbundles;
+  kern<<<(unsigned)grid, threads, smem, st>>>(a);
   astr_count_launch();
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -349,8 +685,9 @@ int astr_sweep2_set_plan(int dir, int optype, const LinePlan& plan, const Filter
   return 0;
 }
 
-// Registers an allocation of `nslots` fields (stride L.fstride) as TMA source `which` (0, 1).
+// Registers an allocation of `nslots` fields (stride L.fstride) as TMA source `which` (0..2).
 int astr_sweep2_register_pool(int which, const double* base, int nslots, const Layout& L) {
+  if (which < 0 || which >= NPOOLS) return astr_fail_msg("sweep2: bad pool index");
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -371,11 +708,24 @@ int astr_sweep2_register_pool(int which, const double* base, int nslots, const L
 // Returns -1 when the request is outside what these kernels cover (the caller then uses the
 // shared-memory engine of sweep.cu), 0 on success, >0 on error.
 int astr_launch_sweep2(int dir, int optype, const LinePlan& plan, const SweepArgs& s, cudaStream_t st) {
-  if (dir == 0 || !plan.ok || s.epi == EPI_ADD) return -1;
-  if (plan.NW * 32 > 512) return -1;
+  if (!plan.ok || s.epi == EPI_ADD) return -1;
+  if (plan.NW < 1 || plan.NW > ASTR_NWMAX) return -1;
+  // in place or disjoint only: a bundle is read completely before any of its rows is written
+  Sweep2Args a;
+  a.L = s.L;
+  for (int i = 0; i < ASTR_MAXF; ++i) { a.in[i] = s.in[i]; a.out[i] = s.out[i]; a.slot[i] = 0; }
+  a.nf = s.nf; a.epi = s.epi; a.o_lo = s.o_lo; a.o_hi = s.o_hi;
+  a.rb = a.nbox = a.sp = 0;
+  if (dir == 0) {
+    switch (optype) {
+      case OP_DERIV: return launch2i<OP_DERIV>(a, plan, st);
+      case OP_FILTER: return launch2i<OP_FILTER>(a, plan, st);
+      case OP_FLUXP: return launch2i<OP_FLUXP>(a, plan, st);
+      default: return launch2i<OP_FLUXM>(a, plan, st);
+    }
+  }
   // every input field must be a slot of one registered allocation
   const PoolMap* pm = nullptr;
-  Sweep2Args a;
   for (int i = 0; i < s.nf; ++i) {
     const PoolMap* hit = nullptr;
     for (const PoolMap& m : g_maps) {
@@ -387,10 +737,15 @@ int astr_launch_sweep2(int dir, int optype, const LinePlan& plan, const SweepArg
     pm = hit;
   }
   if (!pm) return -1;
-  if ((size_t)pm->rb[dir] * pm->nbox[dir] * 256 > 200 * 1024) return -1;
-  a.L = s.L; a.NW = plan.NW;
-  for (int i = 0; i < ASTR_MAXF; ++i) a.out[i] = s.out[i];
-  a.nf = s.nf; a.epi = s.epi; a.o_lo = s.o_lo; a.o_hi = s.o_hi;
-  if (optype == OP_DERIV) return dir == 1 ? launch2<1, OP_DERIV>(a, *pm, st) : launch2<2, OP_DERIV>(a, *pm, st);
-  return dir == 1 ? launch2<1, OP_FILTER>(a, *pm, st) : launch2<2, OP_FILTER>(a, *pm, st);
+  if ((size_t)pm->rb[dir] * pm->nbox[dir] * 256 > 190 * 1024) return -1;
+#define ASTR_L2(D)                                                             \
+  switch (optype) {                                                            \
+    case OP_DERIV: return launch2<D, OP_DERIV>(a, *pm, plan.NW, st);           \
+    case OP_FILTER: return launch2<D, OP_FILTER>(a, *pm, plan.NW, st);         \
+    case OP_FLUXP: return launch2<D, OP_FLUXP>(a, *pm, plan.NW, st);           \
+    default: return launch2<D, OP_FLUXM>(a, *pm, plan.NW, st);                 \
+  }
+  if (dir == 1) { ASTR_L2(1) }
+  ASTR_L2(2)
+#undef ASTR_L2
 }

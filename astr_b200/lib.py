@@ -61,6 +61,7 @@ class AstrCfg(ctypes.Structure):
         ("rkscheme", ctypes.c_int), ("lfilter", ctypes.c_int), ("diffterm", ctypes.c_int),
         ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int),
         ("recon_schem", ctypes.c_int), ("conschm_explicit", ctypes.c_int), ("lchardecomp", ctypes.c_int), ("bctype", ctypes.c_int * 6),
+        ("legacy_sweep", ctypes.c_int), ("overlap_visc", ctypes.c_int), ("xchg_nccl", ctypes.c_int),
         ("alfa_filter", ctypes.c_double),
         ("reynolds", ctypes.c_double), ("mach", ctypes.c_double), ("prandtl", ctypes.c_double),
         ("gamma", ctypes.c_double), ("ref_tem", ctypes.c_double),

@@ -63,14 +63,17 @@ class RhsEngine:
                  device: int = -1, flowtype: int = 0, bctype: Sequence[int] = (1,) * 6,
                  twall: Sequence[float] = (0.0,) * 6, explicit: bool = False, conschm: Optional[int] = None,
                  lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
-                 conschm_explicit: bool = False):
+                 conschm_explicit: bool = False, legacy_sweep: bool = False, overlap_visc: bool = False,
+                 xchg_nccl: bool = False):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
         self.thermo = thermo
         self._lib = _l.load()
         c = _l.AstrCfg()
-        c.abi_version = 2
+        c.abi_version = 3
+        # engine switches of ABI v3 (0 = default: register line-solve engine, peer-memory halo exchange)
+        c.legacy_sweep, c.overlap_visc, c.xchg_nccl = int(legacy_sweep), int(overlap_visc), int(xchg_nccl)
         c.device = device
         c.im, c.jm, c.km = block.dims
         c.ia, c.ja, c.ka = global_dims

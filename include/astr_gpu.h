@@ -32,7 +32,7 @@ extern "C" {
 
 #define ASTR_GPU_HM 5          /* src/commvar.F90:184  parameter(hm=5) */
 #define ASTR_GPU_NUMQ 5        /* src/solver.F90:50    numq=5+num_species+num_modequ */
-#define ASTR_GPU_ABI_VERSION 2
+#define ASTR_GPU_ABI_VERSION 3
 
 /* Everything `solvrinit` (src/comsolver.F90:47-146), `refcal` (src/solver.F90:28-173)
  * and `parallelini` (src/parallel.F90:919-1248) have decided by the time the time loop
@@ -73,6 +73,13 @@ typedef struct astr_cfg {
                                  1 periodic/none; 41 isothermal wall (any face);
                                  11 inflow (imin); 21 outflow (imax, jmax); 51 farfield
                                  (jmax); 421 slip adiabatic wall (jmin)                  */
+  /* engine switches (ABI v3; they were environment variables in v2).  0 = default.      */
+  int legacy_sweep;           /* 1: every line solve on the shared-memory engine
+                                 (sweep.cu) instead of the register engine (sweep2.cu)  */
+  int overlap_visc;           /* 1: multi-block only: the sigma/qflux exchange runs on a
+                                 side stream behind the interior stress+flux pass       */
+  int xchg_nccl;              /* 1: halo exchange through ncclSend/ncclRecv instead of
+                                 peer-memory stores (CUDA IPC)                          */
   double alfa_filter;         /* 0.49 in every example                                   */
   double reynolds, mach, prandtl, gamma, ref_tem;
   double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */

@@ -132,7 +132,7 @@ def dimensional_state(c, th, ib=0):
 
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
               lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False,
-              dimensional=False, sponge=None, inflow_from_state=False):
+              dimensional=False, sponge=None, inflow_from_state=False, engine_kw=None):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
@@ -200,7 +200,7 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
             c.set_upwind(543, up_kw["lchardecomp"], up_kw["bfacmpld"], up_kw["shkcrt"])
     block = decompose(n, (1, 1, 1), homo)[0]
     eng = RhsEngine(block, n, homo, th, deltat=deltat, lfilter=lfilter, diffterm=diffterm, device=0,
-                    flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw)
+                    flowtype=int(channel), bctype=bctype, twall=twall, explicit=explicit, **up_kw, **(engine_kw or {}))
     eng.set_force(force)
     if open_faces:
         # synthetic inflow data: half of the profile supersonic (blend -> 1), half subsonic (blend -> 0)

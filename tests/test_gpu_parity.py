@@ -318,25 +318,54 @@ def test_launch_counter_counts_kernels(oracle):
     dict(n=(288, 16, 12), homo=(True, True, True), stretch="skew", perturb=1e-2,
          upwind=dict(lchardecomp=True, shkcrt="auto")),
 ], ids=["periodic300", "walls_i320", "upwind288"])
-@pytest.mark.parametrize("variant", ["1", "2"])
-def test_warp_per_line_engine(oracle, kw, variant, monkeypatch):
-    # ASTR_SWEEP_W3=1 / 2: long i lines (8*32..17*32 rows) run on the warp-per-line engine (sweep3_kernel, or its
-    # padded variant sweep3p_kernel): every
-    # operator that sweeps in i -- filter, gradient, flux divergence, compact upwind fluxes -- against the oracle
+def test_long_i_lines(oracle, kw):
+    # long i lines (8-9 regular chunks + head / tail blocks) on the register engine's i kernel (sweep2i_kernel),
+    # short j / k lines on the shared-memory engine: every operator that sweeps in i -- filter, gradient, flux
+    # divergence, compact upwind fluxes -- against the oracle.
     # tolerances: with 300 intervals in i against 16 in j, k the i-derivative of an O(1) field is ~20x smaller
     # than its rounding scale eps*|f|/dx relative to the j, k entries of the same tensor; the shared-memory
     # engine shows the same 1.5e-12 / 5e-12 / 6.5e-12 on these grids (measured), so this is conditioning
-    monkeypatch.setenv("ASTR_SWEEP_W3", variant)
     c, eng = make_pair(oracle, **kw)
     c.filterq(); eng.filterq()
-    assert_fields_close(c, eng, QS, OP_TOL, what="filterq (warp-per-line)")
+    assert_fields_close(c, eng, QS, OP_TOL, what="filterq (long i lines)")
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
-    assert_fields_close(c, eng, DVEL + DTMP, 2e-11, what="gradcal (warp-per-line)")
+    assert_fields_close(c, eng, DVEL + DTMP, 2e-11, what="gradcal (long i lines)")
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
     # upwind: the split fluxes are O(c/dx_i) on this fine-in-i grid while their differences are O(1); the
     # reference's REV*LEV round trip at unflagged interfaces (skipped on the device) is rounding noise of that size
-    assert_fields_close(c, eng, QRHS, 2e-9 if "upwind" in kw else 3e-11, what="rhscal (warp-per-line)")
+    assert_fields_close(c, eng, QRHS, 2e-9 if "upwind" in kw else 3e-11, what="rhscal (long i lines)")
     for rk in (1, 2, 3):
         c.rk_stage(rk); eng.rk_stage(rk)
-    assert_fields_close(c, eng, QS + PRIMS, 1e-11 if "upwind" in kw else STEP_TOL, what="3 rk stages (warp-per-line)")
+    assert_fields_close(c, eng, QS + PRIMS, 1e-11 if "upwind" in kw else STEP_TOL, what="3 rk stages (long i lines)")
+    eng.close(); c.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=(140, 72, 110), homo=(True, True, True), stretch=True),
+    dict(n=(72, 100, 80), homo=(False, False, False), stretch=True),
+    dict(n=(80, 44, 150), homo=(True, False, True), stretch=True),
+], ids=["periodic", "walls", "wall_j"])
+@pytest.mark.parametrize("legacy", [False, True], ids=["register_engine", "shared_memory_engine"])
+def test_line_solve_engines(oracle, kw, legacy):
+    # both line-solve engines on the same inputs, each against the oracle: the register engine (sweep2.cu: 2-4
+    # regular chunks per line here, head / tail blocks of every ntype, all three directions) and the
+    # shared-memory engine (sweep.cu, cfg.legacy_sweep = 1), which stays the fallback for short lines
+    c, eng = make_pair(oracle, engine_kw=dict(legacy_sweep=legacy), **kw)
+    c.filterq(); eng.filterq()
+    assert_fields_close(c, eng, QS, OP_TOL, what="filterq")
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    assert_fields_close(c, eng, DVEL + DTMP, 2e-12, what="gradcal")
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    assert_fields_close(c, eng, QRHS, 3e-12, what="rhscal")
+    eng.close(); c.close()
+
+
+def test_compact_flux_solves_on_the_register_engine(oracle):
+    # conschm 543c on lines long enough for sweep2.cu: OP_FLUXP / OP_FLUXM (flux_compact, src/flux.F90:125-266)
+    # with wall (i, j) and interface (k) closures
+    c, eng = make_pair(oracle, n=(72, 80, 44), homo=(False, False, True), stretch=True, perturb=1e-2,
+                       upwind=dict(lchardecomp=True, shkcrt="auto"))
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    c.zero_qrhs(); c.rhscal(); eng.rhscal()
+    assert_fields_close(c, eng, QRHS, UPWIND_TOL, what="rhscal (543c, register engine)")
     eng.close(); c.close()

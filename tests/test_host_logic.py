@@ -64,8 +64,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/astr_gpu.h but not exported"
     assert sorted(L.SYMBOLS) == declared
-    # the ctypes mirror of struct astr_cfg has the C struct's size (53 ints + 25 doubles, padded to 8)
-    assert lib.astr_gpu_sizeof_cfg() == ctypes.sizeof(L.AstrCfg) == 4 * 54 + 8 * 25
+    # the ctypes mirror of struct astr_cfg has the C struct's size (56 ints + 25 doubles)
+    assert lib.astr_gpu_sizeof_cfg() == ctypes.sizeof(L.AstrCfg) == 4 * 56 + 8 * 25
 
 
 def test_no_gpu_means_loud_failure():
@@ -161,68 +161,76 @@ def test_refcal_dimensional_matches_the_oracle(oracle):
     assert 2.9 < th["mach"] < 3.1      # "M3"
 
 
-def _warp_line_thomas(ac1, ac2, ac3, d):
-    """The warp-per-line engine's algebra (astr_b200/csrc/sweep.cu sweep3_kernel): 32 lane chunks, zero-carry
-    recurrences, carries from Hillis-Steele scans of the affine maps x -> A x + B, exactly as the kernel."""
-    N = d.size
-    cs = [min(17 * c, N) for c in range(33)]      # chunk32_start, astr_b200/csrc/common.cuh
-    ac2 = ac2.copy(); ac3 = ac3.copy(); ac2[0] = 1.0; ac3[0] = 0.0
-    pf = np.zeros(N); qb = np.zeros(N)
-    for c in range(32):
-        p = 1.0
-        for r in range(cs[c], cs[c + 1]):
-            p *= -ac3[r]; pf[r] = p
-        q = 1.0
-        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
-            q *= -ac1[r]; qb[r] = q
-    e = np.zeros(N); A = np.zeros(32); B = np.zeros(32)
-    for c in range(32):
-        prev = 0.0
-        for r in range(cs[c], cs[c + 1]):
-            prev = d[r] * ac2[r] - prev * ac3[r]; e[r] = prev
-        A[c] = pf[cs[c + 1] - 1] if cs[c + 1] > cs[c] else 1.0; B[c] = prev
-    off = 1
-    while off < 32:                       # shfl_up scan
-        Ap, Bp = np.roll(A, off), np.roll(B, off)
-        m = np.arange(32) >= off
-        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
-        off *= 2
-    cin = np.concatenate([[0.0], B[:-1]])
-    g = np.zeros(N); A = np.zeros(32); B = np.zeros(32)
-    for c in range(32):
-        nxt = 0.0
-        for r in range(cs[c + 1] - 1, cs[c] - 1, -1):
-            nxt = (e[r] + pf[r] * cin[c]) - ac1[r] * nxt; g[r] = nxt
-        A[c] = qb[cs[c]] if cs[c + 1] > cs[c] else 1.0; B[c] = nxt
-    off = 1
-    while off < 32:                       # shfl_down scan
-        Ap, Bp = np.roll(A, -off), np.roll(B, -off)
-        m = np.arange(32) + off < 32
-        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
-        off *= 2
-    xin = np.concatenate([B[1:], [0.0]])
-    x = np.zeros(N)
-    for c in range(32):
-        for r in range(cs[c], cs[c + 1]):
-            x[r] = g[r] + qb[r] * xin[c]
-    return x
+# ---- the algebra of the register engine (astr_b200/csrc/linecore.h, driven by tests/emul_sweep2.cpp) -------
+_EMUL = None
 
 
-@pytest.mark.parametrize("is_filter", [False, True])
+def _emul_lib(tmp_path_factory):
+    """g++ build of tests/emul_sweep2.cpp: the device functions of linecore.h, run on the CPU element by element
+    in the kernels' phase order (passes 1-2 and publication of S / S', barrier, truncated reduced scan, pass 3)."""
+    global _EMUL
+    if _EMUL is None:
+        import subprocess
+        out = tmp_path_factory.mktemp("emul") / "libemul_sweep2.so"
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(out),
+                               os.path.join(ROOT, "tests", "emul_sweep2.cpp")])
+        _EMUL = ctypes.CDLL(str(out))
+    return _EMUL
+
+
+@pytest.mark.parametrize("op", [0, 1, 2, 3], ids=["deriv", "filter", "flux+", "flux-"])
 @pytest.mark.parametrize("ntype", [1, 2, 3, 4])
-@pytest.mark.parametrize("n", [300, 512])
-def test_warp_per_line_partition_is_exact(oracle, is_filter, ntype, n):
-    first, a, c, ac1, ac2, ac3 = oracle.scheme_tables(is_filter, ntype, n)
-    N = a.size
-    d = np.random.default_rng(n + ntype).standard_normal(N)
-    dd = d.copy()
-    for i in range(1, N):
-        dd[i] = dd[i] * ac2[i] - dd[i - 1] * ac3[i]
-    x = np.zeros(N); x[-1] = dd[-1]
-    for i in range(N - 2, -1, -1):
-        x[i] = dd[i] - ac1[i] * x[i + 1]
-    xp = _warp_line_thomas(ac1, ac2, ac3, d)
-    assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * np.abs(x).max()
+def test_register_engine_algebra_matches_the_oracle(oracle, tmp_path_factory, op, ntype):
+    # fresh-start chunk factorisation + head / tail blocks with neutral slots + reduced scan truncated where the
+    # dropped coupling is below 1e-20, against the reference's single Thomas sweep (df_compact, compact_filter,
+    # flux_compact restated in oracle/lineops.cpp) -- every line length class: no / small / large head remainder,
+    # 1 to 15 regular chunks, with and without the 16-byte alignment rule of the i direction
+    lib = _emul_lib(tmp_path_factory)
+    rng = np.random.default_rng(10 * op + ntype)
+    covered = 0
+    for n in (44, 48, 64, 99, 100, 128, 255, 256, 300, 512, 527):
+        for align in (0, 1):
+            f = rng.standard_normal(n + 11)
+            alfa = 0.49 if op == 1 else (0.3 if op >= 2 else 0.0)
+            out = np.zeros(n + 20)
+            info = (ctypes.c_int * 6)()
+            rc = lib.emul_line(op, ntype, n, ctypes.c_double(alfa), align, f.ctypes.data_as(ctypes.c_void_p),
+                               out.ctypes.data_as(ctypes.c_void_p), info)
+            if rc:
+                assert n < 48, f"no plan for n={n}"      # short lines stay on the shared-memory engine
+                continue
+            first, nrows, nw, sh, st, w = list(info)
+            assert 1 <= nw <= 15 and sh <= 40 and st <= 6 and 1 <= w <= 8
+            if op == 0:
+                ref, lo = oracle.df_compact(f, ntype), 0
+            elif op == 1:
+                ref, lo = oracle.compact_filter(f, ntype, 0.49), 0
+            else:
+                ref, lo = oracle.flux_compact(f, ntype, op == 2, 0.3), -1
+            got = np.array([out[node - first] for node in range(lo, n + 1)])
+            if op == 1:      # physical-boundary nodes are left unfiltered by the caller (src/filter.F90:141-142)
+                if ntype in (1, 4):
+                    got[0] = ref[0]
+                if ntype in (2, 4):
+                    got[-1] = ref[-1]
+            err = np.abs(got - ref).max() / np.abs(ref).max()
+            assert err < 2e-14, (op, ntype, n, align, list(info), err)
+            covered += 1
+    assert covered >= 18
+
+
+def test_register_engine_falls_back_when_the_coupling_decays_slowly(tmp_path_factory):
+    # alfa -> 1/2: the elimination factors of a whole chunk no longer contract below 1e-20 within 8 elements;
+    # the plan refuses (the shared-memory engine, which does no truncation, takes the line)
+    lib = _emul_lib(tmp_path_factory)
+    n = 512
+    f = np.zeros(n + 11); out = np.zeros(n + 20); info = (ctypes.c_int * 6)()
+    rc = lib.emul_line(1, 3, n, ctypes.c_double(0.4999), 0, f.ctypes.data_as(ctypes.c_void_p),
+                       out.ctypes.data_as(ctypes.c_void_p), info)
+    assert rc == 1
+    rc = lib.emul_line(1, 3, n, ctypes.c_double(0.49), 0, f.ctypes.data_as(ctypes.c_void_p),
+                       out.ctypes.data_as(ctypes.c_void_p), info)
+    assert rc == 0 and info[5] <= 8
 
 
 def test_fortran_module_binds_every_stage_operator():
@@ -251,67 +259,3 @@ def test_fortran_module_binds_every_stage_operator():
             f_members += [re.sub(r"\(\d+\)", "", v).strip() for v in m.group(2).split(",")]
     assert [m.lower() for m in c_members] == [m.lower() for m in f_members]
     assert [f[0] for f in L.AstrCfg._fields_] == [("is_" if m == "is" else m) for m in c_members]
-
-
-def _warp_line_thomas_padded(ac1, ac2, ac3, d):
-    """The experimental padded variant (sweep3p_kernel): tables extended to 32 x 17 neutral rows (ac2 = 1,
-    ac1 = ac3 = 0) and zero right-hand sides there, every lane runs 17 unguarded rows."""
-    N, R = d.size, 32 * 17
-    p1 = np.zeros(R); p2 = np.ones(R); p3 = np.zeros(R); dd = np.zeros(R)
-    p1[:N] = ac1; p2[:N] = ac2; p3[:N] = ac3; p2[0] = 1.0; p3[0] = 0.0; dd[:N] = d
-    pf = np.zeros(R); qb = np.zeros(R)
-    for c in range(32):
-        p = 1.0
-        for r in range(17 * c, 17 * c + 17):
-            p *= -p3[r]; pf[r] = p
-        q = 1.0
-        for r in range(17 * c + 16, 17 * c - 1, -1):
-            q *= -p1[r]; qb[r] = q
-    e = np.zeros(R); A = np.zeros(32); B = np.zeros(32)
-    for c in range(32):
-        prev = 0.0
-        for r in range(17 * c, 17 * c + 17):
-            prev = dd[r] * p2[r] - prev * p3[r]; e[r] = prev
-        A[c] = pf[17 * c + 16]; B[c] = prev
-    off = 1
-    while off < 32:
-        Ap, Bp = np.roll(A, off), np.roll(B, off)
-        m = np.arange(32) >= off
-        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
-        off *= 2
-    cin = np.concatenate([[0.0], B[:-1]])
-    g = np.zeros(R); A = np.zeros(32); B = np.zeros(32)
-    for c in range(32):
-        nxt = 0.0
-        for r in range(17 * c + 16, 17 * c - 1, -1):
-            nxt = (e[r] + pf[r] * cin[c]) - p1[r] * nxt; g[r] = nxt
-        A[c] = qb[17 * c]; B[c] = nxt
-    off = 1
-    while off < 32:
-        Ap, Bp = np.roll(A, -off), np.roll(B, -off)
-        m = np.arange(32) + off < 32
-        B = np.where(m, A * Bp + B, B); A = np.where(m, A * Ap, A)
-        off *= 2
-    xin = np.concatenate([B[1:], [0.0]])
-    x = np.array([g[r] + qb[r] * xin[r // 17] for r in range(R)])
-    assert np.all(x[N:] == 0.0)          # the padding solves to exactly zero
-    return x[:N]
-
-
-@pytest.mark.parametrize("is_filter", [False, True])
-@pytest.mark.parametrize("ntype", [1, 2, 3, 4])
-@pytest.mark.parametrize("n", [300, 512, 536])
-def test_padded_warp_per_line_partition_is_exact(oracle, is_filter, ntype, n):
-    first, a, c, ac1, ac2, ac3 = oracle.scheme_tables(is_filter, ntype, n)
-    N = a.size
-    if N > 32 * 17:
-        pytest.skip("line longer than 32 x 17 rows")
-    d = np.random.default_rng(n + ntype).standard_normal(N)
-    dd = d.copy()
-    for i in range(1, N):
-        dd[i] = dd[i] * ac2[i] - dd[i - 1] * ac3[i]
-    x = np.zeros(N); x[-1] = dd[-1]
-    for i in range(N - 2, -1, -1):
-        x[i] = dd[i] - ac1[i] * x[i + 1]
-    xp = _warp_line_thomas_padded(ac1, ac2, ac3, d)
-    assert np.abs(xp - x).max() <= (2e-13 if is_filter else 2e-15) * np.abs(x).max()

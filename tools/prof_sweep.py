@@ -11,7 +11,7 @@ b = decompose((n, n, n), (1, 1, 1), homo)[0]
 eng = RhsEngine(b, (n, n, n), homo, refcal(1600.0, 0.1), device=0)
 for op in (0, 1):
     for d in (0, 1, 2):
-        ms = eng.bench_sweep(op, d, 5, iters)
-        gbs = 5 * 16.0 * (n + 1) ** 3 / (ms * 1e-3) / 1e9
+        ms = eng.bench_sweep(op, d, 5, max(iters, 1)) if iters > 0 else eng.bench_sweep(op, d, 5, 0)
+        gbs = 5 * 16.0 * (n + 1) ** 3 / (ms * 1e-3) / 1e9 if ms > 0 and ms == ms and ms != float('inf') else 0.0
         print(f"op={'deriv' if op == 0 else 'filter'} dir={'ijk'[d]} {ms:.3f} ms/launch  {gbs:.0f} GB/s", flush=True)
 eng.close()
