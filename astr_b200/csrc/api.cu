@@ -207,6 +207,8 @@ struct Ctx {
   int peer_dims[6][3];
   std::vector<void*> ipc_opened;
   unsigned long long xseq[3] = {0, 0, 0};
+  long long xtimeout_cycles = 0;          // cfg.xchg_timeout_ms in SM clock cycles (<= 0: wait forever)
+  bool xfailed = false;                   // sticky: a peer-memory exchange timed out
   // profiling
   bool profile = false;
   std::vector<ProfSpan> spans;
@@ -345,6 +347,22 @@ int astr_xhalo_exchange(int d) {
   return geom_xhalo_unpack(L, x3, d, lo >= 0 ? g->xbuf[2] : nullptr, hi >= 0 ? g->xbuf[3] : nullptr, g->st);
 }
 
+// communicator, peer mappings and exchange buffers (finalize, or a repeated comm_init)
+static void release_comm() {
+  if (!g) return;
+  if (g->st) cudaStreamSynchronize(g->st);
+  for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
+  g->ipc_opened.clear();
+  for (auto& pa : g->peer_arena) pa = nullptr;
+  if (g->xarena) { cudaFree(g->xarena); g->xarena = nullptr; }
+  for (auto& b : g->xbuf) { if (b) cudaFree(b); b = nullptr; }
+  g->xbuf_doubles = 0;
+  if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
+  g->comm = nullptr;
+  g->p2p = false; g->xfailed = false;
+  for (auto& q : g->xseq) q = 0;
+}
+
 // ---- peer-to-peer exchange: arena layout, IPC set-up ---------------------------------------
 constexpr size_t XHEADER_BYTES = 1024;
 struct XHeader {
@@ -378,15 +396,16 @@ static int p2p_setup() {
     const size_t bytes = xarena_bytes(dims);
     if (cudaMalloc(&g->xarena, bytes) != cudaSuccess) { g->xarena = nullptr; ok = 0; cudaGetLastError(); }
     else {
-      CUDA_OK(cudaMemsetAsync(g->xarena, 0, XHEADER_BYTES, g->st));
-      if (cudaIpcGetMemHandle(&mine.h, g->xarena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      // local failures only clear `ok`: every rank must still reach the two collectives below
+      if (cudaMemsetAsync(g->xarena, 0, XHEADER_BYTES, g->st) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+      if (ok && cudaIpcGetMemHandle(&mine.h, g->xarena) != cudaSuccess) { ok = 0; cudaGetLastError(); }
     }
   }
   for (int k = 0; k < 3; ++k) mine.dims[k] = dims[k];
   mine.ok = ok;
   std::vector<Rec> all(g->nranks);
   char* dbuf = nullptr;
-  CUDA_OK(cudaMalloc(&dbuf, sizeof(Rec) * g->nranks));
+  CUDA_OK(cudaMalloc(&dbuf, sizeof(Rec) * g->nranks));     // 128 bytes per rank: a failure here is fatal for the context anyway
   CUDA_OK(cudaMemcpyAsync(dbuf + sizeof(Rec) * g->rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice, g->st));
   NCCL_OK(g_nccl.AllGather(dbuf + sizeof(Rec) * g->rank, dbuf, sizeof(Rec), ncclChar, g->comm, g->st));
   CUDA_OK(cudaMemcpyAsync(all.data(), dbuf, sizeof(Rec) * g->nranks, cudaMemcpyDeviceToHost, g->st));
@@ -434,6 +453,7 @@ static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
   memset(&sa, 0, sizeof sa); memset(&ra, 0, sizeof ra);
   sa.l0 = ra.l0 = l0; sa.l1 = ra.l1 = l1;
   sa.err = ra.err = &hdr->err;
+  sa.timeout_cycles = ra.timeout_cycles = g->xtimeout_cycles;
   for (int side = 0; side < 2; ++side) {
     const int slot = 2 * d + side;
     if (c.nbr[slot] < 0) continue;
@@ -458,12 +478,19 @@ static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
   return 0;
 }
 
+// Called by every API entry point that synchronises the stream and hands data back to the host: a timed-out
+// exchange poisons the state (k_xface neither moves data nor signals), and the error stays until finalize.
 static int p2p_check() {
   if (!g->p2p) return 0;
-  unsigned int e = 0;
-  CUDA_OK(cudaMemcpyAsync(&e, g->xarena + offsetof(XHeader, err), sizeof e, cudaMemcpyDeviceToHost, g->st));
-  CUDA_OK(cudaStreamSynchronize(g->st));
-  if (e) return astr_fail_msg("halo exchange timed out waiting for a neighbour (peer-to-peer flags)");
+  if (!g->xfailed) {
+    unsigned int e = 0;
+    CUDA_OK(cudaMemcpyAsync(&e, g->xarena + offsetof(XHeader, err), sizeof e, cudaMemcpyDeviceToHost, g->st));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+    g->xfailed = (e != 0);
+  }
+  if (g->xfailed)
+    return astr_fail_msg("halo exchange timed out waiting for a neighbour (peer-memory flags): the device state is "
+                         "invalid from that exchange on; finalize and restart from the last checkpoint");
   return 0;
 }
 
@@ -511,7 +538,7 @@ extern "C" {
 const char* astr_gpu_last_error(void) { return g_err.c_str(); }
 int astr_gpu_sizeof_cfg(void) { return (int)sizeof(astr_cfg); }
 
-int astr_gpu_init(const astr_cfg* cfg) {
+static int init_impl(const astr_cfg* cfg) {
   if (!cfg) return astr_fail_msg("null cfg");
   if (cfg->abi_version != ASTR_GPU_ABI_VERSION) return astr_fail_msg("abi_version mismatch");
   if (cfg->hm != ASTR_HM || cfg->numq != ASTR_GPU_NUMQ) return astr_fail_msg("hm must be 5 and numq 5");
@@ -540,6 +567,7 @@ int astr_gpu_init(const astr_cfg* cfg) {
   } else if (cfg->conschm != cfg->difschm && cfg->conschm != 543)
     return astr_fail_msg("conschm must equal difschm (central), be 543c (upwind compact) or an explicit upwind scheme");
   if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
+  if (cfg->reserved0 != 0) return astr_fail_msg("cfg.reserved0 must be 0");
   for (int d = 0; d < 3; ++d)
     if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
   if (g) astr_gpu_finalize();
@@ -569,6 +597,14 @@ int astr_gpu_init(const astr_cfg* cfg) {
   CUDA_OK(cudaEventCreateWithFlags(&g->ev_shell, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&g->ev_xdone, cudaEventDisableTiming));
   g->cur = g->st;
+  {
+    // flag-wait timeout of the peer-memory exchange in SM clock cycles (clock64 runs at the SM clock)
+    int dev = 0, khz = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    const long long ms = cfg->xchg_timeout_ms == 0 ? 4000 : cfg->xchg_timeout_ms;
+    g->xtimeout_cycles = ms < 0 ? 0 : ms * (long long)khz;
+  }
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);
   CUDA_OK(cudaMalloc(&g->pool, bytes));
   CUDA_OK(cudaMemsetAsync(g->pool, 0, bytes, g->st));
@@ -615,33 +651,45 @@ int astr_gpu_init(const astr_cfg* cfg) {
   return 0;
 }
 
+// A failed init leaves no context behind: later calls report "astr_gpu_init not called" instead of
+// dereferencing a half-built one.
+int astr_gpu_init(const astr_cfg* cfg) {
+  const int rc = init_impl(cfg);
+  if (rc && g) {
+    const std::string keep = g_err;
+    astr_gpu_finalize();
+    g_err = keep;
+  }
+  return rc;
+}
+
+// Safe on a half-built context (astr_gpu_init calls it on every error path): every member is checked.
 int astr_gpu_finalize(void) {
   if (!g) return 0;
-  cudaStreamSynchronize(g->st);
-  prof_collect();
+  if (g->st) { cudaStreamSynchronize(g->st); prof_collect(); }
   for (auto e : g->free_events) cudaEventDestroy(e);
-  if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
-  for (auto& b : g->xbuf) if (b) cudaFree(b);
-  for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
-  if (g->xarena) cudaFree(g->xarena);
-  for (int d = 0; d < 3; ++d) {
-    cudaFree(g->fd[d].d_tab); cudaFree(g->fl[d].d_tab);
-    if (g->fxp[d].d_tab) cudaFree(g->fxp[d].d_tab);
-    if (g->fxm[d].d_tab) cudaFree(g->fxm[d].d_tab);
-  }
+  release_comm();
+  for (int d = 0; d < 3; ++d)
+    for (HostOp* h : {&g->fd[d], &g->fl[d], &g->fxp[d], &g->fxm[d]})
+      if (h->d_tab) cudaFree(h->d_tab);
   if (g->up) cudaFree(g->up);
   for (int k = 0; k < 3; ++k) astr_sweep2_register_pool(k, nullptr, 0, g->L);
-  cudaFree(g->pool); if (g->scr) cudaFree(g->scr);
-  cudaFree(g->d_partial); cudaFree(g->d_out2); cudaFree(g->d_src);
+  if (g->pool) cudaFree(g->pool);
+  if (g->scr) cudaFree(g->scr);
+  if (g->d_partial) cudaFree(g->d_partial);
+  if (g->d_out2) cudaFree(g->d_out2);
+  if (g->d_src) cudaFree(g->d_src);
   if (g->ycoord) cudaFree(g->ycoord);
   if (g->d_inflow) cudaFree(g->d_inflow);
   if (g->stage) cudaFree(g->stage);
   for (auto& sp : g->spg) if (sp.coef) cudaFree(sp.coef);
-  cudaStreamDestroy(g->st);
-  cudaStreamDestroy(g->xst);
-  cudaEventDestroy(g->ev_shell); cudaEventDestroy(g->ev_xdone);
+  if (g->st) cudaStreamDestroy(g->st);
+  if (g->xst) cudaStreamDestroy(g->xst);
+  if (g->ev_shell) cudaEventDestroy(g->ev_shell);
+  if (g->ev_xdone) cudaEventDestroy(g->ev_xdone);
   delete g;
   g = nullptr;
+  cudaGetLastError();
   return 0;
 }
 
@@ -666,6 +714,7 @@ int astr_gpu_comm_init(const char id[128], int nranks, int rank) {
   if (!g_nccl.load()) return astr_fail_msg("cannot load libnccl.so.2");
   ncclUniqueId uid;
   memcpy(&uid, id, 128);
+  release_comm();                                    // a second comm_init replaces the first communicator
   NCCL_OK(g_nccl.CommInitRank(&g->comm, nranks, uid, rank));
   g->nranks = nranks; g->rank = rank;
   return p2p_setup();
@@ -751,6 +800,8 @@ int astr_gpu_set_field(int field_id, const double* host) {
   }
   TRY(copy_field(s, const_cast<double*>(host), false));
   CUDA_OK(cudaStreamSynchronize(g->st));
+  // metrics given field by field (jacob, dxi): the caller vouches for the whole set, as with set_metrics
+  if (s == S_JAC || (s >= S_DXI && s < S_DXI + 9)) g->have_metrics = true;
   return 0;
 }
 
@@ -835,7 +886,7 @@ int astr_gpu_download_state(double* q, double* rho, double* vel, double* prs, do
   if (tmp) TRY(copy_field(S_TMP, tmp, true));
   CUDA_OK(cudaStreamSynchronize(g->st));
   prof_collect();
-  return 0;
+  return p2p_check();
 }
 
 // ---- stage operators -------------------------------------------------------------------
@@ -1150,7 +1201,7 @@ int astr_gpu_rk_steps_timed(int nsteps, double deltat, float* ms) {
   CUDA_OK(cudaEventElapsedTime(ms, a, b));
   cudaEventDestroy(a); cudaEventDestroy(b);
   prof_collect();
-  return rc;
+  return rc ? rc : p2p_check();
 }
 
 int astr_gpu_dataswap(int field_id, int direction) {
@@ -1232,7 +1283,7 @@ int astr_gpu_reduce_tgv(double out[3]) {
   CUDA_OK(cudaMemcpyAsync(h, g->d_out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, g->st));
   CUDA_OK(cudaStreamSynchronize(g->st));
   out[0] = h[0]; out[1] = h[1]; out[2] = 0.0;
-  return 0;
+  return p2p_check();
 }
 
 int astr_gpu_kernel_launches(long long* count) { *count = g_launches; return 0; }

@@ -78,8 +78,13 @@ struct LinePlan {
 // first row of regular chunk w
 ASTR_HD int plan_chunk_row(const LinePlan& p, int w) { return p.sh + w * ASTR_LMAX; }
 
+// ASTR_NO_FMA (the -fmad=false debug library, `make nofma`): every product is rounded before it is added, as
+// in the oracle (which is compiled with -ffp-contract=off, like the reference's golden run).  Whatever then
+// still differs from the oracle is re-association, not contraction (tests/test_gpu_nofma.py).
 ASTR_HD double fma_(double a, double b, double c) {
-#ifdef __CUDA_ARCH__
+#if defined(ASTR_NO_FMA) && defined(__CUDA_ARCH__)
+  return __dadd_rn(__dmul_rn(a, b), c);
+#elif defined(__CUDA_ARCH__)
   return __fma_rn(a, b, c);
 #else
   return std::fma(a, b, c);
@@ -310,36 +315,68 @@ ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_
 }
 
 // ---- head / tail block ----------------------------------------------------------------------
-// d[s]: right-hand side of slot s (any finite value on neutral slots)
+// The slots are processed in groups of ASTR_SG; groups that lie entirely behind the rows of the block
+// (warp-uniform test on `len`) are skipped, neutral slots inside the last group pass values through.
+#define ASTR_SG 8
+template <int S> struct SpecGroups { static constexpr int G = (S % ASTR_SG == 0) ? ASTR_SG : S, N = S / G; };
+
+// d[s]: right-hand side of slot s (any finite value on neutral slots of a processed group)
 template <int S>
 ASTR_HD void spec_forward(const SpecTab<S>& t, const double (&d)[S], double (&e)[S], double& yh, double& yt) {
+  constexpr int G = SpecGroups<S>::G, NG = SpecGroups<S>::N;
+  const int len = t.len;
+  yt = 0.0;
 #pragma unroll
-  for (int s = 0; s < S; ++s) e[s] = (s == 0) ? d[0] * t.m[0] : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d[s] * t.m[s]);
-  yt = e[S - 1];
+  for (int g = 0; g < NG; ++g) {
+    if (g * G < len) {
+#pragma unroll
+      for (int s = g * G; s < g * G + G; ++s)
+        e[s] = (s == 0) ? d[0] * t.m[0] : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d[s] * t.m[s]);
+      yt = e[g * G + G - 1];
+    }
+  }
   double y = 0.0;
 #pragma unroll
-  for (int s = S - 1; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s] * t.q[s]);
+  for (int g = NG - 1; g >= 0; --g) {
+    if (g * G < len) {
+#pragma unroll
+      for (int s = g * G + G - 1; s >= g * G; --s) y = fma_(-t.ac1[s], y, e[s] * t.q[s]);
+    }
+  }
   yh = y;
 }
 template <int S, class ST>
 ASTR_HD void spec_back(const SpecTab<S>& t, const double (&e)[S], double t_prev, double h_next, ST st) {
+  constexpr int G = SpecGroups<S>::G, NG = SpecGroups<S>::N;
+  const int len = t.len;
   double x = h_next;
 #pragma unroll
-  for (int s = S - 1; s >= 0; --s) {
-    x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s] * t.q[s]));
-    st(s, x);
+  for (int g = NG - 1; g >= 0; --g) {
+    if (g * G < len) {
+#pragma unroll
+      for (int s = g * G + G - 1; s >= g * G; --s) {
+        x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s] * t.q[s]));
+        st(s, x);
+      }
+    }
   }
 }
-// right-hand sides of the head block: closure rows first, interior rows behind them
+// right-hand sides of the head block: closure rows first, interior rows behind them (groups behind `len` skipped)
 template <int OP, bool P0, int HWN>
-ASTR_HD void head_rhs(const double (&hw)[HWN], const FilterCoef& fc, int nsf, double (&d)[ASTR_HS]) {
+ASTR_HD void head_rhs(const double (&hw)[HWN], const FilterCoef& fc, int nsf, int len, double (&d)[ASTR_HS]) {
+  constexpr int G = SpecGroups<ASTR_HS>::G, NG = SpecGroups<ASTR_HS>::N;
   double sf[5];
   closure_head<OP, P0>(hw, fc, sf);
 #pragma unroll
-  for (int s = 0; s < ASTR_HS; ++s) {
-    double v = reg_rhs<OP>(hw, s + (OpT<OP>::HB - OpT<OP>::H), fc);
-    if (s < 5) { if (s < nsf) v = sf[s]; }
-    d[s] = v;
+  for (int g = 0; g < NG; ++g) {
+    if (g * G < len) {
+#pragma unroll
+      for (int s = g * G; s < g * G + G; ++s) {
+        double v = reg_rhs<OP>(hw, s + (OpT<OP>::HB - OpT<OP>::H), fc);
+        if (s < 5) { if (s < nsf) v = sf[s]; }
+        d[s] = v;
+      }
+    }
   }
 }
 // tail block: (one interior row when st == nsl + 1,) then the closure rows

@@ -675,7 +675,11 @@ __global__ void k_sponge(const Layout L, double* __restrict__ pool, const Box b,
 // (L1-bypassing loads), and the last CTA acknowledges to the neighbour.
 // Same element order, averaging of shared nodes and plane ranges as k_face above; for i-faces
 // the plane index runs fastest so that the strided gather touches each sector once.
-// A wait that lasts longer than ~4 s raises *err and gives up (no hung GPU).
+// A wait that outlasts a.timeout_cycles (cfg.xchg_timeout_ms; default 4 s, <= 0 waits forever like ncclRecv)
+// POISONS the exchange: *err is set, the CTA neither moves data nor signals, and every later exchange kernel
+// of this rank returns at once; the neighbours then time out in turn.  The host sees the sticky error at the
+// next API call that synchronises (p2p_check in api.cu).  Nothing is ever unpacked from, or written over, a
+// window whose flag did not arrive.
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
@@ -691,14 +695,19 @@ __global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList f
   const int side = blockIdx.z;
   const XSide& xs = a.s[side];
   if (!xs.active) return;
+  __shared__ int s_ok;
   if (threadIdx.x == 0) {
+    int ok = (*reinterpret_cast<volatile unsigned int*>(a.err) == 0u);
     const long long t0 = clock64();
-    while (ld_acquire_sys(xs.wait_flag) < xs.wait_val) {
-      if (clock64() - t0 > (1LL << 33)) { atomicExch(a.err, 1u); break; }
-      __nanosleep(64);
+    while (ok && ld_acquire_sys(xs.wait_flag) < xs.wait_val) {
+      if (a.timeout_cycles > 0 && clock64() - t0 > a.timeout_cycles) { atomicExch(a.err, 1u); ok = 0; }
+      else if (*reinterpret_cast<volatile unsigned int*>(a.err) != 0u) ok = 0;    // another CTA gave up
+      else __nanosleep(64);
     }
+    s_ok = ok;
   }
   __syncthreads();
+  if (!s_ok) return;      // poisoned: no data phase, no signal
   const int n1 = (DIR == 0) ? L.jm + 1 : L.im + 1;
   const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
   const int np = a.l1 - a.l0 + 1;
@@ -931,11 +940,12 @@ static int face_launch(const Layout& L, const FieldList& fl, int dir, int side, 
 }
 template <bool SEND>
 static int xface_launch(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    CUDA_OK(cudaGetDevice(&dev));
+  static int sms = 0, sms_dev = -1;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (dev != sms_dev) {
     CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms_dev = dev;
   }
   // every field must be addressable from field 0 with one 64-bit element offset (same allocation or not:
   // pointer differences of device allocations are fine as plain integers)

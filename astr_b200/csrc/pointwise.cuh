@@ -100,7 +100,11 @@ struct XSide {
   unsigned long long signal_val;
   unsigned int* counter;             // CTA completion counter of this side (this rank's memory)
 };
-struct XArgs { XSide s[2]; int l0, l1; unsigned int* err; };
+struct XArgs {
+  XSide s[2]; int l0, l1;
+  unsigned int* err;                 // sticky error flag of this rank (XHeader::err)
+  long long timeout_cycles;          // flag waits longer than this poison the exchange; <= 0: wait forever
+};
 int pw_xsend(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st);
 int pw_xrecv(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st);
 // Fortran (im+11)(jm+11)(km+11) box <-> padded device box is done with cudaMemcpy3D in api.cu

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           if (k < nsf) {
-            const double e = __fma_rn(-eprev, ac3[r], sf[k] * ac2[r]);
+            const double e = fma_(-eprev, ac3[r], sf[k] * ac2[r]);
             tile[(first_node + r + 5) * SL] = e;
             eprev = e;
             ++r;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
         const int node = first_node + r;
         w[(t + 2 * H) % W] = F(node + H);
         const double d = interior_rhs<OP>(w, t);
-        const double e = __fma_rn(-eprev, ac3[r], d * ac2[r]);
+        const double e = fma_(-eprev, ac3[r], d * ac2[r]);
         eh[t] = e;
         eprev = e;
         ++r;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
           const int t = H + u;
           w[(t + 2 * H) % W] = fn[u];
           const double d = interior_rhs<OP>(w, t);
-          const double e = __fma_rn(-eprev, c3[u], d * c2[u]);
+          const double e = fma_(-eprev, c3[u], d * c2[u]);
           ps[u * SL] = e;
           eprev = e;
         }
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
           const int node = first_node + r;
           w[(t + 2 * H) % W] = F(node + H);
           const double d = interior_rhs<OP>(w, t);
-          const double e = __fma_rn(-eprev, ac3[r], d * ac2[r]);
+          const double e = fma_(-eprev, ac3[r], d * ac2[r]);
           tile[(node + 5) * SL] = e;
           eprev = e;
           ++r;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           if (k < nsl) {
-            const double e = __fma_rn(-eprev, ac3[r], sl[k] * ac2[r]);
+            const double e = fma_(-eprev, ac3[r], sl[k] * ac2[r]);
             tile[(first_node + r + 5) * SL] = e;
             eprev = e;
             ++r;
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const double dp = __fma_rn(pv[u], cin, ev[u]);
-          const double g = __fma_rn(-av[u], gnext, dp);
+          const double dp = fma_(pv[u], cin, ev[u]);
+          const double g = fma_(-av[u], gnext, dp);
           ps[-u * SL] = g;
           gnext = g;
         }
@@ -452,8 +452,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
       }
       for (; r >= ra; --r) {
         double* ps = tile + (first_node + r + 5) * SL;
-        const double dp = __fma_rn(pf[r], cin, *ps);
-        const double g = __fma_rn(-ac1[r], gnext, dp);
+        const double dp = fma_(pf[r], cin, *ps);
+        const double g = fma_(-ac1[r], gnext, dp);
         *ps = g;
         gnext = g;
       }
@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
               const int rx = max(r, 0);   // nd may sit one below the first row (its half is not stored)
               const double2 gv = *reinterpret_cast<const double2*>(srow + nd);
               double2 x;
-              x.x = __fma_rn(qb[rx], xrow[ch[rx] * ASTR_BW], gv.x);
-              x.y = __fma_rn(qb[r + 1], xrow[ch[r + 1] * ASTR_BW], gv.y);
+              x.x = fma_(qb[rx], xrow[ch[rx] * ASTR_BW], gv.x);
+              x.y = fma_(qb[r + 1], xrow[ch[r + 1] * ASTR_BW], gv.y);
               if (epi == EPI_ADD) { x.x = old[k].x + x.x; x.y = old[k].y + x.y; }
               else if (epi == EPI_STOREZ) {
                 if (nd < o_lo || nd > o_hi) x.x = 0.0;
@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(ASTR_BW* C* NG, 1) sweep_kernel(const SweepArg
                 const double2 gv = *reinterpret_cast<const double2*>(scol + r * ASTR_BW);
                 const double qv = qb[r];
                 double2 x;
-                x.x = __fma_rn(qv, xin.x, gv.x);
-                x.y = __fma_rn(qv, xin.y, gv.y);
+                x.x = fma_(qv, xin.x, gv.x);
+                x.y = fma_(qv, xin.y, gv.y);
                 if (epi == EPI_ADD) { x.x = old[k].x + x.x; x.y = old[k].y + x.y; }
                 else if (epi == EPI_STOREZ && (r < o_lo - first_node || r > o_hi - first_node)) { x.x = 0.0; x.y = 0.0; }
                 double* po = ocol + (long long)r * gl;

@@ -102,6 +102,27 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
+// Window loads as volatile asm: they stay in program order in front of the `empty` arrive, so the tile is
+// released (and refilled) before the elimination starts instead of after it (the compiler otherwise sinks the
+// loads next to their uses to save registers).
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -132,10 +153,29 @@ struct OutRange {
 
 // head / tail block right-hand sides, dispatched on the (warp-uniform) end types
 template <int OP, int HWN>
-__device__ __forceinline__ void head_rhs_any(bool p0, const double (&hw)[HWN], const FilterCoef& fc, int nsf,
+__device__ __forceinline__ void head_rhs_any(bool p0, const double (&hw)[HWN], const FilterCoef& fc, int nsf, int len,
                                              double (&d)[ASTR_HS]) {
-  if (p0) head_rhs<OP, true>(hw, fc, nsf, d);
-  else head_rhs<OP, false>(hw, fc, nsf, d);
+  if (p0) head_rhs<OP, true>(hw, fc, nsf, len, d);
+  else head_rhs<OP, false>(hw, fc, nsf, len, d);
+}
+// window of the head block, in groups of 8 slots (groups behind `lim` are skipped, the rest is zero):
+// LD(k) returns f(first_node - HB + k); the first 3 slots may lie in front of the halo (filter, interface end)
+template <int HWN, class LD>
+__device__ __forceinline__ void load_head_window(double (&hw)[HWN], int lim, int hnode0, LD ld) {
+#pragma unroll
+  for (int g = 0; g < (HWN + 7) / 8; ++g) {
+    if (g * 8 < lim) {
+#pragma unroll
+      for (int k = g * 8; k < g * 8 + 8 && k < HWN; ++k) {
+        bool in = k < lim;
+        if (k < 3) in = in && (hnode0 + k >= -ASTR_HM);
+        hw[k] = in ? ld(k) : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int k = g * 8; k < g * 8 + 8 && k < HWN; ++k) hw[k] = 0.0;
+    }
+  }
 }
 template <int OP>
 __device__ __forceinline__ void tail_rhs_any(bool pm, const double (&tw)[16], const FilterCoef& fc, int extra,
@@ -169,7 +209,7 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* 
 
   // tl[node * 32] = f(node) of this thread's pencil
   const double* tl = tile + ASTR_HM * 32 + lane;
-  const double* wp = tl + (node0 - H) * 32;
+  const unsigned wpa = smem_u32(tl + (node0 - H) * 32);
   unsigned phase = 0;
   int par = 0;
   for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
@@ -186,7 +226,7 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* 
     // ---- tile -> registers: the chunk (+ stencil overlap) -------------------------------------
     double wv[WN];
 #pragma unroll
-    for (int s = 0; s < WN; ++s) wv[s] = wp[s * 32];
+    for (int s = 0; s < WN; ++s) wv[s] = lds_f64(wpa + (unsigned)s * 256u);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty);      // this warp is done with the tile
 
@@ -269,22 +309,29 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
     double dh[ASTR_HS], dt[ASTR_TS];
     {
       double hw[HWN], tw[16];
-#pragma unroll
-      for (int k = 0; k < HWN; ++k) {
-        bool in = k < hwlim;
-        if (k < 3) in = in && (hnode0 + k >= -ASTR_HM);   // filter, interface end: slots in front of the halo
-        hw[k] = in ? hp[k * 32] : 0.0;
-      }
+      load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * 32]; });
 #pragma unroll
       for (int k = 0; k < 16; ++k) tw[k] = tp[k * 32];
-      head_rhs_any<OP>(p0, hw, fc, pl.nsf, dh);
+      head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
       tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty);
+    // producer: once every warp has copied its rows into registers the tile is refilled, so that the fetch of
+    // the next bundle runs under the elimination, the scan and the write-out of this one
+    if (lane == 0) {
+      mbar_arrive(empty);
+      if (bnd + (int)gridDim.x < nbundles) {
+        mbar_wait(empty, phase);
+        fetch(bnd + gridDim.x);
+      }
+    }
+    __syncwarp();
+    phase ^= 1;
 
     // ---- eliminate, publish S / S' -------------------------------------------------------------
-    double he[ASTR_HS], te[ASTR_TS];
+    // (in place: the right-hand sides become the eliminated rows)
+    double (&he)[ASTR_HS] = dh;
+    double (&te)[ASTR_TS] = dt;
     {
       double yh, yt;
       spec_forward(pl.head, dh, he, yh, yt);
@@ -294,13 +341,6 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
       sS[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
       sP[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
     }
-    // producer: every warp has copied its rows into registers -> the tile may be overwritten
-    if (lane == 0 && bnd + (int)gridDim.x < nbundles) {
-      mbar_wait(empty, phase);
-      fetch(bnd + gridDim.x);
-    }
-    __syncwarp();
-    phase ^= 1;
     cta_sync(1, nthreads);
 
     // ---- solution of the two blocks, write-out --------------------------------------------------
@@ -379,22 +419,31 @@ struct ICtx {
   int sp, nthreads, nbundles, pl0, npairs;
 };
 
-// registers -> output tile happened for the lanes of round r; now the tile leaves as full aligned lines
+// registers -> output tile happened for the lanes of round r; now the tile leaves as full aligned lines: one
+// bulk store (`cp.async.bulk.global.shared::cta`) per line covers the node pairs that are written unmodified,
+// single lanes write the (at most two) edge nodes.  The issuing lane waits until the bulk engine has READ the
+// tile (not until the data is in HBM) before the tile is handed back.
 __device__ __forceinline__ void copy_out_round(const Sweep2Args& a, const ICtx& c, const OutRange& R, double* __restrict__ gout,
                                                int j0, int by, int r) {
   const Layout& Lay = a.L;
+  fence_async_smem();                                      // staged values -> visible to the bulk engine
   cta_sync(2, c.nthreads);
   const int nl = min(16, Lay.jm - (j0 + 16 * r) + 1);     // valid lines of this round
-  for (int it = threadIdx.x; it < nl * c.npairs; it += c.nthreads) {
-    const int ll = (int)fdiv((unsigned)it, a.dpair);
-    const int node = c.pl0 + 2 * (it - ll * c.npairs);
-    const double2 v = *reinterpret_cast<const double2*>(c.tout + ll * c.sp + 6 + node);
-    double* po = gout + Lay.idx(node, j0 + 16 * r + ll, by);
-    const bool w0 = R.writes(node), w1 = R.writes(node + 1);
-    if (w0 && w1) *reinterpret_cast<double2*>(po) = make_double2(R.value(node, v.x), R.value(node + 1, v.y));
-    else if (w0) po[0] = R.value(node, v.x);
-    else if (w1) po[1] = R.value(node + 1, v.y);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = c.nthreads >> 5;
+  const int lo = max(R.w_lo, R.storez ? R.o_lo : R.w_lo), hi = min(R.w_hi, R.storez ? R.o_hi : R.w_hi);
+  const int nf0 = (lo + 1) & ~1;                           // first node of the first full pair
+  const int nf1 = max((hi + 1) & ~1, nf0);                 // end of the full pairs (exclusive, even)
+  const int e0 = min(nf0, R.w_hi + 1), e1 = max(nf1, R.w_lo);
+  for (int ll = w; ll < nl; ll += nw) {
+    const double* srow = c.tout + ll * c.sp + 6;           // srow[node]
+    double* grow = gout + Lay.idx(0, j0 + 16 * r + ll, by); // grow[node]
+    if (lane == 0 && nf1 > nf0) bulk_store(grow + nf0, srow + nf0, (unsigned)(nf1 - nf0) * 8u);
+    // the written nodes outside the full pairs: [w_lo, e0) and [e1, w_hi]
+    for (int node = R.w_lo + lane; node < e0; node += 32) grow[node] = R.value(node, srow[node]);
+    for (int node = e1 + lane; node <= R.w_hi; node += 32) grow[node] = R.value(node, srow[node]);
   }
+  if (lane == 0) { bulk_commit(); bulk_wait_read(); }
+  __syncwarp();
   // after round 1 the output tile is next written behind barrier 1 of the following bundle
   if (r == 0) cta_sync(3, c.nthreads);
 }
@@ -411,7 +460,7 @@ __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& 
   const int node0 = pl.first_node + plan_chunk_row(pl, w);
   const int me = w + 1;
   // 16-byte loads: node0 - H + 6 is even (build_line_plan, align_even)
-  const double2* wp = reinterpret_cast<const double2*>(c.tin + lane * c.sp + 6 + (node0 - H));
+  const unsigned wpa = smem_u32(c.tin + lane * c.sp + 6 + (node0 - H));
   double* orow = c.tout + (lane & 15) * c.sp + 6 + node0;
   const double* sSl = &c.sS[0][lane];
   const double* sPl = &c.sP[0][lane];
@@ -422,7 +471,7 @@ __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& 
     phase ^= 1;
     double wv[WN];
 #pragma unroll
-    for (int s = 0; s < WN / 2; ++s) { const double2 v = wp[s]; wv[2 * s] = v.x; wv[2 * s + 1] = v.y; }
+    for (int s = 0; s < WN / 2; ++s) { const double2 v = lds_v2f64(wpa + (unsigned)s * 16u); wv[2 * s] = v.x; wv[2 * s + 1] = v.y; }
     __syncwarp();
     if (lane == 0) mbar_arrive(c.empty);
     double e[L];
@@ -449,6 +498,7 @@ __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& 
       copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
     }
   }
+  if (lane == 0) bulk_wait_all();
 }
 
 template <int OP>
@@ -489,20 +539,22 @@ __device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& 
     double dh[ASTR_HS], dt[ASTR_TS];
     {
       double hw[HWN], tw[16];
-#pragma unroll
-      for (int k = 0; k < HWN; ++k) {
-        bool in = k < hwlim;
-        if (k < 3) in = in && (hnode0 + k >= -ASTR_HM);
-        hw[k] = in ? lrow[hnode0 + k] : 0.0;
-      }
+      load_head_window(hw, hwlim, hnode0, [&](int k) { return lrow[hnode0 + k]; });
 #pragma unroll
       for (int k = 0; k < 16; ++k) tw[k] = lrow[n - 10 + k];
-      head_rhs_any<OP>(p0, hw, fc, pl.nsf, dh);
+      head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
       tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(c.empty);
-    double he[ASTR_HS], te[ASTR_TS];
+    if (bnd + (int)gridDim.x < c.nbundles) {        // producer: refill as soon as every warp has its rows
+      if (lane == 0) mbar_wait(c.empty, phase);
+      __syncwarp();
+      fetch(bnd + gridDim.x);
+    }
+    phase ^= 1;
+    double (&he)[ASTR_HS] = dh;                    // in place: the right-hand sides become the eliminated rows
+    double (&te)[ASTR_TS] = dt;
     {
       double yh, yt;
       spec_forward(pl.head, dh, he, yh, yt);
@@ -512,12 +564,6 @@ __device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& 
       c.sS[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
       c.sP[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
     }
-    if (bnd + (int)gridDim.x < c.nbundles) {
-      if (lane == 0) mbar_wait(c.empty, phase);
-      __syncwarp();
-      fetch(bnd + gridDim.x);
-    }
-    phase ^= 1;
     cta_sync(1, c.nthreads);
     auto GS = [&](int idx) { return sSl[idx * 32]; };
     auto GP = [&](int idx) { return sPl[idx * 32]; };
@@ -531,13 +577,18 @@ __device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& 
     for (int r = 0; r < 2; ++r) {
       if ((lane >> 4) == r) {
 #pragma unroll
-        for (int s = 0; s < ASTR_HS; ++s) if (s < pl.sh) orow[pl.first_node + s] = he[s];
+        for (int g = 0; g < ASTR_HS / 8; ++g)
+          if (g * 8 < pl.sh) {
+#pragma unroll
+            for (int s = g * 8; s < g * 8 + 8; ++s) if (s < pl.sh) orow[pl.first_node + s] = he[s];
+          }
 #pragma unroll
         for (int s = 0; s < ASTR_TS; ++s) if (s < pl.st) orow[tnode0 + s] = te[s];
       }
       copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
     }
   }
+  if (lane == 0) bulk_wait_all();
 }
 
 template <int OP>

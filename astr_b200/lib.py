@@ -62,6 +62,7 @@ class AstrCfg(ctypes.Structure):
         ("nondimen", ctypes.c_int), ("flowtype", ctypes.c_int),
         ("recon_schem", ctypes.c_int), ("conschm_explicit", ctypes.c_int), ("lchardecomp", ctypes.c_int), ("bctype", ctypes.c_int * 6),
         ("legacy_sweep", ctypes.c_int), ("overlap_visc", ctypes.c_int), ("xchg_nccl", ctypes.c_int),
+        ("xchg_timeout_ms", ctypes.c_int), ("reserved0", ctypes.c_int),
         ("alfa_filter", ctypes.c_double),
         ("reynolds", ctypes.c_double), ("mach", ctypes.c_double), ("prandtl", ctypes.c_double),
         ("gamma", ctypes.c_double), ("ref_tem", ctypes.c_double),
@@ -76,6 +77,24 @@ class AstrCfg(ctypes.Structure):
 
 def lib_path() -> str:
     return _SO
+
+
+def use_debug_library(path: str):
+    """Tests only: bind another build of the same sources (libastr_gpu_nofma.so, `make nofma`) instead of the
+    production library.  Must be called before the first load()."""
+    global _SO
+    if _lib is not None:
+        raise AstrGpuError("use_debug_library must be called before the library is loaded")
+    _SO = path
+
+
+def build_nofma() -> str:
+    """Compile the -fmad=false debug library astr_b200/libastr_gpu_nofma.so (tests/test_gpu_nofma.py)."""
+    csrc = os.path.join(_HERE, "csrc")
+    r = subprocess.run(["make", "-C", csrc, "-j8", "nofma"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise AstrGpuError("building libastr_gpu_nofma.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return os.path.join(_HERE, "libastr_gpu_nofma.so")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -64,7 +64,7 @@ class RhsEngine:
                  twall: Sequence[float] = (0.0,) * 6, explicit: bool = False, conschm: Optional[int] = None,
                  lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
                  conschm_explicit: bool = False, legacy_sweep: bool = False, overlap_visc: bool = False,
-                 xchg_nccl: bool = False):
+                 xchg_nccl: bool = False, xchg_timeout_ms: int = 0):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -74,6 +74,7 @@ class RhsEngine:
         c.abi_version = 3
         # engine switches of ABI v3 (0 = default: register line-solve engine, peer-memory halo exchange)
         c.legacy_sweep, c.overlap_visc, c.xchg_nccl = int(legacy_sweep), int(overlap_visc), int(xchg_nccl)
+        c.xchg_timeout_ms = int(xchg_timeout_ms)
         c.device = device
         c.im, c.jm, c.km = block.dims
         c.ia, c.ja, c.ka = global_dims

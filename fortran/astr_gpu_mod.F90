@@ -32,6 +32,7 @@ module astr_gpu_mod
     integer(c_int) :: recon_schem,conschm_explicit,lchardecomp
     integer(c_int) :: bctype(6)
     integer(c_int) :: legacy_sweep,overlap_visc,xchg_nccl
+    integer(c_int) :: xchg_timeout_ms,reserved0
     real(c_double) :: alfa_filter
     real(c_double) :: reynolds,mach,prandtl,gamma,ref_tem
     real(c_double) :: const1,const2,const3,const4,const5,const6,const7
@@ -222,6 +223,7 @@ module astr_gpu_mod
     cfg%nondimen=merge(1,0,nondimen); cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall
     cfg%legacy_sweep=0; cfg%overlap_visc=0; cfg%xchg_nccl=0   ! engine switches: defaults
+    cfg%xchg_timeout_ms=0; cfg%reserved0=0
     cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
     cfg%conschm_explicit=merge(1,0,conschm(4:4)=='e' .and. mod(cfg%conschm/100,2)==1)
     cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt; cfg%pinf=pinf

@@ -80,6 +80,11 @@ typedef struct astr_cfg {
                                  side stream behind the interior stress+flux pass       */
   int xchg_nccl;              /* 1: halo exchange through ncclSend/ncclRecv instead of
                                  peer-memory stores (CUDA IPC)                          */
+  int xchg_timeout_ms;        /* peer-memory exchange: a neighbour flag that does not
+                                 arrive within this time poisons the exchange (sticky
+                                 error at the next synchronising call).  0: 4000 ms;
+                                 < 0: wait forever, like ncclRecv / MPI_Sendrecv         */
+  int reserved0;              /* keeps the doubles 8-byte aligned; must be 0            */
   double alfa_filter;         /* 0.49 in every example                                   */
   double reynolds, mach, prandtl, gamma, ref_tem;
   double const1, const2, const3, const4, const5, const6, const7; /* solver.F90:104-126  */

@@ -474,4 +474,14 @@ int oracle_num_threads() {
   return 1;
 #endif
 }
+// bench.py: launchers such as torch.distributed.run export OMP_NUM_THREADS=1; the CPU baseline sets its
+// thread count explicitly and reports what it got
+int oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 }

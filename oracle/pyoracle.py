@@ -75,6 +75,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_scheme_tables.argtypes = [ci, ci, ci, cd, vp, vp, vp, vp, vp, vp]
         L.oracle_scheme_tables.restype = ci
         L.oracle_num_threads.restype = ci
+        L.oracle_set_num_threads.restype = ci
+        L.oracle_set_num_threads.argtypes = [ci]
         L.oracle_case_create.restype = vp
         L.oracle_case_create.argtypes = [ci] * 9 + [cd] * 8
         L.oracle_case_destroy.argtypes = [vp]
@@ -126,6 +128,11 @@ def lib() -> ctypes.CDLL:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the following runs (overrides OMP_NUM_THREADS); returns the count in effect."""
+    return lib().oracle_set_num_threads(int(n))
 
 
 # --------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ int run_line(const LinePlan& pl, const FilterCoef& fc, const double* f5 /* f5[k]
   auto F = [&](int node) { return (node >= -5 && node <= n + 5) ? f5[node + 5] : 0.0; };
   std::vector<double> S(ASTR_EMAX + 2 * ASTR_WPAD, 0.0), SP(ASTR_EMAX + 2 * ASTR_WPAD, 0.0);
   std::vector<std::vector<double>> e(NW, std::vector<double>(L, 0.0));
-  double he[ASTR_HS], te[ASTR_TS];
+  double he[ASTR_HS] = {0}, te[ASTR_TS] = {0};
   auto publish = [&](int el, double yh, double yt) {
     S[el + ASTR_WPAD] = fma_(pl.el[el + ASTR_WPAD].gamma, yh, yt);
     SP[el + ASTR_WPAD] = fma_(pl.el[el + ASTR_WPAD].gammap, yt, yh);
@@ -30,8 +30,8 @@ int run_line(const LinePlan& pl, const FilterCoef& fc, const double* f5 /* f5[k]
   {
     double hw[HWN];
     for (int k = 0; k < HWN; ++k) hw[k] = (k < std::max(14, pl.sh + HB + H)) ? F(pl.first_node - HB + k) : 0.0;   // 14: reach of the closure rows
-    double d[ASTR_HS], yh, yt;
-    head_rhs<OP, P0>(hw, fc, pl.nsf, d);
+    double d[ASTR_HS] = {0}, yh, yt;
+    head_rhs<OP, P0>(hw, fc, pl.nsf, pl.sh, d);
     spec_forward(pl.head, d, he, yh, yt);
     publish(0, yh, yt);
   }

@@ -345,19 +345,30 @@ def test_long_i_lines(oracle, kw):
     dict(n=(72, 100, 80), homo=(False, False, False), stretch=True),
     dict(n=(80, 44, 150), homo=(True, False, True), stretch=True),
 ], ids=["periodic", "walls", "wall_j"])
-@pytest.mark.parametrize("legacy", [False, True], ids=["register_engine", "shared_memory_engine"])
-def test_line_solve_engines(oracle, kw, legacy):
-    # both line-solve engines on the same inputs, each against the oracle: the register engine (sweep2.cu: 2-4
+def test_line_solve_engines(oracle, kw):
+    # both line-solve engines on the same inputs, each against the oracle: the register engine (sweep2.cu: 1-4
     # regular chunks per line here, head / tail blocks of every ntype, all three directions) and the
-    # shared-memory engine (sweep.cu, cfg.legacy_sweep = 1), which stays the fallback for short lines
-    c, eng = make_pair(oracle, engine_kw=dict(legacy_sweep=legacy), **kw)
-    c.filterq(); eng.filterq()
-    assert_fields_close(c, eng, QS, OP_TOL, what="filterq")
-    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
-    assert_fields_close(c, eng, DVEL + DTMP, 2e-12, what="gradcal")
-    c.zero_qrhs(); c.rhscal(); eng.rhscal()
-    assert_fields_close(c, eng, QRHS, 3e-12, what="rhscal")
-    eng.close(); c.close()
+    # shared-memory engine (sweep.cu, cfg.legacy_sweep = 1), which stays the fallback for short lines.
+    # Tolerances: the filter at OP_TOL.  A derivative of a field f with max|f| = F on a grid of spacing h carries
+    # rounding ~ eps F / h whatever the engine; relative to max|df/dx| that is the condition number F / (h |df/dx|):
+    # ~20 for the velocity, 1e2..1e4 for the temperature of a Mach-0.1 flow (T = 1 + O(1e-2)), larger still for
+    # the mass residual of a nearly solenoidal field.  So the derivative-based quantities get a sanity bound here
+    # and the sharp statement is the comparison of the two engines: the register engine must stay within 3x of
+    # the shared-memory engine's own error (+ OP_TOL) on every field.
+    errs = {}
+    for legacy in (False, True):
+        c, eng = make_pair(oracle, engine_kw=dict(legacy_sweep=legacy), **kw)
+        c.filterq(); eng.filterq()
+        e = assert_fields_close(c, eng, QS, OP_TOL, what=f"filterq legacy={legacy}")
+        c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+        e.update(assert_fields_close(c, eng, DVEL, 5e-12, what=f"gradcal dvel legacy={legacy}"))
+        e.update(assert_fields_close(c, eng, DTMP, 1e-10, what=f"gradcal dtmp legacy={legacy}"))
+        c.zero_qrhs(); c.rhscal(); eng.rhscal()
+        e.update(assert_fields_close(c, eng, QRHS, 1e-10, what=f"rhscal legacy={legacy}"))
+        errs[legacy] = e
+        eng.close(); c.close()
+    worse = {k: (errs[False][k], errs[True][k]) for k in errs[False] if errs[False][k] > 3.0 * errs[True][k] + OP_TOL}
+    assert not worse, f"register engine less accurate than the shared-memory engine: {worse}"
 
 
 def test_compact_flux_solves_on_the_register_engine(oracle):
