@@ -1309,9 +1309,15 @@ int astr_gpu_get_profile(double* ms, long long* n, int cap) {
 int astr_gpu_bench_sweep(int op, int dir, int nfields, int iters, float* ms_per_launch) {
   NEED_CTX();
   if (nfields < 1 || nfields > 5 || dir < 0 || dir > 2) return astr_fail_msg("bench_sweep: bad arguments");
+  // op: 0 derivative (q -> G slots), 1 filter (G in place); +10 swaps the placement (derivative in place, filter
+  // out of place) for experiments
+  const bool swap = op >= 10;
+  op %= 10;
+  if (op != OP_DERIV && op != OP_FILTER) return astr_fail_msg("bench_sweep: bad operator");
+  const bool inplace = (op == OP_FILTER) != swap;
   const double* in[5]; double* out[5];
   for (int m = 0; m < nfields; ++m) {
-    in[m] = (op == OP_FILTER) ? g->slot(S_G + m) : g->slot(S_Q + m);
+    in[m] = inplace ? g->slot(S_G + m) : g->slot(S_Q + m);
     out[m] = g->slot(S_G + m);
   }
   cudaEvent_t a, b;

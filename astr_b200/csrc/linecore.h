@@ -135,10 +135,11 @@ struct FilterCoef {
 
 template <int OP> struct OpT;
 // H: half width of the interior stencil; HB: reach of the head block's window in front of the first row
-template <> struct OpT<0> { static constexpr int H = 2, HB = 3; };   // OP_DERIV (interface row: 7-point explicit)
-template <> struct OpT<1> { static constexpr int H = 5, HB = 5; };   // OP_FILTER
-template <> struct OpT<2> { static constexpr int H = 2, HB = 2; };   // OP_FLUXP
-template <> struct OpT<3> { static constexpr int H = 2, HB = 2; };   // OP_FLUXM
+// CR: window slots the closure rows of the first end may read
+template <> struct OpT<0> { static constexpr int H = 2, HB = 3, CR = 7; };    // OP_DERIV (interface row: 7-point explicit)
+template <> struct OpT<1> { static constexpr int H = 5, HB = 5, CR = 14; };   // OP_FILTER
+template <> struct OpT<2> { static constexpr int H = 2, HB = 2, CR = 6; };    // OP_FLUXP
+template <> struct OpT<3> { static constexpr int H = 2, HB = 2, CR = 6; };    // OP_FLUXM
 
 // first row of the system as a node index: fd_scheme_initiate (src/derivative.F90:74-93),
 // compact_filter_initiate (src/filter.F90:44-71), compact_flux_initiate (src/flux.F90:44-70)
@@ -293,6 +294,12 @@ template <int OP, int WN>
 ASTR_HD void chunk_forward(const RegTab& t, const FilterCoef& fc, const double (&wv)[WN], double (&e)[ASTR_LMAX],
                            double& yh, double& yt) {
   constexpr int L = ASTR_LMAX;
+#ifdef ASTR_SKELETON   // experiment build (`make skel`): data movement only, no arithmetic
+#pragma unroll
+  for (int s = 0; s < L; ++s) e[s] = wv[s + OpT<OP>::H];
+  yh = 0.0; yt = 0.0;
+  return;
+#endif
 #pragma unroll
   for (int s = 0; s < L; ++s) {
     const double d = reg_rhs<OP>(wv, s, fc);
@@ -306,6 +313,11 @@ ASTR_HD void chunk_forward(const RegTab& t, const FilterCoef& fc, const double (
 // pass 3: ST(s, x) receives the solution of row s (descending)
 template <class ST>
 ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_prev, double h_next, ST st) {
+#ifdef ASTR_SKELETON
+#pragma unroll
+  for (int s = ASTR_LMAX - 1; s >= 0; --s) st(s, e[s]);
+  return;
+#endif
   double x = h_next;
 #pragma unroll
   for (int s = ASTR_LMAX - 1; s >= 0; --s) {
@@ -321,8 +333,10 @@ ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_
 template <int S> struct SpecGroups { static constexpr int G = (S % ASTR_SG == 0) ? ASTR_SG : S, N = S / G; };
 
 // d[s]: right-hand side of slot s (any finite value on neutral slots of a processed group)
-template <int S>
-ASTR_HD void spec_forward(const SpecTab<S>& t, const double (&d)[S], double (&e)[S], double& yh, double& yt) {
+// S: slots processed (the block has at most S rows); TS: slots of the table
+template <int S, int TS>
+ASTR_HD void spec_forward(const SpecTab<TS>& t, const double (&d)[S], double (&e)[S], double& yh, double& yt) {
+  static_assert(S <= TS, "slots");
   constexpr int G = SpecGroups<S>::G, NG = SpecGroups<S>::N;
   const int len = t.len;
   yt = 0.0;
@@ -345,8 +359,8 @@ ASTR_HD void spec_forward(const SpecTab<S>& t, const double (&d)[S], double (&e)
   }
   yh = y;
 }
-template <int S, class ST>
-ASTR_HD void spec_back(const SpecTab<S>& t, const double (&e)[S], double t_prev, double h_next, ST st) {
+template <int S, int TS, class ST>
+ASTR_HD void spec_back(const SpecTab<TS>& t, const double (&e)[S], double t_prev, double h_next, ST st) {
   constexpr int G = SpecGroups<S>::G, NG = SpecGroups<S>::N;
   const int len = t.len;
   double x = h_next;
@@ -362,9 +376,9 @@ ASTR_HD void spec_back(const SpecTab<S>& t, const double (&e)[S], double t_prev,
   }
 }
 // right-hand sides of the head block: closure rows first, interior rows behind them (groups behind `len` skipped)
-template <int OP, bool P0, int HWN>
-ASTR_HD void head_rhs(const double (&hw)[HWN], const FilterCoef& fc, int nsf, int len, double (&d)[ASTR_HS]) {
-  constexpr int G = SpecGroups<ASTR_HS>::G, NG = SpecGroups<ASTR_HS>::N;
+template <int OP, bool P0, int HWN, int S>
+ASTR_HD void head_rhs(const double (&hw)[HWN], const FilterCoef& fc, int nsf, int len, double (&d)[S]) {
+  constexpr int G = SpecGroups<S>::G, NG = SpecGroups<S>::N;
   double sf[5];
   closure_head<OP, P0>(hw, fc, sf);
 #pragma unroll

@@ -58,7 +58,7 @@ __device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) {
 struct Sweep2Args {
   Layout L;
   int rb, nbox;              // j/k: line nodes per TMA box, boxes per bundle
-  int sp;                    // i: row pitch of the shared-memory line tile (doubles, == 2 mod 16)
+  int sp;                    // i: row pitch of the shared-memory line tile (doubles, sp/2 odd)
   int slot[ASTR_MAXF];       // j/k: 4th tensor coordinate of each input field
   const double* in[ASTR_MAXF];
   double* out[ASTR_MAXF];
@@ -152,9 +152,9 @@ struct OutRange {
 };
 
 // head / tail block right-hand sides, dispatched on the (warp-uniform) end types
-template <int OP, int HWN>
+template <int OP, int HWN, int S>
 __device__ __forceinline__ void head_rhs_any(bool p0, const double (&hw)[HWN], const FilterCoef& fc, int nsf, int len,
-                                             double (&d)[ASTR_HS]) {
+                                             double (&d)[S]) {
   if (p0) head_rhs<OP, true>(hw, fc, nsf, len, d);
   else head_rhs<OP, false>(hw, fc, nsf, len, d);
 }
@@ -257,12 +257,14 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* 
   }
 }
 
-template <int DIR, int OP>
+// HSL: slots of the head block that are processed (8 when the block has at most 8 rows -- the common case, e.g.
+// 512-node lines -- else ASTR_HS): the short variant is straight-line code with everything in registers
+template <int DIR, int OP, int HSL>
 __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensorMap* tm, const double* tile,
                                              double (*sS)[ESZ][32], double (*sP)[ESZ][32], unsigned long long* full,
                                              unsigned long long* empty) {
   constexpr int H = OpT<OP>::H, HB = OpT<OP>::HB;
-  constexpr int HWN = ASTR_HS + HB + H;
+  constexpr int HWN = (HSL + HB + H > OpT<OP>::CR) ? HSL + HB + H : OpT<OP>::CR;
   const LinePlan& pl = c_plan[OP][DIR];
   const FilterCoef& fc = c_fc2;
   const Layout& Lay = a.L;
@@ -274,7 +276,7 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
   const int nbundles = (int)(a.dxy.d * (unsigned)a.nf);
   const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);
   const unsigned tile_bytes = (unsigned)(a.rb * a.nbox) * 256u;
-  const int hwlim = max(14, pl.sh + HB + H);          // 14: reach of the closure rows
+  const int hwlim = max(OpT<OP>::CR, pl.sh + HB + H);  // CR: reach of the closure rows
   const int hnode0 = pl.first_node - HB;              // node of window slot 0
   const int tnode0 = pl.first_node + pl.nrows - pl.st; // node of the first tail row
 
@@ -283,7 +285,10 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
   auto fetch = [&](int bnd) {
     const BundlePos p = locate(bnd, a);
     mbar_expect_tx(full, tile_bytes);
-    for (int b = 0; b < a.nbox; ++b) {
+    // the boxes of a tile are requested in an order rotated by the CTA index: neighbouring CTAs (neighbouring
+    // pencils) otherwise walk the same planes / rows in lockstep and crowd the same DRAM pages
+    for (int b0 = 0; b0 < a.nbox; ++b0) {
+      const int b = (b0 + (int)blockIdx.x) % a.nbox;
       void* dst = const_cast<double*>(tile) + (size_t)b * a.rb * 32;
       if (DIR == 1) tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, b * a.rb, p.by + ASTR_HM, a.slot[p.bz], full);
       else tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, p.by + ASTR_HM, b * a.rb, a.slot[p.bz], full);
@@ -306,7 +311,7 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
 
     mbar_wait(full, phase);
     // ---- tile -> right-hand sides of the two blocks (the windows die before the tile is released) ----
-    double dh[ASTR_HS], dt[ASTR_TS];
+    double dh[HSL], dt[ASTR_TS];
     {
       double hw[HWN], tw[16];
       load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * 32]; });
@@ -330,7 +335,7 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
 
     // ---- eliminate, publish S / S' -------------------------------------------------------------
     // (in place: the right-hand sides become the eliminated rows)
-    double (&he)[ASTR_HS] = dh;
+    double (&he)[HSL] = dh;
     double (&te)[ASTR_TS] = dt;
     {
       double yh, yt;
@@ -386,17 +391,38 @@ sweep2_kernel(const __grid_constant__ Sweep2Args a, const __grid_constant__ CUte
   __syncthreads();
   const int w = threadIdx.x >> 5;
   if (w < NW) regular_loop<DIR, OP>(a, tile, sS, sP, &mbar[0], &mbar[1]);
-  else special_loop<DIR, OP>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
+  else if (c_plan[OP][DIR].sh <= 8) special_loop<DIR, OP, 8>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
+  else special_loop<DIR, OP, ASTR_HS>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
 }
 
 // =============================================================================================
 // i sweeps
 // =============================================================================================
-// regular chunk: x of rows s = 0..L-1 into the output tile row `orow` (node0 at column c0)
+// Two line tiles [LINES][sp] (double buffer).  A bundle lives in ONE tile from its fetch to its write-out: the
+// chunk windows are read into registers, the solution is staged back IN PLACE (every warp has its window by
+// then: barrier 1 lies in between), and one bulk store per line (`cp.async.bulk.global.shared::cta`) moves
+// the written node range out.  Meanwhile the other tile receives the next bundle.
+// Warp roles: warps 0..NW-1 regular chunks, warp NW the head / tail blocks, warp NW+1 the PRODUCER: it alone
+// talks to the bulk engine -- waits until every compute warp has staged its part of a tile (`staged` mbarrier,
+// a non-blocking arrive for the compute warps), issues the stores, waits until the engine has READ the tile and
+// refills it with the bundle after next.  The compute warps therefore only ever wait for data (`full`) and for
+// each other's boundary sums (barrier 1); tools/tma_probe.cu shows that one warp per SM driving 2 x 24 lines
+// through the bulk engine this way sustains the full HBM copy bandwidth.
+// LINES = 32 when two tiles fit in shared memory, else 24 (lanes 24..31 idle): 512-node lines take 4.2 KB each.
+struct ICtx {
+  double* tile[2];           // [LINES][sp]: column c of a row = node c - 6
+  double* sS[2];             // [parity][ESZ][LINES]: boundary sums of the elements; a parity is reused two bundles
+  double* sP[2];             // later, after every reader has signalled `staged` and the tile has been refilled
+  unsigned long long* full;  // [2] tile filled (producer -> compute warps)
+  unsigned long long* staged;// [2] solution staged (compute warps -> producer)
+  int sp, ncompute, nbundles;
+};
+
+// regular chunk: x of rows s = 0..L-1 into the tile row (orow = address of row 0's node)
 template <int OP>
 __device__ __forceinline__ void stage_chunk(double* orow, const double (&x)[ASTR_LMAX]) {
   constexpr int L = ASTR_LMAX;
-  // orow is the address of row 0's node; it is 16-byte aligned when H is even (node0 - H + 6 is even)
+  // 16-byte aligned when H is even (node0 - H + 6 is even)
   if ((OpT<OP>::H & 1) == 0) {
 #pragma unroll
     for (int s = 0; s < L; s += 2) *reinterpret_cast<double2*>(orow + s) = make_double2(x[s], x[s + 1]);
@@ -407,48 +433,14 @@ __device__ __forceinline__ void stage_chunk(double* orow, const double (&x)[ASTR
     orow[L - 1] = x[L - 1];
   }
 }
-
-// state shared by the two role loops of the i kernel
-struct ICtx {
-  double* tin;               // [32][sp]: column c of a row = node c - 6
-  double* tout;              // [16][sp]
-  double (*sS)[32];          // [ESZ][32]
-  double (*sP)[32];
-  unsigned long long* full;
-  unsigned long long* empty;
-  int sp, nthreads, nbundles, pl0, npairs;
-};
-
-// registers -> output tile happened for the lanes of round r; now the tile leaves as full aligned lines: one
-// bulk store (`cp.async.bulk.global.shared::cta`) per line covers the node pairs that are written unmodified,
-// single lanes write the (at most two) edge nodes.  The issuing lane waits until the bulk engine has READ the
-// tile (not until the data is in HBM) before the tile is handed back.
-__device__ __forceinline__ void copy_out_round(const Sweep2Args& a, const ICtx& c, const OutRange& R, double* __restrict__ gout,
-                                               int j0, int by, int r) {
-  const Layout& Lay = a.L;
-  fence_async_smem();                                      // staged values -> visible to the bulk engine
-  cta_sync(2, c.nthreads);
-  const int nl = min(16, Lay.jm - (j0 + 16 * r) + 1);     // valid lines of this round
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = c.nthreads >> 5;
-  const int lo = max(R.w_lo, R.storez ? R.o_lo : R.w_lo), hi = min(R.w_hi, R.storez ? R.o_hi : R.w_hi);
-  const int nf0 = (lo + 1) & ~1;                           // first node of the first full pair
-  const int nf1 = max((hi + 1) & ~1, nf0);                 // end of the full pairs (exclusive, even)
-  const int e0 = min(nf0, R.w_hi + 1), e1 = max(nf1, R.w_lo);
-  for (int ll = w; ll < nl; ll += nw) {
-    const double* srow = c.tout + ll * c.sp + 6;           // srow[node]
-    double* grow = gout + Lay.idx(0, j0 + 16 * r + ll, by); // grow[node]
-    if (lane == 0 && nf1 > nf0) bulk_store(grow + nf0, srow + nf0, (unsigned)(nf1 - nf0) * 8u);
-    // the written nodes outside the full pairs: [w_lo, e0) and [e1, w_hi]
-    for (int node = R.w_lo + lane; node < e0; node += 32) grow[node] = R.value(node, srow[node]);
-    for (int node = e1 + lane; node <= R.w_hi; node += 32) grow[node] = R.value(node, srow[node]);
-  }
-  if (lane == 0) { bulk_commit(); bulk_wait_read(); }
+// a compute warp is done with its part of the tile: make the staged values visible to the bulk engine, tell the producer
+__device__ __forceinline__ void signal_staged(unsigned long long* staged) {
+  fence_async_smem();
   __syncwarp();
-  // after round 1 the output tile is next written behind barrier 1 of the following bundle
-  if (r == 0) cta_sync(3, c.nthreads);
+  if ((threadIdx.x & 31) == 0) mbar_arrive(staged);
 }
 
-template <int OP>
+template <int OP, int LINES>
 __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& c) {
   constexpr int H = OpT<OP>::H;
   constexpr int L = ASTR_LMAX;
@@ -456,33 +448,36 @@ __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& 
   const LinePlan& pl = c_plan[OP][0];
   const FilterCoef& fc = c_fc2;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const OutRange R(a, pl.n);
   const int node0 = pl.first_node + plan_chunk_row(pl, w);
   const int me = w + 1;
+  const int row = min(lane, LINES - 1);                    // lanes past LINES recompute the last line, never staged
+  const bool owner = lane < LINES;
   // 16-byte loads: node0 - H + 6 is even (build_line_plan, align_even)
-  const unsigned wpa = smem_u32(c.tin + lane * c.sp + 6 + (node0 - H));
-  double* orow = c.tout + (lane & 15) * c.sp + 6 + node0;
-  const double* sSl = &c.sS[0][lane];
-  const double* sPl = &c.sP[0][lane];
-  unsigned phase = 0;
-  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x) {
-    const BundlePos bp = locate(bnd, a);
-    mbar_wait(c.full, phase);
-    phase ^= 1;
+  const int woff = row * c.sp + 6 + (node0 - H);
+  int it = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+    const int p = it & 1;
+    const unsigned ph = (unsigned)(it >> 1) & 1u;
+    double* tile = c.tile[p];
+    double* sSl = c.sS[p] + row;
+    double* sPl = c.sP[p] + row;
+    mbar_wait(&c.full[p], ph);
     double wv[WN];
+    {
+      const unsigned wpa = smem_u32(tile + woff);
 #pragma unroll
-    for (int s = 0; s < WN / 2; ++s) { const double2 v = lds_v2f64(wpa + (unsigned)s * 16u); wv[2 * s] = v.x; wv[2 * s + 1] = v.y; }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(c.empty);
+      for (int s = 0; s < WN / 2; ++s) { const double2 v = lds_v2f64(wpa + (unsigned)s * 16u); wv[2 * s] = v.x; wv[2 * s + 1] = v.y; }
+    }
     double e[L];
     {
       double yh, yt;
       chunk_forward<OP>(pl.reg, fc, wv, e, yh, yt);
-      c.sS[me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt);
-      c.sP[me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
+      const double vs = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt), vp = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
+      if (owner) { sSl[(me + ASTR_WPAD) * LINES] = vs; sPl[(me + ASTR_WPAD) * LINES] = vp; }
     }
-    cta_sync(1, c.nthreads);
-    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * 32]; }, [&](int idx) { return sPl[idx * 32]; }, me);
+    cta_sync(1, c.ncompute);            // every compute warp holds its window; S / S' are published
+    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * LINES]; }, [&](int idx) { return sPl[idx * LINES]; }, me);
+#ifndef ASTR_SKELETON
     {
       double x = so.h_next;
 #pragma unroll
@@ -491,52 +486,36 @@ __device__ __forceinline__ void regular_loop_i(const Sweep2Args& a, const ICtx& 
         e[s] = x;
       }
     }
-    // two rounds of 16 lines: registers -> output tile -> global
-#pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
-      if ((lane >> 4) == r) stage_chunk<OP>(orow, e);
-      copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
-    }
+#endif
+    if (owner) stage_chunk<OP>(tile + row * c.sp + 6 + node0, e);
+    signal_staged(&c.staged[p]);
   }
-  if (lane == 0) bulk_wait_all();
 }
 
-template <int OP>
+template <int OP, int LINES, int HSL>
 __device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& c) {
   constexpr int H = OpT<OP>::H, HB = OpT<OP>::HB;
-  constexpr int HWN = ASTR_HS + HB + H;
+  constexpr int HWN = (HSL + HB + H > OpT<OP>::CR) ? HSL + HB + H : OpT<OP>::CR;
   const LinePlan& pl = c_plan[OP][0];
   const FilterCoef& fc = c_fc2;
-  const Layout& Lay = a.L;
   const int lane = threadIdx.x & 31;
   const int n = pl.n, E = pl.E;
-  const OutRange R(a, n);
-  const unsigned line_bytes = (unsigned)(((n + 13) & ~1) * 8);   // nodes -6..n+5 (+1 when n is odd)
   const bool p0 = (pl.ntype == 1 || pl.ntype == 4), pm = (pl.ntype == 2 || pl.ntype == 4);
-  const int hwlim = max(14, pl.sh + HB + H);
+  const int hwlim = max(OpT<OP>::CR, pl.sh + HB + H);
   const int hnode0 = pl.first_node - HB;
   const int tnode0 = pl.first_node + pl.nrows - pl.st;
-  const double* lrow = c.tin + lane * c.sp + 6;            // lrow[node] = f(node) of this thread's line
-  double* orow = c.tout + (lane & 15) * c.sp + 6;          // orow[node]
-  const double* sSl = &c.sS[0][lane];
-  const double* sPl = &c.sP[0][lane];
-
-  // producer: one bulk copy per line of the bundle
-  auto fetch = [&](int bnd) {
-    const BundlePos p = locate(bnd, a);
-    const int j0 = p.bx * 32;
-    const int nvalid = min(32, Lay.jm - j0 + 1);
-    if (lane == 0) mbar_expect_tx(c.full, line_bytes * (unsigned)nvalid);
-    __syncwarp();
-    if (lane < nvalid) bulk_load(c.tin + lane * c.sp, a.in[p.bz] + Lay.idx(-6, j0 + lane, p.by), line_bytes, c.full);
-  };
-  if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x);
-
-  unsigned phase = 0;
-  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x) {
-    const BundlePos bp = locate(bnd, a);
-    mbar_wait(c.full, phase);
-    double dh[ASTR_HS], dt[ASTR_TS];
+  const int row = min(lane, LINES - 1);
+  const bool owner = lane < LINES;
+  int it = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+    const int p = it & 1;
+    const unsigned ph = (unsigned)(it >> 1) & 1u;
+    double* tile = c.tile[p];
+    double* sSl = c.sS[p] + row;
+    double* sPl = c.sP[p] + row;
+    mbar_wait(&c.full[p], ph);
+    const double* lrow = tile + row * c.sp + 6;            // lrow[node] = f(node) of this thread's line
+    double dh[HSL], dt[ASTR_TS];
     {
       double hw[HWN], tw[16];
       load_head_window(hw, hwlim, hnode0, [&](int k) { return lrow[hnode0 + k]; });
@@ -545,79 +524,117 @@ __device__ __forceinline__ void special_loop_i(const Sweep2Args& a, const ICtx& 
       head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
       tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(c.empty);
-    if (bnd + (int)gridDim.x < c.nbundles) {        // producer: refill as soon as every warp has its rows
-      if (lane == 0) mbar_wait(c.empty, phase);
-      __syncwarp();
-      fetch(bnd + gridDim.x);
-    }
-    phase ^= 1;
-    double (&he)[ASTR_HS] = dh;                    // in place: the right-hand sides become the eliminated rows
+    double (&he)[HSL] = dh;                        // in place: the right-hand sides become the eliminated rows
     double (&te)[ASTR_TS] = dt;
     {
       double yh, yt;
       spec_forward(pl.head, dh, he, yh, yt);
-      c.sS[ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gamma, yh, yt);
-      c.sP[ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
+      const double hs = fma_(pl.el[ASTR_WPAD].gamma, yh, yt), hp = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
       spec_forward(pl.tail, dt, te, yh, yt);
-      c.sS[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
-      c.sP[E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+      const double ts = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt), tp = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+      if (owner) {
+        sSl[ASTR_WPAD * LINES] = hs; sPl[ASTR_WPAD * LINES] = hp;
+        sSl[(E - 1 + ASTR_WPAD) * LINES] = ts; sPl[(E - 1 + ASTR_WPAD) * LINES] = tp;
+      }
     }
-    cta_sync(1, c.nthreads);
-    auto GS = [&](int idx) { return sSl[idx * 32]; };
-    auto GP = [&](int idx) { return sPl[idx * 32]; };
+    cta_sync(1, c.ncompute);
+    auto GS = [&](int idx) { return sSl[idx * LINES]; };
+    auto GP = [&](int idx) { return sPl[idx * LINES]; };
     {
       const ScanOut s0 = reduced_scan(pl, GS, GP, 0);
       spec_back(pl.head, he, s0.t_prev, s0.h_next, [&](int s, double x) { he[s] = x; });
       const ScanOut s1 = reduced_scan(pl, GS, GP, E - 1);
       spec_back(pl.tail, te, s1.t_prev, s1.h_next, [&](int s, double x) { te[s] = x; });
     }
-#pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
-      if ((lane >> 4) == r) {
+    if (owner) {
+      double* orow = tile + row * c.sp + 6;                // orow[node]
 #pragma unroll
-        for (int g = 0; g < ASTR_HS / 8; ++g)
-          if (g * 8 < pl.sh) {
+      for (int g = 0; g < HSL / 8; ++g)
+        if (g * 8 < pl.sh) {
 #pragma unroll
-            for (int s = g * 8; s < g * 8 + 8; ++s) if (s < pl.sh) orow[pl.first_node + s] = he[s];
-          }
+          for (int s = g * 8; s < g * 8 + 8; ++s) if (s < pl.sh) orow[pl.first_node + s] = he[s];
+        }
 #pragma unroll
-        for (int s = 0; s < ASTR_TS; ++s) if (s < pl.st) orow[tnode0 + s] = te[s];
-      }
-      copy_out_round(a, c, R, a.out[bp.bz], bp.bx * 32, bp.by, r);
+      for (int s = 0; s < ASTR_TS; ++s) if (s < pl.st) orow[tnode0 + s] = te[s];
     }
+    signal_staged(&c.staged[p]);
   }
-  if (lane == 0) bulk_wait_all();
 }
 
-template <int OP>
-__global__ void __launch_bounds__(512, 1) sweep2i_kernel(const __grid_constant__ Sweep2Args a) {
+// The producer warp: lane l moves line l of a bundle.
+template <int LINES>
+__device__ __forceinline__ void producer_loop_i(const Sweep2Args& a, const ICtx& c, int n) {
+  const Layout& Lay = a.L;
+  const int lane = threadIdx.x & 31;
+  const OutRange R(a, n);
+  const unsigned line_bytes = (unsigned)(((n + 13) & ~1) * 8);   // nodes -6..n+5 (+1 when n is odd)
+  // written nodes: one bulk store covers the node pairs that are written unmodified, [nf0, nf1); the (at most
+  // a few) nodes of [w_lo, w_hi] outside go out as single stores
+  const int lo = max(R.w_lo, R.storez ? R.o_lo : R.w_lo), hi = min(R.w_hi, R.storez ? R.o_hi : R.w_hi);
+  const int nf0 = (lo + 1) & ~1;
+  const int nf1 = max((hi + 1) & ~1, nf0);
+  const int e0 = min(nf0, R.w_hi + 1), e1 = max(nf1, R.w_lo);
+  auto fetch = [&](int bnd, int p) {
+    const BundlePos q = locate(bnd, a);
+    const int j0 = q.bx * LINES;
+    const int nvalid = min(LINES, Lay.jm - j0 + 1);
+    if (lane == 0) mbar_expect_tx(&c.full[p], line_bytes * (unsigned)nvalid);
+    __syncwarp();
+    if (lane < nvalid) bulk_load(c.tile[p] + lane * c.sp, a.in[q.bz] + Lay.idx(-6, j0 + lane, q.by), line_bytes, &c.full[p]);
+  };
+  if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x, 0);
+  if ((int)(blockIdx.x + gridDim.x) < c.nbundles) fetch(blockIdx.x + gridDim.x, 1);
+  int it = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+    const int p = it & 1;
+    const unsigned ph = (unsigned)(it >> 1) & 1u;
+    const BundlePos bp = locate(bnd, a);
+    const int j0 = bp.bx * LINES;
+    const int nl = min(LINES, Lay.jm - j0 + 1);            // valid lines of the bundle
+    mbar_wait(&c.staged[p], ph);                           // every compute warp has staged its rows of tile p
+    if (lane < nl) {
+      const double* srow = c.tile[p] + lane * c.sp + 6;    // srow[node]
+      double* grow = a.out[bp.bz] + Lay.idx(0, j0 + lane, bp.by);   // grow[node]
+      if (nf1 > nf0) bulk_store(grow + nf0, srow + nf0, (unsigned)(nf1 - nf0) * 8u);
+      for (int node = R.w_lo; node < e0; ++node) grow[node] = R.value(node, srow[node]);
+      for (int node = e1; node <= R.w_hi; ++node) grow[node] = R.value(node, srow[node]);
+    }
+    bulk_commit();
+    bulk_wait_read();                                      // the engine has read the tile (the data may still be on its way)
+    __syncwarp();
+    if (bnd + 2 * (int)gridDim.x < c.nbundles) fetch(bnd + 2 * gridDim.x, p);
+  }
+  bulk_wait_all();
+}
+
+template <int OP, int LINES>
+__global__ void __launch_bounds__(544, 1) sweep2i_kernel(const __grid_constant__ Sweep2Args a) {
   extern __shared__ __align__(128) double smem[];
-  __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ __align__(8) unsigned long long mbar[4];
   const LinePlan& pl = c_plan[OP][0];
   ICtx c;
   c.sp = a.sp;
-  c.tin = smem;
-  c.tout = smem + 32 * c.sp;
-  c.sS = reinterpret_cast<double (*)[32]>(c.tout + 16 * c.sp);
-  c.sP = c.sS + ESZ;
-  c.full = &mbar[0]; c.empty = &mbar[1];
+  c.tile[0] = smem;
+  c.tile[1] = smem + LINES * c.sp;
+  double* sbase = smem + 2 * LINES * c.sp;
+  c.sS[0] = sbase; c.sP[0] = sbase + ESZ * LINES; c.sS[1] = sbase + 2 * ESZ * LINES; c.sP[1] = sbase + 3 * ESZ * LINES;
+  c.full = &mbar[0]; c.staged = &mbar[2];
   const int NW = pl.NW;
-  c.nthreads = (NW + 1) * 32;
+  c.ncompute = (NW + 1) * 32;
   c.nbundles = (int)(a.dxy.d * (unsigned)a.nf);
-  const OutRange R(a, pl.n);
-  c.pl0 = R.w_lo & ~1;
-  c.npairs = (int)a.dpair.d;
-  for (int i = threadIdx.x; i < 2 * ESZ * 32; i += blockDim.x) (&c.sS[0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < 4 * ESZ * LINES; i += blockDim.x) sbase[i] = 0.0;
   if (threadIdx.x == 0) {
-    mbar_init(c.full, 1);
-    mbar_init(c.empty, NW + 1);
+    mbar_init(&c.full[0], 1); mbar_init(&c.full[1], 1);
+    mbar_init(&c.staged[0], NW + 1); mbar_init(&c.staged[1], NW + 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if ((int)(threadIdx.x >> 5) < NW) regular_loop_i<OP>(a, c);
-  else special_loop_i<OP>(a, c);
+  const int w = threadIdx.x >> 5;
+  if (w < NW) regular_loop_i<OP, LINES>(a, c);
+  else if (w == NW) {
+    if (pl.sh <= 8) special_loop_i<OP, LINES, 8>(a, c);
+    else special_loop_i<OP, LINES, ASTR_HS>(a, c);
+  } else producer_loop_i<LINES>(a, c, pl.n);
 }
 
 int g_sms = 0;
@@ -697,35 +714,43 @@ int launch2(Sweep2Args& a, const PoolMap& pm, int NW, cudaStream_t st) {
   return 0;
 }
 
-template <int OP>
-int launch2i(Sweep2Args& a, const LinePlan& plan, cudaStream_t st) {
-  auto kern = sweep2i_kernel<OP>;
-  const int NW = plan.NW, n = plan.n;
-  // the chunk windows must start on a 16-byte boundary of the shared-memory line (build_line_plan, align_even)
-  if (((plan.first_node + plan.sh - OpT<OP>::H + 6) & 1) != 0) return -1;
-  const int threads = (NW + 1) * 32;
-  int sp = n + 12;
-  while ((sp & 15) != 2) ++sp;
-  a.sp = sp;
-  const size_t smem = ((size_t)48 * sp + 2 * ESZ * 32) * sizeof(double);
-  if (smem > 227 * 1024) return -1;
+template <int OP, int LINES>
+int launch2i_lines(Sweep2Args& a, const LinePlan& plan, size_t smem, cudaStream_t st) {
+  auto kern = sweep2i_kernel<OP, LINES>;
+  const int threads = (plan.NW + 2) * 32;       // regular chunks + head/tail warp + producer warp
   static LaunchCache lc;
   const int rc = prepare(kern, lc, threads, smem);
   if (rc) return rc;
   const Layout& L = a.L;
-  const long long nbx = (L.jm + 32) / 32;
+  const long long nbx = (L.jm + LINES) / LINES;
   const long long nby = L.km + 1;
   const long long nbundles = nbx * nby * a.nf;
   a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
-  const int w_lo = (a.epi == EPI_STOREZ) ? 0 : a.o_lo, w_hi = (a.epi == EPI_STOREZ) ? n : a.o_hi;
-  const int pl0 = w_lo & ~1;
-  a.dpair = make_fastdiv((unsigned)((w_hi - pl0) / 2 + 1));
+  a.dpair = make_fastdiv(1);
   long long grid = (long long)g_sms * lc.occ;
   if (grid > nbundles) grid = nbundles;
   kern<<<(unsigned)grid, threads, smem, st>>>(a);
   astr_count_launch();
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int OP>
+int launch2i(Sweep2Args& a, const LinePlan& plan, cudaStream_t st) {
+  const int n = plan.n;
+  // the chunk windows must start on a 16-byte boundary of the shared-memory line (build_line_plan, align_even)
+  if (((plan.first_node + plan.sh - OpT<OP>::H + 6) & 1) != 0) return -1;
+  // row pitch of the line tiles: sp / 2 odd, so that the lane-per-line 16-byte accesses of a quarter warp hit
+  // 8 distinct 16-byte bank groups
+  int sp = n + 12 + (n & 1);
+  while ((sp & 15) != 2) sp += 2;
+  a.sp = sp;
+  const size_t cap = 227 * 1024 - 64;
+  const size_t s32 = ((size_t)2 * 32 * sp + 4 * ESZ * 32) * sizeof(double);
+  const size_t s24 = ((size_t)2 * 24 * sp + 4 * ESZ * 24) * sizeof(double);
+  if (s32 <= cap) return launch2i_lines<OP, 32>(a, plan, s32, st);
+  if (s24 <= cap) return launch2i_lines<OP, 24>(a, plan, s24, st);
+  return -1;
 }
 
 }  // namespace

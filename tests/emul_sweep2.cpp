@@ -29,7 +29,7 @@ int run_line(const LinePlan& pl, const FilterCoef& fc, const double* f5 /* f5[k]
   // ---- phase A/B: every element on its own
   {
     double hw[HWN];
-    for (int k = 0; k < HWN; ++k) hw[k] = (k < std::max(14, pl.sh + HB + H)) ? F(pl.first_node - HB + k) : 0.0;   // 14: reach of the closure rows
+    for (int k = 0; k < HWN; ++k) hw[k] = (k < std::max(OpT<OP>::CR, pl.sh + HB + H)) ? F(pl.first_node - HB + k) : 0.0;   // CR: reach of the closure rows
     double d[ASTR_HS] = {0}, yh, yt;
     head_rhs<OP, P0>(hw, fc, pl.nsf, pl.sh, d);
     spec_forward(pl.head, d, he, yh, yt);
