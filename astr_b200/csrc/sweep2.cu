@@ -187,9 +187,19 @@ __device__ __forceinline__ void tail_rhs_any(bool pm, const double (&tw)[16], co
 // =============================================================================================
 // j / k sweeps
 // =============================================================================================
-template <int DIR, int OP>
-__device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* tile, double (*sS)[ESZ][32],
-                                             double (*sP)[ESZ][32], unsigned long long* full, unsigned long long* empty) {
+// PEN pencils per bundle (lanes >= PEN idle), NT tiles.  NT = 2: the tile of bundle b+1 is requested while the
+// warps still read bundle b, so the TMA stream never pauses; chosen when two tiles fit in shared memory.
+struct JKCtx {
+  double* tile[2];           // [node + 5][PEN]
+  double* sS[2];             // [parity][ESZ][PEN]
+  double* sP[2];
+  unsigned long long* full;  // [NT]
+  unsigned long long* empty; // [NT]
+  int nthreads, nbundles;
+};
+
+template <int DIR, int OP, int PEN, int NT>
+__device__ __forceinline__ void regular_loop(const Sweep2Args& a, const JKCtx& c) {
   constexpr int H = OpT<OP>::H;
   constexpr int L = ASTR_LMAX;
   constexpr int WN = L + 2 * H;
@@ -197,53 +207,53 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* 
   const FilterCoef& fc = c_fc2;
   const Layout& Lay = a.L;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = min(lane, PEN - 1);                  // lanes past PEN recompute the last pencil, never stored
   const int n = pl.n;
   const int node0 = pl.first_node + plan_chunk_row(pl, w);
   const OutRange R(a, n);
   // a chunk whose rows are all written unmodified needs no per-row range checks
   const bool plain = node0 >= a.o_lo && node0 + L - 1 <= a.o_hi;
   const int me = w + 1;
-  const int nthreads = (pl.NW + 1) * 32;
-  const int nbundles = (int)(a.dxy.d * (unsigned)a.nf);
   const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);   // bytes per line step
-
-  // tl[node * 32] = f(node) of this thread's pencil
-  const double* tl = tile + ASTR_HM * 32 + lane;
-  const unsigned wpa = smem_u32(tl + (node0 - H) * 32);
-  unsigned phase = 0;
-  int par = 0;
-  for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
+  // tile[(node + 5) * PEN + col] = f(node) of this thread's pencil
+  const int woff = (ASTR_HM + node0 - H) * PEN + col;
+  int it = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+    const int p = (NT == 2) ? (it & 1) : 0, par = it & 1;
+    const unsigned ph = (NT == 2) ? ((unsigned)(it >> 1) & 1u) : ((unsigned)it & 1u);
     const BundlePos bp = locate(bnd, a);
-    const int i0 = bp.bx * 32;
+    const int i0 = bp.bx * PEN;
     // lanes past the last pencil of a ragged bundle compute on halo / zero-filled columns; their stores are
     // predicated off
-    const int valid = (i0 + lane) <= Lay.im;
+    const int valid = (lane < PEN) && (i0 + lane) <= Lay.im;
     const int icol = valid ? i0 + lane : 0;
     double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
 
-    mbar_wait(full, phase);
-    phase ^= 1;
+    mbar_wait(&c.full[p], ph);
     // ---- tile -> registers: the chunk (+ stencil overlap) -------------------------------------
     double wv[WN];
+    {
+      const unsigned wpa = smem_u32(c.tile[p] + woff);
 #pragma unroll
-    for (int s = 0; s < WN; ++s) wv[s] = lds_f64(wpa + (unsigned)s * 256u);
+      for (int s = 0; s < WN; ++s) wv[s] = lds_f64(wpa + (unsigned)(s * PEN * 8));
+    }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty);      // this warp is done with the tile
+    if (lane == 0) mbar_arrive(&c.empty[p]);      // this warp is done with the tile
 
     // ---- eliminate, publish S / S' ------------------------------------------------------------
+    double* sSl = c.sS[par] + col;
+    double* sPl = c.sP[par] + col;
     double e[L];
     {
       double yh, yt;
       chunk_forward<OP>(pl.reg, fc, wv, e, yh, yt);
-      sS[par][me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt);
-      sP[par][me + ASTR_WPAD][lane] = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
+      const double vs = fma_(pl.el[me + ASTR_WPAD].gamma, yh, yt), vp = fma_(pl.el[me + ASTR_WPAD].gammap, yt, yh);
+      if (lane < PEN) { sSl[(me + ASTR_WPAD) * PEN] = vs; sPl[(me + ASTR_WPAD) * PEN] = vp; }
     }
-    cta_sync(1, nthreads);
+    cta_sync(1, c.nthreads);
 
     // ---- boundary values of this chunk, solution, write-out -----------------------------------
-    const double* sSl = &sS[par][0][lane];
-    const double* sPl = &sP[par][0][lane];
-    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * 32]; }, [&](int idx) { return sPl[idx * 32]; }, me);
+    const ScanOut so = reduced_scan(pl, [&](int idx) { return sSl[idx * PEN]; }, [&](int idx) { return sPl[idx * PEN]; }, me);
     double* po = gout + (long long)node0 * (gl8 / 8);
     if (plain) {
       chunk_back(pl.reg, e, so.t_prev, so.h_next, [&](int s, double x) { st_if(row_ptr(po, gl8, s), x, valid); });
@@ -259,100 +269,102 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const double* 
 
 // HSL: slots of the head block that are processed (8 when the block has at most 8 rows -- the common case, e.g.
 // 512-node lines -- else ASTR_HS): the short variant is straight-line code with everything in registers
-template <int DIR, int OP, int HSL>
-__device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensorMap* tm, const double* tile,
-                                             double (*sS)[ESZ][32], double (*sP)[ESZ][32], unsigned long long* full,
-                                             unsigned long long* empty) {
+template <int DIR, int OP, int PEN, int NT, int HSL>
+__device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensorMap* tm, const JKCtx& c) {
   constexpr int H = OpT<OP>::H, HB = OpT<OP>::HB;
   constexpr int HWN = (HSL + HB + H > OpT<OP>::CR) ? HSL + HB + H : OpT<OP>::CR;
   const LinePlan& pl = c_plan[OP][DIR];
   const FilterCoef& fc = c_fc2;
   const Layout& Lay = a.L;
   const int lane = threadIdx.x & 31;
+  const int col = min(lane, PEN - 1);
   const int n = pl.n, E = pl.E;
   const bool p0 = (pl.ntype == 1 || pl.ntype == 4), pm = (pl.ntype == 2 || pl.ntype == 4);
   const OutRange R(a, n);
-  const int nthreads = (pl.NW + 1) * 32;
-  const int nbundles = (int)(a.dxy.d * (unsigned)a.nf);
   const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);
-  const unsigned tile_bytes = (unsigned)(a.rb * a.nbox) * 256u;
+  const unsigned tile_bytes = (unsigned)(a.rb * a.nbox) * (unsigned)(PEN * 8);
   const int hwlim = max(OpT<OP>::CR, pl.sh + HB + H);  // CR: reach of the closure rows
   const int hnode0 = pl.first_node - HB;              // node of window slot 0
   const int tnode0 = pl.first_node + pl.nrows - pl.st; // node of the first tail row
 
-  // elected thread: fetch one bundle into the tile.  Tensor coordinates (x, y, z, slot) =
+  // elected thread: fetch one bundle into tile p.  Tensor coordinates (x, y, z, slot) =
   // (i + 16, j + 5, k + 5, field); out-of-range columns of a ragged bundle are zero-filled.
-  auto fetch = [&](int bnd) {
-    const BundlePos p = locate(bnd, a);
-    mbar_expect_tx(full, tile_bytes);
+  auto fetch = [&](int bnd, int p) {
+    const BundlePos q = locate(bnd, a);
+    mbar_expect_tx(&c.full[p], tile_bytes);
     // the boxes of a tile are requested in an order rotated by the CTA index: neighbouring CTAs (neighbouring
     // pencils) otherwise walk the same planes / rows in lockstep and crowd the same DRAM pages
     for (int b0 = 0; b0 < a.nbox; ++b0) {
       const int b = (b0 + (int)blockIdx.x) % a.nbox;
-      void* dst = const_cast<double*>(tile) + (size_t)b * a.rb * 32;
-      if (DIR == 1) tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, b * a.rb, p.by + ASTR_HM, a.slot[p.bz], full);
-      else tma_load_4d(dst, tm, p.bx * 32 + ASTR_IOFF, p.by + ASTR_HM, b * a.rb, a.slot[p.bz], full);
+      void* dst = c.tile[p] + (size_t)b * a.rb * PEN;
+      if (DIR == 1) tma_load_4d(dst, tm, q.bx * PEN + ASTR_IOFF, b * a.rb, q.by + ASTR_HM, a.slot[q.bz], &c.full[p]);
+      else tma_load_4d(dst, tm, q.bx * PEN + ASTR_IOFF, q.by + ASTR_HM, b * a.rb, a.slot[q.bz], &c.full[p]);
     }
   };
-  if (lane == 0 && (int)blockIdx.x < nbundles) fetch(blockIdx.x);
+  if (lane == 0) {
+    if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x, 0);
+    if (NT == 2 && (int)(blockIdx.x + gridDim.x) < c.nbundles) fetch(blockIdx.x + gridDim.x, 1);
+  }
   __syncwarp();
 
-  const double* tl = tile + ASTR_HM * 32 + lane;
-  const double* hp = tl + hnode0 * 32;
-  const double* tp = tl + (n - 10) * 32;
-  unsigned phase = 0;
-  int par = 0;
-  for (int bnd = blockIdx.x; bnd < nbundles; bnd += gridDim.x, par ^= 1) {
+  int it = 0;
+  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+    const int p = (NT == 2) ? (it & 1) : 0, par = it & 1;
+    const unsigned ph = (NT == 2) ? ((unsigned)(it >> 1) & 1u) : ((unsigned)it & 1u);
     const BundlePos bp = locate(bnd, a);
-    const int i0 = bp.bx * 32;
-    const int valid = (i0 + lane) <= Lay.im;
+    const int i0 = bp.bx * PEN;
+    const int valid = (lane < PEN) && (i0 + lane) <= Lay.im;
     const int icol = valid ? i0 + lane : 0;
     double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
+    const double* tl = c.tile[p] + ASTR_HM * PEN + col;   // tl[node * PEN] = f(node) of this thread's pencil
+    const double* hp = tl + hnode0 * PEN;
+    const double* tp = tl + (n - 10) * PEN;
 
-    mbar_wait(full, phase);
+    mbar_wait(&c.full[p], ph);
     // ---- tile -> right-hand sides of the two blocks (the windows die before the tile is released) ----
     double dh[HSL], dt[ASTR_TS];
     {
       double hw[HWN], tw[16];
-      load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * 32]; });
+      load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * PEN]; });
 #pragma unroll
-      for (int k = 0; k < 16; ++k) tw[k] = tp[k * 32];
+      for (int k = 0; k < 16; ++k) tw[k] = tp[k * PEN];
       head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
       tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
     __syncwarp();
-    // producer: once every warp has copied its rows into registers the tile is refilled, so that the fetch of
-    // the next bundle runs under the elimination, the scan and the write-out of this one
+    // producer: once every warp has copied its rows into registers the tile is refilled with the bundle NT
+    // iterations ahead, so that the fetch runs under the elimination, the scan and the write-out
     if (lane == 0) {
-      mbar_arrive(empty);
-      if (bnd + (int)gridDim.x < nbundles) {
-        mbar_wait(empty, phase);
-        fetch(bnd + gridDim.x);
+      mbar_arrive(&c.empty[p]);
+      if (bnd + NT * (int)gridDim.x < c.nbundles) {
+        mbar_wait(&c.empty[p], ph);
+        fetch(bnd + NT * gridDim.x, p);
       }
     }
     __syncwarp();
-    phase ^= 1;
 
     // ---- eliminate, publish S / S' -------------------------------------------------------------
     // (in place: the right-hand sides become the eliminated rows)
     double (&he)[HSL] = dh;
     double (&te)[ASTR_TS] = dt;
+    double* sSl = c.sS[par] + col;
+    double* sPl = c.sP[par] + col;
     {
       double yh, yt;
       spec_forward(pl.head, dh, he, yh, yt);
-      sS[par][ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gamma, yh, yt);
-      sP[par][ASTR_WPAD][lane] = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
+      const double hs = fma_(pl.el[ASTR_WPAD].gamma, yh, yt), hq = fma_(pl.el[ASTR_WPAD].gammap, yt, yh);
       spec_forward(pl.tail, dt, te, yh, yt);
-      sS[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt);
-      sP[par][E - 1 + ASTR_WPAD][lane] = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+      const double ts = fma_(pl.el[E - 1 + ASTR_WPAD].gamma, yh, yt), tq = fma_(pl.el[E - 1 + ASTR_WPAD].gammap, yt, yh);
+      if (lane < PEN) {
+        sSl[ASTR_WPAD * PEN] = hs; sPl[ASTR_WPAD * PEN] = hq;
+        sSl[(E - 1 + ASTR_WPAD) * PEN] = ts; sPl[(E - 1 + ASTR_WPAD) * PEN] = tq;
+      }
     }
-    cta_sync(1, nthreads);
+    cta_sync(1, c.nthreads);
 
     // ---- solution of the two blocks, write-out --------------------------------------------------
-    const double* sSl = &sS[par][0][lane];
-    const double* sPl = &sP[par][0][lane];
-    auto GS = [&](int idx) { return sSl[idx * 32]; };
-    auto GP = [&](int idx) { return sPl[idx * 32]; };
+    auto GS = [&](int idx) { return sSl[idx * PEN]; };
+    auto GP = [&](int idx) { return sPl[idx * PEN]; };
     {
       const ScanOut so = reduced_scan(pl, GS, GP, 0);
       double* po = gout + (long long)pl.first_node * (gl8 / 8);
@@ -374,25 +386,32 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
   }
 }
 
-template <int DIR, int OP>
+template <int DIR, int OP, int PEN, int NT>
 __global__ void __launch_bounds__(512, 1)
 sweep2_kernel(const __grid_constant__ Sweep2Args a, const __grid_constant__ CUtensorMap tm) {
-  extern __shared__ __align__(128) double tile[];
-  __shared__ double sS[2][ESZ][32];
-  __shared__ double sP[2][ESZ][32];
-  __shared__ __align__(8) unsigned long long mbar[2];
-  const int NW = c_plan[OP][DIR].NW;
-  for (int i = threadIdx.x; i < 2 * ESZ * 32; i += blockDim.x) { (&sS[0][0][0])[i] = 0.0; (&sP[0][0][0])[i] = 0.0; }
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) unsigned long long mbar[4];
+  const LinePlan& pl = c_plan[OP][DIR];
+  const int NW = pl.NW;
+  JKCtx c;
+  const int tile_doubles = a.rb * a.nbox * PEN;
+  c.tile[0] = smem;
+  c.tile[1] = smem + (NT == 2 ? tile_doubles : 0);
+  double* sbase = smem + NT * tile_doubles;
+  c.sS[0] = sbase; c.sP[0] = sbase + ESZ * PEN; c.sS[1] = sbase + 2 * ESZ * PEN; c.sP[1] = sbase + 3 * ESZ * PEN;
+  c.full = &mbar[0]; c.empty = &mbar[2];
+  c.nthreads = (NW + 1) * 32;
+  c.nbundles = (int)(a.dxy.d * (unsigned)a.nf);
+  for (int i = threadIdx.x; i < 4 * ESZ * PEN; i += blockDim.x) sbase[i] = 0.0;
   if (threadIdx.x == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], NW + 1);
+    for (int t = 0; t < NT; ++t) { mbar_init(&c.full[t], 1); mbar_init(&c.empty[t], NW + 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int w = threadIdx.x >> 5;
-  if (w < NW) regular_loop<DIR, OP>(a, tile, sS, sP, &mbar[0], &mbar[1]);
-  else if (c_plan[OP][DIR].sh <= 8) special_loop<DIR, OP, 8>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
-  else special_loop<DIR, OP, ASTR_HS>(a, &tm, tile, sS, sP, &mbar[0], &mbar[1]);
+  if (w < NW) regular_loop<DIR, OP, PEN, NT>(a, c);
+  else if (pl.sh <= 8) special_loop<DIR, OP, PEN, NT, 8>(a, &tm, c);
+  else special_loop<DIR, OP, PEN, NT, ASTR_HS>(a, &tm, c);
 }
 
 // =============================================================================================
@@ -648,26 +667,29 @@ EncodeTiledFn g_encode = nullptr;
 struct PoolMap {
   const double* base = nullptr;
   int nslots = 0;
-  CUtensorMap tm[3];        // per sweep direction (box shape differs); [0] unused
+  CUtensorMap tm[3][2];     // [sweep direction][0: 32-pencil boxes, 1: 24-pencil boxes]; direction 0 unused
   int rb[3] = {0, 0, 0}, nbox[3] = {0, 0, 0};
 };
 constexpr int NPOOLS = 3;
 PoolMap g_maps[NPOOLS];
 
-int make_map(PoolMap& pm, const Layout& L, int dir) {
+int make_map(PoolMap& pm, const Layout& L, int dir, int pv) {
+  const int pen = pv ? 24 : 32;
   const int rows = (dir == 1 ? L.njt : L.nkt);
   const int nbox = (rows + 255) / 256;
-  const int rb = (rows + nbox - 1) / nbox;
+  const int rb = (((rows + nbox - 1) / nbox) + 1) & ~1;     // even: 192-byte rows x rb stays a multiple of 128 bytes (TMA destination alignment)
   pm.rb[dir] = rb; pm.nbox[dir] = nbox;
   const cuuint64_t gdim[4] = {(cuuint64_t)L.pitch, (cuuint64_t)L.njt, (cuuint64_t)L.nkt, (cuuint64_t)pm.nslots};
   const cuuint64_t gstr[3] = {(cuuint64_t)L.sj * 8, (cuuint64_t)L.sk * 8, (cuuint64_t)L.fstride * 8};
-  const cuuint32_t box[4] = {32, (cuuint32_t)(dir == 1 ? rb : 1), (cuuint32_t)(dir == 2 ? rb : 1), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)pen, (cuuint32_t)(dir == 1 ? rb : 1), (cuuint32_t)(dir == 2 ? rb : 1), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  // 128-byte L2 promotion: the 256-byte box rows start at a 128-byte (not 256-byte) boundary, so the 256-byte
-  // promotion made every row fetch two extra half lines (ncu: 17 % more L2 read sectors than TMA bytes)
-  const CUresult r = g_encode(&pm.tm[dir], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(pm.base), gdim, gstr,
+  // L2 promotion no wider than the alignment of the box rows (256-byte rows start on a 128-byte boundary, 192-byte
+  // rows on a 64-byte boundary): the 256-byte promotion made every row fetch two extra half lines (ncu: 17 % more
+  // L2 read sectors than TMA bytes)
+  const CUresult r = g_encode(&pm.tm[dir][pv], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(pm.base), gdim, gstr,
                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              pv ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[96];
     snprintf(buf, sizeof buf, "sweep2: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -691,27 +713,40 @@ int prepare(K kern, LaunchCache& lc, int threads, size_t smem) {
   return 0;
 }
 
-template <int DIR, int OP>
-int launch2(Sweep2Args& a, const PoolMap& pm, int NW, cudaStream_t st) {
-  auto kern = sweep2_kernel<DIR, OP>;
+template <int DIR, int OP, int PEN, int NT>
+int launch2_cfg(Sweep2Args& a, const PoolMap& pm, int NW, size_t smem, cudaStream_t st) {
+  auto kern = sweep2_kernel<DIR, OP, PEN, NT>;
   const int threads = (NW + 1) * 32;
-  a.rb = pm.rb[DIR]; a.nbox = pm.nbox[DIR];
-  const size_t smem = (size_t)a.rb * a.nbox * 256;
   static LaunchCache lc;
   const int rc = prepare(kern, lc, threads, smem);
   if (rc) return rc;
   const Layout& L = a.L;
-  const long long nbx = (L.im + 32) / 32;
+  const long long nbx = (L.im + PEN) / PEN;
   const long long nby = (DIR == 2 ? L.jm : L.km) + 1;
   const long long nbundles = nbx * nby * a.nf;
   a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
   a.dpair = make_fastdiv(1);
   long long grid = (long long)g_sms * lc.occ;
   if (grid > nbundles) grid = nbundles;
-  kern<<<(unsigned)grid, threads, smem, st>>>(a, pm.tm[DIR]);
+  kern<<<(unsigned)grid, threads, smem, st>>>(a, pm.tm[DIR][PEN == 24 ? 1 : 0]);
   astr_count_launch();
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// two 32-pencil tiles when they fit (lines up to ~400 nodes), else one.  24-pencil double buffering, which is what
+// the i kernel does with whole lines, measured SLOWER here (2.44 / 2.53 ms against 2.19 / 2.32 ms for the five-field
+// derivative sweeps at 512^3): the 192-byte row segments cost more DRAM efficiency than the overlap returns
+template <int DIR, int OP>
+int launch2(Sweep2Args& a, const PoolMap& pm, int NW, cudaStream_t st) {
+  a.rb = pm.rb[DIR]; a.nbox = pm.nbox[DIR];
+  const size_t rows = (size_t)a.rb * a.nbox;
+  const size_t cap = 227 * 1024 - 64;
+  const size_t s232 = (2 * rows * 32 + 4 * ESZ * 32) * sizeof(double);
+  const size_t s132 = (rows * 32 + 4 * ESZ * 32) * sizeof(double);
+  if (s232 <= cap) return launch2_cfg<DIR, OP, 32, 2>(a, pm, NW, s232, st);
+  if (s132 <= cap) return launch2_cfg<DIR, OP, 32, 1>(a, pm, NW, s132, st);
+  return -1;
 }
 
 template <int OP, int LINES>
@@ -774,10 +809,11 @@ int astr_sweep2_register_pool(int which, const double* base, int nslots, const L
   PoolMap& pm = g_maps[which];
   pm.base = base; pm.nslots = nslots;
   if (!base) return 0;
-  for (int d = 1; d <= 2; ++d) {
-    const int rc = make_map(pm, L, d);
-    if (rc) return rc;
-  }
+  for (int d = 1; d <= 2; ++d)
+    for (int pv = 0; pv < 2; ++pv) {
+      const int rc = make_map(pm, L, d, pv);
+      if (rc) return rc;
+    }
   return 0;
 }
 
@@ -813,7 +849,6 @@ int astr_launch_sweep2(int dir, int optype, const LinePlan& plan, const SweepArg
     pm = hit;
   }
   if (!pm) return -1;
-  if ((size_t)pm->rb[dir] * pm->nbox[dir] * 256 > 190 * 1024) return -1;
 #define ASTR_L2(D)                                                             \
   switch (optype) {                                                            \
     case OP_DERIV: return launch2<D, OP_DERIV>(a, *pm, plan.NW, st);           \
