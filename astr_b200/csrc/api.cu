@@ -1274,16 +1274,35 @@ int astr_gpu_set_force(const double force[3]) {
   return 0;
 }
 
+static int reduce3(int what, int nout, double* out) {
+  const astr_cfg& c = g->cfg;
+  TRY(pw_reduce(g->L, g->pool, g->ycoord, g->th, what, c.rank[1] == 0, c.rank[1] == c.size[1] - 1, g->d_partial, g->d_out2,
+                g->st));
+  double h[3];
+  CUDA_OK(cudaMemcpyAsync(h, g->d_out2, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  for (int i = 0; i < nout; ++i) out[i] = h[i];
+  return p2p_check();
+}
+
 int astr_gpu_reduce_tgv(double out[3]) {
   NEED_CTX();
   if (g->cfg.ndims != 3) return astr_fail_msg("reduce_tgv covers ndims=3 only");
   if (!g->have_grad) return astr_fail_msg("reduce_tgv before gradcal");
-  TRY(pw_stats(g->L, g->pool, g->d_partial, g->d_out2, g->st));
-  double h[2];
-  CUDA_OK(cudaMemcpyAsync(h, g->d_out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, g->st));
-  CUDA_OK(cudaStreamSynchronize(g->st));
-  out[0] = h[0]; out[1] = h[1]; out[2] = 0.0;
-  return p2p_check();
+  return reduce3(0, 3, out);
+}
+
+int astr_gpu_reduce_cfl(double out[3]) {
+  NEED_CTX();
+  if (!g->have_metrics) return astr_fail_msg("reduce_cfl before set_metrics/gridgeom");
+  return reduce3(1, 3, out);
+}
+
+int astr_gpu_reduce_channel(double out[2]) {
+  NEED_CTX();
+  if (!g->ycoord) return astr_fail_msg("reduce_channel needs node coordinates: call astr_gpu_set_grid or astr_gpu_gridgeom");
+  if (!g->have_grad) return astr_fail_msg("reduce_channel before gradcal");
+  return reduce3(2, 2, out);
 }
 
 int astr_gpu_kernel_launches(long long* count) { *count = g_launches; return 0; }

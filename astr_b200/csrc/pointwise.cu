@@ -474,47 +474,104 @@ __global__ void k_add_force(const Layout L, double* __restrict__ pool, const dou
 }
 
 // ---------------------------------------------------------------------------------
-// kenergycal / enstophycal partial sums (src/statistic.F90:871-990): nodes 1..im,1..jm,1..km
-// one CTA per (j,k) row, fixed-order tree => deterministic
+// Per-step diagnostics of rkfirst / steploop as block-level partial results (the caller applies psum / pmax
+// and the reference's normalisation): one CTA per (j,k) row, fixed-order trees => deterministic.
+//   RED_TGV : kenergycal, enstophycal, diss_rate_cal (src/statistic.F90:938, :871, :994), nodes 1..im,1..jm,1..km
+//   RED_CFL : cflcal's deltai, deltaj, deltak (src/commcal.F90:27-74), nodes 0..im,0..jm,0..km, maxima
+//   RED_CHAN: massfluxchan (src/statistic.F90:1437-1476) and fbcxchan (:1303-1367); rows j = 1..jm, the rows next
+//             to a wall this block owns also carry the wall friction of j = 0 / j = jm
 // ---------------------------------------------------------------------------------
-__global__ void k_stats_rows(const Layout L, const double* __restrict__ pool, double* __restrict__ partial) {
-  const int j = 1 + blockIdx.x, k = 1 + blockIdx.y;
+enum { RED_TGV = 0, RED_CFL = 1, RED_CHAN = 2 };
+template <int KIND>
+__global__ void k_reduce_rows(const Layout L, const double* __restrict__ pool, const double* __restrict__ yc, const Thermo th,
+                              double* __restrict__ partial, const int j0, const int k0, const int wall_lo, const int wall_hi) {
+  const int j = j0 + blockIdx.x, k = k0 + blockIdx.y;
   const long long fs = L.fstride;
-  double ke = 0.0, en = 0.0;
-  for (int i = 1 + threadIdx.x; i <= L.im; i += PW_T) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int i = (KIND == RED_CFL ? 0 : 1) + threadIdx.x; i <= L.im; i += PW_T) {
     const long long x = L.idx(i, j, k);
-    Grad g;
-    load_grad(pool, fs, x, g);
-    const double r = pool[S_RHO * fs + x];
-    const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
-    ke += r * (u * u + v * v + w * w);
-    const double o1 = g.dv[2][1] - g.dv[1][2], o2 = g.dv[0][2] - g.dv[2][0], o3 = g.dv[1][0] - g.dv[0][1];
-    en += r * (o1 * o1 + o2 * o2 + o3 * o3);
+    if (KIND == RED_TGV) {
+      Grad g;
+      load_grad(pool, fs, x, g);
+      const double r = pool[S_RHO * fs + x];
+      const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+      a0 += r * (u * u + v * v + w * w);
+      const double o1 = g.dv[2][1] - g.dv[1][2], o2 = g.dv[0][2] - g.dv[2][0], o3 = g.dv[1][0] - g.dv[0][1];
+      a1 += r * (o1 * o1 + o2 * o2 + o3 * o3);
+      const double miu = th.miu(pool[S_TMP * fs + x]);
+      const double s11 = g.dv[0][0], s12 = 0.5 * (g.dv[0][1] + g.dv[1][0]), s13 = 0.5 * (g.dv[0][2] + g.dv[2][0]);
+      const double s22 = g.dv[1][1], s23 = 0.5 * (g.dv[1][2] + g.dv[2][1]), s33 = g.dv[2][2];
+      const double div = s11 + s22 + s33;
+      a2 += 2.0 * miu * (s11 * s11 + s22 * s22 + s33 * s33 + 2.0 * (s12 * s12 + s13 * s13 + s23 * s23) -
+                         (1.0 / 3.0) * (div * div));
+    } else if (KIND == RED_CFL) {
+      const double u = pool[(S_VEL + 0) * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+      const double css = th.sos(pool[S_TMP * fs + x]);
+      double bar[3], cs[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double d1 = pool[(S_DXI + 3 * d + 0) * fs + x], d2 = pool[(S_DXI + 3 * d + 1) * fs + x],
+                     d3 = pool[(S_DXI + 3 * d + 2) * fs + x];
+        bar[d] = d1 * u + d2 * v + d3 * w;
+        cs[d] = css * sqrt(d1 * d1 + d2 * d2 + d3 * d3);
+      }
+      a0 = fmax(fmax(a0, bar[0]), fmax(bar[0] - cs[0], bar[0] + cs[0]));
+      a1 = fmax(fmax(a1, bar[1]), fmax(bar[1] - cs[1], bar[1] + cs[1]));
+      a2 = fmax(fmax(a2, bar[2]), fmax(bar[2] - cs[2], bar[2] + cs[2]));
+    } else {
+      const long long xm = x - L.sj;
+      const double dy = yc[x] - yc[xm];
+      a0 += 0.5 * (pool[(S_Q + 1) * fs + x] + pool[(S_Q + 1) * fs + xm]) * dy;
+      if (wall_lo && j == 1) {
+        Grad g;
+        load_grad(pool, fs, xm, g);
+        a1 += th.miu(pool[S_TMP * fs + xm]) * g.dv[0][1];
+      }
+      if (wall_hi && j == L.jm) {
+        Grad g;
+        load_grad(pool, fs, x, g);
+        a1 -= th.miu(pool[S_TMP * fs + x]) * g.dv[0][1];
+      }
+    }
   }
-  __shared__ double s0[PW_T], s1[PW_T];
-  s0[threadIdx.x] = ke; s1[threadIdx.x] = en;
+  __shared__ double s0[PW_T], s1[PW_T], s2[PW_T];
+  s0[threadIdx.x] = a0; s1[threadIdx.x] = a1; s2[threadIdx.x] = a2;
   __syncthreads();
   for (int h = PW_T / 2; h > 0; h >>= 1) {
-    if (threadIdx.x < h) { s0[threadIdx.x] += s0[threadIdx.x + h]; s1[threadIdx.x] += s1[threadIdx.x + h]; }
+    if (threadIdx.x < h) {
+      if (KIND == RED_CFL) {
+        s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + h]);
+        s1[threadIdx.x] = fmax(s1[threadIdx.x], s1[threadIdx.x + h]);
+        s2[threadIdx.x] = fmax(s2[threadIdx.x], s2[threadIdx.x + h]);
+      } else {
+        s0[threadIdx.x] += s0[threadIdx.x + h]; s1[threadIdx.x] += s1[threadIdx.x + h]; s2[threadIdx.x] += s2[threadIdx.x + h];
+      }
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     const long long row = (long long)blockIdx.y * gridDim.x + blockIdx.x;
-    partial[2 * row] = s0[0];
-    partial[2 * row + 1] = s1[0];
+    partial[3 * row] = s0[0]; partial[3 * row + 1] = s1[0]; partial[3 * row + 2] = s2[0];
   }
 }
-__global__ void k_stats_final(const double* __restrict__ partial, const long long nrows, double* __restrict__ out2) {
-  __shared__ double s0[256], s1[256];
-  double a = 0.0, b = 0.0;
-  for (long long r = threadIdx.x; r < nrows; r += 256) { a += partial[2 * r]; b += partial[2 * r + 1]; }
-  s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+template <bool ISMAX>
+__global__ void k_reduce_final(const double* __restrict__ partial, const long long nrows, double* __restrict__ out3) {
+  __shared__ double s[3][256];
+  double a[3] = {0.0, 0.0, 0.0};
+  for (long long r = threadIdx.x; r < nrows; r += 256)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) a[m] = ISMAX ? fmax(a[m], partial[3 * r + m]) : a[m] + partial[3 * r + m];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) s[m][threadIdx.x] = a[m];
   __syncthreads();
   for (int h = 128; h > 0; h >>= 1) {
-    if (threadIdx.x < h) { s0[threadIdx.x] += s0[threadIdx.x + h]; s1[threadIdx.x] += s1[threadIdx.x + h]; }
+    if (threadIdx.x < h)
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+        s[m][threadIdx.x] = ISMAX ? fmax(s[m][threadIdx.x], s[m][threadIdx.x + h]) : s[m][threadIdx.x] + s[m][threadIdx.x + h];
     __syncthreads();
   }
-  if (threadIdx.x == 0) { out2[0] = s0[0]; out2[1] = s1[0]; }
+  if (threadIdx.x < 3) out3[threadIdx.x] = s[threadIdx.x][0];
 }
 
 // ---------------------------------------------------------------------------------
@@ -916,11 +973,26 @@ int pw_add_force(const Layout& L, double* pool, const double* src, cudaStream_t 
   return 0;
 }
 
-int pw_stats(const Layout& L, double* pool, double* partial, double* out2, cudaStream_t st) {
-  dim3 grid(L.jm, L.km);
-  k_stats_rows<<<grid, PW_T, 0, st>>>(L, pool, partial);
-  LAUNCH_CHECK();
-  k_stats_final<<<1, 256, 0, st>>>(partial, (long long)L.jm * L.km, out2);
+// what: 0 KE / enstrophy / dissipation sums, 1 CFL maxima, 2 channel mass flux / wall friction sums -> out3
+int pw_reduce(const Layout& L, double* pool, const double* yc, const Thermo& th, int what, int wall_lo, int wall_hi,
+              double* partial, double* out3, cudaStream_t st) {
+  if (what == 0) {
+    dim3 grid(L.jm, L.km);
+    k_reduce_rows<RED_TGV><<<grid, PW_T, 0, st>>>(L, pool, yc, th, partial, 1, 1, 0, 0);
+    LAUNCH_CHECK();
+    k_reduce_final<false><<<1, 256, 0, st>>>(partial, (long long)L.jm * L.km, out3);
+  } else if (what == 1) {
+    dim3 grid(L.jm + 1, L.km + 1);
+    k_reduce_rows<RED_CFL><<<grid, PW_T, 0, st>>>(L, pool, yc, th, partial, 0, 0, 0, 0);
+    LAUNCH_CHECK();
+    k_reduce_final<true><<<1, 256, 0, st>>>(partial, (long long)(L.jm + 1) * (L.km + 1), out3);
+  } else {
+    const int nk = L.km == 0 ? 1 : L.km;               // 2-D blocks: k = 0 only (statistic.F90:1447-1451)
+    dim3 grid(L.jm, nk);
+    k_reduce_rows<RED_CHAN><<<grid, PW_T, 0, st>>>(L, pool, yc, th, partial, 1, L.km == 0 ? 0 : 1, wall_lo, wall_hi);
+    LAUNCH_CHECK();
+    k_reduce_final<false><<<1, 256, 0, st>>>(partial, (long long)L.jm * nk, out3);
+  }
   LAUNCH_CHECK();
   return 0;
 }

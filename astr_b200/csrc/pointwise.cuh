@@ -83,7 +83,9 @@ int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side
 int pw_rk_update(const Layout& L, double* pool, const Thermo& th, const RkCoef& rk, const double* src,
                  cudaStream_t st);
 int pw_add_force(const Layout& L, double* pool, const double* src /*device (force, force.ubulk)*/, cudaStream_t st);
-int pw_stats(const Layout& L, double* pool, double* partial /*2*(jm)*(km)*/, double* out2, cudaStream_t st);
+// block-level diagnostics: what = 0 KE / enstrophy / dissipation sums, 1 CFL maxima, 2 channel mass flux / wall friction
+int pw_reduce(const Layout& L, double* pool, const double* yc, const Thermo& th, int what, int wall_lo, int wall_hi,
+              double* partial, double* out3, cudaStream_t st);
 // face pack / unpack for the multi-block exchange (src/parallel.F90:4180-4218)
 int pw_pack(const Layout& L, const FieldList& fl, int dir, int side, int l0, int l1, double* buf,
             cudaStream_t st);

@@ -33,7 +33,7 @@ SYMBOLS = [
     "astr_gpu_upload_state", "astr_gpu_download_state", "astr_gpu_get_field", "astr_gpu_set_field",
     "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_boucon", "astr_gpu_set_inflow", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
     "astr_gpu_rk_update", "astr_gpu_spongefilter", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps", "astr_gpu_rk_steps_timed",
-    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_kernel_launches",
+    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_reduce_cfl", "astr_gpu_reduce_channel", "astr_gpu_kernel_launches",
     "astr_gpu_set_profile", "astr_gpu_get_profile", "astr_gpu_bench_sweep",
 ]
 
@@ -144,6 +144,8 @@ def load() -> ctypes.CDLL:
     L.astr_gpu_set_sponge.argtypes = [ci, ci, ci, vp]
     L.astr_gpu_set_inflow.argtypes = [vp, vp, vp]
     L.astr_gpu_reduce_tgv.argtypes = [vp]
+    L.astr_gpu_reduce_cfl.argtypes = [vp]
+    L.astr_gpu_reduce_channel.argtypes = [vp]
     L.astr_gpu_kernel_launches.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
     L.astr_gpu_set_profile.argtypes = [ci]
     L.astr_gpu_get_profile.argtypes = [vp, vp, ci]

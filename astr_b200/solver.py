@@ -230,9 +230,48 @@ class RhsEngine:
 
     # ---- statistics (src/statistic.F90:871-990) -----------------------------------------------
     def reduce_tgv(self):
+        """Block sums of rho|u|^2 and rho|omega|^2 (kenergycal / enstophycal before psum)."""
+        return self.reduce_tgv3()[:2]
+
+    def reduce_tgv3(self):
+        """Block sums (rho|u|^2, rho|omega|^2, 2 miu (S:S - div^2/3)): kenergycal, enstophycal, diss_rate_cal."""
         out = (ctypes.c_double * 3)()
         _l.check(self._lib.astr_gpu_reduce_tgv(out))
+        return out[0], out[1], out[2]
+
+    def reduce_cfl(self):
+        """Block maxima (deltai, deltaj, deltak) of cflcal (src/commcal.F90:27-74)."""
+        out = (ctypes.c_double * 3)()
+        _l.check(self._lib.astr_gpu_reduce_cfl(out))
+        return out[0], out[1], out[2]
+
+    def cfl(self, pmax=lambda v: v) -> float:
+        di, dj, dk = self.reduce_cfl()
+        return self.deltat * (pmax(di) + pmax(dj) + pmax(dk))
+
+    def reduce_channel(self):
+        """Block sums of massfluxchan / fbcxchan (src/statistic.F90:1437, :1303) before psum and /norm."""
+        out = (ctypes.c_double * 2)()
+        _l.check(self._lib.astr_gpu_reduce_channel(out))
         return out[0], out[1]
+
+    def channel_stats(self, psum=lambda v: v):
+        """(massflux, fbcx) normalised as massfluxchan / fbcxchan: /ia (2-D) or /(ia*ka)."""
+        mf, fb = self.reduce_channel()
+        ia, ja, ka = self.global_dims
+        norm = float(ia) if ka == 0 else float(ia * ka)
+        return psum(mf) / norm, psum(fb) / norm
+
+    @staticmethod
+    def chanfoce(force: float, massflux: float, friction: float, massflux_target: float, nstep: int, deltat: float,
+                 ly: float = 2.0, uinf: float = 1.0, ref_len: float = 1.0) -> float:
+        """Body force that holds the target mass flux (chanfoce, src/statistic.F90:1494-1537): a scalar formula of the two
+        device reductions; stays on the host."""
+        if nstep == 0:
+            return friction / ly
+        gn = ly * force - friction
+        qn1 = massflux + deltat * gn
+        return force - (2.0 * (qn1 - massflux_target) - 0.2 * (massflux - massflux_target)) / ly * (uinf / ref_len)
 
     def tgv_stats(self, psum=lambda v: v, xmax: float = 2.0 * np.pi):
         """(kenergy, enstrophy) normalised as kenergycal / enstophycal; psum sums over ranks."""

@@ -156,6 +156,16 @@ module astr_gpu_mod
       import :: c_int, c_double
       real(c_double), intent(out) :: out(3)
     end function
+    ! cflcal (src/commcal.F90:27): block maxima deltai,deltaj,deltak; the caller applies pmax
+    integer(c_int) function astr_gpu_reduce_cfl(out) bind(c,name='astr_gpu_reduce_cfl')
+      import :: c_int, c_double
+      real(c_double), intent(out) :: out(3)
+    end function
+    ! massfluxchan / fbcxchan (src/statistic.F90:1437,1303): block sums; the caller applies psum and /norm
+    integer(c_int) function astr_gpu_reduce_channel(out) bind(c,name='astr_gpu_reduce_channel')
+      import :: c_int, c_double
+      real(c_double), intent(out) :: out(2)
+    end function
   end interface
   !
   contains

@@ -178,10 +178,19 @@ int astr_gpu_set_sponge(int face, int beg, int end, const double* coef);
 int astr_gpu_set_force(const double force[3]);
 int astr_gpu_set_grid(const double* x);
 
-/* statistics: out[0]=sum rho*|u|^2, out[1]=sum rho*|omega|^2 over nodes 1..im,1..jm,1..km
- * of this block (src/statistic.F90:871-990 before psum and normalisation), out[2]=0.
- * Requires gradcal of the current stage. */
+/* per-step diagnostics of rkfirst / steploop as BLOCK-level partial results: the caller applies psum / pmax over
+ * the ranks and the reference's normalisation, exactly where the Fortran routines call psum / pmax themselves.
+ * reduce_tgv: out[0] = sum rho |u|^2 (kenergycal, src/statistic.F90:938), out[1] = sum rho |omega|^2 (enstophycal,
+ *   :871), out[2] = sum 2 miu (S:S - div^2/3) (diss_rate_cal, :994) over nodes 1..im,1..jm,1..km; ndims=3.
+ * reduce_cfl: out = max of (Ubar, Ubar -+ c|grad xi|) per direction over nodes 0..im,0..jm,0..km (cflcal,
+ *   src/commcal.F90:27-74); CFL = deltat * (pmax(out[0]) + pmax(out[1]) + pmax(out[2])).
+ * reduce_channel: out[0] = sum of 0.5 (q2(j)+q2(j-1)) dy (massfluxchan, src/statistic.F90:1437), out[1] = wall
+ *   friction sum +miu du/dy at j=0 (jrk=0), -miu du/dy at j=jm (jrk=jrkm) (fbcxchan, :1303); chanfoce (:1494) is a
+ *   scalar formula of these two and stays on the host.
+ * reduce_tgv / reduce_channel require gradcal of the current stage. */
 int astr_gpu_reduce_tgv(double out[3]);
+int astr_gpu_reduce_cfl(double out[3]);
+int astr_gpu_reduce_channel(double out[2]);
 
 /* introspection for bench / tests */
 int astr_gpu_kernel_launches(long long* count);       /* launches since init            */

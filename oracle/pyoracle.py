@@ -122,6 +122,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_run.argtypes = [vp, ci]
         L.oracle_case_run.restype = ci
         L.oracle_case_history.argtypes = [vp, vp]
+        L.oracle_case_reduce.argtypes = [vp, ci, vp]
         _lib = L
     return _lib
 
@@ -348,6 +349,13 @@ class Case:
     def boucon(self):
         if lib().oracle_case_boucon(self._h) != 0:
             raise NotImplementedError("oracle boucon: bctype not restated")
+
+    def reduce(self, what: int) -> np.ndarray:
+        """Raw block-summed diagnostics: 0 (KE, enstrophy, dissipation sums), 1 (CFL maxima), 2 (channel mass flux,
+        wall friction sums) -- see oracle_case_reduce."""
+        out = np.zeros(3)
+        lib().oracle_case_reduce(self._h, int(what), out.ctypes.data)
+        return out
 
     def history(self) -> np.ndarray:
         rows = lib().oracle_case_run(self._h, 0)

@@ -1273,6 +1273,84 @@ void oracle_case_set_flags(void* h, int lfilter, int diffterm) {
   c->lfilter = lfilter; c->diffterm = diffterm;
 }
 // nsteps full RK3 steps (mainloop.F90:103-205: rk stages, then nstep++, time+=dt)
+// ---- per-step diagnostics of rkfirst / steploop, as raw partial sums / maxima summed (psum) or
+// maximised (pmax) over the blocks, BEFORE the reference's normalisation by ia*ja*ka etc. ----
+// what = 0: kenergycal, enstophycal, diss_rate_cal  (src/statistic.F90:938, :871, :994)    -> out[0..2]
+//        1: cflcal deltai, deltaj, deltak           (src/commcal.F90:27-74)                -> out[0..2]
+//        2: massfluxchan, fbcxchan                  (src/statistic.F90:1437-1476, :1303)   -> out[0..1]
+// Needs gradcal of the current state (dvel) for 0 and 2.
+void oracle_case_reduce(void* h, int what, double* out) {
+  Case& c = *static_cast<Case*>(h);
+  const Thermo& th = c.th;
+  out[0] = out[1] = out[2] = 0.0;
+  const int jrkm = c.size[1] - 1;
+  for (Block& b : c.blk) {
+    if (what == 0) {
+      double ke = 0.0, en = 0.0, di = 0.0;
+      for (int k = 1; k <= b.km; ++k)
+        for (int j = 1; j <= b.jm; ++j)
+          for (int i = 1; i <= b.im; ++i) {
+            const double u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+            const double var1 = u * u + v * v + w * w;
+            ke = ke + b.rho(i, j, k) * var1;
+            const double o1 = b.dvel[2][1](i, j, k) - b.dvel[1][2](i, j, k);
+            const double o2 = b.dvel[0][2](i, j, k) - b.dvel[2][0](i, j, k);
+            const double o3 = b.dvel[1][0](i, j, k) - b.dvel[0][1](i, j, k);
+            en = en + b.rho(i, j, k) * (o1 * o1 + o2 * o2 + o3 * o3);
+            // diss_rate_cal, src/statistic.F90:1011-1036
+            const double miu = th.miu_eff(b.tmp(i, j, k));
+            const double du11 = b.dvel[0][0](i, j, k), du12 = b.dvel[0][1](i, j, k), du13 = b.dvel[0][2](i, j, k);
+            const double du21 = b.dvel[1][0](i, j, k), du22 = b.dvel[1][1](i, j, k), du23 = b.dvel[1][2](i, j, k);
+            const double du31 = b.dvel[2][0](i, j, k), du32 = b.dvel[2][1](i, j, k), du33 = b.dvel[2][2](i, j, k);
+            const double s11 = du11, s12 = 0.5 * (du12 + du21), s13 = 0.5 * (du13 + du31);
+            const double s22 = du22, s23 = 0.5 * (du23 + du32), s33 = du33;
+            const double div = s11 + s22 + s33;
+            const double var2 = 2.0 * miu * (s11 * s11 + s22 * s22 + s33 * s33 + 2.0 * (s12 * s12 + s13 * s13 + s23 * s23) -
+                                             num1d3 * (div * div));
+            di = di + var2;
+          }
+      out[0] += ke; out[1] += en; out[2] += di;
+    } else if (what == 1) {
+      double di = 0.0, dj = 0.0, dk = 0.0;
+      for (int k = 0; k <= b.km; ++k)
+        for (int j = 0; j <= b.jm; ++j)
+          for (int i = 0; i <= b.im; ++i) {
+            const double u = b.vel[0](i, j, k), v = b.vel[1](i, j, k), w = b.vel[2](i, j, k);
+            const double ubar = b.dxi[0][0](i, j, k) * u + b.dxi[0][1](i, j, k) * v + b.dxi[0][2](i, j, k) * w;
+            const double vbar = b.dxi[1][0](i, j, k) * u + b.dxi[1][1](i, j, k) * v + b.dxi[1][2](i, j, k) * w;
+            const double wbar = b.dxi[2][0](i, j, k) * u + b.dxi[2][1](i, j, k) * v + b.dxi[2][2](i, j, k) * w;
+            const double css = th.sos(b.tmp(i, j, k));
+            auto nrm = [&](int a) {
+              const double d1 = b.dxi[a][0](i, j, k), d2 = b.dxi[a][1](i, j, k), d3 = b.dxi[a][2](i, j, k);
+              return Thermo::std_sqrt(d1 * d1 + d2 * d2 + d3 * d3);
+            };
+            const double csi = css * nrm(0), csj = css * nrm(1), csk = css * nrm(2);
+            di = std::max(std::max(di, ubar), std::max(ubar - csi, ubar + csi));
+            dj = std::max(std::max(dj, vbar), std::max(vbar - csj, vbar + csj));
+            dk = std::max(std::max(dk, wbar), std::max(wbar - csk, wbar + csk));
+          }
+      out[0] = std::max(out[0], di); out[1] = std::max(out[1], dj); out[2] = std::max(out[2], dk);
+    } else {
+      const int k1 = c.ndims() == 2 ? 0 : 1, k2 = c.ndims() == 2 ? 0 : b.km;
+      double mf = 0.0, fb = 0.0;
+      for (int k = k1; k <= k2; ++k)
+        for (int j = 1; j <= b.jm; ++j)
+          for (int i = 1; i <= b.im; ++i) {
+            const double dy = b.x[1](i, j, k) - b.x[1](i, j - 1, k);
+            const double var1 = 0.5 * (b.q[1](i, j, k) + b.q[1](i, j - 1, k));
+            mf = mf + var1 * dy;
+          }
+      if (b.rk[1] == 0)
+        for (int k = k1; k <= k2; ++k)
+          for (int i = 1; i <= b.im; ++i) fb = fb + th.miu_eff(b.tmp(i, 0, k)) * b.dvel[0][1](i, 0, k);
+      if (b.rk[1] == jrkm)
+        for (int k = k1; k <= k2; ++k)
+          for (int i = 1; i <= b.im; ++i) fb = fb - th.miu_eff(b.tmp(i, b.jm, k)) * b.dvel[0][1](i, b.jm, k);
+      out[0] += mf; out[1] += fb;
+    }
+  }
+}
+
 int oracle_case_run(void* h, int nsteps) {
   Case* c = static_cast<Case*>(h);
   for (int s = 0; s < nsteps; ++s) {

@@ -37,19 +37,26 @@ def test_report(errors):
         print(f"{k:32s} fma {errors['fma'][k]:.3e}   nofma {errors['nofma'][k]:.3e}", file=sys.stderr)
 
 
-# (case, bound of the production build as used in test_gpu_parity.py, bound of the no-contraction build)
+# (case, bound of the production build = the tolerance tests/test_gpu_parity.py uses, bound of the no-contraction
+# build).  Measured on a B200 (round 2): rhscal of every case collapses to <= 8e-14 without contraction -- 2.4e-15,
+# i.e. the last bit, for the explicit WENO / WENO-Z / ROUND reconstructions -- so the production build's 4.6e-12
+# (WENO-Z) and 1.3e-12 (device gridgeom -> 7e-14) are FMA contraction amplified by stiff nonlinear weights / nested
+# derivatives.  What does NOT collapse is the state after several stages of the WENO-Z case (3.5e-12 -> 2.3e-12):
+# there the re-associated line solves (partitioned Thomas) feed the same stiff weights.
 CASES = [
-    ("upwind_periodic:rhscal", 2e-11, 2e-12),
-    ("upwind_walls:rhscal", 2e-11, 2e-12),
+    ("upwind_periodic:rhscal", 2e-12, 2e-13),
+    ("upwind_walls:rhscal", 2e-12, 2e-13),
     ("upwind_periodic:3stages", 1e-12, 1e-12),
     ("upwind_walls:3stages", 1e-12, 1e-12),
-    ("upwind288:rhscal", 2e-9, 2e-10),
-    ("explicit_recon1:rhscal", 2e-10, 2e-11),
-    ("explicit_recon2:rhscal", 2e-10, 2e-11),
-    ("explicit_recon6:rhscal", 2e-10, 2e-11),
-    ("device_gridgeom", 1e-11, 1e-11),
+    ("upwind288:rhscal", 1e-11, 2e-13),
+    ("upwind288:3stages", 1e-11, 5e-12),
+    ("explicit_recon1:rhscal", 2e-11, 2e-14),
+    ("explicit_recon2:rhscal", 2e-11, 2e-14),
+    ("explicit_recon6:rhscal", 2e-11, 2e-14),
+    ("explicit_recon2:2stages", 1e-11, 1e-11),
+    ("device_gridgeom", 5e-12, 2e-13),
     ("golden:ke", 1e-12, 1e-12),
-    ("golden:enstrophy", 1e-11, 1e-11),
+    ("golden:enstrophy", 2e-12, 2e-12),
 ]
 
 

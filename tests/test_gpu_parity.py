@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 OP_TOL = 2e-13
 STEP_TOL = 1e-12
-UPWIND_TOL = 2e-11
+UPWIND_TOL = 2e-12      # measured <= 1.3e-13 on the cases of tests/nofma_worker.py (2e-11 until round 2)
 
 DVEL = [f"dvel{m + 1}{n + 1}" for m in range(3) for n in range(3)]
 DTMP = [f"dtmp{n + 1}" for n in range(3)]
@@ -204,7 +204,8 @@ def test_explicit_upwind_family(oracle, recon_schem, lchardecomp):
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
     # WENO weights divide by (beta+1e-6)^2 and ROUND by a1c^4, a2c^8: smooth but stiff functions of the data
-    tol = 2e-10 if recon_schem in (1, 2, 6) else UPWIND_TOL
+    # measured (tests/test_gpu_nofma.py): 4.6e-12 for WENO-Z with FMA contraction, 2.4e-15 without
+    tol = 2e-11 if recon_schem in (1, 2, 6) else UPWIND_TOL
     assert_fields_close(c, eng, QRHS, tol, what=f"convrsduwd recon_schem={recon_schem}")
     if lchardecomp or recon_schem == 5:
         np.testing.assert_array_equal(core(eng.get("lshock")), core(c.get("lshock")))
@@ -279,7 +280,9 @@ def test_device_gridgeom(oracle):
             got, ref = eng.get(name), c.get(name)
             scale = np.abs(c.get("dxi11")).max() if name != "jacob" else np.abs(ref).max()
             worst[name] = np.abs(got - ref).max() / scale
-        assert max(worst.values()) < 1e-11, worst   # two nested derivative levels + cancellation in the conservative form
+        # two nested derivative levels + cancellation in the conservative form: 1.3e-12 with FMA contraction,
+        # 7e-14 without (tests/test_gpu_nofma.py)
+        assert max(worst.values()) < 5e-12, worst
         eng.close(); c.close()
 
 
@@ -300,7 +303,7 @@ def test_golden_history_through_the_gpu_path(oracle, golden):
     hist = np.array(hist)
     ke_err = np.abs(hist[:, 0] - golden[:rows, 2]).max() / golden[0, 2]
     en_err = np.abs(hist[:, 1] - golden[:rows, 3]).max() / golden[0, 3]
-    assert ke_err < 1e-12 and en_err < 1e-11, (ke_err, en_err, hist, golden[:rows])
+    assert ke_err < 1e-12 and en_err < 2e-12, (ke_err, en_err, hist, golden[:rows])
     eng.close(); c.close()
 
 
@@ -333,7 +336,7 @@ def test_long_i_lines(oracle, kw):
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
     # upwind: the split fluxes are O(c/dx_i) on this fine-in-i grid while their differences are O(1); the
     # reference's REV*LEV round trip at unflagged interfaces (skipped on the device) is rounding noise of that size
-    assert_fields_close(c, eng, QRHS, 2e-9 if "upwind" in kw else 3e-11, what="rhscal (long i lines)")
+    assert_fields_close(c, eng, QRHS, 1e-11 if "upwind" in kw else 3e-11, what="rhscal (long i lines)")
     for rk in (1, 2, 3):
         c.rk_stage(rk); eng.rk_stage(rk)
     assert_fields_close(c, eng, QS + PRIMS, 1e-11 if "upwind" in kw else STEP_TOL, what="3 rk stages (long i lines)")
@@ -379,4 +382,32 @@ def test_compact_flux_solves_on_the_register_engine(oracle):
     c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
     c.zero_qrhs(); c.rhscal(); eng.rhscal()
     assert_fields_close(c, eng, QRHS, UPWIND_TOL, what="rhscal (543c, register engine)")
+    eng.close(); c.close()
+
+
+def test_device_diagnostics(oracle):
+    # diss_rate_cal (src/statistic.F90:994), cflcal (src/commcal.F90:27) on a periodic curvilinear block
+    c, eng = make_pair(oracle, n=(40, 32, 36), stretch=True)
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    ref = c.reduce(0)
+    got = np.array(eng.reduce_tgv3())
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref)), (got, ref)
+    ref = c.reduce(1)
+    got = np.array(eng.reduce_cfl())
+    assert np.all(got == ref), (got, ref)        # maxima of identical expressions: bit for bit
+    assert eng.cfl() > 0.0
+    eng.close(); c.close()
+
+
+def test_channel_diagnostics(oracle):
+    # massfluxchan / fbcxchan (src/statistic.F90:1437, :1303) and the chanfoce formula (:1494) on the channel case
+    c, eng = make_pair(oracle, n=(32, 40, 24), homo=(True, False, True), channel=True, perturb=0.0)
+    c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+    ref = c.reduce(2)[:2]
+    got = np.array(eng.reduce_channel())
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.abs(ref)), (got, ref)
+    mf, fb = eng.channel_stats()
+    assert mf > 0.5 and fb > 0.0                  # laminar profile: unit bulk mass flux scale, positive wall friction
+    f1 = eng.chanfoce(0.0, mf, fb, mf, nstep=0, deltat=1e-3)
+    assert abs(f1 - fb / 2.0) < 1e-15
     eng.close(); c.close()
