@@ -547,10 +547,11 @@ static int init_impl(const astr_cfg* cfg) {
     return astr_fail_msg("ndims must be 3 (km>=1) or 2 (km=0, ksize=1)");
   for (int n = 0; n < 6; ++n)
     if (!(cfg->bctype[n] == 1 || cfg->bctype[n] == 41 || (cfg->bctype[n] == 11 && n == 0) ||
-          (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n == 3) ||
-          (cfg->bctype[n] == 421 && n == 2)))
+          (cfg->bctype[n] == 21 && (n == 1 || n == 3)) || (cfg->bctype[n] == 51 && n >= 2) ||
+          (cfg->bctype[n] == 421 && (n == 2 || n == 3))))
       return astr_fail_msg("bctype on the device: 1 (periodic), 41 (isothermal wall, any face), 11 (inflow, imin), "
-                           "21 (outflow, imax or jmax), 51 (farfield, jmax), 421 (slip adiabatic wall, jmin)");
+                           "21 (outflow, imax or jmax), 51 (farfield, jmin / jmax / kmin / kmax), 421 (slip adiabatic "
+                           "wall, jmin / jmax) -- the faces the reference's own routines implement");
 
   // 643c: compact_central; 642e: explicit_central (diff6ec ignores the scheme digits, derivative.F90:319)
   if (!(cfg->scheme_compact ? cfg->difschm == 643 : (cfg->difschm / 100) == 6))
@@ -919,11 +920,13 @@ int astr_gpu_boucon(void) {
       if (!mine) continue;
       ProfScope ps(PC_HALO);
       TRY(pw_noslip(g->L, g->pool, g->th, d, side, c.twall[n], g->st));
-    } else if ((bt == 11 && n == 0) || (bt == 21 && (n == 1 || n == 3)) || (bt == 51 && n == 3) || (bt == 421 && n == 2)) {
-      // inflow(1) bc.F90:1366, outflow(2|4) :3404, farfield(4) :3008, slipadibwall(3) :7231
+    } else if ((bt == 11 && n == 0) || (bt == 21 && (n == 1 || n == 3)) || (bt == 51 && n >= 2) ||
+               (bt == 421 && (n == 2 || n == 3))) {
+      // inflow(1) bc.F90:1366, outflow(2|4) :3404, farfield(3..6) :3008, slipadibwall(3|4) :7231
       if (!mine) continue;
       BcArgs a;
       a.kind = bt; a.side = side; a.pinf = c.pinf; a.deltat = c.deltat;
+      a.vinf[0] = c.uinf; a.vinf[1] = c.vinf; a.vinf[2] = c.winf; a.roinf = c.roinf;
       a.vel_in = a.tmp_in = a.tmp_prof = nullptr;
       if (bt == 11) {
         if (!g->d_inflow) return astr_fail_msg("boucon: bctype 11 needs astr_gpu_set_inflow");

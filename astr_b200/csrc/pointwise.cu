@@ -606,8 +606,8 @@ __global__ void k_face(const Layout L, const FieldList fl, const int side, const
 }
 
 // ---------------------------------------------------------------------------------
-// inflow(1) (src/bc.F90:1366-1562), outflow(2) / outflow(4) (:3404-3617), farfield(4) (:3008-3392);
-// nondimensional gas, no species.  extrapolate(v1,v2,dv=0) = (4 v1 - v2)/3 (commfunc.F90:277-285).
+// inflow(1) (src/bc.F90:1366-1562), outflow(2) / outflow(4) (:3404-3617), farfield(3..6) (:3008-3392),
+// slipadibwall(3 | 4) (:7231-7430); no species.  extrapolate(v1,v2,dv=0) = (4 v1 - v2)/3 (commfunc.F90:277-285).
 // Threads run over the two other indices of the face (a fastest).
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ double extrap2(double v1, double v2) { return (1.0 / 3.0) * (4.0 * v1 - v2 - 2.0 * 0.0); }
@@ -641,11 +641,47 @@ __global__ void k_bcface(const Layout L, double* __restrict__ pool, const Thermo
     prs[x] = p;
     v0[x] = vin0 + (a.pinf - p) / rho_ref / css;
     rho[x] = th.rho_of(p, tmp[x]);
-  } else if (a.kind == 421) {              // slipadibwall(3), bc.F90:7231-7430: slip, adiabatic
+  } else if (a.kind == 51 && !(DIR == 1 && a.side == 1)) {
+    // farfield(3 | 5 | 6), bc.F90:3024-3104, :3235-3390: subsonic characteristic inflow / outflow against the free stream
+    double* vv[3] = {v0, v1, v2};
+    const double ext[3] = {extrap2(v0[x + sg], v0[x + 2 * sg]), extrap2(v1[x + sg], v1[x + 2 * sg]),
+                           extrap2(v2[x + sg], v2[x + 2 * sg])};
+    const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]), roe = extrap2(rho[x + sg], rho[x + 2 * sg]);
+    const double css = th.sos(tmp[x]);
+    const double csse = extrap2(th.sos(tmp[x + sg]), th.sos(tmp[x + 2 * sg]));
+    const double vn = vv[DIR][x], vne = ext[DIR], vninf = a.vinf[DIR];
+    const bool inflow = a.side ? (vn <= 0.0) : (vn >= 0.0);
+    if (inflow) {
+      const double rho0 = rho[x];
+      double vnew, pnew;
+      if (!a.side) {
+        vnew = 0.5 * (a.pinf - pe) / (rho0 * css) + 0.5 * (vninf + vne);
+        pnew = 0.5 * (a.pinf + pe) + 0.5 * rho0 * css * (vninf - vne);
+      } else {
+        vnew = -0.5 * (a.pinf - pe) / (rho0 * css) + 0.5 * (vninf + vne);
+        pnew = 0.5 * (a.pinf + pe) - 0.5 * rho0 * css * (vninf - vne);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) vv[m][x] = a.vinf[m];
+      vv[DIR][x] = vnew;
+      prs[x] = pnew;
+      rho[x] = a.roinf * pow(pnew / a.pinf, 1.0 / th.gamma);
+    } else {
+      const double pnew = a.pinf;
+      prs[x] = pnew;
+      rho[x] = roe + (pnew - pe) / csse / csse;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) vv[m][x] = ext[m];
+      vv[DIR][x] = a.side ? vne + (pe - pnew) / roe / csse : vne - (pe - pnew) / roe / csse;
+    }
+    tmp[x] = th.T_of(prs[x], rho[x]);
+    from_T = false;
+  } else if (a.kind == 421) {              // slipadibwall(3 | 4), bc.F90:7231-7430: slip, adiabatic
     const double pe = extrap2(prs[x + sg], prs[x + 2 * sg]);
     const double te = extrap2(tmp[x + sg], tmp[x + 2 * sg]);
     const double ue = extrap2(v0[x + sg], v0[x + 2 * sg]);
-    v0[x] = ue; v1[x] = 0.0; v2[x] = 0.0;
+    const double ve = extrap2(v1[x + sg], v1[x + 2 * sg]);
+    v0[x] = ue; v1[x] = a.side ? ve : 0.0; v2[x] = 0.0;      // jmax keeps the extrapolated v (bc.F90:7386-7390)
     tmp[x] = te; prs[x] = pe;
     rho[x] = th.rho_of(pe, te);
     from_T = false;

@@ -72,6 +72,7 @@ int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st);
 struct BcArgs {
   int kind, side;
   double pinf, deltat;
+  double vinf[3], roinf;   // free stream of the far-field faces (commvar uinf, vinf, winf, roinf)
   const double* vel_in;    // device (0:jm,0:km,3)   inflow only
   const double* tmp_in;    // device (0:jm,0:km)
   const double* tmp_prof;  // device (0:jm)

@@ -72,6 +72,7 @@ class AstrCfg(ctypes.Structure):
         ("tempconst", ctypes.c_double), ("tempconst1", ctypes.c_double),
         ("deltat", ctypes.c_double), ("twall", ctypes.c_double * 6),
         ("pinf", ctypes.c_double), ("bfacmpld", ctypes.c_double), ("shkcrt", ctypes.c_double),
+        ("uinf", ctypes.c_double), ("vinf", ctypes.c_double), ("winf", ctypes.c_double), ("roinf", ctypes.c_double),
     ]
 
 

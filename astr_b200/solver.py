@@ -64,7 +64,8 @@ class RhsEngine:
                  twall: Sequence[float] = (0.0,) * 6, explicit: bool = False, conschm: Optional[int] = None,
                  lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
                  conschm_explicit: bool = False, legacy_sweep: bool = False, overlap_visc: bool = False,
-                 xchg_nccl: bool = False, xchg_timeout_ms: int = 0):
+                 xchg_nccl: bool = False, xchg_timeout_ms: int = 0,
+                 freestream: Sequence[float] = (1.0, 0.0, 0.0, 1.0)):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -99,6 +100,8 @@ class RhsEngine:
         c.alfa_filter = alfa_filter
         # roinf*tinf/const2 with roinf=tinf=1 (src/solver.F90:113-120), or thermal(tinf,roinf) for nondimen=f
         c.pinf = thermo.get("pinf", 1.0 / thermo["const2"])
+        # free stream of the far-field faces (commvar uinf, vinf, winf, roinf)
+        c.uinf, c.vinf, c.winf, c.roinf = freestream
         for k, v in thermo.items():
             if k not in ("nondimen", "rgas", "cp", "cv", "pinf"):
                 setattr(c, k, v)

@@ -41,6 +41,7 @@ module astr_gpu_mod
     real(c_double) :: twall(6)
     real(c_double) :: pinf
     real(c_double) :: bfacmpld,shkcrt
+    real(c_double) :: uinf,vinf,winf,roinf
   end type astr_cfg
   !
   interface
@@ -199,7 +200,8 @@ module astr_gpu_mod
                            nbr,mpirank,lfilter,diffterm,alfa_filter,reynolds,mach, &
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
                            device,flowtype,conschm,difschm,bctype,twall, &
-                           recon_schem,lchardecomp,bfacmpld,shkcrt,pinf,ndims,nondimen)
+                           recon_schem,lchardecomp,bfacmpld,shkcrt,pinf,ndims,nondimen, &
+                           uinf,vinf,winf,roinf)
     character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
     character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
     integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
@@ -207,6 +209,7 @@ module astr_gpu_mod
     logical, intent(in) :: lchardecomp              ! commvar lchardecomp
     real(8), intent(in) :: bfacmpld,shkcrt          ! commvar bfacmpld, shkcrt
     real(8), intent(in) :: pinf                     ! commvar pinf
+    real(8), intent(in) :: uinf,vinf,winf,roinf     ! commvar free stream (farfield faces)
     integer, intent(in) :: ndims                    ! commvar ndims (3, or 2 with km=0)
     logical, intent(in) :: nondimen                 ! commvar nondimen
     real(8), intent(in) :: twall(6)                 ! commvar twall(1:6)
@@ -237,6 +240,7 @@ module astr_gpu_mod
     cfg%recon_schem=recon_schem; cfg%lchardecomp=merge(1,0,lchardecomp)
     cfg%conschm_explicit=merge(1,0,conschm(4:4)=='e' .and. mod(cfg%conschm/100,2)==1)
     cfg%bfacmpld=bfacmpld; cfg%shkcrt=shkcrt; cfg%pinf=pinf
+    cfg%uinf=uinf; cfg%vinf=vinf; cfg%winf=winf; cfg%roinf=roinf
     cfg%alfa_filter=alfa_filter
     cfg%reynolds=reynolds; cfg%mach=mach; cfg%prandtl=prandtl; cfg%gamma=gamma; cfg%ref_tem=ref_tem
     cfg%const1=const(1); cfg%const2=const(2); cfg%const3=const(3); cfg%const4=const(4)

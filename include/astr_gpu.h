@@ -72,7 +72,8 @@ typedef struct astr_cfg {
                                  kmax (src/bc.F90:327-407 boucon).  On the device:
                                  1 periodic/none; 41 isothermal wall (any face);
                                  11 inflow (imin); 21 outflow (imax, jmax); 51 farfield
-                                 (jmax); 421 slip adiabatic wall (jmin)                  */
+                                 (jmin, jmax, kmin, kmax); 421 slip adiabatic wall
+                                 (jmin, jmax)                                            */
   /* engine switches (ABI v3; they were environment variables in v2).  0 = default.      */
   int legacy_sweep;           /* 1: every line solve on the shared-memory engine
                                  (sweep.cu) instead of the register engine (sweep2.cu)  */
@@ -94,6 +95,8 @@ typedef struct astr_cfg {
   double pinf;                /* free-stream pressure roinf*tinf/const2 (solver.F90:120) */
   double bfacmpld;            /* blending factor of the compact upwind scheme (flux.F90) */
   double shkcrt;              /* shock-sensor threshold of ducrossensor (commcal.F90)    */
+  double uinf, vinf, winf, roinf; /* free stream of the far-field faces (commvar; nondimensional
+                                 defaults 1, 0, 0, 1: src/solver.F90:113-120)            */
 } astr_cfg;
 
 /* ---- field ids for astr_gpu_get_field / set_field / device_ptr ----------------------

@@ -61,6 +61,8 @@ struct Case {
   int bctype[6] = {1, 1, 1, 1, 1, 1};      // src/readwrite.F90 bctype(1:6): imin,imax,jmin,jmax,kmin,kmax
   double twall[6] = {0, 0, 0, 0, 0, 0};
   double pinf = 0.0;                       // src/solver.F90:120 pinf=roinf*tinf/const2 (set in create)
+  // free stream of the far-field faces (commvar uinf, vinf, winf, roinf; src/solver.F90:113-120): nondimensional 1, 0, 0, 1
+  double uinf = 1.0, vinf = 0.0, winf = 0.0, roinf = 1.0;
   // inflow(1) data of the blocks with irk==0 (bc.F90 alloinflow :69-83): vel_in(0:jm,0:km,3),
   // tmp_in(0:jm,0:km), tmp_prof(0:jm); indexed [block]
   std::vector<std::vector<double>> vel_in, tmp_in, tmp_prof;
@@ -856,42 +858,81 @@ static int outflow(Case& c, int ndir) {
   return 0;
 }
 
-// src/bc.F90:3008-3392 farfield(ndir): restated for ndir==4 (the face the HBL / SWLBI inputs use): plain
-// second-order extrapolation of the primitives
+// src/bc.F90:3008-3392 farfield(ndir).  ndir==4 (jmax, the face the HBL / SWLBI inputs use): plain second-order
+// extrapolation of the primitives (:3106-3232).  ndir==3 (jmin, :3024-3104), 5 (kmin, :3235-3312), 6 (kmax,
+// :3314-3390): subsonic characteristic inflow / outflow against the free stream (uinf, vinf, winf, roinf, pinf).
 static int farfield(Case& c, int ndir) {
-  if (ndir != 4) return -1;
+  if (ndir < 3 || ndir > 6) return -1;
+  const int d = (ndir - 1) / 2, side = (ndir - 1) % 2;      // direction (1: j, 2: k), 0 = low face
+  const double vinf3[3] = {c.uinf, c.vinf, c.winf};
   for (Block& b : c.blk) {
-    if (b.rk[1] != c.size[1] - 1) continue;
-    const int j = b.jm;
-    for (int k = 0; k <= b.km; ++k)
-      for (int i = 0; i <= b.im; ++i) {
-        const double ue = extrapolate2(b.vel[0](i, j - 1, k), b.vel[0](i, j - 2, k));
-        const double ve = extrapolate2(b.vel[1](i, j - 1, k), b.vel[1](i, j - 2, k));
-        const double we = extrapolate2(b.vel[2](i, j - 1, k), b.vel[2](i, j - 2, k));
-        const double pe = extrapolate2(b.prs(i, j - 1, k), b.prs(i, j - 2, k));
-        const double roe = extrapolate2(b.rho(i, j - 1, k), b.rho(i, j - 2, k));
-        b.prs(i, j, k) = pe; b.rho(i, j, k) = roe;
-        b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ve; b.vel[2](i, j, k) = we;
-        b.tmp(i, j, k) = c.th.thermal_T(b.prs(i, j, k), b.rho(i, j, k));
-        fvar2q_T(c.th, b, i, j, k);
+    if (side ? (b.rk[d] != c.size[d] - 1) : (b.rk[d] != 0)) continue;
+    const int dm = b.dim(d), l = side ? dm : 0, sg = side ? -1 : 1;
+    const int n1 = b.im, n2 = (d == 1) ? b.km : b.jm;
+    for (int p2 = 0; p2 <= n2; ++p2)
+      for (int i = 0; i <= n1; ++i) {
+        auto at = [&](Field& f, int off) -> double& { return d == 1 ? f(i, l + sg * off, p2) : f(i, p2, l + sg * off); };
+        const double ue = extrapolate2(at(b.vel[0], 1), at(b.vel[0], 2));
+        const double ve = extrapolate2(at(b.vel[1], 1), at(b.vel[1], 2));
+        const double we = extrapolate2(at(b.vel[2], 1), at(b.vel[2], 2));
+        const double pe = extrapolate2(at(b.prs, 1), at(b.prs, 2));
+        const double roe = extrapolate2(at(b.rho, 1), at(b.rho, 2));
+        const int ii = i, jj = d == 1 ? l : p2, kk = d == 1 ? p2 : l;
+        if (ndir == 4) {
+          b.prs(ii, jj, kk) = pe; b.rho(ii, jj, kk) = roe;
+          b.vel[0](ii, jj, kk) = ue; b.vel[1](ii, jj, kk) = ve; b.vel[2](ii, jj, kk) = we;
+          b.tmp(ii, jj, kk) = c.th.thermal_T(pe, roe);
+          fvar2q_T(c.th, b, ii, jj, kk);
+          continue;
+        }
+        const double css = c.th.sos(b.tmp(ii, jj, kk));
+        const double csse = extrapolate2(c.th.sos(at(b.tmp, 1)), c.th.sos(at(b.tmp, 2)));
+        const double ext[3] = {ue, ve, we};
+        const double vn = b.vel[d](ii, jj, kk), vne = ext[d], vninf = vinf3[d];
+        const bool inflow = side ? (vn <= 0.0) : (vn >= 0.0);
+        if (inflow) {
+          const double rho0 = b.rho(ii, jj, kk);
+          double vnew, pnew;
+          if (!side) {
+            vnew = 0.5 * (c.pinf - pe) / (rho0 * css) + 0.5 * (vninf + vne);
+            pnew = 0.5 * (c.pinf + pe) + 0.5 * rho0 * css * (vninf - vne);
+          } else {
+            vnew = -0.5 * (c.pinf - pe) / (rho0 * css) + 0.5 * (vninf + vne);
+            pnew = 0.5 * (c.pinf + pe) - 0.5 * rho0 * css * (vninf - vne);
+          }
+          for (int m = 0; m < 3; ++m) b.vel[m](ii, jj, kk) = vinf3[m];
+          b.vel[d](ii, jj, kk) = vnew;
+          b.prs(ii, jj, kk) = pnew;
+          b.rho(ii, jj, kk) = c.roinf * std::pow(pnew / c.pinf, 1.0 / c.th.gamma);
+        } else {
+          const double pnew = c.pinf;
+          b.prs(ii, jj, kk) = pnew;
+          b.rho(ii, jj, kk) = roe + (pnew - pe) / csse / csse;
+          for (int m = 0; m < 3; ++m) b.vel[m](ii, jj, kk) = ext[m];
+          b.vel[d](ii, jj, kk) = side ? vne + (pe - pnew) / roe / csse : vne - (pe - pnew) / roe / csse;
+        }
+        b.tmp(ii, jj, kk) = c.th.thermal_T(b.prs(ii, jj, kk), b.rho(ii, jj, kk));
+        fvar2q_P(c.th, b, ii, jj, kk);
       }
   }
   return 0;
 }
 
-// src/bc.F90:7231-7430 slipadibwall(ndir), restated for ndir==3 (jmin, the SWLBI input): slip (u extrapolated,
-// v=w=0), adiabatic (T extrapolated), p extrapolated, rho=thermal(p,T), q=fvar2q(pressure)
+// src/bc.F90:7231-7430 slipadibwall(ndir): adiabatic (T extrapolated), p extrapolated, rho=thermal(p,T),
+// q=fvar2q(pressure).  ndir==3 (jmin, the SWLBI input, :7255-7373): u extrapolated, v=w=0; ndir==4 (jmax,
+// :7375-7424): u and v extrapolated, w=0 -- as the reference writes them.
 static int slipadibwall(Case& c, int ndir) {
-  if (ndir != 3) return -1;
+  if (ndir != 3 && ndir != 4) return -1;
   for (Block& b : c.blk) {
-    if (b.rk[1] != 0) continue;
-    const int j = 0;
+    if (ndir == 3 ? (b.rk[1] != 0) : (b.rk[1] != c.size[1] - 1)) continue;
+    const int j = ndir == 3 ? 0 : b.jm, sg = ndir == 3 ? 1 : -1;
     for (int k = 0; k <= b.km; ++k)
       for (int i = 0; i <= b.im; ++i) {
-        const double pe = num1d3 * (4.0 * b.prs(i, 1, k) - b.prs(i, 2, k));
-        const double te = num1d3 * (4.0 * b.tmp(i, 1, k) - b.tmp(i, 2, k));
-        const double ue = num1d3 * (4.0 * b.vel[0](i, 1, k) - b.vel[0](i, 2, k));
-        b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = 0.0; b.vel[2](i, j, k) = 0.0;
+        const double pe = num1d3 * (4.0 * b.prs(i, j + sg, k) - b.prs(i, j + 2 * sg, k));
+        const double te = num1d3 * (4.0 * b.tmp(i, j + sg, k) - b.tmp(i, j + 2 * sg, k));
+        const double ue = num1d3 * (4.0 * b.vel[0](i, j + sg, k) - b.vel[0](i, j + 2 * sg, k));
+        const double ve = num1d3 * (4.0 * b.vel[1](i, j + sg, k) - b.vel[1](i, j + 2 * sg, k));
+        b.vel[0](i, j, k) = ue; b.vel[1](i, j, k) = ndir == 3 ? 0.0 : ve; b.vel[2](i, j, k) = 0.0;
         b.tmp(i, j, k) = te; b.prs(i, j, k) = pe;
         b.rho(i, j, k) = c.th.thermal_rho(pe, te);
         fvar2q_P(c.th, b, i, j, k);

@@ -39,6 +39,7 @@ int main(int argc, char** argv) {
   c.conschm = c.difschm = 643; c.scheme_compact = 1; c.rkscheme = 3;
   c.lfilter = 1; c.diffterm = 1; c.nondimen = 1; c.flowtype = 0;
   c.alfa_filter = 0.49;
+  c.uinf = 1.0; c.vinf = 0.0; c.winf = 0.0; c.roinf = 1.0;
   c.reynolds = reynolds; c.mach = mach; c.prandtl = prandtl; c.gamma = gamma; c.ref_tem = ref_tem;
   /* refcal, src/solver.F90:104-126 */
   c.const1 = 1.0 / (gamma * (gamma - 1.0) * mach * mach);

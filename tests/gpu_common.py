@@ -132,7 +132,7 @@ def dimensional_state(c, th, ib=0):
 
 def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, stretch=False, seed=1234,
               lfilter=True, diffterm=True, sutherland_s=110.3, device_metrics=False, channel=False, explicit=False, upwind=None, open_faces=False,
-              dimensional=False, sponge=None, inflow_from_state=False, engine_kw=None):
+              dimensional=False, sponge=None, inflow_from_state=False, engine_kw=None, bc=None):
     reynolds, mach = (3000.0, 0.3) if channel else (1600.0, 0.1)    # input.chl / input.tgv
     lengths = (2 * np.pi, 2.0, np.pi) if channel else None
     th = refcal(reynolds, mach, sutherland_s=sutherland_s)
@@ -162,6 +162,9 @@ def make_pair(oracle, n=(32, 32, 32), homo=(True, True, True), perturb=1e-3, str
         twall = (0, 0, 568.89 if dimensional else 1.05, 0, 0, 0)       # input.M3: `41, 568.89d0`
         if open_faces == "swbli":      # examples/SWLBI/datin/input.2d: slip adiabatic wall at jmin
             bctype = (11, 21, 421, 51, 1, 1)
+        c.set_bc(bctype, twall)
+    if bc is not None:          # explicit (bctype(1:6), twall(1:6)) for faces no named option set covers
+        bctype, twall = tuple(bc[0]), tuple(bc[1])
         c.set_bc(bctype, twall)
     if channel:
         pass

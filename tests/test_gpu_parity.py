@@ -411,3 +411,21 @@ def test_channel_diagnostics(oracle):
     f1 = eng.chanfoce(0.0, mf, fb, mf, nstep=0, deltat=1e-3)
     assert abs(f1 - fb / 2.0) < 1e-15
     eng.close(); c.close()
+
+
+def test_boucon_remaining_faces(oracle):
+    # the faces of the listed boundary types that none of the five configs uses, as the reference's routines
+    # implement them: farfield at jmin / kmin / kmax (src/bc.F90:3024, :3235, :3314: subsonic characteristic inflow /
+    # outflow against the free stream -- the Taylor-Green velocities cross every face in both directions) and the
+    # slip adiabatic wall at jmax (:7375)
+    bc = ((1, 1, 51, 421, 51, 51), (0.0,) * 6)
+    c, eng = make_pair(oracle, n=(36, 32, 24), homo=(True, False, False), stretch=True, bc=bc)
+    vj = core(c.get("v"))[:, 0, :]
+    wk0, wk1 = core(c.get("w"))[:, :, 0], core(c.get("w"))[:, :, -1]
+    assert vj.max() > 0 > vj.min(), "jmin face does not see both branches"
+    c.boucon(); eng.boucon()
+    assert_fields_close(c, eng, QS + PRIMS, OP_TOL, region=whole, what="boucon: farfield 3/5/6, slip wall 4")
+    c.rk_stage(1); eng.rk_stage(1)
+    assert np.isfinite(core(c.get("q5"))).all()
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="rk stage with farfield 3/5/6 and slip wall 4")
+    eng.close(); c.close()

@@ -64,8 +64,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/astr_gpu.h but not exported"
     assert sorted(L.SYMBOLS) == declared
-    # the ctypes mirror of struct astr_cfg has the C struct's size (58 ints + 25 doubles)
-    assert lib.astr_gpu_sizeof_cfg() == ctypes.sizeof(L.AstrCfg) == 4 * 58 + 8 * 25
+    # the ctypes mirror of struct astr_cfg has the C struct's size (58 ints + 29 doubles)
+    assert lib.astr_gpu_sizeof_cfg() == ctypes.sizeof(L.AstrCfg) == 4 * 58 + 8 * 29
 
 
 def test_no_gpu_means_loud_failure():
