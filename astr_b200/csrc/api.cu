@@ -853,7 +853,6 @@ int astr_gpu_set_grid(const double* x) {
 
 int astr_gpu_gridgeom(const double* x) {
   NEED_CTX();
-  if (g->cfg.ndims != 3) return astr_fail_msg("device gridgeom covers ndims=3 only: pass the metrics with astr_gpu_set_metrics");
   TRY(ensure_scratch());
   const size_t ne = host_field_elems();
   for (int m = 0; m < 3; ++m) TRY(copy_field(S_G + m, const_cast<double*>(x) + (size_t)m * ne, false));

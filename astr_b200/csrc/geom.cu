@@ -60,6 +60,24 @@ __global__ void k_jacobian(const Layout L, const DX9 dx, double* __restrict__ ja
 #undef DXV
 }
 
+// ---- 2-D blocks (ndims==2): Jacobian (geom.F90:371-375) and dxi (:520-527) from the four in-plane dx ----------
+__global__ void k_jacobian2d(const Layout L, const DX9 dx, double* __restrict__ jac) {
+  const int i = blockIdx.x * GT + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+  if (i > L.im) return;
+  const long long x = L.idx(i, j, k);
+  jac[x] = dx.d[0][x] * dx.d[4][x] - dx.d[1][x] * dx.d[3][x];      // dx(1,1) dx(2,2) - dx(1,2) dx(2,1)
+}
+struct F9w { double* f[9]; };
+__global__ void k_dxi2d(const Layout L, const DX9 dx, const F9w f) {
+  const int i = blockIdx.x * GT + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+  if (i > L.im) return;
+  const long long x = L.idx(i, j, k);
+  f.f[0][x] = dx.d[4][x];        // dxi(1,1) =  dx(2,2)
+  f.f[1][x] = -dx.d[1][x];       // dxi(1,2) = -dx(1,2)
+  f.f[3][x] = -dx.d[3][x];       // dxi(2,1) = -dx(2,1)
+  f.f[4][x] = dx.d[0][x];        // dxi(2,2) =  dx(1,1)
+}
+
 // ---- phi = 0.5*(dx(m1,n1)*x(c1) - dx(m2,n2)*x(c2)) on a box (geom.F90:402-510) ------------
 struct PhiTerm { const double *da, *xa, *db, *xb; double* out; };
 struct PhiTerms { PhiTerm t[6]; };
@@ -119,9 +137,14 @@ int geom_xhalo_unpack(const Layout& L, double* x3[3], int d, const double* from_
 int geom_gridgeom(const Layout& L, const astr_cfg& cfg, cudaStream_t st) {
   const int dimv[3] = {L.im, L.jm, L.km};
   // 1. coordinate halos
-  for (int d = 0; d < 3; ++d) TRYG(astr_xhalo_exchange(d));
-  // 2. dx(m,n) = d x_m / d xi_n -> scratch slot S_SCR + 3m+n   (geom.F90:130-164)
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < cfg.ndims; ++d) TRYG(astr_xhalo_exchange(d));   // 2-D: the k planes are never differentiated
+  if (cfg.ndims == 2)     // d x_m / d zeta = 0: the slots may hold something else from an earlier use of the scratch pool
+    for (int m = 0; m < 3; ++m)
+      CUDA_OK(cudaMemsetAsync(astr_slot_ptr(S_SCR + 3 * m + 2), 0, (size_t)L.fstride * sizeof(double), st));
+  // 2. dx(m,n) = d x_m / d xi_n -> scratch slot S_SCR + 3m+n   (geom.F90:130-164; 2-D blocks: no zeta sweeps, the
+  //    scratch slots are zero-initialised)
+  const int nd = cfg.ndims;
+  for (int d = 0; d < nd; ++d) {
     int in[3], out[3];
     for (int m = 0; m < 3; ++m) { in[m] = S_G + m; out[m] = S_SCR + 3 * m + d; }
     TRYG(astr_sweep_slots(d, OP_DERIV, in, out, 3, EPI_STORE, 0, dimv[d]));
@@ -134,7 +157,8 @@ int geom_gridgeom(const Layout& L, const astr_cfg& cfg, cudaStream_t st) {
     DX9 dx;
     for (int n = 0; n < 9; ++n) dx.d[n] = astr_slot_ptr(S_SCR + n);
     dim3 grid((L.im + GT) / GT, L.jm + 1, L.km + 1);
-    k_jacobian<<<grid, GT, 0, st>>>(L, dx, astr_slot_ptr(S_JAC));
+    if (nd == 2) k_jacobian2d<<<grid, GT, 0, st>>>(L, dx, astr_slot_ptr(S_JAC));
+    else k_jacobian<<<grid, GT, 0, st>>>(L, dx, astr_slot_ptr(S_JAC));
     astr_count_launch();
     CUDA_OK(cudaGetLastError());
     int js = S_JAC;
@@ -153,7 +177,17 @@ int geom_gridgeom(const Layout& L, const astr_cfg& cfg, cudaStream_t st) {
   for (int n = 0; n < 9; ++n)
     CUDA_OK(cudaMemsetAsync(astr_slot_ptr(S_DXI + n), 0, (size_t)L.fstride * sizeof(double), st));
   bool seen[9] = {false, false, false, false, false, false, false, false, false};
-  for (int d = 0; d < 3; ++d) {
+  if (nd == 2) {      // geom.F90:520-527: the in-plane metrics are plain copies, everything else stays zero
+    DX9 dx;
+    for (int n = 0; n < 9; ++n) dx.d[n] = astr_slot_ptr(S_SCR + n);
+    F9w f;
+    for (int n = 0; n < 9; ++n) f.f[n] = astr_slot_ptr(S_DXI + n);
+    dim3 grid((L.im + GT) / GT, L.jm + 1, L.km + 1);
+    k_dxi2d<<<grid, GT, 0, st>>>(L, dx, f);
+    astr_count_launch();
+    CUDA_OK(cudaGetLastError());
+  }
+  for (int d = 0; d < 3 && nd == 3; ++d) {
     PhiTerms pt;
     int in[6], out[6];
     bool add[6];

@@ -783,6 +783,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Window order (both sides agree on it): DIR 0: [field][k][j][plane], plane fastest, so that the strided gather of
+// an i face touches each sector once; DIR 1, 2: [field][p2][plane][i], i fastest.  One CTA per window row (the
+// (field, k) row of np*n1 values for DIR 0, the (field, p2, plane) row of n1 values otherwise): the index
+// arithmetic is per CTA, the threads run along the row.
 template <int DIR, bool SEND>
 __global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList fl, const XArgs a) {
   const int side = blockIdx.z;
@@ -805,53 +809,49 @@ __global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList f
   const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
   const int np = a.l1 - a.l0 + 1;
   const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
-  // flat index over the window: DIR 0: [field][k][j][plane] (plane fastest, so that the strided gather
-  // touches every sector once); DIR 1, 2: [field][p2][plane][i] (i fastest)
-  const long long total = (long long)fl.nf * n2 * np * n1;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  constexpr int U = 4;
-  for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += U * stride) {
-    double v[U];
-    long long x[U], bi[U];
-    int lz[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      bi[u] = base + u * stride;
-      long long r = bi[u] < total ? bi[u] : 0;
-      int p1, p2, l;
-      if (DIR == 0) { l = (int)(r % np); r /= np; p1 = (int)(r % n1); r /= n1; }
-      else { p1 = (int)(r % n1); r /= n1; l = (int)(r % np); r /= np; }
-      p2 = (int)(r % n2);
-      const int fld = (int)(r / n2);
-      l += a.l0;
-      lz[u] = l;
-      const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
-      const long long xx = (DIR == 0) ? L.idx(node, p1, p2) : (DIR == 1 ? L.idx(p1, node, p2) : L.idx(p1, p2, node));
-      x[u] = (long long)(fl.f[fld] - fl.f[0]) + xx;      // element offset from field 0
-    }
-    double* f0 = fl.f[0];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (bi[u] < total) {
-        if (SEND) v[u] = f0[x[u]];
+  const int p1 = blockIdx.x * 256 + threadIdx.x;
+  if (DIR == 0) {
+    const int p2 = blockIdx.y % n2, fld = blockIdx.y / n2;
+    if (p1 < n1) {
+      double* f = fl.f[fld];
+      const long long wb = (((long long)fld * n2 + p2) * n1 + p1) * np;
+#pragma unroll 6
+      for (int lr = 0; lr < np; ++lr) {
+        const int l = a.l0 + lr;
+        const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
+        const long long x = L.idx(node, p1, p2);
+        if (SEND) xs.remote[wb + lr] = f[x];
         else {
-          v[u] = __ldcg(xs.local + bi[u]);
-          if (lz[u] == 0) v[u] = 0.5 * (f0[x[u]] + v[u]);
+          double v = __ldcg(xs.local + wb + lr);
+          if (l == 0) v = 0.5 * (f[x] + v);
+          f[x] = v;
         }
       }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (bi[u] < total) {
-        if (SEND) xs.remote[bi[u]] = v[u];
-        else f0[x[u]] = v[u];
+    }
+  } else {
+    const int lr = blockIdx.y % np;
+    const int r2 = blockIdx.y / np;
+    const int p2 = r2 % n2, fld = r2 / n2;
+    if (p1 < n1) {
+      double* f = fl.f[fld];
+      const int l = a.l0 + lr;
+      const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
+      const long long x = (DIR == 1) ? L.idx(p1, node, p2) : L.idx(p1, p2, node);
+      const long long bi = (((long long)fld * n2 + p2) * np + lr) * n1 + p1;
+      if (SEND) xs.remote[bi] = f[x];
+      else {
+        double v = __ldcg(xs.local + bi);
+        if (l == 0) v = 0.5 * (f[x] + v);
+        f[x] = v;
       }
+    }
   }
   // one system-scope release per CTA: the barrier orders the CTA's stores before thread 0's fence
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     const unsigned prev = atomicAdd(xs.counter, 1u);
-    if (prev == gridDim.x - 1) {
+    if (prev == gridDim.x * gridDim.y - 1) {
       *xs.counter = 0u;
       __threadfence_system();
       st_release_sys(xs.signal_flag, xs.signal_val);
@@ -1048,16 +1048,11 @@ static int face_launch(const Layout& L, const FieldList& fl, int dir, int side, 
 }
 template <bool SEND>
 static int xface_launch(const Layout& L, const FieldList& fl, int dir, const XArgs& a, cudaStream_t st) {
-  static int sms = 0, sms_dev = -1;
-  int dev = 0;
-  CUDA_OK(cudaGetDevice(&dev));
-  if (dev != sms_dev) {
-    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    sms_dev = dev;
-  }
-  // every field must be addressable from field 0 with one 64-bit element offset (same allocation or not:
-  // pointer differences of device allocations are fine as plain integers)
-  dim3 grid(sms * 2, 1, 2);       // 2 CTAs of 256 threads per SM and side
+  const int n1 = (dir == 0) ? L.jm + 1 : L.im + 1;
+  const int n2 = (dir == 2) ? L.jm + 1 : L.km + 1;
+  const int np = a.l1 - a.l0 + 1;
+  // one CTA per window row segment of 256 values, both sides in one launch
+  dim3 grid((n1 + 255) / 256, (dir == 0) ? fl.nf * n2 : fl.nf * n2 * np, 2);
   if (dir == 0) k_xface<0, SEND><<<grid, 256, 0, st>>>(L, fl, a);
   else if (dir == 1) k_xface<1, SEND><<<grid, 256, 0, st>>>(L, fl, a);
   else k_xface<2, SEND><<<grid, 256, 0, st>>>(L, fl, a);

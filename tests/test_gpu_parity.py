@@ -274,7 +274,10 @@ def test_five_steps_and_history(oracle):
 def test_device_gridgeom(oracle):
     for kw in (dict(n=(32, 32, 32)), dict(n=(40, 32, 36), stretch=True),
                dict(n=(32, 48, 32), homo=(True, False, True), stretch=True),
-               dict(n=(32, 48, 32), homo=(True, False, True), stretch=True, explicit=True)):
+               dict(n=(32, 48, 32), homo=(True, False, True), stretch=True, explicit=True),
+               # 2-D blocks (the shape of the HBL / SWLBI inputs): src/geom.F90 ndims==2 branches (:371-375, :520-527)
+               dict(n=(48, 40, 0), homo=(True, True, True), stretch=True),
+               dict(n=(40, 48, 0), homo=(False, False, True), stretch=True)):
         c, eng = make_pair(oracle, device_metrics=True, **kw)
         names = ["jacob"] + [f"dxi{a + 1}{b + 1}" for a in range(3) for b in range(3)]
         worst = {}
