@@ -580,7 +580,7 @@ static int init_impl(const astr_cfg* cfg) {
   g->cfg = *cfg;
   Layout& L = g->L;
   L.im = cfg->im; L.jm = cfg->jm; L.km = cfg->km;
-  L.pitch = ((ASTR_IOFF + cfg->im + 1 + ASTR_HM + 1) + 15) / 16 * 16;
+  L.pitch = ((ASTR_IOFF + cfg->im + 1 + ASTR_HM + 1) + 31) / 32 * 32;
   L.njt = cfg->jm + 1 + 2 * ASTR_HM; L.nkt = cfg->km + 1 + 2 * ASTR_HM;
   L.sj = L.pitch; L.sk = (long long)L.pitch * L.njt;
   L.org = ASTR_IOFF + L.sj * ASTR_HM + L.sk * ASTR_HM;

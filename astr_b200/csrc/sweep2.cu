@@ -66,6 +66,15 @@ struct Sweep2Args {
   FastDiv dx, dxy;           // bundle index -> (bx, by, bz)
   int nby;
   FastDiv dpair;             // i: copy-out item -> (line, node pair)
+  // j/k: PACKED bundles (indices >= nfull).  When the pencils of a row do not fill whole bundles (513 = 16 x 32 + 1)
+  // the rag_r left-over pencils of rag_G different rows share one bundle: lane = g * rag_r + x.  Their windows are
+  // read straight from global memory (no tile), so they cost their share of the traffic instead of a whole bundle.
+  int nfull, rag_r, rag_G, rag_i0;
+  FastDiv dpk, drr;          // packed index -> (bundle of the field, field); lane -> g
+  // i: lines are numbered j + (jm + 1) k across the planes of a field; a bundle is LINES consecutive lines
+  FastDiv dline;             // line -> (j, k)
+  int nlines;                // lines of a field
+  int nbundles;
 };
 
 __device__ __forceinline__ void cta_sync(int id, int nthreads) {
@@ -137,6 +146,43 @@ __device__ __forceinline__ BundlePos locate(unsigned bnd, const Sweep2Args& a) {
   p.bz = (int)z;
   p.by = (int)(q - z * (unsigned)a.nby);
   return p;
+}
+
+// Where a lane's pencil of a j/k bundle lives: offset of node 0 of the line, field, and whether it exists
+struct LanePos { long long off; int bz, valid, packed; };
+struct FalseT { static constexpr bool value = false; };
+struct TrueT { static constexpr bool value = true; };
+template <int DIR, int PEN, bool PACKED>
+__device__ __forceinline__ LanePos lane_pos(unsigned bnd, int lane, const Sweep2Args& a) {
+  const Layout& Lay = a.L;
+  LanePos r;
+  r.packed = PACKED;
+  int icol, by;
+  if (!PACKED) {
+    const BundlePos bp = locate(bnd, a);
+    const int i0 = bp.bx * PEN;
+    // lanes past the last pencil of a ragged bundle compute on zero-filled columns; their stores are predicated off
+    r.valid = (lane < PEN) && (i0 + lane) <= Lay.im;
+    icol = r.valid ? i0 + lane : 0;
+    by = bp.by; r.bz = bp.bz;
+  } else {
+    const unsigned q = bnd - (unsigned)a.nfull;
+    const unsigned z = fdiv(q, a.dpk);
+    const int pb = (int)(q - z * a.dpk.d);
+    const int g = (int)fdiv((unsigned)lane, a.drr);
+    const int x = lane - g * a.rag_r;
+    by = pb * a.rag_G + g;
+    r.valid = g < a.rag_G && by < a.nby;
+    if (!r.valid) by = 0;
+    icol = a.rag_i0 + x; r.bz = (int)z;
+  }
+  r.off = (DIR == 1) ? Lay.idx(icol, 0, by) : Lay.idx(icol, by, 0);
+  return r;
+}
+__device__ __forceinline__ double ldg_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
 
 // epilogue of one solution value: is node written, and with what
@@ -217,28 +263,30 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const JKCtx& c
   const unsigned gl8 = (unsigned)((DIR == 1 ? Lay.sj : Lay.sk) * 8);   // bytes per line step
   // tile[(node + 5) * PEN + col] = f(node) of this thread's pencil
   const int woff = (ASTR_HM + node0 - H) * PEN + col;
-  int it = 0;
-  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+  // one bundle; PACKED is a compile-time copy of the body so that the tile path keeps its register allocation
+  auto body = [&](int bnd, int it, auto packed_tag) {
+    constexpr bool PACKED = decltype(packed_tag)::value;
     const int p = (NT == 2) ? (it & 1) : 0, par = it & 1;
     const unsigned ph = (NT == 2) ? ((unsigned)(it >> 1) & 1u) : ((unsigned)it & 1u);
-    const BundlePos bp = locate(bnd, a);
-    const int i0 = bp.bx * PEN;
-    // lanes past the last pencil of a ragged bundle compute on halo / zero-filled columns; their stores are
-    // predicated off
-    const int valid = (lane < PEN) && (i0 + lane) <= Lay.im;
-    const int icol = valid ? i0 + lane : 0;
-    double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
+    const LanePos lp = lane_pos<DIR, PEN, PACKED>((unsigned)bnd, lane, a);
+    const int valid = lp.valid;
+    double* __restrict__ gout = a.out[lp.bz] + lp.off;
 
-    mbar_wait(&c.full[p], ph);
-    // ---- tile -> registers: the chunk (+ stencil overlap) -------------------------------------
     double wv[WN];
-    {
+    if (!PACKED) {
+      mbar_wait(&c.full[p], ph);
+      // ---- tile -> registers: the chunk (+ stencil overlap) -------------------------------------
       const unsigned wpa = smem_u32(c.tile[p] + woff);
 #pragma unroll
       for (int s = 0; s < WN; ++s) wv[s] = lds_f64(wpa + (unsigned)(s * PEN * 8));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c.empty[p]);      // this warp is done with the tile
+    } else {
+      // ---- packed bundle: global memory -> registers (every load of the CTA precedes barrier 1, every store follows it)
+      const double* gp = a.in[lp.bz] + lp.off + (long long)(node0 - H) * (gl8 / 8);
+#pragma unroll
+      for (int s = 0; s < WN; ++s) wv[s] = ldg_f64(row_ptr(const_cast<double*>(gp), gl8, s));
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&c.empty[p]);      // this warp is done with the tile
 
     // ---- eliminate, publish S / S' ------------------------------------------------------------
     double* sSl = c.sS[par] + col;
@@ -264,7 +312,10 @@ __device__ __forceinline__ void regular_loop(const Sweep2Args& a, const JKCtx& c
       });
     }
     // sS/sP are double-buffered by bundle parity: a warp can run at most one barrier ahead of the slowest one
-  }
+  };
+  int it = 0, bnd = blockIdx.x;
+  for (; bnd < a.nfull; bnd += gridDim.x, ++it) body(bnd, it, FalseT());
+  for (; bnd < c.nbundles; bnd += gridDim.x, ++it) body(bnd, it, TrueT());
 }
 
 // HSL: slots of the head block that are processed (8 when the block has at most 8 rows -- the common case, e.g.
@@ -302,46 +353,57 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
     }
   };
   if (lane == 0) {
-    if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x, 0);
-    if (NT == 2 && (int)(blockIdx.x + gridDim.x) < c.nbundles) fetch(blockIdx.x + gridDim.x, 1);
+    if ((int)blockIdx.x < a.nfull) fetch(blockIdx.x, 0);
+    if (NT == 2 && (int)(blockIdx.x + gridDim.x) < a.nfull) fetch(blockIdx.x + gridDim.x, 1);
   }
   __syncwarp();
 
-  int it = 0;
-  for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
+  auto body = [&](int bnd, int it, auto packed_tag) {
+    constexpr bool PACKED = decltype(packed_tag)::value;
     const int p = (NT == 2) ? (it & 1) : 0, par = it & 1;
     const unsigned ph = (NT == 2) ? ((unsigned)(it >> 1) & 1u) : ((unsigned)it & 1u);
-    const BundlePos bp = locate(bnd, a);
-    const int i0 = bp.bx * PEN;
-    const int valid = (lane < PEN) && (i0 + lane) <= Lay.im;
-    const int icol = valid ? i0 + lane : 0;
-    double* __restrict__ gout = a.out[bp.bz] + ((DIR == 1) ? Lay.idx(icol, 0, bp.by) : Lay.idx(icol, bp.by, 0));
-    const double* tl = c.tile[p] + ASTR_HM * PEN + col;   // tl[node * PEN] = f(node) of this thread's pencil
-    const double* hp = tl + hnode0 * PEN;
-    const double* tp = tl + (n - 10) * PEN;
+    const LanePos lp = lane_pos<DIR, PEN, PACKED>((unsigned)bnd, lane, a);
+    const int valid = lp.valid;
+    double* __restrict__ gout = a.out[lp.bz] + lp.off;
 
-    mbar_wait(&c.full[p], ph);
-    // ---- tile -> right-hand sides of the two blocks (the windows die before the tile is released) ----
     double dh[HSL], dt[ASTR_TS];
-    {
-      double hw[HWN], tw[16];
-      load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * PEN]; });
+    if (!PACKED) {
+      const double* tl = c.tile[p] + ASTR_HM * PEN + col;   // tl[node * PEN] = f(node) of this thread's pencil
+      const double* hp = tl + hnode0 * PEN;
+      const double* tp = tl + (n - 10) * PEN;
+      mbar_wait(&c.full[p], ph);
+      // ---- tile -> right-hand sides of the two blocks (the windows die before the tile is released) ----
+      {
+        double hw[HWN], tw[16];
+        load_head_window(hw, hwlim, hnode0, [&](int k) { return hp[k * PEN]; });
 #pragma unroll
-      for (int k = 0; k < 16; ++k) tw[k] = tp[k * PEN];
+        for (int k = 0; k < 16; ++k) tw[k] = tp[k * PEN];
+        head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
+        tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
+      }
+      __syncwarp();
+      // producer: once every warp has copied its rows into registers the tile is refilled with the bundle NT
+      // iterations ahead, so that the fetch runs under the elimination, the scan and the write-out
+      if (lane == 0) {
+        mbar_arrive(&c.empty[p]);
+        if (bnd + NT * (int)gridDim.x < a.nfull) {
+          mbar_wait(&c.empty[p], ph);
+          fetch(bnd + NT * gridDim.x, p);
+        }
+      }
+      __syncwarp();
+    } else {
+      // packed bundle: the windows come straight from global memory
+      double* gin = const_cast<double*>(a.in[lp.bz]) + lp.off;
+      double* hp = gin + (long long)hnode0 * (gl8 / 8);
+      double* tp = gin + (long long)(n - 10) * (gl8 / 8);
+      double hw[HWN], tw[16];
+      load_head_window(hw, hwlim, hnode0, [&](int k) { return ldg_f64(row_ptr(hp, gl8, k)); });
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tw[k] = ldg_f64(row_ptr(tp, gl8, k));
       head_rhs_any<OP>(p0, hw, fc, pl.nsf, pl.sh, dh);
       tail_rhs_any<OP>(pm, tw, fc, pl.st - pl.nsl, dt);
     }
-    __syncwarp();
-    // producer: once every warp has copied its rows into registers the tile is refilled with the bundle NT
-    // iterations ahead, so that the fetch runs under the elimination, the scan and the write-out
-    if (lane == 0) {
-      mbar_arrive(&c.empty[p]);
-      if (bnd + NT * (int)gridDim.x < c.nbundles) {
-        mbar_wait(&c.empty[p], ph);
-        fetch(bnd + NT * gridDim.x, p);
-      }
-    }
-    __syncwarp();
 
     // ---- eliminate, publish S / S' -------------------------------------------------------------
     // (in place: the right-hand sides become the eliminated rows)
@@ -383,7 +445,10 @@ __device__ __forceinline__ void special_loop(const Sweep2Args& a, const CUtensor
         st_if(row_ptr(po, gl8, s), R.value(node, x), valid && s < st && R.writes(node));
       });
     }
-  }
+  };
+  int it = 0, bnd = blockIdx.x;
+  for (; bnd < a.nfull; bnd += gridDim.x, ++it) body(bnd, it, FalseT());
+  for (; bnd < c.nbundles; bnd += gridDim.x, ++it) body(bnd, it, TrueT());
 }
 
 template <int DIR, int OP, int PEN, int NT>
@@ -401,7 +466,7 @@ sweep2_kernel(const __grid_constant__ Sweep2Args a, const __grid_constant__ CUte
   c.sS[0] = sbase; c.sP[0] = sbase + ESZ * PEN; c.sS[1] = sbase + 2 * ESZ * PEN; c.sP[1] = sbase + 3 * ESZ * PEN;
   c.full = &mbar[0]; c.empty = &mbar[2];
   c.nthreads = (NW + 1) * 32;
-  c.nbundles = (int)(a.dxy.d * (unsigned)a.nf);
+  c.nbundles = a.nbundles;
   for (int i = threadIdx.x; i < 4 * ESZ * PEN; i += blockDim.x) sbase[i] = 0.0;
   if (threadIdx.x == 0) {
     for (int t = 0; t < NT; ++t) { mbar_init(&c.full[t], 1); mbar_init(&c.empty[t], NW + 1); }
@@ -593,13 +658,24 @@ __device__ __forceinline__ void producer_loop_i(const Sweep2Args& a, const ICtx&
   const int nf0 = (lo + 1) & ~1;
   const int nf1 = max((hi + 1) & ~1, nf0);
   const int e0 = min(nf0, R.w_hi + 1), e1 = max(nf1, R.w_lo);
+  // bundle -> field and first line; this lane's line as an offset (node 0) into the field
+  struct LinePos { int bz, nvalid; long long off; };
+  auto line_of = [&](int bnd) {
+    LinePos r;
+    const unsigned z = fdiv((unsigned)bnd, a.dx);             // dx: bundles per field
+    const int l0 = (int)((unsigned)bnd - z * a.dx.d) * LINES;
+    r.bz = (int)z;
+    r.nvalid = min(LINES, a.nlines - l0);
+    const unsigned l = (unsigned)min(l0 + lane, a.nlines - 1);
+    const unsigned k = fdiv(l, a.dline);
+    r.off = Lay.idx(0, (int)(l - k * a.dline.d), (int)k);
+    return r;
+  };
   auto fetch = [&](int bnd, int p) {
-    const BundlePos q = locate(bnd, a);
-    const int j0 = q.bx * LINES;
-    const int nvalid = min(LINES, Lay.jm - j0 + 1);
-    if (lane == 0) mbar_expect_tx(&c.full[p], line_bytes * (unsigned)nvalid);
+    const LinePos q = line_of(bnd);
+    if (lane == 0) mbar_expect_tx(&c.full[p], line_bytes * (unsigned)q.nvalid);
     __syncwarp();
-    if (lane < nvalid) bulk_load(c.tile[p] + lane * c.sp, a.in[q.bz] + Lay.idx(-6, j0 + lane, q.by), line_bytes, &c.full[p]);
+    if (lane < q.nvalid) bulk_load(c.tile[p] + lane * c.sp, a.in[q.bz] + q.off - 6, line_bytes, &c.full[p]);
   };
   if ((int)blockIdx.x < c.nbundles) fetch(blockIdx.x, 0);
   if ((int)(blockIdx.x + gridDim.x) < c.nbundles) fetch(blockIdx.x + gridDim.x, 1);
@@ -607,13 +683,12 @@ __device__ __forceinline__ void producer_loop_i(const Sweep2Args& a, const ICtx&
   for (int bnd = blockIdx.x; bnd < c.nbundles; bnd += gridDim.x, ++it) {
     const int p = it & 1;
     const unsigned ph = (unsigned)(it >> 1) & 1u;
-    const BundlePos bp = locate(bnd, a);
-    const int j0 = bp.bx * LINES;
-    const int nl = min(LINES, Lay.jm - j0 + 1);            // valid lines of the bundle
+    const LinePos bp = line_of(bnd);
+    const int nl = bp.nvalid;                              // valid lines of the bundle
     mbar_wait(&c.staged[p], ph);                           // every compute warp has staged its rows of tile p
     if (lane < nl) {
       const double* srow = c.tile[p] + lane * c.sp + 6;    // srow[node]
-      double* grow = a.out[bp.bz] + Lay.idx(0, j0 + lane, bp.by);   // grow[node]
+      double* grow = a.out[bp.bz] + bp.off;                // grow[node]
       if (nf1 > nf0) bulk_store(grow + nf0, srow + nf0, (unsigned)(nf1 - nf0) * 8u);
       for (int node = R.w_lo; node < e0; ++node) grow[node] = R.value(node, srow[node]);
       for (int node = e1; node <= R.w_hi; ++node) grow[node] = R.value(node, srow[node]);
@@ -640,7 +715,7 @@ __global__ void __launch_bounds__(544, 1) sweep2i_kernel(const __grid_constant__
   c.full = &mbar[0]; c.staged = &mbar[2];
   const int NW = pl.NW;
   c.ncompute = (NW + 1) * 32;
-  c.nbundles = (int)(a.dxy.d * (unsigned)a.nf);
+  c.nbundles = a.nbundles;
   for (int i = threadIdx.x; i < 4 * ESZ * LINES; i += blockDim.x) sbase[i] = 0.0;
   if (threadIdx.x == 0) {
     mbar_init(&c.full[0], 1); mbar_init(&c.full[1], 1);
@@ -721,11 +796,23 @@ int launch2_cfg(Sweep2Args& a, const PoolMap& pm, int NW, size_t smem, cudaStrea
   const int rc = prepare(kern, lc, threads, smem);
   if (rc) return rc;
   const Layout& L = a.L;
-  const long long nbx = (L.im + PEN) / PEN;
+  long long nbx = (L.im + PEN) / PEN;
   const long long nby = (DIR == 2 ? L.jm : L.km) + 1;
-  const long long nbundles = nbx * nby * a.nf;
+  // left-over pencils of a row: packed rag_G rows to a bundle when at least two rows fit
+  const int rag = (L.im + 1) % PEN;
+  long long npk = 0;
+  a.rag_r = 1; a.rag_G = 0; a.rag_i0 = 0;
+  if (rag > 0 && 2 * rag <= 32 && nbx > 1) {
+    nbx -= 1;
+    a.rag_r = rag; a.rag_G = 32 / rag; a.rag_i0 = (int)nbx * PEN;
+    npk = (nby + a.rag_G - 1) / a.rag_G;
+  }
+  a.nfull = (int)(nbx * nby * a.nf);
+  const long long nbundles = a.nfull + npk * a.nf;
   a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
-  a.dpair = make_fastdiv(1);
+  a.dpk = make_fastdiv((unsigned)(npk > 0 ? npk : 1)); a.drr = make_fastdiv((unsigned)a.rag_r);
+  a.dpair = make_fastdiv(1); a.dline = make_fastdiv(1); a.nlines = 0;
+  a.nbundles = (int)nbundles;
   long long grid = (long long)g_sms * lc.occ;
   if (grid > nbundles) grid = nbundles;
   kern<<<(unsigned)grid, threads, smem, st>>>(a, pm.tm[DIR][PEN == 24 ? 1 : 0]);
@@ -757,11 +844,13 @@ int launch2i_lines(Sweep2Args& a, const LinePlan& plan, size_t smem, cudaStream_
   const int rc = prepare(kern, lc, threads, smem);
   if (rc) return rc;
   const Layout& L = a.L;
-  const long long nbx = (L.jm + LINES) / LINES;
-  const long long nby = L.km + 1;
-  const long long nbundles = nbx * nby * a.nf;
-  a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv((unsigned)(nbx * nby)); a.nby = (int)nby;
-  a.dpair = make_fastdiv(1);
+  const long long nlines = (long long)(L.jm + 1) * (L.km + 1);
+  const long long nbx = (nlines + LINES - 1) / LINES;       // bundles per field
+  const long long nbundles = nbx * a.nf;
+  a.dx = make_fastdiv((unsigned)nbx); a.dxy = make_fastdiv(1); a.nby = 1;
+  a.dline = make_fastdiv((unsigned)(L.jm + 1)); a.nlines = (int)nlines;
+  a.nfull = (int)nbundles; a.rag_r = 1; a.rag_G = 0; a.rag_i0 = 0; a.dpk = make_fastdiv(1); a.drr = make_fastdiv(1);
+  a.dpair = make_fastdiv(1); a.nbundles = (int)nbundles;
   long long grid = (long long)g_sms * lc.occ;
   if (grid > nbundles) grid = nbundles;
   kern<<<(unsigned)grid, threads, smem, st>>>(a);

@@ -40,14 +40,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int 
                ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src)) : "memory");
 }
 
-struct Geo { int nbx, nby, nrb, rows, pen, nf, dir, ns; unsigned tile_bytes; };
+struct Geo { int nbx, nby, nrb, rows, pen, nf, dir, ns, ioff; unsigned tile_bytes; };
 
 // one warp per CTA; lane 0 drives the ring.  STG = 0: TMA store; STG = 1: all lanes copy the tile out with LDS/STG
 template <int STG>
 __global__ void k_ring(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout, Geo g,
                        double* __restrict__ dst, long long sj, long long sk, long long fstride) {
   extern __shared__ __align__(128) char smem[];
-  __shared__ __align__(8) unsigned long long full[8];
+  __shared__ __align__(8) unsigned long long full[40];
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) for (int s = 0; s < g.ns; ++s) mbar_init(&full[s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -62,7 +62,7 @@ __global__ void k_ring(const __grid_constant__ CUtensorMap tin, const __grid_con
     const int bx = (int)(b % g.nbx);
     const int by = (int)((b / g.nbx) % g.nby);
     const int f = (int)(b / ((long long)g.nbx * g.nby));
-    c0 = 16 + bx * g.pen; c3 = f;
+    c0 = g.ioff + bx * g.pen; c3 = f;
     if (g.dir == 1) { c1 = rb * g.rows; c2 = by + 5; } else { c1 = by + 5; c2 = rb * g.rows; }
   };
   auto load = [&](long long q, int s) {
@@ -126,8 +126,8 @@ float time_ms(F f, int iters = 3) {
   return ms / iters;
 }
 
-int main() {
-  const int pitch = 544, njt = 523, nkt = 523, nf = 5, nn = 513;
+int run(int pitch, int njt, bool full_list, int ioff = 16) {
+  const int nkt = 523, nf = 5, nn = 513;
   const long long sj = pitch, sk = (long long)pitch * njt, fstride = sk * nkt;
   const size_t bytes = (size_t)fstride * nf * 8;
   double *src, *dst;
@@ -148,15 +148,19 @@ int main() {
   std::vector<Cfg> cfgs;
   for (int dir = 1; dir <= 2; ++dir) {
     cfgs.push_back({dir, 32, 175, 3, 1, 1, 512});     // today's structure without the arithmetic: one 3-box tile, LDS/STG
+    cfgs.push_back({dir, 32, 88, 9, 1, 0, 32});
+    if (!full_list) continue;
     cfgs.push_back({dir, 32, 175, 3, 1, 0, 32});      // the same tile as a ring of its 3 boxes, TMA stores
     cfgs.push_back({dir, 32, 131, 6, 1, 0, 32});
-    cfgs.push_back({dir, 32, 88, 9, 1, 0, 32});
     cfgs.push_back({dir, 32, 88, 4, 2, 0, 32});
+    cfgs.push_back({dir, 32, 44, 18, 1, 0, 32});
+    cfgs.push_back({dir, 32, 22, 36, 1, 0, 32});
     cfgs.push_back({dir, 16, 175, 6, 1, 0, 32});      // 128-byte segments
     cfgs.push_back({dir, 16, 175, 3, 2, 0, 32});
     cfgs.push_back({dir, 16, 175, 3, 2, 1, 256});
     cfgs.push_back({dir, 64, 88, 4, 1, 0, 32});       // 512-byte segments
     cfgs.push_back({dir, 64, 131, 3, 1, 0, 32});
+    cfgs.push_back({dir, 64, 44, 9, 1, 0, 32});
     cfgs.push_back({dir, 8, 176, 6, 2, 0, 32});       // 64-byte segments
   }
   for (const Cfg& c : cfgs) {
@@ -172,7 +176,7 @@ int main() {
                          CU_TENSOR_MAP_SWIZZLE_NONE, prom, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) { printf("encode failed %d %d\n", (int)r1, (int)r2); continue; }
     Geo g;
-    g.dir = c.dir; g.pen = c.pen; g.rows = c.rows; g.ns = c.ns; g.nf = nf;
+    g.ioff = ioff; g.dir = c.dir; g.pen = c.pen; g.rows = c.rows; g.ns = c.ns; g.nf = nf;
     g.nbx = (nn + c.pen - 1) / c.pen;                 // 513 pencils: the ragged bundle is copied too (as the kernels fetch it)
     g.nby = nn; g.nrb = (523 + c.rows - 1) / c.rows;
     g.tile_bytes = (unsigned)c.rows * c.pen * 8;
@@ -181,8 +185,8 @@ int main() {
     float ms;
     if (c.stg == 0) ms = time_ms([&] { k_ring<0><<<sms * c.ctas, c.threads, smem>>>(tin, tout, g, dst, sj, sk, fstride); });
     else ms = time_ms([&] { k_ring<1><<<sms * c.ctas, c.threads, smem>>>(tin, tout, g, dst, sj, sk, fstride); });
-    printf("dir=%c pen=%2d (%3d B) rows/tile=%3d stages=%d CTAs/SM=%d %s (%3zu KB/SM): %.3f ms  %.0f GB/s algorithmic\n",
-           "ijk"[c.dir], c.pen, c.pen * 8, c.rows, c.ns, c.ctas, c.stg ? "LDS/STG  " : "TMA store", smem * c.ctas / 1024, ms,
+    printf("ioff=%d pitch=%d njt=%d dir=%c pen=%2d (%3d B) rows/tile=%3d stages=%2d CTAs/SM=%d %s (%3zu KB/SM): %.3f ms  %.0f GB/s algorithmic\n",
+           ioff, pitch, njt, "ijk"[c.dir], c.pen, c.pen * 8, c.rows, c.ns, c.ctas, c.stg ? "LDS/STG  " : "TMA store", smem * c.ctas / 1024, ms,
            gb / ms * 1e3);
     fflush(stdout);
   }
@@ -191,6 +195,22 @@ int main() {
   CK(cudaMemcpy(h.data(), (char*)dst + (size_t)(5 * sk + 5 * sj + 16) * 8, 4096, cudaMemcpyDeviceToHost));
   int bad = 0;
   for (int i = 0; i < 4096; ++i) bad += h[i] != 1;
-  printf(bad ? "VERIFY FAILED\n" : "verify ok\n");
-  return 0;
+  if (bad) printf("VERIFY FAILED\n");
+  CK(cudaFree(src)); CK(cudaFree(dst));
+  return bad;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 2) {            // alignment of the row segments: element offset of node 0 inside a row
+    for (int p : {544, 576}) for (int io : {0, 16, 32, 8}) run(p, 523, false, io);
+    return 0;
+  }
+  if (argc > 1) {            // padding scan: row pitch (j stride) and rows per plane (k stride)
+    const int pitches[] = {528, 544, 560, 576, 592, 608};
+    const int njts[] = {523, 524, 525, 526, 527, 528, 531, 536};
+    for (int p : pitches) run(p, 523, false);
+    for (int n : njts) if (n != 523) run(544, n, false);
+    return 0;
+  }
+  return run(544, 523, true);
 }
