@@ -172,6 +172,7 @@ struct Ctx {
   Thermo th;
   double* pool = nullptr;        // S_CORE fields
   double* scr = nullptr;         // 15 scratch fields, lazily allocated
+  double* rhsav = nullptr;       // rk4: 5 fields (src/mainloop.F90:394), allocated at the first rk4 update
   HostOp fd[3], fl[3];
   HostOp fxp[3], fxm[3];         // flux_uw_* / flux_dw_* (conschm 543 only)
   double* up = nullptr;          // UP_TOTAL fields of the upwind path, lazily allocated
@@ -271,7 +272,7 @@ static FieldList fields(int s0, int n) {
 // halo exchange of one direction (dataswap / qswap / datasync, src/parallel.F90)
 // -------------------------------------------------------------------------------------
 constexpr int XMAX_PLANES = 45;            // 9 fields x 5 planes (sigma+qflux) >= 5 fields x 6 planes (qswap)
-static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1);
+static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1, int phases = 3);
 
 static int exchange_dir(const FieldList& fl, int d, int mode) {
   const astr_cfg& c = g->cfg;
@@ -443,12 +444,14 @@ static int p2p_setup() {
 }
 
 // one direction through peer memory: SEND (fused pack + remote stores + ready flag), RECV (wait, unpack, ack)
-static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
+// phases: 1 = SEND, 2 = RECV (of the exchange the last SEND of this direction started), 3 = both
+static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1, int phases) {
   const astr_cfg& c = g->cfg;
   const Layout& L = g->L;
   const int dims[3] = {c.im, c.jm, c.km};
   XHeader* hdr = reinterpret_cast<XHeader*>(g->xarena);
-  const unsigned long long seq = ++g->xseq[d];
+  if (phases & 1) ++g->xseq[d];
+  const unsigned long long seq = g->xseq[d];
   XArgs sa, ra;
   memset(&sa, 0, sizeof sa); memset(&ra, 0, sizeof ra);
   sa.l0 = ra.l0 = l0; sa.l1 = ra.l1 = l1;
@@ -473,8 +476,8 @@ static int exchange_dir_p2p(const FieldList& fl, int d, int l0, int l1) {
     r.signal_flag = &ph->ack[oslot]; r.signal_val = seq;
     r.counter = &hdr->crecv[slot];
   }
-  { ProfScope ps(PC_XPACK); TRY(pw_xsend(L, fl, d, sa, g->cur)); }
-  { ProfScope ps(PC_XUNPACK); TRY(pw_xrecv(L, fl, d, ra, g->cur)); }
+  if (phases & 1) { ProfScope ps(PC_XPACK); TRY(pw_xsend(L, fl, d, sa, g->cur)); }
+  if (phases & 2) { ProfScope ps(PC_XUNPACK); TRY(pw_xrecv(L, fl, d, ra, g->cur)); }
   return 0;
 }
 
@@ -495,6 +498,18 @@ static int p2p_check() {
 }
 
 static int dataswap(const FieldList& fl, int direction /*-1 all*/) {
+  // all directions through peer memory: the three exchanges are independent (planes 1..hm of the interior go out,
+  // halo planes come in, no corner exchange: src/parallel.F90:4172-4173), so every SEND is started before the first
+  // RECV waits -- by then the neighbours' data has long arrived
+  if (direction < 0 && g->p2p && g->comm && fl.nf * ASTR_HM <= XMAX_PLANES) {
+    for (int d = 0; d < 3; ++d) {
+      if (g->cfg.size[d] == 1) TRY(exchange_dir(fl, d, XMODE_SWAP));
+      else TRY(exchange_dir_p2p(fl, d, 1, ASTR_HM, 1));
+    }
+    for (int d = 0; d < 3; ++d)
+      if (g->cfg.size[d] > 1) TRY(exchange_dir_p2p(fl, d, 1, ASTR_HM, 2));
+    return 0;
+  }
   for (int d = 0; d < 3; ++d)
     if (direction < 0 || direction == d) TRY(exchange_dir(fl, d, XMODE_SWAP));
   return 0;
@@ -567,7 +582,7 @@ static int init_impl(const astr_cfg* cfg) {
       return astr_fail_msg("convrsduwd stops for npdcj/npdck == 4 (src/solver.F90:810-821, :1002-1013)");
   } else if (cfg->conschm != cfg->difschm && cfg->conschm != 543)
     return astr_fail_msg("conschm must equal difschm (central), be 543c (upwind compact) or an explicit upwind scheme");
-  if (cfg->rkscheme != 3) return astr_fail_msg("only rk3 is implemented");
+  if (cfg->rkscheme != 3 && cfg->rkscheme != 4) return astr_fail_msg("rkscheme must be 3 (rk3) or 4 (rk4)");
   if (cfg->reserved0 != 0) return astr_fail_msg("cfg.reserved0 must be 0");
   for (int d = 0; d < 3; ++d)
     if (cfg->npdc[d] < 1 || cfg->npdc[d] > 4) return astr_fail_msg("npdc must be 1..4");
@@ -677,6 +692,7 @@ int astr_gpu_finalize(void) {
   for (int k = 0; k < 3; ++k) astr_sweep2_register_pool(k, nullptr, 0, g->L);
   if (g->pool) cudaFree(g->pool);
   if (g->scr) cudaFree(g->scr);
+  if (g->rhsav) cudaFree(g->rhsav);
   if (g->d_partial) cudaFree(g->d_partial);
   if (g->d_out2) cudaFree(g->d_out2);
   if (g->d_src) cudaFree(g->d_src);
@@ -1140,10 +1156,20 @@ int astr_gpu_rhscal(void) {
 }
 
 static int rk_coef(int rkstep, double dt, RkCoef& rk) {
-  if (rkstep < 1 || rkstep > 3) return astr_fail_msg("rkstep must be 1..3");
-  // src/mainloop.F90:350-362
-  const double co[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0}};
-  rk.c1 = co[rkstep - 1][0]; rk.c2 = co[rkstep - 1][1]; rk.c3 = co[rkstep - 1][2];
+  const int nst = g->cfg.rkscheme;
+  if (rkstep < 1 || rkstep > nst) return astr_fail_msg(nst == 4 ? "rkstep must be 1..4" : "rkstep must be 1..3");
+  rk.scheme = nst; rk.last = (rkstep == nst); rk.rhsav = nullptr;
+  if (nst == 4) {
+    // src/mainloop.F90:368-376
+    const double co4[2][4] = {{0.5, 0.5, 1.0, 1.0 / 6.0}, {1.0, 2.0, 2.0, 1.0}};
+    rk.c1 = co4[0][rkstep - 1]; rk.c2 = co4[1][rkstep - 1]; rk.c3 = 0.0;
+    if (!g->rhsav) CUDA_OK(cudaMalloc(&g->rhsav, (size_t)5 * g->L.fstride * sizeof(double)));   // mainloop.F90:394
+    rk.rhsav = g->rhsav;
+  } else {
+    // src/mainloop.F90:350-362
+    const double co[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0}};
+    rk.c1 = co[rkstep - 1][0]; rk.c2 = co[rkstep - 1][1]; rk.c3 = co[rkstep - 1][2];
+  }
   rk.dt = dt; rk.first = (rkstep == 1);
   rk.rhs_in_g = g->rhs_in_g ? 1 : 0;
   return 0;
@@ -1188,7 +1214,7 @@ int astr_gpu_rk_stage(int rkstep, double deltat) {
 int astr_gpu_rk_steps(int nsteps, double deltat) {
   NEED_CTX();
   for (int s = 0; s < nsteps; ++s)
-    for (int rk = 1; rk <= 3; ++rk) TRY(astr_gpu_rk_stage(rk, deltat));
+    for (int rk = 1; rk <= g->cfg.rkscheme; ++rk) TRY(astr_gpu_rk_stage(rk, deltat));
   return 0;
 }
 

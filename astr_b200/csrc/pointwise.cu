@@ -295,7 +295,7 @@ __global__ void k_visc_flux(const Layout L, double* __restrict__ pool, const The
 }
 
 // ---------------------------------------------------------------------------------
-// RK3-TVD update (src/mainloop.F90:427-476) fused with updatefvar (src/fludyna.F90:191)
+// RK3-TVD / RK4 update (src/mainloop.F90:427-476) fused with updatefvar (src/fludyna.F90:191)
 // ---------------------------------------------------------------------------------
 __global__ void k_rk_update(const Layout L, double* __restrict__ pool, const Thermo th, const RkCoef rk,
                             const double* __restrict__ src) {
@@ -322,7 +322,18 @@ __global__ void k_rk_update(const Layout L, double* __restrict__ pool, const The
       rhs = pool[(S_QRHS + m) * fs + x];
     // src_chan (src/solver.F90:341-352), still pending when qrhs lives in the G slots
     if (src != nullptr && m > 0) rhs = rhs + src[m - 1] * jac;
-    const double vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * rhs * rk.dt;
+    double vv;
+    if (rk.scheme == 4) {
+      double* av = rk.rhsav + m * fs + x;
+      if (!rk.last) {
+        vv = qs + rk.c1 * rk.dt * rhs;
+        *av = rk.first ? rk.c2 * rhs : *av + rk.c2 * rhs;       // rhsav = 0 at rkstep 1 (mainloop.F90:436)
+      } else {
+        vv = qs + rk.c1 * rk.dt * (rhs + *av);
+      }
+    } else {
+      vv = rk.c1 * qs + rk.c2 * q * jac + rk.c3 * rhs * rk.dt;
+    }
     pool[(S_Q + m) * fs + x] = vv / jac;
   }
   if (rk.with_fvar) q2fvar_node(pool, fs, x, th);
@@ -784,9 +795,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 // Window order (both sides agree on it): DIR 0: [field][k][j][plane], plane fastest, so that the strided gather of
-// an i face touches each sector once; DIR 1, 2: [field][p2][plane][i], i fastest.  One CTA per window row (the
-// (field, k) row of np*n1 values for DIR 0, the (field, p2, plane) row of n1 values otherwise): the index
-// arithmetic is per CTA, the threads run along the row.
+// an i face touches each sector once; DIR 1, 2: [field][p2][plane][i], i fastest.  One CTA per (field, p2) slice
+// of np * n1 contiguous window values (5 130 CTAs of ~20 KB for a 5-field 513^2 face pair; round 1 ran 77 000 CTAs
+// of 2 KB, each paying the flag poll, the system fence and the counter): the threads run along the slice, so every
+// warp instruction stores 256 contiguous bytes into the neighbour's window.
 template <int DIR, bool SEND>
 __global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList fl, const XArgs a) {
   const int side = blockIdx.z;
@@ -809,40 +821,43 @@ __global__ void __launch_bounds__(256) k_xface(const Layout L, const FieldList f
   const int n2 = (DIR == 2) ? L.jm + 1 : L.km + 1;
   const int np = a.l1 - a.l0 + 1;
   const int dm = (DIR == 0) ? L.im : (DIR == 1 ? L.jm : L.km);
-  const int p1 = blockIdx.x * 256 + threadIdx.x;
+  // one CTA per (field, p2, side): np * n1 values, contiguous in the window
+  const int p2 = blockIdx.x, fld = blockIdx.y;
+  double* __restrict__ f = fl.f[fld];
+  const long long wb = ((long long)fld * n2 + p2) * (long long)n1 * np;
   if (DIR == 0) {
-    const int p2 = blockIdx.y % n2, fld = blockIdx.y / n2;
-    if (p1 < n1) {
-      double* f = fl.f[fld];
-      const long long wb = (((long long)fld * n2 + p2) * n1 + p1) * np;
-#pragma unroll 6
-      for (int lr = 0; lr < np; ++lr) {
-        const int l = a.l0 + lr;
-        const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
-        const long long x = L.idx(node, p1, p2);
-        if (SEND) xs.remote[wb + lr] = f[x];
-        else {
-          double v = __ldcg(xs.local + wb + lr);
-          if (l == 0) v = 0.5 * (f[x] + v);
-          f[x] = v;
-        }
-      }
-    }
-  } else {
-    const int lr = blockIdx.y % np;
-    const int r2 = blockIdx.y / np;
-    const int p2 = r2 % n2, fld = r2 / n2;
-    if (p1 < n1) {
-      double* f = fl.f[fld];
+    // thread t moves window element t = j * np + plane: consecutive threads write consecutive window addresses
+    // (dense 256-byte remote stores per warp instruction) and read the np neighbouring nodes of a few rows
+    const int total = n1 * np;
+    const int dj = 256 / np, dl = 256 - dj * np;
+    int j = threadIdx.x / np, lr = threadIdx.x - j * np;
+    for (int t = threadIdx.x; t < total; t += 256) {
       const int l = a.l0 + lr;
       const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
-      const long long x = (DIR == 1) ? L.idx(p1, node, p2) : L.idx(p1, p2, node);
-      const long long bi = (((long long)fld * n2 + p2) * np + lr) * n1 + p1;
-      if (SEND) xs.remote[bi] = f[x];
+      const long long x = L.idx(node, j, p2);
+      if (SEND) xs.remote[wb + t] = f[x];
       else {
-        double v = __ldcg(xs.local + bi);
+        double v = __ldcg(xs.local + wb + t);
         if (l == 0) v = 0.5 * (f[x] + v);
         f[x] = v;
+      }
+      j += dj; lr += dl;
+      if (lr >= np) { lr -= np; ++j; }
+    }
+  } else {
+    for (int lr = 0; lr < np; ++lr) {
+      const int l = a.l0 + lr;
+      const int node = SEND ? (side ? dm - l : l) : (side ? dm + l : -l);
+      const long long x0 = (DIR == 1) ? L.idx(0, node, p2) : L.idx(0, p2, node);
+      const long long bi = wb + (long long)lr * n1;
+#pragma unroll 3
+      for (int i = threadIdx.x; i < n1; i += 256) {
+        if (SEND) xs.remote[bi + i] = f[x0 + i];
+        else {
+          double v = __ldcg(xs.local + bi + i);
+          if (l == 0) v = 0.5 * (f[x0 + i] + v);
+          f[x0 + i] = v;
+        }
       }
     }
   }
@@ -1051,8 +1066,9 @@ static int xface_launch(const Layout& L, const FieldList& fl, int dir, const XAr
   const int n1 = (dir == 0) ? L.jm + 1 : L.im + 1;
   const int n2 = (dir == 2) ? L.jm + 1 : L.km + 1;
   const int np = a.l1 - a.l0 + 1;
-  // one CTA per window row segment of 256 values, both sides in one launch
-  dim3 grid((n1 + 255) / 256, (dir == 0) ? fl.nf * n2 : fl.nf * n2 * np, 2);
+  // one CTA per (field, p2) slice of a window (np * n1 values), both sides in one launch
+  dim3 grid(n2, fl.nf, 2);
+  (void)n1; (void)np;
   if (dir == 0) k_xface<0, SEND><<<grid, 256, 0, st>>>(L, fl, a);
   else if (dir == 1) k_xface<1, SEND><<<grid, 256, 0, st>>>(L, fl, a);
   else k_xface<2, SEND><<<grid, 256, 0, st>>>(L, fl, a);

@@ -61,7 +61,10 @@ int pw_visc_flux(const Layout& L, double* pool, const Thermo& th, const FluxRang
                  cudaStream_t st);
 int pw_flux(const Layout& L, double* pool, const Box& b, int dmask, const FluxRanges& fr, int diffterm,
             cudaStream_t st);
-struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; };
+// scheme 3: q = (c1 qsave + c2 q jac + c3 dt qrhs) / jac (src/mainloop.F90:441-450)
+// scheme 4: stages 1-3 q = (qsave + c1 dt qrhs) / jac, rhsav += c2 qrhs; stage 4 (last) q = (qsave + c1 dt (qrhs + rhsav)) / jac
+//           (src/mainloop.F90:452-476); rhsav: 5 fields of the common Layout
+struct RkCoef { double c1, c2, c3, dt; int first; int with_fvar; int rhs_in_g; int scheme; int last; double* rhsav; };
 // src: device (force(1:3), force.ubulk) of src_chan still to be added, or nullptr
 int pw_sum_qrhs(const Layout& L, double* pool, const double* src, cudaStream_t st);
 int pw_bulk(const Layout& L, const double* pool, const double* yc, double* partial, double* out4, cudaStream_t st);

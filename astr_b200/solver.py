@@ -65,7 +65,7 @@ class RhsEngine:
                  lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
                  conschm_explicit: bool = False, legacy_sweep: bool = False, overlap_visc: bool = False,
                  xchg_nccl: bool = False, xchg_timeout_ms: int = 0,
-                 freestream: Sequence[float] = (1.0, 0.0, 0.0, 1.0)):
+                 freestream: Sequence[float] = (1.0, 0.0, 0.0, 1.0), rkscheme: int = 3):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -90,6 +90,7 @@ class RhsEngine:
         c.my_rank = block.rank
         # conschm/difschm '643c' (compact_central) or '642e' (explicit_central), comsolver.F90:76-84
         c.conschm, c.difschm, c.scheme_compact, c.rkscheme = (642, 642, 0, 3) if explicit else (643, 643, 1, 3)
+        c.rkscheme = int(rkscheme)   # 3: 'rk3', 4: 'rk4' (src/mainloop.F90:348-388)
         if conschm is not None:      # e.g. 543: upwind compact convection (convrsdcmp) over difschm
             c.conschm = int(conschm)
         c.recon_schem, c.lchardecomp, c.bfacmpld, c.shkcrt = int(recon_schem), int(lchardecomp), bfacmpld, shkcrt

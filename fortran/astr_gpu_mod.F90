@@ -201,8 +201,9 @@ module astr_gpu_mod
                            prandtl,gamma,ref_tem,const,tempconst,tempconst1,deltat, &
                            device,flowtype,conschm,difschm,bctype,twall, &
                            recon_schem,lchardecomp,bfacmpld,shkcrt,pinf,ndims,nondimen, &
-                           uinf,vinf,winf,roinf)
+                           uinf,vinf,winf,roinf,rkscheme)
     character(len=*), intent(in) :: flowtype        ! commvar flowtype: 'channel' enables src_chan
+    character(len=3), intent(in), optional :: rkscheme  ! commvar rkscheme: 'rk3' (default) or 'rk4'
     character(len=4), intent(in) :: conschm,difschm ! '643c' or '642e' (comsolver.F90:76-84)
     integer, intent(in) :: bctype(6)                ! commvar bctype(1:6)
     integer, intent(in) :: recon_schem              ! commvar recon_schem
@@ -232,6 +233,7 @@ module astr_gpu_mod
     read(conschm(1:3),*) cfg%conschm
     read(difschm(1:3),*) cfg%difschm
     cfg%scheme_compact=merge(1,0,difschm(4:4)=='c'); cfg%rkscheme=3
+    if(present(rkscheme)) cfg%rkscheme=merge(4,3,rkscheme=='rk4')
     cfg%lfilter=merge(1,0,lfilter); cfg%diffterm=merge(1,0,diffterm)
     cfg%nondimen=merge(1,0,nondimen); cfg%flowtype=merge(1,0,trim(flowtype)=='channel')
     cfg%bctype=bctype; cfg%twall=twall

@@ -56,7 +56,7 @@ typedef struct astr_cfg {
                                  543: upwind compact convrsdcmp (src/solver.F90:1271)   */
   int difschm;                /* 643 (compact) or 642 (explicit)                         */
   int scheme_compact;         /* difschm(4:4): 1 = 'c' compact_central, 0 = 'e' explicit */
-  int rkscheme;               /* 3 = rk3 (TVD), src/mainloop.F90:350-362                 */
+  int rkscheme;               /* 3 = rk3 (TVD), 4 = rk4: src/mainloop.F90:348-388        */
   int lfilter;                /* filterq enabled                                         */
   int diffterm;               /* viscous terms enabled                                   */
   int nondimen;               /* 1 nondimensional; 0 SI units with rgas=287.1, cp, cv as

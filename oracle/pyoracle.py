@@ -102,6 +102,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_pinf.argtypes = [vp]
         L.oracle_case_pinf.restype = cd
         L.oracle_case_set_scheme.argtypes = [vp, ci]
+        L.oracle_case_set_rkscheme.argtypes = [vp, ci]
+        L.oracle_case_set_rkscheme.restype = ci
         L.oracle_case_set_upwind.argtypes = [vp, ci, ci, cd, cd]
         L.oracle_case_set_upwind_explicit.argtypes = [vp, ci, ci, cd, cd]
         L.oracle_case_convrsduwd.argtypes = [vp]
@@ -345,6 +347,11 @@ class Case:
 
     def set_scheme(self, explicit: bool):
         lib().oracle_case_set_scheme(self._h, int(explicit))
+
+    def set_rkscheme(self, scheme: int):
+        """3: 'rk3' (default), 4: 'rk4' (src/mainloop.F90:348-388)."""
+        if lib().oracle_case_set_rkscheme(self._h, int(scheme)) != 0:
+            raise ValueError("rkscheme must be 3 or 4")
 
     def boucon(self):
         if lib().oracle_case_boucon(self._h) != 0:

@@ -28,6 +28,7 @@ struct Block {
   CompactScheme fds[3], fil[3];
   Field x[3], q[5], rho, vel[3], prs, tmp, jacob, dxi[3][3];
   Field qrhs[5], qsave[5], dvel[3][3], dtmp[3], sigma[6], qflux[3], vor[3];
+  Field rhsav[5];      // rk4 only (src/mainloop.F90:394), allocated by oracle_case_set_rkscheme
   // spongefilter_layer (src/sponge_layer.F90:67-319): per face (i0, im, j0, jm, k0, km) the node range of the
   // layer along the face direction on this block (beg<0: none here) and sponge_damp_coef over the box
   // [beg:end] x [s:e] x [s:e] in Fortran order
@@ -45,6 +46,7 @@ struct Case {
   double alfa_filter = 0.49, deltat = 1e-3, time = 0.0;
   int nstep = 0;
   int nthreads = 0;
+  int rkscheme = 3;          // 3: 'rk3' (TVD), 4: 'rk4' (src/mainloop.F90:348-388)
   Thermo th;
   FilterCoef fc;
   std::vector<Block> blk;
@@ -1040,6 +1042,29 @@ static void statcal(Case& c) {
 
 // RK update, src/mainloop.F90:441-476
 static void rk_update(Case& c, int rkstep /*1-based*/) {
+  if (c.rkscheme == 4) {
+    // src/mainloop.F90:368-376 (coefficients), :452-476 (update); rhsav is zeroed at rkstep 1 (:436)
+    static const double rk4coe[2][4] = {{0.5, 0.5, 1.0, num1d6}, {1.0, 2.0, 2.0, 1.0}};
+    const double c1 = rk4coe[0][rkstep - 1], c2 = rk4coe[1][rkstep - 1];
+    for (Block& b : c.blk)
+      for (int m = 0; m < 5; ++m) {
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int k = 0; k <= b.km; ++k)
+          for (int j = 0; j <= b.jm; ++j)
+            for (int i = 0; i <= b.im; ++i) {
+              if (rkstep == 1) b.rhsav[m](i, j, k) = 0.0;
+              if (rkstep <= 3) {
+                double v = b.qsave[m](i, j, k) + c1 * c.deltat * b.qrhs[m](i, j, k);
+                b.q[m](i, j, k) = v / b.jacob(i, j, k);
+                b.rhsav[m](i, j, k) = b.rhsav[m](i, j, k) + c2 * b.qrhs[m](i, j, k);
+              } else {
+                double v = b.qsave[m](i, j, k) + c1 * c.deltat * (b.qrhs[m](i, j, k) + b.rhsav[m](i, j, k));
+                b.q[m](i, j, k) = v / b.jacob(i, j, k);
+              }
+            }
+      }
+    return;
+  }
   static const double rkcoe[3][3] = {{1.0, 0.0, 1.0}, {0.75, 0.25, 0.25}, {num1d3, num2d3, num2d3}};
   const double c1 = rkcoe[rkstep - 1][0], c2 = rkcoe[rkstep - 1][1], c3 = rkcoe[rkstep - 1][2];
   for (Block& b : c.blk)
@@ -1309,6 +1334,16 @@ int oracle_chardecomp(double gamma, const double* l /*ro,p,E,vel3,ddi3*/, const 
 void oracle_case_set_scheme(void* h, int explicit_scheme) {
   static_cast<Case*>(h)->scheme_kind = explicit_scheme ? 'e' : 'c';
 }
+// rkscheme 'rk3' / 'rk4' (src/mainloop.F90:348-388)
+int oracle_case_set_rkscheme(void* h, int scheme) {
+  Case* c = static_cast<Case*>(h);
+  if (scheme != 3 && scheme != 4) return 1;
+  c->rkscheme = scheme;
+  if (scheme == 4)
+    for (Block& b : c->blk)
+      for (int m = 0; m < 5; ++m) { b.rhsav[m] = b.qsave[m]; std::fill(b.rhsav[m].v.begin(), b.rhsav[m].v.end(), 0.0); }
+  return 0;
+}
 void oracle_case_set_flags(void* h, int lfilter, int diffterm) {
   Case* c = static_cast<Case*>(h);
   c->lfilter = lfilter; c->diffterm = diffterm;
@@ -1395,7 +1430,7 @@ void oracle_case_reduce(void* h, int what, double* out) {
 int oracle_case_run(void* h, int nsteps) {
   Case* c = static_cast<Case*>(h);
   for (int s = 0; s < nsteps; ++s) {
-    for (int rk = 1; rk <= 3; ++rk) rk_stage(*c, rk);
+    for (int rk = 1; rk <= c->rkscheme; ++rk) rk_stage(*c, rk);
     c->nstep += 1;
     c->time = c->time + c->deltat;
   }

@@ -251,6 +251,20 @@ def test_rk_stage(pair):
         np.testing.assert_array_equal(core(eng.get("lshock")), core(c.get("lshock")))
 
 
+@pytest.mark.parametrize("explicit", [False, True])
+def test_rk4_stages(oracle, explicit):
+    # rkscheme='rk4' (src/mainloop.F90:368-386, :452-476): four stages with the rhsav accumulation; the explicit
+    # scheme keeps qrhs in its own array (the compact one in the G slots), so both placements of the update run
+    c, eng = make_pair(oracle, n=(32, 36, 28), stretch=True, explicit=explicit, engine_kw=dict(rkscheme=4))
+    c.set_rkscheme(4)
+    for rk in (1, 2, 3, 4):
+        c.rk_stage(rk); eng.rk_stage(rk)
+        assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what=f"rk4 stage {rk}")
+    with pytest.raises(Exception):
+        eng.rk_stage(5)
+    eng.close(); c.close()
+
+
 def test_five_steps_and_history(oracle):
     c, eng = make_pair(oracle, n=(48, 48, 48), perturb=0.0)
     hist = []

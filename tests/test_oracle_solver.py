@@ -60,6 +60,38 @@ def test_stage_operators_compose_to_rk_stage(oracle):
     a.close(); b.close()
 
 
+def test_rk4_is_the_classical_scheme(oracle):
+    """rkscheme='rk4' (src/mainloop.F90:368-386, :452-476): q_new = (qsave + dt/6 (k1 + 2 k2 + 2 k3 + k4)) / jacob with
+    k_i the qrhs of stage i."""
+    n = 16
+    c = oracle.Case(n, n, n, deltat=2e-3)
+    c.set_flags(lfilter=False, diffterm=True)
+    c.set_rkscheme(4)
+    c.gridgeom(); c.tgvini()
+    ks = []
+    for rk in (1, 2, 3, 4):
+        c.rk_stage(rk)
+        ks.append([c.get(f"qrhs{m + 1}")[5:-5, 5:-5, 5:-5].copy() for m in range(5)])
+        if rk == 1:
+            qsave = [c.get(f"qsave{m + 1}")[5:-5, 5:-5, 5:-5].copy() for m in range(5)]
+    jac = c.get("jacob")[5:-5, 5:-5, 5:-5]
+    for m in range(5):
+        want = (qsave[m] + 2e-3 / 6.0 * (ks[0][m] + 2 * ks[1][m] + 2 * ks[2][m] + ks[3][m])) / jac
+        got = c.get(f"q{m + 1}")[5:-5, 5:-5, 5:-5]
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    c.close()
+
+    # and a full step through oracle_case_run takes the four stages
+    a = oracle.Case(n, n, n, deltat=2e-3); b = oracle.Case(n, n, n, deltat=2e-3)
+    for x in (a, b):
+        x.set_flags(lfilter=False, diffterm=True); x.set_rkscheme(4); x.gridgeom(); x.tgvini()
+    a.run(1)
+    for rk in (1, 2, 3, 4):
+        b.rk_stage(rk)
+    np.testing.assert_array_equal(a.get("q5"), b.get("q5"))
+    a.close(); b.close()
+
+
 def _channel_case(oracle, n=(24, 32, 16), explicit=False, blocks=(1, 1, 1)):
     """examples/Channel/datin/input.chl at reduced size (see tests/gpu_common.py)."""
     sys_path_tests()
