@@ -172,6 +172,15 @@ struct Ctx {
   Thermo th;
   double* pool = nullptr;        // S_CORE fields
   double* scr = nullptr;         // 15 scratch fields, lazily allocated
+  // crash control (src/mainloop.F90:709-1198)
+  double* crinod = nullptr;      // critical nodes as 0/1, one field; nullptr until the crash control is first used
+  double* bak[2] = {nullptr, nullptr};   // databakup: dat_a%q, dat_b%q (5 fields each)
+  int bak_counter[2] = {0, 0};
+  char datpnt = 'o';
+  unsigned long long* d_count = nullptr; // device counters (2)
+  long long* d_list = nullptr;           // crashfix: keys of the flagged nodes
+  bool spg_global = false;       // spg_def='circl'
+  double* spg_global_coef = nullptr;
   double* rhsav = nullptr;       // rk4: 5 fields (src/mainloop.F90:394), allocated at the first rk4 update
   HostOp fd[3], fl[3];
   HostOp fxp[3], fxm[3];         // flux_uw_* / flux_dw_* (conschm 543 only)
@@ -190,7 +199,7 @@ struct Ctx {
   double force[3] = {0, 0, 0};
   double* ycoord = nullptr;      // x(:,:,:,2) for src_chan (flowtype channel only)
   struct Sponge { bool on = false; int beg = -1, end = -2; double* coef = nullptr; } spg[6];   // i0, im, j0, jm, k0, km
-  bool any_sponge() const { for (const Sponge& s : spg) if (s.on) return true; return false; }
+  bool any_sponge() const { if (spg_global) return true; for (const Sponge& s : spg) if (s.on) return true; return false; }
   double* stage = nullptr;       // dense host-layout staging field of the upload path
   double* d_inflow = nullptr;    // vel_in(0:jm,0:km,3) | tmp_in(0:jm,0:km) | tmp_prof(0:jm)  (bctype(1)=11)
   double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
@@ -693,6 +702,11 @@ int astr_gpu_finalize(void) {
   if (g->pool) cudaFree(g->pool);
   if (g->scr) cudaFree(g->scr);
   if (g->rhsav) cudaFree(g->rhsav);
+  if (g->crinod) cudaFree(g->crinod);
+  for (auto& b : g->bak) if (b) cudaFree(b);
+  if (g->d_count) cudaFree(g->d_count);
+  if (g->d_list) cudaFree(g->d_list);
+  if (g->spg_global_coef) cudaFree(g->spg_global_coef);
   if (g->d_partial) cudaFree(g->d_partial);
   if (g->d_out2) cudaFree(g->d_out2);
   if (g->d_src) cudaFree(g->d_src);
@@ -777,8 +791,16 @@ static int api_slot(int field_id, int* slot) {
   return 0;
 }
 
+static int ensure_crinod();
+
 int astr_gpu_get_field(int field_id, double* host) {
   NEED_CTX();
+  if (field_id == ASTR_F_CRINOD) {
+    TRY(ensure_crinod());
+    TRY(copy_dev(g->crinod, host, true));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+    return 0;
+  }
   if (field_id == ASTR_F_SSF || field_id == ASTR_F_LSHOCK) {
     if (!g->up) return astr_fail_msg("ssf/lshock exist only on the upwind convection paths");
     TRY(copy_dev(g->up + (size_t)(field_id == ASTR_F_SSF ? UP_SSF : UP_LSH) * g->L.fstride, host, true));
@@ -806,6 +828,12 @@ int astr_gpu_get_field(int field_id, double* host) {
 
 int astr_gpu_set_field(int field_id, const double* host) {
   NEED_CTX();
+  if (field_id == ASTR_F_CRINOD) {
+    TRY(ensure_crinod());
+    TRY(copy_dev(g->crinod, const_cast<double*>(host), false));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+    return 0;
+  }
   if (field_id >= ASTR_F_SSF) return astr_fail_msg("ssf/lshock are derived fields");
   int s;
   TRY(api_slot(field_id, &s));
@@ -1039,6 +1067,7 @@ static int convrsdcmp_dir(int d, int dst0, int rmw_mask) {
   ua.lee = (nt == 2 || nt == 4) ? dm : dm + ASTR_HM;
   ua.dim = dm; ua.ntype = nt; ua.lchardecomp = c.lchardecomp;
   ua.explicit_recons = c.conschm_explicit; ua.recon_schem = c.recon_schem; ua.bfacmpld = c.bfacmpld;
+  ua.crinod = g->crinod;
   // lshock exists (`allocated(lshock)`) exactly when ducrossensor runs (solver.F90:221,225)
   ua.sson = c.conschm_explicit ? (c.recon_schem == 5 || c.lchardecomp) : c.lchardecomp;
   ProfScope ps(PC_DIV_I + d);
@@ -1276,10 +1305,35 @@ int astr_gpu_set_sponge(int face, int beg, int end, const double* coef) {
   return 0;
 }
 
-// spongefilter -> spongefilter_layer (src/sponge_layer.F90:55-319)
+// spg_def='circl' (spongelayer_define_circle stays on the host, src/sponge_layer.F90:369-440): coef =
+// sponge_damp_coef(is:ie,js:je,ks:ke) of this rank, or NULL when the rank has no damped node (lsponge_loc false:
+// it still takes part in the exchange, lsponge being the global flag).  Switches spongefilter to spongefilter_global.
+int astr_gpu_set_sponge_global(const double* coef) {
+  NEED_CTX();
+  g->spg_global = true;
+  if (g->spg_global_coef) { cudaFree(g->spg_global_coef); g->spg_global_coef = nullptr; }
+  if (coef) {
+    const astr_cfg& c = g->cfg;
+    const size_t cnt = (size_t)(c.ie - c.is + 1) * (size_t)(c.je - c.js + 1) * (size_t)(c.ke - c.ks + 1);
+    CUDA_OK(cudaMalloc(&g->spg_global_coef, cnt * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(g->spg_global_coef, coef, cnt * sizeof(double), cudaMemcpyHostToDevice, g->st));
+    CUDA_OK(cudaStreamSynchronize(g->st));
+  }
+  return 0;
+}
+
+// spongefilter -> spongefilter_layer / spongefilter_global (src/sponge_layer.F90:55-364)
 int astr_gpu_spongefilter(void) {
   NEED_CTX();
   const astr_cfg& c = g->cfg;
+  if (g->spg_global) {
+    // src/sponge_layer.F90:333: dataswap(q) in every direction, then the damped 7-point average over is:ie x js:je x ks:ke
+    TRY(dataswap(fields(S_Q, 5), -1));
+    if (!g->spg_global_coef) return 0;
+    Box b = {{c.is, c.js, c.ks}, {c.ie, c.je, c.ke}};
+    ProfScope ps(PC_FVAR);
+    return pw_sponge(g->L, g->pool, b, g->spg_global_coef, g->st);
+  }
   static const int faces[5] = {0, 1, 3, 4, 5};
   const FieldList fq = fields(S_Q, 5);
   for (int f : faces) {
@@ -1293,6 +1347,114 @@ int astr_gpu_spongefilter(void) {
     ProfScope ps(PC_FVAR);
     TRY(pw_sponge(g->L, g->pool, b, sp.coef, g->st));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// crash control (lcracon), src/mainloop.F90:709-1198
+// ---------------------------------------------------------------------------------
+constexpr long long CRASHFIX_CAP = 1 << 20;       // flagged nodes one crashfix call can repair
+static int ensure_crinod() {
+  if (!g->crinod) {
+    CUDA_OK(cudaMalloc(&g->crinod, (size_t)g->L.fstride * sizeof(double)));
+    CUDA_OK(cudaMemsetAsync(g->crinod, 0, (size_t)g->L.fstride * sizeof(double), g->st));   // crinod=.false., :81
+  }
+  if (!g->d_count) CUDA_OK(cudaMalloc(&g->d_count, 2 * sizeof(unsigned long long)));
+  return 0;
+}
+static int read_count(int which, long long* out) {
+  unsigned long long v = 0;
+  CUDA_OK(cudaMemcpyAsync(&v, g->d_count + which, sizeof v, cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  *out = (long long)v;
+  return 0;
+}
+
+// crashcheck (:709-768), the detection: *nbad = nodes of this rank whose density is not >= 0 (now critical nodes).
+// The decision (`por`, recovery or stop, :770-812) stays with the caller.
+int astr_gpu_crashcheck(long long* nbad) {
+  NEED_CTX();
+  TRY(ensure_crinod());
+  CUDA_OK(cudaMemsetAsync(g->d_count, 0, 2 * sizeof(unsigned long long), g->st));
+  TRY(pw_crashcheck(g->L, g->pool, g->crinod, g->d_count, g->st));
+  TRY(read_count(0, nbad));
+  return p2p_check();
+}
+
+// crinod_expansion (:985-1033): *counter as the reference counts it (27 per flagged node of -1..dim+1), this rank
+int astr_gpu_crinod_expansion(long long* counter) {
+  NEED_CTX();
+  TRY(ensure_crinod());
+  CUDA_OK(cudaMemsetAsync(g->d_count, 0, 2 * sizeof(unsigned long long), g->st));
+  TRY(pw_crinod_dilate(g->L, g->crinod, g->slot(S_QRHS), g->d_count, g->st));      // qrhs is dead between steps
+  FieldList fl; fl.nf = 1; fl.f[0] = g->crinod;
+  TRY(dataswap(fl, -1));
+  if (counter) TRY(read_count(0, counter));
+  return 0;
+}
+
+// databakup (:826-972).  mode 0 'backup', 1 'recovery': two alternating device copies of q.  *slot = copy used
+// (0 dat_a, 1 dat_b): the caller keeps / restores its own scalars (nstep, time, massflux, force ...) per copy;
+// *recover_counter = recover_counter of that copy after this call.  A recovery also runs updatefvar and, from the
+// second recovery of a copy on, crinod_expansion.
+int astr_gpu_databakup(int mode, int* slot, int* recover_counter) {
+  NEED_CTX();
+  const size_t bytes = (size_t)5 * g->L.fstride * sizeof(double);
+  if (mode == 0) {
+    if (g->datpnt == 'o') g->datpnt = 'a';
+    const int s = g->datpnt == 'a' ? 0 : 1;
+    if (!g->bak[s]) CUDA_OK(cudaMalloc(&g->bak[s], bytes));
+    CUDA_OK(cudaMemcpyAsync(g->bak[s], g->slot(S_Q), bytes, cudaMemcpyDeviceToDevice, g->st));
+    g->bak_counter[s] = 0;
+    g->datpnt = s == 0 ? 'b' : 'a';
+    if (slot) *slot = s;
+    if (recover_counter) *recover_counter = 0;
+    return 0;
+  }
+  if (mode != 1) return astr_fail_msg("databakup: mode must be 0 (backup) or 1 (recovery)");
+  if (g->datpnt == 'o') return astr_fail_msg("databakup: no backup data available");
+  const int s = g->datpnt == 'a' ? 0 : 1;
+  // after a single backup datpnt points at the copy that was never written (the reference then reads an
+  // unallocated array, :941)
+  if (!g->bak[s]) return astr_fail_msg("databakup: no backup data available");
+  Box b = {{0, 0, 0}, {g->L.im, g->L.jm, g->L.km}};
+  TRY(pw_copy_box(g->L, g->slot(S_Q), g->bak[s], 5, b, g->st));       // q(0:im,0:jm,0:km,:) only
+  g->bak_counter[s] += 1;
+  g->datpnt = s == 0 ? 'b' : 'a';
+  if (slot) *slot = s;
+  if (recover_counter) *recover_counter = g->bak_counter[s];
+  TRY(astr_gpu_updatefvar());
+  if (g->bak_counter[s] > 1) TRY(astr_gpu_crinod_expansion(nullptr));
+  return 0;
+}
+
+// crashfix (:1045-1198): *nfixed = nodes of this rank that were wiped (the psum and the report stay with the caller);
+// ig0, jg0: global index of the block's node 0 (module parallel), for the domain test of the neighbours (:1108-1110)
+int astr_gpu_crashfix(int ig0, int jg0, long long* nfixed) {
+  NEED_CTX();
+  TRY(ensure_crinod());
+  if (!g->d_list) CUDA_OK(cudaMalloc(&g->d_list, CRASHFIX_CAP * sizeof(long long)));
+  CUDA_OK(cudaMemsetAsync(g->d_count, 0, 2 * sizeof(unsigned long long), g->st));
+  const double eps_rho = 1.0e-5, eps_tmp = 1.0e-5;
+  // thermal(density=eps_rho,temperature=eps_tmp), src/fludyna.F90:45-88
+  const double eps_prs = g->th.nondimen ? eps_rho * eps_tmp / g->th.const2 : eps_rho * eps_tmp * g->th.rgas;
+  TRY(pw_crashfix_flag(g->L, g->pool, g->crinod, eps_rho, eps_prs, eps_tmp, g->d_count, g->d_list, CRASHFIX_CAP, g->st));
+  long long n = 0;
+  TRY(read_count(0, &n));
+  *nfixed = 0;
+  if (n == 0) return 0;
+  if (n > CRASHFIX_CAP) return astr_fail_msg("crashfix: more than 2^20 nodes of this rank have non-positive density, pressure or temperature");
+  // storage order (i fastest), as the reference's loop visits them
+  std::vector<long long> keys((size_t)n);
+  CUDA_OK(cudaMemcpyAsync(keys.data(), g->d_list, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  std::sort(keys.begin(), keys.end());
+  CUDA_OK(cudaMemcpyAsync(g->d_list, keys.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, g->st));
+  CrashFixArgs a;
+  const astr_cfg& c = g->cfg;
+  a.g0[0] = ig0; a.g0[1] = jg0; a.g0[2] = 0; a.ia = c.ia; a.ja = c.ja; a.n = n;
+  TRY(pw_crashfix_apply(g->L, g->pool, g->th, g->d_list, a, g->d_count + 1, g->st));
+  TRY(read_count(1, nfixed));
   return 0;
 }
 

@@ -770,6 +770,95 @@ __global__ void k_sponge(const Layout L, double* __restrict__ pool, const Box b,
 }
 
 // ---------------------------------------------------------------------------------
+// crash control (lcracon), src/mainloop.F90:709-1198.  nodestat <= 0 everywhere (no immersed body).
+// ---------------------------------------------------------------------------------
+// crashcheck (:725-768): fluid nodes whose density is not >= 0 become critical nodes
+__global__ void k_crashcheck(const Layout L, const double* __restrict__ pool, double* __restrict__ crinod,
+                             unsigned long long* __restrict__ count) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long x = L.idx(i, j, k);
+  if (!(pool[S_Q * L.fstride + x] >= 0.0)) { crinod[x] = 1.0; atomicAdd(count, 1ull); }
+}
+// crinod_expansion (:985-1033): every flagged node of -1..dim+1 flags its 27-neighbourhood; count = 27 x flagged
+template <bool COPYBACK>
+__global__ void k_crinod_dilate(const Layout L, double* __restrict__ crinod, double* __restrict__ tmp,
+                                unsigned long long* __restrict__ count) {
+  Box b = {{-2, -2, -2}, {L.im + 2, L.jm + 2, L.km + 2}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long x = L.idx(i, j, k);
+  if (COPYBACK) { crinod[x] = tmp[x]; return; }
+  bool any = false;
+  for (int kk = -1; kk <= 1; ++kk)
+    for (int jj = -1; jj <= 1; ++jj)
+      for (int ii = -1; ii <= 1; ++ii) {
+        const int i1 = i + ii, j1 = j + jj, k1 = k + kk;
+        if (i1 < -1 || i1 > L.im + 1 || j1 < -1 || j1 > L.jm + 1 || k1 < -1 || k1 > L.km + 1) continue;
+        any = any || (crinod[L.idx(i1, j1, k1)] != 0.0);
+      }
+  tmp[x] = any ? 1.0 : 0.0;
+  if (i >= -1 && i <= L.im + 1 && j >= -1 && j <= L.jm + 1 && k >= -1 && k <= L.km + 1 && crinod[x] != 0.0)
+    atomicAdd(count, 27ull);
+}
+// crashfix (:1084-1095), detection: rho / prs / tmp under eps; the repairs follow in storage order (k_crashfix_apply)
+__global__ void k_crashfix_flag(const Layout L, const double* __restrict__ pool, double* __restrict__ crinod,
+                                const double eps_rho, const double eps_prs, const double eps_tmp,
+                                unsigned long long* __restrict__ count, long long* __restrict__ list, const long long cap) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  if (pool[S_RHO * fs + x] >= eps_rho && pool[S_PRS * fs + x] >= eps_prs && pool[S_TMP * fs + x] >= eps_tmp) return;
+  crinod[x] = 1.0;
+  const unsigned long long slot = atomicAdd(count, 1ull);
+  if ((long long)slot < cap) list[slot] = (long long)i + (long long)(L.im + 1) * ((long long)j + (long long)(L.jm + 1) * k);
+}
+// crashfix (:1096-1140), repairs: one thread walks the sorted list, so that a later node sees the earlier repairs
+// exactly as the reference's i-fastest loop does.  The list is empty in a healthy run and short in a sick one.
+__global__ void k_crashfix_apply(const Layout L, double* __restrict__ pool, const Thermo th,
+                                 const long long* __restrict__ list, const CrashFixArgs a,
+                                 unsigned long long* __restrict__ fixed) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long fs = L.fstride;
+  unsigned long long counter = 0;
+  for (long long t = 0; t < a.n; ++t) {
+    const long long key = list[t];
+    const int i = (int)(key % (L.im + 1)), j = (int)((key / (L.im + 1)) % (L.jm + 1)), k = (int)(key / ((long long)(L.im + 1) * (L.jm + 1)));
+    double qavg[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int norm = 0;
+    for (int kk = -1; kk <= 1; ++kk)
+      for (int jj = -1; jj <= 1; ++jj)
+        for (int ii = -1; ii <= 1; ++ii) {
+          if (ii == 0 && jj == 0 && kk == 0) continue;
+          if (a.g0[0] + i + ii < 0 || a.g0[0] + i + ii > a.ia || a.g0[1] + j + jj < 0 || a.g0[1] + j + jj > a.ja) continue;
+          const long long y = L.idx(i + ii, j + jj, k + kk);
+          if (pool[S_RHO * fs + y] >= 0.0 && pool[S_PRS * fs + y] >= 0.0 && pool[S_TMP * fs + y] >= 0.0) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) qavg[m] = qavg[m] + pool[(S_Q + m) * fs + y];
+            norm += 1;
+          }
+        }
+    if (norm >= 1) {
+      const long long x = L.idx(i, j, k);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) pool[(S_Q + m) * fs + x] = qavg[m] / (double)norm;
+      q2fvar_node(pool, fs, x, th);
+      counter += 1;
+    }
+  }
+  *fixed = counter;
+}
+// nf fields of the common Layout, nodes of a box only (databakup restores q(0:im,0:jm,0:km,:), :941)
+__global__ void k_copy_box(const Layout L, double* __restrict__ dst, const double* __restrict__ src, const int nf, const Box b) {
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long x = L.idx(i, j, k);
+  for (int m = 0; m < nf; ++m) dst[m * L.fstride + x] = src[m * L.fstride + x];
+}
+
+// ---------------------------------------------------------------------------------
 // Fused pack + peer-to-peer halo exchange (replaces pack -> ncclSend/Recv -> unpack).
 // SEND: every CTA first waits until the neighbour has consumed what this rank wrote into the
 // neighbour's receive window last time (ack flag, written by the neighbour into THIS rank's
@@ -984,6 +1073,40 @@ int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st) {
 int pw_repitch(const Layout& L, const double* stage, double* field, cudaStream_t st) {
   dim3 grid((L.im + 1 + 2 * ASTR_HM + PW_T - 1) / PW_T, L.njt, L.nkt);
   k_repitch<<<grid, PW_T, 0, st>>>(L, stage, field);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_crashcheck(const Layout& L, const double* pool, double* crinod, unsigned long long* count, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_crashcheck<<<box_grid(b), PW_T, 0, st>>>(L, pool, crinod, count);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_crinod_dilate(const Layout& L, double* crinod, double* tmp, unsigned long long* count, cudaStream_t st) {
+  Box b = {{-2, -2, -2}, {L.im + 2, L.jm + 2, L.km + 2}};
+  k_crinod_dilate<false><<<box_grid(b), PW_T, 0, st>>>(L, crinod, tmp, count);
+  LAUNCH_CHECK();
+  k_crinod_dilate<true><<<box_grid(b), PW_T, 0, st>>>(L, crinod, tmp, count);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_crashfix_flag(const Layout& L, const double* pool, double* crinod, double eps_rho, double eps_prs, double eps_tmp,
+                     unsigned long long* count, long long* list, long long cap, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_crashfix_flag<<<box_grid(b), PW_T, 0, st>>>(L, pool, crinod, eps_rho, eps_prs, eps_tmp, count, list, cap);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_crashfix_apply(const Layout& L, double* pool, const Thermo& th, const long long* list, const CrashFixArgs& a,
+                      unsigned long long* fixed, cudaStream_t st) {
+  k_crashfix_apply<<<1, 32, 0, st>>>(L, pool, th, list, a, fixed);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_copy_box(const Layout& L, double* dst, const double* src, int nf, const Box& b, cudaStream_t st) {
+  if (box_empty(b)) return 0;
+  k_copy_box<<<box_grid(b), PW_T, 0, st>>>(L, dst, src, nf, b);
   LAUNCH_CHECK();
   return 0;
 }

@@ -81,6 +81,15 @@ struct BcArgs {
   const double* tmp_prof;  // device (0:jm)
 };
 int pw_repitch(const Layout& L, const double* stage, double* field, cudaStream_t st);
+// crash control (src/mainloop.F90:709-1198); crinod: one field of the common Layout holding 0/1
+int pw_crashcheck(const Layout& L, const double* pool, double* crinod, unsigned long long* count, cudaStream_t st);
+int pw_crinod_dilate(const Layout& L, double* crinod, double* tmp, unsigned long long* count, cudaStream_t st);
+int pw_crashfix_flag(const Layout& L, const double* pool, double* crinod, double eps_rho, double eps_prs, double eps_tmp,
+                     unsigned long long* count, long long* list, long long cap, cudaStream_t st);
+struct CrashFixArgs { int g0[3], ia, ja; long long n; };
+int pw_crashfix_apply(const Layout& L, double* pool, const Thermo& th, const long long* list, const CrashFixArgs& a,
+                      unsigned long long* fixed, cudaStream_t st);
+int pw_copy_box(const Layout& L, double* dst, const double* src, int nf, const Box& b, cudaStream_t st);
 int pw_sponge(const Layout& L, double* pool, const Box& b, const double* coef, cudaStream_t st);
 int pw_bcface(const Layout& L, double* pool, const Thermo& th, int dir, const BcArgs& a, cudaStream_t st);
 int pw_noslip(const Layout& L, double* pool, const Thermo& th, int dir, int side, double tw, cudaStream_t st);
@@ -134,6 +143,7 @@ struct UpwindArgs {
   int explicit_recons;  // 1: convrsduwd (explicit reconstruction recons_exp), 0: convrsdcmp (compact flux)
   int recon_schem;      // recons_exp scheme: -1, 0 (linear), 1 WENO, 2 WENO-Z, 3 MP, 5 MP-LD, 6 ROUND
   double bfacmpld;
+  const double* crinod; // critical nodes of the crash control as 0/1 (nullptr: none), src/solver.F90:1456-1481
 };
 int uw_sw_split(const Layout& L, const double* pool, double* up, const Thermo& th, int dir, int lss, int lee,
                 cudaStream_t st);

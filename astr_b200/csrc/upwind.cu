@@ -227,6 +227,15 @@ __device__ __forceinline__ bool chardecomp(const double gamma, const double ro_l
   return true;
 }
 
+// hdiss of the interface i+1/2 (src/solver.F90:1456-1462, :660-666): a critical node of the crash control on either side
+__device__ __forceinline__ bool crinod_interface(const double* crinod, long long x, long long sd, int i, int dim) {
+  if (crinod == nullptr) return false;
+  const double* cn = crinod + x;
+  if (i < 0) return cn[sd] != 0.0;
+  if (i + 1 > dim) return cn[0] != 0.0;
+  return (cn[0] != 0.0) || (cn[sd] != 0.0);
+}
+
 // ---------------------------------------------------------------------------------
 // interface loop of convrsdcmp (src/solver.F90:1359-1492 and the j/k copies)
 // ---------------------------------------------------------------------------------
@@ -263,8 +272,9 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
     else lsh = (ls[0] != 0.0) || (ls[sd] != 0.0);
   }
   const bool nolim = (a.ntype == 1 && (i == 0 || i == 1)) || (a.ntype == 2 && (i == a.dim - 1 || i == a.dim - 2));
+  const bool hdiss = crinod_interface(a.crinod, x, sd, i, a.dim);
   double Fh[5];
-  if (nolim || !lsh) {
+  if ((nolim || !lsh) && !hdiss) {
     // the limiter is off at this interface (mplimiter returns the compact value, MP5 with discont=.false. returns
     // ul): Fhc = LEV (fhcp + fhcm) and Fh = REV Fhc = fhcp + fhcm up to rounding (LEV REV = I), so the
     // eigen-decomposition and the stencil projections are skipped.  The reference does the same in convrsduwd
@@ -313,8 +323,9 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
                         e.Lm[m][4] * fcp[4];
       const double hm = e.Lm[m][0] * fcm[0] + e.Lm[m][1] * fcm[1] + e.Lm[m][2] * fcm[2] + e.Lm[m][3] * fcm[3] +
                         e.Lm[m][4] * fcm[4];
-      const double v1 = nolim ? hp : mp5(cp, hp, lsh);
-      const double v2 = nolim ? hm : mp5(cm, hm, lsh);
+      // hdiss: the projected split flux of one node instead of the limited compact value (solver.F90:1466-1471)
+      const double v1 = hdiss ? cp[3] : (nolim ? hp : mp5(cp, hp, lsh));
+      const double v2 = hdiss ? cm[3] : (nolim ? hm : mp5(cm, hm, lsh));
       Fhc[m] = v1 + v2;
     }
 #pragma unroll
@@ -323,8 +334,8 @@ __global__ void k_upwind(const Layout L, const double* __restrict__ pool, double
   } else {
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
-      const double v1 = nolim ? fcp[m] : mp5(fsp[m], fcp[m], lsh);
-      const double v2 = nolim ? fcm[m] : mp5(fsm[m], fcm[m], lsh);
+      const double v1 = hdiss ? fsp[m][3] : (nolim ? fcp[m] : mp5(fsp[m], fcp[m], lsh));
+      const double v2 = hdiss ? fsm[m][3] : (nolim ? fcm[m] : mp5(fsm[m], fcm[m], lsh));
       Fh[m] = v1 + v2;
     }
   }
@@ -352,6 +363,7 @@ __global__ void k_upwind_exp(const Layout L, const double* __restrict__ pool, do
     else lsh = (ls[0] != 0.0) || (ls[sd] != 0.0);
   }
   const bool chr = a.lchardecomp && lsh;
+  const bool hdiss = crinod_interface(a.crinod, x, sd, i, a.dim);
   Eig e;
   if (chr) {
     const long long xr = x + sd;
@@ -395,8 +407,9 @@ __global__ void k_upwind_exp(const Layout L, const double* __restrict__ pool, do
         cm[n] = up[(UP_FSW + 5 + m) * fs + x + om[n]];
       }
     }
-    const double v1 = recons_exp(cp, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
-    const double v2 = recons_exp(cm, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
+    // hdiss (solver.F90:755-759): Flcp(m,4) / Flcm(m,4)
+    const double v1 = hdiss ? cp[3] : recons_exp(cp, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
+    const double v2 = hdiss ? cm[3] : recons_exp(cm, i, a.dim, a.ntype, a.recon_schem, lsh, a.bfacmpld);
     Fhc[m] = v1 + v2;
   }
 #pragma unroll

@@ -23,7 +23,7 @@ FIELD_IDS = {
     **{f"x{n + 1}": 47 + n for n in range(3)},
     **{f"qsave{n + 1}": 50 + n for n in range(5)},
     **{f"vor{n + 1}": 55 + n for n in range(3)},
-    "ssf": 58, "lshock": 59,
+    "ssf": 58, "lshock": 59, "crinod": 60,
 }
 
 # every symbol include/astr_gpu.h declares (tests check the built library exports all)
@@ -33,7 +33,7 @@ SYMBOLS = [
     "astr_gpu_upload_state", "astr_gpu_download_state", "astr_gpu_get_field", "astr_gpu_set_field",
     "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_boucon", "astr_gpu_set_inflow", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
     "astr_gpu_rk_update", "astr_gpu_spongefilter", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps", "astr_gpu_rk_steps_timed",
-    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_reduce_cfl", "astr_gpu_reduce_channel", "astr_gpu_kernel_launches",
+    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_sponge_global", "astr_gpu_crashcheck", "astr_gpu_databakup", "astr_gpu_crinod_expansion", "astr_gpu_crashfix", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_reduce_cfl", "astr_gpu_reduce_channel", "astr_gpu_kernel_launches",
     "astr_gpu_set_profile", "astr_gpu_get_profile", "astr_gpu_bench_sweep",
 ]
 
@@ -143,6 +143,11 @@ def load() -> ctypes.CDLL:
     L.astr_gpu_set_force.argtypes = [vp]
     L.astr_gpu_set_grid.argtypes = [vp]
     L.astr_gpu_set_sponge.argtypes = [ci, ci, ci, vp]
+    L.astr_gpu_set_sponge_global.argtypes = [vp]
+    L.astr_gpu_crashcheck.argtypes = [vp]
+    L.astr_gpu_databakup.argtypes = [ci, vp, vp]
+    L.astr_gpu_crinod_expansion.argtypes = [vp]
+    L.astr_gpu_crashfix.argtypes = [ci, ci, vp]
     L.astr_gpu_set_inflow.argtypes = [vp, vp, vp]
     L.astr_gpu_reduce_tgv.argtypes = [vp]
     L.astr_gpu_reduce_cfl.argtypes = [vp]

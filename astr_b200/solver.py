@@ -206,6 +206,36 @@ class RhsEngine:
         a = np.asfortranarray(coef, dtype=np.float64) if coef is not None else None
         _l.check(self._lib.astr_gpu_set_sponge(face, beg, end, a.ctypes.data if a is not None else None))
 
+    # ---- crash control (src/mainloop.F90:709-1198) ------------------------------------------
+    def crashcheck(self) -> int:
+        """Flags the nodes whose density is not >= 0 as critical nodes (crinod); returns how many on this rank."""
+        n = ctypes.c_longlong(0)
+        _l.check(self._lib.astr_gpu_crashcheck(ctypes.byref(n)))
+        return int(n.value)
+
+    def crashfix(self) -> int:
+        """Wipes nodes with rho / prs / tmp under 1e-5 (mean of the admissible neighbours); returns how many."""
+        n = ctypes.c_longlong(0)
+        g0 = getattr(self.block, "g0", (0, 0, 0))
+        _l.check(self._lib.astr_gpu_crashfix(int(g0[0]), int(g0[1]), ctypes.byref(n)))
+        return int(n.value)
+
+    def crinod_expansion(self) -> int:
+        n = ctypes.c_longlong(0)
+        _l.check(self._lib.astr_gpu_crinod_expansion(ctypes.byref(n)))
+        return int(n.value)
+
+    def databakup(self, mode: str):
+        """'backup' / 'recovery' over two alternating device copies of q; returns (copy used, its recover_counter)."""
+        slot, cnt = ctypes.c_int(0), ctypes.c_int(0)
+        _l.check(self._lib.astr_gpu_databakup({"backup": 0, "recovery": 1}[mode], ctypes.byref(slot), ctypes.byref(cnt)))
+        return int(slot.value), int(cnt.value)
+
+    def set_sponge_global(self, coef: Optional[np.ndarray]):
+        """spg_def='circl': sponge_damp_coef(is:ie,js:je,ks:ke) (src/sponge_layer.F90:369-440), None if this rank has no damped node."""
+        a = None if coef is None else np.asfortranarray(coef, dtype=np.float64)
+        _l.check(self._lib.astr_gpu_set_sponge_global(a.ctypes.data if a is not None else None))
+
     def spongefilter(self):
         _l.check(self._lib.astr_gpu_spongefilter())
 

@@ -135,6 +135,30 @@ module astr_gpu_mod
       integer(c_int), value :: face,beg,end
       real(c_double), intent(in) :: coef(*)
     end function
+    ! crash control (src/mainloop.F90:709-1198): counts are per rank, por / psum stay with the caller
+    integer(c_int) function astr_gpu_crashcheck(nbad) bind(c,name='astr_gpu_crashcheck')
+      import :: c_int, c_long_long
+      integer(c_long_long), intent(out) :: nbad
+    end function
+    integer(c_int) function astr_gpu_databakup(mode,slot,recover_counter) bind(c,name='astr_gpu_databakup')
+      import :: c_int
+      integer(c_int), value :: mode                 ! 0 'backup', 1 'recovery'
+      integer(c_int), intent(out) :: slot,recover_counter
+    end function
+    integer(c_int) function astr_gpu_crinod_expansion(counter) bind(c,name='astr_gpu_crinod_expansion')
+      import :: c_int, c_long_long
+      integer(c_long_long), intent(out) :: counter
+    end function
+    integer(c_int) function astr_gpu_crashfix(ig0,jg0,nfixed) bind(c,name='astr_gpu_crashfix')
+      import :: c_int, c_long_long
+      integer(c_int), value :: ig0,jg0
+      integer(c_long_long), intent(out) :: nfixed
+    end function
+    ! spg_def='circl': coef = c_loc(sponge_damp_coef(is:ie,js:je,ks:ke)), c_null_ptr when lsponge_loc is false
+    integer(c_int) function astr_gpu_set_sponge_global(coef) bind(c,name='astr_gpu_set_sponge_global')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: coef
+    end function
     integer(c_int) function astr_gpu_rk_stage(rkstep,deltat) bind(c,name='astr_gpu_rk_stage')
       import :: c_int, c_double
       integer(c_int), value :: rkstep

@@ -109,7 +109,7 @@ enum {
   ASTR_F_Q = 0, ASTR_F_RHO = 5, ASTR_F_VEL = 6, ASTR_F_PRS = 9, ASTR_F_TMP = 10,
   ASTR_F_QRHS = 11, ASTR_F_JACOB = 16, ASTR_F_DXI = 17, ASTR_F_DVEL = 26,
   ASTR_F_DTMP = 35, ASTR_F_SIGMA = 38, ASTR_F_QFLUX = 44, ASTR_F_X = 47,
-  ASTR_F_QSAVE = 50, ASTR_F_VOR = 55, ASTR_F_SSF = 58, ASTR_F_LSHOCK = 59, ASTR_F_COUNT = 60
+  ASTR_F_QSAVE = 50, ASTR_F_VOR = 55, ASTR_F_SSF = 58, ASTR_F_LSHOCK = 59, ASTR_F_CRINOD = 60, ASTR_F_COUNT = 61
 };
 
 /* replaces solvrinit: builds the line operators (fd_scheme_initiate
@@ -172,6 +172,24 @@ int astr_gpu_dataswap(int field_id, int direction /*0 = all, 1..3*/);
  * along the face direction on this rank, beg<0 = the layer exists (lspg_* set) but not on this rank;
  * coef = sponge_damp_coef over [beg:end] x the is:ie / js:je / ks:ke ranges of the other two directions */
 int astr_gpu_set_sponge(int face, int beg, int end, const double* coef);
+/* spg_def='circl' (src/sponge_layer.F90:321-440): coef = sponge_damp_coef(is:ie,js:je,ks:ke) of this rank as
+ * spongelayer_define_circle leaves it (host, start-up), or NULL on a rank whose lsponge_loc is false; switches
+ * astr_gpu_spongefilter to spongefilter_global (dataswap(q) in every direction + damped 7-point average) */
+int astr_gpu_set_sponge_global(const double* coef);
+
+/* ---- crash control (lcracon), src/mainloop.F90:709-1198.  crinod lives on the device as a 0/1 field
+ * (ASTR_F_CRINOD, all zero until one of these calls sets a node); convrsdcmp / convrsduwd read it (hdiss,
+ * src/solver.F90:1456-1481, :660-759).  Counts are per rank: `por` / `psum`, the messages, the decision to stop and
+ * the scalars saved with a backup (nstep, time, massflux, force ...) stay on the host.
+ * crashcheck: *nbad = nodes with q(:,1) not >= 0 (flagged).  databakup: mode 0 'backup' / 1 'recovery' over two
+ * alternating device copies of q(0:im,0:jm,0:km,:); *slot = copy used (0 dat_a, 1 dat_b), *recover_counter = its
+ * recover_counter afterwards; a recovery runs updatefvar and, from the second recovery of a copy on,
+ * crinod_expansion.  crashfix: nodes with rho / prs / tmp under 1e-5 are flagged and replaced by the mean of their
+ * admissible neighbours in storage order; ig0, jg0 = global index of node 0 (module parallel). */
+int astr_gpu_crashcheck(long long* nbad);
+int astr_gpu_databakup(int mode, int* slot, int* recover_counter);
+int astr_gpu_crinod_expansion(long long* counter);
+int astr_gpu_crashfix(int ig0, int jg0, long long* nfixed);
 
 /* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal when
  * flowtype = 1; `force` is what massfluxchan/chanfoce (src/statistic.F90:1437-1520) keep

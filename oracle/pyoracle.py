@@ -30,7 +30,7 @@ FIELD_IDS = {
     **{f"x{n + 1}": 47 + n for n in range(3)},
     **{f"qsave{n + 1}": 50 + n for n in range(5)},
     **{f"vor{n + 1}": 55 + n for n in range(3)},
-    "ssf": 58, "lshock": 59,
+    "ssf": 58, "lshock": 59, "crinod": 60,
 }
 
 
@@ -97,6 +97,16 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_inflow.argtypes = [vp, ci, vp, vp, vp]
         L.oracle_case_set_sponge.argtypes = [vp, ci, ci, ci, ci, vp]
         L.oracle_case_spongefilter.argtypes = [vp]
+        for name in ("oracle_case_crashcheck", "oracle_case_crashfix", "oracle_case_crinod_expansion"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = ctypes.c_longlong
+        L.oracle_case_databakup.argtypes = [vp, ci]
+        L.oracle_case_databakup.restype = ci
+        L.oracle_case_nstep.argtypes = [vp]
+        L.oracle_case_nstep.restype = ci
+        L.oracle_case_set_sponge_circle.argtypes = [vp, cd, cd, cd, cd, cd]
+        L.oracle_case_sponge_circle_coef.argtypes = [vp, ci, vp]
+        L.oracle_case_sponge_circle_coef.restype = ci
         L.oracle_case_set_dimensional.argtypes = [vp, cd, cd, cd, cd]
         L.oracle_case_thermo.argtypes = [vp, vp]
         L.oracle_case_pinf.argtypes = [vp]
@@ -329,6 +339,39 @@ class Case:
 
     def spongefilter(self):
         lib().oracle_case_spongefilter(self._h)
+
+    # crash control (src/mainloop.F90:709-1198)
+    def crashcheck(self) -> int:
+        """Flags the nodes whose density is not >= 0 as critical nodes; returns how many."""
+        return int(lib().oracle_case_crashcheck(self._h))
+
+    def crashfix(self) -> int:
+        """Wipes nodes with rho / prs / tmp under 1e-5 (mean of the admissible neighbours); returns how many."""
+        return int(lib().oracle_case_crashfix(self._h))
+
+    def crinod_expansion(self) -> int:
+        return int(lib().oracle_case_crinod_expansion(self._h))
+
+    def databakup(self, mode: str):
+        """'backup' / 'recovery' (two alternating in-memory copies of q, src/mainloop.F90:826-972)."""
+        if lib().oracle_case_databakup(self._h, {"backup": 0, "recovery": 1}[mode]) != 0:
+            raise RuntimeError("no backup data available")
+
+    @property
+    def nstep(self) -> int:
+        return int(lib().oracle_case_nstep(self._h))
+
+    def set_sponge_circle(self, centre=(0.0, 0.0, 0.0), range_spange=0.06, dampfac=0.05):
+        """spg_def='circl' (src/sponge_layer.F90:369-440; the reference hard-codes these defaults)."""
+        lib().oracle_case_set_sponge_circle(self._h, *[float(v) for v in centre], float(range_spange), float(dampfac))
+
+    def sponge_circle_coef(self, ib: int = 0):
+        """sponge_damp_coef(is:ie,js:je,ks:ke) of a block, or None when the block has no damped node (lsponge_loc)."""
+        b = self.block_info(ib)
+        se = b["is_ie"]
+        shape = tuple(se[2 * d + 1] - se[2 * d] + 1 for d in range(3))
+        out = np.zeros(shape, order="F")
+        return out if lib().oracle_case_sponge_circle_coef(self._h, ib, out.ctypes.data) else None
 
     def set_dimensional(self, ref_tem: float, ref_vel: float, ref_len: float, ref_den: float):
         """nondimen=f: SI units, rgas=287.1 (src/solver.F90:124-148)."""

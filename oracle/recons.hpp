@@ -292,9 +292,11 @@ static int convrsduwd(Case& c) {
               for (int m = 0; m < 5; ++m) flcm[m][n - 1] = fswm[m][nwd];
             }
           }
+          const bool hdiss = crinod_interface(b, d, i, dm, p1, p2);       // :660-666
           for (int m = 0; m < 5; ++m) {
-            const double var1 = recons_exp(flcp[m], i, dm, nt, c.recon_schem, lsh, c.bfacmpld);
-            const double var2 = recons_exp(flcm[m], i, dm, nt, c.recon_schem, lsh, c.bfacmpld);
+            // :755-769: hdiss (critical node on either side) takes the split flux of one node
+            const double var1 = hdiss ? flcp[m][3] : recons_exp(flcp[m], i, dm, nt, c.recon_schem, lsh, c.bfacmpld);
+            const double var2 = hdiss ? flcm[m][3] : recons_exp(flcm[m], i, dm, nt, c.recon_schem, lsh, c.bfacmpld);
             Fhc[m] = var1 + var2;
           }
           if (chr) {

@@ -34,7 +34,11 @@ struct Block {
   // [beg:end] x [s:e] x [s:e] in Fortran order
   struct SpongeLayer { int beg = -1, end = -2; std::vector<double> coef; };
   SpongeLayer spg[6];
+  // spg_def='circl' (src/sponge_layer.F90:369-440): sponge_damp_coef over the whole [s:e]^3 box of the block
+  std::vector<double> spg_circ;
+  bool spg_circ_loc = false;
   Field ssf, lshock;   // ducrossensor (allocated on first use, commcal.F90:218-219); lshock as 0/1
+  Field crinod;        // critical nodes of the crash control as 0/1 (src/commarray.F90:105; mainloop.F90:81 .false.)
   int dim(int d) const { return d == 0 ? im : (d == 1 ? jm : km); }
 };
 
@@ -69,6 +73,13 @@ struct Case {
   // tmp_in(0:jm,0:km), tmp_prof(0:jm); indexed [block]
   std::vector<std::vector<double>> vel_in, tmp_in, tmp_prof;
   bool lspg[6] = {false, false, false, false, false, false};   // lspg_i0 .. lspg_km (global flags)
+  // databakup (src/mainloop.F90:826-972): two alternating in-memory copies of q with their step counters
+  struct DataBack { int nstep = 0; double time = 0.0; int recover_counter = 0; std::vector<std::vector<double>> q; };
+  DataBack dat_a, dat_b;
+  char datpnt = 'o';
+  int crinod_ntimes = 0;
+  bool spg_def_circl = false;   // spg_def: 'layer' (default) or 'circl'
+  bool lspg_circ = false;    // spg_def='circl': lsponge (global flag, por of lsponge_loc)
   std::vector<double> hist;  // nstep,time,kenergy,enstrophy (statistic.F90:871-990)
   double xmax = 0.0;
 };
@@ -961,8 +972,70 @@ static int boucon(Case& c) {
 
 // src/sponge_layer.F90:67-319 spongefilter_layer: faces i0, im, jm, k0, km (the reference has no j0 block);
 // per face a one-direction dataswap of q, then a damped 7-point average over the layer (Jacobi: qtemp)
+// src/sponge_layer.F90:321-364 spongefilter_global (spg_def='circl'): dataswap(q) in every direction, then the
+// damped 7-point average over the whole [s:e]^3 box of every block that has a damped node (lsponge_loc)
+static void spongefilter_global(Case& c) {
+  Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
+  if (!c.lspg_circ) return;
+  for (int d = 0; d < 3; ++d) dataswap(c, gq, d);
+  for (Block& b : c.blk) {
+    if (b.spg_circ.empty()) continue;
+    const int ni = b.e[0] - b.s[0] + 1, nj = b.e[1] - b.s[1] + 1, nk = b.e[2] - b.s[2] + 1;
+    std::vector<double> qtemp((size_t)5 * ni * nj * nk);
+    for (int n = 0; n < 5; ++n)
+      for (int k = b.s[2]; k <= b.e[2]; ++k)
+        for (int j = b.s[1]; j <= b.e[1]; ++j)
+          for (int i = b.s[0]; i <= b.e[0]; ++i) {
+            const size_t t = (size_t)(i - b.s[0]) + (size_t)ni * ((size_t)(j - b.s[1]) + (size_t)nj * (k - b.s[2]));
+            const double var1 = b.spg_circ[t];
+            const Field& q = b.q[n];
+            qtemp[t + (size_t)n * ni * nj * nk] =
+                (1.0 - var1) * q(i, j, k) + num1d6 * var1 * (q(i + 1, j, k) + q(i - 1, j, k) + q(i, j + 1, k) +
+                                                             q(i, j - 1, k) + q(i, j, k + 1) + q(i, j, k - 1));
+          }
+    for (int n = 0; n < 5; ++n)
+      for (int k = b.s[2]; k <= b.e[2]; ++k)
+        for (int j = b.s[1]; j <= b.e[1]; ++j)
+          for (int i = b.s[0]; i <= b.e[0]; ++i) {
+            const size_t t = (size_t)(i - b.s[0]) + (size_t)ni * ((size_t)(j - b.s[1]) + (size_t)nj * (k - b.s[2]));
+            b.q[n](i, j, k) = qtemp[t + (size_t)n * ni * nj * nk];
+          }
+  }
+}
+
+// src/sponge_layer.F90:369-440 spongelayer_define_circle: damping grows with the square of the distance beyond
+// `range_spange` from the centre (xc, yc, zc), normalised by its global maximum (pmax) and scaled by dampfac.
+// The reference hard-codes centre 0, range 0.06 and dampfac 0.05; they are arguments here so that a test box of any
+// size has an undamped core.
+static void spongelayer_define_circle(Case& c, double xc, double yc, double zc, double range_spange, double dampfac) {
+  double max_dis = 0.0;
+  c.lspg_circ = false;
+  for (Block& b : c.blk) {
+    const int ni = b.e[0] - b.s[0] + 1, nj = b.e[1] - b.s[1] + 1, nk = b.e[2] - b.s[2] + 1;
+    b.spg_circ.assign((size_t)ni * nj * nk, 0.0);
+    bool loc = false;
+    for (int k = b.s[2]; k <= b.e[2]; ++k)
+      for (int j = b.s[1]; j <= b.e[1]; ++j)
+        for (int i = b.s[0]; i <= b.e[0]; ++i) {
+          const double dx = b.x[0](i, j, k) - xc, dy = b.x[1](i, j, k) - yc, dz = b.x[2](i, j, k) - zc;
+          const double var1 = std::sqrt(dx * dx + dy * dy + dz * dz);
+          double var2 = 0.0;
+          if (var1 >= range_spange) { var2 = (var1 - range_spange) * (var1 - range_spange); loc = true; }
+          b.spg_circ[(size_t)(i - b.s[0]) + (size_t)ni * ((size_t)(j - b.s[1]) + (size_t)nj * (k - b.s[2]))] = var2;
+          max_dis = std::max(max_dis, var2);
+        }
+    if (loc) c.lspg_circ = true;
+    b.spg_circ_loc = loc;
+  }
+  for (Block& b : c.blk) {
+    for (double& v : b.spg_circ) v = v / max_dis * dampfac;
+    if (!b.spg_circ_loc) b.spg_circ.clear();     // lsponge_loc false: the block skips the update
+  }
+}
+
 static void spongefilter(Case& c) {
   Getter gq = [](Block& b) { return FieldList{&b.q[0], &b.q[1], &b.q[2], &b.q[3], &b.q[4]}; };
+  if (c.spg_def_circl) { spongefilter_global(c); return; }     // src/sponge_layer.F90:59-63
   static const int faces[5] = {0, 1, 3, 4, 5};
   for (int f : faces) {
     if (!c.lspg[f]) continue;
@@ -1005,6 +1078,121 @@ static void updatefvar(Case& c) {
       for (int j = 0; j <= b.jm; ++j)
         for (int i = 0; i <= b.im; ++i) q2fvar_node(c.th, b, i, j, k);
   }
+}
+
+// ---------------------------------------------------------------------------------
+// crash control (lcracon), src/mainloop.F90:709-1198.  nodestat <= 0 everywhere (no immersed body).
+// ---------------------------------------------------------------------------------
+static void ensure_crinod(Case& c) {
+  for (Block& b : c.blk)
+    if (b.crinod.v.empty()) b.crinod.alloc(b.im, b.jm, b.km);    // crinod=.false. (mainloop.F90:81)
+}
+// crinod_expansion (:985-1033): 3x3x3 dilation of the flags over -1..dim+1, then dataswap(crinod)
+static long long crinod_expansion(Case& c) {
+  ensure_crinod(c);
+  long long counter = 0;
+  for (Block& b : c.blk) {
+    Field tmp; tmp.alloc(b.im, b.jm, b.km);
+    for (int k = -1; k <= b.km + 1; ++k)
+      for (int j = -1; j <= b.jm + 1; ++j)
+        for (int i = -1; i <= b.im + 1; ++i)
+          if (b.crinod(i, j, k) != 0.0)
+            for (int k1 = k - 1; k1 <= k + 1; ++k1)
+              for (int j1 = j - 1; j1 <= j + 1; ++j1)
+                for (int i1 = i - 1; i1 <= i + 1; ++i1) { tmp(i1, j1, k1) = 1.0; counter += 1; }
+    for (int k = -2; k <= b.km + 2; ++k)
+      for (int j = -2; j <= b.jm + 2; ++j)
+        for (int i = -2; i <= b.im + 2; ++i) b.crinod(i, j, k) = tmp(i, j, k);
+  }
+  Getter gc = [](Block& b) { return FieldList{&b.crinod}; };
+  dataswap(c, gc);
+  c.crinod_ntimes += 1;
+  return counter;
+}
+// databakup (:826-972).  mode 0 'backup', 1 'recovery'.  Returns 0, or 1 when a recovery finds no backup.
+static int databakup(Case& c, int mode) {
+  auto save = [&](Case::DataBack& d) {
+    d.nstep = c.nstep; d.time = c.time; d.recover_counter = 0;
+    d.q.resize(c.blk.size() * 5);
+    for (size_t ib = 0; ib < c.blk.size(); ++ib)
+      for (int m = 0; m < 5; ++m) d.q[ib * 5 + m] = c.blk[ib].q[m].v;
+  };
+  auto load = [&](Case::DataBack& d) {
+    c.nstep = d.nstep; c.time = d.time;
+    for (size_t ib = 0; ib < c.blk.size(); ++ib) {
+      Block& b = c.blk[ib];
+      for (int m = 0; m < 5; ++m) {
+        Field old; old.alloc(b.im, b.jm, b.km); old.v = d.q[ib * 5 + m];
+        for (int k = 0; k <= b.km; ++k)               // q(0:im,0:jm,0:km,:) only: the halos keep their values
+          for (int j = 0; j <= b.jm; ++j)
+            for (int i = 0; i <= b.im; ++i) b.q[m](i, j, k) = old(i, j, k);
+      }
+    }
+    d.recover_counter += 1;
+    return d.recover_counter;
+  };
+  if (mode == 0) {
+    if (c.datpnt == 'o') c.datpnt = 'a';
+    if (c.datpnt == 'a') { save(c.dat_a); c.datpnt = 'b'; }
+    else { save(c.dat_b); c.datpnt = 'a'; }
+    return 0;
+  }
+  if (c.datpnt == 'o') return 1;          // ' !! not backup data avaliable !!'
+  // after a single backup datpnt points at the copy that was never written: the reference then reads an unallocated
+  // array (:941); reported as "no backup" here
+  if ((c.datpnt == 'a' ? c.dat_a : c.dat_b).q.empty()) return 1;
+  int counter;
+  if (c.datpnt == 'a') { counter = load(c.dat_a); c.datpnt = 'b'; }
+  else { counter = load(c.dat_b); c.datpnt = 'a'; }
+  updatefvar(c);
+  if (counter > 1) crinod_expansion(c);
+  return 0;
+}
+// crashcheck (:709-818), the detection part: fluid nodes whose density is not >= 0 become critical nodes;
+// returns how many (the caller recovers or stops, :776-812)
+static long long crashcheck(Case& c) {
+  ensure_crinod(c);
+  long long n = 0;
+  for (Block& b : c.blk)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i)
+          if (!(b.q[0](i, j, k) >= 0.0)) { b.crinod(i, j, k) = 1.0; n += 1; }
+  return n;
+}
+// crashfix (:1045-1198): nodes whose density, pressure or temperature fell under eps are flagged and replaced by
+// the mean of their admissible neighbours, one after the other in storage order (later nodes see earlier repairs)
+static long long crashfix(Case& c) {
+  ensure_crinod(c);
+  const double eps_rho = 1.0e-5, eps_tmp = 1.0e-5;
+  const double eps_prs = c.th.thermal_p(eps_rho, eps_tmp);       // thermal(density,temperature), fludyna.F90:45-88
+  long long counter = 0;
+  for (Block& b : c.blk)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) {
+          if (b.rho(i, j, k) >= eps_rho && b.prs(i, j, k) >= eps_prs && b.tmp(i, j, k) >= eps_tmp) continue;
+          b.crinod(i, j, k) = 1.0;
+          double qavg[5] = {0, 0, 0, 0, 0};
+          int norm = 0;
+          for (int kk = -1; kk <= 1; ++kk)
+            for (int jj = -1; jj <= 1; ++jj)
+              for (int ii = -1; ii <= 1; ++ii) {
+                if (ii == 0 && jj == 0 && kk == 0) continue;
+                if (b.g0[0] + i + ii < 0 || b.g0[0] + i + ii > c.ia || b.g0[1] + j + jj < 0 || b.g0[1] + j + jj > c.ja) continue;
+                if (b.rho(i + ii, j + jj, k + kk) >= 0.0 && b.prs(i + ii, j + jj, k + kk) >= 0.0 &&
+                    b.tmp(i + ii, j + jj, k + kk) >= 0.0) {
+                  for (int m = 0; m < 5; ++m) qavg[m] = qavg[m] + b.q[m](i + ii, j + jj, k + kk);
+                  norm += 1;
+                }
+              }
+          if (norm >= 1) {
+            for (int m = 0; m < 5; ++m) b.q[m](i, j, k) = qavg[m] / double(norm);
+            q2fvar_node(c.th, b, i, j, k);
+            counter += 1;
+          }
+        }
+  return counter;
 }
 
 // src/statistic.F90:871-990 kenergycal / enstophycal (ndims==3)
@@ -1221,6 +1409,7 @@ static Field* field_by_id(Block& b, int id) {
   if (id < 58) return &b.vor[id - 55];
   if (id == 58) return &b.ssf;
   if (id == 59) return &b.lshock;
+  if (id == 60) { if (b.crinod.v.empty()) b.crinod.alloc(b.im, b.jm, b.km); return &b.crinod; }
   return nullptr;
 }
 // Copy a field (always in the halo'd shape (im+11)(jm+11)(km+11)) out of / into a block.
@@ -1275,6 +1464,25 @@ void oracle_case_set_sponge(void* h, int ib, int face, int beg, int end, const d
   }
 }
 void oracle_case_spongefilter(void* h) { spongefilter(*static_cast<Case*>(h)); }
+// crash control (src/mainloop.F90:709-1198)
+long long oracle_case_crashcheck(void* h) { return crashcheck(*static_cast<Case*>(h)); }
+long long oracle_case_crashfix(void* h) { return crashfix(*static_cast<Case*>(h)); }
+long long oracle_case_crinod_expansion(void* h) { return crinod_expansion(*static_cast<Case*>(h)); }
+int oracle_case_databakup(void* h, int mode) { return databakup(*static_cast<Case*>(h), mode); }
+int oracle_case_nstep(void* h) { return static_cast<Case*>(h)->nstep; }
+// spg_def='circl': defines the coefficients (spongelayer_define_circle) and switches spongefilter to the global form
+void oracle_case_set_sponge_circle(void* h, double xc, double yc, double zc, double range_spange, double dampfac) {
+  Case* c = static_cast<Case*>(h);
+  c->spg_def_circl = true;
+  spongelayer_define_circle(*c, xc, yc, zc, range_spange, dampfac);
+}
+// sponge_damp_coef(is:ie,js:je,ks:ke) of block ib (Fortran order); returns 0 when the block has no damped node
+int oracle_case_sponge_circle_coef(void* h, int ib, double* out) {
+  const Block& b = static_cast<Case*>(h)->blk[ib];
+  if (b.spg_circ.empty()) return 0;
+  std::memcpy(out, b.spg_circ.data(), b.spg_circ.size() * sizeof(double));
+  return 1;
+}
 double oracle_case_pinf(void* h) { return static_cast<Case*>(h)->pinf; }
 // nondimen=f (src/solver.F90:124-148): SI reference state; Mach, Reynolds, const1..7, pinf follow
 void oracle_case_set_dimensional(void* h, double ref_tem, double ref_vel, double ref_len, double ref_den) {

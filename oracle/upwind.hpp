@@ -322,6 +322,14 @@ static bool chardecomp(double gamma, double ro_l, double p_l, double E_l, const 
   return true;
 }
 
+// hdiss of the interface i+1/2 (src/solver.F90:1456-1462, :660-666): a critical node (crash control) on either side
+static inline bool crinod_interface(const Block& b, int d, int i, int dm, int p1, int p2) {
+  if (b.crinod.v.empty()) return false;
+  if (i < 0) return at(b.crinod, d, i + 1, p1, p2) != 0.0;
+  if (i + 1 > dm) return at(b.crinod, d, i, p1, p2) != 0.0;
+  return at(b.crinod, d, i, p1, p2) != 0.0 || at(b.crinod, d, i + 1, p1, p2) != 0.0;
+}
+
 // src/commcal.F90:196-357 ducrossensor -> b.ssf, b.lshock (0/1 as doubles)
 static void ducrossensor(Case& c) {
   for (Block& b : c.blk) {
@@ -473,9 +481,11 @@ static int convrsdcmp(Case& c) {
             else if (i + 1 > dm) lsh = at(b.lshock, d, i, p1, p2) != 0.0;
             else lsh = at(b.lshock, d, i, p1, p2) != 0.0 || at(b.lshock, d, i + 1, p1, p2) != 0.0;
           }
+          const bool hdiss = crinod_interface(b, d, i, dm, p1, p2);       // :1456-1462
           for (int m = 0; m < 5; ++m) {
-            const double var1 = mplimiter(flcp[m], fhcpc[m], lsh, i, dm, nt);
-            const double var2 = mplimiter(flcm[m], fhcmc[m], lsh, i, dm, nt);
+            // :1466-1481: at a critical node the interface value is the (projected) split flux of one node
+            const double var1 = hdiss ? flcp[m][3] : mplimiter(flcp[m], fhcpc[m], lsh, i, dm, nt);
+            const double var2 = hdiss ? flcm[m][3] : mplimiter(flcm[m], fhcmc[m], lsh, i, dm, nt);
             Fhc[m] = var1 + var2;
           }
           if (c.lchardecomp) {

@@ -113,6 +113,81 @@ def test_spongefilter(oracle, n, faces):
     eng.close(); c.close()
 
 
+def test_spongefilter_global(oracle):
+    # spg_def='circl' (src/sponge_layer.F90:321-440): exchange of q in every direction, then the damped 7-point average
+    # over the whole is:ie x js:je x ks:ke box with the distance-based coefficient of spongelayer_define_circle
+    c, eng = make_pair(oracle, n=(36, 32, 24), homo=(False, False, True), stretch=True)
+    c.set_sponge_circle(centre=(3.0, 3.0, 3.0), range_spange=2.0, dampfac=0.05)
+    coef = c.sponge_circle_coef()
+    assert coef is not None and coef.max() == pytest.approx(0.05) and (coef == 0.0).any()
+    eng.set_sponge_global(coef)
+    c.spongefilter(); eng.spongefilter()
+    assert_fields_close(c, eng, QS, OP_TOL, region=whole, what="spongefilter_global")
+    # and inside a stage (mainloop.F90:478: between the update and updatefvar)
+    c.rk_stage(1); eng.rk_stage(1)
+    assert_fields_close(c, eng, QS + PRIMS, STEP_TOL, what="rk stage with the global sponge")
+    eng.close(); c.close()
+
+
+def _poison(c, eng, nodes):
+    """Negative density / NaN energy at a few nodes, the same on both sides."""
+    for name, val in (("q1", -0.25), ("q5", float("nan"))):
+        a = c.get(name)
+        for (i, j, k) in nodes[name]:
+            a[5 + i, 5 + j, 5 + k] = val
+        c.set(name, a); eng.set(name, a)
+    c.updatefvar(); eng.updatefvar()
+
+
+def test_crash_control(oracle):
+    # lcracon (src/mainloop.F90:709-1198): crashcheck flags, crashfix wipes in storage order (two adjacent sick nodes:
+    # the second one sees the first repair), databakup keeps two copies and expands crinod from the second recovery on
+    c, eng = make_pair(oracle, n=(36, 32, 24), homo=(True, False, True), stretch=True)
+    assert c.crashcheck() == 0 and eng.crashcheck() == 0
+    assert c.crashfix() == 0 and eng.crashfix() == 0
+    for _ in range(2):
+        c.databakup("backup"); eng.databakup("backup")
+        c.rk_stage(1); eng.rk_stage(1)
+    nodes = {"q1": [(7, 9, 11), (8, 9, 11), (0, 0, 5), (36, 32, 24)], "q5": [(20, 16, 3), (21, 17, 4)]}
+    _poison(c, eng, nodes)
+    assert eng.crashcheck() == c.crashcheck() == 4
+    np.testing.assert_array_equal(eng.get("crinod"), c.get("crinod"))
+    nfix = c.crashfix()
+    assert eng.crashfix() == nfix == 6
+    np.testing.assert_array_equal(eng.get("crinod"), c.get("crinod"))
+    assert_fields_close(c, eng, QS + PRIMS, OP_TOL, what="crashfix")
+    assert np.isfinite(core(eng.get("q5"))).all() and core(eng.get("rho")).min() > 0.0
+    # recoveries alternate between the two copies; the third one revisits dat_a (recover_counter 2): crinod expands
+    for want in ((0, 1), (1, 1), (0, 2)):
+        c.databakup("recovery")
+        assert eng.databakup("recovery") == want
+        assert_fields_close(c, eng, QS + PRIMS, OP_TOL, what="databakup recovery")
+    np.testing.assert_array_equal(eng.get("crinod"), c.get("crinod"))
+    assert c.get("crinod").sum() > 6
+    eng.close(); c.close()
+
+
+def test_critical_nodes_switch_the_upwind_flux_to_one_node(oracle):
+    # hdiss (src/solver.F90:1456-1481 compact, :660-759 explicit): interfaces next to a critical node take the split
+    # flux of one node instead of the limited reconstruction
+    for up in (dict(lchardecomp=True, shkcrt="auto"), dict(lchardecomp=True, shkcrt="auto", recon_schem=3)):
+        c, eng = make_pair(oracle, n=(40, 36, 24), stretch="skew", perturb=1e-2, upwind=up)
+        cn = c.get("crinod")
+        cn[5 + 12:5 + 15, 5 + 10:5 + 13, 5 + 6:5 + 9] = 1.0
+        cn[5, 5 + 3, 5 + 3] = 1.0; cn[5 + 40, 5 + 20, 5 + 20] = 1.0
+        c.set("crinod", cn); eng.set("crinod", cn)
+        c.qswap(); eng.qswap(); c.gradcal(); eng.gradcal()
+        c.zero_qrhs(); c.rhscal(); eng.rhscal()
+        ref = [core(c.get(f"qrhs{m + 1}")).copy() for m in range(5)]
+        assert_fields_close(c, eng, [f"qrhs{m + 1}" for m in range(5)], UPWIND_TOL, what="rhscal with critical nodes")
+        # and the flags do change the answer
+        cn[...] = 0.0
+        c.set("crinod", cn)
+        c.zero_qrhs(); c.rhscal()
+        assert max(np.abs(core(c.get(f"qrhs{m + 1}")) - ref[m]).max() for m in range(5)) > 0.0
+        eng.close(); c.close()
+
+
 def test_swbli_like_stage(oracle):
     # the option set of examples/SWLBI/datin/input.2d on a small 2-D block: 543c + 643c, characteristic
     # decomposition + Ducros sensor, inflow / outflow / slip adiabatic wall / farfield, sponge layer at imax

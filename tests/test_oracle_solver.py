@@ -92,6 +92,67 @@ def test_rk4_is_the_classical_scheme(oracle):
     a.close(); b.close()
 
 
+def test_global_sponge_damps_outside_the_core_only(oracle):
+    """spg_def='circl' (src/sponge_layer.F90:321-440): nodes within range_spange of the centre keep q bit for bit,
+    the rest relaxes towards the 6-neighbour mean with a coefficient <= dampfac; two blocks agree with one."""
+    n = (24, 20, 16)
+    cs = []
+    for blocks in ((1, 1, 1), (2, 1, 1)):
+        c = oracle.Case(*n, blocks=blocks)
+        c.gridgeom(); c.tgvini()
+        c.set_sponge_circle(centre=(3.0, 3.0, 3.0), range_spange=2.0, dampfac=0.05)
+        cs.append(c)
+    one, two = cs
+    coef = one.sponge_circle_coef()
+    assert coef.max() == pytest.approx(0.05) and coef.min() == 0.0
+    before = one.get("q2")[5:-5, 5:-5, 5:-5].copy()
+    one.spongefilter(); two.spongefilter()
+    after = one.get("q2")[5:-5, 5:-5, 5:-5]
+    b = one.block_info(0)
+    s_, e_ = b["is_ie"][0::2], b["is_ie"][1::2]
+    box = tuple(slice(s_[d], e_[d] + 1) for d in range(3))
+    core_mask = coef == 0.0
+    np.testing.assert_array_equal(after[box][core_mask], before[box][core_mask])
+    assert np.abs(after[box][~core_mask] - before[box][~core_mask]).max() > 0.0
+    # the two-block run: same coefficients (global maximum), same result
+    left = two.get("q2", 0)[5:-5, 5:-5, 5:-5]
+    im0 = two.block_info(0)["im"]
+    np.testing.assert_allclose(left[1:im0, :, :], after[1:im0, :, :], rtol=0, atol=1e-15)
+    one.close(); two.close()
+
+
+def test_crash_control_restatement(oracle):
+    """lcracon (src/mainloop.F90:709-1198): crashcheck flags negative densities, crashfix replaces sick nodes by the
+    mean of their admissible neighbours in storage order, databakup alternates two copies and a repeated recovery of
+    the same copy expands the critical nodes to their 27-neighbourhoods."""
+    c = oracle.Case(16, 16, 16)
+    c.gridgeom(); c.tgvini()
+    assert c.crashcheck() == 0 and c.crashfix() == 0
+    with pytest.raises(RuntimeError):
+        c.databakup("recovery")                      # ' !! not backup data avaliable !!'
+    c.databakup("backup"); c.run(1); c.databakup("backup"); c.run(1)
+    q = c.get("q1"); q[5 + 3, 5 + 3, 5 + 3] = -1.0; q[5 + 4, 5 + 3, 5 + 3] = -2.0
+    c.set("q1", q); c.updatefvar()
+    clean = c.get("q1")
+    assert c.crashcheck() == 2 and c.get("crinod").sum() == 2.0
+    assert c.crashfix() == 2
+    fixed = c.get("q1")
+    # node (3,3,3) is repaired first from its 25 healthy neighbours, node (4,3,3) then from 25 healthy + the repaired one
+    nb = clean[5 + 2:5 + 5, 5 + 2:5 + 5, 5 + 2:5 + 5]
+    want = (nb.sum() - clean[8, 8, 8] - clean[9, 8, 8]) / 25.0
+    assert fixed[8, 8, 8] == pytest.approx(want, rel=1e-14)
+    nb2 = fixed[5 + 3:5 + 6, 5 + 2:5 + 5, 5 + 2:5 + 5]
+    assert fixed[9, 8, 8] == pytest.approx((nb2.sum() - fixed[9, 8, 8]) / 26.0, rel=1e-14)
+    assert c.get("rho")[9, 8, 8] == fixed[9, 8, 8]
+    assert c.nstep == 2
+    c.databakup("recovery"); assert c.nstep == 0     # dat_a, the older copy
+    c.databakup("recovery"); assert c.nstep == 1     # dat_b
+    before = c.get("crinod").sum()
+    c.databakup("recovery"); assert c.nstep == 0     # dat_a again: recover_counter 2 -> crinod_expansion
+    assert c.get("crinod").sum() > before
+    c.close()
+
+
 def _channel_case(oracle, n=(24, 32, 16), explicit=False, blocks=(1, 1, 1)):
     """examples/Channel/datin/input.chl at reduced size (see tests/gpu_common.py)."""
     sys_path_tests()
