@@ -201,6 +201,8 @@ struct Ctx {
   struct Sponge { bool on = false; int beg = -1, end = -2; double* coef = nullptr; } spg[6];   // i0, im, j0, jm, k0, km
   bool any_sponge() const { if (spg_global) return true; for (const Sponge& s : spg) if (s.on) return true; return false; }
   double* stage = nullptr;       // dense host-layout staging field of the upload path
+  double* dense[2] = {nullptr, nullptr};            // checkpoint staging: dense node arrays
+  cudaEvent_t ev_dense[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_inflow = nullptr;    // vel_in(0:jm,0:km,3) | tmp_in(0:jm,0:km) | tmp_prof(0:jm)  (bctype(1)=11)
   double* d_src = nullptr;       // [0..3] bulk integrals, [4..7] (force, force.ubulk)
   bool src_pending = false;      // src_chan's term is not in the G slots: consumers add d_src+4
@@ -703,6 +705,8 @@ int astr_gpu_finalize(void) {
   if (g->scr) cudaFree(g->scr);
   if (g->rhsav) cudaFree(g->rhsav);
   if (g->crinod) cudaFree(g->crinod);
+  for (auto& d : g->dense) if (d) cudaFree(d);
+  for (auto& e : g->ev_dense) if (e) cudaEventDestroy(e);
   for (auto& b : g->bak) if (b) cudaFree(b);
   if (g->d_count) cudaFree(g->d_count);
   if (g->d_list) cudaFree(g->d_list);
@@ -1455,6 +1459,58 @@ int astr_gpu_crashfix(int ig0, int jg0, long long* nfixed) {
   a.g0[0] = ig0; a.g0[1] = jg0; a.g0[2] = 0; a.ia = c.ia; a.ja = c.ja; a.n = n;
   TRY(pw_crashfix_apply(g->L, g->pool, g->th, g->d_list, a, g->d_count + 1, g->st));
   TRY(read_count(1, nfixed));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// checkpoint staging (writeflfed / readcheckpoint, src/readwrite.F90:1723-1984, :1381-1470): the six datasets
+// ro, u1, u2, u3, p, t as dense node arrays (0:im,0:jm,0:km), Fortran order -- what h5write / h5read take.
+// Two dense device buffers alternate: the pack of field m+1 runs under the copy of field m (copy stream g->xst).
+// ---------------------------------------------------------------------------------
+static int dense_buffers() {
+  const size_t bytes = (size_t)(g->L.im + 1) * (g->L.jm + 1) * (g->L.km + 1) * sizeof(double);
+  for (auto& d : g->dense) if (!d) CUDA_OK(cudaMalloc(&d, bytes));
+  for (auto& e : g->ev_dense) if (!e) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return 0;
+}
+int astr_gpu_stage_checkpoint(double* ro, double* u1, double* u2, double* u3, double* p, double* t) {
+  NEED_CTX();
+  TRY(dense_buffers());
+  double* host[6] = {ro, u1, u2, u3, p, t};
+  const int slots[6] = {S_RHO, S_VEL, S_VEL + 1, S_VEL + 2, S_PRS, S_TMP};
+  const size_t bytes = (size_t)(g->L.im + 1) * (g->L.jm + 1) * (g->L.km + 1) * sizeof(double);
+  for (int m = 0; m < 6; ++m) {
+    const int b = m & 1;
+    if (m >= 2) CUDA_OK(cudaStreamWaitEvent(g->st, g->ev_dense[2 + b], 0));     // the copy that last used this buffer
+    TRY(pw_dense(g->L, g->slot(slots[m]), g->dense[b], true, g->st));
+    CUDA_OK(cudaEventRecord(g->ev_dense[b], g->st));
+    CUDA_OK(cudaStreamWaitEvent(g->xst, g->ev_dense[b], 0));
+    CUDA_OK(cudaMemcpyAsync(host[m], g->dense[b], bytes, cudaMemcpyDeviceToHost, g->xst));
+    CUDA_OK(cudaEventRecord(g->ev_dense[2 + b], g->xst));
+  }
+  CUDA_OK(cudaStreamSynchronize(g->xst));
+  CUDA_OK(cudaStreamSynchronize(g->st));
+  return p2p_check();
+}
+// readcheckpoint (:1448-1453) + updateq (src/fludyna.F90:254-300: q from density, velocity and temperature)
+int astr_gpu_restore_checkpoint(const double* ro, const double* u1, const double* u2, const double* u3, const double* p,
+                                const double* t) {
+  NEED_CTX();
+  TRY(dense_buffers());
+  const double* host[6] = {ro, u1, u2, u3, p, t};
+  const int slots[6] = {S_RHO, S_VEL, S_VEL + 1, S_VEL + 2, S_PRS, S_TMP};
+  const size_t bytes = (size_t)(g->L.im + 1) * (g->L.jm + 1) * (g->L.km + 1) * sizeof(double);
+  for (int m = 0; m < 6; ++m) {
+    const int b = m & 1;
+    if (m >= 2) CUDA_OK(cudaStreamWaitEvent(g->xst, g->ev_dense[2 + b], 0));    // the unpack that last read this buffer
+    CUDA_OK(cudaMemcpyAsync(g->dense[b], host[m], bytes, cudaMemcpyHostToDevice, g->xst));
+    CUDA_OK(cudaEventRecord(g->ev_dense[b], g->xst));
+    CUDA_OK(cudaStreamWaitEvent(g->st, g->ev_dense[b], 0));
+    TRY(pw_dense(g->L, g->slot(slots[m]), g->dense[b], false, g->st));
+    CUDA_OK(cudaEventRecord(g->ev_dense[2 + b], g->st));
+  }
+  TRY(pw_updateq(g->L, g->pool, g->th, g->st));
+  CUDA_OK(cudaStreamSynchronize(g->st));
   return 0;
 }
 

@@ -12,8 +12,15 @@
 //   tables (m, g, ac1, ev), which the kernels read as immediate constant-bank operands, and all
 //   chunk threads run the same straight-line code.
 // * head block: the closure rows of the first end (explicit interface rows, wall rows, filter
-//   end rows) plus the rows that do not fill a whole chunk; tail block: the closure rows of the
-//   last end (+ at most one interior row, see `align_even`).  Generic tables, one dedicated warp.
+//   end rows) plus the rows that do not fill a whole chunk, when the block then has at most 8 rows;
+//   tail block: the closure rows of the last end (+ at most one interior row, see `align_even`).
+//   Generic tables, one dedicated warp.
+// * SHORT first chunk: when head block + left-over rows would exceed 8 rows, the left-over rows
+//   become regular chunk 0 with ls0 < ASTR_LMAX rows instead.  A fresh-start factorisation does not
+//   depend on where the chunk ends, so the short chunk runs the same tables truncated at ls0 (the
+//   slots behind pass values through); only its element coefficients differ.  The head block then
+//   stays on the 8-slot code path for every line length (round 1-2a: up to 40 slots, one warp, the
+//   straggler of every bundle on e.g. 513-row wall-bounded lines).
 //
 // A thread owns one element of one pencil in registers:
 //   pass 1  e(s) = d(s) m(s) - e(s-1) g(s)                       local forward elimination
@@ -51,6 +58,11 @@
 struct RegTab {          // fresh-start factorisation of ASTR_LMAX interior rows (a, 1, c)
   double m[ASTR_LMAX], g[ASTR_LMAX], ac1[ASTR_LMAX], ev[ASTR_LMAX];
 };
+// SHORT first chunk (build_line_plan): the first ls0 slots are the rows (the fresh-start tables truncated), the rest
+// NEUTRAL slots, as in the head / tail blocks below: the code stays straight-line with immediate operands
+struct ShortTab {
+  double m[ASTR_LMAX], g[ASTR_LMAX], q[ASTR_LMAX], ac1[ASTR_LMAX], ev[ASTR_LMAX];
+};
 // Head / tail block: rows first, then NEUTRAL slots (m = 0, g = -1, q = 0, ac1 = -1, ev = 0) that
 // pass e forward and x backward unchanged, so the unrolled code needs no length guards.
 template <int S> struct SpecTab {
@@ -68,15 +80,17 @@ struct LinePlan {
   int E;                 // NW + 2
   int W;                 // reduced scan: elements looked at on each side (<= ASTR_WPAD)
   int ok;                // 0: this line cannot be handled by sweep2 (fall back to sweep.cu)
-  int pad;
+  int ls0;               // rows of regular chunk 0: ASTR_LMAX, or fewer when the rows that do not fill whole chunks
+                         // are too many for the short head block (they then form a SHORT first chunk, see build_line_plan)
   RegTab reg;
+  ShortTab sreg;         // chunk 0 when ls0 < ASTR_LMAX
   SpecTab<ASTR_HS> head;
   SpecTab<ASTR_TS> tail;
   ElemTab el[ASTR_EMAX + 2 * ASTR_WPAD];   // element e at index e + ASTR_WPAD; neutral entries around
 };
 
 // first row of regular chunk w
-ASTR_HD int plan_chunk_row(const LinePlan& p, int w) { return p.sh + w * ASTR_LMAX; }
+ASTR_HD int plan_chunk_row(const LinePlan& p, int w) { return w == 0 ? p.sh : p.sh + p.ls0 + (w - 1) * ASTR_LMAX; }
 
 // ASTR_NO_FMA (the -fmad=false debug library, `make nofma`): every product is rounded before it is added, as
 // in the oracle (which is compiled with -ffp-contract=off, like the reference's golden run).  Whatever then
@@ -310,6 +324,22 @@ ASTR_HD void chunk_forward(const RegTab& t, const FilterCoef& fc, const double (
   for (int s = L - 2; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s]);
   yh = y; yt = e[L - 1];
 }
+// the SHORT chunk: same passes over the ShortTab (neutral slots behind the rows carry e forward and leave y alone;
+// their right-hand sides are finite values of the following chunk's rows, multiplied by zero)
+template <int OP, int WN>
+ASTR_HD void chunk_forward_short(const ShortTab& t, const FilterCoef& fc, const double (&wv)[WN], double (&e)[ASTR_LMAX],
+                                 double& yh, double& yt) {
+  constexpr int L = ASTR_LMAX;
+#pragma unroll
+  for (int s = 0; s < L; ++s) {
+    const double d = reg_rhs<OP>(wv, s, fc);
+    e[s] = (s == 0) ? d : fma_(-e[s > 0 ? s - 1 : 0], t.g[s], d * t.m[s]);
+  }
+  double y = 0.0;
+#pragma unroll
+  for (int s = L - 1; s >= 0; --s) y = fma_(-t.ac1[s], y, e[s] * t.q[s]);
+  yh = y; yt = e[L - 1];
+}
 // pass 3: ST(s, x) receives the solution of row s (descending)
 template <class ST>
 ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_prev, double h_next, ST st) {
@@ -322,6 +352,16 @@ ASTR_HD void chunk_back(const RegTab& t, const double (&e)[ASTR_LMAX], double t_
 #pragma unroll
   for (int s = ASTR_LMAX - 1; s >= 0; --s) {
     x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s]));
+    st(s, x);
+  }
+}
+// SHORT chunk: ST is called for every slot; the caller keeps the slots s < ls0
+template <class ST>
+ASTR_HD void chunk_back_short(const ShortTab& t, const double (&e)[ASTR_LMAX], double t_prev, double h_next, ST st) {
+  double x = h_next;
+#pragma unroll
+  for (int s = ASTR_LMAX - 1; s >= 0; --s) {
+    x = fma_(-t.ac1[s], x, fma_(-t.ev[s], t_prev, e[s] * t.q[s]));
     st(s, x);
   }
 }
@@ -562,13 +602,28 @@ inline void build_line_plan(LinePlan& p, int optype, int ntype, int n, int first
   if (maxw > ASTR_NWMAX) maxw = ASTR_NWMAX;
   int NW = nreg / L;
   if (NW > maxw) return;
-  int rem = nreg - NW * L, rem_t = 0;
-  if (align_even && (((first_node + nsf + rem - H + 6) & 1) != 0)) {
-    if (rem == 0) { NW -= 1; rem = L; }
-    if (NW < 1) return;
-    rem -= 1; rem_t = 1;
+  int rem = nreg - NW * L, rem_t = 0, rem_h = 0, ls0 = L;
+  // (A) the left-over rows join the head block
+  int nwA = NW, remA = rem, remtA = 0;
+  bool okA = true;
+  if (align_even && (((first_node + nsf + remA - H + 6) & 1) != 0)) {
+    if (remA == 0) { nwA -= 1; remA = L; }
+    if (nwA < 1) okA = false;
+    remA -= 1; remtA = 1;
   }
-  p.sh = nsf + rem; p.st = nsl + rem_t; p.NW = NW; p.E = NW + 2;
+  // (B) SHORT first chunk: head block = closure rows (+1 row for the window alignment of i lines), chunk 0 = the
+  // left-over rows (an even number for i lines: one more row may move to the tail block)
+  int nwB = NW, R = rem, remhB = 0, remtB = 0;
+  if (align_even && (((first_node + nsf - H + 6) & 1) != 0)) remhB = 1;
+  if (R - remhB < 2 && nwB > 1) { nwB -= 1; R += L; }          // too few left-over rows: borrow a chunk
+  int lsB = R - remhB;
+  if (align_even && (lsB & 1)) { lsB -= 1; remtB = 1; }
+  const bool okB = lsB >= 2 && lsB < L && nwB + 1 <= maxw && nwB >= 1;
+  if (okA && nsf + remA <= 8) { NW = nwA; rem_h = remA; rem_t = remtA; }
+  else if (okB) { NW = nwB + 1; rem_h = remhB; rem_t = remtB; ls0 = lsB; }
+  else if (okA) { NW = nwA; rem_h = remA; rem_t = remtA; }      // long head block (one warp, up to ASTR_HS slots)
+  else return;
+  p.sh = nsf + rem_h; p.st = nsl + rem_t; p.NW = NW; p.E = NW + 2; p.ls0 = ls0;
   if (p.sh > ASTR_HS || p.st > ASTR_TS) return;
   // tables
   {
@@ -578,8 +633,14 @@ inline void build_line_plan(LinePlan& p, int optype, int ntype, int n, int first
   }
   std::vector<LocalFac> fac(p.E);
   fac[0] = local_factor(a, c, 0, p.sh, true, false);
-  for (int w = 0; w < NW; ++w) fac[w + 1] = local_factor(a, c, plan_chunk_row(p, w), L, false, false);
+  for (int w = 0; w < NW; ++w) fac[w + 1] = local_factor(a, c, plan_chunk_row(p, w), w == 0 ? p.ls0 : L, false, false);
   fac[p.E - 1] = local_factor(a, c, N - p.st, p.st, false, true);
+  for (int i = 0; i < L; ++i) {            // SHORT first chunk: rows, then neutral slots (unused when ls0 == L)
+    const bool r = i < p.ls0;
+    const LocalFac& f = fac[1];
+    p.sreg.m[i] = r ? f.m[i] : 0.0; p.sreg.g[i] = r ? f.g[i] : -1.0; p.sreg.q[i] = r ? 1.0 : 0.0;
+    p.sreg.ac1[i] = r ? f.ac1[i] : -1.0; p.sreg.ev[i] = r ? f.ev[i] : 0.0;
+  }
   fill_spec(p.head, fac[0], p.sh, nsf);
   fill_spec(p.tail, fac[p.E - 1], p.st, nsl);
   const int NE = ASTR_EMAX + 2 * ASTR_WPAD;

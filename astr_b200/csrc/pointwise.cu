@@ -745,6 +745,31 @@ __global__ void k_repitch(const Layout L, const double* __restrict__ src, double
 }
 
 // ---------------------------------------------------------------------------------
+// checkpoint staging: the datasets of writeflfed / readcheckpoint are node arrays without halos
+// (rho(0:im,0:jm,0:km) ..., src/readwrite.F90:1448-1453, :1974-1984)
+// ---------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void k_dense(const Layout L, double* __restrict__ field, double* __restrict__ dense) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long t = (long long)i + (long long)(L.im + 1) * ((long long)j + (long long)(L.jm + 1) * k);
+  if (PACK) dense[t] = field[L.idx(i, j, k)];
+  else field[L.idx(i, j, k)] = dense[t];
+}
+// updateq (src/fludyna.F90:254-300): fvar2q from density, velocity and TEMPERATURE (:425-429)
+__global__ void k_updateq(const Layout L, double* __restrict__ pool, const Thermo th) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  int i, j, k;
+  if (!box_node(b, i, j, k)) return;
+  const long long fs = L.fstride, x = L.idx(i, j, k);
+  const double r = pool[S_RHO * fs + x], u = pool[S_VEL * fs + x], v = pool[(S_VEL + 1) * fs + x], w = pool[(S_VEL + 2) * fs + x];
+  pool[S_Q * fs + x] = r; pool[(S_Q + 1) * fs + x] = r * u; pool[(S_Q + 2) * fs + x] = r * v; pool[(S_Q + 3) * fs + x] = r * w;
+  const double var1 = 0.5 * (u * u + v * v + w * w);
+  pool[(S_Q + 4) * fs + x] = r * (pool[S_TMP * fs + x] * th.cotem() + var1);
+}
+
+// ---------------------------------------------------------------------------------
 // spongefilter_layer (src/sponge_layer.F90:67-319): damped 7-point average of q over the layer box,
 // Jacobi style -- pass 1 writes the qrhs slots (dead between the RK update and the next rhscal), pass 2
 // copies them back.  coef is the box-shaped sponge_damp_coef in Fortran order.
@@ -1073,6 +1098,20 @@ int pw_diff6e(int dir, const SweepArgs& a, cudaStream_t st) {
 int pw_repitch(const Layout& L, const double* stage, double* field, cudaStream_t st) {
   dim3 grid((L.im + 1 + 2 * ASTR_HM + PW_T - 1) / PW_T, L.njt, L.nkt);
   k_repitch<<<grid, PW_T, 0, st>>>(L, stage, field);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int pw_dense(const Layout& L, double* field, double* dense, bool pack, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  if (pack) k_dense<true><<<box_grid(b), PW_T, 0, st>>>(L, field, dense);
+  else k_dense<false><<<box_grid(b), PW_T, 0, st>>>(L, field, dense);
+  LAUNCH_CHECK();
+  return 0;
+}
+int pw_updateq(const Layout& L, double* pool, const Thermo& th, cudaStream_t st) {
+  Box b = {{0, 0, 0}, {L.im, L.jm, L.km}};
+  k_updateq<<<box_grid(b), PW_T, 0, st>>>(L, pool, th);
   LAUNCH_CHECK();
   return 0;
 }

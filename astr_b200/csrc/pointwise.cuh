@@ -89,6 +89,8 @@ int pw_crashfix_flag(const Layout& L, const double* pool, double* crinod, double
 struct CrashFixArgs { int g0[3], ia, ja; long long n; };
 int pw_crashfix_apply(const Layout& L, double* pool, const Thermo& th, const long long* list, const CrashFixArgs& a,
                       unsigned long long* fixed, cudaStream_t st);
+int pw_dense(const Layout& L, double* field, double* dense, bool pack, cudaStream_t st);
+int pw_updateq(const Layout& L, double* pool, const Thermo& th, cudaStream_t st);
 int pw_copy_box(const Layout& L, double* dst, const double* src, int nf, const Box& b, cudaStream_t st);
 int pw_sponge(const Layout& L, double* pool, const Box& b, const double* coef, cudaStream_t st);
 int pw_bcface(const Layout& L, double* pool, const Thermo& th, int dir, const BcArgs& a, cudaStream_t st);

@@ -33,7 +33,7 @@ SYMBOLS = [
     "astr_gpu_upload_state", "astr_gpu_download_state", "astr_gpu_get_field", "astr_gpu_set_field",
     "astr_gpu_device_ptr", "astr_gpu_filterq", "astr_gpu_boucon", "astr_gpu_set_inflow", "astr_gpu_qswap", "astr_gpu_gradcal", "astr_gpu_rhscal",
     "astr_gpu_rk_update", "astr_gpu_spongefilter", "astr_gpu_updatefvar", "astr_gpu_rk_stage", "astr_gpu_rk_steps", "astr_gpu_rk_steps_timed",
-    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_sponge_global", "astr_gpu_crashcheck", "astr_gpu_databakup", "astr_gpu_crinod_expansion", "astr_gpu_crashfix", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_reduce_cfl", "astr_gpu_reduce_channel", "astr_gpu_kernel_launches",
+    "astr_gpu_dataswap", "astr_gpu_set_force", "astr_gpu_set_sponge", "astr_gpu_set_sponge_global", "astr_gpu_crashcheck", "astr_gpu_databakup", "astr_gpu_crinod_expansion", "astr_gpu_crashfix", "astr_gpu_stage_checkpoint", "astr_gpu_restore_checkpoint", "astr_gpu_set_grid", "astr_gpu_reduce_tgv", "astr_gpu_reduce_cfl", "astr_gpu_reduce_channel", "astr_gpu_kernel_launches",
     "astr_gpu_set_profile", "astr_gpu_get_profile", "astr_gpu_bench_sweep",
 ]
 
@@ -148,6 +148,8 @@ def load() -> ctypes.CDLL:
     L.astr_gpu_databakup.argtypes = [ci, vp, vp]
     L.astr_gpu_crinod_expansion.argtypes = [vp]
     L.astr_gpu_crashfix.argtypes = [ci, ci, vp]
+    L.astr_gpu_stage_checkpoint.argtypes = [vp] * 6
+    L.astr_gpu_restore_checkpoint.argtypes = [vp] * 6
     L.astr_gpu_set_inflow.argtypes = [vp, vp, vp]
     L.astr_gpu_reduce_tgv.argtypes = [vp]
     L.astr_gpu_reduce_cfl.argtypes = [vp]

@@ -231,6 +231,21 @@ class RhsEngine:
         _l.check(self._lib.astr_gpu_databakup({"backup": 0, "recovery": 1}[mode], ctypes.byref(slot), ctypes.byref(cnt)))
         return int(slot.value), int(cnt.value)
 
+    # ---- checkpoint staging (src/readwrite.F90:1723-1984, :1381-1470) -------------------------
+    def stage_checkpoint(self):
+        """ro, u1, u2, u3, p, t as dense node arrays (0:im,0:jm,0:km), the datasets writeflfed writes."""
+        dims = tuple(d + 1 for d in self.block.dims)
+        out = [np.empty(dims, order="F") for _ in range(6)]
+        _l.check(self._lib.astr_gpu_stage_checkpoint(*[a.ctypes.data for a in out]))
+        return dict(zip(("ro", "u1", "u2", "u3", "p", "t"), out))
+
+    def restore_checkpoint(self, data):
+        """readcheckpoint + updateq: primitives from the six datasets, q from density, velocity and temperature."""
+        dims = tuple(d + 1 for d in self.block.dims)
+        arrs = [np.asfortranarray(data[k], dtype=np.float64) for k in ("ro", "u1", "u2", "u3", "p", "t")]
+        assert all(a.shape == dims for a in arrs)
+        _l.check(self._lib.astr_gpu_restore_checkpoint(*[a.ctypes.data for a in arrs]))
+
     def set_sponge_global(self, coef: Optional[np.ndarray]):
         """spg_def='circl': sponge_damp_coef(is:ie,js:je,ks:ke) (src/sponge_layer.F90:369-440), None if this rank has no damped node."""
         a = None if coef is None else np.asfortranarray(coef, dtype=np.float64)

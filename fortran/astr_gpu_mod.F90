@@ -154,6 +154,15 @@ module astr_gpu_mod
       integer(c_int), value :: ig0,jg0
       integer(c_long_long), intent(out) :: nfixed
     end function
+    ! checkpoint staging: dense node arrays (0:im,0:jm,0:km) of the datasets ro,u1,u2,u3,p,t (readwrite.F90:1974-1984)
+    integer(c_int) function astr_gpu_stage_checkpoint(ro,u1,u2,u3,p,t) bind(c,name='astr_gpu_stage_checkpoint')
+      import :: c_int, c_double
+      real(c_double), intent(out) :: ro(*),u1(*),u2(*),u3(*),p(*),t(*)
+    end function
+    integer(c_int) function astr_gpu_restore_checkpoint(ro,u1,u2,u3,p,t) bind(c,name='astr_gpu_restore_checkpoint')
+      import :: c_int, c_double
+      real(c_double), intent(in) :: ro(*),u1(*),u2(*),u3(*),p(*),t(*)
+    end function
     ! spg_def='circl': coef = c_loc(sponge_damp_coef(is:ie,js:je,ks:ke)), c_null_ptr when lsponge_loc is false
     integer(c_int) function astr_gpu_set_sponge_global(coef) bind(c,name='astr_gpu_set_sponge_global')
       import :: c_int, c_ptr

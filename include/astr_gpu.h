@@ -191,6 +191,14 @@ int astr_gpu_databakup(int mode, int* slot, int* recover_counter);
 int astr_gpu_crinod_expansion(long long* counter);
 int astr_gpu_crashfix(int ig0, int jg0, long long* nfixed);
 
+/* ---- checkpoint staging: the datasets ro, u1, u2, u3, p, t of writeflfed (src/readwrite.F90:1723-1984) and
+ * readcheckpoint (:1381-1470) as dense node arrays (0:im,0:jm,0:km), Fortran order.  stage: device -> host (packing
+ * on the device overlaps the copies); restore: host -> device, then updateq (q from density, velocity and
+ * temperature, src/fludyna.F90:254-300).  The HDF5 calls stay in Fortran. */
+int astr_gpu_stage_checkpoint(double* ro, double* u1, double* u2, double* u3, double* p, double* t);
+int astr_gpu_restore_checkpoint(const double* ro, const double* u1, const double* u2, const double* u3,
+                                const double* p, const double* t);
+
 /* body force of src_chan (src/solver.F90:295-353), added to qrhs in rhscal when
  * flowtype = 1; `force` is what massfluxchan/chanfoce (src/statistic.F90:1437-1520) keep
  * updating on the Fortran side.  src_chan integrates in y, so the channel case needs the

@@ -97,6 +97,7 @@ def lib() -> ctypes.CDLL:
         L.oracle_case_set_inflow.argtypes = [vp, ci, vp, vp, vp]
         L.oracle_case_set_sponge.argtypes = [vp, ci, ci, ci, ci, vp]
         L.oracle_case_spongefilter.argtypes = [vp]
+        L.oracle_case_updateq.argtypes = [vp]
         for name in ("oracle_case_crashcheck", "oracle_case_crashfix", "oracle_case_crinod_expansion"):
             getattr(L, name).argtypes = [vp]
             getattr(L, name).restype = ctypes.c_longlong
@@ -339,6 +340,10 @@ class Case:
 
     def spongefilter(self):
         lib().oracle_case_spongefilter(self._h)
+
+    def updateq(self):
+        """q from density, velocity and temperature (src/fludyna.F90:254-300), as readcheckpoint ends."""
+        lib().oracle_case_updateq(self._h)
 
     # crash control (src/mainloop.F90:709-1198)
     def crashcheck(self) -> int:

@@ -1431,6 +1431,14 @@ void oracle_case_rhscal(void* h) { rhscal(*static_cast<Case*>(h)); }
 void oracle_case_save_q(void* h) { save_q(*static_cast<Case*>(h)); }
 void oracle_case_rk_update(void* h, int rkstep) { rk_update(*static_cast<Case*>(h), rkstep); }
 void oracle_case_updatefvar(void* h) { updatefvar(*static_cast<Case*>(h)); }
+// updateq (src/fludyna.F90:254-300): q(0:im,0:jm,0:km,:) from density, velocity and temperature
+void oracle_case_updateq(void* h) {
+  Case* c = static_cast<Case*>(h);
+  for (Block& b : c->blk)
+    for (int k = 0; k <= b.km; ++k)
+      for (int j = 0; j <= b.jm; ++j)
+        for (int i = 0; i <= b.im; ++i) fvar2q_T(c->th, b, i, j, k);
+}
 void oracle_case_rk_stage(void* h, int rkstep) { rk_stage(*static_cast<Case*>(h), rkstep); }
 int oracle_case_boucon(void* h) { return boucon(*static_cast<Case*>(h)); }
 // bctype(1:6), twall(1:6) of the input file; flowtype 0 generic / 1 channel; force(1:3) of

@@ -48,7 +48,9 @@ int run_line(const LinePlan& pl, const FilterCoef& fc, const double* f5 /* f5[k]
     double wv[WN];
     for (int s = 0; s < WN; ++s) wv[s] = F(node0 - H + s);
     double ee[L], yh, yt;
-    chunk_forward<OP>(pl.reg, fc, wv, ee, yh, yt);
+    // chunk 0 may be SHORT (pl.ls0 < L rows): the kernels run it through the SHORT instantiation
+    if (w == 0 && pl.ls0 != L) chunk_forward_short<OP>(pl.sreg, fc, wv, ee, yh, yt);
+    else chunk_forward<OP>(pl.reg, fc, wv, ee, yh, yt);
     for (int s = 0; s < L; ++s) e[w][s] = ee[s];
     publish(w + 1, yh, yt);
   }
@@ -68,7 +70,8 @@ int run_line(const LinePlan& pl, const FilterCoef& fc, const double* f5 /* f5[k]
     double ee[L];
     for (int s = 0; s < L; ++s) ee[s] = e[w][s];
     const int r0 = plan_chunk_row(pl, w);
-    chunk_back(pl.reg, ee, so.t_prev, so.h_next, [&](int s, double x) { out[r0 + s] = x; });
+    if (w == 0 && pl.ls0 != L) chunk_back_short(pl.sreg, ee, so.t_prev, so.h_next, [&](int s, double x) { if (s < pl.ls0) out[r0 + s] = x; });
+    else chunk_back(pl.reg, ee, so.t_prev, so.h_next, [&](int s, double x) { out[r0 + s] = x; });
   }
   return 0;
 }
@@ -94,7 +97,7 @@ extern "C" int emul_line(int optype, int ntype, int n, double alfa, int align_ev
   build_line_plan(pl, optype, ntype, n, first_node, nsf, nsl, a, c, ASTR_NWMAX, align_even != 0);
   info[0] = first_node; info[1] = (int)a.size();
   if (!pl.ok) return 1;
-  info[2] = pl.NW; info[3] = pl.sh; info[4] = pl.st; info[5] = pl.W;
+  info[2] = pl.NW; info[3] = pl.sh; info[4] = pl.st; info[5] = pl.W; info[6] = pl.ls0;
   FilterCoef fc;
   build_filter_coef(fc, optype == 1 ? alfa : 0.49, 1.11, 0.98, (optype >= 2) ? alfa : 0.0);
   switch (optype) {

@@ -129,6 +129,29 @@ def test_spongefilter_global(oracle):
     eng.close(); c.close()
 
 
+@pytest.mark.parametrize("kw", [dict(n=(36, 32, 24), homo=(True, False, True), stretch=True),
+                                dict(n=(40, 48, 0), homo=(False, False, True), stretch=True, dimensional=True)])
+def test_checkpoint_staging(oracle, kw):
+    # writeflfed's datasets ro, u1, u2, u3, p, t (src/readwrite.F90:1974-1984) leave the device as dense node arrays,
+    # bit for bit; readcheckpoint + updateq (src/fludyna.F90:254-300) bring a state back and rebuild q from rho, vel, T
+    c, eng = make_pair(oracle, **kw)
+    c.rk_stage(1); eng.rk_stage(1)
+    data = eng.stage_checkpoint()
+    for key, name in zip(("ro", "u1", "u2", "u3", "p", "t"), PRIMS):
+        np.testing.assert_array_equal(data[key], core(eng.get(name)))
+        assert data[key].flags.f_contiguous
+    # a perturbed checkpoint goes back in: primitives bit for bit, q as updateq forms it
+    data["u2"] = data["u2"] * 1.01 + 0.003
+    data["t"] = data["t"] * 0.99
+    eng.restore_checkpoint(data)
+    for key, name in zip(("ro", "u1", "u2", "u3", "p", "t"), PRIMS):
+        np.testing.assert_array_equal(core(eng.get(name)), data[key])
+        a = c.get(name); core(a)[...] = data[key]; c.set(name, a)
+    c.updateq()
+    assert_fields_close(c, eng, QS, OP_TOL, what="updateq after readcheckpoint")
+    eng.close(); c.close()
+
+
 def _poison(c, eng, nodes):
     """Negative density / NaN energy at a few nodes, the same on both sides."""
     for name, val in (("q1", -0.25), ("q5", float("nan"))):

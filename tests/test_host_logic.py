@@ -188,19 +188,24 @@ def test_register_engine_algebra_matches_the_oracle(oracle, tmp_path_factory, op
     lib = _emul_lib(tmp_path_factory)
     rng = np.random.default_rng(10 * op + ntype)
     covered = 0
-    for n in (44, 48, 64, 99, 100, 128, 255, 256, 300, 512, 527):
+    shorts = 0
+    for n in (44, 48, 64, 99, 100, 128, 255, 256, 300, 500, 512, 513, 527):
         for align in (0, 1):
             f = rng.standard_normal(n + 11)
             alfa = 0.49 if op == 1 else (0.3 if op >= 2 else 0.0)
             out = np.zeros(n + 20)
-            info = (ctypes.c_int * 6)()
+            info = (ctypes.c_int * 7)()
             rc = lib.emul_line(op, ntype, n, ctypes.c_double(alfa), align, f.ctypes.data_as(ctypes.c_void_p),
                                out.ctypes.data_as(ctypes.c_void_p), info)
             if rc:
                 assert n < 48, f"no plan for n={n}"      # short lines stay on the shared-memory engine
                 continue
-            first, nrows, nw, sh, st, w = list(info)
-            assert 1 <= nw <= 15 and sh <= 40 and st <= 6 and 1 <= w <= 8
+            first, nrows, nw, sh, st, w, ls0 = list(info)
+            assert 1 <= nw <= 15 and sh <= 40 and st <= 6 and 1 <= w <= 8 and 2 <= ls0 <= 34
+            # the head block stays on the 8-slot path whenever a SHORT first chunk can take the left-over rows
+            assert sh <= 8 or nw == 15 or ls0 == 34, list(info)
+            assert sh + ls0 + (nw - 1) * 34 + st == nrows
+            shorts += ls0 < 34
             if op == 0:
                 ref, lo = oracle.df_compact(f, ntype), 0
             elif op == 1:
@@ -216,7 +221,7 @@ def test_register_engine_algebra_matches_the_oracle(oracle, tmp_path_factory, op
             err = np.abs(got - ref).max() / np.abs(ref).max()
             assert err < 2e-14, (op, ntype, n, align, list(info), err)
             covered += 1
-    assert covered >= 18
+    assert covered >= 18 and shorts >= 4
 
 
 def test_register_engine_falls_back_when_the_coupling_decays_slowly(tmp_path_factory):
@@ -224,7 +229,7 @@ def test_register_engine_falls_back_when_the_coupling_decays_slowly(tmp_path_fac
     # the plan refuses (the shared-memory engine, which does no truncation, takes the line)
     lib = _emul_lib(tmp_path_factory)
     n = 512
-    f = np.zeros(n + 11); out = np.zeros(n + 20); info = (ctypes.c_int * 6)()
+    f = np.zeros(n + 11); out = np.zeros(n + 20); info = (ctypes.c_int * 7)()
     rc = lib.emul_line(1, 3, n, ctypes.c_double(0.4999), 0, f.ctypes.data_as(ctypes.c_void_p),
                        out.ctypes.data_as(ctypes.c_void_p), info)
     assert rc == 1
