@@ -629,7 +629,9 @@ static int init_impl(const astr_cfg* cfg) {
     int dev = 0, khz = 0;
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-    const long long ms = cfg->xchg_timeout_ms == 0 ? 4000 : cfg->xchg_timeout_ms;
+    // default 60 s: ranks of one job skew by seconds around host-side phases (grid generation, uploads, I/O on rank
+    // 0); 4 s (round 1) was exceeded by eight ranks finishing their 20 GB uploads at different times
+    const long long ms = cfg->xchg_timeout_ms == 0 ? 60000 : cfg->xchg_timeout_ms;
     g->xtimeout_cycles = ms < 0 ? 0 : ms * (long long)khz;
   }
   const size_t bytes = (size_t)S_CORE * L.fstride * sizeof(double);

@@ -893,7 +893,7 @@ __global__ void k_copy_box(const Layout L, double* __restrict__ dst, const doubl
 // (L1-bypassing loads), and the last CTA acknowledges to the neighbour.
 // Same element order, averaging of shared nodes and plane ranges as k_face above; for i-faces
 // the plane index runs fastest so that the strided gather touches each sector once.
-// A wait that outlasts a.timeout_cycles (cfg.xchg_timeout_ms; default 4 s, <= 0 waits forever like ncclRecv)
+// A wait that outlasts a.timeout_cycles (cfg.xchg_timeout_ms; default 60 s, < 0 waits forever like ncclRecv)
 // POISONS the exchange: *err is set, the CTA neither moves data nor signals, and every later exchange kernel
 // of this rank returns at once; the neighbours then time out in turn.  The host sees the sticky error at the
 // next API call that synchronises (p2p_check in api.cu).  Nothing is ever unpacked from, or written over, a

@@ -263,7 +263,8 @@ def parity_check(args, torch, dist, world, rank, local_rank, size):
     pn = args.parity_n
     gdims = tuple(pn * s for s in size)
     deltat = 1e-3
-    eng, th, block, cp = gpu_engine(args.case, gdims, size, rank, local_rank, args.conschm, deltat)
+    ekw = {} if args.overlap_visc < 0 else {"overlap_visc": bool(args.overlap_visc)}
+    eng, th, block, cp = gpu_engine(args.case, gdims, size, rank, local_rank, args.conschm, deltat, ekw)
     if world > 1:
         eng.comm_init(world, rank, make_bcast(dist, torch, rank))
     c, _, _ = oracle_case(pyoracle, args.case, gdims, size, args.conschm, deltat)
@@ -361,7 +362,8 @@ def run_gpu(args):
         parity = parity_check(args, torch, dist, world, rank, local_rank, size)
 
     gdims = tuple(n * s for s in size)                      # weak scaling: n^3 per GPU
-    eng, th, block, cp = gpu_engine(args.case, gdims, size, rank, local_rank, args.conschm, 1e-3 * 128 / n)
+    ekw = {} if args.overlap_visc < 0 else {"overlap_visc": bool(args.overlap_visc)}
+    eng, th, block, cp = gpu_engine(args.case, gdims, size, rank, local_rank, args.conschm, 1e-3 * 128 / n, ekw)
     if world > 1:
         eng.comm_init(world, rank, make_bcast(dist, torch, rank))
     # synthetic input: grid (gridcube / grichan) + initial state (tgvini / chanini), metrics on the device
@@ -383,6 +385,7 @@ def run_gpu(args):
             dist.barrier()
 
     # ---- device-resident timing --------------------------------------------------------------
+    barrier()        # the ranks finish their uploads seconds apart: line them up before the first exchange
     eng.steploop(args.warmup)
     barrier()
     eng.set_profile(True)
@@ -522,6 +525,9 @@ def main():
                     help="643: central compact convection (the BASELINE metric); 543: upwind compact path")
     ap.add_argument("--layout", default="", help="block grid isize,jsize,ksize (default: mpisizedis)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--overlap-visc", type=int, default=-1,
+                    help="multi-block runs: sigma/qflux exchange on a side stream behind the interior stress+flux pass "
+                         "(cfg.overlap_visc); -1: the library default")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

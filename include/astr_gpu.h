@@ -83,7 +83,7 @@ typedef struct astr_cfg {
                                  peer-memory stores (CUDA IPC)                          */
   int xchg_timeout_ms;        /* peer-memory exchange: a neighbour flag that does not
                                  arrive within this time poisons the exchange (sticky
-                                 error at the next synchronising call).  0: 4000 ms;
+                                 error at the next synchronising call).  0: 60 s;
                                  < 0: wait forever, like ncclRecv / MPI_Sendrecv         */
   int reserved0;              /* keeps the doubles 8-byte aligned; must be 0            */
   double alfa_filter;         /* 0.49 in every example                                   */
