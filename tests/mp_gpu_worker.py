@@ -65,6 +65,8 @@ def main():
         shk = auto_shkcrt(c)
         c.set_upwind(543, True, 0.3, shk)
         kw.update(conschm=543, lchardecomp=True, bfacmpld=0.3, shkcrt=shk)
+    if "overlap" in modes:      # cfg.overlap_visc: sigma/qflux exchange on the side stream behind the interior pass
+        kw.update(overlap_visc=True)
     eng = RhsEngine(blk, n, homo, th, deltat=1e-3, device=local, **kw)
     if channel:
         eng.set_force(force)

@@ -209,3 +209,40 @@ def flux_compact(f, ntype, dim, plus, bfacmpld=0.3):
         d[last] = np.dot(explicit6, p.window(range(last - 2, last + 4)))
     x = _solve(rows, lower, upper, d)
     return np.array([x[n] for n in range(-1, dim + 1)])
+
+
+# ------------------------------------------------------------------------------------------------
+# explicit 6th-order central derivative with the 2-2-4 wall ladder ('642e', src/derivative.F90:338-413)
+# ------------------------------------------------------------------------------------------------
+def _fd_weights(offsets):
+    """Exact first-derivative weights on the integer stencil `offsets` (unit spacing): the unique weights that
+    differentiate every polynomial of degree < len(offsets) exactly (Vandermonde system over the rationals).
+    The reference hard-codes them (0.75, -0.15, 1/60; 2/3, -1/12; ...); here they are DERIVED."""
+    n = len(offsets)
+    # sum_j w_j * offsets_j**p = d/dx x**p at 0 = (1 if p == 1 else 0)
+    A = [[Fr(o) ** p for o in offsets] + [Fr(1 if p == 1 else 0)] for p in range(n)]
+    for col in range(n):                              # Gauss-Jordan over Fraction
+        piv = next(r for r in range(col, n) if A[r][col] != 0)
+        A[col], A[piv] = A[piv], A[col]
+        A[col] = [v / A[col][col] for v in A[col]]
+        for r in range(n):
+            if r != col and A[r][col] != 0:
+                A[r] = [vr - A[r][col] * vc for vr, vc in zip(A[r], A[col])]
+    return [float(A[r][n]) for r in range(n)]
+
+
+def diff6ec(f, ntype, dim):
+    p = Pencil(f, dim)
+    lo_wall, hi_wall = _wall(ntype)
+    out = np.empty(dim + 1)
+    for i in range(dim + 1):
+        lo, hi = (i if lo_wall else HM), (dim - i if hi_wall else HM)      # nodes available towards each wall
+        if lo == 0:
+            offs = [0, 1, 2]                          # one-sided 2nd order at the wall node
+        elif hi == 0:
+            offs = [0, -1, -2]
+        else:
+            half = min(lo, hi, 3)                     # central: 2nd order next to the wall, 4th, then 6th
+            offs = list(range(-half, half + 1))
+        out[i] = np.dot(_fd_weights(offs), p.window([i + o for o in offs]))
+    return out

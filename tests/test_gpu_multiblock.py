@@ -73,3 +73,12 @@ def test_two_blocks_register_engine_walls_in_i(oracle):
 
 def test_two_blocks_register_engine_walls_in_k(oracle):
     _run(2, "1,1,2", "1,1,0", "48,56,112", 1, 29721)
+
+
+def test_two_blocks_overlapped_stress_exchange(oracle):
+    # cfg.overlap_visc = 1: shell pass -> sigma/qflux exchange on the side stream -> interior stress+flux pass -> join
+    _run(2, "1,1,2", "1,1,1", "32,32,48", 2, 29722, extra=("overlap",))
+
+
+def test_eight_blocks_overlapped_stress_exchange_with_walls(oracle):
+    _run(8, "2,2,2", "1,0,1", "48,48,48", 2, 29723, extra=("overlap",))

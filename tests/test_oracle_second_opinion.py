@@ -68,3 +68,11 @@ def test_second_opinion_is_not_a_copy_of_the_oracle_tables(oracle):
         want[0] = 0.98 if ntype in (1, 4) else 1.11
         want[-1] = 0.98 if ntype in (2, 4) else 1.11
         assert np.array_equal(a, want) and np.array_equal(c, want)
+
+
+@pytest.mark.parametrize("dim", [16, 37])
+@pytest.mark.parametrize("ntype", [1, 2, 3, 4])
+def test_explicit_derivative_ladder(oracle, ntype, dim):
+    """diff6ec against finite-difference weights DERIVED from polynomial exactness on the same stencils."""
+    f = np.random.default_rng(400 + dim + ntype).standard_normal(dim + 1 + 2 * HM)
+    assert _rel(oracle.diff6ec(f, ntype), so.diff6ec(f, ntype, dim)) < TOL
