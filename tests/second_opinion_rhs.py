@@ -10,7 +10,8 @@ Written from the Fortran alone:
   convrsdcal6   src/solver.F90:2173-2341      J*(rho U, rho u U + xi_x p, ..., (E+p) U), compact derivative
   diffrsdcal6   src/solver.F90:2354-2873      sigma, qflux pointwise on 0:N; dataswap; metric contraction * J; derivative
   miucal        src/fludyna.F90:791-812       nondimensional Sutherland law
-  dataswap      src/parallel.F90:4169-4174    single-block periodic wrap: halo -k <- node N-k, halo N+k <- node k
+  dataswap      src/parallel.F90:4132-4370    halo -k <- low neighbour's node N-k, halo N+k <- high neighbour's node k
+                                              (a periodic direction owned by one block wraps onto itself, :4169-4174)
 
 Arrays are the oracle's own (halo'd, Fortran order, index = node + 5); what is compared is everything computed
 from them.  Unlike the oracle this code works on whole arrays (einsum / broadcasting), solves each direction's
@@ -43,19 +44,29 @@ def _core_other_axes(a, axis):
     return a[tuple(sl)]
 
 
-def wrap_halos(a, homo):
-    """dataswap of a single block: periodic directions wrap (shared end node), the others keep what they have."""
-    for ax in range(3):
-        if not homo[ax]:
-            continue
-        n = a.shape[ax] - 1 - 2 * HM
-        idx = [slice(HM, -HM)] * 3            # the reference copies 0:jm, 0:km of the other two directions only
-        lo, src_lo, hi, src_hi = list(idx), list(idx), list(idx), list(idx)
-        lo[ax], src_lo[ax] = slice(0, HM), slice(n, n + HM)                       # -5..-1  <-  N-5..N-1
-        hi[ax], src_hi[ax] = slice(n + HM + 1, n + 2 * HM + 1), slice(HM + 1, 2 * HM + 1)   # N+1..N+5 <- 1..5
-        a[tuple(lo)] = a[tuple(src_lo)]
-        a[tuple(hi)] = a[tuple(src_hi)]
-    return a
+def exchange_halos(arrs, blocks, homo):
+    """dataswap of one field over all blocks (src/parallel.F90:4132-4370): halo planes -5..-1 take the low
+    neighbour's nodes N-5..N-1, halo planes N+1..N+5 the high neighbour's nodes 1..5 (blocks share their end
+    nodes); a periodic direction owned by one block wraps onto itself (:4169-4174); faces without a neighbour keep
+    what they have.  Only nodes 0..N of the two other directions travel."""
+    out = [a.copy() for a in arrs]
+    for b, F in enumerate(blocks):
+        for ax in range(3):
+            n = arrs[b].shape[ax] - 1 - 2 * HM
+            lo_nb, hi_nb = F.nb[2 * ax], F.nb[2 * ax + 1]
+            if lo_nb < 0 and hi_nb < 0 and homo[ax]:
+                lo_nb = hi_nb = b
+            idx = [slice(HM, -HM)] * 3
+            if lo_nb >= 0:
+                nn = arrs[lo_nb].shape[ax] - 1 - 2 * HM
+                dst, src = list(idx), list(idx)
+                dst[ax], src[ax] = slice(0, HM), slice(nn, nn + HM)                            # -5..-1 <- N-5..N-1
+                out[b][tuple(dst)] = arrs[lo_nb][tuple(src)]
+            if hi_nb >= 0:
+                dst, src = list(idx), list(idx)
+                dst[ax], src[ax] = slice(n + HM + 1, n + 2 * HM + 1), slice(HM + 1, 2 * HM + 1)    # N+1..N+5 <- 1..5
+                out[b][tuple(dst)] = arrs[hi_nb][tuple(src)]
+    return out
 
 
 class Fields:
@@ -70,6 +81,7 @@ class Fields:
         self.dxi = [[g(f"dxi{d + 1}{n + 1}") for n in range(3)] for d in range(3)]     # dxi[d][n] = d xi_d / d x_n
         info = c.block_info(ib)
         self.npdc = info["npdc"]
+        self.nb = info["nb"]                     # neighbour block per face (ilo, ihi, jlo, jhi, klo, khi) or -1
         r = info["is_ie"]
         self.lo, self.hi = (r[0], r[2], r[4]), (r[1], r[3], r[5])                 # is, js, ks / ie, je, ke
 
@@ -108,46 +120,53 @@ def stress_and_heat_flux(F, dvel, dtmp, th):
     return tau, qf
 
 
-def rhscal(F, th, homo, diffterm=True):
-    """qrhs(5) on nodes 0..N, zero outside the ranges the reference updates."""
-    shape = core(F.prs).shape
-    qrhs = [np.zeros(shape) for _ in range(5)]
-    lo, hi = F.lo, F.hi
+def rhscal_blocks(blocks, th, homo, diffterm=True):
+    """qrhs(5) on nodes 0..N of every block, zero outside the ranges the reference updates."""
 
     def box(ranges):
         return tuple(slice(a, b + 1) for a, b in ranges)
 
-    # ---- convection: loops over js:je, ks:ke (resp.) and adds on is:ie -> the box is:ie x js:je x ks:ke --------------
-    conv_box = box(zip(lo, hi))
-    for d in range(3):
-        U = sum(F.dxi[d][n] * F.vel[n] for n in range(3))
-        flux = [F.jacob * F.q[0] * U] + \
-               [F.jacob * (F.q[1 + n] * U + F.dxi[d][n] * F.prs) for n in range(3)] + \
-               [F.jacob * (F.q[4] + F.prs) * U]
-        for m in range(5):
-            qrhs[m][conv_box] += core_d(deriv(flux[m], d, ntype_of(F.npdc[d])), d)[conv_box]
-    qrhs = [-r for r in qrhs]
+    out = []
+    for F in blocks:
+        qrhs = [np.zeros(core(F.prs).shape) for _ in range(5)]
+        # convection: loops over js:je, ks:ke (resp.) and adds on is:ie -> the box is:ie x js:je x ks:ke
+        conv_box = box(zip(F.lo, F.hi))
+        for d in range(3):
+            U = sum(F.dxi[d][n] * F.vel[n] for n in range(3))
+            flux = [F.jacob * F.q[0] * U] + \
+                   [F.jacob * (F.q[1 + n] * U + F.dxi[d][n] * F.prs) for n in range(3)] + \
+                   [F.jacob * (F.q[4] + F.prs) * U]
+            for m in range(5):
+                qrhs[m][conv_box] += core_d(deriv(flux[m], d, ntype_of(F.npdc[d])), d)[conv_box]
+        out.append([-r for r in qrhs])
     if not diffterm:
-        return qrhs
-    # ---- diffusion -----------------------------------------------------------------------------------------------
-    dvel, dtmp = gradcal(F)
-    tau, qf = stress_and_heat_flux(F, dvel, dtmp, th)
+        return out
+    # diffusion: pointwise stresses per block, one exchange of the 9 fields, then the contracted fluxes
+    fields = [[] for _ in range(9)]
+    for F in blocks:
+        dvel, dtmp = gradcal(F)
+        tau, qf = stress_and_heat_flux(F, dvel, dtmp, th)
+        for slot, a in enumerate([tau[0][0], tau[0][1], tau[0][2], tau[1][1], tau[1][2], tau[2][2]] + qf):
+            full = np.zeros(F.prs.shape)
+            core(full)[...] = a
+            fields[slot].append(full)
+    fields = [exchange_halos(f, blocks, homo) for f in fields]
+    sym = {(0, 0): 0, (0, 1): 1, (0, 2): 2, (1, 1): 3, (1, 2): 4, (2, 2): 5}
+    for b, F in enumerate(blocks):
+        tauh = [[fields[sym[(min(a, c), max(a, c))]][b] for c in range(3)] for a in range(3)]
+        qfh = [fields[6 + n][b] for n in range(3)]
+        n_nodes = [s - 1 for s in core(F.prs).shape]
+        for d in range(3):
+            # loops over 0:N of the two other directions, adds on (is:ie | js:je | ks:ke) of direction d only
+            ranges = [(0, n_nodes[a]) for a in range(3)]
+            ranges[d] = (F.lo[d], F.hi[d])
+            dbox = box(ranges)
+            cols = [sum(tauh[m][n] * F.dxi[d][n] for n in range(3)) * F.jacob for m in range(3)] + \
+                   [sum(qfh[n] * F.dxi[d][n] for n in range(3)) * F.jacob]
+            for m in range(4):
+                out[b][1 + m][dbox] += core_d(deriv(cols[m], d, ntype_of(F.npdc[d])), d)[dbox]
+    return out
 
-    def halo_field(a):
-        full = np.zeros(F.prs.shape)
-        core(full)[...] = a
-        return wrap_halos(full, homo)
 
-    tauh = [[halo_field(tau[a][b]) for b in range(3)] for a in range(3)]
-    qfh = [halo_field(q) for q in qf]
-    n_nodes = [s - 1 for s in shape]
-    for d in range(3):
-        # loops over 0:N of the two other directions, adds on (is:ie | js:je | ks:ke) of direction d only
-        ranges = [(0, n_nodes[a]) for a in range(3)]
-        ranges[d] = (lo[d], hi[d])
-        dbox = box(ranges)
-        cols = [sum(tauh[m][n] * F.dxi[d][n] for n in range(3)) * F.jacob for m in range(3)] + \
-               [sum(qfh[n] * F.dxi[d][n] for n in range(3)) * F.jacob]
-        for m in range(4):
-            qrhs[1 + m][dbox] += core_d(deriv(cols[m], d, ntype_of(F.npdc[d])), d)[dbox]
-    return qrhs
+def rhscal(F, th, homo, diffterm=True):
+    return rhscal_blocks([F], th, homo, diffterm)[0]

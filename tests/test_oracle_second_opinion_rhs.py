@@ -1,0 +1,73 @@
+"""oracle/solver.cpp's gradcal and rhscal (central compact path) against the independent NumPy restatement
+tests/second_opinion_rhs.py on curvilinear grids: periodic, wall-bounded (ranges is:ie ...) and multi-block
+(interface closures ntype 1 / 2, exchanged stress halos).  SURVEY.md 8c lists exactly these as not pinned by any
+stored number of the reference."""
+import numpy as np
+import pytest
+
+import second_opinion_rhs as R
+from gpu_common import stretched_x
+
+# measured: <= 9.5e-15 (continuity, whose scale is 1e-2 of the others), <= 3.5e-15 for the other fields
+TOL = 1e-13
+GAMMA, PRANDTL = 1.4, 0.72
+
+
+def _case(oracle, n, homo, blocks=(1, 1, 1), reynolds=1600.0, mach=0.1):
+    c = oracle.Case(*n, blocks=blocks, homo=homo, reynolds=reynolds, mach=mach)
+    x = stretched_x(n, homo)
+    if blocks == (1, 1, 1):
+        c.set_x(x)
+    else:      # every block gets its part of the global grid (blocks share their end nodes)
+        for ib in range(c.nblocks):
+            info = c.block_info(ib)
+            g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+            c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom()
+    c.tgvini()
+    rng = np.random.default_rng(5)
+    for ib in range(c.nblocks):
+        for m in range(5):
+            a = c.get(f"q{m + 1}", ib)
+            a *= 1.0 + 1e-2 * rng.standard_normal(a.shape)
+            c.set(f"q{m + 1}", a, ib)
+    c.updatefvar(); c.qswap(); c.zero_qrhs(); c.gradcal(); c.rhscal()
+    th = dict(tempconst=110.3 / 273.15, reynolds=reynolds, prandtl=PRANDTL, const5=(GAMMA - 1.0) * mach ** 2)
+    return c, th
+
+
+def _check(c, th, homo):
+    blocks = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    worst = 0.0
+    for ib, F in enumerate(blocks):
+        dvel, dtmp = R.gradcal(F)
+        ref = [[R.core(c.get(f"dvel{a + 1}{b + 1}", ib)) for b in range(3)] for a in range(3)]
+        scale = max(np.abs(r).max() for row in ref for r in row)
+        worst = max(worst, max(np.abs(dvel[a][b] - ref[a][b]).max() for a in range(3) for b in range(3)) / scale)
+        reft = [R.core(c.get(f"dtmp{a + 1}", ib)) for a in range(3)]
+        scale = max(np.abs(r).max() for r in reft)
+        worst = max(worst, max(np.abs(dtmp[a] - reft[a]).max() for a in range(3)) / scale)
+    got = R.rhscal_blocks(blocks, th, homo)
+    for ib in range(c.nblocks):
+        for m in range(5):
+            ref = R.core(c.get(f"qrhs{m + 1}", ib))
+            worst = max(worst, np.abs(got[ib][m] - ref).max() / np.abs(ref).max())
+    return worst
+
+
+@pytest.mark.parametrize("n,homo", [((16, 14, 12), (True, True, True)),
+                                    ((16, 14, 12), (True, False, True)),       # channel-like: walls in j (ntype 4)
+                                    ((14, 16, 12), (False, True, False))])
+def test_rhs_single_block(oracle, n, homo):
+    c, th = _case(oracle, n, homo)
+    assert _check(c, th, homo) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("n,homo,blocks", [((28, 12, 12), (False, True, True), (2, 1, 1)),   # ntype 1 | 2 in i
+                                           ((12, 28, 14), (True, False, True), (1, 2, 1)),
+                                           ((24, 12, 24), (True, True, True), (2, 1, 2))])   # periodic pairs
+def test_rhs_multi_block(oracle, n, homo, blocks):
+    c, th = _case(oracle, n, homo, blocks)
+    assert _check(c, th, homo) < TOL
+    c.close()
