@@ -1,0 +1,109 @@
+"""A SECOND, independent restatement of one Runge-Kutta stage of the main solver's `time_integration_rk`
+(src/mainloop.F90:396-482) for periodic block grids, in whole-array NumPy on top of tests/second_opinion.py and
+tests/second_opinion_rhs.py.  Test infrastructure: it cross-checks the STAGE ORDER and the exchange semantics of
+oracle/solver.cpp, which no stored number of the reference pins.
+
+  filterq   src/comsolver.F90:514-632   per direction: dataswap(q, direction) -- a plain copy -- then the filter
+  qswap     src/parallel.F90:4848-5318  per direction i, j, k: 5 halo planes + the shared end node AVERAGED, then
+                                        q2fvar on the slabs -5..0 and N..N+5 only (interior primitives stay pre-filter)
+  qsave = q J at stage 1; rhscal; RK3 update (coefficients :350-366); updatefvar = q2fvar on 0..N
+  q2fvar    src/fludyna.F90:545-634 with thermal_3d :136-179 (nondimensional)
+Physical boundaries (boucon) are not restated: every direction of the test cases is periodic.
+"""
+import numpy as np
+
+import second_opinion as so
+import second_opinion_rhs as R
+
+HM = 5
+RKCOE = [(1.0, 0.0, 1.0), (0.75, 0.25, 0.25), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0)]
+
+
+def _sl(ax, s, n_other=slice(HM, -HM)):
+    idx = [n_other] * 3
+    idx[ax] = s
+    return tuple(idx)
+
+
+def _n(a, ax):
+    return a.shape[ax] - 1 - 2 * HM
+
+
+def _neighbours(b, F, ax, homo):
+    lo, hi = F.nb[2 * ax], F.nb[2 * ax + 1]
+    if lo < 0 and hi < 0 and homo[ax]:
+        lo = hi = b
+    return lo, hi
+
+
+def filter_axis(a, ax, ntype, alfa):
+    """compact_filter along `ax` for every pencil of nodes 0..N of the other two directions; in place on 0..N."""
+    Fm = np.moveaxis(a, ax, 0)
+    shp = Fm.shape
+    dim = shp[0] - 1 - 2 * HM
+    out = so.compact_filter(Fm.reshape(shp[0], -1), ntype, dim, alfa).reshape((dim + 1,) + shp[1:])
+    out = np.moveaxis(out, 0, ax)
+    a[_sl(ax, slice(HM, -HM))] = out[_sl(ax, slice(None))]
+
+
+def filterq(blocks, homo, alfa=0.49):
+    for ax in range(3):
+        for m in range(5):
+            new = R.exchange_halos([F.q[m] for F in blocks], blocks, [h if a == ax else False for a, h in enumerate(homo)])
+            for F, a in zip(blocks, new):
+                # exchange_halos treats every direction: keep only this direction's halos
+                F.q[m][_sl(ax, slice(0, HM))] = a[_sl(ax, slice(0, HM))]
+                F.q[m][_sl(ax, slice(-HM, None))] = a[_sl(ax, slice(-HM, None))]
+        for F in blocks:
+            for m in range(5):
+                filter_axis(F.q[m], ax, R.ntype_of(F.npdc[ax]), alfa)
+
+
+def q2fvar(F, idx, th):
+    rho = F.q[0][idx]
+    v = [F.q[1 + n][idx] / rho for n in range(3)]
+    prs = (F.q[4][idx] - 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)) / th["const6"]
+    F.rho[idx] = rho
+    for n in range(3):
+        F.vel[n][idx] = v[n]
+    F.prs[idx] = prs
+    F.tmp[idx] = prs / rho * th["const2"]
+
+
+def qswap(blocks, homo, th):
+    for ax in range(3):
+        pre = [[q.copy() for q in F.q] for F in blocks]          # what the send buffers hold
+        for b, F in enumerate(blocks):
+            lo, hi = _neighbours(b, F, ax, homo)
+            n = _n(F.q[0], ax)
+            for m in range(5):
+                if hi >= 0:
+                    F.q[m][_sl(ax, slice(n + HM + 1, n + 2 * HM + 1))] = pre[hi][m][_sl(ax, slice(HM + 1, 2 * HM + 1))]
+                    F.q[m][_sl(ax, slice(n + HM, n + HM + 1))] = 0.5 * (pre[b][m][_sl(ax, slice(n + HM, n + HM + 1))] +
+                                                                      pre[hi][m][_sl(ax, slice(HM, HM + 1))])
+                if lo >= 0:
+                    nl = _n(pre[lo][m], ax)
+                    F.q[m][_sl(ax, slice(0, HM))] = pre[lo][m][_sl(ax, slice(nl, nl + HM))]
+                    F.q[m][_sl(ax, slice(HM, HM + 1))] = 0.5 * (pre[b][m][_sl(ax, slice(HM, HM + 1))] +
+                                                               pre[lo][m][_sl(ax, slice(nl + HM, nl + HM + 1))])
+            if hi >= 0:
+                q2fvar(F, _sl(ax, slice(n + HM, n + 2 * HM + 1)), th)
+            if lo >= 0:
+                q2fvar(F, _sl(ax, slice(0, HM + 1)), th)
+
+
+def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49):
+    """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1."""
+    filterq(blocks, homo, alfa)
+    qswap(blocks, homo, th)
+    c = (slice(HM, -HM),) * 3
+    if rkstep == 1:
+        for b, F in enumerate(blocks):
+            qsave[b] = [F.q[m][c] * F.jacob[c] for m in range(5)]
+    qrhs = R.rhscal_blocks(blocks, th, homo)
+    a1, a2, a3 = RKCOE[rkstep - 1]
+    for b, F in enumerate(blocks):
+        J = F.jacob[c]
+        for m in range(5):
+            F.q[m][c] = (a1 * qsave[b][m] + a2 * F.q[m][c] * J + a3 * qrhs[b][m] * deltat) / J
+        q2fvar(F, c, th)
