@@ -14,7 +14,8 @@ What is restated, and how it differs from the oracle's line-by-line form:
   iwind6                src/solver.F90:1236-1257   clamped 5-node stencils, mirrored for the '-' flux
   mplimiter, MP5        src/flux.F90:363-379, :434-501 (minmod2 / minmod4 src/commfunc.F90:699-738)
   flux_compact          tests/second_opinion.py (dense solves)
-`lshock` (the Ducros flags) is an input; `crinod` is all false.
+`lshock` (the Ducros flags) is an input of `convrsdcmp`; `ducros_ssf` / `ducros_flags` below restate the sensor itself
+(src/commcal.F90:196-357).  `crinod` is all false.
 """
 import numpy as np
 
@@ -191,3 +192,42 @@ def convrsdcmp(F, gamma, lshock, lchardecomp=True, bfacmpld=0.3):
         for m in range(5):
             qrhs[m][tuple(tgt)] += inc[m]
     return qrhs
+
+
+# ------------------------------------------------------------------------------------------------
+# ducrossensor (src/commcal.F90:196-357)
+# ------------------------------------------------------------------------------------------------
+def _shift(a, ax, off, npdc, core_only=True):
+    """a(node + off) along `ax` on nodes 0..N of every direction; the index is clamped at a physical boundary of an
+    end block (npdc 1: below 0, npdc 2: above N), exactly as the reference does -- and NOT for npdc 4."""
+    n = a.shape[ax] - 1 - 2 * HM
+    idx = np.arange(n + 1) + off
+    if npdc == 1:
+        idx = np.maximum(idx, 0)
+    if npdc == 2:
+        idx = np.minimum(idx, n)
+    sl = [slice(HM, -HM)] * 3
+    out = np.take(a, idx + HM, axis=ax)
+    sl[ax] = slice(None)
+    return out[tuple(sl)]
+
+
+def ducros_ssf(F, dvel):
+    """ssf on nodes 0..N from the velocity gradient dvel[m][n] (nodes 0..N) and the halo'd pressure."""
+    div2 = (dvel[0][0] + dvel[1][1] + dvel[2][2]) ** 2
+    vort = (dvel[2][1] - dvel[1][2]) ** 2 + (dvel[0][2] - dvel[2][0]) ** 2 + (dvel[1][0] - dvel[0][1]) ** 2
+    p0 = F.prs[HM:-HM, HM:-HM, HM:-HM]
+    dp = []
+    for ax in range(3):
+        pp, pm = _shift(F.prs, ax, 1, F.npdc[ax]), _shift(F.prs, ax, -1, F.npdc[ax])
+        dp.append(np.abs(pp - 2.0 * p0 + pm) / (pp + 2.0 * p0 + pm))
+    return div2 / (div2 + vort + 1e-30) * np.maximum(np.maximum(dp[0], dp[1]), dp[2])
+
+
+def ducros_flags(ssf_halo, npdc, shkcrt):
+    """lshock (0/1) on nodes 0..N from the halo'd (exchanged) sensor: maximum over nodes -4..+5 of each direction."""
+    best = np.zeros(tuple(s - 2 * HM for s in ssf_halo.shape))
+    for ax in range(3):
+        for off in range(-HM + 1, HM + 1):
+            best = np.maximum(best, _shift(ssf_halo, ax, off, npdc[ax]))
+    return (best > shkcrt).astype(float)

@@ -98,3 +98,42 @@ def test_convrsdcmp_with_supersonic_pockets(oracle):
     worst, _ = _compare(c, True)
     assert worst < TOL
     c.close()
+
+
+@pytest.mark.parametrize("n,homo,blocks", [((16, 14, 12), (True, True, True), (1, 1, 1)),
+                                           ((24, 14, 24), (True, True, True), (2, 1, 2)),
+                                           ((28, 12, 12), (False, True, True), (2, 1, 1)),     # clamped at the walls
+                                           ((16, 14, 12), (True, False, True), (1, 1, 1))])
+def test_ducrossensor(oracle, n, homo, blocks):
+    """ssf to rounding, lshock flag for flag (the threshold sits in the widest gap of the sensor values).  For a
+    direction with both walls in one block (npdc 4) the reference neither clamps the index nor fills the halo of
+    ssf (allocated, never set: src/commcal.F90:212); like the oracle this restatement reads zeros there."""
+    c = oracle.Case(*n, blocks=blocks, homo=homo)
+    _grid(c, n, homo)
+    c.tgvini()
+    rng = np.random.default_rng(5)
+    for ib in range(c.nblocks):
+        for m in range(5):
+            a = c.get(f"q{m + 1}", ib)
+            a *= 1.0 + 2e-2 * rng.standard_normal(a.shape)
+            c.set(f"q{m + 1}", a, ib)
+    c.updatefvar()
+    shk = auto_shkcrt(c, 0.3)
+    c.set_upwind(543, True, 0.3, shk)
+    c.qswap(); c.gradcal(); c.ducrossensor()
+    blk = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    ssf = []
+    for ib, F in enumerate(blk):
+        dvel, _ = R.gradcal(F)
+        s = U.ducros_ssf(F, dvel)
+        ref = R.core(c.get("ssf", ib))
+        assert np.abs(s - ref).max() <= 1e-13 * ref.max()
+        full = np.zeros(F.prs.shape)
+        R.core(full)[...] = s
+        ssf.append(full)
+    ssf = R.exchange_halos(ssf, blk, homo)
+    for ib, F in enumerate(blk):
+        ref = R.core(c.get("lshock", ib))
+        assert 0.2 < ref.mean() < 0.8
+        assert np.array_equal(U.ducros_flags(ssf[ib], F.npdc, shk), ref)
+    c.close()
