@@ -170,3 +170,23 @@ def rhscal_blocks(blocks, th, homo, diffterm=True):
 
 def rhscal(F, th, homo, diffterm=True):
     return rhscal_blocks([F], th, homo, diffterm)[0]
+
+
+def src_chan(blocks, ys, force):
+    """src_chan (src/solver.F90:295-353): trapezoidal bulk integrals of q1..q4 over y, summed over cells i = 1..N,
+    k = 1..N of every block (psum), then force * J on the momentum and force . u_bulk * J on the energy equation.
+    ys[b]: halo'd y coordinate of block b.  Returns the increments of qrhs(5) per block (nodes 0..N)."""
+    tot = np.zeros(4)
+    for F, y in zip(blocks, ys):
+        yc = core(y)
+        dy = (yc[1:, 1:, 1:] - yc[1:, :-1, 1:])
+        for m in range(4):
+            qm = core(F.q[m])
+            tot[m] += np.sum(0.5 * (qm[1:, :-1, 1:] + qm[1:, 1:, 1:]) * dy)
+    ubulk = tot[1:] / tot[0]
+    out = []
+    for F in blocks:
+        J = core(F.jacob)
+        out.append([np.zeros(J.shape)] + [force[n] * J for n in range(3)] +
+                   [(force[0] * ubulk[0] + force[1] * ubulk[1] + force[2] * ubulk[2]) * J])
+    return out

@@ -71,3 +71,38 @@ def test_rhs_multi_block(oracle, n, homo, blocks):
     c, th = _case(oracle, n, homo, blocks)
     assert _check(c, th, homo) < TOL
     c.close()
+
+
+@pytest.mark.parametrize("n,blocks", [((16, 20, 12), (1, 1, 1)), ((24, 28, 12), (2, 2, 1))])
+def test_rhs_channel_with_bulk_forcing(oracle, n, blocks):
+    """examples/Channel option set: walls in y (one block: ntype 4; split in y: ntype 1 | 2), grichan stretching,
+    src_chan with the bulk velocity summed over blocks."""
+    from gpu_common import channel_state, channel_x
+    homo, lengths, force = (True, False, True), (2 * np.pi, 2.0, np.pi), (2.5e-3, 1e-4, 3e-4)
+    reynolds, mach = 3000.0, 0.3
+    c = oracle.Case(*n, blocks=blocks, homo=homo, reynolds=reynolds, mach=mach, lengths=lengths)
+    c.set_bc((1, 1, 41, 41, 1, 1), (0, 0, 1.0, 1.0, 0, 0))
+    c.set_flow(1, force)
+    x = channel_x(n, lengths)
+    for ib in range(c.nblocks):
+        info = c.block_info(ib)
+        g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+        c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom()
+    th = dict(tempconst=110.3 / 273.15, reynolds=reynolds, prandtl=PRANDTL, const5=(GAMMA - 1.0) * mach ** 2,
+              gamma=GAMMA, mach=mach, const1=1.0 / (GAMMA * (GAMMA - 1.0) * mach ** 2), const2=GAMMA * mach ** 2)
+    for ib in range(c.nblocks):
+        channel_state(c, th, ib=ib)
+    c.updatefvar(); c.qswap(); c.zero_qrhs(); c.gradcal(); c.rhscal()
+    blk = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    got = R.rhscal_blocks(blk, th, homo)
+    src = R.src_chan(blk, [c.get("x2", ib) for ib in range(c.nblocks)], force)
+    for ib in range(c.nblocks):
+        for m in range(5):
+            ref = R.core(c.get(f"qrhs{m + 1}", ib))
+            # measured 5.6e-14 / 5.9e-14
+            assert np.abs(got[ib][m] + src[ib][m] - ref).max() <= 1e-12 * np.abs(ref).max(), (ib, m)
+        # the forcing itself is visible: without it the x-momentum row is off by force * J
+        ref2 = R.core(c.get("qrhs2", ib))
+        assert np.abs(got[ib][1] - ref2).max() > 1e-4 * np.abs(src[ib][1]).max()
+    c.close()
