@@ -8,7 +8,7 @@ oracle/solver.cpp, which no stored number of the reference pins (q
                                         q2fvar on the slabs -5..0 and N..N+5 only (interior primitives stay pre-filter)
   qsave = q J at stage 1; rhscal; RK3 update (coefficients :350-366); updatefvar = q2fvar on 0..N
   q2fvar    src/fludyna.F90:545-634 with thermal_3d :136-179 (nondimensional)
-Physical boundaries (boucon) are not restated: every direction of the test cases is periodic.
+Physical boundaries: the isothermal no-slip wall (bctype 41) is restated (`noslip`), the other types are not.
 """
 import numpy as np
 
@@ -92,15 +92,47 @@ def qswap(blocks, homo, th):
                 q2fvar(F, _sl(ax, slice(0, HM + 1)), th)
 
 
-def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49):
-    """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1."""
+def noslip(blocks, homo, bctype, twall, th):
+    """boucon -> noslip (bctype 41) on the faces a block owns (src/bc.F90:327-407, :6306-6723): wall pressure
+    extrapolated from the two interior nodes (pe = (4 p1 - p2)/3, from the primitives as they stand: quirk Q10), zero
+    velocity, wall temperature; density from the gas law, q from fvar2q with pressure (src/fludyna.F90:312-376)."""
+    for face in range(6):                               # imin, imax, jmin, jmax, kmin, kmax: the reference's order
+        if bctype[face] != 41:
+            continue
+        ax, side = face // 2, face % 2
+        for F in blocks:
+            if homo[ax] or F.nb[face] >= 0:
+                continue
+            n = _n(F.prs, ax)
+            w, s = (n, -1) if side else (0, 1)
+            at = lambda i: _sl(ax, slice(i + HM, i + HM + 1))
+            pe = (4.0 * F.prs[at(w + s)] - F.prs[at(w + 2 * s)]) / 3.0
+            for v in F.vel:
+                v[at(w)] = 0.0
+            F.prs[at(w)] = pe
+            F.tmp[at(w)] = twall[face]
+            F.rho[at(w)] = pe / twall[face] * th["const2"]
+            F.q[0][at(w)] = F.rho[at(w)]
+            for m in (1, 2, 3):
+                F.q[m][at(w)] = 0.0
+            F.q[4][at(w)] = pe * th["const6"]
+
+
+def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None):
+    """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: faces with
+    no-slip walls (41); force, ys: the channel's body force and the halo'd y coordinate per block (src_chan)."""
     filterq(blocks, homo, alfa)
+    if bctype is not None:
+        noslip(blocks, homo, bctype, twall, th)
     qswap(blocks, homo, th)
     c = (slice(HM, -HM),) * 3
     if rkstep == 1:
         for b, F in enumerate(blocks):
             qsave[b] = [F.q[m][c] * F.jacob[c] for m in range(5)]
     qrhs = R.rhscal_blocks(blocks, th, homo)
+    if force is not None:
+        src = R.src_chan(blocks, ys, force)
+        qrhs = [[qrhs[b][m] + src[b][m] for m in range(5)] for b in range(len(blocks))]
     a1, a2, a3 = RKCOE[rkstep - 1]
     for b, F in enumerate(blocks):
         J = F.jacob[c]

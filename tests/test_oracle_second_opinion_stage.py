@@ -50,3 +50,44 @@ def test_three_stages(oracle, n, blocks):
             for nm in ("q1", "q5", "rho", "prs", "tmp"):
                 assert np.abs(R.core(got[nm]) - ref[nm]).max() <= TOL * np.abs(ref[nm]).max(), (rk, ib, nm)
     c.close()
+
+
+@pytest.mark.parametrize("n,blocks", [((16, 20, 12), (1, 1, 1)), ((24, 28, 12), (2, 2, 1))])
+def test_three_stages_of_the_channel(oracle, n, blocks):
+    """examples/Channel option set (config 2): isothermal no-slip walls 41 at jmin / jmax through boucon, wall
+    closures of filter and derivative (one block: ntype 4; split in y: ntype 1 | 2), src_chan."""
+    from gpu_common import channel_state, channel_x
+    homo, lengths, force = (True, False, True), (2 * np.pi, 2.0, np.pi), (2.5e-3, 0.0, 1e-4)
+    bctype, twall = (1, 1, 41, 41, 1, 1), (0.0, 0.0, 1.0, 1.0, 0.0, 0.0)
+    reynolds, mach = 3000.0, 0.3
+    c = oracle.Case(*n, blocks=blocks, homo=homo, reynolds=reynolds, mach=mach, lengths=lengths, deltat=DT)
+    c.set_bc(bctype, twall)
+    c.set_flow(1, force)
+    x = channel_x(n, lengths)
+    for ib in range(c.nblocks):
+        info = c.block_info(ib)
+        g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+        c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom()
+    th = dict(tempconst=110.3 / 273.15, reynolds=reynolds, prandtl=PRANDTL, const5=(GAMMA - 1.0) * mach ** 2,
+              const6=1.0 / (GAMMA - 1.0), const2=GAMMA * mach ** 2, gamma=GAMMA, mach=mach,
+              const1=1.0 / (GAMMA * (GAMMA - 1.0) * mach ** 2))
+    for ib in range(c.nblocks):
+        channel_state(c, th, ib=ib)
+    c.updatefvar()
+    state = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    ys = [c.get("x2", ib) for ib in range(c.nblocks)]
+    qsave = [None] * c.nblocks
+    for rk in (1, 2, 3):
+        c.rk_stage(rk)
+        S.rk_stage(state, rk, th, homo, DT, qsave, bctype=bctype, twall=twall, force=force, ys=ys)
+        for ib, F in enumerate(state):
+            got = dict(zip(NAMES, F.q + [F.rho] + F.vel + [F.prs, F.tmp]))
+            ref = {nm: R.core(c.get(nm, ib)) for nm in NAMES}
+            for grp in (["q2", "q3", "q4"], ["u", "v", "w"]):
+                s = max(np.abs(ref[nm]).max() for nm in grp)
+                for nm in grp:
+                    assert np.abs(R.core(got[nm]) - ref[nm]).max() <= TOL * s, (rk, ib, nm)
+            for nm in ("q1", "q5", "rho", "prs", "tmp"):
+                assert np.abs(R.core(got[nm]) - ref[nm]).max() <= TOL * np.abs(ref[nm]).max(), (rk, ib, nm)
+    c.close()
