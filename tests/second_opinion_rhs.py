@@ -107,15 +107,22 @@ def miucal(T, tempconst):
     return T * np.sqrt(T) * (1.0 + tempconst) / (T + tempconst)
 
 
+def miucal_dimensional(T):
+    """src/fludyna.F90:806-809: Sutherland's law in SI units (nondimen = .false.)."""
+    tn = T / 273.15
+    return 1.716e-5 * tn * np.sqrt(tn) * (273.15 + 110.4) / (T + 110.4)
+
+
 def stress_and_heat_flux(F, dvel, dtmp, th):
     """sigma(6) [11 12 13 22 23 33] and qflux(3) on nodes 0..N (diffrsdcal6's pointwise block, nondimensional)."""
     T, v = core(F.tmp), [core(u) for u in F.vel]
-    miu = miucal(T, th["tempconst"]) / th["reynolds"]
+    dimensional = th.get("dimensional", False)          # nondimen = .false.: SI viscosity, hcc = cp miu / Pr
+    miu = miucal_dimensional(T) if dimensional else miucal(T, th["tempconst"]) / th["reynolds"]
     S = [[0.5 * (dvel[a][b] + dvel[b][a]) for b in range(3)] for a in range(3)]
     skk = (S[0][0] + S[1][1] + S[2][2]) / 3.0
     two_mu = 2.0 * miu
     tau = [[two_mu * (S[a][b] - (skk if a == b else 0.0)) for b in range(3)] for a in range(3)]
-    hcc = (miu / th["prandtl"]) / th["const5"]
+    hcc = th["cp"] * miu / th["prandtl"] if dimensional else (miu / th["prandtl"]) / th["const5"]
     qf = [hcc * dtmp[n] + sum(tau[n][b] * v[b] for b in range(3)) for n in range(3)]
     return tau, qf
 

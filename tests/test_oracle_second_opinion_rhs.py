@@ -106,3 +106,29 @@ def test_rhs_channel_with_bulk_forcing(oracle, n, blocks):
         ref2 = R.core(c.get("qrhs2", ib))
         assert np.abs(got[ib][1] - ref2).max() > 1e-4 * np.abs(src[ib][1]).max()
     c.close()
+
+
+def test_rhs_dimensional_gas(oracle):
+    """nondimen = .false. (the HBL input): SI Sutherland law, hcc = cp miu / Pr, rgas = 287.1
+    (src/solver.F90:128-139, src/fludyna.F90:806-809, src/solver.F90:2497-2501)."""
+    from gpu_common import dimensional_state
+    from astr_b200 import refcal_dimensional
+    n, homo = (16, 14, 12), (True, True, True)
+    ref = (226.65, 900.0, 1.0, 0.0180119)              # examples/Hypersonic_Boundary_Layer/datin/input.M3
+    c = oracle.Case(*n, homo=homo, deltat=1e-5)
+    c.set_dimensional(*ref)
+    c.set_x(stretched_x(n, homo))
+    c.gridgeom()
+    dimensional_state(c, refcal_dimensional(*ref))
+    c.updatefvar(); c.qswap(); c.zero_qrhs(); c.gradcal(); c.rhscal()
+    rgas = 287.1
+    th = dict(dimensional=True, prandtl=PRANDTL, cp=GAMMA / (GAMMA - 1.0) * rgas)
+    F = R.Fields(c)
+    got = R.rhscal(F, th, homo)
+    for m in range(5):
+        want = R.core(c.get(f"qrhs{m + 1}"))
+        assert np.abs(got[m] - want).max() <= TOL * np.abs(want).max(), m
+    # the viscous part is visible at this Reynolds number: without it the energy row moves by far more than TOL
+    inviscid = R.rhscal(F, th, homo, diffterm=False)
+    assert np.abs(inviscid[4] - R.core(c.get("qrhs5"))).max() > 1e-6 * np.abs(R.core(c.get("qrhs5"))).max()
+    c.close()
