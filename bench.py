@@ -303,6 +303,19 @@ def parity_check(args, torch, dist, world, rank, local_rank, size):
                     "(max-norm relative per field)"}
 
 
+_ORIGINAL_AFFINITY = set()     # this process's CPU set before bind_to_gpu_numa_node narrowed it
+
+
+def unbind_from_numa_node():
+    """Give the process its original CPU set back (rank 0, before the CPU baseline leg: the other ranks idle at a
+    barrier by then, and the baseline is quoted on every host core the process may use -- at every N)."""
+    if _ORIGINAL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, sorted(_ORIGINAL_AFFINITY))
+        except OSError as e:
+            sys.stderr.write(f"bench.py: could not restore the CPU affinity ({e})\n")
+
+
 def bind_to_gpu_numa_node(torch, local_rank):
     """Pin this rank's threads (and therefore the first-touch placement of its pinned staging buffers) to the
     NUMA node its GPU hangs off: with eight ranks staging 2 x 5.7 GB per step, buffers that all land on one node
@@ -321,6 +334,7 @@ def bind_to_gpu_numa_node(torch, local_rank):
             cpus += list(range(int(lo), int(hi or lo) + 1))
         allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
         if allowed:
+            _ORIGINAL_AFFINITY.update(os.sched_getaffinity(0))
             os.sched_setaffinity(0, allowed)
             return node
     except Exception as e:       # no sysfs / no permission: leave the affinity alone
@@ -472,6 +486,7 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu:      # rank 0, every N: the same bounded sample on all host cores
+        unbind_from_numa_node()
         v, cms, cores = cpu_reference(args.case, args.cpu_n, args.cpu_steps, 1, args.conschm)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_n}^3 block of the workload, {args.cpu_steps} RK3 steps after 1 warm-up "
