@@ -197,3 +197,54 @@ def src_chan(blocks, ys, force):
         out.append([np.zeros(J.shape)] + [force[n] * J for n in range(3)] +
                    [(force[0] * ubulk[0] + force[1] * ubulk[1] + force[2] * ubulk[2]) * J])
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# per-step diagnostics (raw block sums / maxima before the reference's normalisation)
+# ------------------------------------------------------------------------------------------------
+def tgv_sums(blocks, th):
+    """kenergycal, enstophycal, diss_rate_cal (src/statistic.F90:938-990, :871-936, :994-1046): sums over cells
+    1..N of every block of rho |u|^2, rho |curl u|^2 and 2 mu (S:S - div^2/3)."""
+    out = np.zeros(3)
+    inner = (slice(1, None),) * 3
+    for F in blocks:
+        dvel, _ = gradcal(F)
+        g = np.array([[dvel[a][b][inner] for b in range(3)] for a in range(3)])       # g[a][b] = d u_a / d x_b
+        rho, T = core(F.rho)[inner], core(F.tmp)[inner]
+        u2 = sum(core(v)[inner] ** 2 for v in F.vel)
+        curl2 = (g[2, 1] - g[1, 2]) ** 2 + (g[0, 2] - g[2, 0]) ** 2 + (g[1, 0] - g[0, 1]) ** 2
+        S = 0.5 * (g + np.swapaxes(g, 0, 1))
+        div = S[0, 0] + S[1, 1] + S[2, 2]
+        miu = miucal_dimensional(T) if th.get("dimensional") else miucal(T, th["tempconst"]) / th["reynolds"]
+        out += [np.sum(rho * u2), np.sum(rho * curl2), np.sum(2.0 * miu * ((S * S).sum(axis=(0, 1)) - div ** 2 / 3.0))]
+    return out
+
+
+def cfl_maxima(blocks, th):
+    """cflcal (src/commcal.F90:27-74): max over nodes 0..N and blocks of the contravariant speeds U, U -+ c |grad xi|
+    (and 0) per direction; nondimensional sound speed sqrt(T)/M (src/fludyna.F90 sos)."""
+    out = np.zeros(3)
+    for F in blocks:
+        c = np.sqrt(core(F.tmp)) / th["mach"]
+        for d in range(3):
+            U = sum(core(F.dxi[d][n]) * core(F.vel[n]) for n in range(3))
+            cs = c * np.sqrt(sum(core(F.dxi[d][n]) ** 2 for n in range(3)))
+            out[d] = max(out[d], 0.0, U.max(), (U + cs).max(), (U - cs).max())
+    return out
+
+
+def channel_sums(blocks, ys, th, jsize):
+    """massfluxchan and fbcxchan (src/statistic.F90:1437-1476, :1303-1367) before the division by ia*ka: the
+    trapezoidal integral of rho u over y on cells 1..N, and mu du/dy at the two walls (lower wall +, upper wall -)
+    summed over i = 1..N, k = 1..N of the blocks that own a wall."""
+    mf = fb = 0.0
+    for F, y in zip(blocks, ys):
+        yc, q2 = core(y), core(F.q[1])
+        mf += np.sum(0.5 * (q2[1:, 1:, 1:] + q2[1:, :-1, 1:]) * (yc[1:, 1:, 1:] - yc[1:, :-1, 1:]))
+        dvel, _ = gradcal(F)
+        mu = miucal(core(F.tmp), th["tempconst"]) / th["reynolds"]
+        if F.nb[2] < 0:                                   # jrk == 0: the lower wall
+            fb += np.sum((mu * dvel[0][1])[1:, 0, 1:])
+        if F.nb[3] < 0:                                   # jrk == jrkm
+            fb -= np.sum((mu * dvel[0][1])[1:, -1, 1:])
+    return mf, fb

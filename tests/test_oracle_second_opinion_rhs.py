@@ -105,6 +105,10 @@ def test_rhs_channel_with_bulk_forcing(oracle, n, blocks):
         # the forcing itself is visible: without it the x-momentum row is off by force * J
         ref2 = R.core(c.get("qrhs2", ib))
         assert np.abs(got[ib][1] - ref2).max() > 1e-4 * np.abs(src[ib][1]).max()
+    # massfluxchan / fbcxchan sums
+    mf, fb = R.channel_sums(blk, [c.get("x2", ib) for ib in range(c.nblocks)], th, blocks[1])
+    want = c.reduce(2)
+    assert abs(mf - want[0]) <= 1e-13 * abs(want[0]) and abs(fb - want[1]) <= 1e-12 * abs(want[1]), (mf, fb, want)
     c.close()
 
 
@@ -131,4 +135,18 @@ def test_rhs_dimensional_gas(oracle):
     # the viscous part is visible at this Reynolds number: without it the energy row moves by far more than TOL
     inviscid = R.rhscal(F, th, homo, diffterm=False)
     assert np.abs(inviscid[4] - R.core(c.get("qrhs5"))).max() > 1e-6 * np.abs(R.core(c.get("qrhs5"))).max()
+    c.close()
+
+
+@pytest.mark.parametrize("n,blocks", [((16, 14, 12), (1, 1, 1)), ((24, 14, 24), (2, 1, 2))])
+def test_step_diagnostics(oracle, n, blocks):
+    """kenergycal / enstophycal / diss_rate_cal sums and the CFL maxima."""
+    homo = (True, True, True)
+    c, th = _case(oracle, n, homo, blocks)
+    th["mach"] = 0.1
+    blk = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    got, want = R.tgv_sums(blk, th), c.reduce(0)
+    assert np.all(np.abs(got - want) <= 1e-13 * np.abs(want)), (got, want)
+    got, want = R.cfl_maxima(blk, th), c.reduce(1)
+    assert np.all(np.abs(got - want) <= 1e-13 * np.abs(want)), (got, want)
     c.close()
