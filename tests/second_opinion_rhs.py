@@ -127,14 +127,35 @@ def stress_and_heat_flux(F, dvel, dtmp, th):
     return tau, qf
 
 
-def rhscal_blocks(blocks, th, homo, diffterm=True):
-    """qrhs(5) on nodes 0..N of every block, zero outside the ranges the reference updates."""
+def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
+    """qrhs(5) on nodes 0..N of every block, zero outside the ranges the reference updates.
+    upwind: None for the central path (convrsdcal6), or dict(shkcrt, lchardecomp, bfacmpld) for conschm 543c:
+    ducrossensor (when lchardecomp) + convrsdcmp (src/solver.F90:224-226)."""
 
     def box(ranges):
         return tuple(slice(a, b + 1) for a, b in ranges)
 
     out = []
-    for F in blocks:
+    if upwind is not None:
+        import second_opinion_upwind as U
+        lchar = upwind.get("lchardecomp", True)
+        flags = [np.ones(F.prs.shape) for F in blocks]
+        if lchar:
+            ssf = []
+            for F in blocks:
+                full = np.zeros(F.prs.shape)
+                core(full)[...] = U.ducros_ssf(F, gradcal(F)[0])
+                ssf.append(full)
+            ssf = exchange_halos(ssf, blocks, homo)
+            flags = []
+            for F, s in zip(blocks, ssf):
+                full = np.zeros(F.prs.shape)
+                core(full)[...] = U.ducros_flags(s, F.npdc, upwind["shkcrt"])
+                flags.append(full)
+        for F, fl in zip(blocks, flags):
+            conv = U.convrsdcmp(F, th["gamma"], th["mach"], fl, lchar, upwind.get("bfacmpld", 0.3))
+            out.append([-r for r in conv])
+    for F in ([] if upwind is not None else blocks):
         qrhs = [np.zeros(core(F.prs).shape) for _ in range(5)]
         # convection: loops over js:je, ks:ke (resp.) and adds on is:ie -> the box is:ie x js:je x ks:ke
         conv_box = box(zip(F.lo, F.hi))

@@ -118,18 +118,24 @@ def noslip(blocks, homo, bctype, twall, th):
             F.q[4][at(w)] = pe * th["const6"]
 
 
-def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None):
-    """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: faces with
-    no-slip walls (41); force, ys: the channel's body force and the halo'd y coordinate per block (src_chan)."""
+def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None,
+             upwind=None, bc_extra=None):
+    """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: boundary
+    types per face; only no-slip walls (41) unless bc_extra = dict(free=..., inflow_data=...) brings the data of the
+    open types (tests/second_opinion_bc.py); force, ys: the channel's body force and the halo'd y coordinate per
+    block (src_chan); upwind: see second_opinion_rhs.rhscal_blocks."""
     filterq(blocks, homo, alfa)
-    if bctype is not None:
+    if bctype is not None and bc_extra is not None:
+        import second_opinion_bc as B
+        B.boucon(blocks, homo, bctype, twall, th, bc_extra["free"], deltat, bc_extra.get("inflow_data"))
+    elif bctype is not None:
         noslip(blocks, homo, bctype, twall, th)
     qswap(blocks, homo, th)
     c = (slice(HM, -HM),) * 3
     if rkstep == 1:
         for b, F in enumerate(blocks):
             qsave[b] = [F.q[m][c] * F.jacob[c] for m in range(5)]
-    qrhs = R.rhscal_blocks(blocks, th, homo)
+    qrhs = R.rhscal_blocks(blocks, th, homo, upwind=upwind)
     if force is not None:
         src = R.src_chan(blocks, ys, force)
         qrhs = [[qrhs[b][m] + src[b][m] for m in range(5)] for b in range(len(blocks))]

@@ -5,10 +5,11 @@ stored number of the reference pins ("the whole upwind/shock path"
 
 What is restated, and how it differs from the oracle's line-by-line form:
   convrsdcmp            src/solver.F90:1271-1937   one generic direction routine applied along each axis
-  flux_steger_warming   src/riemann.F90:23-161     NOT the closed form: F+- = J R diag(lambda+-) R^-1 q from the
+  flux_steger_warming   src/riemann.F90:23-161     NOT the closed form: F+- = J R diag(lambda+-) R^-1 U from the
                                                    eigen-decomposition of the flux Jacobian at the node (perfect gas:
-                                                   F = A q), with the reference's smoothed lambda+- (eps = 0.04) and
-                                                   its full-flux switch at local Mach >= 1
+                                                   F = A U), with the reference's smoothed lambda+- (eps = 0.04), its
+                                                   full-flux switch at local Mach >= 1 and its mixed use of the
+                                                   primitives and q(5) (see steger_warming)
   chardecomp            src/solver.F90:1958-2162   right eigenvectors R transcribed (3 pivot branches on the raw
                                                    metric); the LEFT eigenvectors are NOT transcribed: L = R^-1 by LU
   iwind6                src/solver.F90:1236-1257   clamped 5-node stencils, mirrored for the '-' flux
@@ -65,11 +66,18 @@ def _apply(Mx, v):
     return np.einsum("abm,bm->am", Mx, v)
 
 
-def steger_warming(rho, vel, prs, q, ddi, jac, gamma):
-    """F+ and F- (5,M) at nodes from the eigen-decomposition."""
-    H = (q[4] + prs) / rho
+def steger_warming(rho, vel, prs, tmp, q, ddi, jac, gamma, mach):
+    """F+ and F- (5,M) at nodes from the eigen-decomposition.
+
+    Inside an RK stage the reference calls this with primitives and q that do NOT belong to the same state: the
+    interior primitives are pre-filter, q is post-filter (quirk Q2).  Its closed form takes rho, u, p and the sound
+    speed sqrt(T)/M from the PRIMITIVES and only the total energy from q(5), which enters the energy flux alone, as
+    lambda_1 * q5.  The eigen-form equivalent: decompose the state the primitives define (energy E_c = p/(gamma-1) +
+    rho |u|^2 / 2), then add J lambda_1 (q5 - E_c) to the energy flux.  The full-flux (supersonic) branches use q."""
     K = 0.5 * (vel ** 2).sum(axis=0)
-    c = np.sqrt((gamma - 1.0) * (H - K))
+    Ec = prs / (gamma - 1.0) + rho * K
+    c = np.sqrt(tmp) / mach
+    H = (Ec + prs) / rho
     R, g, ug = right_eigenvectors(vel, H, c, ddi)
     L = _inv(R)
     mag = np.sqrt((ddi ** 2).sum(axis=0))
@@ -77,8 +85,10 @@ def steger_warming(rho, vel, prs, q, ddi, jac, gamma):
     lam = np.stack([uu - csa, uu, uu, uu, uu + csa])
     lamp = 0.5 * (lam + np.sqrt(lam ** 2 + EPS_SW ** 2))
     lamm = lam - lamp
-    w = _apply(L, q)
+    w = _apply(L, np.stack([rho, rho * vel[0], rho * vel[1], rho * vel[2], Ec]))
     fp, fm = jac * _apply(R, lamp * w), jac * _apply(R, lamm * w)
+    fp[4] += jac * lamp[1] * (q[4] - Ec)
+    fm[4] += jac * lamm[1] * (q[4] - Ec)
     full = jac * np.stack([q[0] * uu, q[1] * uu + ddi[0] * prs, q[2] * uu + ddi[1] * prs, q[3] * uu + ddi[2] * prs,
                            (q[4] + prs) * uu])
     lmach = uu / csa
@@ -118,11 +128,11 @@ def _pencils(a, ax, F):
     return m.reshape(m.shape[0], -1), m.shape
 
 
-def direction(F, ax, gamma, lshock, lchardecomp=True, bfacmpld=0.3):
+def direction(F, ax, gamma, mach, lshock, lchardecomp=True, bfacmpld=0.3):
     """Fh(i+1/2) differences of one direction: returns the increment of qrhs(5) on nodes 0..N (zero outside is:ie)."""
     npdc = F.npdc[ax]
     rho, shp = _pencils(F.rho, ax, F)
-    prs = _pencils(F.prs, ax, F)[0]
+    prs, tmp = _pencils(F.prs, ax, F)[0], _pencils(F.tmp, ax, F)[0]
     vel = np.stack([_pencils(v, ax, F)[0] for v in F.vel])               # (3, L, M)
     q = np.stack([_pencils(v, ax, F)[0] for v in F.q])                   # (5, L, M)
     ddi = np.stack([_pencils(F.dxi[ax][n], ax, F)[0] for n in range(3)])
@@ -136,8 +146,8 @@ def direction(F, ax, gamma, lshock, lchardecomp=True, bfacmpld=0.3):
     fp, fm = np.zeros((5, Lh, M)), np.zeros((5, Lh, M))
     sl = slice(iss + HM, iee + HM + 1)
     n_nodes = iee - iss + 1
-    a, b = steger_warming(rho[sl].ravel(), vel[:, sl].reshape(3, -1), prs[sl].ravel(), q[:, sl].reshape(5, -1),
-                          ddi[:, sl].reshape(3, -1), jac[sl].ravel(), gamma)
+    a, b = steger_warming(rho[sl].ravel(), vel[:, sl].reshape(3, -1), prs[sl].ravel(), tmp[sl].ravel(),
+                          q[:, sl].reshape(5, -1), ddi[:, sl].reshape(3, -1), jac[sl].ravel(), gamma, mach)
     fp[:, sl], fm[:, sl] = a.reshape(5, n_nodes, M), b.reshape(5, n_nodes, M)
     fhp = np.stack([so.flux_compact(fp[m], npdc, dim, True, bfacmpld) for m in range(5)])     # (5, dim+2, M): i = -1..dim
     fhm = np.stack([so.flux_compact(fm[m], npdc, dim, False, bfacmpld) for m in range(5)])
@@ -181,12 +191,12 @@ def direction(F, ax, gamma, lshock, lchardecomp=True, bfacmpld=0.3):
     return res
 
 
-def convrsdcmp(F, gamma, lshock, lchardecomp=True, bfacmpld=0.3):
+def convrsdcmp(F, gamma, mach, lshock, lchardecomp=True, bfacmpld=0.3):
     """qrhs(5) on nodes 0..N (before rhscal's sign flip)."""
     shape = tuple(s - 2 * HM for s in F.prs.shape)
     qrhs = [np.zeros(shape) for _ in range(5)]
     for ax in range(3):
-        inc = direction(F, ax, gamma, lshock, lchardecomp, bfacmpld)
+        inc = direction(F, ax, gamma, mach, lshock, lchardecomp, bfacmpld)
         tgt = [slice(F.lo[a], F.hi[a] + 1) for a in range(3)]       # the other two directions: js:je | ks:ke ... only
         tgt[ax] = slice(None)
         for m in range(5):

@@ -91,3 +91,60 @@ def test_three_stages_of_the_channel(oracle, n, blocks):
             for nm in ("q1", "q5", "rho", "prs", "tmp"):
                 assert np.abs(R.core(got[nm]) - ref[nm]).max() <= TOL * np.abs(ref[nm]).max(), (rk, ib, nm)
     c.close()
+
+
+@pytest.mark.parametrize("n,blocks", [((16, 14, 10), (1, 1, 1)), ((24, 16, 10), (2, 2, 1))])
+def test_three_stages_of_a_swbli_like_case(oracle, n, blocks):
+    """The SWLBI option set (config 4) in 3-D: conschm 543c with characteristic MP5 and the Ducros sensor, inflow 11 at
+    imin, outflow 21 at imax, slip wall 421 at jmin, far field 51 at jmax, periodic in k.  Inside a stage the split
+    fluxes see pre-filter primitives next to post-filter q (quirk Q2): this is the test that exercises the reference's
+    mixed use of the two in flux_steger_warming (tests/second_opinion_upwind.py::steger_warming)."""
+    import second_opinion_bc  # noqa: F401  (used through S.rk_stage)
+    from gpu_common import auto_shkcrt, clean_metrics, skewed_x
+    homo, bctype, twall, mach = (False, False, True), (11, 21, 421, 51, 1, 1), (0.0,) * 6, 0.5
+    c = oracle.Case(*n, homo=homo, blocks=blocks, mach=mach, reynolds=REYNOLDS, deltat=DT)
+    c.set_bc(bctype, twall)
+    x = skewed_x(n, homo)
+    for ib in range(c.nblocks):
+        info = c.block_info(ib)
+        g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+        c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom(); clean_metrics(c); c.tgvini()
+    th = dict(mach=mach, gamma=GAMMA, const1=1.0 / (GAMMA * (GAMMA - 1.0) * mach ** 2), const2=GAMMA * mach ** 2,
+              const6=1.0 / (GAMMA - 1.0), const5=(GAMMA - 1.0) * mach ** 2, tempconst=110.3 / 273.15,
+              reynolds=REYNOLDS, prandtl=PRANDTL)
+    inflow = []
+    for ib in range(c.nblocks):
+        X = [c.get(f"x{d + 1}", ib) for d in range(3)]
+        fields = dict(rho=1.0 + 0.1 * np.sin(X[0]) * np.cos(X[1]), tmp=1.0 + 0.05 * np.cos(X[1]) * np.sin(X[2] + 0.3),
+                      u=1.0 + 0.3 * np.sin(X[1]) * np.cos(X[2]), v=0.3 * np.sin(X[0] + 0.4) * np.cos(X[2]),
+                      w=0.2 * np.sin(X[0]) * np.cos(X[1] + 0.2))
+        for nm, a in fields.items():
+            c.set(nm, np.asfortranarray(a), ib)
+        info = c.block_info(ib)
+        jm, km = info["jm"], info["km"]
+        yy = (np.arange(jm + 1) + info["g0"][1]) / n[1]
+        vel_in = np.zeros((jm + 1, km + 1, 3), order="F")
+        vel_in[:, :, 0] = (0.6 + 1.0 * yy)[:, None]
+        vel_in[:, :, 2] = 0.02
+        tmp_in = np.asfortranarray(1.0 + 0.05 * yy[:, None] * np.ones((1, km + 1)))
+        tmp_prof = 1.0 + 0.05 * yy
+        c.set_inflow(vel_in, tmp_in, tmp_prof, ib)
+        inflow.append((vel_in, tmp_in, tmp_prof))
+    c.updateq(); c.updatefvar()
+    shk = auto_shkcrt(c, 0.3)
+    c.set_upwind(543, True, 0.3, shk)
+    state = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    qsave = [None] * c.nblocks
+    extra = dict(free=(1.0, 0.0, 0.0, 1.0, c.pinf), inflow_data=inflow)
+    for rk in (1, 2, 3):
+        c.rk_stage(rk)
+        S.rk_stage(state, rk, th, homo, DT, qsave, bctype=bctype, twall=twall,
+                   upwind=dict(shkcrt=shk, lchardecomp=True, bfacmpld=0.3), bc_extra=extra)
+        for ib, F in enumerate(state):
+            got = dict(zip(NAMES, F.q + [F.rho] + F.vel + [F.prs, F.tmp]))
+            for nm in NAMES:
+                ref = R.core(c.get(nm, ib))
+                # measured <= 5.2e-14; velocities / momenta relative to the free-stream speed 1
+                assert np.abs(R.core(got[nm]) - ref).max() <= TOL * max(np.abs(ref).max(), 0.3), (rk, ib, nm)
+    c.close()
