@@ -52,6 +52,8 @@ def refcal_dimensional(ref_tem: float, ref_vel: float, ref_len: float, ref_den: 
     reynolds = ref_den * ref_vel * ref_len / ref_miu
     th = refcal(float(reynolds), float(mach), ref_tem=ref_tem, gamma=gamma, prandtl=prandtl)
     th.update(nondimen=0, rgas=rgas, cp=cp, cv=cv, pinf=float(pinf))
+    # free stream of the far-field faces: uinf=ref_vel, vinf=winf=0, roinf=ref_den (src/solver.F90:131-139)
+    th.update(uinf=float(ref_vel), vinf=0.0, winf=0.0, roinf=float(ref_den))
     return th
 
 
@@ -65,7 +67,7 @@ class RhsEngine:
                  lchardecomp: bool = False, bfacmpld: float = 0.3, shkcrt: float = 0.01, recon_schem: int = 3,
                  conschm_explicit: bool = False, legacy_sweep: bool = False, overlap_visc: bool = False,
                  xchg_nccl: bool = False, xchg_timeout_ms: int = 0,
-                 freestream: Sequence[float] = (1.0, 0.0, 0.0, 1.0), rkscheme: int = 3):
+                 freestream: Optional[Sequence[float]] = None, rkscheme: int = 3):
         self.block = block
         self.global_dims = tuple(global_dims)
         self.deltat = deltat
@@ -101,11 +103,15 @@ class RhsEngine:
         c.alfa_filter = alfa_filter
         # roinf*tinf/const2 with roinf=tinf=1 (src/solver.F90:113-120), or thermal(tinf,roinf) for nondimen=f
         c.pinf = thermo.get("pinf", 1.0 / thermo["const2"])
-        # free stream of the far-field faces (commvar uinf, vinf, winf, roinf)
-        c.uinf, c.vinf, c.winf, c.roinf = freestream
+        # free stream of the far-field faces (commvar uinf, vinf, winf, roinf): 1, 0, 0, 1 for the nondimensional
+        # gas (src/solver.F90:113-120); refcal_dimensional brings ref_vel, 0, 0, ref_den (:131-139); an explicit
+        # `freestream` wins over both
+        c.uinf, c.vinf, c.winf, c.roinf = 1.0, 0.0, 0.0, 1.0
         for k, v in thermo.items():
             if k not in ("nondimen", "rgas", "cp", "cv", "pinf"):
                 setattr(c, k, v)
+        if freestream is not None:
+            c.uinf, c.vinf, c.winf, c.roinf = freestream
         c.deltat = deltat
         self.cfg = c
         _l.check(self._lib.astr_gpu_init(ctypes.byref(c)))

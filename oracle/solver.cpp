@@ -1498,6 +1498,8 @@ void oracle_case_set_dimensional(void* h, double ref_tem, double ref_vel, double
   c->th.ref_tem = ref_tem; c->th.ref_vel = ref_vel; c->th.ref_len = ref_len; c->th.ref_den = ref_den;
   c->th.refcal_dimensional();
   c->pinf = c->th.pinf;
+  // src/solver.F90:131-139: uinf=ref_vel, vinf=winf=0, roinf=ref_den (tinf=ref_tem, pinf=thermal(tinf,roinf))
+  c->uinf = ref_vel; c->vinf = 0.0; c->winf = 0.0; c->roinf = ref_den;
 }
 // out: reynolds, mach, const1..const7, rgas, cp, cv, pinf, nondimen
 void oracle_case_thermo(void* h, double* out) {

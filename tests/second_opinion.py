@@ -234,7 +234,7 @@ def _fd_weights(offsets):
 def diff6ec(f, ntype, dim):
     p = Pencil(f, dim)
     lo_wall, hi_wall = _wall(ntype)
-    out = np.empty(dim + 1)
+    out = np.empty((dim + 1,) + p.f.shape[1:])
     for i in range(dim + 1):
         lo, hi = (i if lo_wall else HM), (dim - i if hi_wall else HM)      # nodes available towards each wall
         if lo == 0:

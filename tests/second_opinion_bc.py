@@ -16,7 +16,7 @@ either transcription breaks the agreement.
   extrapolate   src/commfunc.F90:277-285   (4 v1 - v2 - 2 dv)/3
   fvar2q        src/fludyna.F90:312-376    energy from temperature (const1) or from pressure (const6)
   thermal       src/fludyna.F90:136-179    nondimensional gas law with const2
-Nondimensional gas only.  Every routine works on nodes 0..N of the two in-plane directions of a face the block owns.
+Both gas modes (tests/second_opinion_rhs.py::Gas).  Every routine works on nodes 0..N of the two in-plane directions of a face the block owns.
 """
 import numpy as np
 
@@ -36,7 +36,12 @@ def _ext(a, ax, w, s):
 
 
 def _sos(T, th):
-    return np.sqrt(T) / th["mach"]
+    return _gas(th).sos(T)
+
+
+def _gas(th):
+    import second_opinion_rhs as R
+    return R.Gas(th)
 
 
 def _store(F, ax, w, rho, vel, prs, tmp, th, energy_from):
@@ -49,7 +54,8 @@ def _store(F, ax, w, rho, vel, prs, tmp, th, energy_from):
     _plane(F.q[0], ax, w)[...] = rho
     for n in range(3):
         _plane(F.q[1 + n], ax, w)[...] = rho * vel[n]
-    _plane(F.q[4], ax, w)[...] = rho * (tmp * th["const1"] + k) if energy_from == "temperature" else prs * th["const6"] + rho * k
+    g = _gas(th)
+    _plane(F.q[4], ax, w)[...] = rho * (tmp * g.cotem + k) if energy_from == "temperature" else prs * g.const6 + rho * k
 
 
 def _cur(F, ax, w):
@@ -66,7 +72,7 @@ def inflow_imin(F, th, vel_in, tmp_in, tmp_prof, pinf):
     blend = 0.5 * (np.tanh((vel_in[..., 0] / css - 1.0) * 6.0) + 1.0)
     prs = (0.5 * (pinf + pe) + 0.5 * rho_ref * css * (vel_in[..., 0] - ue)) * (1.0 - blend) + pinf * blend
     u = vel_in[..., 0] + (pinf - prs) / rho_ref / css
-    rho = prs / tmp_in * th["const2"]
+    rho = _gas(th).rho_of(prs, tmp_in)
     _store(F, ax, w, rho, [u, vel_in[..., 1], vel_in[..., 2]], prs, tmp_in, th, "temperature")
 
 
@@ -77,7 +83,7 @@ def outflow(F, th, ax, pinf, deltat):
     if ax == 0:        # every primitive copied from the neighbour plane, density from the gas law
         vel = [_plane(v, ax, w + s).copy() for v in F.vel]
         prs, tmp = _plane(F.prs, ax, w + s).copy(), _plane(F.tmp, ax, w + s).copy()
-        _store(F, ax, w, prs / tmp * th["const2"], vel, prs, tmp, th, "temperature")
+        _store(F, ax, w, _gas(th).rho_of(prs, tmp), vel, prs, tmp, th, "temperature")
         return
     css = _sos(tmp0, th)
     ve = [_ext(v, ax, w, s) for v in F.vel]
@@ -86,8 +92,8 @@ def outflow(F, th, ax, pinf, deltat):
     sup = vel0[ax] >= css
     pwave = (prs0 + alpha * deltat * pinf + rho0 * css * (ve[ax] - vel0[ax])) / (1.0 + alpha * deltat)
     prs = np.where(sup, pe, pwave)
-    rho = np.where(sup, roe, pwave / te * th["const2"])
-    _store(F, ax, w, rho, ve, prs, prs / rho * th["const2"], th, "pressure")
+    rho = np.where(sup, roe, _gas(th).rho_of(pwave, te))
+    _store(F, ax, w, rho, ve, prs, _gas(th).T_of(prs, rho), th, "pressure")
 
 
 def farfield(F, th, ax, side, free):
@@ -99,7 +105,7 @@ def farfield(F, th, ax, side, free):
     ve = [_ext(v, ax, w, s) for v in F.vel]
     pe, roe = _ext(F.prs, ax, w, s), _ext(F.rho, ax, w, s)
     if ax == 1 and side == 1:          # jmax: plain extrapolation, energy from the temperature
-        _store(F, ax, w, roe, ve, pe, pe / roe * th["const2"], th, "temperature")
+        _store(F, ax, w, roe, ve, pe, _gas(th).T_of(pe, roe), th, "temperature")
         return
     css = _sos(tmp0, th)
     csse = (4.0 * _sos(_plane(F.tmp, ax, w + s), th) - _sos(_plane(F.tmp, ax, w + 2 * s), th)) / 3.0
@@ -119,7 +125,7 @@ def farfield(F, th, ax, side, free):
             vel.append(np.where(entering, vinf[m], ve[m]))
     prs = np.where(entering, p_in, pinf)
     rho = np.where(entering, rho_in, rho_out)
-    _store(F, ax, w, rho, vel, prs, prs / rho * th["const2"], th, "pressure")
+    _store(F, ax, w, rho, vel, prs, _gas(th).T_of(prs, rho), th, "pressure")
 
 
 def slipadibwall(F, th, side):
@@ -129,7 +135,7 @@ def slipadibwall(F, th, side):
     w, s = (n, -1) if side else (0, 1)
     pe, te, ue = _ext(F.prs, ax, w, s), _ext(F.tmp, ax, w, s), _ext(F.vel[0], ax, w, s)
     v = _ext(F.vel[1], ax, w, s) if side else np.zeros_like(pe)        # the reference keeps v at jmax
-    _store(F, ax, w, pe / te * th["const2"], [ue, v, np.zeros_like(pe)], pe, te, th, "pressure")
+    _store(F, ax, w, _gas(th).rho_of(pe, te), [ue, v, np.zeros_like(pe)], pe, te, th, "pressure")
 
 
 def boucon(blocks, homo, bctype, twall, th, free, deltat, inflow_data=None):

@@ -24,13 +24,42 @@ import second_opinion as so
 HM = 5
 
 
-def deriv(F, axis, ntype):
-    """Compact 6th-order d/dxi along `axis` of a halo'd array: nodes 0..N along that axis, every index elsewhere."""
+def deriv(F, axis, ntype, explicit=False):
+    """d/dxi along `axis` of a halo'd array (`fds%central`): compact 6th order ('643c') or, with explicit=True, the
+    explicit 6th-order ladder ('642e'); nodes 0..N along that axis, every index elsewhere."""
     Fm = np.moveaxis(F, axis, 0)
     shp = Fm.shape
     dim = shp[0] - 1 - 2 * HM
-    out = so.df_compact(Fm.reshape(shp[0], -1), ntype, dim).reshape((dim + 1,) + shp[1:])
+    op = so.diff6ec if explicit else so.df_compact
+    out = op(Fm.reshape(shp[0], -1), ntype, dim).reshape((dim + 1,) + shp[1:])
     return np.moveaxis(out, 0, axis)
+
+
+class Gas:
+    """The gas law and its constants in both modes of the reference (src/fludyna.F90:136-179 thermal, :832-859 sos,
+    :312-376 fvar2q's cotem): nondimensional (const1, const2, Mach) or SI (rgas = 287.1, cv)."""
+
+    def __init__(self, th):
+        self.dim = bool(th.get("dimensional", False))
+        self.gamma = th.get("gamma", 1.4)
+        if self.dim:
+            self.rgas = th.get("rgas", 287.1)
+            self.cotem = self.rgas / (self.gamma - 1.0)
+        else:
+            self.mach = th.get("mach")          # only what the caller's dictionary allows; the rest stays None
+            m2 = None if self.mach is None else self.mach ** 2
+            self.const2 = th.get("const2", None if m2 is None else self.gamma * m2)
+            self.cotem = th.get("const1", None if m2 is None else 1.0 / (self.gamma * (self.gamma - 1.0) * m2))
+        self.const6 = 1.0 / (self.gamma - 1.0)
+
+    def T_of(self, p, rho):
+        return p / rho / self.rgas if self.dim else p / rho * self.const2
+
+    def rho_of(self, p, T):
+        return p / T / self.rgas if self.dim else p / T * self.const2
+
+    def sos(self, T):
+        return np.sqrt(self.gamma * self.rgas * T) if self.dim else np.sqrt(T) / self.mach
 
 
 def core(a):
@@ -84,6 +113,7 @@ class Fields:
         self.nb = info["nb"]                     # neighbour block per face (ilo, ihi, jlo, jhi, klo, khi) or -1
         r = info["is_ie"]
         self.lo, self.hi = (r[0], r[2], r[4]), (r[1], r[3], r[5])                 # is, js, ks / ie, je, ke
+        self.explicit = False                    # difschm '642e': fds%central is the explicit ladder
 
 
 def ntype_of(npdc):
@@ -94,7 +124,7 @@ def ntype_of(npdc):
 def gradcal(F):
     """dvel[m][n], dtmp[n] on nodes 0..N."""
     scal = F.vel + [F.tmp]
-    raw = [[core_d(deriv(f, d, ntype_of(F.npdc[d])), d) for d in range(3)] for f in scal]      # raw[f][d]
+    raw = [[core_d(deriv(f, d, ntype_of(F.npdc[d]), F.explicit), d) for d in range(3)] for f in scal]      # raw[f][d]
     grad = [[sum(raw[f][d] * core(F.dxi[d][n]) for d in range(3)) for n in range(3)] for f in range(4)]
     return grad[:3], grad[3]
 
@@ -153,7 +183,7 @@ def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
                 core(full)[...] = U.ducros_flags(s, F.npdc, upwind["shkcrt"])
                 flags.append(full)
         for F, fl in zip(blocks, flags):
-            conv = U.convrsdcmp(F, th["gamma"], th["mach"], fl, lchar, upwind.get("bfacmpld", 0.3))
+            conv = U.convrsdcmp(F, th["gamma"], Gas(th).sos if th.get("dimensional") else th["mach"], fl, lchar, upwind.get("bfacmpld", 0.3))
             out.append([-r for r in conv])
     for F in ([] if upwind is not None else blocks):
         qrhs = [np.zeros(core(F.prs).shape) for _ in range(5)]
@@ -165,7 +195,7 @@ def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
                    [F.jacob * (F.q[1 + n] * U + F.dxi[d][n] * F.prs) for n in range(3)] + \
                    [F.jacob * (F.q[4] + F.prs) * U]
             for m in range(5):
-                qrhs[m][conv_box] += core_d(deriv(flux[m], d, ntype_of(F.npdc[d])), d)[conv_box]
+                qrhs[m][conv_box] += core_d(deriv(flux[m], d, ntype_of(F.npdc[d]), F.explicit), d)[conv_box]
         out.append([-r for r in qrhs])
     if not diffterm:
         return out
@@ -192,7 +222,7 @@ def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
             cols = [sum(tauh[m][n] * F.dxi[d][n] for n in range(3)) * F.jacob for m in range(3)] + \
                    [sum(qfh[n] * F.dxi[d][n] for n in range(3)) * F.jacob]
             for m in range(4):
-                out[b][1 + m][dbox] += core_d(deriv(cols[m], d, ntype_of(F.npdc[d])), d)[dbox]
+                out[b][1 + m][dbox] += core_d(deriv(cols[m], d, ntype_of(F.npdc[d]), F.explicit), d)[dbox]
     return out
 
 

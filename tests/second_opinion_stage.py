@@ -62,12 +62,12 @@ def filterq(blocks, homo, alfa=0.49):
 def q2fvar(F, idx, th):
     rho = F.q[0][idx]
     v = [F.q[1 + n][idx] / rho for n in range(3)]
-    prs = (F.q[4][idx] - 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)) / th["const6"]
+    prs = (F.q[4][idx] - 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)) / R.Gas(th).const6
     F.rho[idx] = rho
     for n in range(3):
         F.vel[n][idx] = v[n]
     F.prs[idx] = prs
-    F.tmp[idx] = prs / rho * th["const2"]
+    F.tmp[idx] = R.Gas(th).T_of(prs, rho)
 
 
 def qswap(blocks, homo, th):
@@ -111,20 +111,21 @@ def noslip(blocks, homo, bctype, twall, th):
                 v[at(w)] = 0.0
             F.prs[at(w)] = pe
             F.tmp[at(w)] = twall[face]
-            F.rho[at(w)] = pe / twall[face] * th["const2"]
+            F.rho[at(w)] = R.Gas(th).rho_of(pe, twall[face])
             F.q[0][at(w)] = F.rho[at(w)]
             for m in (1, 2, 3):
                 F.q[m][at(w)] = 0.0
-            F.q[4][at(w)] = pe * th["const6"]
+            F.q[4][at(w)] = pe * R.Gas(th).const6
 
 
 def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None,
-             upwind=None, bc_extra=None):
+             upwind=None, bc_extra=None, lfilter=True):
     """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: boundary
     types per face; only no-slip walls (41) unless bc_extra = dict(free=..., inflow_data=...) brings the data of the
     open types (tests/second_opinion_bc.py); force, ys: the channel's body force and the halo'd y coordinate per
     block (src_chan); upwind: see second_opinion_rhs.rhscal_blocks."""
-    filterq(blocks, homo, alfa)
+    if lfilter:
+        filterq(blocks, homo, alfa)
     if bctype is not None and bc_extra is not None:
         import second_opinion_bc as B
         B.boucon(blocks, homo, bctype, twall, th, bc_extra["free"], deltat, bc_extra.get("inflow_data"))

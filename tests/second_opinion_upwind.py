@@ -66,7 +66,7 @@ def _apply(Mx, v):
     return np.einsum("abm,bm->am", Mx, v)
 
 
-def steger_warming(rho, vel, prs, tmp, q, ddi, jac, gamma, mach):
+def steger_warming(rho, vel, prs, tmp, q, ddi, jac, gamma, sos):
     """F+ and F- (5,M) at nodes from the eigen-decomposition.
 
     Inside an RK stage the reference calls this with primitives and q that do NOT belong to the same state: the
@@ -76,7 +76,7 @@ def steger_warming(rho, vel, prs, tmp, q, ddi, jac, gamma, mach):
     rho |u|^2 / 2), then add J lambda_1 (q5 - E_c) to the energy flux.  The full-flux (supersonic) branches use q."""
     K = 0.5 * (vel ** 2).sum(axis=0)
     Ec = prs / (gamma - 1.0) + rho * K
-    c = np.sqrt(tmp) / mach
+    c = sos(tmp)
     H = (Ec + prs) / rho
     R, g, ug = right_eigenvectors(vel, H, c, ddi)
     L = _inv(R)
@@ -129,7 +129,8 @@ def _pencils(a, ax, F):
 
 
 def direction(F, ax, gamma, mach, lshock, lchardecomp=True, bfacmpld=0.3):
-    """Fh(i+1/2) differences of one direction: returns the increment of qrhs(5) on nodes 0..N (zero outside is:ie)."""
+    """Fh(i+1/2) differences of one direction: returns the increment of qrhs(5) on nodes 0..N (zero outside is:ie).
+    mach: the Mach number of the nondimensional gas, or a callable T -> sound speed (dimensional gas)."""
     npdc = F.npdc[ax]
     rho, shp = _pencils(F.rho, ax, F)
     prs, tmp = _pencils(F.prs, ax, F)[0], _pencils(F.tmp, ax, F)[0]
@@ -147,7 +148,8 @@ def direction(F, ax, gamma, mach, lshock, lchardecomp=True, bfacmpld=0.3):
     sl = slice(iss + HM, iee + HM + 1)
     n_nodes = iee - iss + 1
     a, b = steger_warming(rho[sl].ravel(), vel[:, sl].reshape(3, -1), prs[sl].ravel(), tmp[sl].ravel(),
-                          q[:, sl].reshape(5, -1), ddi[:, sl].reshape(3, -1), jac[sl].ravel(), gamma, mach)
+                          q[:, sl].reshape(5, -1), ddi[:, sl].reshape(3, -1), jac[sl].ravel(), gamma,
+                          mach if callable(mach) else (lambda T: np.sqrt(T) / mach))
     fp[:, sl], fm[:, sl] = a.reshape(5, n_nodes, M), b.reshape(5, n_nodes, M)
     fhp = np.stack([so.flux_compact(fp[m], npdc, dim, True, bfacmpld) for m in range(5)])     # (5, dim+2, M): i = -1..dim
     fhm = np.stack([so.flux_compact(fm[m], npdc, dim, False, bfacmpld) for m in range(5)])

@@ -148,3 +148,75 @@ def test_three_stages_of_a_swbli_like_case(oracle, n, blocks):
                 # measured <= 5.2e-14; velocities / momenta relative to the free-stream speed 1
                 assert np.abs(R.core(got[nm]) - ref).max() <= TOL * max(np.abs(ref).max(), 0.3), (rk, ib, nm)
     c.close()
+
+
+@pytest.mark.parametrize("n,blocks,bctype,homo", [
+    ((16, 14, 10), (1, 1, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),
+    ((24, 16, 10), (2, 2, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),
+    # far field with the dimensional free stream (uinf = ref_vel, roinf = ref_den, src/solver.F90:131-139) on the
+    # faces whose characteristic branches use it, outflow at jmax
+    ((16, 14, 10), (1, 1, 1), (11, 21, 51, 21, 51, 51), (False, False, False))])
+def test_three_stages_of_an_hbl_like_case(oracle, n, blocks, bctype, homo):
+    """The HBL option set (config 3, examples/Hypersonic_Boundary_Layer/datin/input.M3) in 3-D: dimensional gas
+    (nondimen = f), conschm 543c + difschm 642e (fds%central is the explicit ladder in gradcal and diffrsdcal6), no
+    filter, inflow 11 / outflow 21 / isothermal wall 41 (568.89 K) / far field 51."""
+    from gpu_common import auto_shkcrt, clean_metrics, skewed_x
+    ref = (226.65, 900.0, 1.0, 0.0180119)
+    dt, twall = 1e-6, (0, 0, 568.89, 0, 0, 0)
+    c = oracle.Case(*n, homo=homo, blocks=blocks, deltat=dt)
+    c.set_dimensional(*ref)
+    c.set_flags(lfilter=False, diffterm=True)
+    c.set_scheme(True)
+    c.set_bc(bctype, twall)
+    x = skewed_x(n, homo)
+    for ib in range(c.nblocks):
+        info = c.block_info(ib)
+        g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+        c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom(); clean_metrics(c); c.tgvini()
+    th = dict(dimensional=True, gamma=GAMMA, prandtl=PRANDTL, rgas=287.1, cp=GAMMA / (GAMMA - 1.0) * 287.1)
+    inflow = []
+    for ib in range(c.nblocks):
+        X = [c.get(f"x{d + 1}", ib) for d in range(3)]
+        fields = dict(rho=ref[3] * (1.0 + 0.1 * np.sin(X[0]) * np.cos(X[1])),
+                      tmp=ref[0] * (1.0 + 0.05 * np.cos(X[1]) * np.sin(X[2] + 0.3)),
+                      u=ref[1] * (0.6 + 0.2 * np.sin(X[1]) * np.cos(X[2])),
+                      v=ref[1] * 0.1 * np.sin(X[0] + 0.4) * np.cos(X[2]),
+                      w=ref[1] * 0.05 * np.sin(X[0]) * np.cos(X[1] + 0.2))
+        for nm, a in fields.items():
+            c.set(nm, np.asfortranarray(a), ib)
+        info = c.block_info(ib)
+        jm, km = info["jm"], info["km"]
+        yy = (np.arange(jm + 1) + info["g0"][1]) / n[1]
+        vel_in = np.zeros((jm + 1, km + 1, 3), order="F")
+        vel_in[:, :, 0] = ref[1] * (0.2 + 0.8 * yy)[:, None]          # Mach 0.6 .. 3 against ~302 m/s
+        vel_in[:, :, 2] = ref[1] * 0.01
+        tmp_in = np.asfortranarray(ref[0] * (1.0 + 0.05 * yy[:, None] * np.ones((1, km + 1))))
+        tmp_prof = ref[0] * (1.0 + 0.05 * yy)
+        c.set_inflow(vel_in, tmp_in, tmp_prof, ib)
+        inflow.append((vel_in, tmp_in, tmp_prof))
+    c.updateq(); c.updatefvar()
+    shk = auto_shkcrt(c, 0.1)
+    c.set_upwind(543, True, 0.1, shk)
+    state = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    for F in state:
+        F.explicit = True
+    qsave = [None] * c.nblocks
+    extra = dict(free=(ref[1], 0.0, 0.0, ref[3], c.pinf), inflow_data=inflow)
+    scale = dict(u=ref[1], v=ref[1], w=ref[1], q2=ref[1] * ref[3], q3=ref[1] * ref[3], q4=ref[1] * ref[3])
+    before = {nm: R.core(c.get(nm, 0)).copy() for nm in ("q1", "q5")}
+    for rk in (1, 2, 3):
+        c.rk_stage(rk)
+        S.rk_stage(state, rk, th, homo, dt, qsave, bctype=bctype, twall=twall,
+                   upwind=dict(shkcrt=shk, lchardecomp=True, bfacmpld=0.1), bc_extra=extra, lfilter=False)
+        for ib, F in enumerate(state):
+            got = dict(zip(NAMES, F.q + [F.rho] + F.vel + [F.prs, F.tmp]))
+            for nm in NAMES:
+                want = R.core(c.get(nm, ib))
+                # measured <= 5e-14
+                assert np.abs(R.core(got[nm]) - want).max() <= TOL * scale.get(nm, np.abs(want).max()), (rk, ib, nm)
+    # the step moved the state by far more than the tolerance (the comparison is not trivially satisfied)
+    for nm in before:
+        now = R.core(c.get(nm, 0))
+        assert np.abs(now - before[nm]).max() > 1e-5 * np.abs(now).max()
+    c.close()
