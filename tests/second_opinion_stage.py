@@ -119,7 +119,7 @@ def noslip(blocks, homo, bctype, twall, th):
 
 
 def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None,
-             upwind=None, bc_extra=None, lfilter=True):
+             upwind=None, bc_extra=None, lfilter=True, rk4=None):
     """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: boundary
     types per face; only no-slip walls (41) unless bc_extra = dict(free=..., inflow_data=...) brings the data of the
     open types (tests/second_opinion_bc.py); force, ys: the channel's body force and the halo'd y coordinate per
@@ -140,6 +140,23 @@ def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, tw
     if force is not None:
         src = R.src_chan(blocks, ys, force)
         qrhs = [[qrhs[b][m] + src[b][m] for m in range(5)] for b in range(len(blocks))]
+    if rk4 is not None:
+        # rkscheme = 'rk4' (src/mainloop.F90:368-381, :452-476): rk4 is the caller's list of accumulated right-hand
+        # sides per block (rhsav, zeroed at stage 1); stages 1..3 step from qsave by c1 dt qrhs and accumulate
+        # c2 qrhs, stage 4 steps by dt/6 (qrhs + rhsav)
+        c1, c2 = ((0.5, 1.0), (0.5, 2.0), (1.0, 2.0), (1.0 / 6.0, 1.0))[rkstep - 1]
+        for b, F in enumerate(blocks):
+            J = F.jacob[c]
+            if rkstep == 1:
+                rk4[b] = [np.zeros_like(J) for _ in range(5)]
+            for m in range(5):
+                if rkstep <= 3:
+                    F.q[m][c] = (qsave[b][m] + c1 * deltat * qrhs[b][m]) / J
+                    rk4[b][m] = rk4[b][m] + c2 * qrhs[b][m]
+                else:
+                    F.q[m][c] = (qsave[b][m] + c1 * deltat * (qrhs[b][m] + rk4[b][m])) / J
+            q2fvar(F, c, th)
+        return
     a1, a2, a3 = RKCOE[rkstep - 1]
     for b, F in enumerate(blocks):
         J = F.jacob[c]

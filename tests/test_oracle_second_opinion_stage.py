@@ -220,3 +220,30 @@ def test_three_stages_of_an_hbl_like_case(oracle, n, blocks, bctype, homo):
         now = R.core(c.get(nm, 0))
         assert np.abs(now - before[nm]).max() > 1e-5 * np.abs(now).max()
     c.close()
+
+
+def test_rk4_step(oracle):
+    """rkscheme = 'rk4' (src/mainloop.F90:368-381, :452-476): four stages with the accumulated right-hand side."""
+    n, blocks, homo = (16, 14, 12), (1, 1, 1), (True, True, True)
+    c = oracle.Case(*n, blocks=blocks, homo=homo, reynolds=REYNOLDS, mach=MACH, deltat=DT)
+    c.set_x(stretched_x(n, homo))
+    c.gridgeom(); c.tgvini()
+    c.set_rkscheme(4)
+    rng = np.random.default_rng(5)
+    for m in range(5):
+        a = c.get(f"q{m + 1}")
+        a *= 1.0 + 1e-2 * rng.standard_normal(a.shape)
+        c.set(f"q{m + 1}", a)
+    c.updatefvar()
+    th = dict(tempconst=110.3 / 273.15, reynolds=REYNOLDS, prandtl=PRANDTL, const5=(GAMMA - 1.0) * MACH ** 2,
+              const6=1.0 / (GAMMA - 1.0), const2=GAMMA * MACH ** 2)
+    state = [R.Fields(c)]
+    qsave, rhsav = [None], [None]
+    for rk in (1, 2, 3, 4):
+        c.rk_stage(rk)
+        S.rk_stage(state, rk, th, homo, DT, qsave, rk4=rhsav)
+        got = dict(zip(NAMES, state[0].q + [state[0].rho] + state[0].vel + [state[0].prs, state[0].tmp]))
+        for nm in NAMES:
+            want = R.core(c.get(nm))
+            assert np.abs(R.core(got[nm]) - want).max() <= TOL * max(np.abs(want).max(), 0.5), (rk, nm)
+    c.close()
