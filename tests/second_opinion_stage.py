@@ -6,7 +6,8 @@ oracle/solver.cpp, which no stored number of the reference pins (q
   filterq   src/comsolver.F90:514-632   per direction: dataswap(q, direction) -- a plain copy -- then the filter
   qswap     src/parallel.F90:4848-5318  per direction i, j, k: 5 halo planes + the shared end node AVERAGED, then
                                         q2fvar on the slabs -5..0 and N..N+5 only (interior primitives stay pre-filter)
-  qsave = q J at stage 1; rhscal; RK3 update (coefficients :350-366); updatefvar = q2fvar on 0..N
+  qsave = q J at stage 1; rhscal; RK3 update (coefficients :350-366); spongefilter (src/sponge_layer.F90:55-364);
+  updatefvar = q2fvar on 0..N
   q2fvar    src/fludyna.F90:545-634 with thermal_3d :136-179 (nondimensional)
 Physical boundaries: the isothermal no-slip wall (bctype 41) is restated (`noslip`), the other types are not.
 """
@@ -118,8 +119,78 @@ def noslip(blocks, homo, bctype, twall, th):
             F.q[4][at(w)] = pe * R.Gas(th).const6
 
 
+def _swap_q(blocks, homo, axes):
+    """dataswap(q, direction): plain copies of the 5 halo planes of the given directions."""
+    for ax in axes:
+        for m in range(5):
+            new = R.exchange_halos([F.q[m] for F in blocks], blocks, [h if a == ax else False for a, h in enumerate(homo)])
+            for F, a in zip(blocks, new):
+                F.q[m][_sl(ax, slice(0, HM))] = a[_sl(ax, slice(0, HM))]
+                F.q[m][_sl(ax, slice(-HM, None))] = a[_sl(ax, slice(-HM, None))]
+
+
+def _damp(F, box, coef):
+    """q <- (1 - c) q + c/6 * (sum of the six neighbours) on `box` (node ranges per direction), all five fields from
+    the values before the update (the reference's qtemp)."""
+    idx = tuple(slice(lo + HM, hi + HM + 1) for lo, hi in box)
+    new = []
+    for m in range(5):
+        q = F.q[m]
+        nb = 0.0
+        for ax in range(3):
+            for off in (1, -1):
+                sh = list(idx)
+                sh[ax] = slice(idx[ax].start + off, idx[ax].stop + off)
+                nb = nb + q[tuple(sh)]
+        new.append((1.0 - coef) * q[idx] + coef / 6.0 * nb)
+    for m in range(5):
+        F.q[m][idx] = new[m]
+
+
+def spongefilter_layer(blocks, homo, layers):
+    """spongefilter_layer (src/sponge_layer.F90:67-319): faces in the order i0, im, jm, k0, km; for each one
+    dataswap(q, direction) on every block, then the damped average on the blocks the layer reaches.
+    layers: {face: [per block (beg, end, coef) or None]} with face 0 i0, 1 im, 3 jm, 4 k0, 5 km and coef on
+    (beg:end along the face's direction) x (is:ie ... of the other two)."""
+    for face in (0, 1, 3, 4, 5):
+        if face not in layers:
+            continue
+        ax = face // 2
+        _swap_q(blocks, homo, [ax])
+        for F, lay in zip(blocks, layers[face]):
+            if lay is None or lay[0] < 0:
+                continue
+            box = [(F.lo[a], F.hi[a]) for a in range(3)]
+            box[ax] = (lay[0], lay[1])
+            _damp(F, box, lay[2])
+
+
+def sponge_circle_coefficients(blocks, xs, centre, range_spange, dampfac):
+    """spongelayer_define_circle (src/sponge_layer.F90:369-440): squared excess distance beyond range_spange from the
+    centre on is:ie x js:je x ks:ke, normalised by its maximum over all blocks (pmax), times dampfac; None for a block
+    without a damped node (lsponge_loc)."""
+    raw = []
+    for F, x in zip(blocks, xs):
+        idx = tuple(slice(F.lo[a] + HM, F.hi[a] + HM + 1) for a in range(3))
+        dist = np.sqrt(sum((x[m][idx] - centre[m]) ** 2 for m in range(3)))
+        raw.append(np.where(dist >= range_spange, (dist - range_spange) ** 2, 0.0))
+    big = max(r.max() for r in raw)
+    return [r / big * dampfac if (r > 0).any() else None for r in raw]
+
+
+def spongefilter_global(blocks, homo, coefs):
+    """spongefilter_global (src/sponge_layer.F90:321-364): dataswap(q) in every direction when any block has a damped
+    node, then the damped average over is:ie x js:je x ks:ke of the blocks that have one."""
+    if all(c is None for c in coefs):
+        return
+    _swap_q(blocks, homo, [0, 1, 2])
+    for F, c in zip(blocks, coefs):
+        if c is not None:
+            _damp(F, [(F.lo[a], F.hi[a]) for a in range(3)], c)
+
+
 def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, twall=None, force=None, ys=None,
-             upwind=None, bc_extra=None, lfilter=True, rk4=None):
+             upwind=None, bc_extra=None, lfilter=True, rk4=None, sponge=None):
     """One stage; `qsave` is a list (per block) of 5 arrays on 0..N, filled at stage 1.  bctype / twall: boundary
     types per face; only no-slip walls (41) unless bc_extra = dict(free=..., inflow_data=...) brings the data of the
     open types (tests/second_opinion_bc.py); force, ys: the channel's body force and the halo'd y coordinate per
@@ -162,4 +233,7 @@ def rk_stage(blocks, rkstep, th, homo, deltat, qsave, alfa=0.49, bctype=None, tw
         J = F.jacob[c]
         for m in range(5):
             F.q[m][c] = (a1 * qsave[b][m] + a2 * F.q[m][c] * J + a3 * qrhs[b][m] * deltat) / J
+    if sponge is not None:                  # call spongefilter (mainloop.F90:478), before updatefvar
+        sponge(blocks)
+    for F in blocks:
         q2fvar(F, c, th)

@@ -247,3 +247,78 @@ def test_rk4_step(oracle):
             want = R.core(c.get(nm))
             assert np.abs(R.core(got[nm]) - want).max() <= TOL * max(np.abs(want).max(), 0.5), (rk, nm)
     c.close()
+
+
+def _periodic_case(oracle, n, blocks):
+    homo = (True, True, True)
+    c = oracle.Case(*n, blocks=blocks, homo=homo, reynolds=REYNOLDS, mach=MACH, deltat=DT)
+    x = stretched_x(n, homo)
+    for ib in range(c.nblocks):
+        info = c.block_info(ib)
+        g0, dims = info["g0"], (info["im"], info["jm"], info["km"])
+        c.set_x(np.asfortranarray(x[tuple(slice(g, g + d + 1) for g, d in zip(g0, dims))]), ib)
+    c.gridgeom(); c.tgvini()
+    rng = np.random.default_rng(5)
+    for ib in range(c.nblocks):
+        for m in range(5):
+            a = c.get(f"q{m + 1}", ib)
+            a *= 1.0 + 1e-2 * rng.standard_normal(a.shape)
+            c.set(f"q{m + 1}", a, ib)
+    c.updatefvar()
+    th = dict(tempconst=110.3 / 273.15, reynolds=REYNOLDS, prandtl=PRANDTL, const5=(GAMMA - 1.0) * MACH ** 2,
+              const6=1.0 / (GAMMA - 1.0), const2=GAMMA * MACH ** 2)
+    return c, th, homo
+
+
+def _assert_state(c, state, what):
+    for ib, F in enumerate(state):
+        got = dict(zip(NAMES, F.q + [F.rho] + F.vel + [F.prs, F.tmp]))
+        for nm in NAMES:
+            want = R.core(c.get(nm, ib))
+            assert np.abs(R.core(got[nm]) - want).max() <= TOL * max(np.abs(want).max(), 0.5), (what, ib, nm)
+
+
+@pytest.mark.parametrize("form", ["layer", "circl"])
+def test_three_stages_with_a_sponge(oracle, form):
+    """spongefilter between the RK update and updatefvar (src/mainloop.F90:478; src/sponge_layer.F90:55-364): the layer
+    form (imax and kmax layers, 6 nodes deep, on the blocks that own those faces) and the global 'circl' form with the
+    coefficients of spongelayer_define_circle (maximum over blocks), 2 x 1 x 2 periodic blocks."""
+    n, blocks = (24, 14, 24), (2, 1, 2)
+    c, th, homo = _periodic_case(oracle, n, blocks)
+    state = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    if form == "layer":
+        layers, rng = {1: [], 5: []}, np.random.default_rng(9)
+        for ib, F in enumerate(state):
+            info = c.block_info(ib)
+            ext = [info["im"], info["jm"], info["km"]]
+            for face in (1, 5):
+                ax = face // 2
+                if info["g0"][ax] + ext[ax] == n[ax]:          # the block at the high end of that direction
+                    beg, end = ext[ax] - 6, F.hi[ax]
+                    shape = [F.hi[a] - F.lo[a] + 1 for a in range(3)]
+                    shape[ax] = end - beg + 1
+                    coef = 0.05 * rng.random(shape)
+                    layers[face].append((beg, end, coef))
+                    c.set_sponge(face, beg, end, np.asfortranarray(coef), ib)
+                else:
+                    layers[face].append(None)
+                    c.set_sponge(face, -1, -1, None, ib)
+        sponge = lambda b: S.spongefilter_layer(b, homo, layers)
+    else:
+        centre, radius, dampfac = (3.0, 3.0, 3.0), 2.5, 0.05
+        c.set_sponge_circle(centre, radius, dampfac)
+        xs = [[c.get(f"x{m + 1}", ib) for m in range(3)] for ib in range(c.nblocks)]
+        coefs = S.sponge_circle_coefficients(state, xs, centre, radius, dampfac)
+        for ib in range(c.nblocks):
+            np.testing.assert_allclose(coefs[ib], c.sponge_circle_coef(ib), rtol=1e-14, atol=0)
+        assert max(co.max() for co in coefs) == dampfac
+        sponge = lambda b: S.spongefilter_global(b, homo, coefs)
+    # the same stages without the sponge end up somewhere else: the damping is visible at the tolerance
+    c0, _, _ = _periodic_case(oracle, n, blocks)
+    qsave = [None] * c.nblocks
+    for rk in (1, 2, 3):
+        c.rk_stage(rk); c0.rk_stage(rk)
+        S.rk_stage(state, rk, th, homo, DT, qsave, sponge=sponge)
+        _assert_state(c, state, f"{form} stage {rk}")
+    assert max(np.abs(R.core(c.get("q2", ib)) - R.core(c0.get("q2", ib))).max() for ib in range(c.nblocks)) > 1e-6
+    c.close(); c0.close()
