@@ -57,6 +57,8 @@ def gridgeom(xs, blocks, homo):
     """xs[b][m]: halo'd coordinate x_m of block b.  Returns (jacob[b], dxi[b][a][n]) as halo'd arrays."""
     nb = len(blocks)
     shape = [xs[b][0].shape for b in range(nb)]
+    if R.ndims_of(xs[0][0]) == 2:
+        return _gridgeom_2d(xs, blocks, homo)
     # dx[b][m][c] = d x_m / d xi_c on 0..N, then halos by exchange
     dx = [[[None] * 3 for _ in range(3)] for _ in range(nb)]
     for m in range(3):
@@ -91,6 +93,27 @@ def gridgeom(xs, blocks, homo):
                                     phi = phi + 0.5 * s * xs[b][m] * dx[b][p][c]
                         acc = acc + R.core_d(R.deriv(phi, bb, R.ntype_of(blocks[b].npdc[bb])), bb)
                 cores.append(acc / R.core(jac[b]))
+            full = datasync(R.exchange_halos([_embed(cores[b], shape[b]) for b in range(nb)], blocks, homo), blocks, homo)
+            for b in range(nb):
+                dxi[b][a][n] = full[b]
+    return jac, dxi
+
+
+def _gridgeom_2d(xs, blocks, homo):
+    """ndims == 2 (ka = 0; src/geom.F90:130-164, :383-389, :521-528): J = x_xi y_eta - x_eta y_xi and the four metrics
+    are the cofactors of the 2 x 2 Jacobian matrix (no conservative form needed in 2-D), the third row and column zero."""
+    nb = len(blocks)
+    shape = [xs[b][0].shape for b in range(nb)]
+    d = [[[R.core_d(R.deriv(xs[b][m], c, R.ntype_of(blocks[b].npdc[c])), c) for c in range(2)] for m in range(2)]
+         for b in range(nb)]                                        # d[b][m][c] = d x_m / d xi_c on nodes 0..N
+    jac = [_embed(d[b][0][0] * d[b][1][1] - d[b][0][1] * d[b][1][0], shape[b]) for b in range(nb)]
+    jac = datasync(R.exchange_halos(jac, blocks, homo), blocks, homo)
+    dxi = [[[None] * 3 for _ in range(3)] for _ in range(nb)]
+    cof = {(0, 0): lambda D: D[1][1], (0, 1): lambda D: -D[0][1], (1, 0): lambda D: -D[1][0], (1, 1): lambda D: D[0][0]}
+    for a in range(3):
+        for n in range(3):
+            cores = [cof[(a, n)](d[b]) / R.core(jac[b]) if (a, n) in cof else np.zeros(R.core(jac[b]).shape)
+                     for b in range(nb)]
             full = datasync(R.exchange_halos([_embed(cores[b], shape[b]) for b in range(nb)], blocks, homo), blocks, homo)
             for b in range(nb):
                 dxi[b][a][n] = full[b]

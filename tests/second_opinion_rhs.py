@@ -66,6 +66,11 @@ def core(a):
     return a[HM:-HM, HM:-HM, HM:-HM]
 
 
+def ndims_of(a):
+    """2 for a 2-D block (ka = 0: one node plane and its ten halo planes), else 3."""
+    return 2 if a.shape[2] == 1 + 2 * HM else 3
+
+
 def _core_other_axes(a, axis):
     """Restrict the two axes other than `axis` to nodes 0..N (the derivative already did so along `axis`)."""
     sl = [slice(HM, -HM)] * 3
@@ -82,6 +87,11 @@ def exchange_halos(arrs, blocks, homo):
     for b, F in enumerate(blocks):
         for ax in range(3):
             n = arrs[b].shape[ax] - 1 - 2 * HM
+            if ax == 2 and n == 0:
+                # 2-D block (ka = 0): every plane -5..5 is a copy of plane 0 (src/parallel.F90:4296-4299)
+                if homo[2]:
+                    out[b][HM:-HM, HM:-HM, :] = arrs[b][HM:-HM, HM:-HM, HM:HM + 1]
+                continue
             lo_nb, hi_nb = F.nb[2 * ax], F.nb[2 * ax + 1]
             if lo_nb < 0 and hi_nb < 0 and homo[ax]:
                 lo_nb = hi_nb = b
@@ -124,8 +134,9 @@ def ntype_of(npdc):
 def gradcal(F):
     """dvel[m][n], dtmp[n] on nodes 0..N."""
     scal = F.vel + [F.tmp]
-    raw = [[core_d(deriv(f, d, ntype_of(F.npdc[d]), F.explicit), d) for d in range(3)] for f in scal]      # raw[f][d]
-    grad = [[sum(raw[f][d] * core(F.dxi[d][n]) for d in range(3)) for n in range(3)] for f in range(4)]
+    nd = ndims_of(F.prs)                       # the k sweep exists for ndims == 3 only (comsolver.F90:418)
+    raw = [[core_d(deriv(f, d, ntype_of(F.npdc[d]), F.explicit), d) for d in range(nd)] for f in scal]      # raw[f][d]
+    grad = [[sum(raw[f][d] * core(F.dxi[d][n]) for d in range(nd)) for n in range(3)] for f in range(4)]
     return grad[:3], grad[3]
 
 
@@ -189,7 +200,7 @@ def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
         qrhs = [np.zeros(core(F.prs).shape) for _ in range(5)]
         # convection: loops over js:je, ks:ke (resp.) and adds on is:ie -> the box is:ie x js:je x ks:ke
         conv_box = box(zip(F.lo, F.hi))
-        for d in range(3):
+        for d in range(ndims_of(F.prs)):          # solver.F90:2284, :2312: j for ndims >= 2, k for ndims == 3
             U = sum(F.dxi[d][n] * F.vel[n] for n in range(3))
             flux = [F.jacob * F.q[0] * U] + \
                    [F.jacob * (F.q[1 + n] * U + F.dxi[d][n] * F.prs) for n in range(3)] + \
@@ -214,7 +225,7 @@ def rhscal_blocks(blocks, th, homo, diffterm=True, upwind=None):
         tauh = [[fields[sym[(min(a, c), max(a, c))]][b] for c in range(3)] for a in range(3)]
         qfh = [fields[6 + n][b] for n in range(3)]
         n_nodes = [s - 1 for s in core(F.prs).shape]
-        for d in range(3):
+        for d in range(ndims_of(F.prs)):
             # loops over 0:N of the two other directions, adds on (is:ie | js:je | ks:ke) of direction d only
             ranges = [(0, n_nodes[a]) for a in range(3)]
             ranges[d] = (F.lo[d], F.hi[d])
@@ -237,10 +248,11 @@ def src_chan(blocks, ys, force):
     tot = np.zeros(4)
     for F, y in zip(blocks, ys):
         yc = core(y)
-        dy = (yc[1:, 1:, 1:] - yc[1:, :-1, 1:])
+        ks = slice(0, 1) if ndims_of(F.prs) == 2 else slice(1, None)       # ndims == 2: k1 = k2 = 0
+        dy = (yc[1:, 1:, ks] - yc[1:, :-1, ks])
         for m in range(4):
             qm = core(F.q[m])
-            tot[m] += np.sum(0.5 * (qm[1:, :-1, 1:] + qm[1:, 1:, 1:]) * dy)
+            tot[m] += np.sum(0.5 * (qm[1:, :-1, ks] + qm[1:, 1:, ks]) * dy)
     ubulk = tot[1:] / tot[0]
     out = []
     for F in blocks:

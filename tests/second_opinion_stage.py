@@ -48,7 +48,7 @@ def filter_axis(a, ax, ntype, alfa):
 
 
 def filterq(blocks, homo, alfa=0.49):
-    for ax in range(3):
+    for ax in range(R.ndims_of(blocks[0].prs)):       # comsolver.F90:559, :588: j for ndims >= 2, k for ndims == 3
         for m in range(5):
             new = R.exchange_halos([F.q[m] for F in blocks], blocks, [h if a == ax else False for a, h in enumerate(homo)])
             for F, a in zip(blocks, new):
@@ -77,6 +77,14 @@ def qswap(blocks, homo, th):
         for b, F in enumerate(blocks):
             lo, hi = _neighbours(b, F, ax, homo)
             n = _n(F.q[0], ax)
+            if ax == 2 and n == 0:
+                # 2-D block (ka = 0, src/parallel.F90:5161-5164): planes -5..5 copy plane 0, no averaging, then q2fvar
+                # on the two slabs (which are all eleven planes)
+                if homo[2]:
+                    for m in range(5):
+                        F.q[m][HM:-HM, HM:-HM, :] = pre[b][m][HM:-HM, HM:-HM, HM:HM + 1]
+                    q2fvar(F, (slice(HM, -HM), slice(HM, -HM), slice(None)), th)
+                continue
             for m in range(5):
                 if hi >= 0:
                     F.q[m][_sl(ax, slice(n + HM + 1, n + 2 * HM + 1))] = pre[hi][m][_sl(ax, slice(HM + 1, 2 * HM + 1))]

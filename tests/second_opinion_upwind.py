@@ -197,7 +197,7 @@ def convrsdcmp(F, gamma, mach, lshock, lchardecomp=True, bfacmpld=0.3):
     """qrhs(5) on nodes 0..N (before rhscal's sign flip)."""
     shape = tuple(s - 2 * HM for s in F.prs.shape)
     qrhs = [np.zeros(shape) for _ in range(5)]
-    for ax in range(3):
+    for ax in range(2 if F.prs.shape[2] == 1 + 2 * HM else 3):       # 2-D block: i and j only (solver.F90:1719)
         inc = direction(F, ax, gamma, mach, lshock, lchardecomp, bfacmpld)
         tgt = [slice(F.lo[a], F.hi[a] + 1) for a in range(3)]       # the other two directions: js:je | ks:ke ... only
         tgt[ax] = slice(None)

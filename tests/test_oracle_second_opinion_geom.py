@@ -17,7 +17,9 @@ TOL = 1e-12
 @pytest.mark.parametrize("n,blocks,homo", [((16, 14, 12), (1, 1, 1), (True, True, True)),
                                            ((16, 14, 12), (1, 1, 1), (True, False, True)),
                                            ((24, 14, 24), (2, 1, 2), (True, True, True)),
-                                           ((28, 12, 12), (2, 1, 1), (False, True, True))])
+                                           ((28, 12, 12), (2, 1, 1), (False, True, True)),
+                                           ((24, 20, 0), (1, 1, 1), (False, False, True)),       # ka = 0: 2-D metrics
+                                           ((32, 24, 0), (2, 2, 1), (True, False, True))])
 def test_gridgeom(oracle, n, blocks, homo):
     c = oracle.Case(*n, blocks=blocks, homo=homo)
     x = stretched_x(n, homo)

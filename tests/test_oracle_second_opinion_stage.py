@@ -93,10 +93,12 @@ def test_three_stages_of_the_channel(oracle, n, blocks):
     c.close()
 
 
-@pytest.mark.parametrize("n,blocks", [((16, 14, 10), (1, 1, 1)), ((24, 16, 10), (2, 2, 1))])
+@pytest.mark.parametrize("n,blocks", [((16, 14, 10), (1, 1, 1)), ((24, 16, 10), (2, 2, 1)),
+                                      ((24, 20, 0), (1, 1, 1)), ((32, 24, 0), (2, 2, 1))])      # ka = 0: true 2-D blocks
 def test_three_stages_of_a_swbli_like_case(oracle, n, blocks):
     """The SWLBI option set (config 4) in 3-D: conschm 543c with characteristic MP5 and the Ducros sensor, inflow 11 at
-    imin, outflow 21 at imax, slip wall 421 at jmin, far field 51 at jmax, periodic in k.  Inside a stage the split
+    imin, outflow 21 at imax, slip wall 421 at jmin, far field 51 at jmax, a sponge layer at imax, periodic in k (3-D) or
+    ka = 0 (the input's own 2-D mode).  Inside a stage the split
     fluxes see pre-filter primitives next to post-filter q (quirk Q2): this is the test that exercises the reference's
     mixed use of the two in flux_steger_warming (tests/second_opinion_upwind.py::steger_warming)."""
     import second_opinion_bc  # noqa: F401  (used through S.rk_stage)
@@ -135,12 +137,25 @@ def test_three_stages_of_a_swbli_like_case(oracle, n, blocks):
     shk = auto_shkcrt(c, 0.3)
     c.set_upwind(543, True, 0.3, shk)
     state = [R.Fields(c, ib) for ib in range(c.nblocks)]
+    # examples/SWLBI/datin/input.2d has a sponge layer at imax: 8 nodes deep on the blocks that own the face
+    layers, rng = {1: []}, np.random.default_rng(11)
+    for ib, F in enumerate(state):
+        info = c.block_info(ib)
+        if info["g0"][0] + info["im"] == n[0]:
+            beg, end = info["im"] - 8, F.hi[0]
+            coef = 0.05 * rng.random((end - beg + 1, F.hi[1] - F.lo[1] + 1, F.hi[2] - F.lo[2] + 1))
+            layers[1].append((beg, end, coef))
+            c.set_sponge(1, beg, end, np.asfortranarray(coef), ib)
+        else:
+            layers[1].append(None)
+            c.set_sponge(1, -1, -1, None, ib)
     qsave = [None] * c.nblocks
     extra = dict(free=(1.0, 0.0, 0.0, 1.0, c.pinf), inflow_data=inflow)
     for rk in (1, 2, 3):
         c.rk_stage(rk)
         S.rk_stage(state, rk, th, homo, DT, qsave, bctype=bctype, twall=twall,
-                   upwind=dict(shkcrt=shk, lchardecomp=True, bfacmpld=0.3), bc_extra=extra)
+                   upwind=dict(shkcrt=shk, lchardecomp=True, bfacmpld=0.3), bc_extra=extra,
+                   sponge=lambda blk: S.spongefilter_layer(blk, homo, layers))
         for ib, F in enumerate(state):
             got = dict(zip(NAMES, F.q + [F.rho] + F.vel + [F.prs, F.tmp]))
             for nm in NAMES:
@@ -153,6 +168,8 @@ def test_three_stages_of_a_swbli_like_case(oracle, n, blocks):
 @pytest.mark.parametrize("n,blocks,bctype,homo", [
     ((16, 14, 10), (1, 1, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),
     ((24, 16, 10), (2, 2, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),
+    ((24, 20, 0), (1, 1, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),       # ka = 0: the input's own 2-D mode
+    ((32, 24, 0), (2, 2, 1), (11, 21, 41, 51, 1, 1), (False, False, True)),
     # far field with the dimensional free stream (uinf = ref_vel, roinf = ref_den, src/solver.F90:131-139) on the
     # faces whose characteristic branches use it, outflow at jmax
     ((16, 14, 10), (1, 1, 1), (11, 21, 51, 21, 51, 51), (False, False, False))])
